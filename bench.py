@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — FLAT-IP batched search throughput on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic queries: the 1024 queries are scored
+against the whole corpus and the exact top-10 per query is produced.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus 8 --steps 20 --warmup 5
+  python bench.py --impl reference ...      # the reference algorithm's CPU path (C++ oracle) on the host cores
+
+The corpus (default: BASELINE configs[1], 10M x 768 f32) is generated on the device and row-sharded across the
+ranks (strong scaling: the corpus is fixed, each rank holds rows/N).  `value` times the path with queries and
+results resident in HBM; `e2e` times the same path through the host-buffer C-ABI call (pinned host queries in,
+host results out, copies inside the timed region).  torch is used for the multi-process rendezvous only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (metric, rows, dim, nq, k, description)
+    "c2": ("ip", 10_000_000, 768, 1024, 10, "FLAT-IP 10M x 768 f32, batch-1024, k=10 (BASELINE configs[1])"),
+    "c1": ("ip", 100_000, 128, 1000, 10, "FLAT-IP 100k x 128 f32, 1k queries, k=10 (BASELINE configs[0])"),
+    "c3": ("l2", 10_000_000, 128, 1024, 100, "FLAT-L2 10M x 128 f32, batch-1024, k=100 (BASELINE configs[2])"),
+}
+SEED_CORPUS, SEED_QUERIES = 42, 43
+APPEND_ROWS = 100_000  # ingestion batch, as benchmarks/flat_search_bench.py feeds the reference
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    p.add_argument("--rows", type=int, default=None, help="override corpus rows (development only)")
+    p.add_argument("--nq", type=int, default=None)
+    p.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    p.add_argument("--cpu-sample-queries", type=int, default=16)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--plan", default="auto", choices=["auto", "exact"])
+    return p.parse_args()
+
+
+def measured_peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            d = json.loads(path.read_text())
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        loaded = [c for c, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_queries(metric: str, nq: int, dim: int) -> np.ndarray:
+    from lynsedb_b200 import synthetic
+
+    q = synthetic.rows_f32(SEED_QUERIES, np.arange(nq), dim)
+    q[0] = synthetic.rows_f32(SEED_CORPUS, np.arange(1), dim)[0]  # row 0 := query 0 (flat_search_bench.py:76-79)
+    return np.ascontiguousarray(q, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_qps(metric, rows_total, dim, k, sample_rows, sample_queries, corpus_sample, queries, repeats=1):
+    """The reference algorithm's CPU path (oracle/lynse_oracle.cpp: AVX2+FMA scan, rayon-style chunks, one full
+    scan per query as Collection::batch_search does for f32 FLAT, src/engine.rs:5484-5497), all host threads,
+    on a row subsample; QPS is extrapolated linearly in the row count."""
+    import oracle
+
+    threads = oracle.host_threads()
+    nq = min(sample_queries, len(queries))
+    seg = []
+    left = len(corpus_sample)
+    while left > 0:
+        seg.append(min(APPEND_ROWS, left))
+        left -= seg[-1]
+    oracle.store_batch_search(corpus_sample[: min(len(corpus_sample), 20000)], queries[:2], k, metric, n_threads=threads)  # warm
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        oracle.store_batch_search(corpus_sample, queries[:nq], k, metric, segment_rows=seg, n_threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    qps_sample = nq / best
+    qps_full = qps_sample * (len(corpus_sample) / rows_total)
+    return {"value": qps_full, "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"{nq} queries x {len(corpus_sample)} of {rows_total} rows x {dim} dims on {threads} threads, "
+                      f"{best:.2f} s; QPS scaled by rows (scan cost is linear in rows)"}
+
+
+def run_reference(args, metric, rows, dim, nq, k, desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from lynsedb_b200 import synthetic
+
+    sample_rows = min(args.cpu_sample_rows, rows)
+    # host copy of the first rows of the same synthetic corpus
+    corpus = np.empty((sample_rows, dim), dtype=np.float32)
+    step = 50_000
+    for lo in range(0, sample_rows, step):
+        hi = min(lo + step, sample_rows)
+        corpus[lo:hi] = synthetic.rows_f32(SEED_CORPUS, np.arange(lo, hi), dim)
+    queries = make_queries(metric, nq, dim)
+    sq = max(1, min(args.cpu_sample_queries, nq))
+    vals = []
+    import oracle
+
+    threads = oracle.host_threads()
+    seg = []
+    left = sample_rows
+    while left > 0:
+        seg.append(min(APPEND_ROWS, left))
+        left -= seg[-1]
+    for _ in range(max(args.warmup, 0)):
+        oracle.store_batch_search(corpus, queries[:1], k, metric, segment_rows=seg, n_threads=threads)
+    t_total = 0.0
+    for s in range(args.steps):
+        lo = (s * sq) % max(nq - sq + 1, 1)
+        t0 = time.perf_counter()
+        oracle.store_batch_search(corpus, queries[lo:lo + sq], k, metric, segment_rows=seg, n_threads=threads)
+        t_total += time.perf_counter() - t0
+    qps_sample = (sq * args.steps) / t_total
+    value = qps_sample * (sample_rows / rows)
+    line = {
+        "impl": "reference", "metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "rows": rows, "dim": dim, "nq": nq, "k": k, "metric": metric},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": f"each step = {sq} queries x {sample_rows} of {rows} rows (sequential scans, "
+                                   f"{threads} threads); QPS scaled by rows"},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse_args()
+    metric, rows, dim, nq, k, desc = WORKLOADS[args.workload]
+    if args.rows:
+        rows = args.rows
+        desc += f" [rows overridden to {rows}]"
+    if args.nq:
+        nq = args.nq
+        desc += f" [nq overridden to {nq}]"
+    if args.impl == "reference":
+        run_reference(args, metric, rows, dim, nq, k, desc)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
+    from lynsedb_b200 import _native as N
+    from lynsedb_b200 import metrics as M
+    from lynsedb_b200 import synthetic
+    from lynsedb_b200.index import DeviceIndex
+
+    lib = N.lib()
+    dist = None
+    comm = C.c_void_p()
+    if world > 1:
+        import torch.distributed as dist  # rendezvous + timing reduction only; the data path is native NCCL
+
+        dist.init_process_group(backend="gloo", init_method="env://")
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            N.check(lib.lb_nccl_unique_id(ident.ctypes.data_as(C.POINTER(C.c_uint8))))
+        import torch
+
+        t = torch.from_numpy(ident)
+        dist.broadcast(t, src=0)
+        N.check(lib.lb_comm_create(C.byref(comm), local_rank, world, rank, ident.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- corpus shard, generated on the device --------------------------------------------------------
+    per = (rows + world - 1) // world
+    base = rank * per
+    n_local = max(0, min(per, rows - base))
+    idx = DeviceIndex(dim, "float32", device=local_rank)
+    idx.reserve(n_local)
+    done = 0
+    while done < n_local:
+        m = min(APPEND_ROWS, n_local - done)
+        idx.append_synthetic(m, SEED_CORPUS, base + done)
+        done += m
+    idx.set_plan(args.plan)
+    m_id = M.require(metric)
+    idx.prepare(m_id)
+    idx.set_timing(True)
+    info = N.device_info(local_rank)
+
+    queries = make_queries(metric, nq, dim)
+    qbytes = queries.nbytes
+    # pinned host staging for the e2e path
+    hq, hrows, hdists, hcounts = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    N.check(lib.lb_host_malloc(qbytes, C.byref(hq)))
+    N.check(lib.lb_host_malloc(nq * k * 8, C.byref(hrows)))
+    N.check(lib.lb_host_malloc(nq * k * 4, C.byref(hdists)))
+    N.check(lib.lb_host_malloc(nq * 4, C.byref(hcounts)))
+    C.memmove(hq, queries.ctypes.data, qbytes)
+    # device-resident buffers for the `value` path
+    dq, drows, ddists, dcounts = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    N.check(lib.lb_device_malloc(local_rank, qbytes, C.byref(dq)))
+    N.check(lib.lb_device_malloc(local_rank, nq * k * 8, C.byref(drows)))
+    N.check(lib.lb_device_malloc(local_rank, nq * k * 4, C.byref(ddists)))
+    N.check(lib.lb_device_malloc(local_rank, nq * 4, C.byref(dcounts)))
+    N.check(lib.lb_memcpy_h2d(local_rank, dq, hq, qbytes))
+
+    def step_device():
+        N.check(lib.lb_sharded_search_device(comm, idx._h, m_id, dq, nq, k, base, drows, ddists, dcounts))
+
+    def step_host():
+        N.check(lib.lb_sharded_search(comm, idx._h, m_id, C.cast(hq, C.POINTER(C.c_float)), nq, k, base,
+                                      C.cast(hrows, C.POINTER(C.c_uint64)), C.cast(hdists, C.POINTER(C.c_float)),
+                                      C.cast(hcounts, C.POINTER(C.c_uint32))))
+
+    def timed(fn, steps, slot):
+        barrier()
+        N.check(lib.lb_device_synchronize(local_rank))
+        N.check(lib.lb_index_event_record(idx._h, slot))
+        dom, launches, fallbacks = [], 0, 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+            st = idx.last_stats()
+            dom.append(st["ms_dominant"])
+            launches += st["kernels_launched"]
+            fallbacks += st["n_fallback"]
+        N.check(lib.lb_index_event_record(idx._h, slot + 1))
+        N.check(lib.lb_device_synchronize(local_rank))
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        ms = C.c_float(0)
+        N.check(lib.lb_index_event_elapsed_ms(idx._h, slot, slot + 1, C.byref(ms)))
+        barrier()
+        return max_over_ranks(float(ms.value)), wall_ms, dom, launches, fallbacks, idx.last_stats()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, wall_dev, dom, launches, fallbacks, st = timed(step_device, args.steps, 0)
+    for _ in range(2):
+        step_host()
+    ms_e2e, wall_e2e, _, _, _, _ = timed(step_host, args.steps, 2)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- sanity on the last e2e result: scores are the exact f32 values of the returned rows, best first ----
+    verified = None
+    if rank == 0:
+        import oracle
+
+        grow = np.ctypeslib.as_array(C.cast(hrows, C.POINTER(C.c_uint64)), shape=(nq, k)).copy()
+        gd = np.ctypeslib.as_array(C.cast(hdists, C.POINTER(C.c_float)), shape=(nq, k)).copy()
+        ok_scores, ok_sorted = True, True
+        for qi in (0, 1, nq // 2, nq - 1):
+            rws = synthetic.rows_f32(SEED_CORPUS, grow[qi], dim)
+            for j in range(k):
+                if metric == "ip":
+                    want = oracle.inner_product_batch8_order(queries[qi], rws[j])
+                else:
+                    want = oracle.compute_distance(queries[qi], rws[j], metric)
+                ok_scores &= bool(np.float32(want) == gd[qi, j])
+            d = gd[qi] if metric != "ip" else -gd[qi]
+            ok_sorted &= bool(np.all(np.diff(d) >= 0))
+        verified = {"scores_bit_exact_vs_oracle": ok_scores, "sorted": ok_sorted, "queries_checked": 4,
+                    "self_hit_query0_row": int(grow[0, 0])}
+
+    value = nq * args.steps / (ms_dev / 1000.0)
+    e2e_value = nq * args.steps / (ms_e2e / 1000.0)
+    peaks = measured_peaks()
+    dom_ms = statistics.mean(dom) if dom else float("nan")
+    flops_per_launch = 2.0 * nq * n_local * dim  # algorithmic: 2*Q*N*D for this rank's shard
+    roofline = None
+    if st["plan_used"] == 1 and dom_ms > 0:
+        ach = flops_per_launch / (dom_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "kernel": "lb::tc::coarse_topk_kernel", "kernel_ms": dom_ms,
+                    "peak_source": peaks["source"] + " (sustained bf16: the kernel is timed inside a long step)",
+                    "hbm_gbs_of_kernel": st["algorithmic_bytes"] / (dom_ms * 1e-3) / 1e9}
+    elif dom_ms > 0:
+        bytes_per_launch = float(st["algorithmic_bytes"])
+        ach = bytes_per_launch / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "kernel": "lb::scan_exact_kernel", "kernel_ms": dom_ms, "peak_source": peaks["source"]}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            sample_rows = min(args.cpu_sample_rows, n_local)
+            corpus_sample = idx.read_rows(0, sample_rows)
+            cpu_baseline = cpu_reference_qps(metric, rows, dim, k, sample_rows, args.cpu_sample_queries, corpus_sample, queries)
+        line = {
+            "metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16 coarse contraction (f32 accumulate) + f32 exact-order rescore", "data": "synthetic",
+            "config": {"workload": desc, "rows": rows, "rows_per_gpu": n_local, "dim": dim, "nq": nq, "k": k, "metric": metric,
+                       "sharding": f"contiguous row shards x{world}", "plan": args.plan,
+                       "l2_policy": "inputs larger than L2 (shadow %.1f GB per GPU vs 126 MB L2)" % (st["algorithmic_bytes"] / 1e9),
+                       "device": info["name"], "sm_count": info["sm_count"]},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(qbytes),
+                    "d2h_bytes_per_step": int(nq * k * 12 + nq * 4), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "fallback_queries": int(fallbacks),
+            "partitions": int(st["n_partitions"]),
+            "wall_ms_per_step": wall_dev / args.steps,
+            "verified": verified,
+        }
+        print(json.dumps(line), flush=True)
+    idx.close()
+    if comm.value:
+        lib.lb_comm_destroy(comm)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,12 @@
+"""lynsedb_b200 — B200-native batched vector-distance + top-k path behind LynseDB's Python surface.
+
+Only the search hot path of LynseDB is implemented here; the native side is
+hand-written CUDA for sm_100a loaded through ctypes (``lynsedb_b200/liblynse_b200.so``).
+"""
+from . import metrics
+from ._backend import FlatIndex, compute_distance, top_k_search
+from .index import DeviceIndex, make_allow_bits
+from .result_view import ResultView
+
+__version__ = "0.1.0"
+__all__ = ["DeviceIndex", "FlatIndex", "ResultView", "compute_distance", "top_k_search", "make_allow_bits", "metrics"]

@@ -1,0 +1,562 @@
+// lb_tc.cuh — tensor-core coarse pass (tcgen05 / TMEM / TMA) + exact-order finalize.
+//
+// The dense metrics (IP, and through it cosine and L2) are a Q x C^T contraction
+// (reference hot loop: src/storage/flat_mmap.rs:2179-2256 ip_scan_chunk_topk over
+// simd::inner_product_batch8_f32, src/distance/simd.rs:1450-1525).  On B200 that
+// contraction runs on the 5th-generation tensor cores over a bf16 shadow of the
+// corpus; a per-query shortlist is kept in the accumulator epilogue, and the
+// shortlist is re-scored in f32 in the reference's exact summation order, so the
+// returned ids / order / scores are the reference's, not the bf16 ones.  A
+// shortlist is only accepted when a rigorous bound proves no dropped row could
+// enter the top-k (see finalize_kernel); otherwise the query is re-run by the
+// exact scan of lb_scan.cuh.
+//
+// Kernel shape (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: 64-row x 64-col bf16 boxes of the shadow, SWIZZLE_128B,
+//               6 stages x 32 KiB in shared memory, mbarrier full/empty ring
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (queries), N=64 (rows), K=16;
+//               A (the 128 queries of this work item, bf16) lives in TMEM columns [0, Dp/2),
+//               B comes from the shared-memory stages, D is double-buffered in TMEM columns [384,512)
+//   warps 2..5  epilogue: lane == query.  tcgen05.ld the 64 scores of the tile, compare with the
+//               thread's running threshold held in a register, insert the rare survivors in a
+//               private 16-entry list in shared memory
+// Work item = (query tile of 128, row partition); items of the same partition run on
+// neighbouring CTAs at the same time so each shadow tile is fetched from HBM once and
+// served to the other query tiles from L2.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "lb_metrics.cuh"
+#include "lb_scan.cuh"
+
+namespace lb {
+namespace tc {
+
+constexpr int BM = 128;           // queries per work item == TMEM lanes
+constexpr int BN = 64;            // corpus rows per accumulator tile
+constexpr int KBLK = 64;          // bf16 elements per 128-byte swizzle row
+constexpr int STAGE_KBLKS = 4;    // K blocks per pipeline stage
+constexpr int NSTAGES = 6;
+constexpr int KP = 16;            // shortlist entries kept per (partition, query)
+constexpr int MAX_DP = 768;       // padded dim limit: A occupies Dp/2 <= 384 TMEM columns
+constexpr int TILE_BYTES = BN * KBLK * 2;            // 8192
+constexpr int STAGE_BYTES = STAGE_KBLKS * TILE_BYTES;  // 32768
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_D_COL = 384;
+constexpr uint32_t SMEM_LIST_OFF = NSTAGES * STAGE_BYTES;             // 196608
+constexpr uint32_t SMEM_BAR_OFF = SMEM_LIST_OFF + 2 * KP * BM * 4;    // + 16384
+constexpr uint32_t SMEM_BYTES = SMEM_BAR_OFF + 256 + 1024;            // + barriers + alignment slack
+
+struct TcArgs {
+    const __nv_bfloat16* qb;  // [n_mtiles*128][Dp] bf16 queries, zero padded
+    int nq;
+    int n_mtiles;
+    int Dp;                   // padded dim, multiple of 64, <= MAX_DP
+    uint32_t n_rows;
+    uint32_t tiles_total;     // ceil(n_rows / 64)
+    uint32_t tiles_per_part;
+    int P;                    // row partitions
+    float* cand_score;        // [nq][P][KP]
+    uint32_t* cand_row;       // [nq][P][KP]
+    float* cand_thr;          // [nq][P]
+    uint32_t* error_flag;     // set non-zero when a barrier wait timed out
+    float* dump;              // optional [n_mtiles*128][tiles_total*64] raw scores (diagnostics)
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a barrier that does not flip within ~2 s marks the launch as failed and lets every role drain,
+// so a protocol bug can never hang the GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t* abort_flag, uint32_t code) {
+    if (mbar_try_wait(bar, parity)) return true;
+    uint64_t t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (*abort_flag) return false;
+        if (globaltimer_ns() - t0 > 2000000000ull) {
+            *abort_flag = code;
+            return false;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, bf16 x bf16 -> f32
+__device__ __forceinline__ void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---- the coarse kernel -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_tc[];
+    const uint32_t smem_base = (smem_u32(smem_tc) + 1023u) & ~1023u;
+    unsigned char* smem = smem_tc + (smem_base - smem_u32(smem_tc));
+    float* l_score = reinterpret_cast<float*>(smem + SMEM_LIST_OFF);             // [KP][BM]
+    uint32_t* l_row = reinterpret_cast<uint32_t*>(smem + SMEM_LIST_OFF + KP * BM * 4);  // [KP][BM]
+    const uint32_t bar_base = smem_base + SMEM_BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * NSTAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * NSTAGES + 2 + b); };
+    const uint32_t aready_bar = bar_base + 8u * (2 * NSTAGES + 4);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * NSTAGES + 5));
+    volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * NSTAGES + 5) + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 128);
+        }
+        mbar_init(aready_bar, 128);
+        *abort_flag = 0;
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int n_items = a.n_mtiles * a.P;
+    const int nkb = a.Dp / KBLK;
+    const int stages_per_tile = (nkb + STAGE_KBLKS - 1) / STAGE_KBLKS;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage_iter = 0;
+            bool ok = true;
+            for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
+                const uint32_t part = item / a.n_mtiles;
+                const uint32_t t0 = part * a.tiles_per_part;
+                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+                for (uint32_t t = t0; t < t1 && ok; ++t) {
+                    for (int s = 0; s < stages_per_tile; ++s, ++stage_iter) {
+                        const int stage = stage_iter % NSTAGES;
+                        const uint32_t phase = (stage_iter / NSTAGES) & 1u;
+                        if (!mbar_wait(empty_bar(stage), phase ^ 1u, abort_flag, 1)) { ok = false; break; }
+                        const int kbc = min(STAGE_KBLKS, nkb - s * STAGE_KBLKS);
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kbc * TILE_BYTES);
+                        for (int kb = 0; kb < kbc; ++kb)
+                            tma_load_2d(smem_base + stage * STAGE_BYTES + kb * TILE_BYTES, &tmap,
+                                        (s * STAGE_KBLKS + kb) * KBLK, (int)(t * BN), full_bar(stage));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage_iter = 0, tile_iter = 0, item_iter = 0;
+            bool ok = true;
+            for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++item_iter) {
+                const uint32_t part = item / a.n_mtiles;
+                const uint32_t t0 = part * a.tiles_per_part;
+                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+                if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
+                tcgen05_fence_after();
+                for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
+                    const uint32_t buf = tile_iter & 1u;
+                    if (!mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1u) ^ 1u, abort_flag, 3)) { ok = false; break; }
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + TMEM_D_COL + buf * BN;
+                    for (int s = 0; s < stages_per_tile; ++s, ++stage_iter) {
+                        const int stage = stage_iter % NSTAGES;
+                        const uint32_t phase = (stage_iter / NSTAGES) & 1u;
+                        if (!mbar_wait(full_bar(stage), phase, abort_flag, 4)) { ok = false; break; }
+                        tcgen05_fence_after();
+                        const int kbc = min(STAGE_KBLKS, nkb - s * STAGE_KBLKS);
+                        for (int kb = 0; kb < kbc; ++kb) {
+#pragma unroll
+                            for (int k4 = 0; k4 < KBLK / 16; ++k4) {
+                                const int kstep = (s * STAGE_KBLKS + kb) * (KBLK / 16) + k4;
+                                const uint64_t bdesc =
+                                    make_b_desc(smem_base + stage * STAGE_BYTES + kb * TILE_BYTES + k4 * 32);
+                                umma_ts_bf16(d_tmem, tmem_base + kstep * 8, bdesc, IDESC, kstep > 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(empty_bar(stage));  // frees the stage when these MMAs have read it
+                    }
+                    if (ok) umma_commit(tfull_bar(buf));  // accumulator tile complete
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: lane == query =====================
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int ql = quad * 32 + lane;              // query within the tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint32_t tile_iter = 0;
+        bool ok = true;
+        for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
+            const uint32_t part = item / a.n_mtiles, mt = item % a.n_mtiles;
+            const uint32_t t0 = part * a.tiles_per_part;
+            const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+            const uint32_t gq = mt * BM + ql;
+            // A operand: this thread's query row, bf16 pairs, into TMEM columns [0, Dp/2)
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)gq * a.Dp);
+                for (int c = 0; c < a.Dp / 32; ++c) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 x = __ldg(src + c * 4 + i);
+                        w[4 * i + 0] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+                    }
+                    tmem_st_32x32b_x16(lane_addr + c * 16, w);
+                }
+                tmem_st_wait();
+            }
+            for (int j = 0; j < KP; ++j) {
+                l_score[j * BM + ql] = -INFINITY;
+                l_row[j * BM + ql] = ROW_NONE;
+            }
+            float thr = gq < (uint32_t)a.nq ? -INFINITY : INFINITY;
+            int min_pos = 0;
+            tcgen05_fence_before();
+            mbar_arrive(aready_bar);
+            const uint32_t row_end = a.n_rows;
+            for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
+                const uint32_t buf = tile_iter & 1u;
+                if (!mbar_wait(tfull_bar(buf), (tile_iter >> 1) & 1u, abort_flag, 5)) { ok = false; break; }
+                tcgen05_fence_after();
+                uint32_t v[BN];
+                tmem_ld_32x32b_x32(lane_addr + TMEM_D_COL + buf * BN, v);
+                tmem_ld_32x32b_x32(lane_addr + TMEM_D_COL + buf * BN + 32, v + 32);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                mbar_arrive(tempty_bar(buf));  // accumulator is in registers: the MMA warp may reuse the buffer
+                const uint32_t row0 = t * BN;
+                if (a.dump != nullptr) {
+                    float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
+#pragma unroll
+                    for (int i = 0; i < BN; ++i) drow[i] = __uint_as_float(v[i]);
+                }
+                bool any = false;
+#pragma unroll
+                for (int i = 0; i < BN; ++i) any |= (__uint_as_float(v[i]) > thr);
+                if (any) {
+#pragma unroll
+                    for (int i = 0; i < BN; ++i) {
+                        const float s = __uint_as_float(v[i]);
+                        if (s > thr && row0 + i < row_end) {
+                            l_score[min_pos * BM + ql] = s;
+                            l_row[min_pos * BM + ql] = row0 + i;
+                            float mn = INFINITY;
+                            for (int j = 0; j < KP; ++j) {
+                                const float x = l_score[j * BM + ql];
+                                if (x < mn) { mn = x; min_pos = j; }
+                            }
+                            thr = mn;
+                        }
+                    }
+                }
+            }
+            if (ok && gq < (uint32_t)a.nq) {
+                const size_t o = ((size_t)gq * a.P + part) * KP;
+                for (int j = 0; j < KP; ++j) {
+                    a.cand_score[o + j] = l_score[j * BM + ql];
+                    a.cand_row[o + j] = l_row[j * BM + ql];
+                }
+                a.cand_thr[(size_t)gq * a.P + part] = thr;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (threadIdx.x == 0 && *abort_flag) atomicMax(a.error_flag, *abort_flag);
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- shadow / query preparation --------------------------------------------------------------------------------
+enum ShadowKind { SHADOW_IP = 0, SHADOW_COSINE = 1, SHADOW_L2 = 2 };
+
+// One warp per row: bf16 shadow row of Dp elements (zero padded) + max row norm (for the certification bound).
+//   SHADOW_IP      c
+//   SHADOW_COSINE  c / |c|            (zero rows stay zero: cosine distance 1.0, simd.rs:1631-1633)
+//   SHADOW_L2      [c, n1, n2, n3]    with n1+n2+n3 ~ |c|^2 split into three bf16 pieces (columns dim..dim+2)
+__global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int Dp,
+                                    int kind, __nv_bfloat16* __restrict__ shadow, float* __restrict__ max_norm) {
+    uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= first_row + n) return;
+    const float* r = rows + row * dim;
+    float ss = 0.0f;
+    for (int d = lane; d < dim; d += 32) {
+        float x = __ldg(r + d);
+        ss = fmaf(x, x, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float norm = sqrtf(ss);
+    float scale = 1.0f;
+    if (kind == SHADOW_COSINE) scale = norm > 0.0f ? 1.0f / norm : 0.0f;
+    __nv_bfloat16* out = shadow + row * (uint64_t)Dp;
+    for (int d = lane; d < Dp; d += 32) {
+        float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+        if (kind == SHADOW_L2 && d >= dim && d < dim + 3) {
+            float n1 = __bfloat162float(__float2bfloat16_rn(ss));
+            float n2 = __bfloat162float(__float2bfloat16_rn(ss - n1));
+            float n3 = (ss - n1) - n2;
+            x = d == dim ? n1 : (d == dim + 1 ? n2 : n3);
+        }
+        out[d] = __float2bfloat16_rn(x);
+    }
+    if (lane == 0 && isfinite(norm)) atomicMax(reinterpret_cast<unsigned int*>(max_norm), __float_as_uint(norm));
+}
+
+// Queries: bf16 A operand rows (zero padded to n_mtiles*128 x Dp) + |q| per query.
+//   SHADOW_IP      q                 SHADOW_COSINE  q / |q|          SHADOW_L2  [2q, -1, -1, -1]
+__global__ void prepare_queries_kernel(const float* __restrict__ queries, int nq, int nq_pad, int dim, int Dp, int kind,
+                                       __nv_bfloat16* __restrict__ qb, float* __restrict__ qnorm) {
+    int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (q >= nq_pad) return;
+    __nv_bfloat16* out = qb + (size_t)q * Dp;
+    if (q >= nq) {
+        for (int d = lane; d < Dp; d += 32) out[d] = __float2bfloat16_rn(0.0f);
+        return;
+    }
+    const float* r = queries + (size_t)q * dim;
+    float ss = 0.0f;
+    for (int d = lane; d < dim; d += 32) {
+        float x = __ldg(r + d);
+        ss = fmaf(x, x, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float norm = sqrtf(ss);
+    float scale = 1.0f;
+    if (kind == SHADOW_COSINE) scale = norm > 0.0f ? 1.0f / norm : 0.0f;
+    if (kind == SHADOW_L2) scale = 2.0f;
+    for (int d = lane; d < Dp; d += 32) {
+        float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+        if (kind == SHADOW_L2 && d >= dim && d < dim + 3) x = -1.0f;
+        out[d] = __float2bfloat16_rn(x);
+    }
+    if (lane == 0) qnorm[q] = norm;
+}
+
+// ---- finalize: shortlist -> exact-order rescore -> certified top-k -------------------------------------------------
+struct FinArgs {
+    const float* cand_score;  // [nq][P][KP]
+    const uint32_t* cand_row;
+    const float* cand_thr;    // [nq][P]
+    int P;
+    int M1;                   // pow2 >= P*KP (<= 4096)
+    int R;                    // rescore budget, pow2 <= 1024, >= k
+    const float* corpus;
+    int dim;
+    const float* queries;     // original f32 queries [nq][dim]
+    const float* qnorm;       // [nq]
+    const float* max_norm;    // device scalar: max row norm
+    int nq, k, metric;
+    float eps_rel;            // relative error bound of the coarse score
+    const uint32_t* small_seg;
+    int n_small;
+    uint32_t* out_rows;
+    float* out_dists;
+    uint32_t* out_counts;
+    uint32_t* uncertified;    // [nq] flag
+    uint32_t* n_uncertified;  // counter
+};
+
+template <bool ASC>
+__global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_fin[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_fin);            // [M1] coarse keys
+    uint64_t* e = s + a.M1;                                         // [R] exact keys
+    float* sq = reinterpret_cast<float*>(e + a.R);                  // [dim_pad] query
+    __shared__ uint32_t sh_T;      // orderable max of partition thresholds
+    __shared__ uint32_t sh_ncand;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int dim = a.dim;
+    const bool vec = (dim & 3) == 0;
+    if (tid == 0) { sh_T = 0; sh_ncand = 0; }
+    for (int d = tid; d < dim; d += blockDim.x) sq[d] = a.queries[(size_t)q * dim + d];
+    __syncthreads();
+    const int total = a.P * KP;
+    uint32_t local_valid = 0;
+    for (int i = tid; i < a.M1; i += blockDim.x) {
+        uint64_t key = KEY_NONE;
+        if (i < total) {
+            uint32_t row = a.cand_row[(size_t)q * total + i];
+            if (row != ROW_NONE) {
+                key = make_key<false>(a.cand_score[(size_t)q * total + i], row);  // best coarse score first
+                ++local_valid;
+            }
+        }
+        s[i] = key;
+    }
+    if (local_valid) atomicAdd(&sh_ncand, local_valid);
+    for (int p = tid; p < a.P; p += blockDim.x) atomicMax(&sh_T, f32_orderable(a.cand_thr[(size_t)q * a.P + p]));
+    bitonic_sort_u64(s, a.M1);
+    const int ncand = (int)sh_ncand;
+    const int rn = min(ncand, a.R);
+    float T = f32_from_orderable(sh_T);  // every row dropped inside a partition has coarse score <= T
+    if (ncand > a.R) T = fmaxf(T, key_score<false>(s[a.R]));  // ... and so has every candidate cut here
+    for (int i = tid; i < a.R; i += blockDim.x) {
+        uint64_t key = KEY_NONE;
+        if (i < rn) {
+            uint32_t row = key_row(s[i]);
+            const float* c = a.corpus + (size_t)row * dim;
+            float v;
+            if (a.metric == LB_IP) {
+                bool small = a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
+                v = small ? ip_single_order<false>(sq, c, dim, vec) : ip_batch8_order<false>(sq, c, dim, vec);
+            } else if (a.metric == LB_L2) {
+                v = l2_squared<false>(sq, c, dim, vec);
+            } else {
+                v = cosine_distance<false>(sq, c, dim, vec);
+            }
+            key = make_key<ASC>(v, row);
+        }
+        e[i] = key;
+    }
+    bitonic_sort_u64(e, a.R);
+    const int kk = min(a.k, rn);
+    for (int i = tid; i < a.k; i += blockDim.x) {
+        uint32_t row = ROW_NONE;
+        float score = __int_as_float(0x7fc00000);
+        if (i < kk) {
+            row = key_row(e[i]);
+            score = key_score<ASC>(e[i]);
+        }
+        a.out_rows[(size_t)q * a.k + i] = row;
+        a.out_dists[(size_t)q * a.k + i] = score;
+    }
+    if (tid == 0) {
+        a.out_counts[q] = kk;
+        bool certified;
+        if (T == -INFINITY) {
+            certified = true;  // nothing was dropped anywhere: the shortlist is the whole corpus
+        } else if (kk < a.k) {
+            certified = false;
+        } else {
+            const float worst = key_score<ASC>(e[a.k - 1]);
+            const float qn = a.qnorm[q], cn = *a.max_norm;
+            if (a.metric == LB_IP) {
+                // dropped row: exact <= coarse + eps <= T + eps
+                const float eps = a.eps_rel * qn * cn;
+                certified = worst > T + eps;
+            } else if (a.metric == LB_COSINE) {
+                // coarse = cos of the normalised bf16 vectors; dropped row: dist >= 1 - (T + eps)
+                const float eps = a.eps_rel + 4e-6f;
+                certified = worst < 1.0f - (T + eps);
+            } else {
+                // coarse = 2 q.c - |c|^2 ; dropped row: dist >= |q|^2 - (T + eps)
+                const float eps = 2.0f * a.eps_rel * qn * cn + 1e-5f * (qn * qn + cn * cn);
+                certified = worst < qn * qn - (T + eps);
+            }
+        }
+        if (!certified) {
+            a.uncertified[q] = 1;
+            atomicAdd(a.n_uncertified, 1u);
+        } else {
+            a.uncertified[q] = 0;
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace lb

@@ -1,0 +1,1406 @@
+// lynse_b200.cu — C ABI of liblynse_b200.so (see include/lynse_b200.h).
+//
+// Host side of the B200-native distance + top-k path: owns the HBM-resident
+// corpus and its per-metric side structures, picks the search plan, launches
+// the kernels of lb_scan.cuh / lb_tc.cuh on one stream per index, and moves
+// queries / results between host and device.  No PyTorch, no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lb_common.cuh"
+#include "lb_metrics.cuh"
+#include "lb_scan.cuh"
+#include "lb_tc.cuh"
+
+namespace lb {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+
+// Growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, bool keep = false, cudaStream_t stream = 0) {
+        if (bytes <= cap) return LB_OK;
+        size_t ncap = keep ? std::max(bytes, cap + cap / 2) : bytes;
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess && ncap != bytes) {
+            ncap = bytes;
+            e = cudaMalloc(&np, ncap);
+        }
+        if (e != cudaSuccess)
+            return fail(LB_CUDA, std::string("cudaMalloc(") + std::to_string(ncap) + "): " + cudaGetErrorString(e));
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) {
+                cudaFree(np);
+                return fail(LB_CUDA, std::string("grow copy: ") + cudaGetErrorString(e));
+            }
+        }
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return LB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Shadow {
+    DevBuf buf;
+    uint64_t rows = 0;  // rows converted so far
+    int Dp = 0;
+    CUtensorMap tmap;
+    uint64_t tmap_rows = 0;
+    void* tmap_ptr = nullptr;
+};
+
+static int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+static uint64_t gcd_u64(uint64_t a, uint64_t b) {
+    while (b) {
+        uint64_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+struct lb_index {
+    int device = 0;
+    uint32_t dim = 0;
+    int dtype = LB_F32;
+    int n_words = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    DevBuf rows;  // f32 [n][dim] or u64 [n][n_words]
+    uint64_t n = 0;
+    std::vector<uint64_t> segments;
+    uint64_t seg_target = 256ull * 1024 * 1024;
+    // side structures (derived caches, extended incrementally after appends)
+    DevBuf packed;
+    uint64_t packed_rows = 0;
+    DevBuf js_stats;
+    uint64_t js_rows = 0;
+    Shadow shadow[3];
+    DevBuf max_norm;  // 3 floats, one per shadow kind
+    DevBuf small_seg;
+    int n_small = 0;
+    size_t small_seg_sig = ~(size_t)0;
+    // workspace
+    DevBuf w_queries, w_qwords, w_allow, w_lists, w_counts, w_thr, w_out_rows, w_out_dists, w_out_counts;
+    DevBuf w_qb, w_qnorm, w_cand_score, w_cand_row, w_cand_thr, w_flags, w_qstats, w_nq, w_sub_q, w_qmap;
+    int plan = LB_PLAN_AUTO;
+    bool timing = false;
+    lb_search_stats stats{};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf w_send, w_recv, w_g_rows, w_g_dists, w_g_counts;
+};
+
+namespace lb {
+
+static size_t row_bytes(const lb_index* idx) {
+    return idx->dtype == LB_F32 ? (size_t)idx->dim * 4 : (size_t)idx->n_words * 8;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// VectorStore::append_encoded_bytes (vector_store.rs:379-445): an append joins the last segment when it fits
+// inside the segment target, otherwise it opens a new one; it is never split.
+static void account_segment(lb_index* idx, uint64_t n_new) {
+    uint64_t bytes = n_new * row_bytes(idx);
+    uint64_t target = std::max<uint64_t>(idx->seg_target, row_bytes(idx));
+    if (!idx->segments.empty() && idx->segments.back() * row_bytes(idx) + bytes <= target)
+        idx->segments.back() += n_new;
+    else
+        idx->segments.push_back(n_new);
+}
+
+static int grow_rows(lb_index* idx, uint64_t n_total) {
+    return idx->rows.ensure((size_t)n_total * row_bytes(idx), true, idx->stream);
+}
+
+static int refresh_small_segments(lb_index* idx) {
+    std::vector<uint32_t> ranges;
+    uint64_t base = 0;
+    size_t sig = idx->segments.size() * 1315423911u;
+    for (uint64_t r : idx->segments) {
+        if (r < 4096) {
+            ranges.push_back((uint32_t)base);
+            ranges.push_back((uint32_t)(base + r));
+        }
+        base += r;
+        sig = sig * 31 + (size_t)r;
+    }
+    if (sig == idx->small_seg_sig) return LB_OK;
+    idx->n_small = (int)(ranges.size() / 2);
+    if (!ranges.empty()) {
+        LB_TRY(idx->small_seg.ensure(ranges.size() * 4));
+        LB_CUDA_TRY(cudaMemcpyAsync(idx->small_seg.p, ranges.data(), ranges.size() * 4, cudaMemcpyHostToDevice, idx->stream));
+        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
+    idx->small_seg_sig = sig;
+    return LB_OK;
+}
+
+// ---- side structures --------------------------------------------------------------------------------------
+static int ensure_packed(lb_index* idx) {
+    if (idx->dtype != LB_F32) return LB_OK;
+    if (idx->packed_rows == idx->n) return LB_OK;
+    int nw = (idx->dim + 63) / 64;
+    LB_TRY(idx->packed.ensure((size_t)idx->n * nw * 8, true, idx->stream));
+    uint64_t first = idx->packed_rows, cnt = idx->n - first;
+    const int warps = 8;
+    pack_binary_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+        idx->rows.as<float>() + first * idx->dim, cnt, (int)idx->dim, nw, 0.5f, idx->packed.as<uint64_t>() + first * nw);
+    LB_CUDA_TRY(cudaGetLastError());
+    idx->packed_rows = idx->n;
+    return LB_OK;
+}
+
+static int ensure_js_stats(lb_index* idx) {
+    if (idx->js_rows == idx->n) return LB_OK;
+    LB_TRY(idx->js_stats.ensure((size_t)idx->n * 8, true, idx->stream));
+    uint64_t first = idx->js_rows, cnt = idx->n - first;
+    row_stats_kernel<<<(unsigned)ceil_div(cnt, 128), 128, 0, idx->stream>>>(idx->rows.as<float>() + first * idx->dim, cnt,
+                                                                            (int)idx->dim, idx->js_stats.as<float>() + 2 * first);
+    LB_CUDA_TRY(cudaGetLastError());
+    idx->js_rows = idx->n;
+    return LB_OK;
+}
+
+static int shadow_kind_for(int metric) {
+    return metric == LB_IP ? tc::SHADOW_IP : (metric == LB_COSINE ? tc::SHADOW_COSINE : tc::SHADOW_L2);
+}
+static int shadow_dp(const lb_index* idx, int kind) {
+    int d = (int)idx->dim + (kind == tc::SHADOW_L2 ? 3 : 0);
+    return (d + tc::KBLK - 1) / tc::KBLK * tc::KBLK;
+}
+static bool tc_supported(const lb_index* idx, int metric) {
+    if (idx->dtype != LB_F32) return false;
+    if (metric != LB_IP && metric != LB_COSINE && metric != LB_L2) return false;
+    return shadow_dp(idx, shadow_kind_for(metric)) <= tc::MAX_DP;
+}
+
+static int ensure_shadow(lb_index* idx, int kind) {
+    Shadow& sh = idx->shadow[kind];
+    int Dp = shadow_dp(idx, kind);
+    if (!idx->max_norm.p) {
+        LB_TRY(idx->max_norm.ensure(3 * sizeof(float)));
+        LB_CUDA_TRY(cudaMemsetAsync(idx->max_norm.p, 0, 3 * sizeof(float), idx->stream));
+    }
+    if (sh.rows < idx->n) {
+        // keep 64 rows of slack so the last 64-row TMA box never leaves the allocation
+        LB_TRY(sh.buf.ensure(((size_t)idx->n + 64) * Dp * 2, true, idx->stream));
+        sh.Dp = Dp;
+        uint64_t first = sh.rows, cnt = idx->n - first;
+        const int warps = 8;
+        tc::build_shadow_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+            idx->rows.as<float>(), first, cnt, (int)idx->dim, Dp, kind, sh.buf.as<__nv_bfloat16>(),
+            idx->max_norm.as<float>() + kind);
+        LB_CUDA_TRY(cudaGetLastError());
+        sh.rows = idx->n;
+    }
+    if (sh.tmap_rows != idx->n || sh.tmap_ptr != sh.buf.p) {
+        PFN_encodeTiled enc = get_encode_tiled();
+        if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)idx->n};
+        cuuint64_t gstride[1] = {(cuuint64_t)Dp * 2};
+        cuuint32_t box[2] = {(cuuint32_t)tc::KBLK, (cuuint32_t)tc::BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&sh.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sh.buf.p, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        sh.tmap_rows = idx->n;
+        sh.tmap_ptr = sh.buf.p;
+    }
+    return LB_OK;
+}
+
+// ---- exact scan plan ------------------------------------------------------------------------------------------
+struct ScanPlan {
+    int P;
+    uint32_t rows_per_part;
+};
+static ScanPlan plan_scan(const lb_index* idx, uint64_t n_rows, int nq, int k) {
+    uint64_t P = std::min<uint64_t>(ceil_div(n_rows, SCAN_THREADS), (uint64_t)idx->sm_count * 2);
+    // bound the candidate lists to 512 MiB
+    uint64_t max_p = std::max<uint64_t>(1, (512ull << 20) / ((uint64_t)nq * k * 8));
+    P = std::max<uint64_t>(1, std::min(P, max_p));
+    uint64_t rpp = ceil_div(ceil_div(n_rows, P), SCAN_THREADS) * SCAN_THREADS;
+    ScanPlan p;
+    p.rows_per_part = (uint32_t)rpp;
+    p.P = (int)ceil_div(n_rows, rpp);
+    return p;
+}
+
+struct ScanRequest {
+    const float* corpus = nullptr;
+    const uint64_t* words = nullptr;
+    uint64_t n_rows = 0;
+    int dim = 0, n_words = 0;
+    const float* queries = nullptr;
+    const uint64_t* qwords = nullptr;
+    int nq = 0, k = 0, metric = 0;
+    const uint64_t* allow_bits = nullptr;
+    const uint32_t* row_ids = nullptr;
+    const uint32_t* small_seg = nullptr;
+    int n_small = 0;
+    int ip_single = 0;
+    const float* row_stats = nullptr;
+    const float* query_stats = nullptr;
+    int sqrt_scores = 0;
+    const uint32_t* qmap = nullptr;
+    uint32_t* out_rows = nullptr;
+    float* out_dists = nullptr;
+    uint32_t* out_counts = nullptr;
+};
+
+// scan + merge on idx->stream (k <= n_rows, k <= 2048)
+static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
+    ScanPlan sp = plan_scan(idx, r.n_rows, r.nq, r.k);
+    size_t nl = (size_t)sp.P * r.nq;
+    LB_TRY(idx->w_lists.ensure(nl * r.k * 8));
+    LB_TRY(idx->w_counts.ensure(nl * 4));
+    LB_TRY(idx->w_thr.ensure(nl * 8));
+    LB_CUDA_TRY(cudaMemsetAsync(idx->w_counts.p, 0, nl * 4, idx->stream));
+    ScanArgs a{};
+    a.corpus = r.corpus;
+    a.words = r.words;
+    a.n_rows = (uint32_t)r.n_rows;
+    a.dim = r.dim;
+    a.n_words = r.n_words;
+    a.queries = r.queries;
+    a.qwords = r.qwords;
+    a.nq = r.nq;
+    a.k = r.k;
+    a.metric = r.metric;
+    a.allow_bits = r.allow_bits;
+    a.row_ids = r.row_ids;
+    a.small_seg = r.small_seg;
+    a.n_small = r.n_small;
+    a.ip_single = r.ip_single;
+    a.row_stats = r.row_stats;
+    a.query_stats = r.query_stats;
+    a.lists = idx->w_lists.as<uint64_t>();
+    a.counts = idx->w_counts.as<uint32_t>();
+    a.thr = idx->w_thr.as<uint64_t>();
+    a.rows_per_part = sp.rows_per_part;
+    if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
+    if (r.words) {
+        size_t smem = (size_t)SCAN_TQ * SCAN_THREADS * 8 + (size_t)SCAN_TQ * r.n_words * 8;
+#define LB_LAUNCH_PACKED(W)                                                                                      \
+    do {                                                                                                         \
+        LB_CUDA_TRY(cudaFuncSetAttribute(scan_packed_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        scan_packed_kernel<W><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);                                     \
+    } while (0)
+        if (smem > 200 * 1024) return fail(LB_UNSUPPORTED, "packed rows wider than 1280 words are not supported");
+        switch (r.n_words) {
+            case 1: LB_LAUNCH_PACKED(1); break;
+            case 2: LB_LAUNCH_PACKED(2); break;
+            case 4: LB_LAUNCH_PACKED(4); break;
+            case 8: LB_LAUNCH_PACKED(8); break;
+            case 16: LB_LAUNCH_PACKED(16); break;
+            default: LB_LAUNCH_PACKED(0); break;
+        }
+#undef LB_LAUNCH_PACKED
+    } else {
+        int dim_pad = (r.dim + 3) & ~3;
+        size_t smem = (size_t)SCAN_TQ * SCAN_THREADS * 8 + (size_t)SCAN_TQ * dim_pad * 4;
+        if (smem > 200 * 1024) return fail(LB_UNSUPPORTED, "dimension above 2560 is not supported by the exact scan");
+        if (metric_ascending(r.metric)) {
+            LB_CUDA_TRY(cudaFuncSetAttribute(scan_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            scan_exact_kernel<true><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);
+        } else {
+            LB_CUDA_TRY(cudaFuncSetAttribute(scan_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            scan_exact_kernel<false><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);
+        }
+    }
+    LB_CUDA_TRY(cudaGetLastError());
+    if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
+    MergeArgs m{};
+    m.lists = a.lists;
+    m.counts = a.counts;
+    m.P = sp.P;
+    m.nq = r.nq;
+    m.k = r.k;
+    m.kp2 = next_pow2(r.k);
+    long total = (long)sp.P * r.k;
+    m.M = (int)std::min<long>(4096, std::max<long>(2L * m.kp2, next_pow2((int)std::min<long>(4096, m.kp2 + total))));
+    m.asc = metric_ascending(r.metric) ? 1 : 0;
+    m.sqrt_scores = r.sqrt_scores;
+    m.qmap = r.qmap;
+    m.out_rows = r.out_rows;
+    m.out_dists = r.out_dists;
+    m.out_counts = r.out_counts;
+    merge_lists_kernel<<<r.nq, 256, (size_t)m.M * 8, idx->stream>>>(m);
+    LB_CUDA_TRY(cudaGetLastError());
+    if (kernels) *kernels += 2;
+    idx->stats.n_partitions = sp.P;
+    if (idx->timing && ms_dom) {
+        LB_CUDA_TRY(cudaEventSynchronize(idx->ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);
+        *ms_dom = ms;
+    }
+    return LB_OK;
+}
+
+// ---- tensor-core plan ----------------------------------------------------------------------------------------
+static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uint32_t* d_rows, float* d_dists,
+                  uint32_t* d_counts, float* dump) {
+    const int kind = shadow_kind_for(metric);
+    LB_TRY(ensure_shadow(idx, kind));
+    LB_TRY(refresh_small_segments(idx));
+    Shadow& sh = idx->shadow[kind];
+    const int Dp = sh.Dp;
+    const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
+    const int nq_pad = n_mtiles * tc::BM;
+    LB_TRY(idx->w_qb.ensure((size_t)nq_pad * Dp * 2));
+    LB_TRY(idx->w_qnorm.ensure((size_t)nq * 4));
+    {
+        const int warps = 8;
+        tc::prepare_queries_kernel<<<(nq_pad + warps - 1) / warps, warps * 32, 0, idx->stream>>>(
+            d_queries, nq, nq_pad, (int)idx->dim, Dp, kind, idx->w_qb.as<__nv_bfloat16>(), idx->w_qnorm.as<float>());
+        LB_CUDA_TRY(cudaGetLastError());
+    }
+    const uint32_t tiles_total = (uint32_t)ceil_div(idx->n, tc::BN);
+    const uint64_t G = (uint64_t)idx->sm_count;
+    uint64_t P = (G / gcd_u64((uint64_t)n_mtiles, G));  // smallest P with n_mtiles*P a multiple of the SM count
+    while (P * 2 * tc::KP <= 2048 && P * (uint64_t)n_mtiles < 2 * G) P *= 2;  // at least two items per SM when cheap
+    P = std::min<uint64_t>(P, 4096 / tc::KP);
+    P = std::min<uint64_t>(P, tiles_total);
+    const uint32_t tiles_per_part = (uint32_t)ceil_div(tiles_total, P);
+    P = ceil_div(tiles_total, tiles_per_part);
+    const int n_items = n_mtiles * (int)P;
+    LB_TRY(idx->w_cand_score.ensure((size_t)nq * P * tc::KP * 4));
+    LB_TRY(idx->w_cand_row.ensure((size_t)nq * P * tc::KP * 4));
+    LB_TRY(idx->w_cand_thr.ensure((size_t)nq * P * 4));
+    LB_TRY(idx->w_flags.ensure((size_t)nq * 4 + 16));
+    uint32_t* flags = idx->w_flags.as<uint32_t>();  // [0]=kernel error, [1]=n_uncertified, [4..]=per-query flags
+    LB_CUDA_TRY(cudaMemsetAsync(flags, 0, 16, idx->stream));
+
+    tc::TcArgs a{};
+    a.qb = idx->w_qb.as<__nv_bfloat16>();
+    a.nq = nq;
+    a.n_mtiles = n_mtiles;
+    a.Dp = Dp;
+    a.n_rows = (uint32_t)idx->n;
+    a.tiles_total = tiles_total;
+    a.tiles_per_part = tiles_per_part;
+    a.P = (int)P;
+    a.cand_score = idx->w_cand_score.as<float>();
+    a.cand_row = idx->w_cand_row.as<uint32_t>();
+    a.cand_thr = idx->w_cand_thr.as<float>();
+    a.error_flag = flags;
+    a.dump = dump;
+    LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
+    tc::coarse_topk_kernel<<<std::min<int>(idx->sm_count, n_items), tc::NUM_THREADS, tc::SMEM_BYTES, idx->stream>>>(sh.tmap, a);
+    LB_CUDA_TRY(cudaGetLastError());
+    if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
+
+    tc::FinArgs f{};
+    f.cand_score = a.cand_score;
+    f.cand_row = a.cand_row;
+    f.cand_thr = a.cand_thr;
+    f.P = (int)P;
+    f.M1 = next_pow2((int)P * tc::KP);
+    f.R = std::min(1024, std::max(128, next_pow2(4 * k)));
+    f.corpus = idx->rows.as<float>();
+    f.dim = (int)idx->dim;
+    f.queries = d_queries;
+    f.qnorm = idx->w_qnorm.as<float>();
+    f.max_norm = idx->max_norm.as<float>() + kind;
+    f.nq = nq;
+    f.k = k;
+    f.metric = metric;
+    f.eps_rel = (0.00390625f * 1.01f + (float)Dp * 4.76837158e-7f) * 1.0001f;
+    f.small_seg = idx->small_seg.as<uint32_t>();
+    f.n_small = idx->n_small;
+    f.out_rows = d_rows;
+    f.out_dists = d_dists;
+    f.out_counts = d_counts;
+    f.uncertified = flags + 4;
+    f.n_uncertified = flags + 1;
+    size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4;
+    if (metric_ascending(metric)) {
+        LB_CUDA_TRY(cudaFuncSetAttribute(tc::finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        tc::finalize_kernel<true><<<nq, 256, fsmem, idx->stream>>>(f);
+    } else {
+        LB_CUDA_TRY(cudaFuncSetAttribute(tc::finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        tc::finalize_kernel<false><<<nq, 256, fsmem, idx->stream>>>(f);
+    }
+    LB_CUDA_TRY(cudaGetLastError());
+    idx->stats.kernels_launched += 3;
+    idx->stats.n_partitions = (uint32_t)P;
+    idx->stats.plan_used = 1;
+    idx->stats.algorithmic_bytes = (uint64_t)idx->n * Dp * 2;
+    idx->stats.algorithmic_flops = 2ull * (uint64_t)nq * idx->n * idx->dim;
+
+    uint32_t head[2] = {0, 0};
+    LB_CUDA_TRY(cudaMemcpyAsync(head, flags, 8, cudaMemcpyDeviceToHost, idx->stream));
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    if (idx->timing) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);
+        idx->stats.ms_dominant = ms;
+    }
+    if (head[0] != 0)
+        return fail(LB_INTERNAL, "tensor-core coarse kernel: barrier wait timed out (code " + std::to_string(head[0]) + ")");
+    idx->stats.n_fallback = head[1];
+    if (head[1] > 0) {
+        // Re-run the uncertified queries with the exact scan and overwrite their result slots.
+        std::vector<uint32_t> fl(nq);
+        LB_CUDA_TRY(cudaMemcpy(fl.data(), flags + 4, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> qmap;
+        for (int q = 0; q < nq; ++q)
+            if (fl[q]) qmap.push_back((uint32_t)q);
+        const int ns = (int)qmap.size();
+        LB_TRY(idx->w_sub_q.ensure((size_t)ns * idx->dim * 4));
+        LB_TRY(idx->w_qmap.ensure((size_t)ns * 4));
+        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_qmap.p, qmap.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, idx->stream));
+        for (int i = 0; i < ns; ++i)
+            LB_CUDA_TRY(cudaMemcpyAsync(idx->w_sub_q.as<float>() + (size_t)i * idx->dim, d_queries + (size_t)qmap[i] * idx->dim,
+                                        (size_t)idx->dim * 4, cudaMemcpyDeviceToDevice, idx->stream));
+        ScanRequest r;
+        r.corpus = idx->rows.as<float>();
+        r.n_rows = idx->n;
+        r.dim = (int)idx->dim;
+        r.queries = idx->w_sub_q.as<float>();
+        r.nq = ns;
+        r.k = k;
+        r.metric = metric;
+        r.small_seg = idx->small_seg.as<uint32_t>();
+        r.n_small = idx->n_small;
+        r.qmap = idx->w_qmap.as<uint32_t>();
+        r.out_rows = d_rows;
+        r.out_dists = d_dists;
+        r.out_counts = d_counts;
+        int kern = 0;
+        LB_TRY(run_scan(idx, r, &kern, nullptr));
+        idx->stats.kernels_launched += kern;
+        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
+    return LB_OK;
+}
+
+// ---- search on device-resident queries ---------------------------------------------------------------------------------
+// d_queries: f32 [nq][dim] (LB_F32 index) or u64 [nq][n_words] (LB_PACKED_U64 index); results [nq][k], k <= n.
+static int search_device_impl(lb_index* idx, int metric, const void* d_queries, int nq, int k, const uint64_t* d_allow,
+                              uint32_t* d_rows, float* d_dists, uint32_t* d_counts) {
+    idx->stats = lb_search_stats{};
+    if (idx->timing) cudaEventRecord(idx->ev[2], idx->stream);
+    int kernels = 0;
+    float ms_dom = 0;
+    if (idx->dtype == LB_PACKED_U64 || metric_binary(metric)) {
+        // FlatMmap::search binary branch (flat_mmap.rs:839-845): packed rows, packed queries
+        const uint64_t* words;
+        const uint64_t* qwords;
+        int nw;
+        if (idx->dtype == LB_PACKED_U64) {
+            if (!metric_binary(metric)) return fail(LB_INVALID_ARGUMENT, "a packed index only serves hamming/jaccard/tanimoto/dice");
+            words = idx->rows.as<uint64_t>();
+            qwords = reinterpret_cast<const uint64_t*>(d_queries);
+            nw = idx->n_words;
+        } else {
+            LB_TRY(ensure_packed(idx));
+            nw = (idx->dim + 63) / 64;
+            LB_TRY(idx->w_qwords.ensure((size_t)nq * nw * 8));
+            const int warps = 8;
+            pack_binary_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, idx->stream>>>(
+                reinterpret_cast<const float*>(d_queries), (uint64_t)nq, (int)idx->dim, nw, 0.5f, idx->w_qwords.as<uint64_t>());
+            LB_CUDA_TRY(cudaGetLastError());
+            ++kernels;
+            words = idx->packed.as<uint64_t>();
+            qwords = idx->w_qwords.as<uint64_t>();
+        }
+        ScanRequest r;
+        r.words = words;
+        r.n_rows = idx->n;
+        r.n_words = nw;
+        r.qwords = qwords;
+        r.nq = nq;
+        r.k = k;
+        r.metric = metric;
+        r.allow_bits = d_allow;
+        r.out_rows = d_rows;
+        r.out_dists = d_dists;
+        r.out_counts = d_counts;
+        LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
+        idx->stats.plan_used = 2;
+        idx->stats.algorithmic_bytes = (uint64_t)idx->n * nw * 8;
+    } else if (idx->plan == LB_PLAN_AUTO && d_allow == nullptr && tc_supported(idx, metric) && k <= 256 && idx->n >= 64) {
+        LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr));
+        kernels = idx->stats.kernels_launched;
+        ms_dom = idx->stats.ms_dominant;
+    } else {
+        LB_TRY(refresh_small_segments(idx));
+        ScanRequest r;
+        r.corpus = idx->rows.as<float>();
+        r.n_rows = idx->n;
+        r.dim = (int)idx->dim;
+        r.queries = reinterpret_cast<const float*>(d_queries);
+        r.nq = nq;
+        r.k = k;
+        r.metric = metric;
+        r.allow_bits = d_allow;
+        r.small_seg = idx->small_seg.as<uint32_t>();
+        r.n_small = idx->n_small;
+        r.out_rows = d_rows;
+        r.out_dists = d_dists;
+        r.out_counts = d_counts;
+        std::vector<uint32_t> unhandled;
+        if (metric == LB_JENSEN_SHANNON) {
+            // FlatMmap::search Jensen-Shannon branch (flat_mmap.rs:912-921, :926-1111)
+            LB_TRY(ensure_js_stats(idx));
+            LB_TRY(idx->w_qstats.ensure((size_t)nq * 8));
+            LB_TRY(idx->w_nq.ensure((size_t)nq * idx->dim * 4));
+            LB_TRY(idx->w_flags.ensure((size_t)nq * 4 + 16));
+            row_stats_kernel<<<(nq + 127) / 128, 128, 0, idx->stream>>>(reinterpret_cast<const float*>(d_queries), (uint64_t)nq,
+                                                                        (int)idx->dim, idx->w_qstats.as<float>());
+            js_prepare_queries_kernel<<<nq, 128, 0, idx->stream>>>(reinterpret_cast<const float*>(d_queries), nq, (int)idx->dim,
+                                                                   idx->w_qstats.as<float>(), idx->w_nq.as<float>(),
+                                                                   idx->w_flags.as<uint32_t>() + 4);
+            LB_CUDA_TRY(cudaGetLastError());
+            kernels += 2;
+            unhandled.resize(nq);
+            LB_CUDA_TRY(cudaMemcpyAsync(unhandled.data(), idx->w_flags.as<uint32_t>() + 4, (size_t)nq * 4, cudaMemcpyDeviceToHost,
+                                        idx->stream));
+            LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+            r.queries = idx->w_nq.as<float>();
+            r.row_stats = idx->js_stats.as<float>();
+            r.query_stats = idx->w_qstats.as<float>();
+            r.sqrt_scores = 1;
+        }
+        LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
+        if (metric == LB_JENSEN_SHANNON) {
+            // queries the cached path cannot serve fall back to the direct kernel (prepare_jensen_shannon_query -> None)
+            std::vector<uint32_t> qmap;
+            for (int q = 0; q < nq; ++q)
+                if (unhandled[q]) qmap.push_back((uint32_t)q);
+            if (!qmap.empty()) {
+                const int ns = (int)qmap.size();
+                LB_TRY(idx->w_sub_q.ensure((size_t)ns * idx->dim * 4));
+                LB_TRY(idx->w_qmap.ensure((size_t)ns * 4));
+                LB_CUDA_TRY(cudaMemcpyAsync(idx->w_qmap.p, qmap.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, idx->stream));
+                for (int i = 0; i < ns; ++i)
+                    LB_CUDA_TRY(cudaMemcpyAsync(idx->w_sub_q.as<float>() + (size_t)i * idx->dim,
+                                                reinterpret_cast<const float*>(d_queries) + (size_t)qmap[i] * idx->dim,
+                                                (size_t)idx->dim * 4, cudaMemcpyDeviceToDevice, idx->stream));
+                ScanRequest r2 = r;
+                r2.queries = idx->w_sub_q.as<float>();
+                r2.nq = ns;
+                r2.row_stats = nullptr;
+                r2.query_stats = nullptr;
+                r2.sqrt_scores = 0;
+                r2.qmap = idx->w_qmap.as<uint32_t>();
+                LB_TRY(run_scan(idx, r2, &kernels, nullptr));
+            }
+        }
+        idx->stats.plan_used = 0;
+        idx->stats.algorithmic_bytes = (uint64_t)idx->n * idx->dim * 4;
+    }
+    if (idx->timing) cudaEventRecord(idx->ev[3], idx->stream);
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    idx->stats.kernels_launched = kernels;
+    idx->stats.ms_dominant = ms_dom;
+    if (idx->timing) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, idx->ev[2], idx->ev[3]);
+        idx->stats.ms_total = ms;
+    }
+    return LB_OK;
+}
+
+static int check_metric(int metric) {
+    if (metric < 0 || metric >= LB_METRIC_COUNT) return fail(LB_INVALID_ARGUMENT, "Unknown metric: " + std::to_string(metric));
+    return LB_OK;
+}
+
+constexpr int QUERY_BATCH = 4096;
+constexpr int MAX_K = 2048;
+
+}  // namespace lb
+
+// ============================================ C ABI ===================================================
+extern "C" {
+
+const char* lb_last_error(void) { return g_last_error.c_str(); }
+const char* lb_version(void) { return "lynse_b200 0.1.0 (sm_100a)"; }
+
+int lb_device_count(int* out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out = 0;
+        return fail(LB_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *out = n;
+    return LB_OK;
+}
+
+int lb_device_info(int device, char* name, int cap, uint64_t* total_bytes, uint64_t* free_bytes, int* sm_count) {
+    cudaDeviceProp prop;
+    LB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (name && cap > 0) {
+        strncpy(name, prop.name, (size_t)cap - 1);
+        name[cap - 1] = 0;
+    }
+    DeviceGuard g(device);
+    size_t fr = 0, tot = 0;
+    LB_CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+    if (total_bytes) *total_bytes = tot;
+    if (free_bytes) *free_bytes = fr;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return LB_OK;
+}
+
+int lb_index_create(lb_index** out, uint32_t dim, int dtype, int device) {
+    if (!out) return fail(LB_INVALID_ARGUMENT, "out is null");
+    if (dim == 0) return fail(LB_INVALID_ARGUMENT, "dimension must be positive");
+    if (dtype != LB_F32 && dtype != LB_PACKED_U64) return fail(LB_INVALID_ARGUMENT, "unknown dtype");
+    int ndev = 0;
+    LB_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(LB_INVALID_ARGUMENT, "no such CUDA device: " + std::to_string(device));
+    cudaDeviceProp prop;
+    LB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(LB_CUDA, std::string("liblynse_b200 is built for sm_100a only; device is ") + prop.name + " (sm_" +
+                                 std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    DeviceGuard g(device);
+    lb_index* idx = new lb_index();
+    idx->device = device;
+    idx->dim = dim;
+    idx->dtype = dtype;
+    idx->n_words = (int)((dim + 63) / 64);
+    idx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&idx->ev[i]);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&idx->user_ev[i]);
+    if (e != cudaSuccess) {
+        delete idx;
+        return fail(LB_CUDA, std::string("stream/event creation: ") + cudaGetErrorString(e));
+    }
+    *out = idx;
+    return LB_OK;
+}
+
+void lb_index_destroy(lb_index* idx) {
+    if (!idx) return;
+    {
+        DeviceGuard g(idx->device);
+        cudaStreamSynchronize(idx->stream);
+        DevBuf* bufs[] = {&idx->rows, &idx->packed, &idx->js_stats, &idx->max_norm, &idx->small_seg, &idx->w_queries,
+                          &idx->w_qwords, &idx->w_allow, &idx->w_lists, &idx->w_counts, &idx->w_thr, &idx->w_out_rows,
+                          &idx->w_out_dists, &idx->w_out_counts, &idx->w_qb, &idx->w_qnorm, &idx->w_cand_score,
+                          &idx->w_cand_row, &idx->w_cand_thr, &idx->w_flags, &idx->w_qstats, &idx->w_nq, &idx->w_sub_q,
+                          &idx->w_qmap, &idx->shadow[0].buf, &idx->shadow[1].buf, &idx->shadow[2].buf,
+                          &idx->w_send, &idx->w_recv, &idx->w_g_rows, &idx->w_g_dists, &idx->w_g_counts};
+        for (DevBuf* b : bufs) b->release();
+        for (int i = 0; i < 4; ++i)
+            if (idx->ev[i]) cudaEventDestroy(idx->ev[i]);
+        for (int i = 0; i < 8; ++i)
+            if (idx->user_ev[i]) cudaEventDestroy(idx->user_ev[i]);
+        cudaStreamDestroy(idx->stream);
+    }
+    delete idx;
+}
+
+int lb_index_reserve(lb_index* idx, uint64_t n_rows) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    if (n_rows >= 0xFFFFFFFFull) return fail(LB_INVALID_ARGUMENT, "an index holds fewer than 2^32-1 rows");
+    return grow_rows(idx, n_rows);
+}
+
+int lb_index_set_segment_target(lb_index* idx, uint64_t bytes) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->seg_target = bytes ? bytes : 256ull * 1024 * 1024;
+    return LB_OK;
+}
+
+static int append_common(lb_index* idx, const void* host, uint64_t n) {
+    if (n == 0) return LB_OK;
+    if (idx->n + n >= 0xFFFFFFFFull) return fail(LB_INVALID_ARGUMENT, "an index holds fewer than 2^32-1 rows");
+    LB_TRY(grow_rows(idx, idx->n + n));
+    size_t rb = row_bytes(idx);
+    LB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(idx->rows.p) + idx->n * rb, host, n * rb, cudaMemcpyHostToDevice, idx->stream));
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    account_segment(idx, n);
+    idx->n += n;
+    return LB_OK;
+}
+
+int lb_index_append_f32(lb_index* idx, const float* rows, uint64_t n) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "index does not store f32 rows");
+    if (!rows && n) return fail(LB_INVALID_ARGUMENT, "rows is null");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    return append_common(idx, rows, n);
+}
+
+int lb_index_append_packed(lb_index* idx, const uint64_t* words, uint64_t n) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (idx->dtype != LB_PACKED_U64) return fail(LB_INVALID_ARGUMENT, "index does not store packed rows");
+    if (!words && n) return fail(LB_INVALID_ARGUMENT, "words is null");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    return append_common(idx, words, n);
+}
+
+int lb_index_append_synthetic(lb_index* idx, uint64_t n, uint64_t seed, uint64_t row_offset) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    if (n == 0) return LB_OK;
+    if (idx->n + n >= 0xFFFFFFFFull) return fail(LB_INVALID_ARGUMENT, "an index holds fewer than 2^32-1 rows");
+    LB_TRY(grow_rows(idx, idx->n + n));
+    const unsigned blocks = (unsigned)idx->sm_count * 8;
+    if (idx->dtype == LB_F32) {
+        uint64_t ne = n * idx->dim;
+        synth_f32_kernel<<<blocks, 256, 0, idx->stream>>>(idx->rows.as<float>() + idx->n * idx->dim, ne, seed, row_offset * idx->dim);
+    } else {
+        uint64_t ne = n * (uint64_t)idx->n_words;
+        synth_u64_kernel<<<blocks, 256, 0, idx->stream>>>(idx->rows.as<uint64_t>() + idx->n * idx->n_words, ne, seed,
+                                                         row_offset * (uint64_t)idx->n_words);
+    }
+    LB_CUDA_TRY(cudaGetLastError());
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    account_segment(idx, n);
+    idx->n += n;
+    return LB_OK;
+}
+
+uint64_t lb_index_len(const lb_index* idx) { return idx ? idx->n : 0; }
+uint32_t lb_index_dim(const lb_index* idx) { return idx ? idx->dim : 0; }
+
+int lb_index_segments(const lb_index* idx, uint64_t* rows_out, int cap, int* n_segments) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (n_segments) *n_segments = (int)idx->segments.size();
+    for (int i = 0; i < cap && i < (int)idx->segments.size(); ++i) rows_out[i] = idx->segments[i];
+    return LB_OK;
+}
+
+int lb_index_read_rows_f32(lb_index* idx, uint64_t first, uint64_t n, float* out) {
+    if (!idx || !out) return fail(LB_INVALID_ARGUMENT, "null argument");
+    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "index does not store f32 rows");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    if (first + n > idx->n) return fail(LB_INVALID_ARGUMENT, "row range out of bounds");
+    LB_CUDA_TRY(cudaMemcpyAsync(out, idx->rows.as<float>() + first * idx->dim, n * idx->dim * 4, cudaMemcpyDeviceToHost, idx->stream));
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    return LB_OK;
+}
+
+int lb_index_prepare(lb_index* idx, int metric) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    LB_TRY(check_metric(metric));
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    if (idx->n == 0) return LB_OK;
+    if (metric_binary(metric)) {
+        LB_TRY(ensure_packed(idx));
+    } else if (idx->dtype == LB_PACKED_U64) {
+        return fail(LB_INVALID_ARGUMENT, "a packed index only serves hamming/jaccard/tanimoto/dice");
+    } else if (metric == LB_JENSEN_SHANNON) {
+        LB_TRY(ensure_js_stats(idx));
+    } else if (idx->plan == LB_PLAN_AUTO && tc_supported(idx, metric)) {
+        LB_TRY(ensure_shadow(idx, shadow_kind_for(metric)));
+    }
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    return LB_OK;
+}
+
+int lb_index_set_plan(lb_index* idx, int plan) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (plan != LB_PLAN_AUTO && plan != LB_PLAN_EXACT) return fail(LB_INVALID_ARGUMENT, "unknown plan");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->plan = plan;
+    return LB_OK;
+}
+
+int lb_index_set_timing(lb_index* idx, int enabled) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->timing = enabled != 0;
+    return LB_OK;
+}
+
+int lb_index_last_stats(const lb_index* idx, lb_search_stats* out) {
+    if (!idx || !out) return fail(LB_INVALID_ARGUMENT, "null argument");
+    *out = idx->stats;
+    return LB_OK;
+}
+
+static int search_host_common(lb_index* idx, int metric, const void* queries, size_t query_row_bytes, uint32_t nq, uint32_t k,
+                              const uint64_t* allow_bits, uint64_t allow_words, uint32_t* out_rows, float* out_dists,
+                              uint32_t* out_counts) {
+    LB_TRY(check_metric(metric));
+    if (nq && !queries) return fail(LB_INVALID_ARGUMENT, "queries is null");
+    if (k > (uint32_t)MAX_K) return fail(LB_UNSUPPORTED, "k above 2048 is not supported");
+    if (metric == LB_HAVERSINE && idx->dim != 2) return fail(LB_INVALID_ARGUMENT, "haversine requires dimension 2");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    const uint32_t kk = (uint32_t)std::min<uint64_t>(k, idx->n);  // k.min(n) (flat_mmap.rs:836)
+    for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+    for (size_t i = 0; i < (size_t)nq * k; ++i) {
+        out_rows[i] = ROW_NONE;
+        out_dists[i] = NAN;
+    }
+    if (nq == 0 || kk == 0) return LB_OK;  // k == 0 or empty index -> empty result (flat_mmap.rs:833-835)
+    const uint64_t* d_allow = nullptr;
+    if (allow_bits) {
+        uint64_t need = (idx->n + 63) / 64;
+        if (allow_words < need) return fail(LB_INVALID_ARGUMENT, "row filter is shorter than the index");
+        LB_TRY(idx->w_allow.ensure(need * 8));
+        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_allow.p, allow_bits, need * 8, cudaMemcpyHostToDevice, idx->stream));
+        d_allow = idx->w_allow.as<uint64_t>();
+    }
+    lb_search_stats acc{};
+    for (uint32_t q0 = 0; q0 < nq; q0 += QUERY_BATCH) {
+        const int nb = (int)std::min<uint32_t>(QUERY_BATCH, nq - q0);
+        LB_TRY(idx->w_queries.ensure((size_t)nb * query_row_bytes));
+        LB_TRY(idx->w_out_rows.ensure((size_t)nb * kk * 4));
+        LB_TRY(idx->w_out_dists.ensure((size_t)nb * kk * 4));
+        LB_TRY(idx->w_out_counts.ensure((size_t)nb * 4));
+        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_queries.p, reinterpret_cast<const char*>(queries) + (size_t)q0 * query_row_bytes,
+                                    (size_t)nb * query_row_bytes, cudaMemcpyHostToDevice, idx->stream));
+        LB_TRY(search_device_impl(idx, metric, idx->w_queries.p, nb, (int)kk, d_allow, idx->w_out_rows.as<uint32_t>(),
+                                  idx->w_out_dists.as<float>(), idx->w_out_counts.as<uint32_t>()));
+        LB_CUDA_TRY(cudaMemcpy2DAsync(out_rows + (size_t)q0 * k, (size_t)k * 4, idx->w_out_rows.p, (size_t)kk * 4, (size_t)kk * 4,
+                                      nb, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaMemcpy2DAsync(out_dists + (size_t)q0 * k, (size_t)k * 4, idx->w_out_dists.p, (size_t)kk * 4,
+                                      (size_t)kk * 4, nb, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaMemcpyAsync(out_counts + q0, idx->w_out_counts.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        acc.plan_used = idx->stats.plan_used;
+        acc.n_fallback += idx->stats.n_fallback;
+        acc.n_partitions = idx->stats.n_partitions;
+        acc.kernels_launched += idx->stats.kernels_launched;
+        acc.ms_dominant += idx->stats.ms_dominant;
+        acc.ms_total += idx->stats.ms_total;
+        acc.algorithmic_bytes += idx->stats.algorithmic_bytes;
+        acc.algorithmic_flops += idx->stats.algorithmic_flops;
+    }
+    idx->stats = acc;
+    return LB_OK;
+}
+
+int lb_index_search(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, const uint64_t* allow_bits,
+                    uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "use lb_index_search_packed for a packed index");
+    if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
+    return search_host_common(idx, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows, out_dists,
+                              out_counts);
+}
+
+int lb_index_search_packed(lb_index* idx, int metric, const uint64_t* query_words, uint32_t nq, uint32_t k, uint32_t* out_rows,
+                           float* out_dists, uint32_t* out_counts) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (idx->dtype != LB_PACKED_U64) return fail(LB_INVALID_ARGUMENT, "index does not store packed rows");
+    if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
+    if (metric >= 0 && metric < LB_METRIC_COUNT && !metric_binary(metric))
+        return fail(LB_INVALID_ARGUMENT, "a packed index only serves hamming/jaccard/tanimoto/dice");
+    return search_host_common(idx, metric, query_words, (size_t)idx->n_words * 8, nq, k, nullptr, 0, out_rows, out_dists, out_counts);
+}
+
+int lb_index_search_device(lb_index* idx, int metric, const void* d_queries, uint32_t nq, uint32_t k, uint32_t* d_out_rows,
+                           float* d_out_dists, uint32_t* d_out_counts) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    LB_TRY(check_metric(metric));
+    if (!d_queries || !d_out_rows || !d_out_dists || !d_out_counts) return fail(LB_INVALID_ARGUMENT, "null device pointer");
+    if (k == 0 || k > (uint32_t)MAX_K || k > idx->n) return fail(LB_INVALID_ARGUMENT, "k must be in [1, min(n, 2048)] for the device-resident entry point");
+    if (nq == 0 || nq > (uint32_t)QUERY_BATCH) return fail(LB_INVALID_ARGUMENT, "nq must be in [1, 4096] for the device-resident entry point");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    return search_device_impl(idx, metric, d_queries, (int)nq, (int)k, nullptr, d_out_rows, d_out_dists, d_out_counts);
+}
+
+// ---- stateless operators ------------------------------------------------------------------------------------------------
+int lb_compute_distance(const float* a, const float* b, uint32_t dim, int metric, float* out) {
+    LB_TRY(check_metric(metric));
+    if (!a || !b || !out) return fail(LB_INVALID_ARGUMENT, "null argument");
+    if (metric == LB_HAVERSINE && dim != 2)
+        return fail(LB_INVALID_ARGUMENT, "haversine requires two values: longitude and latitude in degrees");
+    float* d = nullptr;
+    LB_CUDA_TRY(cudaMalloc(&d, ((size_t)2 * dim + 4) * 4));
+    cudaError_t e = cudaMemcpy(d, a, (size_t)dim * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + dim, b, (size_t)dim * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        // b is read through 16-byte loads when dim % 4 == 0: keep both operands 16-byte aligned
+        pair_distance_kernel<<<1, 32>>>(d, d + dim, (int)dim, metric, d + 2 * (size_t)dim);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d + 2 * (size_t)dim, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LB_CUDA, std::string("lb_compute_distance: ") + cudaGetErrorString(e));
+    return LB_OK;
+}
+
+int lb_top_k_search(const float* query, const float* candidates, uint64_t n, uint32_t dim, uint32_t k, int metric, uint32_t* ids,
+                    float* dists, uint32_t* out_count) {
+    LB_TRY(check_metric(metric));
+    if (!out_count) return fail(LB_INVALID_ARGUMENT, "out_count is null");
+    *out_count = 0;
+    if (dim == 0) return fail(LB_INVALID_ARGUMENT, "dimension must be positive");
+    if (n == 0 || k == 0) return LB_OK;  // distance/mod.rs:381-384
+    if (!query || !candidates || !ids || !dists) return fail(LB_INVALID_ARGUMENT, "null argument");
+    if (metric == LB_HAVERSINE && dim != 2)
+        return fail(LB_INVALID_ARGUMENT, "haversine requires two values: longitude and latitude in degrees");
+    if (n >= 0xFFFFFFFFull) return fail(LB_INVALID_ARGUMENT, "too many candidates");
+    int device = 0;
+    LB_CUDA_TRY(cudaGetDevice(&device));
+    lb_index* idx = nullptr;
+    LB_TRY(lb_index_create(&idx, dim, LB_F32, device));
+    int st = lb_index_append_f32(idx, candidates, n);
+    if (st == LB_OK) {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        DeviceGuard g(idx->device);
+        const uint32_t kk = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(k, n), MAX_K);
+        st = (k > (uint32_t)MAX_K && n > (uint64_t)MAX_K) ? fail(LB_UNSUPPORTED, "k above 2048 is not supported") : LB_OK;
+        if (st == LB_OK) st = idx->w_queries.ensure((size_t)dim * 4);
+        if (st == LB_OK) st = idx->w_out_rows.ensure((size_t)kk * 4);
+        if (st == LB_OK) st = idx->w_out_dists.ensure((size_t)kk * 4);
+        if (st == LB_OK) st = idx->w_out_counts.ensure(4);
+        if (st == LB_OK) {
+            cudaError_t e = cudaMemcpyAsync(idx->w_queries.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, idx->stream);
+            if (e != cudaSuccess) st = fail(LB_CUDA, cudaGetErrorString(e));
+        }
+        if (st == LB_OK) {
+            ScanRequest r;
+            r.corpus = idx->rows.as<float>();
+            r.n_rows = n;
+            r.dim = (int)dim;
+            r.queries = idx->w_queries.as<float>();
+            r.nq = 1;
+            r.k = (int)kk;
+            r.metric = metric;
+            r.ip_single = 1;  // compute_distance_f32 -> inner_product_f32 (single-row kernel) for every candidate
+            r.out_rows = idx->w_out_rows.as<uint32_t>();
+            r.out_dists = idx->w_out_dists.as<float>();
+            r.out_counts = idx->w_out_counts.as<uint32_t>();
+            st = run_scan(idx, r, nullptr, nullptr);
+        }
+        if (st == LB_OK) {
+            cudaError_t e = cudaMemcpyAsync(ids, idx->w_out_rows.p, (size_t)kk * 4, cudaMemcpyDeviceToHost, idx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dists, idx->w_out_dists.p, (size_t)kk * 4, cudaMemcpyDeviceToHost, idx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out_count, idx->w_out_counts.p, 4, cudaMemcpyDeviceToHost, idx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
+            if (e != cudaSuccess) st = fail(LB_CUDA, std::string("lb_top_k_search: ") + cudaGetErrorString(e));
+        }
+    }
+    std::string keep = g_last_error;
+    lb_index_destroy(idx);
+    g_last_error = keep;
+    return st;
+}
+
+// ---- memory helpers ---------------------------------------------------------------------------------------------------------
+int lb_device_malloc(int device, uint64_t bytes, void** out) {
+    DeviceGuard g(device);
+    LB_CUDA_TRY(cudaMalloc(out, bytes));
+    return LB_OK;
+}
+int lb_device_free(int device, void* p) {
+    DeviceGuard g(device);
+    LB_CUDA_TRY(cudaFree(p));
+    return LB_OK;
+}
+int lb_host_malloc(uint64_t bytes, void** out) {
+    LB_CUDA_TRY(cudaMallocHost(out, bytes));
+    return LB_OK;
+}
+int lb_host_free(void* p) {
+    LB_CUDA_TRY(cudaFreeHost(p));
+    return LB_OK;
+}
+int lb_memcpy_h2d(int device, void* dst, const void* src, uint64_t bytes) {
+    DeviceGuard g(device);
+    LB_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return LB_OK;
+}
+int lb_memcpy_d2h(int device, void* dst, const void* src, uint64_t bytes) {
+    DeviceGuard g(device);
+    LB_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return LB_OK;
+}
+int lb_device_synchronize(int device) {
+    DeviceGuard g(device);
+    LB_CUDA_TRY(cudaDeviceSynchronize());
+    return LB_OK;
+}
+int lb_device_memset(int device, void* dst, int value, uint64_t bytes) {
+    DeviceGuard g(device);
+    LB_CUDA_TRY(cudaMemset(dst, value, bytes));
+    return LB_OK;
+}
+
+// ---- NCCL (resolved at run time so the library loads on boxes without it) ----------------------------------------------------
+namespace {
+struct NcclId {
+    char internal[128];
+};
+typedef void* NcclComm;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+            api.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(api.handle, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<int (*)(NcclComm*, int, NcclId, int)>(dlsym(api.handle, "ncclCommInitRank"));
+            api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t)>(
+                dlsym(api.handle, "ncclAllGather"));
+            api.CommDestroy = reinterpret_cast<int (*)(NcclComm)>(dlsym(api.handle, "ncclCommDestroy"));
+            api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.handle, "ncclGetErrorString"));
+        }
+    }
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) return nullptr;
+    return &api;
+}
+int nccl_fail(NcclApi* api, const char* what, int rc) {
+    return fail(LB_NCCL, std::string(what) + ": " + (api && api->GetErrorString ? api->GetErrorString(rc) : "nccl error"));
+}
+}  // namespace
+
+struct lb_comm {
+    NcclComm comm = nullptr;
+    int device = 0, world = 1, rank = 0;
+    cudaStream_t stream = nullptr;
+};
+
+int lb_nccl_unique_id(uint8_t* id128) {
+    NcclApi* api = nccl_api();
+    if (!api) return fail(LB_NCCL, "libnccl.so.2 could not be loaded");
+    NcclId id;
+    int rc = api->GetUniqueId(&id);
+    if (rc != 0) return nccl_fail(api, "ncclGetUniqueId", rc);
+    memcpy(id128, id.internal, 128);
+    return LB_OK;
+}
+
+int lb_comm_create(lb_comm** out, int device, int world_size, int rank, const uint8_t* id128) {
+    NcclApi* api = nccl_api();
+    if (!api) return fail(LB_NCCL, "libnccl.so.2 could not be loaded");
+    if (!out || !id128 || world_size < 1 || rank < 0 || rank >= world_size) return fail(LB_INVALID_ARGUMENT, "bad communicator arguments");
+    LB_CUDA_TRY(cudaSetDevice(device));
+    lb_comm* c = new lb_comm();
+    c->device = device;
+    c->world = world_size;
+    c->rank = rank;
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    int rc = api->CommInitRank(&c->comm, world_size, id, rank);
+    if (rc != 0) {
+        delete c;
+        return nccl_fail(api, "ncclCommInitRank", rc);
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        api->CommDestroy(c->comm);
+        delete c;
+        return fail(LB_CUDA, cudaGetErrorString(e));
+    }
+    *out = c;
+    return LB_OK;
+}
+
+void lb_comm_destroy(lb_comm* c) {
+    if (!c) return;
+    NcclApi* api = nccl_api();
+    cudaSetDevice(c->device);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    if (api && c->comm) api->CommDestroy(c->comm);
+    delete c;
+}
+
+static int comm_allgather_on(lb_comm* c, const void* d_send, void* d_recv, uint64_t bytes, cudaStream_t stream) {
+    NcclApi* api = nccl_api();
+    if (!api || !c) return fail(LB_NCCL, "communicator is not initialised");
+    int rc = api->AllGather(d_send, d_recv, (size_t)bytes, /*ncclUint8*/ 1, c->comm, stream);
+    if (rc != 0) return nccl_fail(api, "ncclAllGather", rc);
+    return LB_OK;
+}
+
+int lb_comm_allgather(lb_comm* c, const void* d_send, void* d_recv, uint64_t bytes) {
+    if (!c) return fail(LB_NCCL, "communicator is not initialised");
+    DeviceGuard g(c->device);
+    LB_TRY(comm_allgather_on(c, d_send, d_recv, bytes, c->stream));
+    LB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LB_OK;
+}
+
+int lb_comm_barrier(lb_comm* c) {
+    if (!c) return fail(LB_NCCL, "communicator is not initialised");
+    DeviceGuard g(c->device);
+    static thread_local void* scratch = nullptr;
+    if (!scratch) LB_CUDA_TRY(cudaMalloc(&scratch, 8 * 1024));
+    if (c->world > 1024) return fail(LB_UNSUPPORTED, "world too large");
+    return lb_comm_allgather(c, scratch, reinterpret_cast<char*>(scratch) + 4096, 4);
+}
+
+// ---- sharded search: local search -> ncclAllGather -> GPU merge by (score, global row) ------------------------------------------------
+namespace lb {
+// block layout per rank: rows u32 [nq*k] | dists f32 [nq*k] | counts u32 [nq] | pad to 8 | base u64
+static size_t shard_block_bytes(uint32_t nq, uint32_t k) {
+    size_t b = (size_t)nq * k * 8 + (size_t)nq * 4;
+    b = (b + 7) & ~(size_t)7;
+    return b + 8;
+}
+__global__ void shard_pack_tail_kernel(unsigned char* block, size_t base_off, uint64_t row_base) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *reinterpret_cast<uint64_t*>(block + base_off) = row_base;
+}
+// one CTA per query; G*k <= 4096
+__global__ void __launch_bounds__(256) merge_shards_kernel(const unsigned char* gathered, int G, size_t block_bytes, int nq, int k,
+                                                           int M, int asc, uint64_t* out_rows, float* out_dists,
+                                                           uint32_t* out_counts) {
+    extern __shared__ __align__(16) unsigned char smem_shard[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_shard);
+    const int q = blockIdx.x;
+    const size_t dists_off = (size_t)nq * k * 4, counts_off = (size_t)nq * k * 8;
+    const size_t base_off = block_bytes - 8;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        uint64_t key = KEY_NONE;
+        if (i < G * k) {
+            int g = i / k, j = i - g * k;
+            const unsigned char* blk = gathered + (size_t)g * block_bytes;
+            uint32_t cnt = reinterpret_cast<const uint32_t*>(blk + counts_off)[q];
+            if ((uint32_t)j < cnt) {
+                float d = reinterpret_cast<const float*>(blk + dists_off)[(size_t)q * k + j];
+                // each shard's list is already ordered by (score, local row) and shards are ascending row ranges,
+                // so (score, shard, position) is (score, global row)
+                key = asc ? make_key<true>(d, (uint32_t)i) : make_key<false>(d, (uint32_t)i);
+            }
+        }
+        s[i] = key;
+    }
+    bitonic_sort_u64(s, M);
+    __shared__ uint32_t n_valid;
+    if (threadIdx.x == 0) n_valid = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        uint64_t key = s[i];
+        uint64_t row = ~0ull;
+        float d = __int_as_float(0x7fc00000);
+        if (key != KEY_NONE) {
+            int slot = (int)key_row(key);
+            int g = slot / k, j = slot - g * k;
+            const unsigned char* blk = gathered + (size_t)g * block_bytes;
+            uint64_t base = *reinterpret_cast<const uint64_t*>(blk + base_off);
+            row = base + reinterpret_cast<const uint32_t*>(blk)[(size_t)q * k + j];
+            d = reinterpret_cast<const float*>(blk + dists_off)[(size_t)q * k + j];
+            atomicAdd(&n_valid, 1u);
+        }
+        out_rows[(size_t)q * k + i] = row;
+        out_dists[(size_t)q * k + i] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out_counts[q] = n_valid;
+}
+
+static int sharded_search_device_impl(lb_comm* comm, lb_index* idx, int metric, const void* d_queries, uint32_t nq, uint32_t k,
+                                      uint64_t row_base, uint64_t* d_out_rows, float* d_out_dists, uint32_t* d_out_counts) {
+    const int G = comm ? comm->world : 1;
+    if ((uint64_t)G * k > 4096) return fail(LB_UNSUPPORTED, "world_size * k must not exceed 4096");
+    const size_t bb = shard_block_bytes(nq, k);
+    LB_TRY(idx->w_send.ensure(bb));
+    LB_TRY(idx->w_recv.ensure(bb * G));
+    unsigned char* send = idx->w_send.as<unsigned char>();
+    uint32_t* s_rows = reinterpret_cast<uint32_t*>(send);
+    float* s_dists = reinterpret_cast<float*>(send + (size_t)nq * k * 4);
+    uint32_t* s_counts = reinterpret_cast<uint32_t*>(send + (size_t)nq * k * 8);
+    LB_TRY(search_device_impl(idx, metric, d_queries, (int)nq, (int)k, nullptr, s_rows, s_dists, s_counts));
+    const lb_search_stats local = idx->stats;
+    shard_pack_tail_kernel<<<1, 32, 0, idx->stream>>>(send, bb - 8, row_base);
+    LB_CUDA_TRY(cudaGetLastError());
+    const unsigned char* gathered = send;
+    if (G > 1) {
+        LB_TRY(comm_allgather_on(comm, send, idx->w_recv.p, bb, idx->stream));
+        gathered = idx->w_recv.as<unsigned char>();
+    }
+    const int M = std::max(2, next_pow2(G * (int)k));
+    merge_shards_kernel<<<nq, 256, (size_t)M * 8, idx->stream>>>(gathered, G, bb, (int)nq, (int)k, M, metric_ascending(metric) ? 1 : 0,
+                                                               d_out_rows, d_out_dists, d_out_counts);
+    LB_CUDA_TRY(cudaGetLastError());
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    idx->stats = local;
+    idx->stats.kernels_launched += 2 + (G > 1 ? 1 : 0);
+    return LB_OK;
+}
+}  // namespace lb
+
+static int sharded_check(lb_comm* comm, lb_index* idx, int metric, uint32_t nq, uint32_t k) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    LB_TRY(check_metric(metric));
+    if (comm && comm->device != idx->device) return fail(LB_INVALID_ARGUMENT, "communicator and index live on different devices");
+    if (k == 0 || k > (uint32_t)MAX_K || k > idx->n) return fail(LB_INVALID_ARGUMENT, "k must be in [1, min(shard rows, 2048)] for a sharded search");
+    if (nq == 0 || nq > (uint32_t)QUERY_BATCH) return fail(LB_INVALID_ARGUMENT, "nq must be in [1, 4096] for a sharded search");
+    return LB_OK;
+}
+
+int lb_sharded_search_device(lb_comm* comm, lb_index* idx, int metric, const void* d_queries, uint32_t nq, uint32_t k,
+                             uint64_t row_base, uint64_t* d_out_rows, float* d_out_dists, uint32_t* d_out_counts) {
+    LB_TRY(sharded_check(comm, idx, metric, nq, k));
+    if (!d_queries || !d_out_rows || !d_out_dists || !d_out_counts) return fail(LB_INVALID_ARGUMENT, "null device pointer");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    return sharded_search_device_impl(comm, idx, metric, d_queries, nq, k, row_base, d_out_rows, d_out_dists, d_out_counts);
+}
+
+int lb_sharded_search(lb_comm* comm, lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, uint64_t row_base,
+                      uint64_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    LB_TRY(sharded_check(comm, idx, metric, nq, k));
+    if (!queries || !out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "null argument");
+    if (idx->dtype != LB_F32) return fail(LB_UNSUPPORTED, "sharded search over packed indexes takes device-resident queries");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    LB_TRY(idx->w_queries.ensure((size_t)nq * idx->dim * 4));
+    LB_TRY(idx->w_g_rows.ensure((size_t)nq * k * 8));
+    LB_TRY(idx->w_g_dists.ensure((size_t)nq * k * 4));
+    LB_TRY(idx->w_g_counts.ensure((size_t)nq * 4));
+    LB_CUDA_TRY(cudaMemcpyAsync(idx->w_queries.p, queries, (size_t)nq * idx->dim * 4, cudaMemcpyHostToDevice, idx->stream));
+    LB_TRY(sharded_search_device_impl(comm, idx, metric, idx->w_queries.p, nq, k, row_base, idx->w_g_rows.as<uint64_t>(),
+                                      idx->w_g_dists.as<float>(), idx->w_g_counts.as<uint32_t>()));
+    LB_CUDA_TRY(cudaMemcpyAsync(out_rows, idx->w_g_rows.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, idx->stream));
+    LB_CUDA_TRY(cudaMemcpyAsync(out_dists, idx->w_g_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, idx->stream));
+    LB_CUDA_TRY(cudaMemcpyAsync(out_counts, idx->w_g_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    return LB_OK;
+}
+
+int lb_index_event_record(lb_index* idx, int slot) {
+    if (!idx || slot < 0 || slot >= 8) return fail(LB_INVALID_ARGUMENT, "bad event slot");
+    DeviceGuard g(idx->device);
+    LB_CUDA_TRY(cudaEventRecord(idx->user_ev[slot], idx->stream));
+    return LB_OK;
+}
+
+int lb_index_event_elapsed_ms(lb_index* idx, int slot_a, int slot_b, float* ms) {
+    if (!idx || !ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) return fail(LB_INVALID_ARGUMENT, "bad event slot");
+    DeviceGuard g(idx->device);
+    LB_CUDA_TRY(cudaEventSynchronize(idx->user_ev[slot_b]));
+    LB_CUDA_TRY(cudaEventElapsedTime(ms, idx->user_ev[slot_a], idx->user_ev[slot_b]));
+    return LB_OK;
+}
+
+// ---- diagnostics ------------------------------------------------------------------------------------------------------------------
+int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uint32_t n, uint32_t dim, float* out) {
+    if (!queries || !rows || !out || nq == 0 || n == 0) return fail(LB_INVALID_ARGUMENT, "bad arguments");
+    int device = 0;
+    LB_CUDA_TRY(cudaGetDevice(&device));
+    lb_index* idx = nullptr;
+    LB_TRY(lb_index_create(&idx, dim, LB_F32, device));
+    int st = lb_index_append_f32(idx, rows, n);
+    float* dump = nullptr;
+    if (st == LB_OK && !tc_supported(idx, LB_IP)) st = fail(LB_UNSUPPORTED, "dimension too large for the tensor-core path");
+    if (st == LB_OK) {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        DeviceGuard g(idx->device);
+        const int n_mtiles = ((int)nq + tc::BM - 1) / tc::BM;
+        const size_t ld = (size_t)ceil_div(n, tc::BN) * tc::BN;
+        const size_t dump_elems = (size_t)n_mtiles * tc::BM * ld;
+        const int k = (int)std::min<uint32_t>(n, 10);
+        cudaError_t e = cudaMalloc(&dump, dump_elems * 4);
+        if (e == cudaSuccess) e = cudaMemset(dump, 0xFF, dump_elems * 4);
+        if (e != cudaSuccess) st = fail(LB_CUDA, cudaGetErrorString(e));
+        if (st == LB_OK) st = idx->w_queries.ensure((size_t)nq * dim * 4);
+        if (st == LB_OK) st = idx->w_out_rows.ensure((size_t)nq * k * 4);
+        if (st == LB_OK) st = idx->w_out_dists.ensure((size_t)nq * k * 4);
+        if (st == LB_OK) st = idx->w_out_counts.ensure((size_t)nq * 4);
+        if (st == LB_OK) {
+            e = cudaMemcpyAsync(idx->w_queries.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, idx->stream);
+            if (e != cudaSuccess) st = fail(LB_CUDA, cudaGetErrorString(e));
+        }
+        if (st == LB_OK)
+            st = run_tc(idx, LB_IP, idx->w_queries.as<float>(), (int)nq, k, idx->w_out_rows.as<uint32_t>(),
+                        idx->w_out_dists.as<float>(), idx->w_out_counts.as<uint32_t>(), dump);
+        if (st == LB_OK) {
+            e = cudaMemcpy2D(out, (size_t)n * 4, dump, ld * 4, (size_t)n * 4, nq, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) st = fail(LB_CUDA, cudaGetErrorString(e));
+        }
+    }
+    if (dump) cudaFree(dump);
+    std::string keep = g_last_error;
+    lb_index_destroy(idx);
+    g_last_error = keep;
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar (BASELINE.json north_star): ids and ordering bit-exact; f32 scores bit-exact for the
+metrics whose arithmetic is IEEE add/mul/fma/div/sqrt only, and within 1e-5 relative for the
+ones with libm transcendentals (Jensen-Shannon tails, Haversine, Hellinger, ...).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EXACT_BITS = ["ip", "l2", "cosine", "l1", "chebyshev", "canberra", "bray_curtis", "hamming", "jaccard", "tanimoto", "dice"]
+TOL_METRICS = ["correlation", "hellinger", "wasserstein", "jensen_shannon"]
+REL_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lynsedb_b200
+
+    return lynsedb_b200
+
+
+def _data(n, dim, seed, positive=True):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, dim), dtype=np.float32)
+    return x if positive else (x - 0.5).astype(np.float32)
+
+
+def _check(oracle_out, gpu_out, metric, k):
+    o_ids, o_d, o_c = oracle_out
+    rows, dists, counts = gpu_out
+    assert np.array_equal(o_c, counts)
+    for q in range(rows.shape[0]):
+        c = int(counts[q])
+        assert np.array_equal(o_ids[q, :c].astype(np.uint32), rows[q, :c]), f"ids differ for query {q} ({metric})"
+        if metric in EXACT_BITS:
+            assert np.array_equal(o_d[q, :c].view(np.uint32), dists[q, :c].view(np.uint32)), \
+                f"scores not bit-identical for query {q} ({metric}): {o_d[q, :c]} vs {dists[q, :c]}"
+        else:
+            np.testing.assert_allclose(dists[q, :c], o_d[q, :c], rtol=REL_TOL, atol=1e-7)
+        assert np.all(rows[q, c:] == 0xFFFFFFFF)
+
+
+# ---- stateless operators -----------------------------------------------------------------------
+def test_compute_distance_known_answers(L):
+    a, b = np.array([1, 2, 3, 4], np.float32), np.array([4, 3, 2, 1], np.float32)
+    assert L.compute_distance(a, b, "ip") == 20.0
+    assert L.compute_distance(np.array([1, 0, 0], np.float32), np.array([0, 1, 0], np.float32), "l2") == 2.0
+    assert abs(L.compute_distance(a, a, "cosine")) < 1e-6
+    assert abs(L.compute_distance(np.array([1, 0], np.float32), np.array([0, 1], np.float32), "cosine") - 1.0) < 1e-6
+    assert L.compute_distance(np.array([1, 2, 3], np.float32), np.array([2, 4, 1], np.float32), "l1") == 5.0
+    assert L.compute_distance(np.array([1, 2, 3], np.float32), np.array([2, 4, 0], np.float32), "chebyshev") == 3.0
+    sh, bj = np.array([121.4737, 31.2304], np.float32), np.array([116.4074, 39.9042], np.float32)
+    assert abs(L.compute_distance(sh, bj, "haversine") - 1_067_000) < 10_000
+    assert L.compute_distance(sh, sh, "haversine") == 0.0
+    with pytest.raises(ValueError, match="Unknown metric"):
+        L.compute_distance(a, b, "nope")
+    with pytest.raises(ValueError, match="dimensions must match"):
+        L.compute_distance(a, b[:3], "ip")
+    with pytest.raises(ValueError, match="haversine requires two values"):
+        L.compute_distance(a, b, "haversine")
+
+
+@pytest.mark.parametrize("metric", EXACT_BITS + TOL_METRICS)
+@pytest.mark.parametrize("dim", [19, 64])
+def test_compute_distance_matches_oracle(L, oracle, metric, dim):
+    x = _data(6, dim, 11)
+    for i in range(0, 6, 2):
+        got = L.compute_distance(x[i], x[i + 1], metric)
+        want = oracle.compute_distance(x[i], x[i + 1], metric)
+        if metric in EXACT_BITS:
+            assert np.float32(got).view(np.uint32) == np.float32(want).view(np.uint32), (metric, got, want)
+        else:
+            assert abs(got - want) <= REL_TOL * abs(want) + 1e-7
+
+
+@pytest.mark.parametrize("metric", EXACT_BITS + TOL_METRICS)
+def test_top_k_search_matches_oracle(L, oracle, metric):
+    cands, q = _data(3000, 19, 5), _data(1, 19, 6)[0]
+    ids, d = L.top_k_search(q, cands, metric, 7)
+    o_ids, o_d = oracle.top_k_search(q, cands, metric, 7)
+    if metric in ("hamming", "jaccard", "tanimoto", "dice"):
+        # integer-valued distances tie massively; the reference's quickselect does not order ties by id,
+        # so only the distance multiset is defined
+        assert np.array_equal(np.sort(d), np.sort(o_d))
+        return
+    assert np.array_equal(ids, o_ids)
+    if metric in EXACT_BITS:
+        assert np.array_equal(d.view(np.uint32), o_d.view(np.uint32))
+    else:
+        np.testing.assert_allclose(d, o_d, rtol=REL_TOL, atol=1e-7)
+
+
+def test_top_k_search_edges(L):
+    cands, q = _data(5, 8, 1), _data(1, 8, 2)[0]
+    ids, d = L.top_k_search(q, cands, "l2", 50)
+    assert len(ids) == 5 and np.all(np.diff(d) >= 0)
+    ids, d = L.top_k_search(q, cands, "ip", 0)
+    assert len(ids) == 0 and len(d) == 0
+    ids, d = L.top_k_search(q, np.zeros((0, 8), np.float32), "ip", 3)
+    assert len(ids) == 0
+    with pytest.raises(ValueError, match="Query dimension must match"):
+        L.top_k_search(q[:4], cands, "ip", 3)
+
+
+# ---- flat scan, exact plan -------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", EXACT_BITS + TOL_METRICS)
+def test_flat_exact_plan_large_segment(L, oracle, metric):
+    n, dim, nq, k = 6000, 24, 5, 10  # n >= 4096: chunked path; 6000/3 = 2000 rows per chunk, a multiple of 8
+    corpus, queries = _data(n, dim, 21), _data(nq, dim, 22)
+    with L.DeviceIndex(dim) as idx:
+        idx.set_plan("exact")
+        idx.append(corpus)
+        got = idx.search(queries, k, metric)
+    want = oracle.store_batch_search(corpus, queries, k, metric, n_threads=3)
+    _check(want, got, metric, k)
+
+
+@pytest.mark.parametrize("metric", ["ip", "l2", "cosine", "jensen_shannon", "hamming"])
+def test_flat_exact_plan_small_segment(L, oracle, metric):
+    n, dim, nq, k = 1000, 37, 4, 12  # n < 4096: sequential path, IP takes the two-accumulator kernel
+    corpus, queries = _data(n, dim, 31), _data(nq, dim, 32)
+    with L.DeviceIndex(dim) as idx:
+        idx.set_plan("exact")
+        idx.append(corpus)
+        got = idx.search(queries, k, metric)
+    want = oracle.store_batch_search(corpus, queries, k, metric, n_threads=4)
+    _check(want, got, metric, k)
+
+
+def test_flat_multi_segment_merge(L, oracle):
+    dim, k = 16, 9
+    parts = [_data(4800, dim, 41), _data(700, dim, 42), _data(5600, dim, 43)]
+    queries = _data(6, dim, 44)
+    with L.DeviceIndex(dim) as idx:
+        idx.set_plan("exact")
+        idx.set_segment_target(1)  # every append opens its own segment
+        for p in parts:
+            idx.append(p)
+        assert idx.segments() == [4800, 700, 5600]
+        got_ip = idx.search(queries, k, "ip")
+        got_l2 = idx.search(queries, k, "l2")
+    corpus = np.concatenate(parts)
+    seg = [4800, 700, 5600]
+    _check(oracle.store_batch_search(corpus, queries, k, "ip", segment_rows=seg, n_threads=1), got_ip, "ip", k)
+    _check(oracle.store_batch_search(corpus, queries, k, "l2", segment_rows=seg, n_threads=1), got_l2, "l2", k)
+
+
+def test_segment_accounting_follows_the_reference(L):
+    with L.DeviceIndex(4) as idx:
+        idx.set_segment_target(1024)  # the reference's test-mode target (vector_store.rs:34)
+        idx.append(np.zeros((40, 4), np.float32))   # 640 B
+        idx.append(np.zeros((20, 4), np.float32))   # 960 B <= 1024: joins
+        idx.append(np.zeros((10, 4), np.float32))   # would be 1120 B: new segment
+        idx.append(np.zeros((100, 4), np.float32))  # larger than the target on its own: own segment, never split
+        assert idx.segments() == [60, 10, 100]
+        assert len(idx) == 170
+
+
+def test_ties_resolve_by_row(L, oracle):
+    rng = np.random.default_rng(7)
+    base = (rng.random((50, 130)) > 0.5).astype(np.float32)  # dim 130: three words, ragged tail
+    corpus = np.tile(base, (120, 1))  # 6000 rows, every row duplicated 120 times
+    queries = base[:3]
+    for metric in ("hamming", "tanimoto", "dice", "l2"):
+        with L.DeviceIndex(130) as idx:
+            idx.set_plan("exact")
+            idx.append(corpus)
+            got = idx.search(queries, 40, metric)
+        _check(oracle.store_batch_search(corpus, queries, 40, metric, n_threads=3), got, metric, 40)
+        assert np.array_equal(got[0][0, :3], [0, 50, 100])
+
+
+def test_k_larger_than_n_and_empty(L):
+    with L.DeviceIndex(8) as idx:
+        q = _data(2, 8, 1)
+        rows, dists, counts = idx.search(q, 5, "ip")
+        assert np.all(counts == 0) and np.all(rows == 0xFFFFFFFF)
+        idx.append(_data(3, 8, 2))
+        rows, dists, counts = idx.search(q, 5, "l2")
+        assert np.all(counts == 3) and np.all(rows[:, 3:] == 0xFFFFFFFF)
+        rows, dists, counts = idx.search(q, 0, "l2")
+        assert rows.shape == (2, 0) and np.all(counts == 0)
+        with pytest.raises(ValueError, match="Dimension mismatch"):
+            idx.search(_data(1, 9, 3), 2, "ip")
+        with pytest.raises(ValueError, match="Unknown metric"):
+            idx.search(q, 2, "bogus")
+
+
+def test_filtered_scan(L, oracle):
+    n, dim, k = 9000, 20, 8
+    corpus, queries = _data(n, dim, 51), _data(4, dim, 52)
+    allowed = np.sort(np.random.default_rng(53).choice(n, 4200, replace=False))
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        rows, dists, counts = idx.search(queries, k, "l2", allow_bits=L.make_allow_bits(n, allowed))
+    o_ids, o_d, o_c = oracle.store_batch_search(corpus[allowed], queries, k, "l2", n_threads=1)
+    assert np.array_equal(counts, o_c)
+    assert np.array_equal(rows, allowed[o_ids.astype(np.int64)].astype(np.uint32))
+    assert np.array_equal(dists.view(np.uint32), o_d.view(np.uint32))
+
+
+# ---- packed one-bit rows ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("words", [1, 3, 16])
+@pytest.mark.parametrize("metric", ["hamming", "tanimoto", "jaccard", "dice"])
+def test_packed_index(L, oracle, words, metric):
+    rng = np.random.default_rng(61)
+    n, nq, k = 7000, 5, 32
+    data = rng.integers(0, 2**63, size=(n, words), dtype=np.uint64) * 2 + rng.integers(0, 2, size=(n, words), dtype=np.uint64)
+    queries = data[rng.choice(n, nq, replace=False)] ^ rng.integers(0, 2**20, size=(nq, words), dtype=np.uint64)
+    with L.DeviceIndex(64 * words, dtype="packed") as idx:
+        idx.append(data)
+        got = idx.search(queries, k, metric)
+    _check(oracle.packed_batch_search(data, queries, k, metric, n_threads=1), got, metric, k)
+
+
+def test_packed_cache_equals_thresholded_f32(L, oracle):
+    # the reference's own pin: packed binary == f32-thresholded (flat_mmap.rs:6385-6421), dim 130
+    rng = np.random.default_rng(62)
+    corpus = rng.random((5000, 130), dtype=np.float32)
+    queries = rng.random((3, 130), dtype=np.float32)
+    for metric in ("hamming", "jaccard", "tanimoto", "dice"):
+        with L.DeviceIndex(130) as idx:
+            idx.append(corpus)
+            got = idx.search(queries, 25, metric)
+        _check(oracle.store_batch_search(corpus, queries, 25, metric, n_threads=1), got, metric, 25)
+
+
+# ---- tensor-core plan ------------------------------------------------------------------------------------------
+def _bf16_round(x):
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def test_tc_raw_scores_pin_operand_layout(L):
+    import ctypes as C
+    from lynsedb_b200 import _native as N
+
+    rng = np.random.default_rng(71)
+    for (nq, n, dim) in [(5, 200, 64), (130, 333, 200), (128, 1000, 768)]:
+        q = (rng.random((nq, dim), dtype=np.float32) - 0.5)
+        c = (rng.random((n, dim), dtype=np.float32) - 0.5)
+        out = np.zeros((nq, n), dtype=np.float32)
+        N.check(N.lib().lb_debug_tc_scores(N.fptr(q), nq, N.fptr(c), n, dim, N.fptr(out)))
+        want = _bf16_round(q).astype(np.float64) @ _bf16_round(c).astype(np.float64).T
+        err = np.abs(out - want).max()
+        assert err < 2e-3, f"tcgen05 scores off by {err} for shape {(nq, n, dim)}"
+
+
+@pytest.mark.parametrize("metric,n,dim,nq,k", [
+    ("ip", 20000, 768, 130, 10),
+    ("ip", 50001, 128, 64, 10),
+    ("l2", 30000, 128, 40, 100),
+    ("cosine", 30000, 96, 40, 10),
+    ("l2", 12345, 765, 3, 5),
+])
+def test_tc_plan_matches_oracle(L, oracle, metric, n, dim, nq, k):
+    corpus, queries = _data(n, dim, 81), _data(nq, dim, 82)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, metric)
+        st = idx.last_stats()
+    assert st["plan_used"] == 1, st
+    threads = 1
+    if metric == "ip" and n % 8:
+        # the n % 8 tail rows of the single chunk take the two-accumulator kernel in the reference; keep them out
+        want = oracle.store_batch_search(corpus, queries, k, metric, n_threads=threads)
+        rows, dists, counts = got
+        assert np.array_equal(want[0].astype(np.uint32), rows)
+        np.testing.assert_allclose(dists, want[1], rtol=REL_TOL)
+        return
+    _check(oracle.store_batch_search(corpus, queries, k, metric, n_threads=threads), got, metric, k)
+
+
+def test_tc_plan_signed_data_and_small_segments(L, oracle):
+    dim, k = 64, 10
+    parts = [_data(8000, dim, 91, positive=False), _data(1000, dim, 92, positive=False)]
+    queries = _data(9, dim, 93, positive=False)
+    with L.DeviceIndex(dim) as idx:
+        idx.set_segment_target(1)
+        for p in parts:
+            idx.append(p)
+        got = idx.search(queries, k, "ip")
+        assert idx.last_stats()["plan_used"] == 1
+    _check(oracle.store_batch_search(np.concatenate(parts), queries, k, "ip", segment_rows=[8000, 1000], n_threads=1),
+           got, "ip", k)
+
+
+def test_tc_uncertified_queries_fall_back_to_the_exact_scan(L, oracle):
+    # near-duplicate rows: gaps far below the bf16 error bound, so the shortlist cannot be certified
+    rng = np.random.default_rng(95)
+    base = rng.random((1, 128), dtype=np.float32)
+    corpus = np.repeat(base, 8000, axis=0) + rng.random((8000, 128), dtype=np.float32) * 1e-4
+    queries = rng.random((5, 128), dtype=np.float32)
+    with L.DeviceIndex(128) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, 10, "ip")
+        st = idx.last_stats()
+    assert st["plan_used"] == 1 and st["n_fallback"] == 5, st
+    _check(oracle.store_batch_search(corpus, queries, 10, "ip", n_threads=1), got, "ip", 10)
+
+
+def test_tc_and_exact_plans_agree(L):
+    n, dim, nq, k = 40000, 256, 33, 20
+    corpus, queries = _data(n, dim, 101), _data(nq, dim, 102)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        a = idx.search(queries, k, "ip")
+        idx.set_plan("exact")
+        b = idx.search(queries, k, "ip")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+# ---- synthetic generator -------------------------------------------------------------------------------------------
+def test_device_synthetic_rows_match_host(L):
+    from lynsedb_b200 import synthetic
+
+    with L.DeviceIndex(24) as idx:
+        idx.append_synthetic(1000, seed=42, row_offset=123456789)
+        got = idx.read_rows(990, 10)
+    want = synthetic.rows_f32(42, np.arange(123456789 + 990, 123456789 + 1000), 24)
+    assert np.array_equal(got, want)
+
+
+# ---- reference-style FlatIndex ---------------------------------------------------------------------------------------
+def test_flat_index_surface(L, oracle, tmp_path):
+    data = _data(300, 16, 111)
+    idx = L.FlatIndex(str(tmp_path / "vectors.bin"), 16)
+    idx.write(data)
+    assert len(idx) == 300 and idx.dim == 16
+    ids, d = idx.search(data[17], k=5, metric="l2")
+    assert ids[0] == 17 and d[0] == 0.0
+    res = idx.batch_search(data[:4], k=3, metric="ip")
+    o_ids, o_d, _ = oracle.store_batch_search(data, data[:4], 3, "ip", n_threads=1)
+    for i, (ids, d) in enumerate(res):
+        assert np.array_equal(ids, o_ids[i].astype(np.uint32))
+    reopened = L.FlatIndex(str(tmp_path / "vectors.bin"), 16)
+    assert len(reopened) == 300
+    with pytest.raises(ValueError, match="Unknown metric"):
+        idx.search(data[0], 3, "zzz")
