@@ -202,6 +202,9 @@ int lb_index_event_elapsed_ms(lb_index* idx, int slot_a, int slot_b, float* ms);
  * accumulator scores [nq][n] (debug builds of the parity tests use it to pin
  * the tcgen05 operand layouts). */
 int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uint32_t n, uint32_t dim, float* out);
+/* tcgen05.mma issue-rate probe (M=128, K=16, bf16): `iters` MMAs round-robin over n_acc accumulators of n columns,
+ * A from TMEM (a_in_tmem=1) or shared memory; returns SM cycles (max over CTAs) to completion and to end of issue. */
+int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int grid, uint64_t* cycles_total, uint64_t* cycles_issue);
 
 #ifdef __cplusplus
 }

@@ -34,17 +34,14 @@ namespace lb {
 namespace tc {
 
 constexpr int BM = 128;           // queries per work item == TMEM lanes
-constexpr int BN = 64;            // corpus rows per accumulator tile
+constexpr int BN = 64;            // default corpus rows per accumulator tile (see TileCfg)
 constexpr int KBLK = 64;          // bf16 elements per 128-byte swizzle row
-constexpr int STAGE_KBLKS = 4;    // K blocks per pipeline stage
 constexpr int NSTAGES = 6;
 constexpr int KP = 16;            // shortlist entries kept per (partition, query)
 constexpr int MAX_DP = 768;       // padded dim limit: A occupies Dp/2 <= 384 TMEM columns
-constexpr int TILE_BYTES = BN * KBLK * 2;            // 8192
-constexpr int STAGE_BYTES = STAGE_KBLKS * TILE_BYTES;  // 32768
+constexpr int STAGE_BYTES = 32768;  // one pipeline stage of corpus K-blocks
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int TMEM_D_COL = 384;
 constexpr uint32_t SMEM_LIST_OFF = NSTAGES * STAGE_BYTES;             // 196608
 constexpr uint32_t SMEM_BAR_OFF = SMEM_LIST_OFF + 2 * KP * BM * 4;    // + 16384
 constexpr uint32_t SMEM_BYTES = SMEM_BAR_OFF + 256 + 1024;            // + barriers + alignment slack
@@ -52,7 +49,7 @@ constexpr uint32_t SMEM_BYTES = SMEM_BAR_OFF + 256 + 1024;            // + barri
 struct TcArgs {
     const __nv_bfloat16* qb;  // [n_mtiles*128][Dp] bf16 queries, zero padded
     int nq;
-    int n_mtiles;
+    int n_mtiles;             // query tiles of 128; qb is padded to a multiple of the cluster size tiles
     int Dp;                   // padded dim, multiple of 64, <= MAX_DP
     uint32_t n_rows;
     uint32_t tiles_total;     // ceil(n_rows / 64)
@@ -61,6 +58,8 @@ struct TcArgs {
     float* cand_score;        // [nq][P][KP]
     uint32_t* cand_row;       // [nq][P][KP]
     float* cand_thr;          // [nq][P]
+    int share_floor;          // 1: partitions of a query share their shortlist floor through gthr (needs k <= KP - 4)
+    uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable f32 bits)
     uint32_t* error_flag;     // set non-zero when a barrier wait timed out
     float* dump;              // optional [n_mtiles*128][tiles_total*64] raw scores (diagnostics)
 };
@@ -137,6 +136,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
         ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// multicast variants: the box lands at the same CTA-relative offset of every CTA in cta_mask and completes
+// tx bytes on the mbarrier at the same offset there; the commit arrives on the mbarrier of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar,
+                                                  uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -171,16 +194,51 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ---- the coarse kernel -----------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// Tile shape: BN_ corpus rows per accumulator, NBUF accumulators in TMEM columns [512 - NBUF*BN_, 512);
+// the A operand (queries) needs Dp/2 <= 512 - NBUF*BN_ columns.  Stages are always 32 KiB:
+// KPS = 32768 / (BN_*128) K-blocks of [BN_ rows x 64 bf16] each.
+template <int BN_, int NBUF>
+struct TileCfg {
+    static constexpr int kBN = BN_;
+    static constexpr int kNBuf = NBUF;
+    static constexpr int kDCol = TMEM_COLS - NBUF * BN_;
+    static constexpr int kMaxDp = 2 * kDCol;
+    static constexpr int kTileBytes = BN_ * KBLK * 2;
+    static constexpr int kKPS = STAGE_BYTES / kTileBytes;
+    static constexpr uint32_t kIdesc =
+        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+// CLUSTER = 2: two CTAs of a cluster work on the same row partition for two neighbouring query tiles; each loads
+// half of every corpus K-block and multicasts it into both CTAs' shared memory, so every shadow byte crosses
+// the L2 -> SM fabric once per CTA pair instead of once per CTA.
+template <int BN_, int NBUF, int CLUSTER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+    using Cfg = TileCfg<BN_, NBUF>;
+    constexpr int KPS = Cfg::kKPS;
+    constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1u);
+    const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
+    // work items are per cluster: (query-tile group, partition); this CTA takes query tile group*CLUSTER + crank
+    const int n_mgroups = (a.n_mtiles + CLUSTER - 1) / CLUSTER;
+    const int first_item = (int)(blockIdx.x / CLUSTER), item_stride = (int)(gridDim.x / CLUSTER);
     extern __shared__ __align__(16) unsigned char smem_tc[];
     const uint32_t smem_base = (smem_u32(smem_tc) + 1023u) & ~1023u;
     unsigned char* smem = smem_tc + (smem_base - smem_u32(smem_tc));
-    float* l_score = reinterpret_cast<float*>(smem + SMEM_LIST_OFF);             // [KP][BM]
-    uint32_t* l_row = reinterpret_cast<uint32_t*>(smem + SMEM_LIST_OFF + KP * BM * 4);  // [KP][BM]
+    float* l_score = reinterpret_cast<float*>(smem + SMEM_LIST_OFF);                     // [KP][BM]
+    uint32_t* l_row = reinterpret_cast<uint32_t*>(smem + SMEM_LIST_OFF + KP * BM * 4);   // [KP][BM]
     const uint32_t bar_base = smem_base + SMEM_BAR_OFF;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
@@ -195,7 +253,7 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CLUSTER);  // every CTA of the cluster must have drained the stage
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
@@ -213,20 +271,21 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();  // peers' barriers are initialised before anything remote can arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int n_items = a.n_mtiles * a.P;
+    const int n_items = n_mgroups * a.P;
     const int nkb = a.Dp / KBLK;
-    const int stages_per_tile = (nkb + STAGE_KBLKS - 1) / STAGE_KBLKS;
+    const int stages_per_tile = (nkb + KPS - 1) / KPS;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage_iter = 0;
             bool ok = true;
-            for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
-                const uint32_t part = item / a.n_mtiles;
+            for (int item = first_item; item < n_items && ok; item += item_stride) {
+                const uint32_t part = item / n_mgroups;
                 const uint32_t t0 = part * a.tiles_per_part;
                 const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
                 for (uint32_t t = t0; t < t1 && ok; ++t) {
@@ -234,50 +293,70 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
                         const int stage = stage_iter % NSTAGES;
                         const uint32_t phase = (stage_iter / NSTAGES) & 1u;
                         if (!mbar_wait(empty_bar(stage), phase ^ 1u, abort_flag, 1)) { ok = false; break; }
-                        const int kbc = min(STAGE_KBLKS, nkb - s * STAGE_KBLKS);
-                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kbc * TILE_BYTES);
-                        for (int kb = 0; kb < kbc; ++kb)
-                            tma_load_2d(smem_base + stage * STAGE_BYTES + kb * TILE_BYTES, &tmap,
-                                        (s * STAGE_KBLKS + kb) * KBLK, (int)(t * BN), full_bar(stage));
+                        const int kbc = min(KPS, nkb - s * KPS);
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kbc * Cfg::kTileBytes);
+                        for (int kb = 0; kb < kbc; ++kb) {
+                            if (CLUSTER == 1) {
+                                tma_load_2d(smem_base + stage * STAGE_BYTES + kb * Cfg::kTileBytes, &tmap,
+                                            (s * KPS + kb) * KBLK, (int)(t * BN_), full_bar(stage));
+                            } else {
+                                // this CTA fetches rows [crank*BN/CLUSTER, ...) of the K-block for the whole cluster
+                                constexpr int kRowsPer = BN_ / CLUSTER;
+                                tma_load_2d_mcast(smem_base + stage * STAGE_BYTES + kb * Cfg::kTileBytes + crank * (kRowsPer * 128),
+                                                  &tmap, (s * KPS + kb) * KBLK, (int)(t * BN_ + crank * kRowsPer),
+                                                  full_bar(stage), kMask);
+                            }
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t stage_iter = 0, tile_iter = 0, item_iter = 0;
-            bool ok = true;
-            for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++item_iter) {
-                const uint32_t part = item / a.n_mtiles;
-                const uint32_t t0 = part * a.tiles_per_part;
-                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
-                if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
+        // ===================== MMA issuer (whole warp walks the loops; one elected lane issues) =====================
+        const bool leader = elect_one();
+        uint32_t stage_iter = 0, tile_iter = 0, item_iter = 0;
+        bool ok = true;
+        for (int item = first_item; item < n_items && ok; item += item_stride, ++item_iter) {
+            const uint32_t part = item / n_mgroups;
+            const uint32_t t0 = part * a.tiles_per_part;
+            const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+            if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
+            tcgen05_fence_after();
+            for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
+                const uint32_t buf = tile_iter % NBUF;
+                if (!mbar_wait(tempty_bar(buf), ((tile_iter / NBUF) & 1u) ^ 1u, abort_flag, 3)) { ok = false; break; }
                 tcgen05_fence_after();
-                for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
-                    const uint32_t buf = tile_iter & 1u;
-                    if (!mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1u) ^ 1u, abort_flag, 3)) { ok = false; break; }
+                const uint32_t d_tmem = tmem_base + Cfg::kDCol + buf * BN_;
+                for (int s = 0; s < stages_per_tile; ++s, ++stage_iter) {
+                    const int stage = stage_iter % NSTAGES;
+                    const uint32_t phase = (stage_iter / NSTAGES) & 1u;
+                    if (!mbar_wait(full_bar(stage), phase, abort_flag, 4)) { ok = false; break; }
                     tcgen05_fence_after();
-                    const uint32_t d_tmem = tmem_base + TMEM_D_COL + buf * BN;
-                    for (int s = 0; s < stages_per_tile; ++s, ++stage_iter) {
-                        const int stage = stage_iter % NSTAGES;
-                        const uint32_t phase = (stage_iter / NSTAGES) & 1u;
-                        if (!mbar_wait(full_bar(stage), phase, abort_flag, 4)) { ok = false; break; }
-                        tcgen05_fence_after();
-                        const int kbc = min(STAGE_KBLKS, nkb - s * STAGE_KBLKS);
-                        for (int kb = 0; kb < kbc; ++kb) {
+                    if (leader) {
+                        const int kbc = min(KPS, nkb - s * KPS);
+                        // descriptors of one stage differ only in the start-address field: +2 per K=16 step inside a
+                        // 128-byte swizzle row, + kTileBytes/16 per K block
+                        const uint64_t bdesc0 = make_b_desc(smem_base + stage * STAGE_BYTES);
+                        const uint32_t a0 = tmem_base + (uint32_t)(s * KPS * (KBLK / 16) * 8);
 #pragma unroll
-                            for (int k4 = 0; k4 < KBLK / 16; ++k4) {
-                                const int kstep = (s * STAGE_KBLKS + kb) * (KBLK / 16) + k4;
-                                const uint64_t bdesc =
-                                    make_b_desc(smem_base + stage * STAGE_BYTES + kb * TILE_BYTES + k4 * 32);
-                                umma_ts_bf16(d_tmem, tmem_base + kstep * 8, bdesc, IDESC, kstep > 0 ? 1u : 0u);
+                        for (int kb = 0; kb < KPS; ++kb) {
+                            if (kb < kbc) {
+#pragma unroll
+                                for (int k4 = 0; k4 < KBLK / 16; ++k4) {
+                                    const uint32_t acc = (kb == 0 && k4 == 0) ? (s > 0 ? 1u : 0u) : 1u;
+                                    umma_ts_bf16(d_tmem, a0 + (uint32_t)((kb * (KBLK / 16) + k4) * 8),
+                                                 bdesc0 + (uint64_t)(kb * (Cfg::kTileBytes >> 4) + k4 * 2), Cfg::kIdesc, acc);
+                                }
                             }
                         }
-                        umma_commit(empty_bar(stage));  // frees the stage when these MMAs have read it
+                        // frees the stage (in every CTA that multicast into it) when these MMAs have read it
+                        if (CLUSTER == 1) umma_commit(empty_bar(stage));
+                        else umma_commit_mcast(empty_bar(stage), kMask);
                     }
-                    if (ok) umma_commit(tfull_bar(buf));  // accumulator tile complete
+                    __syncwarp();
                 }
+                if (ok && leader) umma_commit(tfull_bar(buf));  // accumulator tile complete
+                __syncwarp();
             }
         }
     } else {
@@ -287,11 +366,12 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t tile_iter = 0;
         bool ok = true;
-        for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
-            const uint32_t part = item / a.n_mtiles, mt = item % a.n_mtiles;
+        for (int item = first_item; item < n_items && ok; item += item_stride) {
+            const uint32_t part = item / n_mgroups, mt = (item % n_mgroups) * CLUSTER + crank;
             const uint32_t t0 = part * a.tiles_per_part;
             const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
             const uint32_t gq = mt * BM + ql;
+            const bool q_valid = gq < (uint32_t)a.nq;
             // A operand: this thread's query row, bf16 pairs, into TMEM columns [0, Dp/2)
             {
                 const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)gq * a.Dp);
@@ -310,59 +390,78 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
                 l_score[j * BM + ql] = -INFINITY;
                 l_row[j * BM + ql] = ROW_NONE;
             }
-            float thr = gq < (uint32_t)a.nq ? -INFINITY : INFINITY;
+            // thr_l: worst score kept in this thread's list.  thr_g: best such value any partition of this query has
+            // published; a row at or below it can never be needed, so it also gates the list.
+            float thr_l = q_valid ? -INFINITY : INFINITY;
+            float thr_g = -INFINITY, thr_pub = -INFINITY;
             int min_pos = 0;
+            uint32_t* gthr = a.gthr + (q_valid ? gq : 0);
             tcgen05_fence_before();
             mbar_arrive(aready_bar);
             const uint32_t row_end = a.n_rows;
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
-                const uint32_t buf = tile_iter & 1u;
-                if (!mbar_wait(tfull_bar(buf), (tile_iter >> 1) & 1u, abort_flag, 5)) { ok = false; break; }
+                const uint32_t buf = tile_iter % NBUF;
+                const uint32_t g_bits = a.share_floor ? *reinterpret_cast<volatile uint32_t*>(gthr) : 0u;  // used after the wait
+                if (!mbar_wait(tfull_bar(buf), (tile_iter / NBUF) & 1u, abort_flag, 5)) { ok = false; break; }
                 tcgen05_fence_after();
-                uint32_t v[BN];
-                tmem_ld_32x32b_x32(lane_addr + TMEM_D_COL + buf * BN, v);
-                tmem_ld_32x32b_x32(lane_addr + TMEM_D_COL + buf * BN + 32, v + 32);
-                tmem_ld_wait();
-                tcgen05_fence_before();
-                mbar_arrive(tempty_bar(buf));  // accumulator is in registers: the MMA warp may reuse the buffer
-                const uint32_t row0 = t * BN;
-                if (a.dump != nullptr) {
-                    float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
+                if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
 #pragma unroll
-                    for (int i = 0; i < BN; ++i) drow[i] = __uint_as_float(v[i]);
-                }
-                bool any = false;
+                for (int h = 0; h < BN_ / 64; ++h) {
+                    uint32_t v[64];
+                    tmem_ld_32x32b_x32(lane_addr + Cfg::kDCol + buf * BN_ + h * 64, v);
+                    tmem_ld_32x32b_x32(lane_addr + Cfg::kDCol + buf * BN_ + h * 64 + 32, v + 32);
+                    tmem_ld_wait();
+                    if (h == BN_ / 64 - 1) {
+                        tcgen05_fence_before();
+                        mbar_arrive(tempty_bar(buf));  // accumulator is in registers: the MMA warp may reuse the buffer
+                    }
+                    const uint32_t row0 = t * BN_ + h * 64;
+                    if (a.dump != nullptr) {
+                        float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN_) + row0;
 #pragma unroll
-                for (int i = 0; i < BN; ++i) any |= (__uint_as_float(v[i]) > thr);
-                if (any) {
+                        for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
+                    }
+                    float thr = fmaxf(thr_l, thr_g);
+                    bool any = false;
 #pragma unroll
-                    for (int i = 0; i < BN; ++i) {
-                        const float s = __uint_as_float(v[i]);
-                        if (s > thr && row0 + i < row_end) {
-                            l_score[min_pos * BM + ql] = s;
-                            l_row[min_pos * BM + ql] = row0 + i;
-                            float mn = INFINITY;
-                            for (int j = 0; j < KP; ++j) {
-                                const float x = l_score[j * BM + ql];
-                                if (x < mn) { mn = x; min_pos = j; }
+                    for (int i = 0; i < 64; ++i) any |= (__uint_as_float(v[i]) > thr);
+                    if (any) {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) {
+                            const float sc = __uint_as_float(v[i]);
+                            if (sc > thr && row0 + i < row_end) {
+                                l_score[min_pos * BM + ql] = sc;
+                                l_row[min_pos * BM + ql] = row0 + i;
+                                float mn = INFINITY;
+                                for (int j = 0; j < KP; ++j) {
+                                    const float x = l_score[j * BM + ql];
+                                    if (x < mn) { mn = x; min_pos = j; }
+                                }
+                                thr_l = mn;
+                                thr = fmaxf(thr_l, thr_g);
                             }
-                            thr = mn;
+                        }
+                        if (a.share_floor && q_valid && thr_l > thr_pub && thr_l > thr_g) {  // list is full and its floor rose: publish
+                            atomicMax(gthr, f32_orderable(thr_l));
+                            thr_pub = thr_l;
                         }
                     }
                 }
             }
-            if (ok && gq < (uint32_t)a.nq) {
+            if (ok && q_valid) {
                 const size_t o = ((size_t)gq * a.P + part) * KP;
                 for (int j = 0; j < KP; ++j) {
                     a.cand_score[o + j] = l_score[j * BM + ql];
                     a.cand_row[o + j] = l_row[j * BM + ql];
                 }
-                a.cand_thr[(size_t)gq * a.P + part] = thr;
+                // every row this thread dropped scored <= max(thr_l, thr_g) at the time, and both only grow
+                a.cand_thr[(size_t)gq * a.P + part] = fmaxf(thr_l, thr_g);
             }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
     tcgen05_fence_after();
     if (threadIdx.x == 0 && *abort_flag) atomicMax(a.error_flag, *abort_flag);
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -556,6 +655,79 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
             a.uncertified[q] = 0;
         }
     }
+}
+
+// ---- diagnostics: tcgen05.mma issue-rate probe ------------------------------------------------------------------
+// One warp issues `iters` MMAs (M=128, K=16, bf16) round-robin over `n_acc` independent accumulators of N columns;
+// operands are whatever is in shared memory / TMEM (timing only).  Reports SM cycles from first issue to last commit.
+__device__ __forceinline__ void umma_ss_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int N, int NACC, bool TS>
+__global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters16, unsigned long long* cycles_out) {
+    extern __shared__ __align__(16) unsigned char smem_probe[];
+    const uint32_t smem_base = (smem_u32(smem_probe) + 1023u) & ~1023u;
+    unsigned char* smem = smem_probe + (smem_base - smem_u32(smem_probe));
+    const uint32_t bar = smem_base + 49152;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 49152 + 16);
+    for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+        tmem_relinquish();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp == 0) {
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint64_t a_desc = make_b_desc(smem_base);           // 128 rows x 64 bf16, SW128
+        const uint64_t b_desc = make_b_desc(smem_base + 16384);   // up to 256 rows x 64 bf16
+        constexpr uint32_t d_col0 = TMEM_COLS - NACC * N;
+        long long t0 = clock64(), t1 = t0;
+        if (leader) {
+            for (int it = 0; it < iters16; ++it) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t d = tmem_base + d_col0 + (uint32_t)((j % NACC) * N);
+                    const uint32_t acc = (j < NACC) ? (it > 0 ? 1u : 0u) : 1u;
+                    if (TS)
+                        umma_ts_bf16(d, tmem_base + (uint32_t)(j * 8), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
+                    else
+                        umma_ss_bf16(d, a_desc + (uint64_t)((j & 3) * 2), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
+                }
+            }
+            umma_commit(bar);
+            t1 = clock64();
+        }
+        __syncwarp();
+        while (!mbar_try_wait(bar, 0)) {
+        }
+        long long t2 = clock64();
+        if (leader) {
+            cycles_out[2 * blockIdx.x] = (unsigned long long)(t2 - t0);
+            cycles_out[2 * blockIdx.x + 1] = (unsigned long long)(t1 - t0);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace tc

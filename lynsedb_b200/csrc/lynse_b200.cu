@@ -73,6 +73,7 @@ struct Shadow {
     CUtensorMap tmap;
     uint64_t tmap_rows = 0;
     void* tmap_ptr = nullptr;
+    int tmap_bn = 0;    // box rows the tensor map was encoded for
 };
 
 static int next_pow2(int x) {
@@ -237,7 +238,26 @@ static bool tc_supported(const lb_index* idx, int metric) {
     return shadow_dp(idx, shadow_kind_for(metric)) <= tc::MAX_DP;
 }
 
-static int ensure_shadow(lb_index* idx, int kind) {
+// Accumulator tile of the coarse kernel: 128 corpus rows per MMA when two accumulators still fit next to the
+// A operand in TMEM (Dp <= 512), otherwise 64 rows double-buffered.  LYNSE_B200_TC_TILE=64|128|128x1 overrides.
+static int tc_tile_variant(int Dp) {
+    const char* env = getenv("LYNSE_B200_TC_TILE");
+    if (env) {
+        if (!strcmp(env, "64")) return 0;
+        if (!strcmp(env, "128x1")) return 1;
+        if (!strcmp(env, "128") && Dp <= tc::TileCfg<128, 2>::kMaxDp) return 2;
+    }
+    return Dp <= tc::TileCfg<128, 2>::kMaxDp ? 2 : 0;
+}
+static int tc_variant_bn(int v) { return v == 0 ? 64 : 128; }
+// CTAs per cluster sharing corpus tiles by TMA multicast: 2 when there are at least two query tiles.
+static int tc_cluster_size(int n_mtiles) {
+    const char* env = getenv("LYNSE_B200_TC_CLUSTER");
+    if (env && !strcmp(env, "1")) return 1;
+    return n_mtiles >= 2 ? 2 : 1;
+}
+
+static int ensure_shadow(lb_index* idx, int kind, int box_rows = 0) {
     Shadow& sh = idx->shadow[kind];
     int Dp = shadow_dp(idx, kind);
     if (!idx->max_norm.p) {
@@ -245,8 +265,8 @@ static int ensure_shadow(lb_index* idx, int kind) {
         LB_CUDA_TRY(cudaMemsetAsync(idx->max_norm.p, 0, 3 * sizeof(float), idx->stream));
     }
     if (sh.rows < idx->n) {
-        // keep 64 rows of slack so the last 64-row TMA box never leaves the allocation
-        LB_TRY(sh.buf.ensure(((size_t)idx->n + 64) * Dp * 2, true, idx->stream));
+        // keep a tile of slack rows so the last TMA box never leaves the allocation
+        LB_TRY(sh.buf.ensure(((size_t)idx->n + 128) * Dp * 2, true, idx->stream));
         sh.Dp = Dp;
         uint64_t first = sh.rows, cnt = idx->n - first;
         const int warps = 8;
@@ -256,12 +276,13 @@ static int ensure_shadow(lb_index* idx, int kind) {
         LB_CUDA_TRY(cudaGetLastError());
         sh.rows = idx->n;
     }
-    if (sh.tmap_rows != idx->n || sh.tmap_ptr != sh.buf.p) {
+    if (box_rows == 0) box_rows = tc_variant_bn(tc_tile_variant(Dp));
+    if (sh.tmap_rows != idx->n || sh.tmap_ptr != sh.buf.p || sh.tmap_bn != box_rows) {
         PFN_encodeTiled enc = get_encode_tiled();
         if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
         cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)idx->n};
         cuuint64_t gstride[1] = {(cuuint64_t)Dp * 2};
-        cuuint32_t box[2] = {(cuuint32_t)tc::KBLK, (cuuint32_t)tc::BN};
+        cuuint32_t box[2] = {(cuuint32_t)tc::KBLK, (cuuint32_t)box_rows};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&sh.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sh.buf.p, gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -269,6 +290,7 @@ static int ensure_shadow(lb_index* idx, int kind) {
         if (r != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
         sh.tmap_rows = idx->n;
         sh.tmap_ptr = sh.buf.p;
+        sh.tmap_bn = box_rows;
     }
     return LB_OK;
 }
@@ -406,12 +428,17 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
 static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uint32_t* d_rows, float* d_dists,
                   uint32_t* d_counts, float* dump) {
     const int kind = shadow_kind_for(metric);
-    LB_TRY(ensure_shadow(idx, kind));
+    const int variant = tc_tile_variant(shadow_dp(idx, kind));
+    const int BN = tc_variant_bn(variant);
+    LB_TRY(ensure_shadow(idx, kind, BN));
     LB_TRY(refresh_small_segments(idx));
     Shadow& sh = idx->shadow[kind];
     const int Dp = sh.Dp;
     const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
-    const int nq_pad = n_mtiles * tc::BM;
+    const int cluster = tc_cluster_size(n_mtiles);
+    const int n_mgroups = (n_mtiles + cluster - 1) / cluster;
+    const int nq_pad = n_mgroups * cluster * tc::BM;
+    LB_TRY(ensure_shadow(idx, kind, BN / cluster));  // tensor-map box = the rows one CTA fetches per K-block
     LB_TRY(idx->w_qb.ensure((size_t)nq_pad * Dp * 2));
     LB_TRY(idx->w_qnorm.ensure((size_t)nq * 4));
     {
@@ -420,21 +447,27 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
             d_queries, nq, nq_pad, (int)idx->dim, Dp, kind, idx->w_qb.as<__nv_bfloat16>(), idx->w_qnorm.as<float>());
         LB_CUDA_TRY(cudaGetLastError());
     }
-    const uint32_t tiles_total = (uint32_t)ceil_div(idx->n, tc::BN);
-    const uint64_t G = (uint64_t)idx->sm_count;
-    uint64_t P = (G / gcd_u64((uint64_t)n_mtiles, G));  // smallest P with n_mtiles*P a multiple of the SM count
-    while (P * 2 * tc::KP <= 2048 && P * (uint64_t)n_mtiles < 2 * G) P *= 2;  // at least two items per SM when cheap
+    const uint32_t tiles_total = (uint32_t)ceil_div(idx->n, BN);
+    const uint64_t G = (uint64_t)(idx->sm_count / cluster);  // clusters resident at once
+    uint64_t P = (G / gcd_u64((uint64_t)n_mgroups, G));  // smallest P with n_mgroups*P a multiple of the resident clusters
+    while (P * 2 * tc::KP <= 2048 && P * (uint64_t)n_mgroups < 2 * G) P *= 2;  // at least two items per cluster when cheap
+    // The union of the per-partition shortlists must reach well below rank k: aim at P*KP >= 32*k candidates.
+    {
+        const uint64_t base = P, want = ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
+        while (P < want && P + base <= 4096 / tc::KP) P += base;
+    }
     P = std::min<uint64_t>(P, 4096 / tc::KP);
     P = std::min<uint64_t>(P, tiles_total);
     const uint32_t tiles_per_part = (uint32_t)ceil_div(tiles_total, P);
     P = ceil_div(tiles_total, tiles_per_part);
-    const int n_items = n_mtiles * (int)P;
+    const int n_items = n_mgroups * (int)P;
     LB_TRY(idx->w_cand_score.ensure((size_t)nq * P * tc::KP * 4));
     LB_TRY(idx->w_cand_row.ensure((size_t)nq * P * tc::KP * 4));
     LB_TRY(idx->w_cand_thr.ensure((size_t)nq * P * 4));
-    LB_TRY(idx->w_flags.ensure((size_t)nq * 4 + 16));
-    uint32_t* flags = idx->w_flags.as<uint32_t>();  // [0]=kernel error, [1]=n_uncertified, [4..]=per-query flags
+    LB_TRY(idx->w_flags.ensure((size_t)nq * 8 + 16));
+    uint32_t* flags = idx->w_flags.as<uint32_t>();  // [0]=kernel error, [1]=n_uncertified, [4..]=per-query flags, then gthr[nq]
     LB_CUDA_TRY(cudaMemsetAsync(flags, 0, 16, idx->stream));
+    LB_CUDA_TRY(cudaMemsetAsync(flags + 4 + nq, 0, (size_t)nq * 4, idx->stream));
 
     tc::TcArgs a{};
     a.qb = idx->w_qb.as<__nv_bfloat16>();
@@ -448,11 +481,42 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     a.cand_score = idx->w_cand_score.as<float>();
     a.cand_row = idx->w_cand_row.as<uint32_t>();
     a.cand_thr = idx->w_cand_thr.as<float>();
+    a.gthr = flags + 4 + nq;
+    // A published floor is the KP-th best score of one partition: rows at or below it are outside the global top KP,
+    // which is only enough when k fits inside KP with some room for the bf16 error.
+    a.share_floor = (k <= tc::KP - 4) ? 1 : 0;
     a.error_flag = flags;
     a.dump = dump;
-    LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
-    tc::coarse_topk_kernel<<<std::min<int>(idx->sm_count, n_items), tc::NUM_THREADS, tc::SMEM_BYTES, idx->stream>>>(sh.tmap, a);
+    const int grid = std::min<int>(idx->sm_count / cluster, n_items) * cluster;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(tc::NUM_THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = idx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define LB_LAUNCH_TC(BNV, NB, CL)                                                                                          \
+    do {                                                                                                                   \
+        LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_topk_kernel<BNV, NB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)tc::SMEM_BYTES));                                                            \
+        if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);                                                         \
+        LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_topk_kernel<BNV, NB, CL>, sh.tmap, a));                            \
+    } while (0)
+    if (cluster == 1) {
+        if (variant == 0) LB_LAUNCH_TC(64, 2, 1);
+        else if (variant == 1) LB_LAUNCH_TC(128, 1, 1);
+        else LB_LAUNCH_TC(128, 2, 1);
+    } else {
+        if (variant == 0) LB_LAUNCH_TC(64, 2, 2);
+        else if (variant == 1) LB_LAUNCH_TC(128, 1, 2);
+        else LB_LAUNCH_TC(128, 2, 2);
+    }
+#undef LB_LAUNCH_TC
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
 
@@ -1373,8 +1437,10 @@ int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uin
     if (st == LB_OK) {
         std::lock_guard<std::mutex> lock(idx->mu);
         DeviceGuard g(idx->device);
-        const int n_mtiles = ((int)nq + tc::BM - 1) / tc::BM;
-        const size_t ld = (size_t)ceil_div(n, tc::BN) * tc::BN;
+        int n_mtiles = ((int)nq + tc::BM - 1) / tc::BM;
+        n_mtiles = (n_mtiles + 1) & ~1;  // room for the padded query tile of a 2-CTA cluster
+        const int dbg_bn = tc_variant_bn(tc_tile_variant(shadow_dp(idx, tc::SHADOW_IP)));
+        const size_t ld = (size_t)ceil_div(n, dbg_bn) * dbg_bn;
         const size_t dump_elems = (size_t)n_mtiles * tc::BM * ld;
         const int k = (int)std::min<uint32_t>(n, 10);
         cudaError_t e = cudaMalloc(&dump, dump_elems * 4);
@@ -1401,6 +1467,51 @@ int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uin
     lb_index_destroy(idx);
     g_last_error = keep;
     return st;
+}
+
+int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int grid, uint64_t* cycles_total, uint64_t* cycles_issue) {
+    if (iters < 16 || grid < 1) return fail(LB_INVALID_ARGUMENT, "bad probe arguments");
+    unsigned long long* d = nullptr;
+    LB_CUDA_TRY(cudaMalloc(&d, (size_t)grid * 16));
+    const size_t smem = 49152 + 64 + 1024;
+    cudaError_t e = cudaSuccess;
+    bool found = false;
+#define LB_PROBE(NN, NA, TSV)                                                                                         \
+    if (!found && n == NN && n_acc == NA && (a_in_tmem != 0) == TSV) {                                              \
+        found = true;                                                                                                \
+        e = cudaFuncSetAttribute(tc::mma_rate_kernel<NN, NA, TSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) {                                                                                      \
+            tc::mma_rate_kernel<NN, NA, TSV><<<grid, 64, smem>>>(iters / 16, d);                                     \
+            e = cudaDeviceSynchronize();                                                                             \
+        }                                                                                                            \
+    }
+    LB_PROBE(64, 1, true)
+    LB_PROBE(64, 2, true)
+    LB_PROBE(128, 1, true)
+    LB_PROBE(64, 1, false)
+    LB_PROBE(64, 2, false)
+    LB_PROBE(64, 4, false)
+    LB_PROBE(128, 1, false)
+    LB_PROBE(128, 2, false)
+    LB_PROBE(256, 1, false)
+    LB_PROBE(256, 2, false)
+#undef LB_PROBE
+    if (!found) {
+        cudaFree(d);
+        return fail(LB_INVALID_ARGUMENT, "probe shape not instantiated");
+    }
+    std::vector<unsigned long long> h((size_t)grid * 2);
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LB_CUDA, std::string("mma probe: ") + cudaGetErrorString(e));
+    unsigned long long mt = 0, mi = 0;
+    for (int i = 0; i < grid; ++i) {
+        mt = std::max(mt, h[2 * i]);
+        mi = std::max(mi, h[2 * i + 1]);
+    }
+    *cycles_total = mt;
+    *cycles_issue = mi;
+    return LB_OK;
 }
 
 }  // extern "C"

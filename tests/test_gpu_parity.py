@@ -302,6 +302,22 @@ def test_tc_uncertified_queries_fall_back_to_the_exact_scan(L, oracle):
     _check(oracle.store_batch_search(corpus, queries, 10, "ip", n_threads=1), got, "ip", 10)
 
 
+@pytest.mark.parametrize("cluster", ["1", "2"])
+@pytest.mark.parametrize("tile,nq", [("64", 150), ("128x1", 150), ("128", 150), ("64", 300), ("128", 300)])
+def test_tc_tile_variants_agree_with_oracle(L, oracle, tile, nq, cluster, monkeypatch):
+    monkeypatch.setenv("LYNSE_B200_TC_TILE", tile)
+    monkeypatch.setenv("LYNSE_B200_TC_CLUSTER", cluster)
+    n, dim, k = 33333, 320, 10
+    corpus, queries = _data(n, dim, 97), _data(nq, dim, 98)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "ip")
+        assert idx.last_stats()["plan_used"] == 1
+    want = oracle.store_batch_search(corpus, queries, k, "ip", n_threads=1)
+    assert np.array_equal(want[0].astype(np.uint32), got[0])
+    np.testing.assert_allclose(got[1], want[1], rtol=REL_TOL)
+
+
 def test_tc_and_exact_plans_agree(L):
     n, dim, nq, k = 40000, 256, 33, 20
     corpus, queries = _data(n, dim, 101), _data(nq, dim, 102)
