@@ -27,6 +27,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "lb_metrics.cuh"
 #include "lb_scan.cuh"
 
@@ -62,7 +64,19 @@ struct TcArgs {
     uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable f32 bits)
     uint32_t* error_flag;     // set non-zero when a barrier wait timed out
     float* dump;              // optional [n_mtiles*128][tiles_total*64] raw scores (diagnostics)
+    // Work mapping: cluster c serves query group (c % n_mgroups) of slot (c / n_mgroups); slot s walks the row
+    // partitions s, s + n_slots, s + 2 n_slots, ...  All query groups of a slot stream the same shadow tiles at the
+    // same time, so HBM is read once per slot and the other groups are served from L2.
+    int n_slots;
+    int parts_per_slot;
+    uint32_t* progress;       // [n_slots][PROGRESS_STRIDE] tiles issued per (slot, query group); zeroed per launch; null = free-running
+    int window;               // a query group never runs more than `window` tiles ahead of the slowest group of its slot
+    int prefetch_tiles;       // L2 prefetch distance of the TMA producer, in tiles (0 = off)
+    unsigned long long* prof; // optional [grid][8] cycle counters of the MMA issuer / epilogue (diagnostics)
+    int debug_mode;           // diagnostics only (results are garbage): bit 0 = producer skips the TMA loads,
+                              // bit 1 = epilogue releases accumulators unread, bit 2 = epilogue reads but does not scan
 };
+constexpr int PROGRESS_STRIDE = 32;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,16 +105,34 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
+// non-blocking probe (try_wait may suspend the thread for a hardware time slice; test_wait never does)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 // Bounded wait: a barrier that does not flip within ~2 s marks the launch as failed and lets every role drain,
 // so a protocol bug can never hang the GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t* abort_flag, uint32_t code) {
-    if (mbar_try_wait(bar, parity)) return true;
-    uint64_t t0 = globaltimer_ns();
+    // fast path: try_wait itself suspends the thread for a hardware time slice, so spin on it alone; the clock and
+    // the abort flag are only consulted every 1024 failed probes (reading %globaltimer is slow)
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (*abort_flag) return false;
-        if (globaltimer_ns() - t0 > 2000000000ull) {
-            *abort_flag = code;
-            return false;
+        if ((++spins & 1023u) == 0u) {
+            if (*abort_flag) return false;
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 2000000000ull) {
+                *abort_flag = code;
+                return false;
+            }
         }
     }
     return true;
@@ -145,6 +177,17 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t smem_dst, const CUten
         "[%0], [%1, {%2, %3}], [%4], %5;"
         ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
         : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -231,9 +274,11 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
     constexpr int KPS = Cfg::kKPS;
     constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1u);
     const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
-    // work items are per cluster: (query-tile group, partition); this CTA takes query tile group*CLUSTER + crank
+    // this cluster: query group `mgroup` (query tile mgroup*CLUSTER + crank in this CTA) of slot `slot`
     const int n_mgroups = (a.n_mtiles + CLUSTER - 1) / CLUSTER;
-    const int first_item = (int)(blockIdx.x / CLUSTER), item_stride = (int)(gridDim.x / CLUSTER);
+    const int cluster_id = (int)(blockIdx.x / CLUSTER);
+    const int mgroup = cluster_id % n_mgroups, slot = cluster_id / n_mgroups;
+    const int n_rounds = slot < a.n_slots ? a.parts_per_slot : 0;
     extern __shared__ __align__(16) unsigned char smem_tc[];
     const uint32_t smem_base = (smem_u32(smem_tc) + 1023u) & ~1023u;
     unsigned char* smem = smem_tc + (smem_base - smem_u32(smem_tc));
@@ -275,7 +320,6 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int n_items = n_mgroups * a.P;
     const int nkb = a.Dp / KBLK;
     const int stages_per_tile = (nkb + KPS - 1) / KPS;
 
@@ -284,16 +328,48 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
         if (lane == 0) {
             uint32_t stage_iter = 0;
             bool ok = true;
-            for (int item = first_item; item < n_items && ok; item += item_stride) {
-                const uint32_t part = item / n_mgroups;
+            // lockstep: only the rank-0 CTA of a cluster throttles; its peer follows through the shared stage ring
+            bool lockstep = a.progress != nullptr && n_mgroups > 1 && crank == 0;
+            uint32_t* prog = a.progress != nullptr ? a.progress + (size_t)slot * PROGRESS_STRIDE : nullptr;
+            uint32_t seq = 0, known_min = 0;
+            const uint32_t window = (uint32_t)a.window;
+            const int pf = a.prefetch_tiles;
+            constexpr int kRowsPer = BN_ / CLUSTER;
+            auto prefetch_tile = [&](uint32_t t) {
+                for (int kb = 0; kb < nkb; ++kb) tma_prefetch_2d(&tmap, kb * KBLK, (int)(t * BN_ + crank * kRowsPer));
+            };
+            for (int r = 0; r < n_rounds && ok; ++r) {
+                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
+                if (part >= (uint32_t)a.P) break;
                 const uint32_t t0 = part * a.tiles_per_part;
                 const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+                if (pf > 0)
+                    for (uint32_t t = t0; t < min(t0 + (uint32_t)pf, t1); ++t) prefetch_tile(t);
                 for (uint32_t t = t0; t < t1 && ok; ++t) {
+                    if (lockstep && seq >= known_min + window) {
+                        const uint64_t w0 = globaltimer_ns();
+                        while (true) {
+                            uint32_t mn = 0xFFFFFFFFu;
+                            for (int m = 0; m < n_mgroups; ++m) mn = min(mn, ld_relaxed_gpu(prog + m));
+                            known_min = mn;
+                            if (seq < known_min + window) break;
+                            if (globaltimer_ns() - w0 > 20000000ull) {  // a peer is not making progress: run free
+                                lockstep = false;
+                                break;
+                            }
+                            __nanosleep(100);
+                        }
+                    }
+                    if (pf > 0 && t + (uint32_t)pf < t1) prefetch_tile(t + (uint32_t)pf);
                     for (int s = 0; s < stages_per_tile; ++s, ++stage_iter) {
                         const int stage = stage_iter % NSTAGES;
                         const uint32_t phase = (stage_iter / NSTAGES) & 1u;
                         if (!mbar_wait(empty_bar(stage), phase ^ 1u, abort_flag, 1)) { ok = false; break; }
                         const int kbc = min(KPS, nkb - s * KPS);
+                        if (a.debug_mode & 1) {
+                            mbar_arrive(full_bar(stage));
+                            continue;
+                        }
                         mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kbc * Cfg::kTileBytes);
                         for (int kb = 0; kb < kbc; ++kb) {
                             if (CLUSTER == 1) {
@@ -301,52 +377,136 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
                                             (s * KPS + kb) * KBLK, (int)(t * BN_), full_bar(stage));
                             } else {
                                 // this CTA fetches rows [crank*BN/CLUSTER, ...) of the K-block for the whole cluster
-                                constexpr int kRowsPer = BN_ / CLUSTER;
                                 tma_load_2d_mcast(smem_base + stage * STAGE_BYTES + kb * Cfg::kTileBytes + crank * (kRowsPer * 128),
                                                   &tmap, (s * KPS + kb) * KBLK, (int)(t * BN_ + crank * kRowsPer),
                                                   full_bar(stage), kMask);
                             }
                         }
                     }
+                    ++seq;
+                    if (prog != nullptr && crank == 0 && n_mgroups > 1) st_relaxed_gpu(prog + mgroup, seq);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp walks the loops; one elected lane issues) =====================
+        // tcgen05.mma issue is paced by execution (about one MMA of queue slack), so every cycle spent between two
+        // MMAs on anything else is a tensor-pipe bubble.  The barrier of the NEXT stage (and the accumulator buffer
+        // of the next tile) is therefore probed in the shadow of the current stage's MMAs, and the blocking wait is
+        // only taken when that probe failed.  The loops stay warp-uniform so the descriptors live in uniform registers.
         const bool leader = elect_one();
         uint32_t stage_iter = 0, tile_iter = 0, item_iter = 0;
         bool ok = true;
-        for (int item = first_item; item < n_items && ok; item += item_stride, ++item_iter) {
-            const uint32_t part = item / n_mgroups;
+        uint32_t full_ready = 0;    // full barrier of stage_iter already observed complete
+        uint32_t tempty_ready = 0;  // accumulator buffer of tile_iter already observed free
+        bool n_rounds_done = false;
+        // Fast path (Dp == 768 with 64-row tiles): a tile is exactly 3 stages, so the 6-stage ring holds two tiles and
+        // tile parity fixes the stage numbers, the accumulator buffer and every barrier / descriptor address at
+        // compile time; only the phase bits are computed at run time.
+        if (BN_ == 64 && NBUF == 2 && KPS == 4 && nkb == 12 && !(a.debug_mode & 8)) {
+            const uint64_t desc_base = make_b_desc(smem_base);
+            auto tile_body = [&](auto bc, uint32_t ph) -> bool {
+                constexpr int b = decltype(bc)::value;
+                if (!tempty_ready && !mbar_wait(tempty_bar(b), ph ^ 1u, abort_flag, 3)) return false;
+                tempty_ready = 0;
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + Cfg::kDCol + b * BN_;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int stage = b * 3 + s;
+                    if (!full_ready && !mbar_wait(full_bar(stage), ph, abort_flag, 4)) return false;
+                    if (leader) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma_ts_bf16(d_tmem, tmem_base + (uint32_t)((s * 16 + k4) * 8),
+                                         desc_base + (uint64_t)((stage * STAGE_BYTES) >> 4) + (uint64_t)(k4 * 2), Cfg::kIdesc,
+                                         (k4 == 0 && s == 0) ? 0u : 1u);
+                    }
+                    if (s < 2) {
+                        full_ready = mbar_try_wait(full_bar(stage + 1), ph);
+                    } else {
+                        full_ready = mbar_try_wait(full_bar((1 - b) * 3), b == 0 ? ph : (ph ^ 1u));
+                        tempty_ready = mbar_try_wait(tempty_bar(1 - b), b == 0 ? (ph ^ 1u) : ph);
+                    }
+                    if (leader) {
+#pragma unroll
+                        for (int kb = 1; kb < 4; ++kb)
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma_ts_bf16(d_tmem, tmem_base + (uint32_t)((s * 16 + kb * 4 + k4) * 8),
+                                             desc_base + (uint64_t)((stage * STAGE_BYTES + kb * Cfg::kTileBytes) >> 4) + (uint64_t)(k4 * 2),
+                                             Cfg::kIdesc, 1u);
+                        if (CLUSTER == 1) umma_commit(empty_bar(stage));
+                        else umma_commit_mcast(empty_bar(stage), kMask);
+                    }
+                    __syncwarp();
+                }
+                if (leader) umma_commit(tfull_bar(b));
+                __syncwarp();
+                return true;
+            };
+            for (int r = 0; r < n_rounds && ok; ++r, ++item_iter) {
+                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
+                if (part >= (uint32_t)a.P) break;
+                const uint32_t t0 = part * a.tiles_per_part;
+                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+                if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
+                tcgen05_fence_after();
+                for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
+                    const uint32_t ph = (tile_iter >> 1) & 1u;
+                    if ((tile_iter & 1u) == 0u) ok = tile_body(std::integral_constant<int, 0>{}, ph);
+                    else ok = tile_body(std::integral_constant<int, 1>{}, ph);
+                }
+            }
+            n_rounds_done = true;
+        }
+        for (int r = 0; r < n_rounds && ok && !n_rounds_done; ++r, ++item_iter) {
+            const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
+            if (part >= (uint32_t)a.P) break;
             const uint32_t t0 = part * a.tiles_per_part;
             const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
             if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
             tcgen05_fence_after();
             for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter % NBUF;
-                if (!mbar_wait(tempty_bar(buf), ((tile_iter / NBUF) & 1u) ^ 1u, abort_flag, 3)) { ok = false; break; }
+                if (!tempty_ready && !mbar_wait(tempty_bar(buf), ((tile_iter / NBUF) & 1u) ^ 1u, abort_flag, 3)) { ok = false; break; }
+                tempty_ready = 0;
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + Cfg::kDCol + buf * BN_;
                 for (int s = 0; s < stages_per_tile; ++s, ++stage_iter) {
                     const int stage = stage_iter % NSTAGES;
                     const uint32_t phase = (stage_iter / NSTAGES) & 1u;
-                    if (!mbar_wait(full_bar(stage), phase, abort_flag, 4)) { ok = false; break; }
-                    tcgen05_fence_after();
+                    if (!full_ready && !mbar_wait(full_bar(stage), phase, abort_flag, 4)) { ok = false; break; }
+                    const int kbc = min(KPS, nkb - s * KPS);
+                    // descriptors of one stage differ only in the start-address field: +2 per K=16 step inside a
+                    // 128-byte swizzle row, + kTileBytes/16 per K block
+                    const uint64_t bdesc0 = make_b_desc(smem_base + stage * STAGE_BYTES);
+                    const uint32_t a0 = tmem_base + (uint32_t)(s * KPS * (KBLK / 16) * 8);
                     if (leader) {
-                        const int kbc = min(KPS, nkb - s * KPS);
-                        // descriptors of one stage differ only in the start-address field: +2 per K=16 step inside a
-                        // 128-byte swizzle row, + kTileBytes/16 per K block
-                        const uint64_t bdesc0 = make_b_desc(smem_base + stage * STAGE_BYTES);
-                        const uint32_t a0 = tmem_base + (uint32_t)(s * KPS * (KBLK / 16) * 8);
 #pragma unroll
-                        for (int kb = 0; kb < KPS; ++kb) {
+                        for (int k4 = 0; k4 < KBLK / 16; ++k4)
+                            umma_ts_bf16(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), Cfg::kIdesc,
+                                         (k4 == 0) ? (s > 0 ? 1u : 0u) : 1u);
+                    }
+                    // probe what the next iteration will need while the pipe is busy
+                    {
+                        const uint32_t nsi = stage_iter + 1;
+                        full_ready = mbar_try_wait(full_bar(nsi % NSTAGES), (nsi / NSTAGES) & 1u);
+                        if (s == stages_per_tile - 1) {
+                            const uint32_t nti = tile_iter + 1;
+                            tempty_ready = mbar_try_wait(tempty_bar(nti % NBUF), ((nti / NBUF) & 1u) ^ 1u);
+                        }
+                    }
+                    if (leader) {
+#pragma unroll
+                        for (int kb = 1; kb < KPS; ++kb) {
                             if (kb < kbc) {
 #pragma unroll
-                                for (int k4 = 0; k4 < KBLK / 16; ++k4) {
-                                    const uint32_t acc = (kb == 0 && k4 == 0) ? (s > 0 ? 1u : 0u) : 1u;
+                                for (int k4 = 0; k4 < KBLK / 16; ++k4)
                                     umma_ts_bf16(d_tmem, a0 + (uint32_t)((kb * (KBLK / 16) + k4) * 8),
-                                                 bdesc0 + (uint64_t)(kb * (Cfg::kTileBytes >> 4) + k4 * 2), Cfg::kIdesc, acc);
-                                }
+                                                 bdesc0 + (uint64_t)(kb * (Cfg::kTileBytes >> 4) + k4 * 2), Cfg::kIdesc, 1u);
                             }
                         }
                         // frees the stage (in every CTA that multicast into it) when these MMAs have read it
@@ -366,8 +526,9 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t tile_iter = 0;
         bool ok = true;
-        for (int item = first_item; item < n_items && ok; item += item_stride) {
-            const uint32_t part = item / n_mgroups, mt = (item % n_mgroups) * CLUSTER + crank;
+        for (int r = 0; r < n_rounds && ok; ++r) {
+            const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots, mt = (uint32_t)mgroup * CLUSTER + crank;
+            if (part >= (uint32_t)a.P) break;
             const uint32_t t0 = part * a.tiles_per_part;
             const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
             const uint32_t gq = mt * BM + ql;
@@ -396,15 +557,25 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
             float thr_g = -INFINITY, thr_pub = -INFINITY;
             int min_pos = 0;
             uint32_t* gthr = a.gthr + (q_valid ? gq : 0);
+            uint32_t g_bits = 0u;
             tcgen05_fence_before();
             mbar_arrive(aready_bar);
             const uint32_t row_end = a.n_rows;
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter % NBUF;
-                const uint32_t g_bits = a.share_floor ? *reinterpret_cast<volatile uint32_t*>(gthr) : 0u;  // used after the wait
+                // refresh the shared floor every 8th tile; the load issued now is consumed 8 tiles later, so its
+                // (loaded) L2 latency never sits on the per-tile critical path
+                if (a.share_floor && (tile_iter & 7u) == 0u) {
+                    if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
+                    g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
+                }
                 if (!mbar_wait(tfull_bar(buf), (tile_iter / NBUF) & 1u, abort_flag, 5)) { ok = false; break; }
                 tcgen05_fence_after();
-                if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
+                if (a.debug_mode & 2) {
+                    tcgen05_fence_before();
+                    mbar_arrive(tempty_bar(buf));
+                    continue;
+                }
 #pragma unroll
                 for (int h = 0; h < BN_ / 64; ++h) {
                     uint32_t v[64];
@@ -422,6 +593,7 @@ coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
                         for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
                     }
                     float thr = fmaxf(thr_l, thr_g);
+                    if (a.debug_mode & 4) thr = INFINITY;
                     bool any = false;
 #pragma unroll
                     for (int i = 0; i < 64; ++i) any |= (__uint_as_float(v[i]) > thr);
@@ -671,15 +843,17 @@ __device__ __forceinline__ void umma_ss_bf16(uint32_t d_tmem, uint64_t a_desc, u
 }
 
 template <int N, int NACC, bool TS>
-__global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters16, unsigned long long* cycles_out) {
+__global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters16, int commit_every16, unsigned long long* cycles_out) {
     extern __shared__ __align__(16) unsigned char smem_probe[];
     const uint32_t smem_base = (smem_u32(smem_probe) + 1023u) & ~1023u;
     unsigned char* smem = smem_probe + (smem_base - smem_u32(smem_probe));
     const uint32_t bar = smem_base + 49152;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 49152 + 16);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 49152 + 32);
     for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    const uint32_t bar2 = bar + 8;  // receives the intermediate commits; nobody waits on it
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar2, 1);
         fence_barrier_init();
     }
     const int warp = threadIdx.x >> 5;
@@ -711,6 +885,7 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters16, unsigned l
                     else
                         umma_ss_bf16(d, a_desc + (uint64_t)((j & 3) * 2), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
                 }
+                if (commit_every16 > 0 && (it + 1) % commit_every16 == 0) umma_commit(bar2);
             }
             umma_commit(bar);
             t1 = clock64();

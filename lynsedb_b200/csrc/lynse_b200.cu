@@ -19,6 +19,7 @@
 #include "lb_metrics.cuh"
 #include "lb_scan.cuh"
 #include "lb_tc.cuh"
+#include "lb_tc2.cuh"
 
 namespace lb {
 
@@ -81,15 +82,6 @@ static int next_pow2(int x) {
     while (p < x) p <<= 1;
     return p;
 }
-static uint64_t gcd_u64(uint64_t a, uint64_t b) {
-    while (b) {
-        uint64_t t = a % b;
-        a = b;
-        b = t;
-    }
-    return a;
-}
-
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -139,7 +131,7 @@ struct lb_index {
     lb_search_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf w_send, w_recv, w_g_rows, w_g_dists, w_g_counts;
+    DevBuf w_send, w_recv, w_g_rows, w_g_dists, w_g_counts, w_progress, w_prof;
 };
 
 namespace lb {
@@ -250,6 +242,10 @@ static int tc_tile_variant(int Dp) {
     return Dp <= tc::TileCfg<128, 2>::kMaxDp ? 2 : 0;
 }
 static int tc_variant_bn(int v) { return v == 0 ? 64 : 128; }
+static int tc_env_int(const char* name, int dflt) {
+    const char* env = getenv(name);
+    return env && *env ? atoi(env) : dflt;
+}
 // CTAs per cluster sharing corpus tiles by TMA multicast: 2 when there are at least two query tiles.
 static int tc_cluster_size(int n_mtiles) {
     const char* env = getenv("LYNSE_B200_TC_CLUSTER");
@@ -428,14 +424,23 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
 static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uint32_t* d_rows, float* d_dists,
                   uint32_t* d_counts, float* dump) {
     const int kind = shadow_kind_for(metric);
-    const int variant = tc_tile_variant(shadow_dp(idx, kind));
+    const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
+    int cluster = tc_cluster_size(n_mtiles);
+    // two or more query tiles: CTA pairs (tcgen05 cta_group::2, lb_tc2.cuh); LYNSE_B200_TC_PAIR=0 keeps the one-CTA kernel
+    const bool pair = cluster == 2 && tc_env_int("LYNSE_B200_TC_PAIR", 1) != 0;
+    if (pair) {
+        // clusters of 2 / 4 / 8 CTAs: a shadow tile is read from L2 once per cluster and multicast to its pairs
+        int cl = n_mtiles > 4 ? 8 : (n_mtiles > 2 ? 4 : 2);
+        const int env_cl = tc_env_int("LYNSE_B200_TC_CL", 0);
+        if (env_cl == 2 || env_cl == 4 || env_cl == 8) cl = env_cl;
+        cluster = cl;
+    }
+    const int variant = pair ? 0 : tc_tile_variant(shadow_dp(idx, kind));
     const int BN = tc_variant_bn(variant);
     LB_TRY(ensure_shadow(idx, kind, BN));
     LB_TRY(refresh_small_segments(idx));
     Shadow& sh = idx->shadow[kind];
     const int Dp = sh.Dp;
-    const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
-    const int cluster = tc_cluster_size(n_mtiles);
     const int n_mgroups = (n_mtiles + cluster - 1) / cluster;
     const int nq_pad = n_mgroups * cluster * tc::BM;
     LB_TRY(ensure_shadow(idx, kind, BN / cluster));  // tensor-map box = the rows one CTA fetches per K-block
@@ -448,19 +453,48 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
         LB_CUDA_TRY(cudaGetLastError());
     }
     const uint32_t tiles_total = (uint32_t)ceil_div(idx->n, BN);
-    const uint64_t G = (uint64_t)(idx->sm_count / cluster);  // clusters resident at once
-    uint64_t P = (G / gcd_u64((uint64_t)n_mgroups, G));  // smallest P with n_mgroups*P a multiple of the resident clusters
-    while (P * 2 * tc::KP <= 2048 && P * (uint64_t)n_mgroups < 2 * G) P *= 2;  // at least two items per cluster when cheap
-    // The union of the per-partition shortlists must reach well below rank k: aim at P*KP >= 32*k candidates.
-    {
-        const uint64_t base = P, want = ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
-        while (P < want && P + base <= 4096 / tc::KP) P += base;
+    // Slots: groups of n_mgroups co-resident clusters (one per query group) that stream the same row partitions in
+    // lockstep, so every shadow tile comes from HBM once and is served to the other query groups of the slot from L2.
+    uint64_t G = (uint64_t)(idx->sm_count / cluster);  // clusters resident at once (one CTA per SM)
+    if (pair && cluster > 2) {
+        // clusters of 4 / 8 must fit inside a GPC: ask the driver how many can be co-resident
+        cudaLaunchConfig_t qcfg{};
+        qcfg.gridDim = dim3((unsigned)(idx->sm_count / cluster * cluster));
+        qcfg.blockDim = dim3(tc::NUM_THREADS);
+        qcfg.dynamicSmemBytes = tc::P_SMEM_BYTES;
+        cudaLaunchAttribute qattr[1];
+        qattr[0].id = cudaLaunchAttributeClusterDimension;
+        qattr[0].val.clusterDim.x = (unsigned)cluster;
+        qattr[0].val.clusterDim.y = 1;
+        qattr[0].val.clusterDim.z = 1;
+        qcfg.attrs = qattr;
+        qcfg.numAttrs = 1;
+        int n_active = 0;
+        cudaError_t qe;
+        if (cluster == 8) {
+            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::P_SMEM_BYTES));
+            qe = cudaOccupancyMaxActiveClusters(&n_active, tc::coarse_pair_kernel<0, 8>, &qcfg);
+        } else {
+            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::P_SMEM_BYTES));
+            qe = cudaOccupancyMaxActiveClusters(&n_active, tc::coarse_pair_kernel<0, 4>, &qcfg);
+        }
+        if (qe != cudaSuccess || n_active < 1) return fail(LB_CUDA, std::string("cudaOccupancyMaxActiveClusters: ") + cudaGetErrorString(qe));
+        G = (uint64_t)n_active;
+        idx->stats.n_fallback = 0;
     }
-    P = std::min<uint64_t>(P, 4096 / tc::KP);
-    P = std::min<uint64_t>(P, tiles_total);
+    uint64_t n_slots = std::max<uint64_t>(1, G / (uint64_t)n_mgroups);
+    n_slots = std::min<uint64_t>(n_slots, tiles_total);
+    n_slots = std::min<uint64_t>(n_slots, 4096 / tc::KP);
+    // The union of the per-partition shortlists must reach well below rank k: aim at P*KP >= 32*k candidates.
+    uint64_t parts_per_slot = 1;
+    {
+        const uint64_t want = ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
+        while (n_slots * parts_per_slot < want && n_slots * (parts_per_slot + 1) <= 4096 / tc::KP) ++parts_per_slot;
+    }
+    uint64_t P = std::min<uint64_t>(n_slots * parts_per_slot, tiles_total);
     const uint32_t tiles_per_part = (uint32_t)ceil_div(tiles_total, P);
     P = ceil_div(tiles_total, tiles_per_part);
-    const int n_items = n_mgroups * (int)P;
+    parts_per_slot = ceil_div(P, n_slots);
     LB_TRY(idx->w_cand_score.ensure((size_t)nq * P * tc::KP * 4));
     LB_TRY(idx->w_cand_row.ensure((size_t)nq * P * tc::KP * 4));
     LB_TRY(idx->w_cand_thr.ensure((size_t)nq * P * 4));
@@ -487,7 +521,25 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     a.share_floor = (k <= tc::KP - 4) ? 1 : 0;
     a.error_flag = flags;
     a.dump = dump;
-    const int grid = std::min<int>(idx->sm_count / cluster, n_items) * cluster;
+    a.n_slots = (int)n_slots;
+    a.parts_per_slot = (int)parts_per_slot;
+    a.window = tc_env_int("LYNSE_B200_TC_WINDOW", 16);
+    a.prefetch_tiles = tc_env_int("LYNSE_B200_TC_PREFETCH", 0);
+    a.debug_mode = tc_env_int("LYNSE_B200_TC_DEBUG", 0);
+    a.prof = nullptr;
+    const bool want_prof = getenv("LYNSE_B200_TC_PROF") != nullptr;
+    if (want_prof) {
+        LB_TRY(idx->w_prof.ensure((size_t)idx->sm_count * 8 * 8));
+        LB_CUDA_TRY(cudaMemsetAsync(idx->w_prof.p, 0, (size_t)idx->sm_count * 8 * 8, idx->stream));
+        a.prof = idx->w_prof.as<unsigned long long>();
+    }
+    a.progress = nullptr;
+    if (n_mgroups > 1 && a.window > 0) {
+        LB_TRY(idx->w_progress.ensure((size_t)n_slots * tc::PROGRESS_STRIDE * 4));
+        LB_CUDA_TRY(cudaMemsetAsync(idx->w_progress.p, 0, (size_t)n_slots * tc::PROGRESS_STRIDE * 4, idx->stream));
+        a.progress = idx->w_progress.as<uint32_t>();
+    }
+    const int grid = (int)n_slots * n_mgroups * cluster;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(tc::NUM_THREADS);
@@ -507,7 +559,24 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
         if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);                                                         \
         LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_topk_kernel<BNV, NB, CL>, sh.tmap, a));                            \
     } while (0)
-    if (cluster == 1) {
+#define LB_LAUNCH_PAIR(NKB, CLV)                                                                                          \
+    do {                                                                                                           \
+        cfg.dynamicSmemBytes = tc::P_SMEM_BYTES;                                                                   \
+        LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<NKB, CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)tc::P_SMEM_BYTES));                                                  \
+        if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);                                                 \
+        LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<NKB, CLV>, sh.tmap, a));                            \
+    } while (0)
+    if (pair) {
+        if (cluster == 8) {
+            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<0, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            LB_LAUNCH_PAIR(0, 8);
+        } else if (cluster == 4) {
+            LB_LAUNCH_PAIR(0, 4);
+        } else {
+            LB_LAUNCH_PAIR(0, 2);
+        }
+    } else if (cluster == 1) {
         if (variant == 0) LB_LAUNCH_TC(64, 2, 1);
         else if (variant == 1) LB_LAUNCH_TC(128, 1, 1);
         else LB_LAUNCH_TC(128, 2, 1);
@@ -517,6 +586,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
         else LB_LAUNCH_TC(128, 2, 2);
     }
 #undef LB_LAUNCH_TC
+#undef LB_LAUNCH_PAIR
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
 
@@ -558,14 +628,40 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     idx->stats.algorithmic_bytes = (uint64_t)idx->n * Dp * 2;
     idx->stats.algorithmic_flops = 2ull * (uint64_t)nq * idx->n * idx->dim;
 
-    uint32_t head[2] = {0, 0};
-    LB_CUDA_TRY(cudaMemcpyAsync(head, flags, 8, cudaMemcpyDeviceToHost, idx->stream));
+    uint32_t head[4] = {0, 0, 0, 0};
+    LB_CUDA_TRY(cudaMemcpyAsync(head, flags, 16, cudaMemcpyDeviceToHost, idx->stream));
     LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
     if (idx->timing) {
         float ms = 0;
         cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);
         idx->stats.ms_dominant = ms;
     }
+    if (want_prof) {
+        std::vector<unsigned long long> pr((size_t)idx->sm_count * 8);
+        LB_CUDA_TRY(cudaMemcpy(pr.data(), idx->w_prof.p, pr.size() * 8, cudaMemcpyDeviceToHost));
+        double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int n_lead = 0, n_cta = 0;
+        for (int b = 0; b < grid && b < idx->sm_count; ++b) {
+            if (pr[(size_t)b * 8] > 0) {
+                ++n_lead;
+                for (int i = 0; i < 6; ++i) sum[i] += (double)pr[(size_t)b * 8 + i];
+            }
+            if (pr[(size_t)b * 8 + 6] + pr[(size_t)b * 8 + 7] > 0) {
+                ++n_cta;
+                sum[6] += (double)pr[(size_t)b * 8 + 6];
+                sum[7] += (double)pr[(size_t)b * 8 + 7];
+            }
+        }
+        if (n_lead > 0 && n_cta > 0 && sum[5] > 0)
+            fprintf(stderr,
+                    "[lynse_b200] per tile (cycles): mma loop %.0f, wait tempty %.0f (%.2f waits/tile), wait full %.0f (%.2f waits/tile); "
+                    "epilogue wait tfull %.0f, read+release %.0f\n",
+                    sum[0] / sum[5], sum[1] / sum[5], sum[3] / sum[5], sum[2] / sum[5], sum[4] / sum[5],
+                    sum[6] / n_cta / (sum[5] / n_lead), sum[7] / n_cta / (sum[5] / n_lead));
+    }
+    if (getenv("LYNSE_B200_TC_TRACE") && head[3] > 0)
+        fprintf(stderr, "[lynse_b200] coarse kernel: %.3f ms, %.0f SM MHz, grid %d, cluster %d, slots %d, P %d\n", head[3] * 1e-6,
+                (double)head[2] * 16.0 / (double)head[3] * 1e3, grid, cluster, (int)n_slots, (int)P);
     if (head[0] != 0)
         return fail(LB_INTERNAL, "tensor-core coarse kernel: barrier wait timed out (code " + std::to_string(head[0]) + ")");
     idx->stats.n_fallback = head[1];
@@ -816,7 +912,7 @@ void lb_index_destroy(lb_index* idx) {
                           &idx->w_out_dists, &idx->w_out_counts, &idx->w_qb, &idx->w_qnorm, &idx->w_cand_score,
                           &idx->w_cand_row, &idx->w_cand_thr, &idx->w_flags, &idx->w_qstats, &idx->w_nq, &idx->w_sub_q,
                           &idx->w_qmap, &idx->shadow[0].buf, &idx->shadow[1].buf, &idx->shadow[2].buf,
-                          &idx->w_send, &idx->w_recv, &idx->w_g_rows, &idx->w_g_dists, &idx->w_g_counts};
+                          &idx->w_send, &idx->w_recv, &idx->w_g_rows, &idx->w_g_dists, &idx->w_g_counts, &idx->w_progress, &idx->w_prof};
         for (DevBuf* b : bufs) b->release();
         for (int i = 0; i < 4; ++i)
             if (idx->ev[i]) cudaEventDestroy(idx->ev[i]);
@@ -1481,7 +1577,7 @@ int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int grid, uint
         found = true;                                                                                                \
         e = cudaFuncSetAttribute(tc::mma_rate_kernel<NN, NA, TSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e == cudaSuccess) {                                                                                      \
-            tc::mma_rate_kernel<NN, NA, TSV><<<grid, 64, smem>>>(iters / 16, d);                                     \
+            tc::mma_rate_kernel<NN, NA, TSV><<<grid, 64, smem>>>(iters / 16, tc_env_int("LYNSE_B200_PROBE_COMMIT", 0), d);                                     \
             e = cudaDeviceSynchronize();                                                                             \
         }                                                                                                            \
     }
