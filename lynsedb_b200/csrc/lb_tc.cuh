@@ -11,18 +11,20 @@
 // enter the top-k (see finalize_kernel); otherwise the query is re-run by the
 // exact scan of lb_scan.cuh.
 //
-// Kernel shape (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer: 64-row x 64-col bf16 boxes of the shadow, SWIZZLE_128B,
-//               6 stages x 32 KiB in shared memory, mbarrier full/empty ring
-//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (queries), N=64 (rows), K=16;
-//               A (the 128 queries of this work item, bf16) lives in TMEM columns [0, Dp/2),
-//               B comes from the shared-memory stages, D is double-buffered in TMEM columns [384,512)
-//   warps 2..5  epilogue: lane == query.  tcgen05.ld the 64 scores of the tile, compare with the
-//               thread's running threshold held in a register, insert the rare survivors in a
-//               private 16-entry list in shared memory
-// Work item = (query tile of 128, row partition); items of the same partition run on
-// neighbouring CTAs at the same time so each shadow tile is fetched from HBM once and
-// served to the other query tiles from L2.
+// Shadow layout in HBM (a derived structure, so it is stored the way the tensor core wants to read it): rows are
+// grouped in tiles of 64, a tile is cut in K blocks of 64 bf16, and every (tile, K block) is two 4 KiB half blocks
+// of 32 rows x 128 B whose 16-byte chunks are already permuted with the 128-byte shared-memory swizzle
+// (chunk c of row r sits at chunk c ^ (r & 7)).  A pipeline stage is therefore ONE contiguous TMA box
+// (SWIZZLE_NONE) instead of 4 boxes of 32-64 strided rows, DRAM pages are read front to back, and the bytes
+// land in shared memory exactly as a SWIZZLE_128B K-major UMMA descriptor expects them.
+//   byte offset of element (row, d):  (((row/64) * NKB + d/64) * 2 + (row%64)/32) * 4096
+//                                     + (row%32) * 128 + ((((d%64)/8) ^ (row & 7)) << 4) + (d%8) * 2
+//
+// Kernels: lb_tc1.cuh (one CTA per 128 queries; used when a batch has a single query tile) and lb_tc2.cuh
+// (CTA pairs, tcgen05 cta_group::2, for two or more query tiles).  Both keep the A operand (the 128 queries
+// of the CTA, bf16) in TMEM columns [0, Dp/2), stream 64-row corpus tiles through a shared-memory ring, double
+// buffer the f32 accumulators in TMEM columns [384, 512), and run a lane == query epilogue that keeps a private
+// KP-entry shortlist per (query, row partition).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -36,16 +38,17 @@ namespace lb {
 namespace tc {
 
 constexpr int BM = 128;           // queries per work item == TMEM lanes
-constexpr int BN = 64;            // default corpus rows per accumulator tile (see TileCfg)
+constexpr int BN = 64;            // corpus rows per accumulator tile
 constexpr int KBLK = 64;          // bf16 elements per 128-byte swizzle row
-constexpr int NSTAGES = 6;
 constexpr int KP = 16;            // shortlist entries kept per (partition, query)
 constexpr int MAX_DP = 768;       // padded dim limit: A occupies Dp/2 <= 384 TMEM columns
-constexpr int STAGE_BYTES = 32768;  // one pipeline stage of corpus K-blocks
+constexpr int HALF_BLOCK_BYTES = 4096;  // 32 rows x one K block, swizzled
+constexpr int KPS = 4;                  // K blocks per pipeline stage
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr uint32_t SMEM_LIST_OFF = NSTAGES * STAGE_BYTES;             // 196608
-constexpr uint32_t SMEM_BAR_OFF = SMEM_LIST_OFF + 2 * KP * BM * 4;    // + 16384
+constexpr int DCOL = TMEM_COLS - 2 * BN;  // accumulators: two buffers of BN columns at [384, 512)
+constexpr uint32_t SMEM_RING_BYTES = 196608;                          // staging ring of either kernel
+constexpr uint32_t SMEM_BAR_OFF = SMEM_RING_BYTES;
 constexpr uint32_t SMEM_BYTES = SMEM_BAR_OFF + 256 + 1024;            // + barriers + alignment slack
 
 struct TcArgs {
@@ -53,6 +56,7 @@ struct TcArgs {
     int nq;
     int n_mtiles;             // query tiles of 128; qb is padded to a multiple of the cluster size tiles
     int Dp;                   // padded dim, multiple of 64, <= MAX_DP
+    int rem_kb;               // (Dp / 64) % KPS: K blocks of the last, partial stage of a tile (0 = none; uses tmap_rem)
     uint32_t n_rows;
     uint32_t tiles_total;     // ceil(n_rows / 64)
     uint32_t tiles_per_part;
@@ -72,6 +76,8 @@ struct TcArgs {
     uint32_t* progress;       // [n_slots][PROGRESS_STRIDE] tiles issued per (slot, query group); zeroed per launch; null = free-running
     int window;               // a query group never runs more than `window` tiles ahead of the slowest group of its slot
     int prefetch_tiles;       // L2 prefetch distance of the TMA producer, in tiles (0 = off)
+    int sample_tiles;         // > 0: every CTA first scans tiles [0, sample_tiles) only to warm up its shortlist floors
+                              // (round -1, nothing recorded), so the real partitions never start with an open gate
     unsigned long long* prof; // optional [grid][8] cycle counters of the MMA issuer / epilogue (diagnostics)
     int debug_mode;           // diagnostics only (results are garbage): bit 0 = producer skips the TMA loads,
                               // bit 1 = epilogue releases accumulators unread, bit 2 = epilogue reads but does not scan
@@ -178,6 +184,13 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t smem_dst, const CUten
         ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
         : "memory");
 }
+// 4-D box of the tiled shadow: coordinates (0, 0, half, K block index)
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tmap, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_dst), "l"(tmap), "r"(0), "r"(0), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
 }
@@ -238,7 +251,7 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 
-// ---- the coarse kernel -----------------------------------------------------------------------------------------
+// ---- pieces shared by the two coarse kernels ------------------------------------------------------------------
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -248,406 +261,185 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-
-// Tile shape: BN_ corpus rows per accumulator, NBUF accumulators in TMEM columns [512 - NBUF*BN_, 512);
-// the A operand (queries) needs Dp/2 <= 512 - NBUF*BN_ columns.  Stages are always 32 KiB:
-// KPS = 32768 / (BN_*128) K-blocks of [BN_ rows x 64 bf16] each.
-template <int BN_, int NBUF>
-struct TileCfg {
-    static constexpr int kBN = BN_;
-    static constexpr int kNBuf = NBUF;
-    static constexpr int kDCol = TMEM_COLS - NBUF * BN_;
-    static constexpr int kMaxDp = 2 * kDCol;
-    static constexpr int kTileBytes = BN_ * KBLK * 2;
-    static constexpr int kKPS = STAGE_BYTES / kTileBytes;
-    static constexpr uint32_t kIdesc =
-        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-};
-
-// CLUSTER = 2: two CTAs of a cluster work on the same row partition for two neighbouring query tiles; each loads
-// half of every corpus K-block and multicasts it into both CTAs' shared memory, so every shadow byte crosses
-// the L2 -> SM fabric once per CTA pair instead of once per CTA.
-template <int BN_, int NBUF, int CLUSTER>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-coarse_topk_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
-    using Cfg = TileCfg<BN_, NBUF>;
-    constexpr int KPS = Cfg::kKPS;
-    constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1u);
-    const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
-    // this cluster: query group `mgroup` (query tile mgroup*CLUSTER + crank in this CTA) of slot `slot`
-    const int n_mgroups = (a.n_mtiles + CLUSTER - 1) / CLUSTER;
-    const int cluster_id = (int)(blockIdx.x / CLUSTER);
-    const int mgroup = cluster_id % n_mgroups, slot = cluster_id / n_mgroups;
-    const int n_rounds = slot < a.n_slots ? a.parts_per_slot : 0;
-    extern __shared__ __align__(16) unsigned char smem_tc[];
-    const uint32_t smem_base = (smem_u32(smem_tc) + 1023u) & ~1023u;
-    unsigned char* smem = smem_tc + (smem_base - smem_u32(smem_tc));
-    float* l_score = reinterpret_cast<float*>(smem + SMEM_LIST_OFF);                     // [KP][BM]
-    uint32_t* l_row = reinterpret_cast<uint32_t*>(smem + SMEM_LIST_OFF + KP * BM * 4);   // [KP][BM]
-    const uint32_t bar_base = smem_base + SMEM_BAR_OFF;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
-    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * NSTAGES + b); };
-    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * NSTAGES + 2 + b); };
-    const uint32_t aready_bar = bar_base + 8u * (2 * NSTAGES + 4);
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * NSTAGES + 5));
-    volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * NSTAGES + 5) + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), CLUSTER);  // every CTA of the cluster must have drained the stage
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 128);
-        }
-        mbar_init(aready_bar, 128);
-        *abort_flag = 0;
-        fence_barrier_init();
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    }
-    if (warp == 0) {
-        __syncwarp();
-        tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
-        tmem_relinquish();
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (CLUSTER > 1) cluster_sync_all();  // peers' barriers are initialised before anything remote can arrive
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-
-    const int nkb = a.Dp / KBLK;
-    const int stages_per_tile = (nkb + KPS - 1) / KPS;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t stage_iter = 0;
-            bool ok = true;
-            // lockstep: only the rank-0 CTA of a cluster throttles; its peer follows through the shared stage ring
-            bool lockstep = a.progress != nullptr && n_mgroups > 1 && crank == 0;
-            uint32_t* prog = a.progress != nullptr ? a.progress + (size_t)slot * PROGRESS_STRIDE : nullptr;
-            uint32_t seq = 0, known_min = 0;
-            const uint32_t window = (uint32_t)a.window;
-            const int pf = a.prefetch_tiles;
-            constexpr int kRowsPer = BN_ / CLUSTER;
-            auto prefetch_tile = [&](uint32_t t) {
-                for (int kb = 0; kb < nkb; ++kb) tma_prefetch_2d(&tmap, kb * KBLK, (int)(t * BN_ + crank * kRowsPer));
-            };
-            for (int r = 0; r < n_rounds && ok; ++r) {
-                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
-                if (part >= (uint32_t)a.P) break;
-                const uint32_t t0 = part * a.tiles_per_part;
-                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
-                if (pf > 0)
-                    for (uint32_t t = t0; t < min(t0 + (uint32_t)pf, t1); ++t) prefetch_tile(t);
-                for (uint32_t t = t0; t < t1 && ok; ++t) {
-                    if (lockstep && seq >= known_min + window) {
-                        const uint64_t w0 = globaltimer_ns();
-                        while (true) {
-                            uint32_t mn = 0xFFFFFFFFu;
-                            for (int m = 0; m < n_mgroups; ++m) mn = min(mn, ld_relaxed_gpu(prog + m));
-                            known_min = mn;
-                            if (seq < known_min + window) break;
-                            if (globaltimer_ns() - w0 > 20000000ull) {  // a peer is not making progress: run free
-                                lockstep = false;
-                                break;
-                            }
-                            __nanosleep(100);
-                        }
-                    }
-                    if (pf > 0 && t + (uint32_t)pf < t1) prefetch_tile(t + (uint32_t)pf);
-                    for (int s = 0; s < stages_per_tile; ++s, ++stage_iter) {
-                        const int stage = stage_iter % NSTAGES;
-                        const uint32_t phase = (stage_iter / NSTAGES) & 1u;
-                        if (!mbar_wait(empty_bar(stage), phase ^ 1u, abort_flag, 1)) { ok = false; break; }
-                        const int kbc = min(KPS, nkb - s * KPS);
-                        if (a.debug_mode & 1) {
-                            mbar_arrive(full_bar(stage));
-                            continue;
-                        }
-                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kbc * Cfg::kTileBytes);
-                        for (int kb = 0; kb < kbc; ++kb) {
-                            if (CLUSTER == 1) {
-                                tma_load_2d(smem_base + stage * STAGE_BYTES + kb * Cfg::kTileBytes, &tmap,
-                                            (s * KPS + kb) * KBLK, (int)(t * BN_), full_bar(stage));
-                            } else {
-                                // this CTA fetches rows [crank*BN/CLUSTER, ...) of the K-block for the whole cluster
-                                tma_load_2d_mcast(smem_base + stage * STAGE_BYTES + kb * Cfg::kTileBytes + crank * (kRowsPer * 128),
-                                                  &tmap, (s * KPS + kb) * KBLK, (int)(t * BN_ + crank * kRowsPer),
-                                                  full_bar(stage), kMask);
-                            }
-                        }
-                    }
-                    ++seq;
-                    if (prog != nullptr && crank == 0 && n_mgroups > 1) st_relaxed_gpu(prog + mgroup, seq);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp walks the loops; one elected lane issues) =====================
-        // tcgen05.mma issue is paced by execution (about one MMA of queue slack), so every cycle spent between two
-        // MMAs on anything else is a tensor-pipe bubble.  The barrier of the NEXT stage (and the accumulator buffer
-        // of the next tile) is therefore probed in the shadow of the current stage's MMAs, and the blocking wait is
-        // only taken when that probe failed.  The loops stay warp-uniform so the descriptors live in uniform registers.
-        const bool leader = elect_one();
-        uint32_t stage_iter = 0, tile_iter = 0, item_iter = 0;
-        bool ok = true;
-        uint32_t full_ready = 0;    // full barrier of stage_iter already observed complete
-        uint32_t tempty_ready = 0;  // accumulator buffer of tile_iter already observed free
-        bool n_rounds_done = false;
-        // Fast path (Dp == 768 with 64-row tiles): a tile is exactly 3 stages, so the 6-stage ring holds two tiles and
-        // tile parity fixes the stage numbers, the accumulator buffer and every barrier / descriptor address at
-        // compile time; only the phase bits are computed at run time.
-        if (BN_ == 64 && NBUF == 2 && KPS == 4 && nkb == 12 && !(a.debug_mode & 8)) {
-            const uint64_t desc_base = make_b_desc(smem_base);
-            auto tile_body = [&](auto bc, uint32_t ph) -> bool {
-                constexpr int b = decltype(bc)::value;
-                if (!tempty_ready && !mbar_wait(tempty_bar(b), ph ^ 1u, abort_flag, 3)) return false;
-                tempty_ready = 0;
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + Cfg::kDCol + b * BN_;
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
-                    const int stage = b * 3 + s;
-                    if (!full_ready && !mbar_wait(full_bar(stage), ph, abort_flag, 4)) return false;
-                    if (leader) {
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)
-                            umma_ts_bf16(d_tmem, tmem_base + (uint32_t)((s * 16 + k4) * 8),
-                                         desc_base + (uint64_t)((stage * STAGE_BYTES) >> 4) + (uint64_t)(k4 * 2), Cfg::kIdesc,
-                                         (k4 == 0 && s == 0) ? 0u : 1u);
-                    }
-                    if (s < 2) {
-                        full_ready = mbar_try_wait(full_bar(stage + 1), ph);
-                    } else {
-                        full_ready = mbar_try_wait(full_bar((1 - b) * 3), b == 0 ? ph : (ph ^ 1u));
-                        tempty_ready = mbar_try_wait(tempty_bar(1 - b), b == 0 ? (ph ^ 1u) : ph);
-                    }
-                    if (leader) {
-#pragma unroll
-                        for (int kb = 1; kb < 4; ++kb)
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4)
-                                umma_ts_bf16(d_tmem, tmem_base + (uint32_t)((s * 16 + kb * 4 + k4) * 8),
-                                             desc_base + (uint64_t)((stage * STAGE_BYTES + kb * Cfg::kTileBytes) >> 4) + (uint64_t)(k4 * 2),
-                                             Cfg::kIdesc, 1u);
-                        if (CLUSTER == 1) umma_commit(empty_bar(stage));
-                        else umma_commit_mcast(empty_bar(stage), kMask);
-                    }
-                    __syncwarp();
-                }
-                if (leader) umma_commit(tfull_bar(b));
-                __syncwarp();
-                return true;
-            };
-            for (int r = 0; r < n_rounds && ok; ++r, ++item_iter) {
-                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
-                if (part >= (uint32_t)a.P) break;
-                const uint32_t t0 = part * a.tiles_per_part;
-                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
-                if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
-                tcgen05_fence_after();
-                for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
-                    const uint32_t ph = (tile_iter >> 1) & 1u;
-                    if ((tile_iter & 1u) == 0u) ok = tile_body(std::integral_constant<int, 0>{}, ph);
-                    else ok = tile_body(std::integral_constant<int, 1>{}, ph);
-                }
-            }
-            n_rounds_done = true;
-        }
-        for (int r = 0; r < n_rounds && ok && !n_rounds_done; ++r, ++item_iter) {
-            const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
-            if (part >= (uint32_t)a.P) break;
-            const uint32_t t0 = part * a.tiles_per_part;
-            const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
-            if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
-            tcgen05_fence_after();
-            for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
-                const uint32_t buf = tile_iter % NBUF;
-                if (!tempty_ready && !mbar_wait(tempty_bar(buf), ((tile_iter / NBUF) & 1u) ^ 1u, abort_flag, 3)) { ok = false; break; }
-                tempty_ready = 0;
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + Cfg::kDCol + buf * BN_;
-                for (int s = 0; s < stages_per_tile; ++s, ++stage_iter) {
-                    const int stage = stage_iter % NSTAGES;
-                    const uint32_t phase = (stage_iter / NSTAGES) & 1u;
-                    if (!full_ready && !mbar_wait(full_bar(stage), phase, abort_flag, 4)) { ok = false; break; }
-                    const int kbc = min(KPS, nkb - s * KPS);
-                    // descriptors of one stage differ only in the start-address field: +2 per K=16 step inside a
-                    // 128-byte swizzle row, + kTileBytes/16 per K block
-                    const uint64_t bdesc0 = make_b_desc(smem_base + stage * STAGE_BYTES);
-                    const uint32_t a0 = tmem_base + (uint32_t)(s * KPS * (KBLK / 16) * 8);
-                    if (leader) {
-#pragma unroll
-                        for (int k4 = 0; k4 < KBLK / 16; ++k4)
-                            umma_ts_bf16(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), Cfg::kIdesc,
-                                         (k4 == 0) ? (s > 0 ? 1u : 0u) : 1u);
-                    }
-                    // probe what the next iteration will need while the pipe is busy
-                    {
-                        const uint32_t nsi = stage_iter + 1;
-                        full_ready = mbar_try_wait(full_bar(nsi % NSTAGES), (nsi / NSTAGES) & 1u);
-                        if (s == stages_per_tile - 1) {
-                            const uint32_t nti = tile_iter + 1;
-                            tempty_ready = mbar_try_wait(tempty_bar(nti % NBUF), ((nti / NBUF) & 1u) ^ 1u);
-                        }
-                    }
-                    if (leader) {
-#pragma unroll
-                        for (int kb = 1; kb < KPS; ++kb) {
-                            if (kb < kbc) {
-#pragma unroll
-                                for (int k4 = 0; k4 < KBLK / 16; ++k4)
-                                    umma_ts_bf16(d_tmem, a0 + (uint32_t)((kb * (KBLK / 16) + k4) * 8),
-                                                 bdesc0 + (uint64_t)(kb * (Cfg::kTileBytes >> 4) + k4 * 2), Cfg::kIdesc, 1u);
-                            }
-                        }
-                        // frees the stage (in every CTA that multicast into it) when these MMAs have read it
-                        if (CLUSTER == 1) umma_commit(empty_bar(stage));
-                        else umma_commit_mcast(empty_bar(stage), kMask);
-                    }
-                    __syncwarp();
-                }
-                if (ok && leader) umma_commit(tfull_bar(buf));  // accumulator tile complete
-                __syncwarp();
-            }
-        }
-    } else {
-        // ===================== epilogue: lane == query =====================
-        const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
-        const int ql = quad * 32 + lane;              // query within the tile
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        uint32_t tile_iter = 0;
-        bool ok = true;
-        for (int r = 0; r < n_rounds && ok; ++r) {
-            const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots, mt = (uint32_t)mgroup * CLUSTER + crank;
-            if (part >= (uint32_t)a.P) break;
-            const uint32_t t0 = part * a.tiles_per_part;
-            const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
-            const uint32_t gq = mt * BM + ql;
-            const bool q_valid = gq < (uint32_t)a.nq;
-            // A operand: this thread's query row, bf16 pairs, into TMEM columns [0, Dp/2)
-            {
-                const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)gq * a.Dp);
-                for (int c = 0; c < a.Dp / 32; ++c) {
-                    uint32_t w[16];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 x = __ldg(src + c * 4 + i);
-                        w[4 * i + 0] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
-                    }
-                    tmem_st_32x32b_x16(lane_addr + c * 16, w);
-                }
-                tmem_st_wait();
-            }
-            for (int j = 0; j < KP; ++j) {
-                l_score[j * BM + ql] = -INFINITY;
-                l_row[j * BM + ql] = ROW_NONE;
-            }
-            // thr_l: worst score kept in this thread's list.  thr_g: best such value any partition of this query has
-            // published; a row at or below it can never be needed, so it also gates the list.
-            float thr_l = q_valid ? -INFINITY : INFINITY;
-            float thr_g = -INFINITY, thr_pub = -INFINITY;
-            int min_pos = 0;
-            uint32_t* gthr = a.gthr + (q_valid ? gq : 0);
-            uint32_t g_bits = 0u;
-            tcgen05_fence_before();
-            mbar_arrive(aready_bar);
-            const uint32_t row_end = a.n_rows;
-            for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
-                const uint32_t buf = tile_iter % NBUF;
-                // refresh the shared floor every 8th tile; the load issued now is consumed 8 tiles later, so its
-                // (loaded) L2 latency never sits on the per-tile critical path
-                if (a.share_floor && (tile_iter & 7u) == 0u) {
-                    if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
-                    g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
-                }
-                if (!mbar_wait(tfull_bar(buf), (tile_iter / NBUF) & 1u, abort_flag, 5)) { ok = false; break; }
-                tcgen05_fence_after();
-                if (a.debug_mode & 2) {
-                    tcgen05_fence_before();
-                    mbar_arrive(tempty_bar(buf));
-                    continue;
-                }
-#pragma unroll
-                for (int h = 0; h < BN_ / 64; ++h) {
-                    uint32_t v[64];
-                    tmem_ld_32x32b_x32(lane_addr + Cfg::kDCol + buf * BN_ + h * 64, v);
-                    tmem_ld_32x32b_x32(lane_addr + Cfg::kDCol + buf * BN_ + h * 64 + 32, v + 32);
-                    tmem_ld_wait();
-                    if (h == BN_ / 64 - 1) {
-                        tcgen05_fence_before();
-                        mbar_arrive(tempty_bar(buf));  // accumulator is in registers: the MMA warp may reuse the buffer
-                    }
-                    const uint32_t row0 = t * BN_ + h * 64;
-                    if (a.dump != nullptr) {
-                        float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN_) + row0;
-#pragma unroll
-                        for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
-                    }
-                    float thr = fmaxf(thr_l, thr_g);
-                    if (a.debug_mode & 4) thr = INFINITY;
-                    bool any = false;
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) any |= (__uint_as_float(v[i]) > thr);
-                    if (any) {
-#pragma unroll
-                        for (int i = 0; i < 64; ++i) {
-                            const float sc = __uint_as_float(v[i]);
-                            if (sc > thr && row0 + i < row_end) {
-                                l_score[min_pos * BM + ql] = sc;
-                                l_row[min_pos * BM + ql] = row0 + i;
-                                float mn = INFINITY;
-                                for (int j = 0; j < KP; ++j) {
-                                    const float x = l_score[j * BM + ql];
-                                    if (x < mn) { mn = x; min_pos = j; }
-                                }
-                                thr_l = mn;
-                                thr = fmaxf(thr_l, thr_g);
-                            }
-                        }
-                        if (a.share_floor && q_valid && thr_l > thr_pub && thr_l > thr_g) {  // list is full and its floor rose: publish
-                            atomicMax(gthr, f32_orderable(thr_l));
-                            thr_pub = thr_l;
-                        }
-                    }
-                }
-            }
-            if (ok && q_valid) {
-                const size_t o = ((size_t)gq * a.P + part) * KP;
-                for (int j = 0; j < KP; ++j) {
-                    a.cand_score[o + j] = l_score[j * BM + ql];
-                    a.cand_row[o + j] = l_row[j * BM + ql];
-                }
-                // every row this thread dropped scored <= max(thr_l, thr_g) at the time, and both only grow
-                a.cand_thr[(size_t)gq * a.P + part] = fmaxf(thr_l, thr_g);
-            }
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (CLUSTER > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
-    tcgen05_fence_after();
-    if (threadIdx.x == 0 && *abort_flag) atomicMax(a.error_flag, *abort_flag);
-    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
 }
+
+// A operand: the calling thread's query row (bf16 pairs) into TMEM columns [0, Dp/2) of its lane.
+__device__ __forceinline__ void load_query_to_tmem(const __nv_bfloat16* qrow, int Dp, uint32_t lane_addr) {
+    const uint4* src = reinterpret_cast<const uint4*>(qrow);
+    for (int c = 0; c < Dp / 32; ++c) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 x = __ldg(src + c * 4 + i);
+            w[4 * i + 0] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+        }
+        tmem_st_32x32b_x16(lane_addr + c * 16, w);
+    }
+    tmem_st_wait();
+}
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Per-thread shortlist of one (query, row partition): the KP best coarse scores, held in REGISTERS (every index is
+// a compile-time constant) and gated by a register threshold — shared-memory lists stall for thousands of cycles
+// behind the tensor core's operand reads and the TMA writes.  lmin = worst score kept; thr_g = best floor any
+// partition of the query has published through gthr (a row at or below it is outside the global top KP).
+struct Shortlist {
+    float sc[KP];
+    uint32_t rw[KP];
+    float lmin, thr_g, thr_pub;
+    uint32_t g_bits;
+    uint32_t* gthr;
+    bool q_valid, share;
+
+    __device__ __forceinline__ void reset(bool valid, bool share_floor, uint32_t* gthr_q) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            sc[j] = -INFINITY;
+            rw[j] = ROW_NONE;
+        }
+        q_valid = valid;
+        share = share_floor;
+        gthr = gthr_q;
+        lmin = -INFINITY;
+        thr_pub = -INFINITY;
+    }
+    __device__ __forceinline__ void init_floor() {
+        thr_g = -INFINITY;
+        g_bits = 0u;
+    }
+    __device__ __forceinline__ float gate() const { return q_valid ? fmaxf(lmin, thr_g) : INFINITY; }
+    // end of the warm-up round: the KP-th best score of the sample is a valid floor for every partition (KP rows of
+    // the corpus score at least that much), so it becomes the shared floor and the list starts over
+    __device__ __forceinline__ void absorb_sample() {
+        if (share && q_valid && lmin > thr_g) {
+            thr_g = lmin;
+            atomicMax(gthr, f32_orderable(lmin));
+        }
+    }
+    // refresh the shared floor every 8th tile; the load issued now is consumed 8 tiles later, so its (loaded) L2
+    // latency never sits on the per-tile critical path
+    __device__ __forceinline__ void poll_floor(uint32_t tile_iter) {
+        if (share && (tile_iter & 7u) == 0u) {
+            if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
+            g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
+        }
+    }
+    // replace the current minimum by (score, row) and recompute the minimum: ~70 ALU instructions, no memory
+    __device__ __forceinline__ void insert(float score, uint32_t row) {
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            const bool hit = !done && sc[j] == lmin;
+            sc[j] = hit ? score : sc[j];
+            rw[j] = hit ? row : rw[j];
+            done = done || hit;
+        }
+        float m0 = fmin3(sc[0], sc[1], sc[2]), m1 = fmin3(sc[3], sc[4], sc[5]);
+        m0 = fmin3(m0, sc[6], sc[7]);
+        m1 = fmin3(m1, sc[8], sc[9]);
+        m0 = fmin3(m0, sc[10], sc[11]);
+        m1 = fmin3(m1, sc[12], sc[13]);
+        lmin = fmin3(fminf(m0, m1), sc[14], sc[15]);
+    }
+    // 64 accumulator columns of this thread's query = rows row0 .. row0+63.  Called by whole warps.
+    __device__ __forceinline__ void scan64(const uint32_t* v, uint32_t row0, uint32_t row_end, bool disabled) {
+        float thr = disabled ? INFINITY : gate();
+        // tile maximum with 3-input max: 32 instructions for 64 scores
+        float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+        float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+#pragma unroll
+        for (int i = 6; i + 3 < 64; i += 4) {
+            m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
+        m0 = fmax3(m0, __uint_as_float(v[62]), __uint_as_float(v[63]));
+        // Slow path, entered by the whole warp when any lane has a candidate.  It must stay SMALL: a fully unrolled
+        // "for each of the 64 scores: compare, insert" is ~90 KB of code whose sparse execution misses the instruction
+        // cache at every step (~7700 cycles per tile measured).  So: (1) a 64-bit hit mask per lane from straight
+        // compares, (2) a rolled loop that pops each lane's lowest hit and fetches the score with a select tree.
+        if (__any_sync(0xffffffffu, fmaxf(m0, m1) > thr)) {
+            uint32_t mlo = 0u, mhi = 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                mlo |= (__uint_as_float(v[i]) > thr ? 1u : 0u) << i;
+                mhi |= (__uint_as_float(v[32 + i]) > thr ? 1u : 0u) << i;
+            }
+            if (row0 + 64u > row_end) {  // last tile: rows past the end of the corpus never enter a list
+                const uint32_t n_ok = row_end > row0 ? row_end - row0 : 0u;
+                mlo &= n_ok >= 32u ? 0xffffffffu : ((1u << n_ok) - 1u);
+                mhi &= n_ok >= 64u ? 0xffffffffu : (n_ok > 32u ? ((1u << (n_ok - 32u)) - 1u) : 0u);
+            }
+#pragma unroll 1
+            while (__any_sync(0xffffffffu, (mlo | mhi) != 0u)) {
+                if ((mlo | mhi) != 0u) {
+                    int idx;
+                    if (mlo != 0u) {
+                        idx = __ffs((int)mlo) - 1;
+                        mlo &= mlo - 1u;
+                    } else {
+                        idx = 32 + __ffs((int)mhi) - 1;
+                        mhi &= mhi - 1u;
+                    }
+                    // v[idx] with a run-time idx: 6-level select tree over the register array (63 selects)
+                    uint32_t t5[32], t4[16], t3[8], t2[4], t1[2];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t5[j] = (idx & 32) ? v[32 + j] : v[j];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) t4[j] = (idx & 16) ? t5[16 + j] : t5[j];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t3[j] = (idx & 8) ? t4[8 + j] : t4[j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) t2[j] = (idx & 4) ? t3[4 + j] : t3[j];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) t1[j] = (idx & 2) ? t2[2 + j] : t2[j];
+                    const float x = __uint_as_float((idx & 1) ? t1[1] : t1[0]);
+                    if (x > gate()) insert(x, row0 + (uint32_t)idx);  // the gate may have risen since the mask was taken
+                }
+            }
+            if (share && q_valid && lmin > thr_pub && lmin > thr_g) {  // list is full and its floor rose: publish
+                atomicMax(gthr, f32_orderable(lmin));
+                thr_pub = lmin;
+            }
+        }
+    }
+    __device__ __forceinline__ void flush(const TcArgs& a, uint32_t gq, uint32_t part) {
+        if (!q_valid) return;
+        const size_t o = ((size_t)gq * a.P + part) * KP;
+#pragma unroll
+        for (int j = 0; j < KP; j += 4) {
+            *reinterpret_cast<float4*>(a.cand_score + o + j) = make_float4(sc[j], sc[j + 1], sc[j + 2], sc[j + 3]);
+            *reinterpret_cast<uint4*>(a.cand_row + o + j) = make_uint4(rw[j], rw[j + 1], rw[j + 2], rw[j + 3]);
+        }
+        // every row this thread dropped scored <= max(lmin, thr_g) at the time, and both only grow
+        a.cand_thr[(size_t)gq * a.P + part] = fmaxf(lmin, thr_g);
+    }
+};
 
 // ---- shadow / query preparation --------------------------------------------------------------------------------
 enum ShadowKind { SHADOW_IP = 0, SHADOW_COSINE = 1, SHADOW_L2 = 2 };
 
-// One warp per row: bf16 shadow row of Dp elements (zero padded) + max row norm (for the certification bound).
+// One warp per row: the row's Dp bf16 values (zero padded) written into the tiled, pre-swizzled layout described
+// at the top of this file, + max row norm (for the certification bound).
 //   SHADOW_IP      c
 //   SHADOW_COSINE  c / |c|            (zero rows stay zero: cosine distance 1.0, simd.rs:1631-1633)
 //   SHADOW_L2      [c, n1, n2, n3]    with n1+n2+n3 ~ |c|^2 split into three bf16 pieces (columns dim..dim+2)
+__host__ __device__ inline size_t shadow_chunk_offset(uint64_t row, int chunk /* 16-byte chunk = 8 elements */, int nkb) {
+    const uint64_t tile = row >> 6;
+    const uint32_t half = (uint32_t)(row >> 5) & 1u, r = (uint32_t)row & 31u;
+    const uint32_t kb = (uint32_t)chunk >> 3, c = (uint32_t)chunk & 7u;
+    return (size_t)(((tile * (uint64_t)nkb + kb) * 2 + half) * HALF_BLOCK_BYTES) + (size_t)r * 128 + (size_t)((c ^ (r & 7u)) << 4);
+}
 __global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int Dp,
-                                    int kind, __nv_bfloat16* __restrict__ shadow, float* __restrict__ max_norm) {
+                                    int kind, unsigned char* __restrict__ shadow, float* __restrict__ max_norm) {
     uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= first_row + n) return;
@@ -662,16 +454,22 @@ __global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t fir
     float norm = sqrtf(ss);
     float scale = 1.0f;
     if (kind == SHADOW_COSINE) scale = norm > 0.0f ? 1.0f / norm : 0.0f;
-    __nv_bfloat16* out = shadow + row * (uint64_t)Dp;
-    for (int d = lane; d < Dp; d += 32) {
-        float x = d < dim ? __ldg(r + d) * scale : 0.0f;
-        if (kind == SHADOW_L2 && d >= dim && d < dim + 3) {
-            float n1 = __bfloat162float(__float2bfloat16_rn(ss));
-            float n2 = __bfloat162float(__float2bfloat16_rn(ss - n1));
-            float n3 = (ss - n1) - n2;
-            x = d == dim ? n1 : (d == dim + 1 ? n2 : n3);
+    const int nkb = Dp / KBLK;
+    for (int chunk = lane; chunk < Dp / 8; chunk += 32) {
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int d = chunk * 8 + e;
+            float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+            if (kind == SHADOW_L2 && d >= dim && d < dim + 3) {
+                float n1 = __bfloat162float(__float2bfloat16_rn(ss));
+                float n2 = __bfloat162float(__float2bfloat16_rn(ss - n1));
+                float n3 = (ss - n1) - n2;
+                x = d == dim ? n1 : (d == dim + 1 ? n2 : n3);
+            }
+            v[e] = __float2bfloat16_rn(x);
         }
-        out[d] = __float2bfloat16_rn(x);
+        *reinterpret_cast<uint4*>(shadow + shadow_chunk_offset(row, chunk, nkb)) = *reinterpret_cast<const uint4*>(v);
     }
     if (lane == 0 && isfinite(norm)) atomicMax(reinterpret_cast<unsigned int*>(max_norm), __float_as_uint(norm));
 }

@@ -1,35 +1,26 @@
-// lb_tc2.cuh — tensor-core coarse pass on CTA PAIRS (tcgen05 cta_group::2).
+// lb_tc2.cuh — tensor-core coarse pass on CTA PAIRS (tcgen05 cta_group::2), for batches of two or more query tiles.
 //
-// Same contract as coarse_topk_kernel in lb_tc.cuh (per-(query, partition) shortlists of KP coarse scores with
-// a certified floor), but the two CTAs of a cluster form one tcgen05 CTA pair:
+// The two CTAs of a cluster form one tcgen05 CTA pair:
 //   * the MMA is M = 256 (128 queries in the TMEM of each CTA) x N = 64 corpus rows x K = 16, issued by ONE
-//     thread of the rank-0 CTA for both SMs;
-//   * each CTA stages only HALF of every corpus tile (32 of the 64 rows) in its shared memory and the tensor
-//     cores of both SMs read both halves, so an SM ingests 32 B/clk of shadow at full MMA rate instead of the
-//     64 B/clk of the one-CTA kernel — that ingest (L2 -> SM) is what bounded the one-CTA kernel;
-//   * the same 192 KiB of staging therefore holds 12 stages x 16 KiB = four 768-dim tiles per CTA: twice the
-//     latency tolerance.
-// Barriers: full[s] (rank 0 only; both CTAs' TMA complete_tx on it), empty[s] / tfull[b] (every CTA; tcgen05.commit
-// multicast), tempty[b] / aready (rank 0 only; one arrive per epilogue warp of both CTAs).
+//     thread of the even CTA for both SMs;
+//   * each CTA stages only HALF of every corpus tile (its 32 rows: one 16 KiB box of the tiled shadow per stage)
+//     and the tensor cores of both SMs read both halves, so the same 192 KiB ring holds 12 stages = four 768-dim
+//     tiles per CTA;
+//   * barriers: full[s] (even CTA only; both CTAs' TMA complete_tx on it), empty[s] / tfull[b] (both CTAs;
+//     tcgen05.commit multicast), tempty[b] / aready (even CTA only; one RELAXED remote arrive per epilogue warp of
+//     both CTAs — a release at cluster scope costs ~1400 cycles under a loaded memory system).
+// Work: cluster c serves query group (c % n_mgroups) of slot (c / n_mgroups); the query groups of a slot stream the
+// same row partitions in lockstep (TcArgs::progress / window) so HBM is read once per slot.
 #pragma once
 #include "lb_tc.cuh"
 
 namespace lb {
 namespace tc {
 
-constexpr int P_BN = 64;                 // corpus rows per accumulator tile
-constexpr int P_ROWS = P_BN / 2;         // rows staged by each CTA
-constexpr int P_KB_BYTES = P_ROWS * 128; // one K block (64 bf16) of this CTA's rows: 4 KiB
-constexpr int P_KPS = 4;                 // K blocks per stage
-constexpr int P_STAGE_BYTES = P_KPS * P_KB_BYTES;  // 16 KiB
-constexpr int P_NSTAGES = 12;
-constexpr int P_NBUF = 2;
-constexpr int P_DCOL = TMEM_COLS - P_NBUF * P_BN;  // 384: A operand occupies [0, Dp/2) <= 384 columns
-constexpr uint32_t P_SMEM_LIST_OFF = P_NSTAGES * P_STAGE_BYTES;        // 196608
-constexpr uint32_t P_SMEM_BAR_OFF = P_SMEM_LIST_OFF + 2 * KP * BM * 4; // + 16384
-constexpr uint32_t P_SMEM_BYTES = P_SMEM_BAR_OFF + 256 + 1024;
+constexpr int P_STAGE_BYTES = KPS * HALF_BLOCK_BYTES;        // 16 KiB
+constexpr int P_NSTAGES = SMEM_RING_BYTES / P_STAGE_BYTES;   // 12
 // instruction descriptor: D=f32, A=B=bf16, K-major, N=64, M=256
-constexpr uint32_t P_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t P_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
     uint32_t r;
@@ -42,20 +33,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // `bar` is this CTA's own barrier address with the peer bit cleared: the bytes are counted on the barrier at that
-// offset in the even CTA of the pair the data lands in (for every destination of a multicast).
+// offset in the even CTA of the pair.
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t smem_dst, const CUtensorMap* tmap, int c2, int c3, uint32_t bar) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar,
-                                                       uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-        "[%0], [%1, {%2, %3}], [%4], %5;"
-        ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_dst), "l"(tmap), "r"(0), "r"(0), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
 __device__ __forceinline__ void umma_pair_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -66,9 +50,9 @@ __device__ __forceinline__ void umma_pair_ts_bf16(uint32_t d_tmem, uint32_t a_tm
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_pair_commit(uint32_t bar, uint16_t cta_mask) {
+__device__ __forceinline__ void umma_pair_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(cta_mask) : "memory");
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -79,38 +63,23 @@ __device__ __forceinline__ void tmem_relinquish_pair() {
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-    float d;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
 
-// NKB_T: K blocks per tile (Dp / 64) known at compile time, 0 = read a.Dp at run time.
-// CL: CTAs per cluster (2, 4 or 8) = CL/2 pairs working on CL query tiles.  Every 32-row half tile is fetched from
-// L2 ONCE per cluster: the CL/2 CTAs of the same parity each load 64/CL of its rows and multicast them to all CTAs
-// of that parity, so L2 is read n_mtiles/CL times per shadow byte (L2 bandwidth, ~5 TB/s, is what bounds the
-// pass when every pair reads the shadow on its own).
-template <int NKB_T, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
-    constexpr int NPAIRS = CL / 2;
-    constexpr int PIECE_ROWS = P_BN / CL;  // rows of a tile this CTA fetches (and multicasts)
-    const uint32_t crank = cluster_ctarank();
-    const uint32_t parity = crank & 1u, pair_leader = crank & ~1u;
-    const int n_mgroups = (a.n_mtiles + CL - 1) / CL;
-    const int cluster_id = (int)(blockIdx.x / CL);
+coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
+    const uint32_t crank = cluster_ctarank();  // 0 = even CTA (issues the MMAs), 1 = odd CTA
+    const int n_mgroups = (a.n_mtiles + 1) / 2;
+    const int cluster_id = (int)(blockIdx.x >> 1);
     const int mgroup = cluster_id % n_mgroups, slot = cluster_id / n_mgroups;
     const int n_rounds = slot < a.n_slots ? a.parts_per_slot : 0;
+    const int first_round = a.sample_tiles > 0 ? -1 : 0;  // round -1 = warm-up over the sample tiles
     extern __shared__ __align__(16) unsigned char smem_tc2[];
     const uint32_t smem_base = (smem_u32(smem_tc2) + 1023u) & ~1023u;
     unsigned char* smem = smem_tc2 + (smem_base - smem_u32(smem_tc2));
-    float* l_score = reinterpret_cast<float*>(smem + P_SMEM_LIST_OFF);                     // [KP][BM]
-    uint32_t* l_row = reinterpret_cast<uint32_t*>(smem + P_SMEM_LIST_OFF + KP * BM * 4);   // [KP][BM]
-    const uint32_t bar_base = smem_base + P_SMEM_BAR_OFF;
+    const uint32_t bar_base = smem_base + SMEM_BAR_OFF;
     const uint32_t full0 = bar_base, empty0 = bar_base + 8u * P_NSTAGES, tfull0 = bar_base + 8u * (2 * P_NSTAGES),
                    tempty0 = tfull0 + 16u, aready_bar = tfull0 + 32u;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + P_SMEM_BAR_OFF + 8 * (2 * P_NSTAGES + 5));
-    volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(smem + P_SMEM_BAR_OFF + 8 * (2 * P_NSTAGES + 5) + 4);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * P_NSTAGES + 5));
+    volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * P_NSTAGES + 5) + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long prof_c0 = clock64();
@@ -118,16 +87,17 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < P_NSTAGES; ++s) {
             mbar_init(full0 + 8u * s, 1);
-            mbar_init(empty0 + 8u * s, NPAIRS);  // every pair of the cluster must have drained the stage
+            mbar_init(empty0 + 8u * s, 1);
         }
-        for (int b = 0; b < P_NBUF; ++b) {
+        for (int b = 0; b < 2; ++b) {
             mbar_init(tfull0 + 8u * b, 1);
             mbar_init(tempty0 + 8u * b, 8);  // 4 epilogue warps x 2 CTAs
         }
         mbar_init(aready_bar, 8);
         *abort_flag = 0;
         fence_barrier_init();
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_full) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_rem) : "memory");
     }
     if (warp == 0) {
         __syncwarp();
@@ -140,27 +110,26 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int nkb = NKB_T > 0 ? NKB_T : a.Dp / KBLK;
-    const int spt = (nkb + P_KPS - 1) / P_KPS;  // stages per tile; the ring walks in whole tiles
+    const int nkb = a.Dp / KBLK;
+    const int n_full = nkb / KPS, rem = a.rem_kb;
+    const int spt = n_full + (rem ? 1 : 0);  // stages per tile
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs; each loads its 32 rows of every tile) =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             bool ok = true;
+            // lockstep: only the even CTA throttles; its peer follows through the shared stage ring
             bool lockstep = a.progress != nullptr && n_mgroups > 1 && crank == 0;
             uint32_t* prog = a.progress != nullptr ? a.progress + (size_t)slot * PROGRESS_STRIDE : nullptr;
             uint32_t seq = 0, known_min = 0;
             const uint32_t window = (uint32_t)a.window;
             const uint32_t pair_full0 = full0 & PEER_BIT_MASK;
-            constexpr uint16_t kParityMask = (uint16_t)((CL == 8 ? 0x55u : (CL == 4 ? 0x5u : 0x1u)));
-            const uint16_t mcast = (uint16_t)(kParityMask << parity);
-            const uint32_t piece_off = (crank >> 1) * (PIECE_ROWS * 128);
-            for (int r = 0; r < n_rounds && ok; ++r) {
-                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
+            for (int r = first_round; r < n_rounds && ok; ++r) {
+                const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
                 if (part >= (uint32_t)a.P) break;
-                const uint32_t t0 = part * a.tiles_per_part;
-                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+                const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
+                const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
                 for (uint32_t t = t0; t < t1 && ok; ++t) {
                     if (lockstep && seq >= known_min + window) {
                         const uint64_t w0 = globaltimer_ns();
@@ -176,24 +145,17 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
                             __nanosleep(100);
                         }
                     }
-                    const int row = (int)(t * P_BN + parity * P_ROWS + (crank >> 1) * PIECE_ROWS);
                     for (int s = 0; s < spt; ++s) {
                         if (!mbar_wait(empty0 + 8u * stage, phase ^ 1u, abort_flag, 1)) { ok = false; break; }
-                        const int kbc = min(P_KPS, nkb - s * P_KPS);
-                        if ((a.debug_mode & 1) || ((a.debug_mode & 16) && seq >= 4) || ((a.debug_mode & 32) && seq >= 4 && (stage & 1u)) ||
-                            ((a.debug_mode & 64) && seq >= 4 && (stage & 3u))) {
+                        const int kbc = s < n_full ? KPS : rem;
+                        if ((a.debug_mode & 1) || ((a.debug_mode & 16) && seq >= 4)) {
                             // bit 4: real data for the first tiles only, then the stale stages are re-used without loads
-                            if (parity == 0) mbar_arrive(full0 + 8u * stage);
+                            if (crank == 0) mbar_arrive(full0 + 8u * stage);
                         } else {
-                            // a pair's full barrier lives in its even CTA and counts the bytes landing in both CTAs
-                            if (parity == 0) mbar_arrive_expect_tx(full0 + 8u * stage, 2u * (uint32_t)kbc * P_KB_BYTES);
-                            for (int kb = 0; kb < kbc; ++kb) {
-                                const uint32_t dst = smem_base + stage * P_STAGE_BYTES + kb * P_KB_BYTES + piece_off;
-                                if (CL == 2)
-                                    tma_load_2d_pair(dst, &tmap, (s * P_KPS + kb) * KBLK, row, pair_full0 + 8u * stage);
-                                else
-                                    tma_load_2d_pair_mcast(dst, &tmap, (s * P_KPS + kb) * KBLK, row, pair_full0 + 8u * stage, mcast);
-                            }
+                            // the pair's full barrier lives in the even CTA and counts the bytes landing in both CTAs
+                            if (crank == 0) mbar_arrive_expect_tx(full0 + 8u * stage, 2u * (uint32_t)kbc * HALF_BLOCK_BYTES);
+                            tma_load_4d_pair(smem_base + stage * P_STAGE_BYTES, s < n_full ? &tmap_full : &tmap_rem, (int)crank,
+                                             (int)(t * (uint32_t)nkb) + s * KPS, pair_full0 + 8u * stage);
                         }
                         if (++stage == P_NSTAGES) { stage = 0; phase ^= 1u; }
                     }
@@ -203,24 +165,22 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: even CTA of each pair, warp-uniform loops, one elected lane issues =====
+        // ===================== MMA issuer: even CTA only, warp-uniform loops, one elected lane issues ============
         // Issue is paced by execution with little queue slack, so the next stage's barrier (and the next tile's
-        // accumulator buffer) is probed in the shadow of the current stage's MMAs.
-        if (parity == 0) {
+        // accumulator buffer) is probed with test_wait in the shadow of the current stage's MMAs.
+        if (crank == 0) {
             const bool leader = elect_one();
-            constexpr uint16_t kAllMask = (uint16_t)((1u << CL) - 1u);
-            const uint16_t pair_mask = (uint16_t)(3u << crank);
             uint32_t stage = 0, phase = 0, tile_iter = 0, item_iter = 0;
             bool ok = true;
             uint32_t full_ready = 0, tempty_ready = 0;
             const uint64_t desc_base = make_b_desc(smem_base);
             long long w_tempty = 0, w_full = 0, n_w_tempty = 0, n_w_full = 0;
             const long long mma_c0 = clock64();
-            for (int r = 0; r < n_rounds && ok; ++r, ++item_iter) {
-                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
+            for (int r = first_round; r < n_rounds && ok; ++r, ++item_iter) {
+                const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
                 if (part >= (uint32_t)a.P) break;
-                const uint32_t t0 = part * a.tiles_per_part;
-                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+                const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
+                const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
                 if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
                 tcgen05_fence_after();
                 for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
@@ -233,7 +193,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
                     }
                     tempty_ready = 0;
                     tcgen05_fence_after();
-                    const uint32_t d_tmem = tmem_base + P_DCOL + buf * P_BN;
+                    const uint32_t d_tmem = tmem_base + DCOL + buf * BN;
 #pragma unroll 1
                     for (int s = 0; s < spt; ++s) {
                         if (!full_ready) {
@@ -242,9 +202,9 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
                             w_full += clock64() - c0;
                             ++n_w_full;
                         }
-                        const int kbc = min(P_KPS, nkb - s * P_KPS);
+                        const int kbc = s < n_full ? KPS : rem;
                         const uint64_t bdesc0 = desc_base + (uint64_t)((stage * P_STAGE_BYTES) >> 4);
-                        const uint32_t a0 = tmem_base + (uint32_t)(s * P_KPS * 4 * 8);
+                        const uint32_t a0 = tmem_base + (uint32_t)(s * KPS * 4 * 8);
                         if (leader) {
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
@@ -262,20 +222,20 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
                         }
                         if (leader) {
 #pragma unroll
-                            for (int kb = 1; kb < P_KPS; ++kb) {
+                            for (int kb = 1; kb < KPS; ++kb) {
                                 if (kb < kbc) {
 #pragma unroll
                                     for (int k4 = 0; k4 < 4; ++k4)
                                         umma_pair_ts_bf16(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
-                                                          bdesc0 + (uint64_t)(kb * (P_KB_BYTES >> 4) + k4 * 2), P_IDESC, 1u);
+                                                          bdesc0 + (uint64_t)(kb * (HALF_BLOCK_BYTES >> 4) + k4 * 2), P_IDESC, 1u);
                                 }
                             }
-                            umma_pair_commit(empty0 + 8u * stage, kAllMask);  // one of the NPAIRS releases of this stage, in every CTA
+                            umma_pair_commit(empty0 + 8u * stage);  // frees the stage in both CTAs once these MMAs have read it
                         }
                         __syncwarp();
                         if (++stage == P_NSTAGES) { stage = 0; phase ^= 1u; }
                     }
-                    if (ok && leader) umma_pair_commit(tfull0 + 8u * buf, pair_mask);  // accumulator tile complete (both CTAs of the pair)
+                    if (ok && leader) umma_pair_commit(tfull0 + 8u * buf);  // accumulator tile complete (both CTAs)
                     __syncwarp();
                 }
             }
@@ -294,119 +254,72 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
         const int quad = warp & 3;
         const int ql = quad * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint32_t leader_tempty0 = mapa_rank(tempty0, pair_leader), leader_aready = mapa_rank(aready_bar, pair_leader);
+        const uint32_t even_tempty0 = mapa_rank(tempty0, 0), even_aready = mapa_rank(aready_bar, 0);
+        Shortlist sl;
         uint32_t tile_iter = 0;
         bool ok = true;
-        long long e_wait = 0, e_ld = 0;
-        for (int r = 0; r < n_rounds && ok; ++r) {
-            const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots, mt = (uint32_t)mgroup * CL + crank;
+        long long e_wait = 0, e_ld = 0, e_scan = 0, e_slow = 0, n_slow = 0, e_max = 0;
+        const uint32_t gq = ((uint32_t)mgroup * 2u + crank) * BM + (uint32_t)ql;
+        const bool q_valid = gq < (uint32_t)a.nq;
+        sl.init_floor();
+        for (int r = first_round; r < n_rounds && ok; ++r) {
+            const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
             if (part >= (uint32_t)a.P) break;
-            const uint32_t t0 = part * a.tiles_per_part;
-            const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
-            const uint32_t gq = mt * BM + ql;
-            const bool q_valid = gq < (uint32_t)a.nq;
-            {
-                const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)gq * a.Dp);
-                for (int c = 0; c < a.Dp / 32; ++c) {
-                    uint32_t w[16];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 x = __ldg(src + c * 4 + i);
-                        w[4 * i + 0] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
-                    }
-                    tmem_st_32x32b_x16(lane_addr + c * 16, w);
-                }
-                tmem_st_wait();
-            }
-            for (int j = 0; j < KP; ++j) {
-                l_score[j * BM + ql] = -INFINITY;
-                l_row[j * BM + ql] = ROW_NONE;
-            }
-            float thr_l = q_valid ? -INFINITY : INFINITY;
-            float thr_g = -INFINITY, thr_pub = -INFINITY;
-            int min_pos = 0;
-            uint32_t* gthr = a.gthr + (q_valid ? gq : 0);
-            uint32_t g_bits = 0u;
+            const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
+            const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
+            if (r == first_round) load_query_to_tmem(a.qb + (size_t)gq * a.Dp, a.Dp, lane_addr);  // the query tile never changes
+            sl.reset(q_valid, a.share_floor != 0, a.gthr + (q_valid ? gq : 0));
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_aready);
-            const uint32_t row_end = a.n_rows;
+            if (lane == 0) mbar_arrive_cluster(even_aready);
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter & 1u;
-                // refresh the shared floor every 8th tile; the load issued now is consumed 8 tiles later, so its
-                // (loaded) L2 latency never sits on the per-tile critical path
-                if (a.share_floor && (tile_iter & 7u) == 0u) {
-                    if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
-                    g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
-                }
+                if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter);
                 const long long ec0 = clock64();
                 if (!mbar_wait(tfull0 + 8u * buf, (tile_iter >> 1) & 1u, abort_flag, 5)) { ok = false; break; }
                 const long long ec1 = clock64();
                 tcgen05_fence_after();
                 uint32_t v[64];
                 if (!(a.debug_mode & 2)) {
-                    tmem_ld_32x32b_x32(lane_addr + P_DCOL + buf * P_BN, v);
-                    tmem_ld_32x32b_x32(lane_addr + P_DCOL + buf * P_BN + 32, v + 32);
+                    tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN, v);
+                    tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + 32, v + 32);
                     tmem_ld_wait();
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * buf);  // accumulator is in registers
+                if (lane == 0) mbar_arrive_cluster(even_tempty0 + 8u * buf);  // accumulator is in registers
                 e_wait += ec1 - ec0;
                 e_ld += clock64() - ec1;
                 if (a.debug_mode & 2) continue;
-                const uint32_t row0 = t * P_BN;
-                if (a.dump != nullptr) {
-                    float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * P_BN) + row0;
+                const uint32_t row0 = t * BN;
+                if (a.dump != nullptr && r >= 0) {
+                    float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
 #pragma unroll
                     for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
                 }
-                float thr = fmaxf(thr_l, thr_g);
-                if (a.debug_mode & 4) thr = INFINITY;
-                // tile maximum with 3-input max: 32 instructions for 64 scores
-                float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-                float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
-#pragma unroll
-                for (int i = 6; i + 3 < 64; i += 4) {
-                    m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-                    m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-                }
-                m0 = fmax3(m0, __uint_as_float(v[62]), __uint_as_float(v[63]));
-                if (fmaxf(m0, m1) > thr) {
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) {
-                        const float sc = __uint_as_float(v[i]);
-                        if (sc > thr && row0 + i < row_end) {
-                            l_score[min_pos * BM + ql] = sc;
-                            l_row[min_pos * BM + ql] = row0 + i;
-                            float mn = INFINITY;
-                            for (int j = 0; j < KP; ++j) {
-                                const float x = l_score[j * BM + ql];
-                                if (x < mn) { mn = x; min_pos = j; }
-                            }
-                            thr_l = mn;
-                            thr = fmaxf(thr_l, thr_g);
-                        }
-                    }
-                    if (a.share_floor && q_valid && thr_l > thr_pub && thr_l > thr_g) {
-                        atomicMax(gthr, f32_orderable(thr_l));
-                        thr_pub = thr_l;
-                    }
-                }
+                const long long sc0 = clock64();
+                sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0);
+                const long long sd = clock64() - sc0;
+                e_scan += sd;
+                if (sd > 400) { ++n_slow; e_slow += sd; }
+                if (sd > e_max) e_max = sd;
             }
-            if (ok && q_valid) {
-                const size_t o = ((size_t)gq * a.P + part) * KP;
-                for (int j = 0; j < KP; ++j) {
-                    a.cand_score[o + j] = l_score[j * BM + ql];
-                    a.cand_row[o + j] = l_row[j * BM + ql];
-                }
-                a.cand_thr[(size_t)gq * a.P + part] = fmaxf(thr_l, thr_g);
+            if (ok) {
+                if (r < 0) sl.absorb_sample();
+                else sl.flush(a, gq, part);
             }
         }
         if (a.prof != nullptr && warp == 2 && lane == 0) {
             unsigned long long* pr = a.prof + (size_t)blockIdx.x * 8;
             pr[6] = (unsigned long long)e_wait;
             pr[7] = (unsigned long long)e_ld;
+            if (crank == 1) {  // the odd CTA has no MMA issuer: its slots 0..3 carry the scan statistics of one warp
+                pr[0] = (unsigned long long)e_scan;
+                pr[1] = (unsigned long long)e_slow;
+                pr[2] = (unsigned long long)n_slow;
+                pr[3] = (unsigned long long)e_max;
+                pr[4] = tile_iter;
+            }
         }
     }
     tcgen05_fence_before();

@@ -19,6 +19,7 @@
 #include "lb_metrics.cuh"
 #include "lb_scan.cuh"
 #include "lb_tc.cuh"
+#include "lb_tc1.cuh"
 #include "lb_tc2.cuh"
 
 namespace lb {
@@ -68,13 +69,15 @@ struct DevBuf {
 };
 
 struct Shadow {
-    DevBuf buf;
-    uint64_t rows = 0;  // rows converted so far
+    DevBuf buf;           // tiled, pre-swizzled bf16 rows (layout: lb_tc.cuh)
+    uint64_t rows = 0;    // rows converted so far
+    uint64_t cap_tiles = 0;
     int Dp = 0;
-    CUtensorMap tmap;
-    uint64_t tmap_rows = 0;
+    // [0] one-CTA kernel (both halves of a K block per box), [1] CTA-pair kernel (one half); .full = KPS K blocks per
+    // box, .rem = the partial last stage of a tile ((Dp/64) % KPS K blocks)
+    CUtensorMap tmap_full[2], tmap_rem[2];
+    uint64_t tmap_tiles = 0;
     void* tmap_ptr = nullptr;
-    int tmap_bn = 0;    // box rows the tensor map was encoded for
 };
 
 static int next_pow2(int x) {
@@ -230,63 +233,65 @@ static bool tc_supported(const lb_index* idx, int metric) {
     return shadow_dp(idx, shadow_kind_for(metric)) <= tc::MAX_DP;
 }
 
-// Accumulator tile of the coarse kernel: 128 corpus rows per MMA when two accumulators still fit next to the
-// A operand in TMEM (Dp <= 512), otherwise 64 rows double-buffered.  LYNSE_B200_TC_TILE=64|128|128x1 overrides.
-static int tc_tile_variant(int Dp) {
-    const char* env = getenv("LYNSE_B200_TC_TILE");
-    if (env) {
-        if (!strcmp(env, "64")) return 0;
-        if (!strcmp(env, "128x1")) return 1;
-        if (!strcmp(env, "128") && Dp <= tc::TileCfg<128, 2>::kMaxDp) return 2;
-    }
-    return Dp <= tc::TileCfg<128, 2>::kMaxDp ? 2 : 0;
-}
-static int tc_variant_bn(int v) { return v == 0 ? 64 : 128; }
 static int tc_env_int(const char* name, int dflt) {
     const char* env = getenv(name);
     return env && *env ? atoi(env) : dflt;
 }
-// CTAs per cluster sharing corpus tiles by TMA multicast: 2 when there are at least two query tiles.
-static int tc_cluster_size(int n_mtiles) {
-    const char* env = getenv("LYNSE_B200_TC_CLUSTER");
-    if (env && !strcmp(env, "1")) return 1;
-    return n_mtiles >= 2 ? 2 : 1;
+
+static int encode_shadow_map(CUtensorMap* out, void* base, int nkb, uint64_t n_tiles, int box_halves, int box_kb) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    // (256 bf16 = 512 B, 8 rows of 512 B = one 4 KiB half block, 2 halves, tiles * K blocks)
+    cuuint64_t gdim[4] = {256, 8, 2, (cuuint64_t)n_tiles * (cuuint64_t)nkb};
+    cuuint64_t gstride[3] = {512, 4096, 8192};
+    cuuint32_t box[4] = {256, 8, (cuuint32_t)box_halves, (cuuint32_t)box_kb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return LB_OK;
 }
 
-static int ensure_shadow(lb_index* idx, int kind, int box_rows = 0) {
+static int ensure_shadow(lb_index* idx, int kind) {
     Shadow& sh = idx->shadow[kind];
-    int Dp = shadow_dp(idx, kind);
+    const int Dp = shadow_dp(idx, kind);
+    const int nkb = Dp / tc::KBLK;
     if (!idx->max_norm.p) {
         LB_TRY(idx->max_norm.ensure(3 * sizeof(float)));
         LB_CUDA_TRY(cudaMemsetAsync(idx->max_norm.p, 0, 3 * sizeof(float), idx->stream));
     }
+    const uint64_t need_tiles = ceil_div(idx->n, tc::BN);
+    if (need_tiles > sh.cap_tiles) {
+        // grow with head-room; the tiled image is rebuilt from the f32 rows (a derived structure, like the reference's
+        // lazily built caches that are dropped on append, flat_mmap.rs:341)
+        const uint64_t cap = std::max<uint64_t>(need_tiles, sh.cap_tiles + sh.cap_tiles / 2);
+        const uint64_t reserve_tiles = ceil_div(idx->rows.cap / row_bytes(idx), tc::BN);
+        const uint64_t want = std::max(cap, std::min<uint64_t>(reserve_tiles, need_tiles * 4));
+        const size_t bytes = (size_t)want * nkb * 2 * tc::HALF_BLOCK_BYTES;
+        sh.buf.release();
+        LB_TRY(sh.buf.ensure(bytes));
+        LB_CUDA_TRY(cudaMemsetAsync(sh.buf.p, 0, bytes, idx->stream));
+        sh.cap_tiles = want;
+        sh.rows = 0;
+    }
+    sh.Dp = Dp;
     if (sh.rows < idx->n) {
-        // keep a tile of slack rows so the last TMA box never leaves the allocation
-        LB_TRY(sh.buf.ensure(((size_t)idx->n + 128) * Dp * 2, true, idx->stream));
-        sh.Dp = Dp;
         uint64_t first = sh.rows, cnt = idx->n - first;
         const int warps = 8;
         tc::build_shadow_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
-            idx->rows.as<float>(), first, cnt, (int)idx->dim, Dp, kind, sh.buf.as<__nv_bfloat16>(),
-            idx->max_norm.as<float>() + kind);
+            idx->rows.as<float>(), first, cnt, (int)idx->dim, Dp, kind, sh.buf.as<unsigned char>(), idx->max_norm.as<float>() + kind);
         LB_CUDA_TRY(cudaGetLastError());
         sh.rows = idx->n;
     }
-    if (box_rows == 0) box_rows = tc_variant_bn(tc_tile_variant(Dp));
-    if (sh.tmap_rows != idx->n || sh.tmap_ptr != sh.buf.p || sh.tmap_bn != box_rows) {
-        PFN_encodeTiled enc = get_encode_tiled();
-        if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-        cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)idx->n};
-        cuuint64_t gstride[1] = {(cuuint64_t)Dp * 2};
-        cuuint32_t box[2] = {(cuuint32_t)tc::KBLK, (cuuint32_t)box_rows};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&sh.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sh.buf.p, gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-        sh.tmap_rows = idx->n;
+    if (sh.tmap_tiles != need_tiles || sh.tmap_ptr != sh.buf.p) {
+        const int rem = nkb % tc::KPS;
+        for (int kernel = 0; kernel < 2; ++kernel) {
+            const int halves = kernel == 0 ? 2 : 1;
+            LB_TRY(encode_shadow_map(&sh.tmap_full[kernel], sh.buf.p, nkb, need_tiles, halves, tc::KPS));
+            LB_TRY(encode_shadow_map(&sh.tmap_rem[kernel], sh.buf.p, nkb, need_tiles, halves, rem ? rem : 1));
+        }
+        sh.tmap_tiles = need_tiles;
         sh.tmap_ptr = sh.buf.p;
-        sh.tmap_bn = box_rows;
     }
     return LB_OK;
 }
@@ -425,25 +430,16 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
                   uint32_t* d_counts, float* dump) {
     const int kind = shadow_kind_for(metric);
     const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
-    int cluster = tc_cluster_size(n_mtiles);
-    // two or more query tiles: CTA pairs (tcgen05 cta_group::2, lb_tc2.cuh); LYNSE_B200_TC_PAIR=0 keeps the one-CTA kernel
-    const bool pair = cluster == 2 && tc_env_int("LYNSE_B200_TC_PAIR", 1) != 0;
-    if (pair) {
-        // clusters of 2 / 4 / 8 CTAs: a shadow tile is read from L2 once per cluster and multicast to its pairs
-        int cl = n_mtiles > 4 ? 8 : (n_mtiles > 2 ? 4 : 2);
-        const int env_cl = tc_env_int("LYNSE_B200_TC_CL", 0);
-        if (env_cl == 2 || env_cl == 4 || env_cl == 8) cl = env_cl;
-        cluster = cl;
-    }
-    const int variant = pair ? 0 : tc_tile_variant(shadow_dp(idx, kind));
-    const int BN = tc_variant_bn(variant);
-    LB_TRY(ensure_shadow(idx, kind, BN));
+    // one query tile: one CTA per partition (lb_tc1.cuh); more: CTA pairs (tcgen05 cta_group::2, lb_tc2.cuh)
+    const bool pair = n_mtiles >= 2;
+    const int cluster = pair ? 2 : 1;
+    const int BN = tc::BN;
+    LB_TRY(ensure_shadow(idx, kind));
     LB_TRY(refresh_small_segments(idx));
     Shadow& sh = idx->shadow[kind];
     const int Dp = sh.Dp;
     const int n_mgroups = (n_mtiles + cluster - 1) / cluster;
     const int nq_pad = n_mgroups * cluster * tc::BM;
-    LB_TRY(ensure_shadow(idx, kind, BN / cluster));  // tensor-map box = the rows one CTA fetches per K-block
     LB_TRY(idx->w_qb.ensure((size_t)nq_pad * Dp * 2));
     LB_TRY(idx->w_qnorm.ensure((size_t)nq * 4));
     {
@@ -455,33 +451,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     const uint32_t tiles_total = (uint32_t)ceil_div(idx->n, BN);
     // Slots: groups of n_mgroups co-resident clusters (one per query group) that stream the same row partitions in
     // lockstep, so every shadow tile comes from HBM once and is served to the other query groups of the slot from L2.
-    uint64_t G = (uint64_t)(idx->sm_count / cluster);  // clusters resident at once (one CTA per SM)
-    if (pair && cluster > 2) {
-        // clusters of 4 / 8 must fit inside a GPC: ask the driver how many can be co-resident
-        cudaLaunchConfig_t qcfg{};
-        qcfg.gridDim = dim3((unsigned)(idx->sm_count / cluster * cluster));
-        qcfg.blockDim = dim3(tc::NUM_THREADS);
-        qcfg.dynamicSmemBytes = tc::P_SMEM_BYTES;
-        cudaLaunchAttribute qattr[1];
-        qattr[0].id = cudaLaunchAttributeClusterDimension;
-        qattr[0].val.clusterDim.x = (unsigned)cluster;
-        qattr[0].val.clusterDim.y = 1;
-        qattr[0].val.clusterDim.z = 1;
-        qcfg.attrs = qattr;
-        qcfg.numAttrs = 1;
-        int n_active = 0;
-        cudaError_t qe;
-        if (cluster == 8) {
-            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::P_SMEM_BYTES));
-            qe = cudaOccupancyMaxActiveClusters(&n_active, tc::coarse_pair_kernel<0, 8>, &qcfg);
-        } else {
-            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::P_SMEM_BYTES));
-            qe = cudaOccupancyMaxActiveClusters(&n_active, tc::coarse_pair_kernel<0, 4>, &qcfg);
-        }
-        if (qe != cudaSuccess || n_active < 1) return fail(LB_CUDA, std::string("cudaOccupancyMaxActiveClusters: ") + cudaGetErrorString(qe));
-        G = (uint64_t)n_active;
-        idx->stats.n_fallback = 0;
-    }
+    const uint64_t G = (uint64_t)(idx->sm_count / cluster);  // clusters resident at once (one CTA per SM)
     uint64_t n_slots = std::max<uint64_t>(1, G / (uint64_t)n_mgroups);
     n_slots = std::min<uint64_t>(n_slots, tiles_total);
     n_slots = std::min<uint64_t>(n_slots, 4096 / tc::KP);
@@ -508,6 +478,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     a.nq = nq;
     a.n_mtiles = n_mtiles;
     a.Dp = Dp;
+    a.rem_kb = (Dp / tc::KBLK) % tc::KPS;
     a.n_rows = (uint32_t)idx->n;
     a.tiles_total = tiles_total;
     a.tiles_per_part = tiles_per_part;
@@ -526,6 +497,10 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     a.window = tc_env_int("LYNSE_B200_TC_WINDOW", 16);
     a.prefetch_tiles = tc_env_int("LYNSE_B200_TC_PREFETCH", 0);
     a.debug_mode = tc_env_int("LYNSE_B200_TC_DEBUG", 0);
+    // optional warm-up sample (LYNSE_B200_TC_SAMPLE tiles, scanned by every CTA before its partitions; off by default:
+    // with the compact slow path the open gate at the start of a partition no longer stalls the tensor pipe)
+    a.sample_tiles = 0;
+    if (a.share_floor && tiles_per_part >= 1024) a.sample_tiles = std::min<int>(tc_env_int("LYNSE_B200_TC_SAMPLE", 0), (int)tiles_total);
     a.prof = nullptr;
     const bool want_prof = getenv("LYNSE_B200_TC_PROF") != nullptr;
     if (want_prof) {
@@ -552,41 +527,15 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-#define LB_LAUNCH_TC(BNV, NB, CL)                                                                                          \
-    do {                                                                                                                   \
-        LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_topk_kernel<BNV, NB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)tc::SMEM_BYTES));                                                            \
-        if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);                                                         \
-        LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_topk_kernel<BNV, NB, CL>, sh.tmap, a));                            \
-    } while (0)
-#define LB_LAUNCH_PAIR(NKB, CLV)                                                                                          \
-    do {                                                                                                           \
-        cfg.dynamicSmemBytes = tc::P_SMEM_BYTES;                                                                   \
-        LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<NKB, CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)tc::P_SMEM_BYTES));                                                  \
-        if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);                                                 \
-        LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<NKB, CLV>, sh.tmap, a));                            \
-    } while (0)
     if (pair) {
-        if (cluster == 8) {
-            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<0, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            LB_LAUNCH_PAIR(0, 8);
-        } else if (cluster == 4) {
-            LB_LAUNCH_PAIR(0, 4);
-        } else {
-            LB_LAUNCH_PAIR(0, 2);
-        }
-    } else if (cluster == 1) {
-        if (variant == 0) LB_LAUNCH_TC(64, 2, 1);
-        else if (variant == 1) LB_LAUNCH_TC(128, 1, 1);
-        else LB_LAUNCH_TC(128, 2, 1);
+        LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
+        LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel, sh.tmap_full[1], sh.tmap_rem[1], a));
     } else {
-        if (variant == 0) LB_LAUNCH_TC(64, 2, 2);
-        else if (variant == 1) LB_LAUNCH_TC(128, 1, 2);
-        else LB_LAUNCH_TC(128, 2, 2);
+        LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
+        LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel, sh.tmap_full[0], sh.tmap_rem[0], a));
     }
-#undef LB_LAUNCH_TC
-#undef LB_LAUNCH_PAIR
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
 
@@ -641,6 +590,18 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
         LB_CUDA_TRY(cudaMemcpy(pr.data(), idx->w_prof.p, pr.size() * 8, cudaMemcpyDeviceToHost));
         double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int n_lead = 0, n_cta = 0;
+        if (pair) {
+            double sc[5] = {0, 0, 0, 0, 0};
+            double mx = 0;
+            for (int b = 1; b < grid && b < idx->sm_count; b += 2) {
+                for (int i = 0; i < 5; ++i) sc[i] += (double)pr[(size_t)b * 8 + i];
+                mx = std::max(mx, (double)pr[(size_t)b * 8 + 3]);
+                for (int i = 0; i < 6; ++i) pr[(size_t)b * 8 + i] = 0;
+            }
+            if (sc[4] > 0)
+                fprintf(stderr, "[lynse_b200] scan (one warp per odd CTA): %.0f cycles/tile, slow tiles %.3f/tile at %.0f cycles each, longest %.0f\n",
+                        sc[0] / sc[4], sc[2] / sc[4], sc[2] > 0 ? sc[1] / sc[2] : 0.0, mx);
+        }
         for (int b = 0; b < grid && b < idx->sm_count; ++b) {
             if (pr[(size_t)b * 8] > 0) {
                 ++n_lead;
@@ -1535,7 +1496,7 @@ int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uin
         DeviceGuard g(idx->device);
         int n_mtiles = ((int)nq + tc::BM - 1) / tc::BM;
         n_mtiles = (n_mtiles + 1) & ~1;  // room for the padded query tile of a 2-CTA cluster
-        const int dbg_bn = tc_variant_bn(tc_tile_variant(shadow_dp(idx, tc::SHADOW_IP)));
+        const int dbg_bn = tc::BN;
         const size_t ld = (size_t)ceil_div(n, dbg_bn) * dbg_bn;
         const size_t dump_elems = (size_t)n_mtiles * tc::BM * ld;
         const int k = (int)std::min<uint32_t>(n, 10);
