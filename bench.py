@@ -52,8 +52,8 @@ def parse_args():
     p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     p.add_argument("--rows", type=int, default=None, help="override corpus rows (development only)")
     p.add_argument("--nq", type=int, default=None)
-    p.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
-    p.add_argument("--cpu-sample-queries", type=int, default=16)
+    p.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
+    p.add_argument("--cpu-sample-queries", type=int, default=96)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--plan", default="auto", choices=["auto", "exact"])
     return p.parse_args()
@@ -69,6 +69,22 @@ def measured_peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic(args, world, nq):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this same command (profiles/r1_coarse_pair_ncu.json); None when the run is not the
+    captured configuration."""
+    if args.workload != "c2" or args.rows or args.nq or world != 1 or args.plan != "auto":
+        return None
+    try:
+        d = json.loads((ROOT / "profiles" / "r1_coarse_pair_ncu.json").read_text())["kernels"][0]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+        return {"bytes_per_launch": rd["value"] * mult[rd["unit"]] + wr["value"] * mult[wr["unit"]],
+                "source": "profiles/r1_coarse_pair_ncu.json (ncu --set full, one launch)"}
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -368,8 +384,8 @@ def main():
     if st["plan_used"] == 1 and dom_ms > 0:
         ach = flops_per_launch / (dom_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                    "kernel": "lb::tc::coarse_topk_kernel", "kernel_ms": dom_ms,
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(args, world, nq),
+                    "kernel": "lb::tc::coarse_pair_kernel" if nq > 128 else "lb::tc::coarse_single_kernel", "kernel_ms": dom_ms,
                     "peak_source": peaks["source"] + " (sustained bf16: the kernel is timed inside a long step)",
                     "hbm_gbs_of_kernel": st["algorithmic_bytes"] / (dom_ms * 1e-3) / 1e9}
     elif dom_ms > 0:

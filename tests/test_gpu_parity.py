@@ -302,12 +302,12 @@ def test_tc_uncertified_queries_fall_back_to_the_exact_scan(L, oracle):
     _check(oracle.store_batch_search(corpus, queries, 10, "ip", n_threads=1), got, "ip", 10)
 
 
-@pytest.mark.parametrize("cluster", ["1", "2"])
-@pytest.mark.parametrize("tile,nq", [("64", 150), ("128x1", 150), ("128", 150), ("64", 300), ("128", 300)])
-def test_tc_tile_variants_agree_with_oracle(L, oracle, tile, nq, cluster, monkeypatch):
-    monkeypatch.setenv("LYNSE_B200_TC_TILE", tile)
-    monkeypatch.setenv("LYNSE_B200_TC_CLUSTER", cluster)
-    n, dim, k = 33333, 320, 10
+# one query tile -> one-CTA kernel, more -> CTA-pair kernel; dims chosen so a tile is 1..12 K blocks, with and
+# without a partial last pipeline stage; row counts that leave a ragged last 64-row tile
+@pytest.mark.parametrize("nq", [1, 128, 129, 300, 1000])
+@pytest.mark.parametrize("n,dim", [(33333, 320), (4100, 64), (20011, 200), (9000, 768), (70001, 130)])
+def test_tc_kernels_agree_with_oracle(L, oracle, n, dim, nq):
+    k = 10
     corpus, queries = _data(n, dim, 97), _data(nq, dim, 98)
     with L.DeviceIndex(dim) as idx:
         idx.append(corpus)
@@ -316,6 +316,25 @@ def test_tc_tile_variants_agree_with_oracle(L, oracle, tile, nq, cluster, monkey
     want = oracle.store_batch_search(corpus, queries, k, "ip", n_threads=1)
     assert np.array_equal(want[0].astype(np.uint32), got[0])
     np.testing.assert_allclose(got[1], want[1], rtol=REL_TOL)
+
+
+def test_tc_shadow_follows_appends(L, oracle):
+    # the tiled shadow is a derived structure: it must track rows appended after a search (partial tiles included)
+    dim, k = 96, 10
+    parts = [_data(5000, dim, 201), _data(37, dim, 202), _data(9000, dim, 203)]
+    queries = _data(200, dim, 204)
+    with L.DeviceIndex(dim) as idx:
+        seen = []
+        for p in parts:
+            idx.append(p)
+            seen.append(p)
+            for metric in ("ip", "l2", "cosine"):
+                got = idx.search(queries, k, metric)
+                assert idx.last_stats()["plan_used"] == 1
+                want = oracle.store_batch_search(np.concatenate(seen), queries, k, metric,
+                                                 segment_rows=[len(np.concatenate(seen))], n_threads=1)
+                assert np.array_equal(want[0].astype(np.uint32), got[0]), metric
+                np.testing.assert_allclose(got[1], want[1], rtol=REL_TOL)
 
 
 def test_tc_and_exact_plans_agree(L):
