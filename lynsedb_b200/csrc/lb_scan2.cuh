@@ -1,0 +1,260 @@
+// lb_scan2.cuh — streaming exact scan for the 8-lane f32 metrics (IP, L2, cosine, L1, Chebyshev, Canberra,
+// Bray-Curtis): every corpus row is read ONCE per query tile and scored against up to 8 queries at a time.
+//
+// Replaces the same reference loops as lb_scan.cuh (fused_topk_ip_parallel / ip_scan_chunk_topk,
+// fused_topk_parallel, fused_topk_parallel_filtered, direct_access_topk — src/storage/flat_mmap.rs:4845-4982,
+// :5223-5274, :5439-5554) with the same per-pair arithmetic order as lb_metrics.cuh (i.e. as
+// src/distance/simd.rs's AVX2+FMA kernels): the eight AVX lanes are eight accumulators per (row, query), the
+// 8-float chunks are consumed in order, the horizontal reductions and the scalar tails follow the same tree.
+// What changes against lb_scan.cuh is the loop nest: lb_scan.cuh evaluates one whole pair at a time and so
+// re-reads the row (from L1) once per query; here the chunk loop is outermost and the accumulators of all the
+// queries of the tile live in registers, which is what lets a small batch run at HBM speed.
+#pragma once
+#include "lb_packed.cuh"
+
+namespace lb {
+
+constexpr int S2_ROWS = 256;   // rows per block step == threads per CTA
+
+__host__ __device__ inline bool scan2_supported(int metric) {
+    return metric == LB_IP || metric == LB_L2 || metric == LB_COSINE || metric == LB_MANHATTAN || metric == LB_CHEBYSHEV ||
+           metric == LB_CANBERRA || metric == LB_BRAY_CURTIS;
+}
+
+// state layout per (row, query): s[0..7] first accumulator vector, s[8..15] second (metrics that have one)
+// IP2: the launch may contain IP rows that take the two-accumulator (single-row) kernel — rows of segments under
+// 4096 rows, or the stateless operator; without it IP needs one accumulator vector only.
+template <int METRIC, bool IP2>
+struct Scan2Op {
+    static constexpr int kState = ((METRIC == LB_IP && IP2) || METRIC == LB_L2 || METRIC == LB_COSINE || METRIC == LB_BRAY_CURTIS) ? 16 : 8;
+    static constexpr int kTQ = 64 / kState;  // queries per tile: 64 accumulator registers per thread either way
+
+    // one 8-float chunk; `odd` = chunk index is odd; `two_acc` = IP rows that take the two-accumulator kernel
+    static __device__ __forceinline__ void step(float* s, const Vec8& q, const Vec8& c, bool odd, bool two_acc) {
+        if (METRIC == LB_IP) {
+            // batch-8 order: one accumulator (simd.rs:1450-1525); single-row order: even chunks -> acc0, odd -> acc1
+            // (simd.rs:1341-1396).  The trailing unpaired chunk has an even index, so it lands in acc0 as it must.
+            if (IP2 && two_acc && odd) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[8 + i] = fmaf(q.v[i], c.v[i], s[8 + i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] = fmaf(q.v[i], c.v[i], s[i]);
+            }
+        } else if (METRIC == LB_L2) {  // simd.rs:1527-1581
+            if (odd) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float d = q.v[i] - c.v[i];
+                    s[8 + i] = fmaf(d, d, s[8 + i]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float d = q.v[i] - c.v[i];
+                    s[i] = fmaf(d, d, s[i]);
+                }
+            }
+        } else if (METRIC == LB_COSINE) {  // simd.rs:1583-1636 (the query norm is the same chain for every row: done once)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s[i] = fmaf(q.v[i], c.v[i], s[i]);
+                s[8 + i] = fmaf(c.v[i], c.v[i], s[8 + i]);
+            }
+        } else if (METRIC == LB_MANHATTAN) {  // simd.rs:2134-2158
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = s[i] + fabsf(q.v[i] - c.v[i]);
+        } else if (METRIC == LB_CHEBYSHEV) {  // simd.rs:2715-2737
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = max_ps(s[i], fabsf(q.v[i] - c.v[i]));
+        } else if (METRIC == LB_CANBERRA) {  // simd.rs:2762-2793
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float num = fabsf(q.v[i] - c.v[i]);
+                const float den = fabsf(q.v[i]) + fabsf(c.v[i]);
+                const float quot = num / den;
+                s[i] = s[i] + ((den != 0.0f) ? quot : 0.0f);
+            }
+        } else {  // Bray-Curtis, simd.rs:2824-2865
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s[i] = s[i] + fabsf(q.v[i] - c.v[i]);
+                s[8 + i] = s[8 + i] + fabsf(q.v[i] + c.v[i]);
+            }
+        }
+    }
+
+    // horizontal reduction + scalar tail (elements [tail0, dim)) + final formula
+    static __device__ __forceinline__ float finish(float* s, const float* __restrict__ q /*smem*/, const float* __restrict__ c /*global*/,
+                                                   int tail0, int dim, bool two_acc, float q_norm2) {
+        if (METRIC == LB_IP) {
+            if (IP2 && two_acc) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] = s[i] + s[8 + i];
+            }
+            float out = hsum8(s);
+            for (int i = tail0; i < dim; ++i) out = out + q[i] * __ldg(c + i);
+            return out;
+        } else if (METRIC == LB_L2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = s[i] + s[8 + i];
+            float sum = hsum8(s);
+            for (int i = tail0; i < dim; ++i) {
+                const float diff = q[i] - __ldg(c + i);
+                sum = sum + diff * diff;
+            }
+            return sum;
+        } else if (METRIC == LB_COSINE) {
+            float dot = hsum8(s), nb = hsum8(s + 8), na = q_norm2;
+            for (int i = tail0; i < dim; ++i) {
+                const float a = q[i], b = __ldg(c + i);
+                dot = dot + a * b;
+                nb = nb + b * b;
+            }
+            const float denom = sqrtf(na * nb);
+            if (denom < 1e-30f) return 1.0f;
+            return 1.0f - dot / denom;
+        } else if (METRIC == LB_MANHATTAN) {
+            float sum = lane_sum8(s);
+            for (int i = tail0; i < dim; ++i) sum = sum + fabsf(q[i] - __ldg(c + i));
+            return sum;
+        } else if (METRIC == LB_CHEBYSHEV) {
+            float m = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m = rust_max(m, s[i]);
+            for (int i = tail0; i < dim; ++i) m = rust_max(m, fabsf(q[i] - __ldg(c + i)));
+            return m;
+        } else if (METRIC == LB_CANBERRA) {
+            float sum = lane_sum8(s);
+            for (int i = tail0; i < dim; ++i) {
+                const float a = q[i], b = __ldg(c + i);
+                const float den = fabsf(a) + fabsf(b);
+                if (den != 0.0f) sum = sum + fabsf(a - b) / den;
+            }
+            return sum;
+        } else {
+            float num = lane_sum8(s), den = lane_sum8(s + 8);
+            for (int i = tail0; i < dim; ++i) {
+                const float a = q[i], b = __ldg(c + i);
+                num = num + fabsf(a - b);
+                den = den + fabsf(a + b);
+            }
+            if (den == 0.0f) return num == 0.0f ? 0.0f : INFINITY;
+            return num / den;
+        }
+    }
+};
+
+// the query-side half of the cosine kernel (simd.rs:1583-1636): |q|^2 with the same lane order, once per query
+__device__ inline float cosine_query_norm2(const float* __restrict__ q /*smem*/, int dim) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int chunks = dim >> 3;
+    for (int j = 0; j < chunks; ++j) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaf(q[8 * j + i], q[8 * j + i], a[i]);
+    }
+    float na = hsum8(a);
+    for (int i = chunks * 8; i < dim; ++i) na = na + q[i] * q[i];
+    return na;
+}
+
+template <int METRIC, bool IP2>
+__global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
+    using Op = Scan2Op<METRIC, IP2>;
+    constexpr int S2_TQ = Op::kTQ;
+    constexpr bool ASC = METRIC != LB_IP;
+    extern __shared__ __align__(16) unsigned char smem_s2[];
+    const int dim = a.dim, dim_pad = (dim + 3) & ~3;
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_s2);                              // [TQ][256]
+    float* sq = reinterpret_cast<float*>(smem_s2 + S2_TQ * S2_ROWS * 8);                // [TQ][dim_pad]
+    uint64_t* sthr = reinterpret_cast<uint64_t*>(sq + S2_TQ * dim_pad);                 // [TQ]
+    uint32_t* scnt = reinterpret_cast<uint32_t*>(sthr + S2_TQ);                         // [TQ]
+    float* sna = reinterpret_cast<float*>(scnt + S2_TQ);                                // [TQ] cosine |q|^2
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int part = blockIdx.x;
+    const bool vec = (dim & 3) == 0;
+    const int chunks = dim >> 3;
+    const uint64_t part_begin = (uint64_t)part * a.rows_per_part;
+    uint64_t part_end = part_begin + a.rows_per_part;
+    if (part_end > a.n_rows) part_end = a.n_rows;
+    const bool single_tile = a.nq <= S2_TQ;
+
+    auto load_tile = [&](int q0, int tq) {
+        for (int i = tid; i < tq * dim; i += S2_ROWS) {
+            const int qq = i / dim, d = i - qq * dim;
+            sq[qq * dim_pad + d] = __ldg(a.queries + (size_t)(q0 + qq) * dim + d);
+        }
+        __syncthreads();
+        if (METRIC == LB_COSINE && tid < tq) sna[tid] = cosine_query_norm2(sq + tid * dim_pad, dim);
+    };
+    if (single_tile) load_tile(0, a.nq);
+
+    for (uint64_t blk = part_begin; blk < part_end; blk += S2_ROWS) {
+        const uint64_t slot = blk + tid;
+        bool valid = slot < part_end;
+        uint32_t row = 0;
+        if (valid) row = a.row_ids ? __ldg(a.row_ids + slot) : (uint32_t)slot;
+        if (valid && !row_allowed(a.allow_bits, row)) valid = false;
+        const float* c = a.corpus + (size_t)row * dim;
+        const bool two_acc = METRIC == LB_IP && (a.ip_single || (valid && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row)));
+        for (int q0 = 0; q0 < a.nq; q0 += S2_TQ) {
+            const int tq = min(S2_TQ, a.nq - q0);
+            if (!single_tile) {
+                __syncthreads();  // the previous tile's queries and candidates are no longer read
+                load_tile(q0, tq);
+            }
+            if (tid < tq) {
+                const size_t lq = (size_t)part * a.nq + (q0 + tid);
+                sthr[tid] = __ldcg(a.counts + lq) < (uint32_t)a.k ? KEY_NONE : __ldcg(a.thr + lq);
+                scnt[tid] = 0u;
+            }
+            __syncthreads();
+            if (valid) {
+                float st[S2_TQ][Op::kState];
+#pragma unroll
+                for (int t = 0; t < S2_TQ; ++t)
+#pragma unroll
+                    for (int i = 0; i < Op::kState; ++i) st[t][i] = 0.0f;
+                // chunk loop outermost: the row streams through registers once, one chunk ahead of the arithmetic
+                Vec8 cv = chunks > 0 ? load8<true>(c, vec) : Vec8{};
+                for (int j = 0; j < chunks; ++j) {
+                    Vec8 nx = cv;
+                    if (j + 1 < chunks) nx = load8<true>(c + 8 * (j + 1), vec);
+                    // one row per thread means one 128-byte line per thread in flight at a time: ask for the lines
+                    // two ahead so that enough bytes are outstanding to cover the HBM latency
+                    if ((j & 3) == 0 && j + 8 < chunks) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 8 * (j + 8)));
+#pragma unroll
+                    for (int t = 0; t < S2_TQ; ++t) {
+                        if (t < tq) {
+                            const Vec8 qv = load8<false>(sq + t * dim_pad + 8 * j, vec);  // broadcast
+                            Op::step(st[t], qv, cv, (j & 1) != 0, two_acc);
+                        }
+                    }
+                    cv = nx;
+                }
+#pragma unroll
+                for (int t = 0; t < S2_TQ; ++t) {
+                    if (t < tq) {
+                        const float v = Op::finish(st[t], sq + t * dim_pad, c, chunks * 8, dim, two_acc, METRIC == LB_COSINE ? sna[t] : 0.0f);
+                        const uint64_t key = make_key<ASC>(v, row);
+                        if (key < sthr[t]) {
+                            const uint32_t pos = atomicAdd(&scnt[t], 1u);
+                            cand[t * S2_ROWS + pos] = key;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int j = warp; j < tq; j += S2_ROWS / 32) {
+                const int n = (int)scnt[j];
+                if (n > 0) {
+                    const size_t lq = (size_t)part * a.nq + (q0 + j);
+                    warp_fold_candidates(cand + j * S2_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                }
+            }
+            if (single_tile) __syncthreads();  // candidates folded before the next block reuses the buffers
+        }
+    }
+}
+
+}  // namespace lb

@@ -21,6 +21,8 @@
 #include "lb_tc.cuh"
 #include "lb_tc1.cuh"
 #include "lb_tc2.cuh"
+#include "lb_packed.cuh"
+#include "lb_scan2.cuh"
 
 namespace lb {
 
@@ -85,6 +87,11 @@ static int next_pow2(int x) {
     while (p < x) p <<= 1;
     return p;
 }
+static int tc_env_int(const char* name, int dflt) {
+    const char* env = getenv(name);
+    return env && *env ? atoi(env) : dflt;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -233,10 +240,6 @@ static bool tc_supported(const lb_index* idx, int metric) {
     return shadow_dp(idx, shadow_kind_for(metric)) <= tc::MAX_DP;
 }
 
-static int tc_env_int(const char* name, int dflt) {
-    const char* env = getenv(name);
-    return env && *env ? atoi(env) : dflt;
-}
 
 static int encode_shadow_map(CUtensorMap* out, void* base, int nkb, uint64_t n_tiles, int box_halves, int box_kb) {
     PFN_encodeTiled enc = get_encode_tiled();
@@ -366,7 +369,32 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
     a.thr = idx->w_thr.as<uint64_t>();
     a.rows_per_part = sp.rows_per_part;
     if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
-    if (r.words) {
+    if (r.words && r.n_words == PK_W && r.row_ids == nullptr && tc_env_int("LYNSE_B200_PACKED_TMA", 1) != 0) {
+        // 1024-bit fingerprints: TMA-staged kernel (lb_packed.cuh)
+        PFN_encodeTiled enc = get_encode_tiled();
+        if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        CUtensorMap tmap;
+        cuuint64_t gdim[2] = {(cuuint64_t)PK_W, (cuuint64_t)r.n_rows};
+        cuuint64_t gstride[1] = {(cuuint64_t)PK_W * 8};
+        cuuint32_t box[2] = {(cuuint32_t)PK_W, (cuuint32_t)PK_ROWS};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<uint64_t*>(r.words), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled (packed rows) failed with CUresult " + std::to_string((int)cr));
+        const bool hs = tc_env_int("LYNSE_B200_PACKED_HS", 0) != 0;
+        const int mode = r.metric == LB_HAMMING ? 0 : (r.metric == LB_DICE ? 2 : 1);
+#define LB_LAUNCH_PK(MODE, HSV)                                                                                              \
+    do {                                                                                                                     \
+        LB_CUDA_TRY(cudaFuncSetAttribute(scan_packed16_kernel<MODE, HSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         (int)PK_SMEM_BYTES));                                                               \
+        scan_packed16_kernel<MODE, HSV><<<sp.P, PK_ROWS, PK_SMEM_BYTES, idx->stream>>>(tmap, a);                             \
+    } while (0)
+        if (mode == 0) { if (hs) LB_LAUNCH_PK(0, true); else LB_LAUNCH_PK(0, false); }
+        else if (mode == 1) { if (hs) LB_LAUNCH_PK(1, true); else LB_LAUNCH_PK(1, false); }
+        else { if (hs) LB_LAUNCH_PK(2, true); else LB_LAUNCH_PK(2, false); }
+#undef LB_LAUNCH_PK
+    } else if (r.words) {
         size_t smem = (size_t)SCAN_TQ * SCAN_THREADS * 8 + (size_t)SCAN_TQ * r.n_words * 8;
 #define LB_LAUNCH_PACKED(W)                                                                                      \
     do {                                                                                                         \
@@ -383,6 +411,28 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
             default: LB_LAUNCH_PACKED(0); break;
         }
 #undef LB_LAUNCH_PACKED
+    } else if (scan2_supported(r.metric) && r.row_stats == nullptr && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+               (size_t)8 * ((r.dim + 3) & ~3) * 4 + 8 * S2_ROWS * 8 + 256 <= 200 * 1024) {
+        // streaming scan: the row is read once per query tile (lb_scan2.cuh)
+        const int dim_pad = (r.dim + 3) & ~3;
+        const bool ip2 = r.ip_single || r.n_small > 0;
+#define LB_LAUNCH_S2(M, IP2V)                                                                                             \
+    do {                                                                                                                  \
+        constexpr int tqv = Scan2Op<M, IP2V>::kTQ;                                                                        \
+        const size_t smem = (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 + (size_t)tqv * 16 + 64;                \
+        LB_CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<M, IP2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        scan_stream_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(a);                                             \
+    } while (0)
+        switch (r.metric) {
+            case LB_IP: if (ip2) LB_LAUNCH_S2(LB_IP, true); else LB_LAUNCH_S2(LB_IP, false); break;
+            case LB_L2: LB_LAUNCH_S2(LB_L2, false); break;
+            case LB_COSINE: LB_LAUNCH_S2(LB_COSINE, false); break;
+            case LB_MANHATTAN: LB_LAUNCH_S2(LB_MANHATTAN, false); break;
+            case LB_CHEBYSHEV: LB_LAUNCH_S2(LB_CHEBYSHEV, false); break;
+            case LB_CANBERRA: LB_LAUNCH_S2(LB_CANBERRA, false); break;
+            default: LB_LAUNCH_S2(LB_BRAY_CURTIS, false); break;
+        }
+#undef LB_LAUNCH_S2
     } else {
         int dim_pad = (r.dim + 3) & ~3;
         size_t smem = (size_t)SCAN_TQ * SCAN_THREADS * 8 + (size_t)SCAN_TQ * dim_pad * 4;
@@ -455,10 +505,15 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     uint64_t n_slots = std::max<uint64_t>(1, G / (uint64_t)n_mgroups);
     n_slots = std::min<uint64_t>(n_slots, tiles_total);
     n_slots = std::min<uint64_t>(n_slots, 4096 / tc::KP);
-    // The union of the per-partition shortlists must reach well below rank k: aim at P*KP >= 32*k candidates.
+    // The certification needs the largest partition floor T (the KP-th best coarse score of one partition) to sit
+    // well below the k-th best score overall, so the union of the shortlists must reach far past rank k: aim at
+    // P*KP >= 32*k candidates (measured on C3, k = 100: P = 36 leaves 1385 of 1024 queries uncertified, P = 72
+    // five, P >= 144 none).  LYNSE_B200_TC_PARTS overrides.
     uint64_t parts_per_slot = 1;
     {
-        const uint64_t want = ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
+        uint64_t want = ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
+        const int env_parts = tc_env_int("LYNSE_B200_TC_PARTS", 0);
+        if (env_parts > 0) want = (uint64_t)env_parts;
         while (n_slots * parts_per_slot < want && n_slots * (parts_per_slot + 1) <= 4096 / tc::KP) ++parts_per_slot;
     }
     uint64_t P = std::min<uint64_t>(n_slots * parts_per_slot, tiles_total);
