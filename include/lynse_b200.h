@@ -77,6 +77,7 @@ typedef enum lb_plan {
 
 typedef struct lb_index lb_index;
 typedef struct lb_comm lb_comm;
+typedef struct lb_ivf lb_ivf;
 
 /* ---- library ----------------------------------------------------------- */
 const char* lb_last_error(void);
@@ -160,6 +161,24 @@ typedef struct lb_search_stats {
 } lb_search_stats;
 int lb_index_set_timing(lb_index* idx, int enabled);
 int lb_index_last_stats(const lb_index* idx, lb_search_stats* out);
+
+/* ---- IVF over one index ------------------------------------------------- */
+/* replaces IVFIndex::build (src/index/ivf.rs:132-179) = kmeans::train_for_metric (src/index/kmeans.rs:74-139:
+ * farthest-point seeding on a sample drawn with the seed-42 LCG, at most max_iter Lloyd steps — the reference
+ * passes 20 — assignment under the routing metric, which is L2 for the binary metrics, ivf.rs:80-87) +
+ * inverted_lists_from_assignments (kmeans.rs:317-345).  The rows stay in `idx`; rebuild after appends. */
+int lb_ivf_train(lb_index* idx, int metric, uint32_t n_clusters, uint32_t max_iter, lb_ivf** out);
+/* the same index from given centroids [n_centroids][dim] and per-row assignments [len(idx)] */
+int lb_ivf_create(lb_index* idx, int metric, const float* centroids, uint32_t n_centroids, const uint32_t* assignments,
+                  lb_ivf** out);
+void lb_ivf_destroy(lb_ivf* ivf);
+int lb_ivf_info(const lb_ivf* ivf, uint32_t* n_centroids, uint64_t* n_rows);
+int lb_ivf_centroids(const lb_ivf* ivf, float* out);         /* [n_centroids][dim] */
+int lb_ivf_assignments(const lb_ivf* ivf, uint32_t* out);    /* [n_rows] */
+/* replaces IVFIndex::search (src/index/ivf.rs:181-348) for a batch of queries; nprobe == 0 means 1.
+ * allow_bits: optional subset filter (SearchParams::subset), same layout as lb_index_search. */
+int lb_ivf_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, uint32_t nprobe, const uint64_t* allow_bits,
+                  uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts);
 
 /* ---- device / pinned memory helpers (bench + tests; no torch) ---------- */
 int lb_device_malloc(int device, uint64_t bytes, void** out);

@@ -67,6 +67,13 @@ SIGNATURES = {
     "lb_index_search_device": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "lb_index_set_timing": (C.c_int, [_vp, C.c_int]),
     "lb_index_last_stats": (C.c_int, [_vp, C.POINTER(SearchStats)]),
+    "lb_ivf_train": (C.c_int, [_vp, C.c_int, C.c_uint32, C.c_uint32, _vpp]),
+    "lb_ivf_create": (C.c_int, [_vp, C.c_int, _f32p, C.c_uint32, _u32p, _vpp]),
+    "lb_ivf_destroy": (None, [_vp]),
+    "lb_ivf_info": (C.c_int, [_vp, _u32p, _u64p]),
+    "lb_ivf_centroids": (C.c_int, [_vp, _f32p]),
+    "lb_ivf_assignments": (C.c_int, [_vp, _u32p]),
+    "lb_ivf_search": (C.c_int, [_vp, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, C.c_uint64, _u32p, _f32p, _u32p]),
     "lb_device_malloc": (C.c_int, [C.c_int, C.c_uint64, _vpp]),
     "lb_device_free": (C.c_int, [C.c_int, _vp]),
     "lb_host_malloc": (C.c_int, [C.c_uint64, _vpp]),

@@ -1,0 +1,503 @@
+"""VectorDBClient / Database / Collection — LynseDB's Python object model for the search path, on the B200 library.
+
+Keeps the names, arguments and return types of the reference for what lies on the path
+(python/lynse/__init__.py:12-323 ``VectorDBClient``; python/lynse/api/local_client.py:35-276 ``LocalClient``,
+:278-1420 ``LocalCollection``: ``add`` / ``commit`` / ``build_index`` / ``search`` / ``batch_search`` / ``delete`` /
+``restore`` / ``shape`` / ``index_mode``), and restates the engine's result post-processing around the scan
+(src/engine.rs:4718-4833): ``search_k = k + |tombstones|``, the scan of the un-flushed pending rows
+(``pending_search`` :3310-3360), ``merge_row_results`` (:3362-3419), row -> external id, ``filter_tombstoned_limit``
+(:3286-3308).  Rows live in HBM (``DeviceIndex``); the database is in-memory — persistence, WAL, metadata SQL,
+snapshots, HTTP and the other index families are outside this package.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _backend
+from . import metrics as M
+from .index import DeviceIndex, make_allow_bits
+from .ivf import DEFAULT_N_CLUSTERS, DEFAULT_NPROBE, IVFIndex
+from .result_view import ResultView
+
+PENDING_FLUSH_ROWS = 10_000          # src/engine.rs:93-94
+PENDING_FLUSH_BYTES = 32 << 20
+MAX_DATABASES = 64                   # python/lynse/__init__.py:128
+KNOWN_BUILD_KEYS = frozenset({"n_clusters", "n_centroids", "m", "ef_construction", "ef_search", "max_level", "r", "l",
+                              "alpha", "max_degree", "nprobe", "replica_count"})  # python/lynse/_index_build.py:49-66
+_DOMAIN_FREE = (M.IP, M.L2, M.COSINE, M.HAMMING, M.JACCARD)
+
+
+def _index_family(mode: str) -> str:
+    upper = mode.upper()
+    for fam in ("DISKANN", "HNSW", "SPANN", "IVF", "FLAT"):
+        if upper.startswith(fam):
+            return fam
+    return "FLAT"
+
+
+class Collection:
+    """``LocalCollection`` for the search path.  ``where`` accepts ``None``, a callable over the row's field dict, or a
+    dict of field == value conditions (the reference's SQL ``where`` strings need its metadata engine, out of scope)."""
+
+    def __init__(self, name: str, dim: Optional[int] = None, *, dtypes: str = "float32", default_index: Optional[str] = "FLAT-IP",
+                 description: Optional[str] = None, device: int = 0):
+        if dtypes != "float32":
+            raise ValueError("only dtypes='float32' is supported on this path (float16 storage is a next-round item)")
+        self.name = name
+        self.description = description
+        self._dim = int(dim) if dim else None
+        self._device = device
+        self._default_index = default_index
+        self._index_mode: Optional[str] = None
+        self._metric = M.IP
+        self._lock = threading.RLock()
+        self._store: Optional[DeviceIndex] = None
+        self._ivf: Optional[IVFIndex] = None
+        self._ivf_params: Dict[str, int] = {}
+        self._pending: List[np.ndarray] = []
+        self._pending_rows = 0
+        self._row_ids: List[Any] = []            # row -> external id (engine.rs:3071-3073)
+        self._id_rows: Dict[Any, int] = {}
+        self._fields: Dict[int, dict] = {}
+        self._tombstones: set = set()
+        self.COMMIT_FLAG = True
+
+    # ------------------------------------------------------------------ basics
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self) -> None:
+        with self._lock:
+            if self._ivf is not None:
+                self._ivf.close()
+                self._ivf = None
+            if self._store is not None:
+                self._store.close()
+                self._store = None
+
+    def exists(self) -> bool:
+        return True
+
+    @property
+    def shape(self):
+        return (len(self._row_ids), self._dim or 0)
+
+    @property
+    def index_mode(self) -> Optional[str]:
+        return self._index_mode
+
+    def max_id(self) -> int:
+        ints = [i for i in self._row_ids if isinstance(i, (int, np.integer)) and not isinstance(i, bool)]
+        return int(max(ints)) if ints else -1
+
+    def is_id_exists(self, id) -> bool:
+        return id in self._id_rows and id not in self._tombstones
+
+    def list_deleted_ids(self) -> list:
+        return sorted(self._tombstones, key=lambda x: (str(type(x)), x))
+
+    def stats(self) -> dict:
+        return {"name": self.name, "rows": len(self._row_ids), "dim": self._dim, "index_mode": self._index_mode,
+                "pending_rows": self._pending_rows, "deleted": len(self._tombstones),
+                "segments": self._store.segments() if self._store is not None else []}
+
+    # ------------------------------------------------------------------ ingest
+    def add(self, ids=None, *, vectors=None, documents=None, embed_func=None, fields=None, batch_size: int = 1000,
+            wire_dtype: str = "float32"):
+        del wire_dtype
+        if documents is not None or embed_func is not None:
+            raise NotImplementedError("document embedding is outside this package's scope; pass vectors")
+        if not isinstance(batch_size, int) or batch_size <= 0:
+            raise ValueError("batch_size must be a positive integer")
+        if vectors is None:
+            raise ValueError("add() requires vectors or documents")
+        vec = np.asarray(vectors, dtype=np.float32)
+        if vec.ndim == 1:
+            vec = vec.reshape(1, -1)
+        elif vec.ndim != 2:
+            raise ValueError("vectors must be a 1D vector or a 2D matrix")
+        vec = np.ascontiguousarray(vec, dtype=np.float32)
+        n = vec.shape[0]
+        if n == 0:
+            raise ValueError("vectors cannot be empty")
+        with self._lock:
+            if self._dim is None:
+                self._dim = int(vec.shape[1])
+            if vec.shape[1] != self._dim:
+                raise ValueError(f"Dimension mismatch: expected {self._dim}, got {vec.shape[1]}")
+            single = False
+            if ids is None:
+                start = self.max_id() + 1
+                ext = list(range(start, start + n))
+            else:
+                single = not isinstance(ids, (list, tuple, np.ndarray))
+                ext = [ids] if single else [i.item() if isinstance(i, np.generic) else i for i in ids]
+                if len(ext) != n:
+                    raise ValueError(f"ids length ({len(ext)}) must match vectors row count ({n})")
+                if len(set(ext)) != len(ext):
+                    raise ValueError("duplicate ids in one add() call")
+                for e in ext:
+                    if e in self._id_rows:
+                        raise ValueError(f"id {e!r} already exists; use upsert")
+            field_list = None
+            if fields is not None:
+                field_list = [fields] if isinstance(fields, dict) else list(fields)
+                if len(field_list) != n:
+                    raise ValueError(f"fields length ({len(field_list)}) must match vectors row count ({n})")
+            base = len(self._row_ids)
+            for j, e in enumerate(ext):
+                self._id_rows[e] = base + j
+                self._row_ids.append(e)
+                if field_list is not None and field_list[j] is not None:
+                    self._fields[base + j] = dict(field_list[j])
+            for s in range(0, n, batch_size):   # one add_items call per batch, as the reference client does
+                chunk = vec[s:s + batch_size]
+                self._pending.append(chunk)
+                self._pending_rows += chunk.shape[0]
+                if self._pending_rows >= PENDING_FLUSH_ROWS or self._pending_rows * self._dim * 4 >= PENDING_FLUSH_BYTES:
+                    self._flush_pending()
+            if self._ivf is not None:
+                self._ivf.close()
+                self._ivf = None        # lists are rebuilt over the new rows on the next search
+            self.COMMIT_FLAG = False
+        self._maybe_build_default_index()
+        if ids is None:
+            return ext[0] if n == 1 else ext
+        return ext[0] if single else ext
+
+    def _ensure_store(self) -> DeviceIndex:
+        if self._store is None:
+            if self._dim is None:
+                raise ValueError("collection dimension is not known yet")
+            self._store = DeviceIndex(self._dim, "float32", self._device)
+        return self._store
+
+    def _flush_pending(self) -> None:
+        """One flush == one ``VectorStore::append`` (never split across segments)."""
+        if not self._pending:
+            return
+        block = self._pending[0] if len(self._pending) == 1 else np.concatenate(self._pending, axis=0)
+        self._ensure_store().append(block)
+        self._pending = []
+        self._pending_rows = 0
+
+    def commit(self) -> None:
+        with self._lock:
+            self._flush_pending()
+            self.COMMIT_FLAG = True
+
+    flush = commit
+
+    def delete(self, ids) -> int:
+        """Tombstone ids (soft delete; ``search`` asks for ``k + |tombstones|`` and filters)."""
+        with self._lock:
+            ids = ids if isinstance(ids, (list, tuple, np.ndarray, set)) else [ids]
+            n = 0
+            for i in ids:
+                i = i.item() if isinstance(i, np.generic) else i
+                if i in self._id_rows and i not in self._tombstones:
+                    self._tombstones.add(i)
+                    n += 1
+            return n
+
+    def restore(self, ids) -> int:
+        with self._lock:
+            ids = ids if isinstance(ids, (list, tuple, np.ndarray, set)) else [ids]
+            n = 0
+            for i in ids:
+                i = i.item() if isinstance(i, np.generic) else i
+                if i in self._tombstones:
+                    self._tombstones.discard(i)
+                    n += 1
+            return n
+
+    # ------------------------------------------------------------------ index
+    def _maybe_build_default_index(self) -> None:
+        if self._index_mode is None and self._default_index and self._row_ids:
+            self.build_index(self._default_index)
+
+    def build_index(self, index_mode: str = "FLAT-IP", **kwargs) -> None:
+        """``build_index(index_mode, **kwargs)`` (local_client.py:701-845; src/engine.rs:4500-4660)."""
+        for key, value in kwargs.items():
+            if value is not None and key not in KNOWN_BUILD_KEYS:
+                raise ValueError(f"unknown index build parameter {key!r}; supported keys: {', '.join(sorted(KNOWN_BUILD_KEYS))}")
+        mode = str(index_mode).upper()
+        family = _index_family(mode)
+        if family not in ("FLAT", "IVF"):
+            raise ValueError(f"index family {family} is outside this package's scope (FLAT-* and IVF-* only)")
+        if mode in ("FLAT", "IVF"):
+            raise ValueError(f"unknown index type '{index_mode}'")       # bare family names are rejected (src/index/mod.rs:827-836)
+        metric = M.from_index_mode(mode)
+        if metric is None:
+            raise ValueError(f"unknown index type '{index_mode}'")
+        if family == "IVF" and metric not in _DOMAIN_FREE and metric not in (M.TANIMOTO, M.DICE):
+            raise ValueError(f"unsupported index/metric combination '{index_mode}'")
+        if any(tok in mode.split("-") for tok in ("SQ8", "PQ", "RABITQ", "POLARVEC")):
+            raise ValueError(f"quantized index '{index_mode}' is outside this package's scope")
+        with self._lock:
+            if self._dim is not None and not M.accepts_dimension(metric, self._dim):
+                raise ValueError(f"metric '{M.NAMES[metric]}' requires dimension 2 as [longitude_degrees, latitude_degrees]")
+            if self._ivf is not None:
+                self._ivf.close()
+                self._ivf = None
+            self._metric = metric
+            self._index_mode = mode
+            self._ivf_params = {}
+            if family == "IVF":
+                n_clusters = kwargs.get("n_clusters") or kwargs.get("n_centroids") or DEFAULT_N_CLUSTERS
+                self._ivf_params = {"n_clusters": int(n_clusters), "nprobe": int(kwargs.get("nprobe") or DEFAULT_NPROBE)}
+                self._flush_pending()
+                self._build_ivf()
+            elif self._store is not None and len(self._store):
+                self._store.prepare(metric)
+
+    def _build_ivf(self) -> None:
+        if self._store is None or len(self._store) == 0:
+            return
+        self._ivf = IVFIndex(self._store, self._metric, n_clusters=self._ivf_params["n_clusters"],
+                             nprobe=self._ivf_params["nprobe"])
+
+    def remove_index(self, field_name: str = "default") -> None:
+        with self._lock:
+            if self._ivf is not None:
+                self._ivf.close()
+            self._ivf = None
+            self._index_mode = None
+            self._metric = M.IP
+
+    # ------------------------------------------------------------------ search
+    def _subset_rows(self, where, filter_ids) -> Optional[np.ndarray]:
+        if where is None and filter_ids is None:
+            return None
+        rows = None
+        if filter_ids is not None:
+            rows = {self._id_rows[i] for i in filter_ids if i in self._id_rows}
+        if where is not None:
+            if isinstance(where, str):
+                raise NotImplementedError("SQL where-strings need the reference's metadata engine; pass a callable or a dict")
+            pred: Callable[[dict], bool]
+            if isinstance(where, dict):
+                cond = dict(where)
+                pred = lambda f: all(f.get(k) == v for k, v in cond.items())  # noqa: E731
+            else:
+                pred = where
+            matched = {r for r in range(len(self._row_ids)) if pred(self._fields.get(r, {}))}
+            rows = matched if rows is None else rows & matched
+        return np.fromiter(sorted(rows), dtype=np.uint64, count=len(rows))
+
+    def _search_rows(self, q: np.ndarray, search_k: int, nprobe: int, subset: Optional[np.ndarray]):
+        """(rows, dists) per query over flushed + pending rows, before id mapping: scan, pending_search, merge_row_results."""
+        nq = q.shape[0]
+        n_store = len(self._store) if self._store is not None else 0
+        out: List[tuple] = [(np.empty(0, np.uint64), np.empty(0, np.float32)) for _ in range(nq)]
+        if n_store and search_k > 0:
+            allow = None
+            if subset is not None:
+                allow = make_allow_bits(n_store, subset[subset < n_store])
+            if self._index_mode and self._index_mode.startswith("IVF"):
+                if self._ivf is None:
+                    self._build_ivf()
+                rows, dists, counts = self._ivf.search(q, search_k, nprobe, allow)
+            else:
+                rows, dists, counts = self._store.search(q, search_k, self._metric, allow)
+            out = [(rows[i, :int(counts[i])].astype(np.uint64), dists[i, :int(counts[i])].copy()) for i in range(nq)]
+        if self._pending_rows and search_k > 0:
+            block = self._pending[0] if len(self._pending) == 1 else np.concatenate(self._pending, axis=0)
+            offsets = np.arange(n_store, n_store + block.shape[0], dtype=np.uint64)
+            if subset is not None:
+                keep = np.isin(offsets, subset)
+                block, offsets = np.ascontiguousarray(block[keep]), offsets[keep]
+            if block.shape[0]:
+                asc = M.is_ascending(self._metric)
+                for i in range(nq):
+                    pi, pd = _backend.top_k_search(q[i], block, M.NAMES[self._metric], search_k)   # pending_search
+                    out[i] = _merge_row_results(out[i][0], out[i][1], offsets[pi], pd, search_k, asc)
+        return out
+
+    def _finish(self, rows: np.ndarray, dists: np.ndarray, k: int, return_fields: bool) -> ResultView:
+        ids, keep = [], []
+        for j, r in enumerate(rows):                      # row_to_user_id + filter_tombstoned_limit
+            e = self._row_ids[int(r)]
+            if e in self._tombstones:
+                continue
+            ids.append(e)
+            keep.append(j)
+            if len(ids) == k:
+                break
+        d = dists[keep] if keep else np.empty(0, np.float32)
+        all_int = all(isinstance(i, (int, np.integer)) and not isinstance(i, bool) for i in ids)
+        id_arr = np.asarray(ids, dtype=np.int64) if all_int else np.asarray(ids, dtype=object)
+        flds = [dict(self._fields.get(int(rows[j]), {})) for j in keep] if return_fields else []
+        idx_type, dist_name = M.parse_index_mode(self._index_mode or "FLAT-IP")
+        return ResultView(ids=id_arr, distances=np.asarray(d, dtype=np.float32), fields=flds, k=len(ids), distance=dist_name,
+                          index=idx_type, result_type="search")
+
+    def search(self, vector=None, k: int = 10, *, document=None, embed_func=None, where=None, return_fields: bool = False,
+               vector_field: str = "default", reranker=None, rerank_k=None, rerank_with_fields: bool = False, nprobe: int = 10,
+               approx: bool = False, eps: float = 1e-4, wire_dtype: str = "float32", filter_ids: Optional[Iterable] = None
+               ) -> ResultView:
+        del wire_dtype, approx, eps, rerank_with_fields   # approx: the exact GPU scan supersedes the CPU shortlist heuristics
+        if (vector is None) == (document is None):
+            raise ValueError("search() requires exactly one of vector or document")
+        if document is not None or embed_func is not None or reranker is not None or rerank_k is not None:
+            raise NotImplementedError("document search and external rerankers are outside this package's scope")
+        if vector_field != "default":
+            raise NotImplementedError("named vector fields are outside this package's scope")
+        return self.batch_search(np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1), k, where=where,
+                                 return_fields=return_fields, nprobe=nprobe, filter_ids=filter_ids)[0]
+
+    def batch_search(self, vectors, k: int = 10, *, where=None, return_fields: bool = False, nprobe: int = 10, reranker=None,
+                     rerank_k=None, rerank_with_fields: bool = False, wire_dtype: str = "float32",
+                     filter_ids: Optional[Iterable] = None) -> List[ResultView]:
+        del wire_dtype, rerank_with_fields
+        if reranker is not None or rerank_k is not None:
+            raise NotImplementedError("external rerankers are outside this package's scope")
+        q = np.ascontiguousarray(vectors, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        k = int(k)
+        with self._lock:
+            if self._dim is None or not self._row_ids:      # empty collection: empty result, not an error
+                return [self._finish(np.empty(0, np.uint64), np.empty(0, np.float32), k, return_fields) for _ in range(q.shape[0])]
+            if q.shape[1] != self._dim:
+                raise ValueError(f"Dimension mismatch: expected {self._dim}, got {q.shape[1]}")
+            subset = self._subset_rows(where, filter_ids)
+            search_k = k + len(self._tombstones)             # engine.rs:4735-4741
+            per_query = self._search_rows(q, search_k, int(nprobe), subset)
+            return [self._finish(r, d, k, return_fields) for (r, d) in per_query]
+
+    def __repr__(self) -> str:
+        return f"Collection(name={self.name!r}, shape={self.shape}, index_mode={self._index_mode!r})"
+
+
+def _merge_row_results(l_rows, l_d, r_rows, r_d, limit: int, ascending: bool):
+    """``Collection::merge_row_results`` (src/engine.rs:3362-3419): best score per row, sort by (score, row), truncate."""
+    if len(r_rows) == 0:
+        return l_rows, l_d
+    if len(l_rows) == 0:
+        return np.asarray(r_rows, np.uint64), np.asarray(r_d, np.float32)
+    best: Dict[int, float] = {}
+    for r, d in zip(l_rows.tolist(), l_d.tolist()):
+        best[r] = d
+    for r, d in zip(np.asarray(r_rows).tolist(), np.asarray(r_d).tolist()):
+        if r not in best or (d < best[r] if ascending else d > best[r]):
+            best[r] = d
+    pairs = sorted(best.items(), key=(lambda p: (p[1], p[0])) if ascending else (lambda p: (-p[1], p[0])))[:limit]
+    return np.asarray([p[0] for p in pairs], np.uint64), np.asarray([p[1] for p in pairs], np.float32)
+
+
+class Database:
+    """``LocalClient``: the collections of one database."""
+
+    def __init__(self, manager: "VectorDBClient", database_name: str):
+        self._manager = manager
+        self.database_name = database_name
+
+    @property
+    def _colls(self) -> Dict[str, Collection]:
+        return self._manager._dbs[self.database_name]
+
+    def require_collection(self, collection: str, dim: Optional[int] = None, n_threads: Optional[int] = 10, warm_up: bool = False,
+                           drop_if_exists: bool = False, description: Optional[str] = None, dtypes: str = "float32",
+                           default_index: Optional[str] = "FLAT-IP") -> Collection:
+        del n_threads, warm_up
+        if drop_if_exists and collection in self._colls:
+            self.drop_collection(collection)
+        if collection not in self._colls:
+            self._colls[collection] = Collection(collection, dim, dtypes=dtypes, default_index=default_index,
+                                                 description=description, device=self._manager._device)
+        coll = self._colls[collection]
+        if dim is not None and coll._dim is not None and int(dim) != coll._dim:
+            raise ValueError(f"collection {collection!r} has dimension {coll._dim}, not {dim}")
+        return coll
+
+    def get_collection(self, collection: str, warm_up: bool = True) -> Collection:
+        del warm_up
+        if collection not in self._colls:
+            raise ValueError(f"Collection '{collection}' does not exist.")
+        return self._colls[collection]
+
+    def drop_collection(self, collection: str) -> None:
+        coll = self._colls.pop(collection, None)
+        if coll is not None:
+            coll.close()
+
+    def show_collections(self) -> List[str]:
+        return sorted(self._colls)
+
+    def show_collections_details(self) -> List[dict]:
+        return [self._colls[c].stats() for c in self.show_collections()]
+
+    def database_exists(self) -> bool:
+        return self.database_name in self._manager._dbs
+
+    def drop_database(self) -> None:
+        self._manager.drop_database(self.database_name)
+
+    def __repr__(self) -> str:
+        return f"Database(name={self.database_name!r}, collections={self.show_collections()})"
+
+
+class VectorDBClient:
+    """``VectorDBClient(uri=None)``: local, in-memory databases whose vectors live on one B200 (``device``)."""
+
+    def __init__(self, uri: Union[str, None] = None, api_key: Optional[str] = None, read_only: bool = False, device: int = 0):
+        del api_key
+        if uri is not None and str(uri).startswith(("http://", "https://")):
+            raise NotImplementedError("the HTTP client is outside this package's scope")
+        if read_only:
+            raise NotImplementedError("read_only opens persisted storage, which is outside this package's scope")
+        self._uri = None if uri is None else str(uri)
+        self._device = int(device)
+        self._dbs: Dict[str, Dict[str, Collection]] = {}
+
+    def create_database(self, database_name: str, drop_if_exists: bool = False) -> Database:
+        if len(self._dbs) >= MAX_DATABASES and database_name not in self._dbs:
+            raise ValueError("The maximum number of databases created is 64.")
+        if drop_if_exists and database_name in self._dbs:
+            self.drop_database(database_name)
+        self._dbs.setdefault(database_name, {})
+        return Database(self, database_name)
+
+    def create_collection(self, database_name: str, collection: str, dim: Optional[int] = None, n_threads: Optional[int] = 10,
+                          warm_up: bool = False, drop_if_exists: bool = False, description: Optional[str] = None,
+                          dtypes: str = "float32", default_index: Optional[str] = "FLAT-IP",
+                          drop_database_if_exists: bool = False) -> Collection:
+        if drop_database_if_exists or database_name not in self._dbs:
+            db = self.create_database(database_name, drop_if_exists=drop_database_if_exists)
+        else:
+            db = self.get_database(database_name)
+        return db.require_collection(collection=collection, dim=dim, n_threads=n_threads, warm_up=warm_up,
+                                     drop_if_exists=drop_if_exists, description=description, dtypes=dtypes,
+                                     default_index=default_index)
+
+    def get_database(self, database_name: str) -> Database:
+        if database_name not in self._dbs:
+            raise ValueError(f"{database_name} does not exist.")
+        return Database(self, database_name)
+
+    def list_databases(self) -> List[str]:
+        return sorted(self._dbs)
+
+    def drop_database(self, database_name: str) -> None:
+        for coll in self._dbs.pop(database_name, {}).values():
+            coll.close()
+
+    def close(self) -> None:
+        for name in list(self._dbs):
+            self.drop_database(name)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __repr__(self) -> str:
+        return f"VectorDBClient(uri={self._uri!r}, databases={self.list_databases()})"

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_packed_kernel(ScanArgs a) {
     for (uint64_t blk = part_begin; blk < part_end; blk += SCAN_THREADS) {
         uint64_t slot = blk + tid;
         bool valid = slot < part_end;
-        uint32_t row = valid ? (uint32_t)slot : 0;
+        uint32_t row = 0;
+        if (valid) row = a.row_ids ? __ldg(a.row_ids + slot) : (uint32_t)slot;
         if (valid && !row_allowed(a.allow_bits, row)) valid = false;
         const uint64_t* rw = a.words + (size_t)row * nw;
         uint64_t r[W > 0 ? W : 1];

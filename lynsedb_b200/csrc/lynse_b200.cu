@@ -23,6 +23,7 @@
 #include "lb_tc2.cuh"
 #include "lb_packed.cuh"
 #include "lb_scan2.cuh"
+#include "lb_ivf.cuh"
 
 namespace lb {
 
@@ -1271,6 +1272,344 @@ int lb_device_memset(int device, void* dst, int value, uint64_t bytes) {
     LB_CUDA_TRY(cudaMemset(dst, value, bytes));
     return LB_OK;
 }
+
+}  // extern "C"
+
+// ---- IVF: k-means build + probe / gather / score search (src/index/ivf.rs, src/index/kmeans.rs) ---------------------------------
+struct lb_ivf {
+    lb_index* idx = nullptr;     // the rows (not owned)
+    lb_index* cidx = nullptr;    // centroids as a tiny index (owned): centroid ranking is one more exact scan
+    int metric = 0, routing = 0;
+    uint32_t nc = 0;
+    uint64_t n = 0;              // rows covered by the lists
+    std::vector<float> centroids;
+    std::vector<uint32_t> assignments, offsets, members;
+    DevBuf d_ids, d_q, d_qw, d_rows, d_dists, d_counts;
+};
+
+namespace lb {
+namespace {
+struct FastRng {  // kmeans.rs:21-48
+    uint64_t s;
+    double next_f64() {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        return (double)(s >> 33) / (double)(1ull << 31);
+    }
+};
+__global__ void ivf_copy_indexed_kernel(const float* src, int dim, const uint32_t* index, float* dst) {
+    const uint32_t r = *index;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) dst[d] = src[(size_t)r * dim + d];
+}
+void build_lists(lb_ivf* ivf) {  // inverted_lists_from_assignments (kmeans.rs:317-345): members in row order
+    ivf->offsets.assign(ivf->nc + 1, 0);
+    for (uint32_t c : ivf->assignments) ivf->offsets[c + 1]++;
+    for (uint32_t c = 0; c < ivf->nc; ++c) ivf->offsets[c + 1] += ivf->offsets[c];
+    ivf->members.resize(ivf->assignments.size());
+    std::vector<uint32_t> cur(ivf->offsets.begin(), ivf->offsets.end() - 1);
+    for (uint32_t i = 0; i < (uint32_t)ivf->assignments.size(); ++i) ivf->members[cur[ivf->assignments[i]]++] = i;
+}
+int ivf_finish(lb_ivf* ivf) {  // centroid index for the routing scan
+    LB_TRY(lb_index_create(&ivf->cidx, ivf->idx->dim, LB_F32, ivf->idx->device));
+    LB_TRY(lb_index_append_f32(ivf->cidx, ivf->centroids.data(), ivf->nc));
+    build_lists(ivf);
+    return LB_OK;
+}
+}  // namespace
+}  // namespace lb
+
+extern "C" {
+
+void lb_ivf_destroy(lb_ivf* ivf) {
+    if (!ivf) return;
+    if (ivf->idx) {
+        DeviceGuard g(ivf->idx->device);
+        DevBuf* bufs[] = {&ivf->d_ids, &ivf->d_q, &ivf->d_qw, &ivf->d_rows, &ivf->d_dists, &ivf->d_counts};
+        for (DevBuf* b : bufs) b->release();
+    }
+    if (ivf->cidx) lb_index_destroy(ivf->cidx);
+    delete ivf;
+}
+
+int lb_ivf_create(lb_index* idx, int metric, const float* centroids, uint32_t n_centroids, const uint32_t* assignments, lb_ivf** out) {
+    if (!idx || !out || !centroids || !assignments) return fail(LB_INVALID_ARGUMENT, "null argument");
+    LB_TRY(check_metric(metric));
+    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "IVF is built over f32 rows");
+    if (n_centroids == 0 || idx->n == 0) return fail(LB_INVALID_ARGUMENT, "IVF needs rows and centroids");
+    lb_ivf* ivf = new lb_ivf();
+    ivf->idx = idx;
+    ivf->metric = metric;
+    ivf->routing = metric_binary(metric) ? LB_L2 : metric;  // ivf.rs:80-87
+    ivf->nc = n_centroids;
+    ivf->n = idx->n;
+    ivf->centroids.assign(centroids, centroids + (size_t)n_centroids * idx->dim);
+    ivf->assignments.assign(assignments, assignments + idx->n);
+    for (uint32_t a : ivf->assignments)
+        if (a >= n_centroids) {
+            delete ivf;
+            return fail(LB_INVALID_ARGUMENT, "assignment out of range");
+        }
+    int st = ivf_finish(ivf);
+    if (st != LB_OK) {
+        lb_ivf_destroy(ivf);
+        return st;
+    }
+    *out = ivf;
+    return LB_OK;
+}
+
+int lb_ivf_train(lb_index* idx, int metric, uint32_t n_clusters, uint32_t max_iter, lb_ivf** out) {
+    if (!idx || !out) return fail(LB_INVALID_ARGUMENT, "null argument");
+    LB_TRY(check_metric(metric));
+    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "IVF is built over f32 rows");
+    if (idx->n == 0 || n_clusters == 0) return fail(LB_INVALID_ARGUMENT, "IVF needs rows and at least one cluster");
+    if (metric == LB_HAVERSINE && idx->dim != 2) return fail(LB_INVALID_ARGUMENT, "haversine requires dimension 2");
+    const int routing = metric_binary(metric) ? LB_L2 : metric;
+    const uint64_t n = idx->n;
+    const int dim = (int)idx->dim;
+    const uint32_t nc = (uint32_t)std::min<uint64_t>(n_clusters, n);
+    lb_ivf* ivf = new lb_ivf();
+    ivf->idx = idx;
+    ivf->metric = metric;
+    ivf->routing = routing;
+    ivf->nc = nc;
+    ivf->n = n;
+    int st = LB_OK;
+    {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        DeviceGuard g(idx->device);
+        cudaStream_t sm = idx->stream;
+        DevBuf d_cent, d_sample, d_sidx, d_minr, d_best, d_assign, d_off, d_mem;
+        auto body = [&]() -> int {
+            // ---- kmeans_pp_init_metric: farthest-point seeding on a seeded sample (kmeans.rs:141-196)
+            FastRng rng{42};
+            uint64_t sample_n = std::min<uint64_t>(n, std::min<uint64_t>(std::max<uint64_t>((uint64_t)nc * 32, 2048), 10000));
+            std::vector<uint32_t> sidx;
+            if (sample_n >= n) {
+                sidx.resize(n);
+                for (uint64_t i = 0; i < n; ++i) sidx[i] = (uint32_t)i;
+            } else {
+                std::vector<uint32_t> all(n);
+                for (uint64_t i = 0; i < n; ++i) all[i] = (uint32_t)i;
+                for (uint64_t i = 0; i < sample_n; ++i) {
+                    uint64_t j = i + std::min<uint64_t>((uint64_t)(rng.next_f64() * (double)(n - i)), n - i - 1);
+                    std::swap(all[i], all[j]);
+                }
+                sidx.assign(all.begin(), all.begin() + sample_n);
+            }
+            sample_n = sidx.size();
+            LB_TRY(d_cent.ensure((size_t)nc * dim * 4));
+            LB_TRY(d_sample.ensure((size_t)sample_n * dim * 4));
+            LB_TRY(d_sidx.ensure((size_t)sample_n * 4));
+            LB_TRY(d_minr.ensure((size_t)sample_n * 4));
+            LB_TRY(d_best.ensure(4));
+            LB_CUDA_TRY(cudaMemcpyAsync(d_sidx.p, sidx.data(), (size_t)sample_n * 4, cudaMemcpyHostToDevice, sm));
+            ivf_gather_rows_kernel<<<(unsigned)ceil_div(sample_n * dim, 256), 256, 0, sm>>>(idx->rows.as<float>(), dim, d_sidx.as<uint32_t>(),
+                                                                                          (uint32_t)sample_n, d_sample.as<float>());
+            std::vector<float> big(sample_n, 3.402823466e+38f);
+            LB_CUDA_TRY(cudaMemcpyAsync(d_minr.p, big.data(), (size_t)sample_n * 4, cudaMemcpyHostToDevice, sm));
+            const uint32_t first = (uint32_t)((uint64_t)(rng.next_f64() * (double)sample_n) % sample_n);
+            LB_CUDA_TRY(cudaMemcpyAsync(d_cent.p, d_sample.as<float>() + (size_t)first * dim, (size_t)dim * 4, cudaMemcpyDeviceToDevice, sm));
+            for (uint32_t c = 1; c < nc; ++c) {
+                ivf_farthest_kernel<<<1, 1024, 0, sm>>>(d_sample.as<float>(), (uint32_t)sample_n, dim, d_cent.as<float>() + (size_t)(c - 1) * dim,
+                                                       routing, d_minr.as<float>(), d_best.as<uint32_t>());
+                ivf_copy_indexed_kernel<<<1, 256, 0, sm>>>(d_sample.as<float>(), dim, d_best.as<uint32_t>(), d_cent.as<float>() + (size_t)c * dim);
+            }
+            LB_CUDA_TRY(cudaGetLastError());
+            // ---- Lloyd iterations (kmeans.rs:96-131)
+            LB_TRY(d_assign.ensure((size_t)n * 4));
+            LB_TRY(d_off.ensure((size_t)(nc + 1) * 4));
+            LB_TRY(d_mem.ensure((size_t)n * 4));
+            ivf->assignments.assign(n, 0xFFFFFFFFu);
+            ivf->centroids.resize((size_t)nc * dim);
+            std::vector<uint32_t> fresh(n);
+            std::vector<float> old_c((size_t)nc * dim);
+            for (uint32_t it = 0; it < max_iter; ++it) {
+                ivf_assign_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, sm>>>(idx->rows.as<float>(), n, dim, d_cent.as<float>(), (int)nc, routing,
+                                                                               d_assign.as<uint32_t>());
+                LB_CUDA_TRY(cudaGetLastError());
+                LB_CUDA_TRY(cudaMemcpyAsync(fresh.data(), d_assign.p, (size_t)n * 4, cudaMemcpyDeviceToHost, sm));
+                LB_CUDA_TRY(cudaMemcpyAsync(old_c.data(), d_cent.p, old_c.size() * 4, cudaMemcpyDeviceToHost, sm));
+                LB_CUDA_TRY(cudaStreamSynchronize(sm));
+                const bool changed = fresh != ivf->assignments;
+                ivf->assignments = fresh;
+                build_lists(ivf);
+                LB_CUDA_TRY(cudaMemcpyAsync(d_off.p, ivf->offsets.data(), (size_t)(nc + 1) * 4, cudaMemcpyHostToDevice, sm));
+                LB_CUDA_TRY(cudaMemcpyAsync(d_mem.p, ivf->members.data(), (size_t)n * 4, cudaMemcpyHostToDevice, sm));
+                ivf_centroid_update_kernel<<<nc, 256, 0, sm>>>(idx->rows.as<float>(), dim, d_off.as<uint32_t>(), d_mem.as<uint32_t>(), d_cent.as<float>());
+                LB_CUDA_TRY(cudaGetLastError());
+                // empty clusters are re-seeded from the largest one, in centroid order (kmeans.rs:118-126)
+                uint32_t max_c = 0, max_count = 0;
+                bool any_empty = false;
+                for (uint32_t c = 0; c < nc; ++c) {
+                    const uint32_t cnt = ivf->offsets[c + 1] - ivf->offsets[c];
+                    if (cnt >= max_count) {  // max_by_key keeps the last maximum
+                        max_count = cnt;
+                        max_c = c;
+                    }
+                    any_empty |= cnt == 0;
+                }
+                if (any_empty && max_count > 1) {
+                    std::vector<float> new_c((size_t)nc * dim);
+                    LB_CUDA_TRY(cudaMemcpyAsync(new_c.data(), d_cent.p, new_c.size() * 4, cudaMemcpyDeviceToHost, sm));
+                    LB_CUDA_TRY(cudaStreamSynchronize(sm));
+                    for (uint32_t c = 0; c < nc; ++c) {
+                        if (ivf->offsets[c + 1] != ivf->offsets[c]) continue;
+                        const float* src = (max_c < c ? new_c.data() : old_c.data()) + (size_t)max_c * dim;
+                        for (int d = 0; d < dim; ++d) new_c[(size_t)c * dim + d] = src[d] * (1.0f + 1e-4f * (float)d);
+                    }
+                    LB_CUDA_TRY(cudaMemcpyAsync(d_cent.p, new_c.data(), new_c.size() * 4, cudaMemcpyHostToDevice, sm));
+                    LB_CUDA_TRY(cudaStreamSynchronize(sm));
+                }
+                if (!changed) break;
+            }
+            ivf_assign_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, sm>>>(idx->rows.as<float>(), n, dim, d_cent.as<float>(), (int)nc, routing,
+                                                                           d_assign.as<uint32_t>());
+            LB_CUDA_TRY(cudaGetLastError());
+            LB_CUDA_TRY(cudaMemcpyAsync(ivf->assignments.data(), d_assign.p, (size_t)n * 4, cudaMemcpyDeviceToHost, sm));
+            LB_CUDA_TRY(cudaMemcpyAsync(ivf->centroids.data(), d_cent.p, ivf->centroids.size() * 4, cudaMemcpyDeviceToHost, sm));
+            LB_CUDA_TRY(cudaStreamSynchronize(sm));
+            return LB_OK;
+        };
+        st = body();
+        DevBuf* bufs[] = {&d_cent, &d_sample, &d_sidx, &d_minr, &d_best, &d_assign, &d_off, &d_mem};
+        for (DevBuf* b : bufs) b->release();
+    }
+    if (st == LB_OK) st = ivf_finish(ivf);
+    if (st != LB_OK) {
+        lb_ivf_destroy(ivf);
+        return st;
+    }
+    *out = ivf;
+    return LB_OK;
+}
+
+int lb_ivf_info(const lb_ivf* ivf, uint32_t* n_centroids, uint64_t* n_rows) {
+    if (!ivf) return fail(LB_INVALID_ARGUMENT, "ivf is null");
+    if (n_centroids) *n_centroids = ivf->nc;
+    if (n_rows) *n_rows = ivf->n;
+    return LB_OK;
+}
+int lb_ivf_centroids(const lb_ivf* ivf, float* out) {
+    if (!ivf || !out) return fail(LB_INVALID_ARGUMENT, "null argument");
+    memcpy(out, ivf->centroids.data(), ivf->centroids.size() * 4);
+    return LB_OK;
+}
+int lb_ivf_assignments(const lb_ivf* ivf, uint32_t* out) {
+    if (!ivf || !out) return fail(LB_INVALID_ARGUMENT, "null argument");
+    memcpy(out, ivf->assignments.data(), ivf->assignments.size() * 4);
+    return LB_OK;
+}
+
+// IVFIndex::search (src/index/ivf.rs:181-348): rank centroids with the routing metric, gather the nprobe nearest
+// lists (whole lists, in probe order), apply the subset filter (an empty probe falls back to the filtered corpus,
+// never to an unfiltered scan), score every candidate with compute_distance_f32 / the packed kernels, keep the k best.
+int lb_ivf_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, uint32_t nprobe, const uint64_t* allow_bits,
+                  uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    if (!ivf || !out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "null argument");
+    if (nq && !queries) return fail(LB_INVALID_ARGUMENT, "queries is null");
+    lb_index* idx = ivf->idx;
+    if (idx->n != ivf->n) return fail(LB_INVALID_ARGUMENT, "the index changed since the IVF lists were built; rebuild the index");
+    if (k > (uint32_t)MAX_K) return fail(LB_UNSUPPORTED, "k above 2048 is not supported");
+    if (allow_bits && allow_words < (ivf->n + 63) / 64) return fail(LB_INVALID_ARGUMENT, "row filter is shorter than the index");
+    for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+    for (size_t i = 0; i < (size_t)nq * k; ++i) {
+        out_rows[i] = ROW_NONE;
+        out_dists[i] = NAN;
+    }
+    if (nq == 0 || k == 0) return LB_OK;
+    const int dim = (int)idx->dim;
+    const uint32_t np = std::min<uint32_t>(std::max<uint32_t>(nprobe, 1), ivf->nc);
+    // 1. centroid ranking for every query: one exact scan over the centroid index (ties keep centroid order, as the
+    //    reference's stable sort does)
+    std::vector<uint32_t> probe((size_t)nq * np), pcount(nq);
+    std::vector<float> pd((size_t)nq * np);
+    {
+        lb_index* c = ivf->cidx;
+        std::lock_guard<std::mutex> lock(c->mu);
+        DeviceGuard g(c->device);
+        LB_TRY(c->w_queries.ensure((size_t)nq * dim * 4));
+        LB_TRY(c->w_out_rows.ensure((size_t)nq * np * 4));
+        LB_TRY(c->w_out_dists.ensure((size_t)nq * np * 4));
+        LB_TRY(c->w_out_counts.ensure((size_t)nq * 4));
+        LB_CUDA_TRY(cudaMemcpyAsync(c->w_queries.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, c->stream));
+        ScanRequest r;
+        r.corpus = c->rows.as<float>();
+        r.n_rows = ivf->nc;
+        r.dim = dim;
+        r.queries = c->w_queries.as<float>();
+        r.nq = (int)nq;
+        r.k = (int)np;
+        r.metric = ivf->routing;
+        r.ip_single = 1;
+        r.out_rows = c->w_out_rows.as<uint32_t>();
+        r.out_dists = c->w_out_dists.as<float>();
+        r.out_counts = c->w_out_counts.as<uint32_t>();
+        LB_TRY(run_scan(c, r, nullptr, nullptr));
+        LB_CUDA_TRY(cudaMemcpyAsync(probe.data(), c->w_out_rows.p, probe.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        LB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    // 2. per query: gather, score, select
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    const bool binary = metric_binary(ivf->metric);
+    const int nw = (dim + 63) / 64;
+    if (binary) LB_TRY(ensure_packed(idx));
+    auto allowed = [&](uint32_t r) { return allow_bits == nullptr || ((allow_bits[r >> 6] >> (r & 63)) & 1ull); };
+    std::vector<uint32_t> cand;
+    for (uint32_t q = 0; q < nq; ++q) {
+        cand.clear();
+        for (uint32_t p = 0; p < np; ++p) {
+            const uint32_t c = probe[(size_t)q * np + p];
+            if (c >= ivf->nc) continue;
+            for (uint32_t m = ivf->offsets[c]; m < ivf->offsets[c + 1]; ++m)
+                if (allowed(ivf->members[m])) cand.push_back(ivf->members[m]);
+        }
+        if (cand.empty())
+            for (uint32_t r = 0; r < (uint32_t)ivf->n; ++r)
+                if (allowed(r)) cand.push_back(r);
+        if (cand.empty()) continue;
+        const uint32_t kk = (uint32_t)std::min<size_t>(k, cand.size());
+        LB_TRY(ivf->d_ids.ensure(cand.size() * 4));
+        LB_TRY(ivf->d_q.ensure((size_t)dim * 4));
+        LB_TRY(ivf->d_rows.ensure((size_t)kk * 4));
+        LB_TRY(ivf->d_dists.ensure((size_t)kk * 4));
+        LB_TRY(ivf->d_counts.ensure(4));
+        LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_ids.p, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice, idx->stream));
+        LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_q.p, queries + (size_t)q * dim, (size_t)dim * 4, cudaMemcpyHostToDevice, idx->stream));
+        ScanRequest r;
+        r.n_rows = cand.size();
+        r.row_ids = ivf->d_ids.as<uint32_t>();
+        r.nq = 1;
+        r.k = (int)kk;
+        r.metric = ivf->metric;
+        r.out_rows = ivf->d_rows.as<uint32_t>();
+        r.out_dists = ivf->d_dists.as<float>();
+        r.out_counts = ivf->d_counts.as<uint32_t>();
+        if (binary) {
+            LB_TRY(ivf->d_qw.ensure((size_t)nw * 8));
+            pack_binary_kernel<<<1, 32, 0, idx->stream>>>(ivf->d_q.as<float>(), 1, dim, nw, 0.5f, ivf->d_qw.as<uint64_t>());
+            LB_CUDA_TRY(cudaGetLastError());
+            r.words = idx->packed.as<uint64_t>();
+            r.n_words = nw;
+            r.qwords = ivf->d_qw.as<uint64_t>();
+        } else {
+            r.corpus = idx->rows.as<float>();
+            r.dim = dim;
+            r.queries = ivf->d_q.as<float>();
+            r.ip_single = 1;  // compute_distance_f32 -> the single-row IP kernel
+        }
+        LB_TRY(run_scan(idx, r, nullptr, nullptr));
+        LB_CUDA_TRY(cudaMemcpyAsync(out_rows + (size_t)q * k, ivf->d_rows.p, (size_t)kk * 4, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaMemcpyAsync(out_dists + (size_t)q * k, ivf->d_dists.p, (size_t)kk * 4, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaMemcpyAsync(out_counts + q, ivf->d_counts.p, 4, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
+    return LB_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- NCCL (resolved at run time so the library loads on boxes without it) ----------------------------------------------------
 namespace {

@@ -68,6 +68,11 @@ def lib():
         L.lo_packed_batch_search.restype = None
         L.lo_packed_batch_search.argtypes = [u64p, C.c_uint64, C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_int,
                                              C.c_int, u64p, f32p, u32p]
+        L.lo_kmeans_train.restype = C.c_uint32
+        L.lo_kmeans_train.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, f32p, u32p]
+        L.lo_ivf_search.restype = C.c_uint32
+        L.lo_ivf_search.argtypes = [f32p, C.c_uint64, C.c_uint64, f32p, C.c_uint32, u32p, f32p, C.c_uint32, C.c_uint32,
+                                    C.c_int, u64p, u32p, f32p]
         L.lo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -196,3 +201,30 @@ def packed_batch_search(data_words, query_words, k, metric, n_threads=None):
                                  n_threads or host_threads(), _p(ids, C.c_uint64), _p(dists, C.c_float),
                                  _p(counts, C.c_uint32))
     return ids, dists, counts
+
+
+def kmeans_train(data, n_clusters, metric, max_iter=20):
+    """kmeans::train_for_metric (src/index/kmeans.rs:74-139) -> (centroids[nc,dim] f32, assignments[n] u32)."""
+    d = _f32(data)
+    n, dim = d.shape
+    cent = np.zeros((max(n_clusters, 1), dim), dtype=np.float32)
+    assign = np.zeros(max(n, 1), dtype=np.uint32)
+    nc = lib().lo_kmeans_train(_p(d, C.c_float), n, dim, n_clusters, max_iter, metric_id(metric), _p(cent, C.c_float),
+                               _p(assign, C.c_uint32))
+    return cent[:nc].copy(), assign[:n].copy()
+
+
+def ivf_search(data, centroids, assignments, query, k, nprobe, metric, allow_bits=None):
+    """IVFIndex::search (src/index/ivf.rs:181-348, no quantizer) for one query -> (u32 rows, f32 dists)."""
+    d, c, q = _f32(data), _f32(centroids), _f32(query).ravel()
+    a = np.ascontiguousarray(assignments, dtype=np.uint32)
+    n, dim = d.shape
+    ids = np.empty(max(k, 1), dtype=np.uint32)
+    dists = np.empty(max(k, 1), dtype=np.float32)
+    ab = None
+    if allow_bits is not None:
+        allow = np.ascontiguousarray(allow_bits, dtype=np.uint64)
+        ab = _p(allow, C.c_uint64)
+    cnt = lib().lo_ivf_search(_p(d, C.c_float), n, dim, _p(c, C.c_float), c.shape[0], _p(a, C.c_uint32), _p(q, C.c_float),
+                              k, nprobe, metric_id(metric), ab, _p(ids, C.c_uint32), _p(dists, C.c_float))
+    return ids[:cnt].copy(), dists[:cnt].copy()

@@ -941,6 +941,170 @@ std::vector<Pair> top_k_search(const float* q, const float* cands, size_t n, siz
     return pairs;
 }
 
+// ---- src/index/kmeans.rs — IVF k-means (farthest-point init on a seeded sample + Lloyd) ----------------
+// kmeans.rs:21-48
+struct FastRng {
+    uint64_t s;
+    explicit FastRng(uint64_t seed) : s(seed) {}
+    double next_f64() {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        return (double)(s >> 33) / (double)(1ull << 31);
+    }
+    std::vector<size_t> sample_indices(size_t n, size_t count) {
+        count = std::min(count, n);
+        std::vector<size_t> idx(n);
+        for (size_t i = 0; i < n; ++i) idx[i] = i;
+        for (size_t i = 0; i < count; ++i) {
+            size_t j = i + std::min((size_t)(next_f64() * (double)(n - i)), n - i - 1);
+            std::swap(idx[i], idx[j]);
+        }
+        idx.resize(count);
+        return idx;
+    }
+};
+inline size_t adaptive_init_sample_size(size_t n, size_t k) {  // kmeans.rs:50-53
+    size_t v = std::min<size_t>(std::max<size_t>(k * 32, 2048), 10000);
+    return std::min(n, v);
+}
+// kmeans.rs:237-264 — first best under strict <
+void assign_metric(const float* data, size_t n, const float* centroids, size_t dim, size_t nc, int metric, uint32_t* out) {
+    bool asc = is_ascending(metric);
+    for (size_t i = 0; i < n; ++i) {
+        size_t best = 0;
+        float best_rank = std::numeric_limits<float>::max();
+        for (size_t c = 0; c < nc; ++c) {
+            float raw = compute_distance(data + i * dim, centroids + c * dim, dim, metric);
+            float rank = asc ? raw : -raw;
+            if (rank < best_rank) {
+                best_rank = rank;
+                best = c;
+            }
+        }
+        out[i] = (uint32_t)best;
+    }
+}
+// kmeans.rs:141-196
+std::vector<float> kmeans_pp_init(const float* data, size_t n, size_t dim, size_t k, int metric) {
+    FastRng rng(42);
+    size_t sample_n = adaptive_init_sample_size(n, k);
+    std::vector<size_t> sidx;
+    if (sample_n >= n) {
+        sidx.resize(n);
+        for (size_t i = 0; i < n; ++i) sidx[i] = i;
+    } else {
+        sidx = rng.sample_indices(n, sample_n);
+    }
+    sample_n = sidx.size();
+    std::vector<float> sample(sample_n * dim);
+    for (size_t i = 0; i < sample_n; ++i) memcpy(&sample[i * dim], data + sidx[i] * dim, dim * 4);
+    bool asc = is_ascending(metric);
+    std::vector<float> centroids(k * dim, 0.0f);
+    size_t first = (size_t)(rng.next_f64() * (double)sample_n) % sample_n;
+    memcpy(&centroids[0], &sample[first * dim], dim * 4);
+    std::vector<float> min_ranks(sample_n, std::numeric_limits<float>::max());
+    for (size_t c = 1; c < k; ++c) {
+        const float* prev = &centroids[(c - 1) * dim];
+        for (size_t i = 0; i < sample_n; ++i) {
+            float raw = compute_distance(&sample[i * dim], prev, dim, metric);
+            float rank = asc ? raw : -raw;
+            if (rank < min_ranks[i]) min_ranks[i] = rank;
+        }
+        // Iterator::max_by keeps the LAST of several equal maxima
+        size_t best = 0;
+        for (size_t i = 1; i < sample_n; ++i)
+            if (!(min_ranks[i] < min_ranks[best])) best = i;
+        memcpy(&centroids[c * dim], &sample[best * dim], dim * 4);
+    }
+    return centroids;
+}
+// kmeans.rs:74-139 (centroid sums in row order, the n < 8192 branch of accumulate_centroid_sums :266-315; the
+// parallel fold/reduce branch for larger n is order-dependent in the reference itself)
+size_t kmeans_train(const float* data, size_t n, size_t dim, size_t requested, size_t max_iter, int metric,
+                    std::vector<float>& centroids, std::vector<uint32_t>& assignments) {
+    size_t nc = std::min(requested, n);
+    centroids.clear();
+    assignments.clear();
+    if (n == 0 || nc == 0 || dim == 0) return 0;
+    centroids = kmeans_pp_init(data, n, dim, nc, metric);
+    assignments.assign(n, 0xFFFFFFFFu);
+    std::vector<uint32_t> fresh(n);
+    for (size_t it = 0; it < max_iter; ++it) {
+        assign_metric(data, n, centroids.data(), dim, nc, metric, fresh.data());
+        bool changed = fresh != assignments;
+        assignments = fresh;
+        std::vector<float> sums(nc * dim, 0.0f);
+        std::vector<uint32_t> counts(nc, 0);
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t c = assignments[i];
+            counts[c] += 1;
+            for (size_t d = 0; d < dim; ++d) sums[c * dim + d] += data[i * dim + d];
+        }
+        size_t max_c = 0;
+        uint32_t max_count = 0;
+        for (size_t c = 0; c < nc; ++c)  // max_by_key keeps the last maximum
+            if (counts[c] >= max_count) {
+                max_count = counts[c];
+                max_c = c;
+            }
+        for (size_t c = 0; c < nc; ++c) {
+            if (counts[c] > 0) {
+                float inv = 1.0f / (float)counts[c];
+                for (size_t d = 0; d < dim; ++d) centroids[c * dim + d] = sums[c * dim + d] * inv;
+            } else if (max_count > 1) {
+                for (size_t d = 0; d < dim; ++d) centroids[c * dim + d] = centroids[max_c * dim + d] * (1.0f + 1e-4f * (float)d);
+            }
+        }
+        if (!changed) break;
+    }
+    assign_metric(data, n, centroids.data(), dim, nc, metric, assignments.data());
+    return nc;
+}
+
+// ---- src/index/ivf.rs:181-348 — IVFIndex::search without a quantizer ---------------------------------------
+// ids are row positions; `allow` (optional) is the subset filter as a row bitset.
+std::vector<Pair> ivf_search(const float* data, size_t n, size_t dim, const float* centroids, size_t nc,
+                             const uint32_t* assignments, const float* query, size_t k, size_t nprobe, int metric,
+                             const uint64_t* allow) {
+    if (n == 0) return {};
+    nprobe = std::max<size_t>(nprobe, 1);
+    bool asc = is_ascending(metric), binary = is_binary(metric);
+    int routing = binary ? L2 : metric;  // ivf.rs:80-87
+    bool rasc = is_ascending(routing);
+    std::vector<std::pair<float, size_t>> cd(nc);
+    for (size_t c = 0; c < nc; ++c) cd[c] = {compute_distance(query, centroids + c * dim, dim, routing), c};
+    std::stable_sort(cd.begin(), cd.end(), [rasc](const auto& a, const auto& b) { return rasc ? a.first < b.first : a.first > b.first; });
+    // inverted lists in row order (kmeans.rs:317-345)
+    std::vector<std::vector<uint32_t>> lists(nc);
+    for (size_t i = 0; i < n; ++i) lists[assignments[i]].push_back((uint32_t)i);
+    auto allowed = [&](uint32_t r) { return allow == nullptr || ((allow[r >> 6] >> (r & 63)) & 1ull); };
+    std::vector<uint32_t> cand;
+    for (size_t p = 0; p < std::min(nprobe, nc); ++p)
+        for (uint32_t r : lists[cd[p].second])
+            if (allowed(r)) cand.push_back(r);
+    if (cand.empty())
+        for (size_t r = 0; r < n; ++r)
+            if (allowed((uint32_t)r)) cand.push_back((uint32_t)r);
+    if (cand.empty()) return {};
+    size_t pool = std::min(k, cand.size());
+    std::vector<Pair> scored(cand.size());
+    if (binary) {
+        size_t words = (dim + 63) / 64;
+        std::vector<uint64_t> pq(words), pr(words);
+        pack_row(query, dim, pq.data(), words, 0.5f);
+        for (size_t i = 0; i < cand.size(); ++i) {
+            pack_row(data + (size_t)cand[i] * dim, dim, pr.data(), words, 0.5f);
+            scored[i] = {packed_distance(pq.data(), pr.data(), words, metric), (uint32_t)i};
+        }
+    } else {
+        for (size_t i = 0; i < cand.size(); ++i) scored[i] = {compute_distance(query, data + (size_t)cand[i] * dim, dim, metric), (uint32_t)i};
+    }
+    quickselect_k(scored, pool, asc);
+    scored.resize(pool);
+    std::stable_sort(scored.begin(), scored.end(), [asc](const Pair& a, const Pair& b) { return asc ? a.d < b.d : a.d > b.d; });
+    for (auto& p : scored) p.i = cand[p.i];
+    return scored;
+}
+
 }  // namespace
 
 // =============================== C ABI =======================================
@@ -1048,6 +1212,31 @@ void lo_packed_batch_search(const uint64_t* data, uint64_t words, uint64_t n, co
             dists[q * k + i] = res[i].dist;
         }
     }
+}
+
+// kmeans::train_for_metric; returns the number of centroids (min(requested, n))
+uint32_t lo_kmeans_train(const float* data, uint64_t n, uint64_t dim, uint32_t requested, uint32_t max_iter, int metric,
+                         float* centroids_out /*[requested][dim]*/, uint32_t* assignments_out /*[n]*/) {
+    std::vector<float> c;
+    std::vector<uint32_t> a;
+    size_t nc = kmeans_train(data, n, dim, requested, max_iter, metric, c, a);
+    if (nc) {
+        memcpy(centroids_out, c.data(), nc * dim * 4);
+        memcpy(assignments_out, a.data(), n * 4);
+    }
+    return (uint32_t)nc;
+}
+
+// IVFIndex::search for one query given centroids and assignments
+uint32_t lo_ivf_search(const float* data, uint64_t n, uint64_t dim, const float* centroids, uint32_t nc,
+                       const uint32_t* assignments, const float* query, uint32_t k, uint32_t nprobe, int metric,
+                       const uint64_t* allow_bits, uint32_t* ids, float* dists) {
+    auto res = ivf_search(data, n, dim, centroids, nc, assignments, query, k, nprobe, metric, allow_bits);
+    for (size_t i = 0; i < res.size(); ++i) {
+        ids[i] = res[i].i;
+        dists[i] = res[i].d;
+    }
+    return (uint32_t)res.size();
 }
 
 int lo_max_threads(void) { return omp_get_max_threads(); }

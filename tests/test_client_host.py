@@ -1,0 +1,160 @@
+"""Host-side logic of the Collection object model (no GPU): id mapping, tombstones, pending rows, merge rules,
+build_index validation.  The device index is replaced by a numpy stand-in with the same method surface, so only the
+Python layer (the restated engine post-processing, src/engine.rs:3286-3419, :4718-4833) is under test here."""
+import numpy as np
+import pytest
+
+import lynsedb_b200.client as client_mod
+from lynsedb_b200 import metrics as M
+from lynsedb_b200.client import Collection, VectorDBClient, _merge_row_results
+
+
+class FakeIndex:
+    """numpy brute force with DeviceIndex's surface: (score best-first, row ascending)."""
+
+    def __init__(self, dim, dtype="float32", device=0):
+        self.dim = dim
+        self.rows = np.empty((0, dim), np.float32)
+        self.appends = []
+
+    def __len__(self):
+        return self.rows.shape[0]
+
+    def append(self, block):
+        self.appends.append(block.shape[0])
+        self.rows = np.concatenate([self.rows, block])
+
+    def segments(self):
+        return list(self.appends)
+
+    def prepare(self, metric):
+        pass
+
+    def close(self):
+        pass
+
+    def search(self, q, k, metric, allow_bits=None):
+        assert metric in (M.IP, M.L2)
+        nq, n = q.shape[0], len(self)
+        rows = np.full((nq, k), 0xFFFFFFFF, np.uint32)
+        dists = np.full((nq, k), np.nan, np.float32)
+        counts = np.zeros(nq, np.uint32)
+        for i in range(nq):
+            s = self.rows @ q[i] if metric == M.IP else ((self.rows - q[i]) ** 2).sum(1)
+            cand = np.arange(n)
+            if allow_bits is not None:
+                ok = np.array([(int(allow_bits[r >> 6]) >> (r & 63)) & 1 for r in range(n)], bool)
+                cand = cand[ok]
+            order = sorted(cand.tolist(), key=lambda r: ((-s[r]) if metric == M.IP else s[r], r))[:k]
+            counts[i] = len(order)
+            rows[i, :len(order)] = order
+            dists[i, :len(order)] = s[order]
+        return rows, dists, counts
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    monkeypatch.setattr(client_mod, "DeviceIndex", FakeIndex)
+
+    def fake_topk(query, block, metric, k):
+        s = block @ query if metric == "ip" else ((block - query) ** 2).sum(1)
+        order = np.argsort(-s if metric == "ip" else s, kind="stable")[:k]
+        return order.astype(np.uint32), s[order].astype(np.float32)
+
+    monkeypatch.setattr(client_mod._backend, "top_k_search", fake_topk)
+
+
+def test_client_object_model(fake):
+    c = VectorDBClient()
+    coll = c.create_collection("db", "docs", dim=4)
+    assert c.list_databases() == ["db"] and c.get_database("db").show_collections() == ["docs"]
+    assert coll.index_mode is None and coll.shape == (0, 4)
+    with pytest.raises(ValueError):
+        c.get_database("nope")
+    r = coll.search(np.ones(4, np.float32), k=3)          # empty collection -> empty result, not an error
+    assert len(r) == 0 and r.distance_metric == "IP" and r.index_type == "Flat"
+    ids = coll.add(vectors=np.eye(4, dtype=np.float32))
+    assert ids == [0, 1, 2, 3] and coll.index_mode == "FLAT-IP"      # default index auto-built after the first write
+    assert coll.add(vectors=[0, 0, 0, 2.0]) == 4
+    assert coll.add("x", vectors=[0, 0, 3.0, 0]) == "x"
+    with pytest.raises(ValueError):
+        coll.add("x", vectors=[1, 0, 0, 0])
+    with pytest.raises(ValueError):
+        coll.add(vectors=np.ones((1, 5), np.float32))
+    ids_, d, f = coll.search([0, 0, 1.0, 1.0], k=3)        # tuple-unpacks as (ids, distances, fields)
+    assert list(ids_) == ["x", 4, 2] and ids_.dtype == object and np.allclose(d, [3, 2, 1]) and f == []
+    c.close()
+
+
+def test_pending_rows_are_searchable_and_flush_thresholds(fake):
+    coll = Collection("c", 8)
+    rng = np.random.default_rng(1)
+    a = rng.random((9000, 8), dtype=np.float32)
+    coll.add(vectors=a, batch_size=4000)
+    assert coll.stats()["pending_rows"] == 9000 and coll.stats()["segments"] == []       # below 10 000 rows / 32 MiB
+    q = rng.random(8, dtype=np.float32)
+    want = np.argsort(-(a @ q), kind="stable")[:5]
+    assert list(coll.search(q, k=5).ids) == want.tolist()                                 # un-committed rows are found
+    coll.add(vectors=rng.random((2000, 8), dtype=np.float32), batch_size=1000)
+    assert coll.stats()["segments"] == [10000] and coll.stats()["pending_rows"] == 1000   # one flush at the threshold
+    coll.commit()
+    assert coll.stats()["segments"] == [10000, 1000] and coll.COMMIT_FLAG    # (the stand-in records appends, not segments)
+
+
+def test_tombstones_ask_for_k_plus_deleted_and_refill(fake):
+    coll = Collection("c", 2, default_index="FLAT-L2")
+    pts = np.array([[i, 0] for i in range(10)], np.float32)
+    coll.add(vectors=pts)
+    coll.commit()
+    assert list(coll.search([0, 0], k=3).ids) == [0, 1, 2]
+    assert coll.delete([0, 1]) == 2 and not coll.is_id_exists(0)
+    r = coll.search([0, 0], k=3)
+    assert list(r.ids) == [2, 3, 4] and np.allclose(r.distances, [4, 9, 16])             # refilled past the tombstones
+    assert coll.restore(0) == 1 and list(coll.search([0, 0], k=2).ids) == [0, 2]
+    assert len(coll.search([0, 0], k=50)) == 9                                            # k > n
+
+
+def test_filters_by_fields_and_ids(fake):
+    coll = Collection("c", 2, default_index="FLAT-L2")
+    coll.add(vectors=np.array([[i, 0] for i in range(8)], np.float32), fields=[{"g": i % 2} for i in range(8)])
+    assert list(coll.search([0, 0], k=3, where={"g": 1}).ids) == [1, 3, 5]
+    assert list(coll.search([0, 0], k=3, where=lambda f: f.get("g") == 0, filter_ids=[2, 4, 6, 7]).ids) == [2, 4, 6]
+    r = coll.search([0, 0], k=2, where={"g": 1}, return_fields=True)
+    assert r.fields == [{"g": 1}, {"g": 1}]
+    with pytest.raises(NotImplementedError):
+        coll.search([0, 0], k=1, where="g = 1")
+
+
+def test_build_index_validation(fake):
+    coll = Collection("c", 3, default_index=None)
+    coll.add(vectors=np.eye(3, dtype=np.float32))
+    with pytest.raises(ValueError, match="unknown index build parameter"):
+        coll.build_index("FLAT-IP", bogus=1)
+    with pytest.raises(ValueError, match="unknown index type"):
+        coll.build_index("FLAT")
+    with pytest.raises(ValueError, match="requires dimension 2"):
+        coll.build_index("FLAT-HAVERSINE")
+    with pytest.raises(ValueError, match="unsupported index/metric combination"):
+        coll.build_index("IVF-WASSERSTEIN")
+    with pytest.raises(ValueError, match="outside this package"):
+        coll.build_index("HNSW-IP")
+    coll.build_index("FLAT-COS", n_clusters=4)              # FLAT ignores the shared kwargs
+    assert coll.index_mode == "FLAT-COS"
+    assert M.parse_index_mode(coll.index_mode) == ("Flat", "Cosine")
+
+
+def test_merge_row_results_rule():
+    rows, d = _merge_row_results(np.array([5, 1], np.uint64), np.array([0.5, 0.7], np.float32),
+                                 np.array([9, 1, 3], np.uint64), np.array([0.5, 0.6, 0.9], np.float32), 3, True)
+    assert rows.tolist() == [5, 9, 1] and np.allclose(d, [0.5, 0.5, 0.6])          # best per row, ties by row, truncated
+    rows, d = _merge_row_results(np.array([5], np.uint64), np.array([0.5], np.float32),
+                                 np.array([2], np.uint64), np.array([0.9], np.float32), 5, False)
+    assert rows.tolist() == [2, 5]                                                   # IP: higher first
+
+
+def test_database_limit(fake):
+    c = VectorDBClient()
+    for i in range(64):
+        c.create_database(f"d{i}")
+    with pytest.raises(ValueError, match="maximum number of databases"):
+        c.create_database("one_too_many")

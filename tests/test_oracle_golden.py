@@ -293,3 +293,41 @@ def test_parallel_scan_matches_bruteforce_order(oracle, metric, threads):
         expect = sorted(range(n), key=lambda i: (float(all_d[i]), i))[:k]
         assert ids.tolist() == expect
         assert np.array_equal(dists, all_d[expect])
+
+
+# ---- IVF (src/index/ivf.rs:545-679) --------------------------------------------------------------------------------
+def _ivf_formula_data(n=800, dim=32):
+    i = np.arange(n).reshape(-1, 1)
+    j = np.arange(dim).reshape(1, -1)
+    return (((i * 131 + j * 17 + 1) % 997).astype(np.float32) / np.float32(997.0) + np.float32(0.01)).astype(np.float32)
+
+
+def test_ivf_filtered_empty_probe_does_not_leak(oracle):
+    data = np.array([[0, 0], [0.1, 0], [10, 10], [10.1, 10]], dtype=np.float32)
+    cent, assign = oracle.kmeans_train(data, 2, "l2")
+    allow = np.array([0b1100], dtype=np.uint64)           # only rows 2 and 3 (the far cluster) are allowed
+    ids, _ = oracle.ivf_search(data, cent, assign, [0.0, 0.0], 2, 1, "l2", allow)
+    assert len(ids) > 0 and set(ids.tolist()) <= {2, 3}
+
+
+def test_ivf_ip_full_probe_is_exact_and_recall_grows(oracle):
+    data = _ivf_formula_data()
+    cent, assign = oracle.kmeans_train(data, 32, "ip")
+    assert cent.shape == (32, 32)
+    q = data[0]
+    exact = set(np.argsort(-(data.astype(np.float64) @ q.astype(np.float64)), kind="stable")[:10].tolist())
+    low, _ = oracle.ivf_search(data, cent, assign, q, 10, 2, "ip")
+    high, _ = oracle.ivf_search(data, cent, assign, q, 10, 32, "ip")
+    rec_low, rec_high = len(exact & set(low.tolist())) / 10, len(exact & set(high.tolist())) / 10
+    assert rec_high >= rec_low and rec_high == 1.0
+
+
+def test_ivf_hamming_full_probe_matches_flat_distances(oracle):
+    n, dim = 256, 32
+    i, j = np.arange(n).reshape(-1, 1), np.arange(dim).reshape(1, -1)
+    data = (((i * 17 + j * 3) % 2) == 0).astype(np.float32)
+    cent, assign = oracle.kmeans_train(data, 16, "l2")    # binary metrics route with L2 (ivf.rs:80-87)
+    q = data[0]
+    want = np.sort(np.array([oracle.compute_distance(q, data[r], "hamming") for r in range(n)], dtype=np.float32), kind="stable")[:10]
+    _, got = oracle.ivf_search(data, cent, assign, q, 10, 16, "hamming")
+    assert np.array_equal(got, want)
