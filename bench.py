@@ -38,7 +38,9 @@ WORKLOADS = {
     "c2": ("ip", 10_000_000, 768, 1024, 10, "FLAT-IP 10M x 768 f32, batch-1024, k=10 (BASELINE configs[1])"),
     "c1": ("ip", 100_000, 128, 1000, 10, "FLAT-IP 100k x 128 f32, 1k queries, k=10 (BASELINE configs[0])"),
     "c3": ("l2", 10_000_000, 128, 1024, 100, "FLAT-L2 10M x 128 f32, batch-1024, k=100 (BASELINE configs[2])"),
+    "c4": ("hamming", 50_000_000, 1024, 4096, 32, "packed Hamming 50M x 1024-bit, batch-4096, k=32 (BASELINE configs[3])"),
 }
+PACKED = {"c4"}
 SEED_CORPUS, SEED_QUERIES = 42, 43
 APPEND_ROWS = 100_000  # ingestion batch, as benchmarks/flat_search_bench.py feeds the reference
 
@@ -143,9 +145,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_queries(metric: str, nq: int, dim: int) -> np.ndarray:
+def make_queries(metric: str, nq: int, dim: int, packed: bool = False) -> np.ndarray:
     from lynsedb_b200 import synthetic
 
+    if packed:
+        q = synthetic.rows_packed(SEED_QUERIES, np.arange(nq), dim // 64)
+        q[0] = synthetic.rows_packed(SEED_CORPUS, np.arange(1), dim // 64)[0]
+        return np.ascontiguousarray(q, dtype=np.uint64)
     q = synthetic.rows_f32(SEED_QUERIES, np.arange(nq), dim)
     q[0] = synthetic.rows_f32(SEED_CORPUS, np.arange(1), dim)[0]  # row 0 := query 0 (flat_search_bench.py:76-79)
     return np.ascontiguousarray(q, dtype=np.float32)
@@ -179,6 +185,27 @@ def cpu_reference_qps(metric, rows_total, dim, k, sample_rows, sample_queries, c
                       f"{best:.2f} s; QPS scaled by rows (scan cost is linear in rows)"}
 
 
+def cpu_reference_packed_qps(metric, rows_total, dim, k, sample_rows, sample_queries, queries):
+    """packed_binary_search (flat_mmap.rs:1345-1409) of the oracle on the first rows of the synthetic fingerprints."""
+    import oracle
+    from lynsedb_b200 import synthetic
+
+    threads = oracle.host_threads()
+    words = dim // 64
+    data = np.empty((sample_rows, words), dtype=np.uint64)
+    for lo in range(0, sample_rows, 500_000):
+        hi = min(lo + 500_000, sample_rows)
+        data[lo:hi] = synthetic.rows_packed(SEED_CORPUS, np.arange(lo, hi), words)
+    nq = min(sample_queries, len(queries))
+    oracle.packed_batch_search(data[:20000], queries[:2], k, metric, n_threads=threads)
+    t0 = time.perf_counter()
+    oracle.packed_batch_search(data, queries[:nq], k, metric, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": (nq / dt) * (sample_rows / rows_total), "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"{nq} queries x {sample_rows} of {rows_total} fingerprints of {dim} bits on {threads} threads (hardware popcnt), "
+                      f"{dt:.2f} s; QPS scaled by rows"}
+
+
 def run_reference(args, metric, rows, dim, nq, k, desc):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -186,6 +213,20 @@ def run_reference(args, metric, rows, dim, nq, k, desc):
     from lynsedb_b200 import synthetic
 
     sample_rows = min(args.cpu_sample_rows, rows)
+    if args.workload in PACKED:
+        queries = make_queries(metric, nq, dim, True)
+        t0 = time.perf_counter()
+        cb = None
+        for _ in range(max(args.steps, 1)):
+            cb = cpu_reference_packed_qps(metric, rows, dim, k, sample_rows, args.cpu_sample_queries, queries)
+        dt = time.perf_counter() - t0
+        line = {"impl": "reference", "metric": "queries/sec", "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": desc, "rows": rows, "dim": dim, "nq": nq, "k": k, "metric": metric}, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
     # host copy of the first rows of the same synthetic corpus
     corpus = np.empty((sample_rows, dim), dtype=np.float32)
     step = 50_000
@@ -282,10 +323,11 @@ def main():
         return float(t.item())
 
     # ---- corpus shard, generated on the device --------------------------------------------------------
-    per = (rows + world - 1) // world
-    base = rank * per
-    n_local = max(0, min(per, rows - base))
-    idx = DeviceIndex(dim, "float32", device=local_rank)
+    from lynsedb_b200.sharding import shard_range
+
+    packed = args.workload in PACKED
+    base, n_local = shard_range(rows, world, rank)
+    idx = DeviceIndex(dim, "packed" if packed else "float32", device=local_rank)
     idx.reserve(n_local)
     done = 0
     while done < n_local:
@@ -298,7 +340,7 @@ def main():
     idx.set_timing(True)
     info = N.device_info(local_rank)
 
-    queries = make_queries(metric, nq, dim)
+    queries = make_queries(metric, nq, dim, packed)
     qbytes = queries.nbytes
     # pinned host staging for the e2e path
     hq, hrows, hdists, hcounts = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -319,6 +361,11 @@ def main():
         N.check(lib.lb_sharded_search_device(comm, idx._h, m_id, dq, nq, k, base, drows, ddists, dcounts))
 
     def step_host():
+        if packed:
+            N.check(lib.lb_sharded_search_packed(comm, idx._h, m_id, C.cast(hq, C.POINTER(C.c_uint64)), nq, k, base,
+                                                 C.cast(hrows, C.POINTER(C.c_uint64)), C.cast(hdists, C.POINTER(C.c_float)),
+                                                 C.cast(hcounts, C.POINTER(C.c_uint32))))
+            return
         N.check(lib.lb_sharded_search(comm, idx._h, m_id, C.cast(hq, C.POINTER(C.c_float)), nq, k, base,
                                       C.cast(hrows, C.POINTER(C.c_uint64)), C.cast(hdists, C.POINTER(C.c_float)),
                                       C.cast(hcounts, C.POINTER(C.c_uint32))))
@@ -364,6 +411,12 @@ def main():
         ok_scores, ok_sorted = True, True
         checked = sorted({0, min(1, nq - 1), nq // 2, nq - 1})
         for qi in checked:
+            if packed:
+                rws = synthetic.rows_packed(SEED_CORPUS, grow[qi], dim // 64)
+                for j in range(k):
+                    ok_scores &= bool(np.float32(oracle.packed_distance(queries[qi], rws[j], metric)) == gd[qi, j])
+                ok_sorted &= bool(np.all(np.diff(gd[qi]) >= 0)) and bool(np.all((np.diff(gd[qi]) > 0) | (np.diff(grow[qi].astype(np.int64)) > 0)))
+                continue
             rws = synthetic.rows_f32(SEED_CORPUS, grow[qi], dim)
             for j in range(k):
                 if metric == "ip":
@@ -392,19 +445,29 @@ def main():
     elif dom_ms > 0:
         bytes_per_launch = float(st["algorithmic_bytes"])
         ach = bytes_per_launch / (dom_ms * 1e-3) / 1e9
+        kname = "lb::scan_packed16_kernel" if st["plan_used"] == 2 else "lb::scan_stream_kernel"
         roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": None, "kernel": "lb::scan_exact_kernel", "kernel_ms": dom_ms, "peak_source": peaks["source"]}
+                    "traffic": None, "kernel": kname, "kernel_ms": dom_ms, "peak_source": peaks["source"]}
+        if st["plan_used"] == 2:
+            # at this batch size the packed scan is bound by the POPC pipe, not by HBM: report both views
+            pairs = float(nq) * n_local
+            roofline["popc_note"] = {"pairs_per_s": pairs / (dom_ms * 1e-3), "popc32_per_pair": dim // 32,
+                                     "bound_pairs_per_s_at_16_popc_per_clk_per_sm": 16.0 * info["sm_count"] * 1.965e9 / (dim // 32)}
 
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             sample_rows = min(args.cpu_sample_rows, n_local)
-            corpus_sample = idx.read_rows(0, sample_rows)
-            cpu_baseline = cpu_reference_qps(metric, rows, dim, k, sample_rows, args.cpu_sample_queries, corpus_sample, queries)
+            if packed:
+                cpu_baseline = cpu_reference_packed_qps(metric, rows, dim, k, sample_rows, args.cpu_sample_queries, queries)
+            else:
+                corpus_sample = idx.read_rows(0, sample_rows)
+                cpu_baseline = cpu_reference_qps(metric, rows, dim, k, sample_rows, args.cpu_sample_queries, corpus_sample, queries)
         line = {
             "metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16 coarse contraction (f32 accumulate) + f32 exact-order rescore", "data": "synthetic",
+            "vs_baseline": None, "dtype": ("u64 popcount" if packed else ("bf16 coarse contraction (f32 accumulate) + f32 exact-order rescore" if st["plan_used"] == 1 else "f32")),
+            "data": "synthetic",
             "config": {"workload": desc, "rows": rows, "rows_per_gpu": n_local, "dim": dim, "nq": nq, "k": k, "metric": metric,
                        "sharding": f"contiguous row shards x{world}", "plan": args.plan,
                        "l2_policy": "inputs larger than L2 (shadow %.1f GB per GPU vs 126 MB L2)" % (st["algorithmic_bytes"] / 1e9),

@@ -209,6 +209,8 @@ int lb_comm_barrier(lb_comm* c);
  * global u64 rows.  comm == NULL means a single shard.  Requires k <= rows of every shard. */
 int lb_sharded_search(lb_comm* comm, lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k,
                       uint64_t row_base, uint64_t* out_rows, float* out_dists, uint32_t* out_counts);
+int lb_sharded_search_packed(lb_comm* comm, lb_index* idx, int metric, const uint64_t* query_words, uint32_t nq, uint32_t k,
+                             uint64_t row_base, uint64_t* out_rows, float* out_dists, uint32_t* out_counts);
 int lb_sharded_search_device(lb_comm* comm, lb_index* idx, int metric, const void* d_queries, uint32_t nq, uint32_t k,
                              uint64_t row_base, uint64_t* d_out_rows, float* d_out_dists, uint32_t* d_out_counts);
 

@@ -88,6 +88,7 @@ SIGNATURES = {
     "lb_comm_allgather": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "lb_comm_barrier": (C.c_int, [_vp]),
     "lb_sharded_search": (C.c_int, [_vp, _vp, C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint64, _u64p, _f32p, _u32p]),
+    "lb_sharded_search_packed": (C.c_int, [_vp, _vp, C.c_int, _u64p, C.c_uint32, C.c_uint32, C.c_uint64, _u64p, _f32p, _u32p]),
     "lb_sharded_search_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_uint64, _vp, _vp, _vp]),
     "lb_index_event_record": (C.c_int, [_vp, C.c_int]),
     "lb_index_event_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),

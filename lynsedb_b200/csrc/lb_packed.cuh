@@ -79,8 +79,9 @@ __device__ __forceinline__ uint32_t popc1024_hs(const uint32_t* x) {
 }
 
 // one warp folds n candidate keys (shared memory) of one query into its (partition, query) list in global memory
-__device__ __forceinline__ void warp_fold_candidates(const uint64_t* __restrict__ cand, int n, uint64_t* list, uint32_t* count_p,
-                                                     uint64_t* thr_p, int k, int lane) {
+// returns the new gate (KEY_NONE while the list is not full)
+__device__ __forceinline__ uint64_t warp_fold_candidates(const uint64_t* __restrict__ cand, int n, uint64_t* list, uint32_t* count_p,
+                                                         uint64_t* thr_p, int k, int lane) {
     uint32_t cnt = *count_p;
     uint64_t thr = cnt < (uint32_t)k ? KEY_NONE : *thr_p;
     for (int base = 0; base < n; base += 32) {
@@ -120,6 +121,7 @@ __device__ __forceinline__ void warp_fold_candidates(const uint64_t* __restrict_
         *count_p = cnt;
         *thr_p = thr;
     }
+    return thr;
 }
 
 // MODE: 0 = Hamming (popc(x ^ y)), 1 = Jaccard / Tanimoto, 2 = Dice (both from popc(x & y) and the two row popcounts)
@@ -154,6 +156,23 @@ __global__ void __launch_bounds__(PK_ROWS, 2) scan_packed16_kernel(const __grid_
         }
     }
 
+    const bool single_tile = a.nq <= PK_TQ;
+    if (single_tile) {
+        if (tid < a.nq * PK_W) sq[tid] = __ldg(a.qwords + tid);
+        if (tid < a.nq) {
+            sthr[tid] = KEY_NONE;  // the lists of this launch start empty (counts are zeroed by the host)
+            scnt[tid] = 0u;
+        }
+        __syncthreads();
+        if (tid < a.nq) {
+            uint32_t p = 0;
+#pragma unroll
+            for (int w = 0; w < PK_W; ++w) p += __popcll(sq[tid * PK_W + w]);
+            sqpop[tid] = p;
+        }
+        __syncthreads();
+    }
+
     for (uint32_t blk = 0; blk < n_blocks; ++blk) {
         const uint32_t stage = blk % PK_NSTAGES, phase = (blk / PK_NSTAGES) & 1u;
         while (!tc::mbar_try_wait(full0 + 8u * stage, phase)) {
@@ -184,21 +203,24 @@ __global__ void __launch_bounds__(PK_ROWS, 2) scan_packed16_kernel(const __grid_
         }
         for (int q0 = 0; q0 < a.nq; q0 += PK_TQ) {
             const int tq = min(PK_TQ, a.nq - q0);
-            // query tile, gates and counters
-            if (tid < tq * PK_W) sq[tid] = __ldg(a.qwords + (size_t)q0 * PK_W + tid);
-            if (tid < tq) {
-                const size_t lq = (size_t)part * a.nq + (q0 + tid);
-                sthr[tid] = __ldcg(a.counts + lq) < (uint32_t)a.k ? KEY_NONE : __ldcg(a.thr + lq);
-                scnt[tid] = 0u;
-            }
-            __syncthreads();
-            if (MODE != 0 && tid < tq) {
-                uint32_t p = 0;
+            // query tile, gates and counters.  A batch that fits one tile keeps them in shared memory for the whole
+            // kernel (loaded before the block loop, gates updated by the fold): nothing global on the per-block path.
+            if (!single_tile) {
+                if (tid < tq * PK_W) sq[tid] = __ldg(a.qwords + (size_t)q0 * PK_W + tid);
+                if (tid < tq) {
+                    const size_t lq = (size_t)part * a.nq + (q0 + tid);
+                    sthr[tid] = __ldcg(a.counts + lq) < (uint32_t)a.k ? KEY_NONE : __ldcg(a.thr + lq);
+                    scnt[tid] = 0u;
+                }
+                __syncthreads();
+                if (MODE != 0 && tid < tq) {
+                    uint32_t p = 0;
 #pragma unroll
-                for (int w = 0; w < PK_W; ++w) p += __popcll(sq[tid * PK_W + w]);
-                sqpop[tid] = p;
+                    for (int w = 0; w < PK_W; ++w) p += __popcll(sq[tid * PK_W + w]);
+                    sqpop[tid] = p;
+                }
+                if (MODE != 0) __syncthreads();
             }
-            if (MODE != 0) __syncthreads();
             for (int j = 0; j < tq; ++j) {
                 const uint4* qp = reinterpret_cast<const uint4*>(sq + j * PK_W);
                 uint32_t x[32];
@@ -242,7 +264,11 @@ __global__ void __launch_bounds__(PK_ROWS, 2) scan_packed16_kernel(const __grid_
                 const int n = (int)scnt[j];
                 if (n > 0) {
                     const size_t lq = (size_t)part * a.nq + (q0 + j);
-                    warp_fold_candidates(cand + j * PK_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                    const uint64_t g = warp_fold_candidates(cand + j * PK_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                    if (lane == 0) {
+                        sthr[j] = g;
+                        scnt[j] = 0u;
+                    }
                 }
             }
             __syncthreads();

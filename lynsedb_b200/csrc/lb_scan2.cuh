@@ -187,7 +187,14 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
         __syncthreads();
         if (METRIC == LB_COSINE && tid < tq) sna[tid] = cosine_query_norm2(sq + tid * dim_pad, dim);
     };
-    if (single_tile) load_tile(0, a.nq);
+    if (single_tile) {
+        load_tile(0, a.nq);
+        if (tid < a.nq) {
+            sthr[tid] = KEY_NONE;  // the lists of this launch start empty (counts are zeroed by the host)
+            scnt[tid] = 0u;
+        }
+        __syncthreads();
+    }
 
     for (uint64_t blk = part_begin; blk < part_end; blk += S2_ROWS) {
         const uint64_t slot = blk + tid;
@@ -203,12 +210,12 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
                 __syncthreads();  // the previous tile's queries and candidates are no longer read
                 load_tile(q0, tq);
             }
-            if (tid < tq) {
+            if (!single_tile && tid < tq) {
                 const size_t lq = (size_t)part * a.nq + (q0 + tid);
                 sthr[tid] = __ldcg(a.counts + lq) < (uint32_t)a.k ? KEY_NONE : __ldcg(a.thr + lq);
                 scnt[tid] = 0u;
             }
-            __syncthreads();
+            if (!single_tile) __syncthreads();
             if (valid) {
                 float st[S2_TQ][Op::kState];
 #pragma unroll
@@ -249,10 +256,172 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
                 const int n = (int)scnt[j];
                 if (n > 0) {
                     const size_t lq = (size_t)part * a.nq + (q0 + j);
-                    warp_fold_candidates(cand + j * S2_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                    const uint64_t g = warp_fold_candidates(cand + j * S2_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                    if (lane == 0) {
+                        sthr[j] = g;   // a single-tile batch keeps its gates in shared memory across row blocks
+                        scnt[j] = 0u;
+                    }
                 }
             }
             if (single_tile) __syncthreads();  // candidates folded before the next block reuses the buffers
+        }
+    }
+}
+
+// ---- the same scan with the rows staged through shared memory by TMA -------------------------------------------
+// One row per thread reading straight from global memory touches 32 rows per load instruction, 32 bytes each:
+// HBM tops out near 3.7 TB/s on that pattern.  Here a block of 256 rows is fetched in column chunks of 32 floats:
+// one TMA box [256 rows x 128 B] per chunk (SWIZZLE_128B, so thread r finds 16-byte piece c of its row at piece
+// c ^ (r & 7) and the 128-bit reads are bank-conflict free), four stages in flight.  The chunk order, and with it
+// every accumulator chain, is unchanged.
+constexpr int S3_NSTAGES = 4;
+constexpr int S3_STAGE_BYTES = S2_ROWS * 128;  // 32 KiB: 256 rows x 32 floats
+
+template <int METRIC, bool IP2>
+__global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __grid_constant__ CUtensorMap tmap, ScanArgs a) {
+    using Op = Scan2Op<METRIC, IP2>;
+    constexpr int S2_TQ = Op::kTQ;
+    constexpr bool ASC = METRIC != LB_IP;
+    extern __shared__ __align__(16) unsigned char smem_s3[];
+    const uint32_t smem_base = (tc::smem_u32(smem_s3) + 1023u) & ~1023u;
+    unsigned char* smem = smem_s3 + (smem_base - tc::smem_u32(smem_s3));
+    const int dim = a.dim, dim_pad = (dim + 3) & ~3;
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem + S3_NSTAGES * S3_STAGE_BYTES);   // [TQ][256]
+    float* sq = reinterpret_cast<float*>(cand + S2_TQ * S2_ROWS);                       // [TQ][dim_pad]
+    uint64_t* sthr = reinterpret_cast<uint64_t*>(sq + S2_TQ * dim_pad);                 // [TQ]
+    uint32_t* scnt = reinterpret_cast<uint32_t*>(sthr + S2_TQ);                         // [TQ]
+    float* sna = reinterpret_cast<float*>(scnt + S2_TQ);                                // [TQ]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sna + S2_TQ + 2);                      // full[NSTAGES]
+    const uint32_t full0 = tc::smem_u32(bars);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int part = blockIdx.x;
+    const int chunks = dim >> 3;                 // whole 8-float chunks (the rest is the scalar tail)
+    const int n_cc = (dim + 31) >> 5;            // column chunks of 32 floats per row block
+    const uint64_t part_begin = (uint64_t)part * a.rows_per_part;
+    uint64_t part_end = part_begin + a.rows_per_part;
+    if (part_end > a.n_rows) part_end = a.n_rows;
+    const uint32_t n_blocks = part_end > part_begin ? (uint32_t)((part_end - part_begin + S2_ROWS - 1) / S2_ROWS) : 0u;
+    const int n_tiles = (a.nq + S2_TQ - 1) / S2_TQ;
+    const bool single_tile = n_tiles == 1;
+    // the stream of boxes this CTA consumes: for every row block, for every query tile, its n_cc column chunks
+    const uint64_t n_boxes = (uint64_t)n_blocks * n_tiles * n_cc;
+
+    if (tid == 0) {
+        for (int s = 0; s < S3_NSTAGES; ++s) tc::mbar_init(full0 + 8u * s, 1);
+        tc::fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    auto issue = [&](uint64_t box) {  // thread 0 only
+        const uint32_t blk = (uint32_t)(box / ((uint64_t)n_tiles * n_cc));
+        const int cc = (int)(box % n_cc);
+        const uint32_t stage = (uint32_t)(box % S3_NSTAGES);
+        tc::mbar_arrive_expect_tx(full0 + 8u * stage, S3_STAGE_BYTES);
+        tc::tma_load_2d(smem_base + stage * S3_STAGE_BYTES, &tmap, cc * 32, (int)(part_begin + (uint64_t)blk * S2_ROWS), full0 + 8u * stage);
+    };
+    auto load_tile = [&](int q0, int tq) {
+        for (int i = tid; i < tq * dim; i += S2_ROWS) {
+            const int qq = i / dim, d = i - qq * dim;
+            sq[qq * dim_pad + d] = __ldg(a.queries + (size_t)(q0 + qq) * dim + d);
+        }
+        __syncthreads();
+        if (METRIC == LB_COSINE && tid < tq) sna[tid] = cosine_query_norm2(sq + tid * dim_pad, dim);
+    };
+    __syncthreads();
+    if (tid == 0)
+        for (uint64_t b = 0; b < (uint64_t)S3_NSTAGES && b < n_boxes; ++b) issue(b);
+    if (single_tile) {
+        load_tile(0, a.nq);
+        if (tid < a.nq) {
+            sthr[tid] = KEY_NONE;
+            scnt[tid] = 0u;
+        }
+        __syncthreads();
+    }
+
+    uint64_t box = 0;
+    for (uint32_t blk = 0; blk < n_blocks; ++blk) {
+        const uint64_t slot = part_begin + (uint64_t)blk * S2_ROWS + tid;
+        bool valid = slot < part_end;
+        const uint32_t row = (uint32_t)slot;
+        if (valid && !row_allowed(a.allow_bits, row)) valid = false;
+        const float* c = a.corpus + (size_t)row * dim;
+        const bool two_acc = METRIC == LB_IP && (a.ip_single || (valid && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row)));
+        for (int q0 = 0; q0 < a.nq; q0 += S2_TQ) {
+            const int tq = min(S2_TQ, a.nq - q0);
+            if (!single_tile) {
+                __syncthreads();
+                load_tile(q0, tq);
+                if (tid < tq) {
+                    const size_t lq = (size_t)part * a.nq + (q0 + tid);
+                    sthr[tid] = __ldcg(a.counts + lq) < (uint32_t)a.k ? KEY_NONE : __ldcg(a.thr + lq);
+                    scnt[tid] = 0u;
+                }
+                __syncthreads();
+            }
+            float st[S2_TQ][Op::kState];
+#pragma unroll
+            for (int t = 0; t < S2_TQ; ++t)
+#pragma unroll
+                for (int i = 0; i < Op::kState; ++i) st[t][i] = 0.0f;
+            for (int cc = 0; cc < n_cc; ++cc, ++box) {
+                const uint32_t stage = (uint32_t)(box % S3_NSTAGES), phase = (uint32_t)((box / S3_NSTAGES) & 1u);
+                while (!tc::mbar_try_wait(full0 + 8u * stage, phase)) {
+                }
+                // my 32 floats of this column chunk
+                Vec8 cv[4];
+                {
+                    const float4* rowp = reinterpret_cast<const float4*>(smem + stage * S3_STAGE_BYTES + tid * 128);
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const float4 x = rowp[p ^ (tid & 7)];
+                        cv[p >> 1].v[(p & 1) * 4 + 0] = x.x; cv[p >> 1].v[(p & 1) * 4 + 1] = x.y;
+                        cv[p >> 1].v[(p & 1) * 4 + 2] = x.z; cv[p >> 1].v[(p & 1) * 4 + 3] = x.w;
+                    }
+                }
+                __syncthreads();  // every thread holds its piece: the stage can be refilled
+                if (tid == 0 && box + S3_NSTAGES < n_boxes) issue(box + S3_NSTAGES);
+                if (valid) {
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const int j = cc * 4 + sub;
+                        if (j < chunks) {
+#pragma unroll
+                            for (int t = 0; t < S2_TQ; ++t) {
+                                if (t < tq) {
+                                    const Vec8 qv = load8<false>(sq + t * dim_pad + 8 * j, true);  // broadcast
+                                    Op::step(st[t], qv, cv[sub], (j & 1) != 0, two_acc);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (valid) {
+#pragma unroll
+                for (int t = 0; t < S2_TQ; ++t) {
+                    if (t < tq) {
+                        const float v = Op::finish(st[t], sq + t * dim_pad, c, chunks * 8, dim, two_acc, METRIC == LB_COSINE ? sna[t] : 0.0f);
+                        const uint64_t key = make_key<ASC>(v, row);
+                        if (key < sthr[t]) {
+                            const uint32_t pos = atomicAdd(&scnt[t], 1u);
+                            cand[t * S2_ROWS + pos] = key;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int j = warp; j < tq; j += S2_ROWS / 32) {
+                const int n = (int)scnt[j];
+                if (n > 0) {
+                    const size_t lq = (size_t)part * a.nq + (q0 + j);
+                    const uint64_t g = warp_fold_candidates(cand + j * S2_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                    if (lane == 0) {
+                        sthr[j] = g;
+                        scnt[j] = 0u;
+                    }
+                }
+            }
+            if (single_tile) __syncthreads();
         }
     }
 }
