@@ -407,6 +407,12 @@ __global__ void pair_distance_kernel(const float* a, const float* b, int dim, in
     if (threadIdx.x == 0 && blockIdx.x == 0) *out = compute_distance<true>(metric, a, b, dim, (dim & 3) == 0);
 }
 
+__global__ void fill_f32_kernel(float* out, uint64_t n, float value) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = value;
+}
+
 // synthetic corpora
 __global__ void synth_f32_kernel(float* out, uint64_t n_elems, uint64_t seed, uint64_t elem_offset) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

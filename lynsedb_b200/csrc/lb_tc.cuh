@@ -64,7 +64,10 @@ struct TcArgs {
     float* cand_score;        // [nq][P][KP]
     uint32_t* cand_row;       // [nq][P][KP]
     float* cand_thr;          // [nq][P]
-    int share_floor;          // 1: partitions of a query share their shortlist floor through gthr (needs k <= KP - 4)
+    int share_floor;          // 1: partitions of a query share a shortlist floor through gthr
+    int floor_group;          // m: a published floor is the minimum of the floors of m consecutive partitions, so that at
+                              // least m * KP rows score above it (m = 1 when k <= KP - 4, else ~10 k / KP)
+    float* gfloor;            // [nq][P] floors of the single partitions (initialised to -inf; used when m > 1)
     uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable f32 bits)
     uint32_t* error_flag;     // set non-zero when a barrier wait timed out
     float* dump;              // optional [n_mtiles*128][tiles_total*64] raw scores (diagnostics)
@@ -298,7 +301,40 @@ struct Shortlist {
     float lmin, thr_g, thr_pub;
     uint32_t g_bits;
     uint32_t* gthr;
+    float* gfloor_q;     // floors of this query's partitions (floor groups)
+    int group_m, n_parts, part;
     bool q_valid, share;
+
+    __device__ __forceinline__ void set_groups(float* gfloor_row, int m, int P) {
+        gfloor_q = gfloor_row;
+        group_m = m;
+        n_parts = P;
+    }
+    // The list is full and its floor rose: make it visible to the other partitions of the query.  With floor groups
+    // the value that may gate everybody is the smallest floor of the m partitions of my group (every member has KP
+    // rows above its own floor, hence m * KP rows above the minimum); incomplete groups publish nothing.
+    __device__ __forceinline__ void publish() {
+        if (group_m <= 1) {
+            atomicMax(gthr, f32_orderable(lmin));
+        } else {
+            __stcg(gfloor_q + part, lmin);
+            const int g0 = (part / group_m) * group_m, g1 = g0 + group_m;
+            if (g1 <= n_parts) {
+                float mn = lmin;
+                int p = g0;
+                for (; p + 8 <= g1; p += 8) {  // independent loads: one L2 round trip per eight floors
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = __ldcg(gfloor_q + p + i);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) mn = fminf(mn, f[i]);
+                }
+                for (; p < g1; ++p) mn = fminf(mn, __ldcg(gfloor_q + p));
+                if (mn > -INFINITY) atomicMax(gthr, f32_orderable(mn));
+            }
+        }
+        thr_pub = lmin;
+    }
 
     __device__ __forceinline__ void reset(bool valid, bool share_floor, uint32_t* gthr_q) {
 #pragma unroll
@@ -320,7 +356,7 @@ struct Shortlist {
     // end of the warm-up round: the KP-th best score of the sample is a valid floor for every partition (KP rows of
     // the corpus score at least that much), so it becomes the shared floor and the list starts over
     __device__ __forceinline__ void absorb_sample() {
-        if (share && q_valid && lmin > thr_g) {
+        if (share && q_valid && group_m <= 1 && lmin > thr_g) {
             thr_g = lmin;
             atomicMax(gthr, f32_orderable(lmin));
         }
@@ -331,6 +367,7 @@ struct Shortlist {
         if (share && (tile_iter & 7u) == 0u) {
             if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
             g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
+            if (group_m > 1 && q_valid && lmin > thr_pub) publish();
         }
     }
     // replace the current minimum by (score, row) and recompute the minimum: ~70 ALU instructions, no memory
@@ -378,6 +415,14 @@ struct Shortlist {
                 mlo &= n_ok >= 32u ? 0xffffffffu : ((1u << n_ok) - 1u);
                 mhi &= n_ok >= 64u ? 0xffffffffu : (n_ok > 32u ? ((1u << (n_ok - 32u)) - 1u) : 0u);
             }
+            // a lane with exactly one hit (the usual case) already holds its score: it is the tile maximum
+            const bool one_hit = __popc(mlo) + __popc(mhi) == 1;
+            if (one_hit) {
+                const int idx = mlo != 0u ? __ffs((int)mlo) - 1 : 32 + __ffs((int)mhi) - 1;
+                insert(fmaxf(m0, m1), row0 + (uint32_t)idx);
+                mlo = 0u;
+                mhi = 0u;
+            }
 #pragma unroll 1
             while (__any_sync(0xffffffffu, (mlo | mhi) != 0u)) {
                 if ((mlo | mhi) != 0u) {
@@ -405,10 +450,8 @@ struct Shortlist {
                     if (x > gate()) insert(x, row0 + (uint32_t)idx);  // the gate may have risen since the mask was taken
                 }
             }
-            if (share && q_valid && lmin > thr_pub && lmin > thr_g) {  // list is full and its floor rose: publish
-                atomicMax(gthr, f32_orderable(lmin));
-                thr_pub = lmin;
-            }
+            // floor groups publish from poll_floor (every 8th tile): the group minimum costs m loads
+            if (share && q_valid && group_m <= 1 && lmin > thr_pub && lmin > thr_g) publish();
         }
     }
     __device__ __forceinline__ void flush(const TcArgs& a, uint32_t gq, uint32_t part) {

@@ -159,6 +159,7 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
         const uint32_t gq = (uint32_t)ql;
         const bool q_valid = gq < (uint32_t)a.nq;
         sl.init_floor();
+        sl.set_groups(a.gfloor != nullptr && q_valid ? a.gfloor + (size_t)gq * a.P : nullptr, a.gfloor != nullptr ? a.floor_group : 1, a.P);
         for (int r = first_round; r < n_rounds && ok; ++r) {
             const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
             if (part >= (uint32_t)a.P) break;
@@ -166,6 +167,7 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
             const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
             if (r == first_round) load_query_to_tmem(a.qb + (size_t)gq * a.Dp, a.Dp, lane_addr);  // the query tile never changes
             sl.reset(q_valid, a.share_floor != 0, a.gthr + (q_valid ? gq : 0));
+            sl.part = (int)part;
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(aready_bar);

@@ -142,7 +142,7 @@ struct lb_index {
     lb_search_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf w_send, w_recv, w_g_rows, w_g_dists, w_g_counts, w_progress, w_prof;
+    DevBuf w_send, w_recv, w_g_rows, w_g_dists, w_g_counts, w_progress, w_prof, w_gfloor;
 };
 
 namespace lb {
@@ -581,9 +581,22 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     a.cand_row = idx->w_cand_row.as<uint32_t>();
     a.cand_thr = idx->w_cand_thr.as<float>();
     a.gthr = flags + 4 + nq;
-    // A published floor is the KP-th best score of one partition: rows at or below it are outside the global top KP,
-    // which is only enough when k fits inside KP with some room for the bf16 error.
-    a.share_floor = (k <= tc::KP - 4) ? 1 : 0;
+    // Shared floors: a published floor must have enough rows above it to be far past rank k (the certification needs
+    // the final floor well below the k-th best score).  For k <= KP - 4 the KP-th best score of one partition will do.
+    // For larger k a valid floor is the minimum over a group of m = ceil(10 k / KP) partitions (>= 10 k rows above it);
+    // that variant is implemented (LYNSE_B200_TC_GROUPS=1) but off: on C3 (k = 100) it only becomes available after
+    // the first m partitions (30 % of the pass) and measured 8.9 ms against 7.6 ms without any sharing.
+    const int m_req = k <= tc::KP - 4 ? 1 : (10 * k + tc::KP - 1) / tc::KP;
+    a.share_floor = ((int)P >= m_req && (m_req == 1 || tc_env_int("LYNSE_B200_TC_GROUPS", 0) != 0)) ? 1 : 0;
+    a.floor_group = m_req;
+    a.gfloor = nullptr;
+    if (a.share_floor && m_req > 1) {
+        LB_TRY(idx->w_gfloor.ensure((size_t)nq * P * 4));
+        fill_f32_kernel<<<(unsigned)std::min<uint64_t>(ceil_div((uint64_t)nq * P, 256), 1024), 256, 0, idx->stream>>>(
+            idx->w_gfloor.as<float>(), (uint64_t)nq * P, -INFINITY);
+        LB_CUDA_TRY(cudaGetLastError());
+        a.gfloor = idx->w_gfloor.as<float>();
+    }
     a.error_flag = flags;
     a.dump = dump;
     a.n_slots = (int)n_slots;
@@ -967,7 +980,7 @@ void lb_index_destroy(lb_index* idx) {
                           &idx->w_out_dists, &idx->w_out_counts, &idx->w_qb, &idx->w_qnorm, &idx->w_cand_score,
                           &idx->w_cand_row, &idx->w_cand_thr, &idx->w_flags, &idx->w_qstats, &idx->w_nq, &idx->w_sub_q,
                           &idx->w_qmap, &idx->shadow[0].buf, &idx->shadow[1].buf, &idx->shadow[2].buf,
-                          &idx->w_send, &idx->w_recv, &idx->w_g_rows, &idx->w_g_dists, &idx->w_g_counts, &idx->w_progress, &idx->w_prof};
+                          &idx->w_send, &idx->w_recv, &idx->w_g_rows, &idx->w_g_dists, &idx->w_g_counts, &idx->w_progress, &idx->w_prof, &idx->w_gfloor};
         for (DevBuf* b : bufs) b->release();
         for (int i = 0; i < 4; ++i)
             if (idx->ev[i]) cudaEventDestroy(idx->ev[i]);
