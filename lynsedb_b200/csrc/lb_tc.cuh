@@ -573,6 +573,76 @@ struct FinArgs {
     uint32_t* n_uncertified;  // counter
 };
 
+// Exact-order rescore of one row by EIGHT threads: thread i owns AVX lane i (elements i, i+8, i+16, ...), so every
+// accumulator still sees its products in the reference's order; the horizontal sums are the reference's trees done
+// with shuffles.  The row comes from `rowbuf` (shared memory, filled with coalesced loads by the same warp), 256
+// columns at a time.  lanes: lane & 7 = AVX lane, lane >> 3 = which of the warp's four rows.
+constexpr int FIN_COLS = 256;   // columns staged per round
+__device__ __forceinline__ float hsum8_shfl(float a) {   // simd.rs:1427-1436 over the 8 threads of a row
+    a = a + __shfl_xor_sync(0xffffffffu, a, 4);           // s[i] = acc[i] + acc[i+4]
+    a = a + __shfl_xor_sync(0xffffffffu, a, 1);           // t0 = s0 + s1, t2 = s2 + s3
+    return a + __shfl_xor_sync(0xffffffffu, a, 2);        // t0 + t2
+}
+__device__ __forceinline__ float rescore_row_lanes(int metric, bool two_acc_ip, const float* __restrict__ sq, const float* __restrict__ c,
+                                                   int dim, float* rowbuf /* this row's FIN_COLS floats */, bool row_ok, int lane) {
+    const int i = lane & 7, sub = lane & 7;
+    const int chunks = dim >> 3;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    for (int col0 = 0; col0 < chunks * 8; col0 += FIN_COLS) {
+        const int ncol = min(FIN_COLS, chunks * 8 - col0);
+        __syncwarp();
+        // the row's 8 threads fetch its columns [col0, col0 + ncol): 8 x 16 B = 128 contiguous bytes per step
+        if (row_ok)
+            for (int x = sub * 4; x < ncol; x += 32) *reinterpret_cast<float4*>(rowbuf + x) = __ldg(reinterpret_cast<const float4*>(c + col0 + x));
+        __syncwarp();
+        if (row_ok) {
+            const int j0 = col0 >> 3, nj = ncol >> 3;
+#pragma unroll 4
+            for (int jj = 0; jj < nj; ++jj) {
+                const float qv = sq[col0 + 8 * jj + i], cv = rowbuf[8 * jj + i];
+                const bool odd = ((j0 + jj) & 1) != 0;
+                if (metric == LB_IP) {
+                    if (two_acc_ip && odd) a1 = fmaf(qv, cv, a1);
+                    else a0 = fmaf(qv, cv, a0);
+                } else if (metric == LB_L2) {
+                    const float d = qv - cv;
+                    if (odd) a1 = fmaf(d, d, a1);
+                    else a0 = fmaf(d, d, a0);
+                } else {
+                    a0 = fmaf(qv, cv, a0);
+                    a1 = fmaf(qv, qv, a1);
+                    a2 = fmaf(cv, cv, a2);
+                }
+            }
+        }
+    }
+    const int t0 = chunks * 8;
+    if (metric == LB_IP) {
+        if (two_acc_ip) a0 = a0 + a1;
+        float out = hsum8_shfl(a0);
+        for (int x = t0; x < dim; ++x) out = out + sq[x] * __ldg(c + (row_ok ? x : 0));
+        return out;
+    } else if (metric == LB_L2) {
+        a0 = a0 + a1;
+        float sum = hsum8_shfl(a0);
+        for (int x = t0; x < dim; ++x) {
+            const float diff = sq[x] - __ldg(c + (row_ok ? x : 0));
+            sum = sum + diff * diff;
+        }
+        return sum;
+    }
+    float dot = hsum8_shfl(a0), na = hsum8_shfl(a1), nb = hsum8_shfl(a2);
+    for (int x = t0; x < dim; ++x) {
+        const float qa = sq[x], cb = __ldg(c + (row_ok ? x : 0));
+        dot = dot + qa * cb;
+        na = na + qa * qa;
+        nb = nb + cb * cb;
+    }
+    const float denom = sqrtf(na * nb);
+    if (denom < 1e-30f) return 1.0f;
+    return 1.0f - dot / denom;
+}
+
 template <bool ASC>
 __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
     extern __shared__ __align__(16) unsigned char smem_fin[];
@@ -607,23 +677,38 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
     const int rn = min(ncand, a.R);
     float T = f32_from_orderable(sh_T);  // every row dropped inside a partition has coarse score <= T
     if (ncand > a.R) T = fmaxf(T, key_score<false>(s[a.R]));  // ... and so has every candidate cut here
-    for (int i = tid; i < a.R; i += blockDim.x) {
-        uint64_t key = KEY_NONE;
-        if (i < rn) {
-            uint32_t row = key_row(s[i]);
+    if (vec) {
+        // eight threads per row, four rows per warp, 32 rows per pass of the block (rows are independent: warp-local syncs only)
+        float* rowbuf = sq + ((dim + 3) & ~3) + (tid >> 3) * FIN_COLS;
+        const int lane = tid & 31;
+        for (int base = 0; base < a.R; base += 32) {
+            const int i = base + (tid >> 3);
+            const bool row_ok = i < rn;
+            const uint32_t row = row_ok ? key_row(s[i]) : 0u;
             const float* c = a.corpus + (size_t)row * dim;
-            float v;
-            if (a.metric == LB_IP) {
-                bool small = a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
-                v = small ? ip_single_order<false>(sq, c, dim, vec) : ip_batch8_order<false>(sq, c, dim, vec);
-            } else if (a.metric == LB_L2) {
-                v = l2_squared<false>(sq, c, dim, vec);
-            } else {
-                v = cosine_distance<false>(sq, c, dim, vec);
-            }
-            key = make_key<ASC>(v, row);
+            const bool two = a.metric == LB_IP && row_ok && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
+            const float v = rescore_row_lanes(a.metric, two, sq, c, dim, rowbuf, row_ok, lane);
+            if ((tid & 7) == 0 && i < a.R) e[i] = row_ok ? make_key<ASC>(v, row) : KEY_NONE;
         }
-        e[i] = key;
+    } else {
+        for (int i = tid; i < a.R; i += blockDim.x) {
+            uint64_t key = KEY_NONE;
+            if (i < rn) {
+                uint32_t row = key_row(s[i]);
+                const float* c = a.corpus + (size_t)row * dim;
+                float v;
+                if (a.metric == LB_IP) {
+                    bool small = a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
+                    v = small ? ip_single_order<false>(sq, c, dim, vec) : ip_batch8_order<false>(sq, c, dim, vec);
+                } else if (a.metric == LB_L2) {
+                    v = l2_squared<false>(sq, c, dim, vec);
+                } else {
+                    v = cosine_distance<false>(sq, c, dim, vec);
+                }
+                key = make_key<ASC>(v, row);
+            }
+            e[i] = key;
+        }
     }
     bitonic_sort_u64(e, a.R);
     const int kk = min(a.k, rn);

@@ -669,7 +669,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     f.out_counts = d_counts;
     f.uncertified = flags + 4;
     f.n_uncertified = flags + 1;
-    size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4;
+    size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)32 * tc::FIN_COLS * 4;  // + 32 row buffers
     if (metric_ascending(metric)) {
         LB_CUDA_TRY(cudaFuncSetAttribute(tc::finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         tc::finalize_kernel<true><<<nq, 256, fsmem, idx->stream>>>(f);
