@@ -140,6 +140,12 @@ int lb_index_set_plan(lb_index* idx, int plan);
 int lb_index_search(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k,
                     const uint64_t* allow_bits, uint64_t allow_words, uint32_t* out_rows, float* out_dists,
                     uint32_t* out_counts);
+/* The same search with every pair scored by compute_distance_f32 (src/distance/mod.rs:193-213: the single-row
+ * kernels, which for IP means two accumulators) on the exact scan — what Collection::search_range
+ * (src/engine.rs:6410-6483) and the pending-rows search (:3310-3360) do. */
+int lb_index_search_pairwise(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k,
+                             const uint64_t* allow_bits, uint64_t allow_words, uint32_t* out_rows, float* out_dists,
+                             uint32_t* out_counts);
 int lb_index_search_packed(lb_index* idx, int metric, const uint64_t* query_words, uint32_t nq, uint32_t k,
                            uint32_t* out_rows, float* out_dists, uint32_t* out_counts);
 

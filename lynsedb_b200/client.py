@@ -192,6 +192,58 @@ class Collection:
             self._flush_pending()
             self.COMMIT_FLAG = True
 
+    def load_lynsedb_directory(self, collection_path, dtype: str = "float32") -> int:
+        """Load the vectors of an existing LynseDB collection directory (vector_manifest.json + segment files + id_map.bin,
+        src/storage/vector_store.rs:24-60, :157-243) into this collection; one append per segment file.  Returns the rows added."""
+        from . import storage_reader as R
+
+        with self._lock:
+            if self._dim is None:
+                raise ValueError("collection dimension must be set to read a raw vector store")
+            if self._row_ids:
+                raise ValueError("load_lynsedb_directory needs an empty collection")
+            segments, id_map_path = R.read_manifest(collection_path, self._dim, dtype)
+            total = sum(r for _, r in segments)
+            ids = R.read_id_map(id_map_path, total)
+            ext = ids.tolist() if ids is not None else list(range(total))
+            if len(set(ext)) != len(ext):
+                raise IOError("id map holds duplicate ids")
+            for path, rows in segments:
+                if rows:
+                    self._ensure_store().append(R.read_segment(path, rows, self._dim, dtype))
+            self._row_ids = list(ext)
+            self._id_rows = {e: i for i, e in enumerate(ext)}
+        self._maybe_build_default_index()
+        return total
+
+    def search_range(self, vector, threshold: float, max_results: int = 1000):
+        """``(ids, distances)`` of every live row within ``threshold`` (<= for distances, >= for IP), best first, at most
+        ``max_results`` — ``Collection::search_range`` (src/engine.rs:6410-6483): per-pair ``compute_distance_f32`` order."""
+        q = np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1)
+        max_results = int(max_results)
+        with self._lock:
+            if max_results <= 0 or self._dim is None or not self._row_ids:
+                return np.empty(0, np.int64), np.empty(0, np.float32)
+            if q.shape[1] != self._dim:
+                raise ValueError(f"Dimension mismatch: expected {self._dim}, got {q.shape[1]}")
+            self._flush_pending()
+            want = min(max_results + len(self._tombstones), len(self._store))
+            if want > 2048:
+                raise ValueError("search_range is limited to max_results + deleted rows <= 2048 on this path")
+            rows, dists, counts = self._store.search(q, want, self._metric, pairwise=True)
+            asc = M.is_ascending(self._metric)
+            ids, out = [], []
+            for r, d in zip(rows[0, :int(counts[0])].tolist(), dists[0, :int(counts[0])].tolist()):
+                e = self._row_ids[r]
+                if e in self._tombstones or not (d <= threshold if asc else d >= threshold):
+                    continue
+                ids.append(e)
+                out.append(d)
+                if len(ids) == max_results:
+                    break
+            all_int = all(isinstance(i, (int, np.integer)) for i in ids)
+            return (np.asarray(ids, dtype=np.int64 if all_int else object), np.asarray(out, dtype=np.float32))
+
     flush = commit
 
     def delete(self, ids) -> int:

@@ -138,6 +138,7 @@ struct lb_index {
     DevBuf w_queries, w_qwords, w_allow, w_lists, w_counts, w_thr, w_out_rows, w_out_dists, w_out_counts;
     DevBuf w_qb, w_qnorm, w_cand_score, w_cand_row, w_cand_thr, w_flags, w_qstats, w_nq, w_sub_q, w_qmap;
     int plan = LB_PLAN_AUTO;
+    bool pairwise = false;  // this search scores every pair with the single-row kernels on the exact scan
     bool timing = false;
     lb_search_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -814,7 +815,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
         idx->stats.plan_used = 2;
         idx->stats.algorithmic_bytes = (uint64_t)idx->n * nw * 8;
-    } else if (idx->plan == LB_PLAN_AUTO && d_allow == nullptr && tc_supported(idx, metric) && k <= 256 && idx->n >= 64) {
+    } else if (idx->plan == LB_PLAN_AUTO && !idx->pairwise && d_allow == nullptr && tc_supported(idx, metric) && k <= 256 && idx->n >= 64) {
         LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr));
         kernels = idx->stats.kernels_launched;
         ms_dom = idx->stats.ms_dominant;
@@ -831,6 +832,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         r.allow_bits = d_allow;
         r.small_seg = idx->small_seg.as<uint32_t>();
         r.n_small = idx->n_small;
+        r.ip_single = idx->pairwise ? 1 : 0;
         r.out_rows = d_rows;
         r.out_dists = d_dists;
         r.out_counts = d_counts;
@@ -1181,6 +1183,23 @@ int lb_index_search(lb_index* idx, int metric, const float* queries, uint32_t nq
     if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
     return search_host_common(idx, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows, out_dists,
                               out_counts);
+}
+
+int lb_index_search_pairwise(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, const uint64_t* allow_bits,
+                             uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "pairwise search needs f32 rows");
+    if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
+    {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        idx->pairwise = true;
+    }
+    int st = search_host_common(idx, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows, out_dists, out_counts);
+    {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        idx->pairwise = false;
+    }
+    return st;
 }
 
 int lb_index_search_packed(lb_index* idx, int metric, const uint64_t* query_words, uint32_t nq, uint32_t k, uint32_t* out_rows,

@@ -149,3 +149,37 @@ def test_collection_ivf_mode(L):
         assert set(full.ids.tolist()) == set(exact.tolist()) and full.index_type == "IVF"
         some = coll.search(data[5], k=10, nprobe=2)
         assert len(some) == 10
+
+
+def test_load_lynsedb_directory_and_search_range(L, oracle, tmp_path):
+    import json
+
+    rng = np.random.default_rng(21)
+    dim = 12
+    blocks = [rng.random((700, dim), dtype=np.float32), rng.random((301, dim), dtype=np.float32)]
+    (tmp_path / "vector_segments").mkdir()
+    segs = []
+    for i, b in enumerate(blocks):
+        name = f"vector_segments/seg_{i}.bin"
+        b.astype("<f4").tofile(tmp_path / name)
+        segs.append({"file": name, "rows": b.shape[0]})
+    (tmp_path / "vector_manifest.json").write_text(json.dumps({"version": 1, "generation": 1, "id_map_file": "id_map.bin", "segments": segs}))
+    ids = np.arange(5000, 6001, dtype="<u8")
+    ids.tofile(tmp_path / "id_map.bin")
+    allv = np.concatenate(blocks)
+    with L.VectorDBClient() as client:
+        coll = client.create_collection("db", "disk", dim=dim, default_index="FLAT-L2")
+        assert coll.load_lynsedb_directory(tmp_path) == 1001 and coll.shape == (1001, dim)
+        q = rng.random(dim, dtype=np.float32)
+        r = coll.search(q, k=5)
+        want = oracle.store_batch_search(allv, q, 5, "l2", segment_rows=[700, 301], n_threads=1)
+        assert list(r.ids) == [int(x) + 5000 for x in want[0][0]]
+        # search_range: every live row within the threshold, per-pair kernel order, best first
+        d_all = np.array([oracle.compute_distance(q, v, "l2") for v in allv], dtype=np.float32)
+        thr = float(np.sort(d_all)[40])
+        coll.delete([int(np.argsort(d_all, kind="stable")[3]) + 5000])
+        got_ids, got_d = coll.search_range(q, thr, max_results=100)
+        order = [i for i in np.argsort(d_all, kind="stable") if d_all[i] <= thr and i != np.argsort(d_all, kind="stable")[3]]
+        assert got_ids.tolist() == [int(i) + 5000 for i in order]
+        assert np.array_equal(got_d.view(np.uint32), d_all[order].view(np.uint32))
+        assert len(coll.search_range(q, thr, max_results=7)[0]) == 7
