@@ -64,7 +64,8 @@ struct TcArgs {
     float* cand_score;        // [nq][P][KP]
     uint32_t* cand_row;       // [nq][P][KP]
     float* cand_thr;          // [nq][P]
-    int share_floor;          // 1: partitions of a query share a shortlist floor through gthr
+    int share_floor;          // 1: partitions of a query share a shortlist floor through gthr; 2: gthr holds a floor seeded by a
+                              // pre-pass over a sample of the corpus and is only read (large k)
     int floor_group;          // m: a published floor is the minimum of the floors of m consecutive partitions, so that at
                               // least m * KP rows score above it (m = 1 when k <= KP - 4, else ~10 k / KP)
     float* gfloor;            // [nq][P] floors of the single partitions (initialised to -inf; used when m > 1)
@@ -303,7 +304,7 @@ struct Shortlist {
     uint32_t* gthr;
     float* gfloor_q;     // floors of this query's partitions (floor groups)
     int group_m, n_parts, part;
-    bool q_valid, share;
+    bool q_valid, share, may_publish;
 
     __device__ __forceinline__ void set_groups(float* gfloor_row, int m, int P) {
         gfloor_q = gfloor_row;
@@ -336,15 +337,20 @@ struct Shortlist {
         thr_pub = lmin;
     }
 
-    __device__ __forceinline__ void reset(bool valid, bool share_floor, uint32_t* gthr_q) {
+    __device__ __forceinline__ void reset(bool valid, int share_floor, uint32_t* gthr_q) {
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             sc[j] = -INFINITY;
             rw[j] = ROW_NONE;
         }
         q_valid = valid;
-        share = share_floor;
+        share = share_floor != 0;
+        may_publish = share_floor == 1;
         gthr = gthr_q;
+        if (share_floor == 2 && valid) {  // seeded floor: available from the first tile
+            const uint32_t bits = *reinterpret_cast<volatile uint32_t*>(gthr_q);
+            if (bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(bits));
+        }
         lmin = -INFINITY;
         thr_pub = -INFINITY;
     }
@@ -356,7 +362,7 @@ struct Shortlist {
     // end of the warm-up round: the KP-th best score of the sample is a valid floor for every partition (KP rows of
     // the corpus score at least that much), so it becomes the shared floor and the list starts over
     __device__ __forceinline__ void absorb_sample() {
-        if (share && q_valid && group_m <= 1 && lmin > thr_g) {
+        if (may_publish && q_valid && group_m <= 1 && lmin > thr_g) {
             thr_g = lmin;
             atomicMax(gthr, f32_orderable(lmin));
         }
@@ -367,7 +373,7 @@ struct Shortlist {
         if (share && (tile_iter & 7u) == 0u) {
             if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
             g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
-            if (group_m > 1 && q_valid && lmin > thr_pub) publish();
+            if (may_publish && group_m > 1 && q_valid && lmin > thr_pub) publish();
         }
     }
     // replace the current minimum by (score, row) and recompute the minimum: ~70 ALU instructions, no memory
@@ -451,7 +457,7 @@ struct Shortlist {
                 }
             }
             // floor groups publish from poll_floor (every 8th tile): the group minimum costs m loads
-            if (share && q_valid && group_m <= 1 && lmin > thr_pub && lmin > thr_g) publish();
+            if (may_publish && q_valid && group_m <= 1 && lmin > thr_pub && lmin > thr_g) publish();
         }
     }
     __device__ __forceinline__ void flush(const TcArgs& a, uint32_t gq, uint32_t part) {
@@ -547,6 +553,25 @@ __global__ void prepare_queries_kernel(const float* __restrict__ queries, int nq
         out[d] = __float2bfloat16_rn(x);
     }
     if (lane == 0) qnorm[q] = norm;
+}
+
+// ---- seeded floors for large k ---------------------------------------------------------------------------------
+// After a pre-pass over a sample of the corpus: the r-th best coarse score of the sample, per query, becomes the
+// floor the main pass starts with (gthr).  It is a heuristic gate — about r * (rows / sample rows) rows of the corpus
+// score above it — and the certification of finalize_kernel is what keeps the result exact: a floor that turns out
+// too high leaves the query uncertified and it is re-run by the exact scan.
+__global__ void __launch_bounds__(256) seed_floor_kernel(const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_row, int P,
+                                                         int M, int r, uint32_t* __restrict__ gthr) {
+    extern __shared__ __align__(16) unsigned char smem_seed[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_seed);
+    const int q = blockIdx.x, total = P * KP;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        uint64_t key = KEY_NONE;
+        if (i < total && cand_row[(size_t)q * total + i] != ROW_NONE) key = make_key<false>(cand_score[(size_t)q * total + i], (uint32_t)i);
+        s[i] = key;
+    }
+    bitonic_sort_u64(s, M);
+    if (threadIdx.x == 0) gthr[q] = (r >= 1 && r <= M && s[r - 1] != KEY_NONE) ? f32_orderable(key_score<false>(s[r - 1])) : 0u;
 }
 
 // ---- finalize: shortlist -> exact-order rescore -> certified top-k -------------------------------------------------

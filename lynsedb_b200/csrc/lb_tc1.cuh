@@ -166,7 +166,7 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
             const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
             const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
             if (r == first_round) load_query_to_tmem(a.qb + (size_t)gq * a.Dp, a.Dp, lane_addr);  // the query tile never changes
-            sl.reset(q_valid, a.share_floor != 0, a.gthr + (q_valid ? gq : 0));
+            sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0));
             sl.part = (int)part;
             tcgen05_fence_before();
             __syncwarp();

@@ -17,10 +17,22 @@
 namespace lb {
 namespace tc {
 
-constexpr int P_STAGE_BYTES = KPS * HALF_BLOCK_BYTES;        // 16 KiB
-constexpr int P_NSTAGES = SMEM_RING_BYTES / P_STAGE_BYTES;   // 12
-// instruction descriptor: D=f32, A=B=bf16, K-major, N=64, M=256
-constexpr uint32_t P_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+// Tile shapes.  BN_ = 64: each CTA stages one 32-row half block per K block (16 KiB stages, 12 of them), accumulators
+// at TMEM columns [384, 512), any Dp <= 768.  BN_ = 128 (Dp <= 512, where the A operand leaves 256 columns free): each
+// CTA stages a whole 64-row shadow tile per K block (even CTA: tile 2t, odd CTA: tile 2t+1; 32 KiB stages, 6 of them),
+// accumulators at [256, 512); a tile is twice the tensor work for the same MMA -> epilogue -> MMA handshake, which is
+// what bounds the pass when a tile is only a few hundred cycles of MMA (small dimensions).
+template <int BN_>
+struct PairCfg {
+    static constexpr int kRowsPerCta = BN_ / 2;
+    static constexpr int kKbBytes = kRowsPerCta * 128;                  // one K block of this CTA's rows
+    static constexpr int kStageBytes = KPS * kKbBytes;                  // 16 / 32 KiB
+    static constexpr int kNStages = SMEM_RING_BYTES / kStageBytes;      // 12 / 6
+    static constexpr int kDCol = TMEM_COLS - 2 * BN_;                   // 384 / 256
+    static constexpr int kMaxDp = 2 * kDCol;                            // 768 / 512
+    // instruction descriptor: D=f32, A=B=bf16, K-major, N=BN_, M=256
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
     uint32_t r;
@@ -64,8 +76,15 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+template <int BN_>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
+    using Cfg = PairCfg<BN_>;
+    constexpr int P_NSTAGES = Cfg::kNStages;
+    constexpr int P_STAGE_BYTES = Cfg::kStageBytes;
+    constexpr uint32_t P_IDESC = Cfg::kIdesc;
+    constexpr int DCOL = Cfg::kDCol;   // shadows tc::DCOL
+    constexpr int BN = BN_;            // shadows tc::BN
     const uint32_t crank = cluster_ctarank();  // 0 = even CTA (issues the MMAs), 1 = odd CTA
     const int n_mgroups = (a.n_mtiles + 1) / 2;
     const int cluster_id = (int)(blockIdx.x >> 1);
@@ -153,9 +172,13 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                             if (crank == 0) mbar_arrive(full0 + 8u * stage);
                         } else {
                             // the pair's full barrier lives in the even CTA and counts the bytes landing in both CTAs
-                            if (crank == 0) mbar_arrive_expect_tx(full0 + 8u * stage, 2u * (uint32_t)kbc * HALF_BLOCK_BYTES);
-                            tma_load_4d_pair(smem_base + stage * P_STAGE_BYTES, s < n_full ? &tmap_full : &tmap_rem, (int)crank,
-                                             (int)(t * (uint32_t)nkb) + s * KPS, pair_full0 + 8u * stage);
+                            if (crank == 0) mbar_arrive_expect_tx(full0 + 8u * stage, 2u * (uint32_t)kbc * Cfg::kKbBytes);
+                            if (BN_ == 64)   // my 32-row half of shadow tile t
+                                tma_load_4d_pair(smem_base + stage * P_STAGE_BYTES, s < n_full ? &tmap_full : &tmap_rem, (int)crank,
+                                                 (int)(t * (uint32_t)nkb) + s * KPS, pair_full0 + 8u * stage);
+                            else             // the whole shadow tile 2t + crank (both halves)
+                                tma_load_4d_pair(smem_base + stage * P_STAGE_BYTES, s < n_full ? &tmap_full : &tmap_rem, 0,
+                                                 (int)((2u * t + crank) * (uint32_t)nkb) + s * KPS, pair_full0 + 8u * stage);
                         }
                         if (++stage == P_NSTAGES) { stage = 0; phase ^= 1u; }
                     }
@@ -227,7 +250,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
 #pragma unroll
                                     for (int k4 = 0; k4 < 4; ++k4)
                                         umma_pair_ts_bf16(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
-                                                          bdesc0 + (uint64_t)(kb * (HALF_BLOCK_BYTES >> 4) + k4 * 2), P_IDESC, 1u);
+                                                          bdesc0 + (uint64_t)(kb * (Cfg::kKbBytes >> 4) + k4 * 2), P_IDESC, 1u);
                                 }
                             }
                             umma_pair_commit(empty0 + 8u * stage);  // frees the stage in both CTAs once these MMAs have read it
@@ -269,7 +292,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
             const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
             if (r == first_round) load_query_to_tmem(a.qb + (size_t)gq * a.Dp, a.Dp, lane_addr);  // the query tile never changes
-            sl.reset(q_valid, a.share_floor != 0, a.gthr + (q_valid ? gq : 0));
+            sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0));
             sl.part = (int)part;
             tcgen05_fence_before();
             __syncwarp();
@@ -282,29 +305,34 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                 const long long ec1 = clock64();
                 tcgen05_fence_after();
                 uint32_t v[64];
-                if (!(a.debug_mode & 2)) {
-                    tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN, v);
-                    tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + 32, v + 32);
-                    tmem_ld_wait();
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(even_tempty0 + 8u * buf);  // accumulator is in registers
-                e_wait += ec1 - ec0;
-                e_ld += clock64() - ec1;
-                if (a.debug_mode & 2) continue;
-                const uint32_t row0 = t * BN;
-                if (a.dump != nullptr && r >= 0) {
-                    float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
+                for (int h = 0; h < BN_ / 64; ++h) {
+                    if (!(a.debug_mode & 2)) {
+                        tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + h * 64, v);
+                        tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + h * 64 + 32, v + 32);
+                        tmem_ld_wait();
+                    }
+                    if (h == BN_ / 64 - 1) {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(even_tempty0 + 8u * buf);  // accumulator is in registers
+                        e_wait += ec1 - ec0;
+                        e_ld += clock64() - ec1;
+                    }
+                    if (a.debug_mode & 2) continue;
+                    const uint32_t row0 = t * BN + h * 64;
+                    if (a.dump != nullptr && r >= 0) {
+                        float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
+                    }
+                    const long long sc0 = clock64();
+                    sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0);
+                    const long long sd = clock64() - sc0;
+                    e_scan += sd;
+                    if (sd > 400) { ++n_slow; e_slow += sd; }
+                    if (sd > e_max) e_max = sd;
                 }
-                const long long sc0 = clock64();
-                sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0);
-                const long long sd = clock64() - sc0;
-                e_scan += sd;
-                if (sd > 400) { ++n_slow; e_slow += sd; }
-                if (sd > e_max) e_max = sd;
             }
             if (ok) {
                 if (r < 0) sl.absorb_sample();

@@ -243,6 +243,12 @@ static bool tc_supported(const lb_index* idx, int metric) {
 }
 
 
+// corpus rows per accumulator tile: 128 for CTA pairs when the A operand leaves room for two 128-column accumulators
+static int tc_rows_per_tile(const lb_index* idx, int kind, bool pair) {
+    if (!pair || shadow_dp(idx, kind) > tc::PairCfg<128>::kMaxDp) return 64;
+    return tc_env_int("LYNSE_B200_TC_BN", 128) == 64 ? 64 : 128;
+}
+
 static int encode_shadow_map(CUtensorMap* out, void* base, int nkb, uint64_t n_tiles, int box_halves, int box_kb) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -265,7 +271,7 @@ static int ensure_shadow(lb_index* idx, int kind) {
         LB_TRY(idx->max_norm.ensure(3 * sizeof(float)));
         LB_CUDA_TRY(cudaMemsetAsync(idx->max_norm.p, 0, 3 * sizeof(float), idx->stream));
     }
-    const uint64_t need_tiles = ceil_div(idx->n, tc::BN);
+    const uint64_t need_tiles = (ceil_div(idx->n, tc::BN) + 1) & ~(uint64_t)1;  // even: the 128-row kernel reads tiles in pairs
     if (need_tiles > sh.cap_tiles) {
         // grow with head-room; the tiled image is rebuilt from the f32 rows (a derived structure, like the reference's
         // lazily built caches that are dropped on append, flat_mmap.rs:341)
@@ -523,7 +529,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     // one query tile: one CTA per partition (lb_tc1.cuh); more: CTA pairs (tcgen05 cta_group::2, lb_tc2.cuh)
     const bool pair = n_mtiles >= 2;
     const int cluster = pair ? 2 : 1;
-    const int BN = tc::BN;
+    const int BN = tc_rows_per_tile(idx, kind, pair);
     LB_TRY(ensure_shadow(idx, kind));
     LB_TRY(refresh_small_segments(idx));
     Shadow& sh = idx->shadow[kind];
@@ -549,9 +555,14 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     // well below the k-th best score overall, so the union of the shortlists must reach far past rank k: aim at
     // P*KP >= 32*k candidates (measured on C3, k = 100: P = 36 leaves 1385 of 1024 queries uncertified, P = 72
     // five, P >= 144 none).  LYNSE_B200_TC_PARTS overrides.
+    // Large k (no single partition floor is far enough past rank k): a pre-pass over 1/64 of the corpus seeds every
+    // query's floor (seed_floor_kernel); the main pass then only needs enough partitions for the true top-k not to
+    // crowd into one 16-entry list: P >= 0.75 k.
+    const bool seeded = k > tc::KP - 4 && tiles_total >= (uint32_t)(64 * 8) * (uint32_t)n_slots && dump == nullptr &&
+                        tc_env_int("LYNSE_B200_TC_SEED", 1) != 0;
     uint64_t parts_per_slot = 1;
     {
-        uint64_t want = ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
+        uint64_t want = seeded ? ((uint64_t)3 * k + 3) / 4 : ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
         const int env_parts = tc_env_int("LYNSE_B200_TC_PARTS", 0);
         if (env_parts > 0) want = (uint64_t)env_parts;
         while (n_slots * parts_per_slot < want && n_slots * (parts_per_slot + 1) <= 4096 / tc::KP) ++parts_per_slot;
@@ -560,9 +571,10 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     const uint32_t tiles_per_part = (uint32_t)ceil_div(tiles_total, P);
     P = ceil_div(tiles_total, tiles_per_part);
     parts_per_slot = ceil_div(P, n_slots);
-    LB_TRY(idx->w_cand_score.ensure((size_t)nq * P * tc::KP * 4));
-    LB_TRY(idx->w_cand_row.ensure((size_t)nq * P * tc::KP * 4));
-    LB_TRY(idx->w_cand_thr.ensure((size_t)nq * P * 4));
+    const uint64_t P_buf = std::max<uint64_t>(P, n_slots);
+    LB_TRY(idx->w_cand_score.ensure((size_t)nq * P_buf * tc::KP * 4));
+    LB_TRY(idx->w_cand_row.ensure((size_t)nq * P_buf * tc::KP * 4));
+    LB_TRY(idx->w_cand_thr.ensure((size_t)nq * P_buf * 4));
     LB_TRY(idx->w_flags.ensure((size_t)nq * 8 + 16));
     uint32_t* flags = idx->w_flags.as<uint32_t>();  // [0]=kernel error, [1]=n_uncertified, [4..]=per-query flags, then gthr[nq]
     LB_CUDA_TRY(cudaMemsetAsync(flags, 0, 16, idx->stream));
@@ -589,9 +601,10 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     // the first m partitions (30 % of the pass) and measured 8.9 ms against 7.6 ms without any sharing.
     const int m_req = k <= tc::KP - 4 ? 1 : (10 * k + tc::KP - 1) / tc::KP;
     a.share_floor = ((int)P >= m_req && (m_req == 1 || tc_env_int("LYNSE_B200_TC_GROUPS", 0) != 0)) ? 1 : 0;
+    if (seeded) a.share_floor = 2;
     a.floor_group = m_req;
     a.gfloor = nullptr;
-    if (a.share_floor && m_req > 1) {
+    if (a.share_floor == 1 && m_req > 1) {
         LB_TRY(idx->w_gfloor.ensure((size_t)nq * P * 4));
         fill_f32_kernel<<<(unsigned)std::min<uint64_t>(ceil_div((uint64_t)nq * P, 256), 1024), 256, 0, idx->stream>>>(
             idx->w_gfloor.as<float>(), (uint64_t)nq * P, -INFINITY);
@@ -635,15 +648,44 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (pair) {
-        LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-        if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
-        LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel, sh.tmap_full[1], sh.tmap_rem[1], a));
-    } else {
-        LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-        if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
-        LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel, sh.tmap_full[0], sh.tmap_rem[0], a));
+    auto launch_coarse = [&](const tc::TcArgs& args) -> int {
+        if (pair && BN == 128) {
+            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128>, sh.tmap_full[0], sh.tmap_rem[0], args));
+        } else if (pair) {
+            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<64>, sh.tmap_full[1], sh.tmap_rem[1], args));
+        } else {
+            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel, sh.tmap_full[0], sh.tmap_rem[0], args));
+        }
+        return LB_OK;
+    };
+    if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
+    if (seeded) {
+        // pre-pass: the first 1/64 of the tiles, one partition per slot, private floors; then the seed
+        tc::TcArgs sa = a;
+        const uint32_t S = std::max<uint32_t>(tiles_total / 64, (uint32_t)n_slots * 8);
+        sa.tiles_total = S;
+        sa.n_rows = (uint32_t)std::min<uint64_t>(idx->n, (uint64_t)S * BN);
+        sa.tiles_per_part = (uint32_t)ceil_div(S, n_slots);
+        sa.P = (int)ceil_div(S, sa.tiles_per_part);
+        sa.parts_per_slot = 1;
+        sa.share_floor = 0;
+        sa.gfloor = nullptr;
+        sa.sample_tiles = 0;
+        LB_TRY(launch_coarse(sa));
+        const int sm = next_pow2(sa.P * tc::KP);
+        // aim at ~10 k rows of the whole corpus above the seeded floor
+        int r = (int)ceil_div((uint64_t)10 * k * S, tiles_total);
+        r = std::max(4, std::min(r, sa.P * tc::KP / 2));
+        LB_CUDA_TRY(cudaFuncSetAttribute(tc::seed_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm * 8));
+        tc::seed_floor_kernel<<<nq, 256, (size_t)sm * 8, idx->stream>>>(sa.cand_score, sa.cand_row, sa.P, sm, r, a.gthr);
+        LB_CUDA_TRY(cudaGetLastError());
+        if (a.progress) LB_CUDA_TRY(cudaMemsetAsync(idx->w_progress.p, 0, (size_t)n_slots * tc::PROGRESS_STRIDE * 4, idx->stream));
+        idx->stats.kernels_launched += 2;
     }
+    LB_TRY(launch_coarse(a));
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
 
@@ -1972,7 +2014,7 @@ int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uin
         DeviceGuard g(idx->device);
         int n_mtiles = ((int)nq + tc::BM - 1) / tc::BM;
         n_mtiles = (n_mtiles + 1) & ~1;  // room for the padded query tile of a 2-CTA cluster
-        const int dbg_bn = tc::BN;
+        const int dbg_bn = tc_rows_per_tile(idx, tc::SHADOW_IP, (int)nq > tc::BM);
         const size_t ld = (size_t)ceil_div(n, dbg_bn) * dbg_bn;
         const size_t dump_elems = (size_t)n_mtiles * tc::BM * ld;
         const int k = (int)std::min<uint32_t>(n, 10);
