@@ -375,3 +375,18 @@ def test_flat_index_surface(L, oracle, tmp_path):
     assert len(reopened) == 300
     with pytest.raises(ValueError, match="Unknown metric"):
         idx.search(data[0], 3, "zzz")
+
+
+# ---- committed golden fixture through the C ABI ---------------------------------------------------------------------
+def test_golden_fixture_through_the_c_abi(L):
+    import json
+    from pathlib import Path
+
+    golden = json.loads((Path(__file__).parent / "golden" / "reference_known_answers.json").read_text())
+    for case in golden["compute_distance"]:
+        got = L.compute_distance(np.asarray(case["a"], np.float32), np.asarray(case["b"], np.float32), case["metric"])
+        assert abs(got - case["expected"]) <= case["abs_tol"], case
+    for case in golden["top_k_search"]:
+        ids, dists = L.top_k_search(np.asarray(case["query"], np.float32), np.asarray(case["candidates"], np.float32), case["metric"], case["k"])
+        assert ids.tolist() == case["ids"], case
+        assert np.allclose(dists, case["dists"], atol=1e-6), case

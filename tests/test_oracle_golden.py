@@ -331,3 +331,24 @@ def test_ivf_hamming_full_probe_matches_flat_distances(oracle):
     want = np.sort(np.array([oracle.compute_distance(q, data[r], "hamming") for r in range(n)], dtype=np.float32), kind="stable")[:10]
     _, got = oracle.ivf_search(data, cent, assign, q, 10, 16, "hamming")
     assert np.array_equal(got, want)
+
+
+# ---- the same pins as a committed fixture (tests/golden/) -------------------------------------------------------------
+def _golden():
+    import json
+    from pathlib import Path
+
+    return json.loads((Path(__file__).parent / "golden" / "reference_known_answers.json").read_text())
+
+
+def test_golden_fixture_compute_distance(oracle):
+    for case in _golden()["compute_distance"]:
+        got = oracle.compute_distance(np.asarray(case["a"], F), np.asarray(case["b"], F), case["metric"])
+        assert abs(got - case["expected"]) <= case["abs_tol"], case
+
+
+def test_golden_fixture_top_k(oracle):
+    for case in _golden()["top_k_search"]:
+        ids, dists = oracle.top_k_search(np.asarray(case["query"], F), np.asarray(case["candidates"], F), case["metric"], case["k"])
+        assert ids.tolist() == case["ids"], case
+        assert np.allclose(dists, case["dists"], atol=1e-6), case
