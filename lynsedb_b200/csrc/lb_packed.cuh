@@ -29,7 +29,8 @@ constexpr uint32_t PK_SMEM_Q = PK_SMEM_CAND + PK_TQ * PK_ROWS * 8;             /
 constexpr uint32_t PK_SMEM_THR = PK_SMEM_Q + PK_TQ * PK_W * 8;                 // gates [TQ] u64
 constexpr uint32_t PK_SMEM_CNT = PK_SMEM_THR + PK_TQ * 8;                      // candidate counts [TQ] u32, query popcounts [TQ] u32
 constexpr uint32_t PK_SMEM_BAR = PK_SMEM_CNT + PK_TQ * 8;                      // full[NSTAGES]
-constexpr uint32_t PK_SMEM_BYTES = PK_SMEM_BAR + 64 + 1024;
+constexpr uint32_t PK_SMEM_LISTS = PK_SMEM_BAR + 64;                           // optional [TQ][k] keys + [TQ] counts
+constexpr uint32_t PK_SMEM_BYTES = PK_SMEM_LISTS + 1024;                       // + the lists when ScanArgs::smem_lists
 
 // carry-save adder on 32-bit lanes: (a + b + c) = sum + 2 * carry, bitwise
 #define LB_CSA(h, l, a, b, c)                  \
@@ -78,14 +79,21 @@ __device__ __forceinline__ uint32_t popc1024_hs(const uint32_t* x) {
            __popc(ones);
 }
 
-// one warp folds n candidate keys (shared memory) of one query into its (partition, query) list in global memory
+// one warp folds n candidate keys (shared memory) of one query into its (partition, query) list; the list lives in
+// global memory (GLOBAL_LIST: read through L2 with __ldcg) or, for batches of a single query tile, in shared memory
+// for the whole kernel (a list update is then tens of cycles instead of two L2 round trips).
 // returns the new gate (KEY_NONE while the list is not full)
-__device__ __forceinline__ uint64_t warp_fold_candidates(const uint64_t* __restrict__ cand, int n, uint64_t* list, uint32_t* count_p,
-                                                         uint64_t* thr_p, int k, int lane) {
-    uint32_t cnt = *count_p;
-    uint64_t thr = cnt < (uint32_t)k ? KEY_NONE : *thr_p;
+template <bool GLOBAL_LIST>
+__device__ __forceinline__ uint64_t warp_fold_candidates_t(const uint64_t* __restrict__ cand, int n, uint64_t* list, uint32_t* count_p,
+                                                           uint64_t* thr_p, int k, int lane) {
+    auto ld = [&](const uint64_t* p) -> uint64_t { return GLOBAL_LIST ? __ldcg(p) : *reinterpret_cast<const volatile uint64_t*>(p); };
+    const uint32_t cnt0 = *reinterpret_cast<volatile uint32_t*>(count_p);
+    uint32_t cnt = cnt0;
+    uint64_t thr = 0xFFFFFFFFFFFFFFFFull;  // KEY_NONE
+    if (cnt0 >= (uint32_t)k) thr = *reinterpret_cast<volatile uint64_t*>(thr_p);
     for (int base = 0; base < n; base += 32) {
-        uint64_t key = base + lane < n ? cand[base + lane] : KEY_NONE;
+        uint64_t key = 0xFFFFFFFFFFFFFFFFull;
+        if (base + lane < n) key = cand[base + lane];
         unsigned m = __ballot_sync(0xffffffffu, key < thr);
         while (m) {
             int src = __ffs(m) - 1;
@@ -99,18 +107,18 @@ __device__ __forceinline__ uint64_t warp_fold_candidates(const uint64_t* __restr
                 if (cnt == (uint32_t)k) {
                     uint64_t mx = 0;
                     for (int idx = lane; idx < k; idx += 32) {
-                        uint64_t v = __ldcg(list + idx);
+                        uint64_t v = ld(list + idx);
                         mx = v > mx ? v : mx;
                     }
                     thr = warp_max_u64(mx);
                 }
             } else {
                 for (int idx = lane; idx < k; idx += 32)
-                    if (__ldcg(list + idx) == thr) list[idx] = kk;  // keys are unique: exactly one slot holds the worst
+                    if (ld(list + idx) == thr) list[idx] = kk;  // keys are unique: exactly one slot holds the worst
                 __syncwarp();
                 uint64_t mx = 0;
                 for (int idx = lane; idx < k; idx += 32) {
-                    uint64_t v = __ldcg(list + idx);
+                    uint64_t v = ld(list + idx);
                     mx = v > mx ? v : mx;
                 }
                 thr = warp_max_u64(mx);
@@ -121,8 +129,33 @@ __device__ __forceinline__ uint64_t warp_fold_candidates(const uint64_t* __restr
         *count_p = cnt;
         *thr_p = thr;
     }
+    __syncwarp();
     return thr;
 }
+__device__ __forceinline__ uint64_t warp_fold_candidates(const uint64_t* __restrict__ cand, int n, uint64_t* list, uint32_t* count_p,
+                                                         uint64_t* thr_p, int k, int lane) {
+    return warp_fold_candidates_t<true>(cand, n, list, count_p, thr_p, k, lane);
+}
+
+// Lists of a single-tile batch kept in shared memory: [tq][k] keys + [tq] counts, written back once at the end.
+struct SmemLists {
+    uint64_t* keys;    // [TQ][k]
+    uint32_t* counts;  // [TQ]
+    __device__ __forceinline__ void init(int tq, int tid, int nthreads) {
+        for (int i = tid; i < tq; i += nthreads) counts[i] = 0u;
+    }
+    __device__ __forceinline__ void write_back(const ScanArgs& a, int part, int tq, const uint64_t* sthr, int warp, int lane, int nwarps) {
+        for (int j = warp; j < tq; j += nwarps) {
+            const size_t lq = (size_t)part * a.nq + j;
+            const uint32_t cnt = counts[j];
+            for (int i = lane; i < (int)cnt; i += 32) a.lists[lq * a.k + i] = keys[(size_t)j * a.k + i];
+            if (lane == 0) {
+                a.counts[lq] = cnt;
+                a.thr[lq] = sthr[j];
+            }
+        }
+    }
+};
 
 // MODE: 0 = Hamming (popc(x ^ y)), 1 = Jaccard / Tanimoto, 2 = Dice (both from popc(x & y) and the two row popcounts)
 template <int MODE, bool HS>
@@ -138,6 +171,9 @@ __global__ void __launch_bounds__(PK_ROWS, 2) scan_packed16_kernel(const __grid_
     const uint32_t full0 = smem_base + PK_SMEM_BAR;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int part = blockIdx.x;
+    SmemLists sl;
+    sl.keys = reinterpret_cast<uint64_t*>(smem + PK_SMEM_LISTS);          // [nq <= TQ][k] when a.smem_lists
+    sl.counts = reinterpret_cast<uint32_t*>(sl.keys + (size_t)PK_TQ * a.k);
     const uint64_t part_begin = (uint64_t)part * a.rows_per_part;
     uint64_t part_end = part_begin + a.rows_per_part;
     if (part_end > a.n_rows) part_end = a.n_rows;
@@ -163,6 +199,7 @@ __global__ void __launch_bounds__(PK_ROWS, 2) scan_packed16_kernel(const __grid_
             sthr[tid] = KEY_NONE;  // the lists of this launch start empty (counts are zeroed by the host)
             scnt[tid] = 0u;
         }
+        if (a.smem_lists) sl.init(a.nq, tid, PK_ROWS);
         __syncthreads();
         if (tid < a.nq) {
             uint32_t p = 0;
@@ -264,7 +301,9 @@ __global__ void __launch_bounds__(PK_ROWS, 2) scan_packed16_kernel(const __grid_
                 const int n = (int)scnt[j];
                 if (n > 0) {
                     const size_t lq = (size_t)part * a.nq + (q0 + j);
-                    const uint64_t g = warp_fold_candidates(cand + j * PK_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                    const uint64_t g = (single_tile && a.smem_lists)
+                                           ? warp_fold_candidates_t<false>(cand + j * PK_ROWS, n, sl.keys + (size_t)j * a.k, sl.counts + j, sthr + j, a.k, lane)
+                                           : warp_fold_candidates(cand + j * PK_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
                     if (lane == 0) {
                         sthr[j] = g;
                         scnt[j] = 0u;
@@ -274,6 +313,7 @@ __global__ void __launch_bounds__(PK_ROWS, 2) scan_packed16_kernel(const __grid_
             __syncthreads();
         }
     }
+    if (single_tile && a.smem_lists) sl.write_back(a, part, a.nq, sthr, warp, lane, PK_ROWS / 32);
 }
 
 }  // namespace lb

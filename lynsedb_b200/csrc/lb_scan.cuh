@@ -49,6 +49,7 @@ struct ScanArgs {
     uint32_t* counts;           // [P][nq]
     uint64_t* thr;              // [P][nq] current worst kept key (valid when count == k)
     uint32_t rows_per_part;     // multiple of SCAN_THREADS
+    int smem_lists;             // 1: a batch of one query tile keeps its top-k lists in shared memory (room reserved by the host)
 };
 
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
@@ -319,7 +320,7 @@ struct MergeArgs {
     uint32_t* out_counts;    // [*]
 };
 
-__global__ void __launch_bounds__(256) merge_lists_kernel(MergeArgs a) {
+__global__ void __launch_bounds__(1024) merge_lists_kernel(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_merge[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_merge);
     const int q = blockIdx.x;

@@ -170,6 +170,9 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
     uint64_t* sthr = reinterpret_cast<uint64_t*>(sq + S2_TQ * dim_pad);                 // [TQ]
     uint32_t* scnt = reinterpret_cast<uint32_t*>(sthr + S2_TQ);                         // [TQ]
     float* sna = reinterpret_cast<float*>(scnt + S2_TQ);                                // [TQ] cosine |q|^2
+    SmemLists sl;
+    sl.keys = reinterpret_cast<uint64_t*>(sna + S2_TQ);                                 // [TQ][k] when a.smem_lists
+    sl.counts = reinterpret_cast<uint32_t*>(sl.keys + (size_t)S2_TQ * a.k);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int part = blockIdx.x;
     const bool vec = (dim & 3) == 0;
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
             sthr[tid] = KEY_NONE;  // the lists of this launch start empty (counts are zeroed by the host)
             scnt[tid] = 0u;
         }
+        if (a.smem_lists) sl.init(a.nq, tid, S2_ROWS);
         __syncthreads();
     }
 
@@ -256,7 +260,9 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
                 const int n = (int)scnt[j];
                 if (n > 0) {
                     const size_t lq = (size_t)part * a.nq + (q0 + j);
-                    const uint64_t g = warp_fold_candidates(cand + j * S2_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                    const uint64_t g = (single_tile && a.smem_lists)
+                                           ? warp_fold_candidates_t<false>(cand + j * S2_ROWS, n, sl.keys + (size_t)j * a.k, sl.counts + j, sthr + j, a.k, lane)
+                                           : warp_fold_candidates(cand + j * S2_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
                     if (lane == 0) {
                         sthr[j] = g;   // a single-tile batch keeps its gates in shared memory across row blocks
                         scnt[j] = 0u;
@@ -266,6 +272,7 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
             if (single_tile) __syncthreads();  // candidates folded before the next block reuses the buffers
         }
     }
+    if (single_tile && a.smem_lists) sl.write_back(a, part, a.nq, sthr, warp, lane, S2_ROWS / 32);
 }
 
 // ---- the same scan with the rows staged through shared memory by TMA -------------------------------------------
@@ -274,13 +281,14 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
 // one TMA box [256 rows x 128 B] per chunk (SWIZZLE_128B, so thread r finds 16-byte piece c of its row at piece
 // c ^ (r & 7) and the 128-bit reads are bank-conflict free), four stages in flight.  The chunk order, and with it
 // every accumulator chain, is unchanged.
-constexpr int S3_NSTAGES = 4;
+constexpr int S3_NSTAGES = 6;                  // 192 KiB in flight per SM: the pass is latency-bound below that
 constexpr int S3_STAGE_BYTES = S2_ROWS * 128;  // 32 KiB: 256 rows x 32 floats
+constexpr int S3_TQ = 4;                       // queries per tile (this kernel serves batches of <= 4)
 
 template <int METRIC, bool IP2>
 __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __grid_constant__ CUtensorMap tmap, ScanArgs a) {
     using Op = Scan2Op<METRIC, IP2>;
-    constexpr int S2_TQ = Op::kTQ;
+    constexpr int S2_TQ = Op::kTQ < S3_TQ ? Op::kTQ : S3_TQ;
     constexpr bool ASC = METRIC != LB_IP;
     extern __shared__ __align__(16) unsigned char smem_s3[];
     const uint32_t smem_base = (tc::smem_u32(smem_s3) + 1023u) & ~1023u;
@@ -293,6 +301,9 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
     float* sna = reinterpret_cast<float*>(scnt + S2_TQ);                                // [TQ]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sna + S2_TQ + 2);                      // full[NSTAGES]
     const uint32_t full0 = tc::smem_u32(bars);
+    SmemLists sl;
+    sl.keys = bars + S3_NSTAGES;                                                        // [TQ][k] when a.smem_lists
+    sl.counts = reinterpret_cast<uint32_t*>(sl.keys + (size_t)S2_TQ * a.k);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int part = blockIdx.x;
     const int chunks = dim >> 3;                 // whole 8-float chunks (the rest is the scalar tail)
@@ -335,6 +346,7 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
             sthr[tid] = KEY_NONE;
             scnt[tid] = 0u;
         }
+        if (a.smem_lists) sl.init(a.nq, tid, S2_ROWS);
         __syncthreads();
     }
 
@@ -414,7 +426,9 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
                 const int n = (int)scnt[j];
                 if (n > 0) {
                     const size_t lq = (size_t)part * a.nq + (q0 + j);
-                    const uint64_t g = warp_fold_candidates(cand + j * S2_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
+                    const uint64_t g = (single_tile && a.smem_lists)
+                                           ? warp_fold_candidates_t<false>(cand + j * S2_ROWS, n, sl.keys + (size_t)j * a.k, sl.counts + j, sthr + j, a.k, lane)
+                                           : warp_fold_candidates(cand + j * S2_ROWS, n, a.lists + lq * a.k, a.counts + lq, a.thr + lq, a.k, lane);
                     if (lane == 0) {
                         sthr[j] = g;
                         scnt[j] = 0u;
@@ -424,6 +438,7 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
             if (single_tile) __syncthreads();
         }
     }
+    if (single_tile && a.smem_lists) sl.write_back(a, part, a.nq, sthr, warp, lane, S2_ROWS / 32);
 }
 
 }  // namespace lb

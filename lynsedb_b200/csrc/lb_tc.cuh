@@ -669,7 +669,7 @@ __device__ __forceinline__ float rescore_row_lanes(int metric, bool two_acc_ip, 
 }
 
 template <bool ASC>
-__global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
+__global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     extern __shared__ __align__(16) unsigned char smem_fin[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_fin);            // [M1] coarse keys
     uint64_t* e = s + a.M1;                                         // [R] exact keys
@@ -703,10 +703,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
     float T = f32_from_orderable(sh_T);  // every row dropped inside a partition has coarse score <= T
     if (ncand > a.R) T = fmaxf(T, key_score<false>(s[a.R]));  // ... and so has every candidate cut here
     if (vec) {
-        // eight threads per row, four rows per warp, 32 rows per pass of the block (rows are independent: warp-local syncs only)
+        // eight threads per row, four rows per warp, blockDim/8 rows per pass of the block (rows are independent:
+        // warp-local syncs only)
         float* rowbuf = sq + ((dim + 3) & ~3) + (tid >> 3) * FIN_COLS;
         const int lane = tid & 31;
-        for (int base = 0; base < a.R; base += 32) {
+        const int rows_per_pass = (int)(blockDim.x >> 3);
+        for (int base = 0; base < a.R; base += rows_per_pass) {
             const int i = base + (tid >> 3);
             const bool row_ok = i < rn;
             const uint32_t row = row_ok ? key_row(s[i]) : 0u;

@@ -312,8 +312,8 @@ struct ScanPlan {
     int P;
     uint32_t rows_per_part;
 };
-static ScanPlan plan_scan(const lb_index* idx, uint64_t n_rows, int nq, int k) {
-    uint64_t P = std::min<uint64_t>(ceil_div(n_rows, SCAN_THREADS), (uint64_t)idx->sm_count * 2);
+static ScanPlan plan_scan(const lb_index* idx, uint64_t n_rows, int nq, int k, int ctas_per_sm = 2) {
+    uint64_t P = std::min<uint64_t>(ceil_div(n_rows, SCAN_THREADS), (uint64_t)idx->sm_count * ctas_per_sm);
     // bound the candidate lists to 512 MiB
     uint64_t max_p = std::max<uint64_t>(1, (512ull << 20) / ((uint64_t)nq * k * 8));
     P = std::max<uint64_t>(1, std::min(P, max_p));
@@ -348,7 +348,12 @@ struct ScanRequest {
 
 // scan + merge on idx->stream (k <= n_rows, k <= 2048)
 static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
-    ScanPlan sp = plan_scan(idx, r.n_rows, r.nq, r.k);
+    // the TMA-staged f32 scan runs one CTA per SM (its ring takes the shared memory): one partition per SM
+    const bool tma_f32 = !r.words && scan2_supported(r.metric) && r.row_stats == nullptr && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+                         r.row_ids == nullptr && (r.dim & 3) == 0 && r.dim >= 8 && r.n_rows >= 4096 && r.nq <= 4 &&
+                         tc_env_int("LYNSE_B200_SCAN_TMA", 1) != 0 &&
+                         (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)S3_TQ * (S2_ROWS * 8 + ((r.dim + 3) & ~3) * 4 + 256 * 8) + 2048 <= 226 * 1024;
+    ScanPlan sp = plan_scan(idx, r.n_rows, r.nq, r.k, tma_f32 ? 1 : 2);
     size_t nl = (size_t)sp.P * r.nq;
     LB_TRY(idx->w_lists.ensure(nl * r.k * 8));
     LB_TRY(idx->w_counts.ensure(nl * 4));
@@ -394,9 +399,11 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
         const int mode = r.metric == LB_HAMMING ? 0 : (r.metric == LB_DICE ? 2 : 1);
 #define LB_LAUNCH_PK(MODE, HSV)                                                                                              \
     do {                                                                                                                     \
+        a.smem_lists = (r.nq <= PK_TQ && r.k <= 256) ? 1 : 0;                                                                \
+        const size_t pk_smem = PK_SMEM_BYTES + (a.smem_lists ? (size_t)PK_TQ * r.k * 8 + PK_TQ * 4 + 16 : 0);                \
         LB_CUDA_TRY(cudaFuncSetAttribute(scan_packed16_kernel<MODE, HSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                         (int)PK_SMEM_BYTES));                                                               \
-        scan_packed16_kernel<MODE, HSV><<<sp.P, PK_ROWS, PK_SMEM_BYTES, idx->stream>>>(tmap, a);                             \
+                                         (int)pk_smem));                                                                     \
+        scan_packed16_kernel<MODE, HSV><<<sp.P, PK_ROWS, pk_smem, idx->stream>>>(tmap, a);                                   \
     } while (0)
         if (mode == 0) { if (hs) LB_LAUNCH_PK(0, true); else LB_LAUNCH_PK(0, false); }
         else if (mode == 1) { if (hs) LB_LAUNCH_PK(1, true); else LB_LAUNCH_PK(1, false); }
@@ -427,9 +434,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
         // contiguous rows of a 16-byte-multiple width go through TMA-staged shared memory
         // (measured on 10M x 768: 4.55 TB/s against 3.74 TB/s at one query, 8.8 against 9.4 ms at four; from eight
         // queries on the pass is bound by the shared-memory reads of the queries and the direct version is as fast)
-        const bool use_tma = r.row_ids == nullptr && (r.dim & 3) == 0 && r.dim >= 8 && r.n_rows >= 4096 && r.nq <= 4 &&
-                             tc_env_int("LYNSE_B200_SCAN_TMA", 1) != 0 &&
-                             (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)8 * (S2_ROWS * 8 + dim_pad * 4) + 2048 <= 220 * 1024;
+        const bool use_tma = tma_f32;
         if (use_tma) {
             PFN_encodeTiled enc = get_encode_tiled();
             if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -444,9 +449,10 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
             if (cr != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled (f32 rows) failed with CUresult " + std::to_string((int)cr));
 #define LB_LAUNCH_S3(M, IP2V)                                                                                                 \
     do {                                                                                                                      \
-        constexpr int tqv = Scan2Op<M, IP2V>::kTQ;                                                                            \
+        constexpr int tqv = Scan2Op<M, IP2V>::kTQ < S3_TQ ? Scan2Op<M, IP2V>::kTQ : S3_TQ;                                    \
+        a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                                   \
         const size_t smem = (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 +      \
-                            (size_t)tqv * 16 + 128 + 1024;                                                                     \
+                            (size_t)tqv * 16 + 128 + 1024 + (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);         \
         LB_CUDA_TRY(cudaFuncSetAttribute(scan_stream_tma_kernel<M, IP2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         scan_stream_tma_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(tmap, a);                                       \
     } while (0)
@@ -464,7 +470,9 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
 #define LB_LAUNCH_S2(M, IP2V)                                                                                             \
     do {                                                                                                                  \
         constexpr int tqv = Scan2Op<M, IP2V>::kTQ;                                                                        \
-        const size_t smem = (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 + (size_t)tqv * 16 + 64;                \
+        a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                               \
+        const size_t smem = (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 + (size_t)tqv * 16 + 64 +                \
+                            (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);                                     \
         LB_CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<M, IP2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         scan_stream_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(a);                                             \
     } while (0)
@@ -508,7 +516,8 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
     m.out_rows = r.out_rows;
     m.out_dists = r.out_dists;
     m.out_counts = r.out_counts;
-    merge_lists_kernel<<<r.nq, 256, (size_t)m.M * 8, idx->stream>>>(m);
+    // few queries: few blocks, so each gets 1024 threads (the block-wide bitonic sort is the latency of a single-query call)
+    merge_lists_kernel<<<r.nq, r.nq <= 64 ? 1024 : 256, (size_t)m.M * 8, idx->stream>>>(m);
     LB_CUDA_TRY(cudaGetLastError());
     if (kernels) *kernels += 2;
     idx->stats.n_partitions = sp.P;
@@ -712,13 +721,14 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     f.out_counts = d_counts;
     f.uncertified = flags + 4;
     f.n_uncertified = flags + 1;
-    size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)32 * tc::FIN_COLS * 4;  // + 32 row buffers
+    const int fin_threads = nq <= 64 ? 1024 : 256;  // few queries: few blocks, so each gets 1024 threads
+    size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)(fin_threads / 8) * tc::FIN_COLS * 4;  // + row buffers
     if (metric_ascending(metric)) {
         LB_CUDA_TRY(cudaFuncSetAttribute(tc::finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        tc::finalize_kernel<true><<<nq, 256, fsmem, idx->stream>>>(f);
+        tc::finalize_kernel<true><<<nq, fin_threads, fsmem, idx->stream>>>(f);
     } else {
         LB_CUDA_TRY(cudaFuncSetAttribute(tc::finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        tc::finalize_kernel<false><<<nq, 256, fsmem, idx->stream>>>(f);
+        tc::finalize_kernel<false><<<nq, fin_threads, fsmem, idx->stream>>>(f);
     }
     LB_CUDA_TRY(cudaGetLastError());
     idx->stats.kernels_launched += 3;
