@@ -44,8 +44,14 @@ class Collection:
 
     def __init__(self, name: str, dim: Optional[int] = None, *, dtypes: str = "float32", default_index: Optional[str] = "FLAT-IP",
                  description: Optional[str] = None, device: int = 0):
-        if dtypes != "float32":
-            raise ValueError("only dtypes='float32' is supported on this path (float16 storage is a next-round item)")
+        if dtypes not in ("float32", "float16"):
+            raise ValueError(f"unsupported dtypes: {dtypes!r}")
+        # float16 collections: vectors are rounded to IEEE binary16 at write time exactly as the reference encodes them
+        # (src/storage/dtype.rs:60-67, round-to-nearest-even) and kept DECODED (f32) in HBM, i.e. every search takes
+        # the arithmetic of the reference's F16 batch path, which decodes the store and runs the f32 kernels
+        # (src/engine.rs:5440-5474); the half-width HBM layout with the scalar f16 kernels of the single-query path
+        # (src/distance/simd.rs:805-1092) is not implemented.
+        self._dtypes = dtypes
         self.name = name
         self.description = description
         self._dim = int(dim) if dim else None
@@ -92,6 +98,9 @@ class Collection:
     def index_mode(self) -> Optional[str]:
         return self._index_mode
 
+    def vector_dtype(self) -> str:
+        return self._dtypes
+
     def max_id(self) -> int:
         ints = [i for i in self._row_ids if isinstance(i, (int, np.integer)) and not isinstance(i, bool)]
         return int(max(ints)) if ints else -1
@@ -123,6 +132,8 @@ class Collection:
         elif vec.ndim != 2:
             raise ValueError("vectors must be a 1D vector or a 2D matrix")
         vec = np.ascontiguousarray(vec, dtype=np.float32)
+        if self._dtypes == "float16":
+            vec = vec.astype(np.float16).astype(np.float32)
         n = vec.shape[0]
         if n == 0:
             raise ValueError("vectors cannot be empty")
@@ -192,7 +203,7 @@ class Collection:
             self._flush_pending()
             self.COMMIT_FLAG = True
 
-    def load_lynsedb_directory(self, collection_path, dtype: str = "float32") -> int:
+    def load_lynsedb_directory(self, collection_path, dtype: Optional[str] = None) -> int:
         """Load the vectors of an existing LynseDB collection directory (vector_manifest.json + segment files + id_map.bin,
         src/storage/vector_store.rs:24-60, :157-243) into this collection; one append per segment file.  Returns the rows added."""
         from . import storage_reader as R
@@ -202,6 +213,7 @@ class Collection:
                 raise ValueError("collection dimension must be set to read a raw vector store")
             if self._row_ids:
                 raise ValueError("load_lynsedb_directory needs an empty collection")
+            dtype = dtype or self._dtypes
             segments, id_map_path = R.read_manifest(collection_path, self._dim, dtype)
             total = sum(r for _, r in segments)
             ids = R.read_id_map(id_map_path, total)

@@ -158,3 +158,20 @@ def test_database_limit(fake):
         c.create_database(f"d{i}")
     with pytest.raises(ValueError, match="maximum number of databases"):
         c.create_database("one_too_many")
+
+
+def test_float16_collection_rounds_like_the_reference_encoder(fake):
+    # src/engine.rs:8043-8077 (f16_collection_batch_search_reuses_decoded_candidates)
+    coll = Collection("c", 4, dtypes="float16")
+    coll.add([10, 11, 12], vectors=np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0.5, 0.5, 0, 0]], np.float32))
+    res = coll.batch_search(np.array([[1, 0, 0, 0], [0, 1, 0, 0]], np.float32), k=2)
+    assert list(res[0].ids) == [10, 12] and list(res[1].ids) == [11, 12]
+    assert coll.vector_dtype() == "float16"
+    coll2 = Collection("d", 2, dtypes="float16", default_index="FLAT-L2")
+    v = np.array([[0.1, 0.2]], np.float32)
+    coll2.add(vectors=v)
+    stored = v.astype(np.float16).astype(np.float32)
+    d = coll2.search(v[0], k=1).distances[0]
+    assert d == pytest.approx(float(((stored[0] - v[0]) ** 2).sum()), rel=1e-6) and d > 0   # the f16 rounding is visible
+    with pytest.raises(ValueError):
+        Collection("e", 2, dtypes="int8")
