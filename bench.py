@@ -62,19 +62,39 @@ def parse_args():
 
 
 def measured_peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) when present, else the profiling guide's fallback.
+    The file's key names are matched loosely: an HBM copy bandwidth, a burst and a sustained bf16 GEMM throughput."""
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     path = ROOT / "MEASURED_PEAKS.json"
-    if path.exists():
-        try:
-            d = json.loads(path.read_text())
-            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
-                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
-        except Exception:
-            pass
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    if not path.exists():
+        return fallback
+    try:
+        flat = {}
+
+        def walk(prefix, node):
+            if isinstance(node, dict):
+                for key, val in node.items():
+                    walk(f"{prefix}.{key}".lower(), val)
+            elif isinstance(node, (int, float)) and not isinstance(node, bool):
+                flat[prefix] = float(node)
+
+        walk("", json.loads(path.read_text()))
+        hbm = [v for k, v in flat.items() if "hbm" in k and ("gb" in k or "tb" in k or "bandwidth" in k or "bw" in k)]
+        sus = [v for k, v in flat.items() if "bf16" in k and "sustain" in k]
+        burst = [v for k, v in flat.items() if "bf16" in k and "sustain" not in k and ("tflop" in k or "tf" in k or "flops" in k)]
+        if not hbm or not (sus or burst):
+            return fallback
+        h = hbm[0] * (1000.0 if hbm[0] < 100 else 1.0)       # TB/s -> GB/s
+        b = (burst or sus)[0]
+        su = (sus or burst)[0]
+        scale = (lambda x: x * 1000.0 if x < 20 else x)       # PFLOP/s -> TFLOP/s
+        return {"hbm_gbs": h, "bf16_tflops": scale(b), "bf16_tflops_sustained": scale(su), "source": "measured"}
+    except Exception:
+        return fallback
 
 
 def ncu_traffic(args, world, nq):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the dominant kernel, per launch, from the committed
     `ncu --set full` capture of this same command (profiles/r1_coarse_pair_ncu.json); None when the run is not the
     captured configuration."""
     if args.workload != "c2" or args.rows or args.nq or world != 1 or args.plan != "auto":
@@ -83,8 +103,7 @@ def ncu_traffic(args, world, nq):
         d = json.loads((ROOT / "profiles" / "r1_coarse_pair_ncu.json").read_text())["kernels"][0]
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
-        return {"bytes_per_launch": rd["value"] * mult[rd["unit"]] + wr["value"] * mult[wr["unit"]],
-                "source": "profiles/r1_coarse_pair_ncu.json (ncu --set full, one launch)"}
+        return rd["value"] * mult[rd["unit"]] + wr["value"] * mult[wr["unit"]]
     except Exception:
         return None
 
@@ -439,6 +458,8 @@ def main():
         ach = flops_per_launch / (dom_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(args, world, nq),
+                    "traffic_source": "profiles/r1_coarse_pair_ncu.json (ncu --set full, one launch of this command)",
+                    "algorithmic_bytes": float(st["algorithmic_bytes"]),
                     "kernel": "lb::tc::coarse_pair_kernel" if nq > 128 else "lb::tc::coarse_single_kernel", "kernel_ms": dom_ms,
                     "peak_source": peaks["source"] + " (sustained bf16: the kernel is timed inside a long step)",
                     "hbm_gbs_of_kernel": st["algorithmic_bytes"] / (dom_ms * 1e-3) / 1e9}

@@ -390,3 +390,54 @@ def test_golden_fixture_through_the_c_abi(L):
         ids, dists = L.top_k_search(np.asarray(case["query"], np.float32), np.asarray(case["candidates"], np.float32), case["metric"], case["k"])
         assert ids.tolist() == case["ids"], case
         assert np.allclose(dists, case["dists"], atol=1e-6), case
+
+
+# ---- mid-size corpora: the lockstep slots, the seeded floors of the large-k path and the 128-row tiles ---------------
+def _oracle_ids_scores(oracle, corpus, queries, k, metric):
+    ids, d, c = oracle.store_batch_search(corpus, queries, k, metric, n_threads=oracle.host_threads())
+    assert np.all(c == k)
+    return ids.astype(np.uint32), d
+
+
+def test_tc_lockstep_mid_size_matches_oracle(L, oracle):
+    n, dim, nq, k = 300_000, 96, 600, 10          # five query tiles -> three query groups streaming in lockstep
+    corpus, queries = _data(n, dim, 301), _data(nq, dim, 302)
+    with L.DeviceIndex(dim) as idx:
+        for lo in range(0, n, 100_000):
+            idx.append(corpus[lo:lo + 100_000])
+        rows, dists, counts = idx.search(queries, k, "ip")
+        st = idx.last_stats()
+    assert st["plan_used"] == 1 and st["n_fallback"] == 0 and np.all(counts == k)
+    want_ids, want_d = _oracle_ids_scores(oracle, corpus, queries, k, "ip")
+    assert np.array_equal(rows, want_ids)
+    assert np.array_equal(dists.view(np.uint32), want_d.view(np.uint32))
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+def test_tc_large_k_seeded_floors_match_oracle(L, oracle, metric):
+    # k > 12 on a corpus long enough for the pre-pass (>= 9216 tiles of 128 rows): seeded floors + 128-row tiles
+    n, dim, nq, k = 1_250_000, 64, 200, 50
+    corpus, queries = _data(n, dim, 311), _data(nq, dim, 312)
+    with L.DeviceIndex(dim) as idx:
+        for lo in range(0, n, 250_000):
+            idx.append(corpus[lo:lo + 250_000])
+        rows, dists, counts = idx.search(queries, k, metric)
+        st = idx.last_stats()
+    assert st["plan_used"] == 1 and np.all(counts == k), st
+    want_ids, want_d = _oracle_ids_scores(oracle, corpus, queries, k, metric)
+    assert np.array_equal(rows, want_ids)
+    assert np.array_equal(dists.view(np.uint32), want_d.view(np.uint32))
+
+
+def test_packed_two_million_rows_matches_oracle(L, oracle):
+    from lynsedb_b200 import synthetic
+
+    n, nq, k = 2_000_000, 40, 32
+    q = synthetic.rows_packed(43, np.arange(nq), 16)
+    with L.DeviceIndex(1024, "packed") as idx:
+        idx.append_synthetic(n, 42, 0)
+        for metric in ("hamming", "tanimoto"):
+            rows, dists, counts = idx.search(q, k, metric)
+            data = synthetic.rows_packed(42, np.arange(n), 16)
+            o_ids, o_d, o_c = oracle.packed_batch_search(data, q, k, metric, n_threads=oracle.host_threads())
+            assert np.array_equal(rows, o_ids.astype(np.uint32)) and np.array_equal(dists.view(np.uint32), o_d.view(np.uint32))
