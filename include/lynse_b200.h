@@ -185,6 +185,13 @@ int lb_ivf_assignments(const lb_ivf* ivf, uint32_t* out);    /* [n_rows] */
  * allow_bits: optional subset filter (SearchParams::subset), same layout as lb_index_search. */
 int lb_ivf_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, uint32_t nprobe, const uint64_t* allow_bits,
                   uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts);
+/* replaces IvfFlatMmap::search (src/storage/ivf_flat_mmap.rs:225-300; pyo3 `_core.IvfFlatIndex.search`,
+ * src/python/mod.rs:2128-2155) over an index trained with metric L2 (IvfFlatMmap::build -> kmeans::train_l2,
+ * ivf_flat_mmap.rs:96-101): partitions are chosen by find_nearest_centroids (:383-446) under the SEARCH metric,
+ * with the routing-dimension shortlist for inner product on dim >= 64 and >= 64 partitions; every row of the
+ * probed partitions is scored with compute_distance_f32; no corpus fallback.  Rows are build-data positions. */
+int lb_ivf_flat_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, uint32_t nprobe, int metric,
+                       uint32_t* out_rows, float* out_dists, uint32_t* out_counts);
 
 /* ---- device / pinned memory helpers (bench + tests; no torch) ---------- */
 int lb_device_malloc(int device, uint64_t bytes, void** out);

@@ -4,12 +4,12 @@ Only the search hot path of LynseDB is implemented here; the nat
 hand-written CUDA for sm_100a loaded through ctypes (``lynsedb_b200/liblynse_b200.so``).
 """
 from . import metrics
-from ._backend import FlatIndex, compute_distance, top_k_search
+from ._backend import FlatIndex, IvfFlatIndex, compute_distance, top_k_search
 from .client import Collection, Database, VectorDBClient
 from .index import DeviceIndex, make_allow_bits
 from .ivf import IVFIndex
 from .result_view import ResultView
 
 __version__ = "0.1.0"
-__all__ = ["VectorDBClient", "Database", "Collection", "DeviceIndex", "IVFIndex", "FlatIndex", "ResultView", "compute_distance",
+__all__ = ["VectorDBClient", "Database", "Collection", "DeviceIndex", "IVFIndex", "FlatIndex", "IvfFlatIndex", "ResultView", "compute_distance",
            "top_k_search", "make_allow_bits", "metrics"]

@@ -75,6 +75,7 @@ SIGNATURES = {
     "lb_ivf_centroids": (C.c_int, [_vp, _f32p]),
     "lb_ivf_assignments": (C.c_int, [_vp, _u32p]),
     "lb_ivf_search": (C.c_int, [_vp, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, C.c_uint64, _u32p, _f32p, _u32p]),
+    "lb_ivf_flat_search": (C.c_int, [_vp, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _u32p, _f32p, _u32p]),
     "lb_device_malloc": (C.c_int, [C.c_int, C.c_uint64, _vpp]),
     "lb_device_free": (C.c_int, [C.c_int, _vp]),
     "lb_host_malloc": (C.c_int, [C.c_uint64, _vpp]),

@@ -1406,7 +1406,8 @@ struct lb_ivf {
     uint64_t n = 0;              // rows covered by the lists
     std::vector<float> centroids;
     std::vector<uint32_t> assignments, offsets, members;
-    DevBuf d_ids, d_q, d_qw, d_rows, d_dists, d_counts;
+    std::vector<uint32_t> routing_dims;  // standalone IVF_FLAT inner-product routing (lb_ivf_flat_search), built lazily
+    DevBuf d_ids, d_q, d_qw, d_rows, d_dists, d_counts, d_subset;
 };
 
 namespace lb {
@@ -1445,7 +1446,7 @@ void lb_ivf_destroy(lb_ivf* ivf) {
     if (!ivf) return;
     if (ivf->idx) {
         DeviceGuard g(ivf->idx->device);
-        DevBuf* bufs[] = {&ivf->d_ids, &ivf->d_q, &ivf->d_qw, &ivf->d_rows, &ivf->d_dists, &ivf->d_counts};
+        DevBuf* bufs[] = {&ivf->d_ids, &ivf->d_q, &ivf->d_qw, &ivf->d_rows, &ivf->d_dists, &ivf->d_counts, &ivf->d_subset};
         for (DevBuf* b : bufs) b->release();
     }
     if (ivf->cidx) lb_index_destroy(ivf->cidx);
@@ -1622,58 +1623,59 @@ int lb_ivf_assignments(const lb_ivf* ivf, uint32_t* out) {
     return LB_OK;
 }
 
-// IVFIndex::search (src/index/ivf.rs:181-348): rank centroids with the routing metric, gather the nprobe nearest
-// lists (whole lists, in probe order), apply the subset filter (an empty probe falls back to the filtered corpus,
-// never to an unfiltered scan), score every candidate with compute_distance_f32 / the packed kernels, keep the k best.
-int lb_ivf_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, uint32_t nprobe, const uint64_t* allow_bits,
-                  uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
-    if (!ivf || !out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "null argument");
-    if (nq && !queries) return fail(LB_INVALID_ARGUMENT, "queries is null");
+}  // extern "C"
+
+namespace lb {
+namespace {
+// The `np` best centroids for each query under `metric`, best first (ties keep centroid order, as the reference's
+// stable sort does): one exact scan over the centroid index.  `subset` (optional, host) restricts one query's
+// ranking to the listed centroids (the inner-product routing shortlist of the standalone index).
+int ivf_rank_centroids(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t np, int metric, const std::vector<uint32_t>* subset,
+                       std::vector<uint32_t>& probe) {
+    lb_index* c = ivf->cidx;
+    const int dim = (int)c->dim;
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard g(c->device);
+    LB_TRY(c->w_queries.ensure((size_t)nq * dim * 4));
+    LB_TRY(c->w_out_rows.ensure((size_t)nq * np * 4));
+    LB_TRY(c->w_out_dists.ensure((size_t)nq * np * 4));
+    LB_TRY(c->w_out_counts.ensure((size_t)nq * 4));
+    LB_CUDA_TRY(cudaMemcpyAsync(c->w_queries.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, c->stream));
+    ScanRequest r;
+    r.corpus = c->rows.as<float>();
+    r.n_rows = ivf->nc;
+    r.dim = dim;
+    r.queries = c->w_queries.as<float>();
+    r.nq = (int)nq;
+    r.k = (int)np;
+    r.metric = metric;
+    r.ip_single = 1;
+    r.out_rows = c->w_out_rows.as<uint32_t>();
+    r.out_dists = c->w_out_dists.as<float>();
+    r.out_counts = c->w_out_counts.as<uint32_t>();
+    if (subset) {
+        LB_TRY(ivf->d_subset.ensure(subset->size() * 4));  // guarded by the centroid index's mutex
+        LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_subset.p, subset->data(), subset->size() * 4, cudaMemcpyHostToDevice, c->stream));
+        r.row_ids = ivf->d_subset.as<uint32_t>();
+        r.n_rows = subset->size();
+    }
+    LB_TRY(run_scan(c, r, nullptr, nullptr));
+    probe.assign((size_t)nq * np, ROW_NONE);
+    LB_CUDA_TRY(cudaMemcpyAsync(probe.data(), c->w_out_rows.p, probe.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LB_OK;
+}
+
+// Per query: gather the probed lists (whole lists, in probe order), apply the subset filter, score every candidate
+// with compute_distance_f32 / the packed kernels, keep the k best.  `corpus_fallback`: an empty probe falls back to
+// the filtered corpus (IVFIndex::search) instead of returning nothing (IvfFlatMmap::search).
+int ivf_scan_probes(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, int metric, const std::vector<uint32_t>& probe, uint32_t np,
+                    const uint64_t* allow_bits, bool corpus_fallback, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
     lb_index* idx = ivf->idx;
-    if (idx->n != ivf->n) return fail(LB_INVALID_ARGUMENT, "the index changed since the IVF lists were built; rebuild the index");
-    if (k > (uint32_t)MAX_K) return fail(LB_UNSUPPORTED, "k above 2048 is not supported");
-    if (allow_bits && allow_words < (ivf->n + 63) / 64) return fail(LB_INVALID_ARGUMENT, "row filter is shorter than the index");
-    for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
-    for (size_t i = 0; i < (size_t)nq * k; ++i) {
-        out_rows[i] = ROW_NONE;
-        out_dists[i] = NAN;
-    }
-    if (nq == 0 || k == 0) return LB_OK;
     const int dim = (int)idx->dim;
-    const uint32_t np = std::min<uint32_t>(std::max<uint32_t>(nprobe, 1), ivf->nc);
-    // 1. centroid ranking for every query: one exact scan over the centroid index (ties keep centroid order, as the
-    //    reference's stable sort does)
-    std::vector<uint32_t> probe((size_t)nq * np), pcount(nq);
-    std::vector<float> pd((size_t)nq * np);
-    {
-        lb_index* c = ivf->cidx;
-        std::lock_guard<std::mutex> lock(c->mu);
-        DeviceGuard g(c->device);
-        LB_TRY(c->w_queries.ensure((size_t)nq * dim * 4));
-        LB_TRY(c->w_out_rows.ensure((size_t)nq * np * 4));
-        LB_TRY(c->w_out_dists.ensure((size_t)nq * np * 4));
-        LB_TRY(c->w_out_counts.ensure((size_t)nq * 4));
-        LB_CUDA_TRY(cudaMemcpyAsync(c->w_queries.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, c->stream));
-        ScanRequest r;
-        r.corpus = c->rows.as<float>();
-        r.n_rows = ivf->nc;
-        r.dim = dim;
-        r.queries = c->w_queries.as<float>();
-        r.nq = (int)nq;
-        r.k = (int)np;
-        r.metric = ivf->routing;
-        r.ip_single = 1;
-        r.out_rows = c->w_out_rows.as<uint32_t>();
-        r.out_dists = c->w_out_dists.as<float>();
-        r.out_counts = c->w_out_counts.as<uint32_t>();
-        LB_TRY(run_scan(c, r, nullptr, nullptr));
-        LB_CUDA_TRY(cudaMemcpyAsync(probe.data(), c->w_out_rows.p, probe.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-        LB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    }
-    // 2. per query: gather, score, select
     std::lock_guard<std::mutex> lock(idx->mu);
     DeviceGuard g(idx->device);
-    const bool binary = metric_binary(ivf->metric);
+    const bool binary = metric_binary(metric);
     const int nw = (dim + 63) / 64;
     if (binary) LB_TRY(ensure_packed(idx));
     auto allowed = [&](uint32_t r) { return allow_bits == nullptr || ((allow_bits[r >> 6] >> (r & 63)) & 1ull); };
@@ -1686,7 +1688,7 @@ int lb_ivf_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, ui
             for (uint32_t m = ivf->offsets[c]; m < ivf->offsets[c + 1]; ++m)
                 if (allowed(ivf->members[m])) cand.push_back(ivf->members[m]);
         }
-        if (cand.empty())
+        if (cand.empty() && corpus_fallback)
             for (uint32_t r = 0; r < (uint32_t)ivf->n; ++r)
                 if (allowed(r)) cand.push_back(r);
         if (cand.empty()) continue;
@@ -1703,7 +1705,7 @@ int lb_ivf_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, ui
         r.row_ids = ivf->d_ids.as<uint32_t>();
         r.nq = 1;
         r.k = (int)kk;
-        r.metric = ivf->metric;
+        r.metric = metric;
         r.out_rows = ivf->d_rows.as<uint32_t>();
         r.out_dists = ivf->d_dists.as<float>();
         r.out_counts = ivf->d_counts.as<uint32_t>();
@@ -1727,6 +1729,117 @@ int lb_ivf_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, ui
         LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
     }
     return LB_OK;
+}
+
+int ivf_search_prologue(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    if (!ivf || !out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "null argument");
+    if (nq && !queries) return fail(LB_INVALID_ARGUMENT, "queries is null");
+    if (ivf->idx->n != ivf->n) return fail(LB_INVALID_ARGUMENT, "the index changed since the IVF lists were built; rebuild the index");
+    if (k > (uint32_t)MAX_K) return fail(LB_UNSUPPORTED, "k above 2048 is not supported");
+    for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+    for (size_t i = 0; i < (size_t)nq * k; ++i) {
+        out_rows[i] = ROW_NONE;
+        out_dists[i] = NAN;
+    }
+    return LB_OK;
+}
+
+// select_routing_dims (src/storage/ivf_flat_mmap.rs:312-345): the 16 centroid dimensions of highest variance,
+// ascending; empty unless dim >= 64 and there are >= 64 centroids.
+std::vector<uint32_t> ivf_routing_dims(const std::vector<float>& centroids, size_t dim, size_t nc) {
+    if (dim < 64 || nc < 64) return {};
+    std::vector<float> sums(dim, 0.0f), sq(dim, 0.0f);
+    for (size_t c = 0; c < nc; ++c)
+        for (size_t d = 0; d < dim; ++d) {
+            const float v = centroids[c * dim + d];
+            sums[d] += v;
+            sq[d] += v * v;  // unfused, as rustc emits it: host code is built with -ffp-contract=off
+        }
+    const float inv_k = 1.0f / (float)nc;
+    std::vector<std::pair<float, uint32_t>> dims(dim);
+    for (size_t d = 0; d < dim; ++d) {
+        const float mean = sums[d] * inv_k;
+        dims[d] = {sq[d] * inv_k - mean * mean, (uint32_t)d};
+    }
+    std::stable_sort(dims.begin(), dims.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    std::vector<uint32_t> sel(16);
+    for (size_t i = 0; i < 16; ++i) sel[i] = dims[i].second;
+    std::sort(sel.begin(), sel.end());
+    return sel;
+}
+}  // namespace
+}  // namespace lb
+
+extern "C" {
+
+// IVFIndex::search (src/index/ivf.rs:181-348): rank centroids with the routing metric, gather the nprobe nearest
+// lists, apply the subset filter (an empty probe falls back to the filtered corpus, never to an unfiltered scan),
+// score every candidate, keep the k best.
+int lb_ivf_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, uint32_t nprobe, const uint64_t* allow_bits,
+                  uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    LB_TRY(ivf_search_prologue(ivf, queries, nq, k, out_rows, out_dists, out_counts));
+    if (allow_bits && allow_words < (ivf->n + 63) / 64) return fail(LB_INVALID_ARGUMENT, "row filter is shorter than the index");
+    if (nq == 0 || k == 0) return LB_OK;
+    const uint32_t np = std::min<uint32_t>(std::max<uint32_t>(nprobe, 1), ivf->nc);
+    std::vector<uint32_t> probe;
+    LB_TRY(ivf_rank_centroids(ivf, queries, nq, np, ivf->routing, nullptr, probe));
+    return ivf_scan_probes(ivf, queries, nq, k, ivf->metric, probe, np, allow_bits, true, out_rows, out_dists, out_counts);
+}
+
+// IvfFlatMmap::search (src/storage/ivf_flat_mmap.rs:225-300) with find_nearest_centroids (:383-446): the probed
+// partitions are the nprobe nearest centroids under the SEARCH metric — for inner product on dim >= 64 with >= 64
+// partitions, the nearest of a routing-dimension shortlist — and every row of those partitions is scored with
+// compute_distance_f32.  Rows are reported by their position in the build data (the reference's original_ids).
+int lb_ivf_flat_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, uint32_t nprobe, int metric, uint32_t* out_rows,
+                       float* out_dists, uint32_t* out_counts) {
+    LB_TRY(ivf_search_prologue(ivf, queries, nq, k, out_rows, out_dists, out_counts));
+    LB_TRY(check_metric(metric));
+    const size_t dim = ivf->idx->dim;
+    if (metric == LB_HAVERSINE && dim != 2) return fail(LB_INVALID_ARGUMENT, "haversine requires dimension 2");
+    if (nq == 0 || k == 0) return LB_OK;
+    const uint32_t nc = ivf->nc;
+    const uint32_t np = std::min<uint32_t>(std::max<uint32_t>(nprobe, 1), nc);
+    std::vector<uint32_t> probe;
+    if (np >= nc) {
+        probe.resize((size_t)nq * np);
+        for (uint32_t q = 0; q < nq; ++q)
+            for (uint32_t c = 0; c < nc; ++c) probe[(size_t)q * np + c] = c;
+    } else if (metric == LB_IP && dim >= 64 && nc >= 64) {
+        if (ivf->routing_dims.empty()) ivf->routing_dims = ivf_routing_dims(ivf->centroids, dim, nc);
+        const size_t shortlist = std::min<size_t>(std::max<size_t>(std::min<size_t>((size_t)np * 3, 96), 24), nc);
+        probe.assign((size_t)nq * np, ROW_NONE);
+        std::vector<std::pair<float, uint32_t>> best(shortlist);
+        std::vector<uint32_t> subset, ranked;
+        for (uint32_t q = 0; q < nq; ++q) {
+            const float* qv = queries + (size_t)q * dim;
+            size_t len = 0;
+            for (uint32_t c = 0; c < nc; ++c) {
+                const float* cv = ivf->centroids.data() + (size_t)c * dim;
+                float score = 0.0f;
+                for (uint32_t d : ivf->routing_dims) score += qv[d] * cv[d];  // coarse_ip_score: multiply then add, unfused
+                if (len < shortlist) {
+                    best[len++] = {score, c};
+                    continue;
+                }
+                size_t worst = 0;
+                float worst_score = best[0].first;
+                for (size_t i = 1; i < shortlist; ++i)
+                    if (best[i].first < worst_score) {
+                        worst_score = best[i].first;
+                        worst = i;
+                    }
+                if (score > worst_score) best[worst] = {score, c};
+            }
+            subset.resize(len);
+            for (size_t i = 0; i < len; ++i) subset[i] = best[i].second;
+            std::sort(subset.begin(), subset.end());  // ranking ties then fall to the lower centroid
+            LB_TRY(ivf_rank_centroids(ivf, qv, 1, np, LB_IP, &subset, ranked));
+            for (uint32_t p = 0; p < np; ++p) probe[(size_t)q * np + p] = ranked[p];
+        }
+    } else {
+        LB_TRY(ivf_rank_centroids(ivf, queries, nq, np, metric, nullptr, probe));
+    }
+    return ivf_scan_probes(ivf, queries, nq, k, metric, probe, np, nullptr, false, out_rows, out_dists, out_counts);
 }
 
 }  // extern "C"

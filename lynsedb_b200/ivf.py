@@ -23,7 +23,8 @@ KMEANS_MAX_ITER = 20       # IVFIndex::build (src/index/ivf.rs:163-170)
 
 class IVFIndex:
     def __init__(self, index: DeviceIndex, metric, n_clusters: int = DEFAULT_N_CLUSTERS, nprobe: int = DEFAULT_NPROBE,
-                 centroids: Optional[np.ndarray] = None, assignments: Optional[np.ndarray] = None):
+                 centroids: Optional[np.ndarray] = None, assignments: Optional[np.ndarray] = None,
+                 max_iter: int = KMEANS_MAX_ITER):
         self._index = index
         self._metric = M.require(metric)
         self._nprobe = int(nprobe)
@@ -35,7 +36,7 @@ class IVFIndex:
                 raise ValueError("centroids must be [n_centroids, dim] and assignments [len(index)]")
             N.check(N.lib().lb_ivf_create(index._h, self._metric, N.fptr(cent), cent.shape[0], N.u32ptr(assign), C.byref(self._h)))
         else:
-            N.check(N.lib().lb_ivf_train(index._h, self._metric, int(n_clusters), KMEANS_MAX_ITER, C.byref(self._h)))
+            N.check(N.lib().lb_ivf_train(index._h, self._metric, int(n_clusters), int(max_iter), C.byref(self._h)))
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -94,4 +95,19 @@ class IVFIndex:
             allow = np.ascontiguousarray(allow_bits, dtype=np.uint64)
             ab, aw = N.u64ptr(allow), allow.size
         N.check(N.lib().lb_ivf_search(self._h, N.fptr(q), nq, k, np_eff, ab, aw, N.u32ptr(rows), N.fptr(dists), N.u32ptr(counts)))
+        return rows, dists, counts
+
+    def flat_search(self, queries: np.ndarray, k: int, nprobe: int, metric) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """The standalone IVF_FLAT search rule (``IvfFlatMmap::search``, src/storage/ivf_flat_mmap.rs:225-300):
+        partitions chosen under ``metric`` (routing-dimension shortlist for inner product), no corpus fallback."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        if q.shape[1] != self._index.dim:
+            raise ValueError(f"query dimension mismatch: expected {self._index.dim}, got {q.shape[1]}")
+        nq, k = q.shape[0], int(k)
+        rows = np.ascontiguousarray(np.empty((nq, max(k, 1)), dtype=np.uint32)[:, :k])
+        dists = np.ascontiguousarray(np.empty((nq, max(k, 1)), dtype=np.float32)[:, :k])
+        counts = np.zeros(max(nq, 1), dtype=np.uint32)[:nq]
+        N.check(N.lib().lb_ivf_flat_search(self._h, N.fptr(q), nq, k, max(int(nprobe), 0), M.require(metric), N.u32ptr(rows),
+                                           N.fptr(dists), N.u32ptr(counts)))
         return rows, dists, counts

@@ -70,6 +70,11 @@ def lib():
                                              C.c_int, u64p, f32p, u32p]
         L.lo_kmeans_train.restype = C.c_uint32
         L.lo_kmeans_train.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, f32p, u32p]
+        L.lo_ivf_flat_search.restype = C.c_uint32
+        L.lo_ivf_flat_search.argtypes = [f32p, C.c_uint64, C.c_uint64, f32p, C.c_uint32, u32p, f32p, C.c_uint32, C.c_uint32,
+                                         C.c_int, u32p, f32p, u32p, u32p]
+        L.lo_ivf_flat_routing_dims.restype = C.c_uint32
+        L.lo_ivf_flat_routing_dims.argtypes = [f32p, C.c_uint64, C.c_uint32, u32p]
         L.lo_ivf_search.restype = C.c_uint32
         L.lo_ivf_search.argtypes = [f32p, C.c_uint64, C.c_uint64, f32p, C.c_uint32, u32p, f32p, C.c_uint32, C.c_uint32,
                                     C.c_int, u64p, u32p, f32p]
@@ -228,3 +233,28 @@ def ivf_search(data, centroids, assignments, query, k, nprobe, metric, allow_bit
     cnt = lib().lo_ivf_search(_p(d, C.c_float), n, dim, _p(c, C.c_float), c.shape[0], _p(a, C.c_uint32), _p(q, C.c_float),
                               k, nprobe, metric_id(metric), ab, _p(ids, C.c_uint32), _p(dists, C.c_float))
     return ids[:cnt].copy(), dists[:cnt].copy()
+
+
+def ivf_flat_search(data, centroids, assignments, query, k, nprobe, metric, return_probes=False):
+    """IvfFlatMmap::search (src/storage/ivf_flat_mmap.rs:225-300) for one query -> (u32 original ids, f32 dists)."""
+    d, c, q = _f32(data), _f32(centroids), _f32(query).ravel()
+    a = np.ascontiguousarray(assignments, dtype=np.uint32)
+    n, dim = d.shape
+    ids = np.empty(max(k, 1), dtype=np.uint32)
+    dists = np.empty(max(k, 1), dtype=np.float32)
+    probes = np.zeros(max(c.shape[0], 1), dtype=np.uint32)
+    n_probes = np.zeros(1, dtype=np.uint32)
+    cnt = lib().lo_ivf_flat_search(_p(d, C.c_float), n, dim, _p(c, C.c_float), c.shape[0], _p(a, C.c_uint32), _p(q, C.c_float),
+                                   k, nprobe, metric_id(metric), _p(ids, C.c_uint32), _p(dists, C.c_float),
+                                   _p(probes, C.c_uint32), _p(n_probes, C.c_uint32))
+    if return_probes:
+        return ids[:cnt].copy(), dists[:cnt].copy(), probes[: int(n_probes[0])].copy()
+    return ids[:cnt].copy(), dists[:cnt].copy()
+
+
+def ivf_flat_routing_dims(centroids):
+    """select_routing_dims (src/storage/ivf_flat_mmap.rs:312-345)."""
+    c = _f32(centroids)
+    out = np.zeros(16, dtype=np.uint32)
+    cnt = lib().lo_ivf_flat_routing_dims(_p(c, C.c_float), c.shape[1], c.shape[0], _p(out, C.c_uint32))
+    return out[:cnt].copy()

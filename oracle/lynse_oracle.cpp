@@ -1105,6 +1105,105 @@ std::vector<Pair> ivf_search(const float* data, size_t n, size_t dim, const floa
     return scored;
 }
 
+// ---- src/storage/ivf_flat_mmap.rs — the standalone IVF_FLAT index (`_core.IvfFlatIndex`) ----------------------
+// Training is kmeans::train_l2 = train_for_metric(.., L2Squared) (kmeans.rs:53-72), i.e. kmeans_train above.
+// select_routing_dims (ivf_flat_mmap.rs:312-345): the 16 centroid dimensions of highest variance, ascending.
+// The reference picks them with select_nth_unstable_by (ties arbitrary); here ties break on the lower dimension.
+std::vector<size_t> ivf_flat_routing_dims(const float* centroids, size_t dim, size_t nc) {
+    if (nc == 0 || dim == 0 || dim < 64 || nc < 64) return {};
+    std::vector<float> sums(dim, 0.0f), sq(dim, 0.0f);
+    for (size_t c = 0; c < nc; ++c)
+        for (size_t d = 0; d < dim; ++d) {
+            float v = centroids[c * dim + d];
+            sums[d] += v;
+            sq[d] += v * v;
+        }
+    float inv_k = 1.0f / (float)nc;
+    size_t keep = std::min<size_t>(16, dim);
+    std::vector<std::pair<float, size_t>> dims(dim);
+    for (size_t d = 0; d < dim; ++d) {
+        float mean = sums[d] * inv_k;
+        float variance = sq[d] * inv_k - mean * mean;
+        dims[d] = {variance, d};
+    }
+    std::stable_sort(dims.begin(), dims.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    std::vector<size_t> sel(keep);
+    for (size_t i = 0; i < keep; ++i) sel[i] = dims[i].second;
+    std::sort(sel.begin(), sel.end());
+    return sel;
+}
+
+// find_nearest_centroids (ivf_flat_mmap.rs:383-446): every partition when nprobe >= n_partitions; for inner
+// product on dim >= 64 with >= 64 partitions a routing-dimension shortlist (clamp(3*nprobe, 24, 96) entries,
+// shortlist_insert replaces the first worst entry when the new score is strictly larger) re-ranked with the full
+// metric; otherwise the nprobe nearest centroids under the SEARCH metric.  Selection ties are arbitrary in the
+// reference (select_nth_unstable_by); here they break on the lower centroid index.
+std::vector<size_t> ivf_flat_nearest_centroids(const float* query, const float* centroids, size_t dim, size_t nc,
+                                               size_t nprobe, int metric, const std::vector<size_t>& routing_dims) {
+    std::vector<size_t> out;
+    if (nprobe >= nc) {
+        for (size_t c = 0; c < nc; ++c) out.push_back(c);
+        return out;
+    }
+    bool asc = is_ascending(metric);
+    std::vector<std::pair<float, size_t>> dists;
+    if (metric == IP && dim >= 64 && nc >= 64 && !routing_dims.empty()) {
+        size_t shortlist = std::min<size_t>(std::max<size_t>(std::min<size_t>(nprobe * 3, 96), 24), nc);
+        std::vector<std::pair<float, uint32_t>> best(shortlist, {-INFINITY, 0u});
+        size_t len = 0;
+        for (size_t c = 0; c < nc; ++c) {
+            float score = 0.0f;
+            for (size_t d : routing_dims) score += query[d] * centroids[c * dim + d];
+            if (len < best.size()) {
+                best[len++] = {score, (uint32_t)c};
+                continue;
+            }
+            size_t worst = 0;
+            float worst_score = best[0].first;
+            for (size_t i = 1; i < best.size(); ++i)
+                if (best[i].first < worst_score) {
+                    worst_score = best[i].first;
+                    worst = i;
+                }
+            if (score > worst_score) best[worst] = {score, (uint32_t)c};
+        }
+        for (size_t i = 0; i < len; ++i)
+            dists.push_back({compute_distance(query, centroids + (size_t)best[i].second * dim, dim, metric), best[i].second});
+        asc = false;
+    } else {
+        for (size_t c = 0; c < nc; ++c) dists.push_back({compute_distance(query, centroids + c * dim, dim, metric), c});
+    }
+    std::sort(dists.begin(), dists.end(), [asc](const auto& a, const auto& b) {
+        if (a.first != b.first) return asc ? a.first < b.first : a.first > b.first;
+        return a.second < b.second;
+    });
+    for (size_t i = 0; i < std::min(nprobe, dists.size()); ++i) out.push_back(dists[i].second);
+    return out;
+}
+
+// IvfFlatMmap::search (ivf_flat_mmap.rs:225-300): compute_distance_f32 over every row of the probed partitions,
+// select_nth + sort on the distance alone (ties arbitrary in the reference; here the lower original id first).
+std::vector<Pair> ivf_flat_search(const float* data, size_t n, size_t dim, const float* centroids, size_t nc,
+                                  const uint32_t* assignments, const float* query, size_t k, size_t nprobe, int metric) {
+    if (n == 0 || k == 0) return {};
+    k = std::min(k, n);
+    nprobe = std::min(std::max<size_t>(nprobe, 1), nc);
+    bool asc = is_ascending(metric);
+    auto rdims = ivf_flat_routing_dims(centroids, dim, nc);
+    auto parts = ivf_flat_nearest_centroids(query, centroids, dim, nc, nprobe, metric, rdims);
+    std::vector<char> probed(nc, 0);
+    for (size_t p : parts) probed[p] = 1;
+    std::vector<Pair> best;
+    for (size_t i = 0; i < n; ++i)
+        if (probed[assignments[i]]) best.push_back({compute_distance(query, data + i * dim, dim, metric), (uint32_t)i});
+    std::sort(best.begin(), best.end(), [asc](const Pair& a, const Pair& b) {
+        if (a.d != b.d) return asc ? a.d < b.d : a.d > b.d;
+        return a.i < b.i;
+    });
+    if (best.size() > k) best.resize(k);
+    return best;
+}
+
 }  // namespace
 
 // =============================== C ABI =======================================
@@ -1237,6 +1336,32 @@ uint32_t lo_ivf_search(const float* data, uint64_t n, uint64_t dim, const float*
         dists[i] = res[i].d;
     }
     return (uint32_t)res.size();
+}
+
+// IvfFlatMmap::search for one query given centroids and assignments; probes_out (optional) receives the probed
+// partitions, n_probes_out their count
+uint32_t lo_ivf_flat_search(const float* data, uint64_t n, uint64_t dim, const float* centroids, uint32_t nc,
+                            const uint32_t* assignments, const float* query, uint32_t k, uint32_t nprobe, int metric,
+                            uint32_t* ids, float* dists, uint32_t* probes_out, uint32_t* n_probes_out) {
+    auto res = ivf_flat_search(data, n, dim, centroids, nc, assignments, query, k, nprobe, metric);
+    for (size_t i = 0; i < res.size(); ++i) {
+        ids[i] = res[i].i;
+        dists[i] = res[i].d;
+    }
+    if (probes_out && n_probes_out && n && k) {
+        size_t np = std::min<size_t>(std::max<uint32_t>(nprobe, 1), nc);
+        auto parts = ivf_flat_nearest_centroids(query, centroids, dim, nc, np, metric, ivf_flat_routing_dims(centroids, dim, nc));
+        *n_probes_out = (uint32_t)parts.size();
+        for (size_t i = 0; i < parts.size(); ++i) probes_out[i] = (uint32_t)parts[i];
+    }
+    return (uint32_t)res.size();
+}
+
+// select_routing_dims; returns the count (0 or 16)
+uint32_t lo_ivf_flat_routing_dims(const float* centroids, uint64_t dim, uint32_t nc, uint32_t* dims_out) {
+    auto d = ivf_flat_routing_dims(centroids, dim, nc);
+    for (size_t i = 0; i < d.size(); ++i) dims_out[i] = (uint32_t)d[i];
+    return (uint32_t)d.size();
 }
 
 int lo_max_threads(void) { return omp_get_max_threads(); }

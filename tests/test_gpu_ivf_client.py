@@ -183,3 +183,106 @@ def test_load_lynsedb_directory_and_search_range(L, oracle, tmp_path):
         assert got_ids.tolist() == [int(i) + 5000 for i in order]
         assert np.array_equal(got_d.view(np.uint32), d_all[order].view(np.uint32))
         assert len(coll.search_range(q, thr, max_results=7)[0]) == 7
+
+
+# ---- standalone IVF_FLAT index: `_core.IvfFlatIndex` (src/python/mod.rs:2049-2156, src/storage/ivf_flat_mmap.rs) ----
+_IVF_FLAT_12 = np.array([
+    1.0, 0.1, 0.0, 0.0, 0.9, 0.0, 0.1, 0.0, 1.0, 0.0, 0.0, 0.1, 0.8, 0.1, 0.1, 0.0,
+    0.0, 1.0, 0.1, 0.0, 0.1, 0.9, 0.0, 0.0, 0.0, 1.0, 0.0, 0.1, 0.1, 0.8, 0.1, 0.0,
+    0.0, 0.0, 1.0, 0.1, 0.0, 0.1, 0.9, 0.0, 0.1, 0.0, 1.0, 0.0, 0.0, 0.0, 0.8, 0.1], dtype=np.float32).reshape(12, 4)
+
+
+def test_ivf_flat_index_reference_cases(L, oracle, tmp_path):
+    # test_ivf_flat_build_and_search (ivf_flat_mmap.rs:674-719)
+    idx = L.IvfFlatIndex.build(str(tmp_path / "vectors.bin"), _IVF_FLAT_12, dim=4, n_partitions=3, n_iters=10, metric="ip")
+    assert len(idx) == 12 and idx.dim == 4 and idx.n_partitions == 3
+    q = np.array([1.0, 0.0, 0.0, 0.0], dtype=np.float32)
+    ids, dists = idx.search(q, 3, 1, "ip")
+    assert ids.dtype == np.uint32 and dists.dtype == np.float32 and len(ids) == 3 and ids[0] <= 3
+    ids0, dists0 = idx.search(q, 3, 0, "ip")
+    assert np.array_equal(ids0, ids) and np.array_equal(dists0, dists)
+    cent, assign = oracle.kmeans_train(_IVF_FLAT_12, 3, "l2", max_iter=10)
+    want_ids, want_d = oracle.ivf_flat_search(_IVF_FLAT_12, cent, assign, q, 3, 1, "ip")
+    assert np.array_equal(ids, want_ids) and np.array_equal(dists.view(np.uint32), want_d.view(np.uint32))
+    # test_ivf_flat_reopen (:751-773)
+    data = np.array([1.0, 0.0, 0.0, 1.0, -1.0, 0.0, 0.0, -1.0], dtype=np.float32).reshape(4, 2)
+    path = str(tmp_path / "small.bin")
+    L.IvfFlatIndex.build(path, data, 2, 2, 5, "ip").close()
+    again = L.IvfFlatIndex.open(path, 2)
+    assert len(again) == 4 and again.n_partitions == 2
+    assert again.search(np.array([1.0, 0.0], dtype=np.float32), 1, 2, "ip")[0][0] == 0
+    with pytest.raises(IOError, match="dimension mismatch"):
+        L.IvfFlatIndex.open(path, 3)
+    # test_ivf_flat_rejects_invalid_build_inputs (:721-749) + the pyo3 wrapper's own checks (mod.rs:2075-2090)
+    with pytest.raises(IOError):
+        L.IvfFlatIndex.build(str(tmp_path / "x.bin"), np.zeros((2, 2), dtype=np.float32), 2, 0, 5, "l2")
+    with pytest.raises(IOError):
+        L.IvfFlatIndex.build(str(tmp_path / "x.bin"), np.zeros((2, 2), dtype=np.float32), 2, 3, 5, "l2")
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        L.IvfFlatIndex.build(str(tmp_path / "x.bin"), np.zeros((2, 3), dtype=np.float32), 2, 1, 5, "l2")
+    with pytest.raises(ValueError, match="Unknown metric"):
+        L.IvfFlatIndex.build(str(tmp_path / "x.bin"), np.zeros((2, 2), dtype=np.float32), 2, 1, 5, "nope")
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        idx.search(np.zeros(5, dtype=np.float32), 3, 1, "ip")
+
+
+@pytest.mark.parametrize("metric,dim,nc,nprobe", [("ip", 64, 64, 8), ("ip", 96, 80, 40), ("ip", 32, 64, 6), ("l2", 64, 64, 8),
+                                                  ("cosine", 48, 20, 5), ("hamming", 64, 16, 4), ("l1", 24, 12, 3),
+                                                  ("ip", 64, 64, 64)])
+def test_ivf_flat_index_matches_oracle(L, oracle, tmp_path, metric, dim, nc, nprobe):
+    rng = np.random.default_rng(dim * 1000 + nc)
+    data = rng.random((6000, dim), dtype=np.float32)
+    data[:, 3] *= 5.0
+    queries = rng.random((12, dim), dtype=np.float32)
+    path = str(tmp_path / "ivf.bin")
+    idx = L.IvfFlatIndex.build(path, data, dim, n_partitions=nc, n_iters=6, metric=metric)
+    cent, assign = oracle.kmeans_train(data, nc, "l2", max_iter=6)
+    assert np.array_equal(idx._ivf.centroids().view(np.uint32), cent.view(np.uint32))
+    assert np.array_equal(idx._ivf.assignments(), assign)
+    reopened = L.IvfFlatIndex.open(path, dim)
+    for q in queries:
+        want_ids, want_d = oracle.ivf_flat_search(data, cent, assign, q, 10, nprobe, metric)
+        for index in (idx, reopened):
+            ids, dists = index.search(q, 10, nprobe, metric)
+            assert np.array_equal(dists.view(np.uint32), want_d.view(np.uint32))
+            # tied distances: the reference's order is arbitrary; ours is the lower row first, as the oracle's
+            assert np.array_equal(ids, want_ids)
+
+
+def test_ivf_flat_index_files_follow_the_reference_layout(L, tmp_path):
+    # save_metadata (ivf_flat_mmap.rs:450-483): u64 dim, n, partitions; f32 centroids; u64 offsets[p+1]; u32 original ids;
+    # the data file holds the rows partition by partition, in row order inside a partition (:116-131)
+    rng = np.random.default_rng(3)
+    data = rng.random((500, 8), dtype=np.float32)
+    path = tmp_path / "layout.bin"
+    idx = L.IvfFlatIndex.build(str(path), data, 8, n_partitions=7, n_iters=4)
+    meta = (tmp_path / "layout.ivf_meta.bin").read_bytes()
+    dim, n, p = np.frombuffer(meta[:24], dtype="<u8")
+    assert (dim, n, p) == (8, 500, 7)
+    cent = np.frombuffer(meta[24:24 + 4 * 7 * 8], dtype="<f4").reshape(7, 8)
+    off = np.frombuffer(meta[24 + 224:24 + 224 + 64], dtype="<u8")
+    orig = np.frombuffer(meta[24 + 224 + 64:], dtype="<u4")
+    assert orig.size == 500 and off[0] == 0 and off[-1] == 500 and np.all(np.diff(off.astype(np.int64)) >= 0)
+    assign = idx._ivf.assignments()
+    assert np.array_equal(cent, idx._ivf.centroids())
+    for part in range(7):
+        members = orig[int(off[part]):int(off[part + 1])]
+        assert np.array_equal(members, np.flatnonzero(assign == part).astype(np.uint32))
+    stored = np.fromfile(path, dtype="<f4").reshape(500, 8)
+    assert np.array_equal(stored, data[orig])
+
+
+def test_flat_index_write_appends(L, tmp_path):
+    # test_flat_mmap_append (src/storage/flat_mmap.rs:6057-6075): write() appends rows, to the index and to the file
+    path = tmp_path / "vectors.bin"
+    store = L.FlatIndex(str(path), 2)
+    assert len(store) == 0
+    store.write(np.array([[1.0, 2.0], [3.0, 4.0]], dtype=np.float32))
+    assert len(store) == 2
+    store.write(np.array([[5.0, 6.0]], dtype=np.float32))
+    assert len(store) == 3
+    assert np.array_equal(np.fromfile(path, dtype="<f4"), np.array([1, 2, 3, 4, 5, 6], dtype=np.float32))
+    ids, dists = store.search(np.array([1.0, 1.0], dtype=np.float32), 3, "ip")
+    assert ids.tolist() == [2, 1, 0] and dists.tolist() == [11.0, 7.0, 3.0]
+    reopened = L.FlatIndex(str(path), 2)
+    assert len(reopened) == 3

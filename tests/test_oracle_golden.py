@@ -352,3 +352,73 @@ def test_golden_fixture_top_k(oracle):
         ids, dists = oracle.top_k_search(np.asarray(case["query"], F), np.asarray(case["candidates"], F), case["metric"], case["k"])
         assert ids.tolist() == case["ids"], case
         assert np.allclose(dists, case["dists"], atol=1e-6), case
+
+
+# ---- standalone IVF_FLAT (src/storage/ivf_flat_mmap.rs:674-815) ------------------------------------------------------
+_IVF_FLAT_12 = np.array([
+    1.0, 0.1, 0.0, 0.0, 0.9, 0.0, 0.1, 0.0, 1.0, 0.0, 0.0, 0.1, 0.8, 0.1, 0.1, 0.0,
+    0.0, 1.0, 0.1, 0.0, 0.1, 0.9, 0.0, 0.0, 0.0, 1.0, 0.0, 0.1, 0.1, 0.8, 0.1, 0.0,
+    0.0, 0.0, 1.0, 0.1, 0.0, 0.1, 0.9, 0.0, 0.1, 0.0, 1.0, 0.0, 0.0, 0.0, 0.8, 0.1], dtype=np.float32).reshape(12, 4)
+
+
+def _ivf_flat_lcg_data(n=1000, dim=8):
+    """test_ivf_flat_recall's generator (ivf_flat_mmap.rs:786-792)."""
+    rng, out = 42, np.zeros(n * dim, dtype=np.float32)
+    for i in range(n * dim):
+        rng = (rng * 6364136223846793005 + 1) & 0xFFFFFFFFFFFFFFFF
+        out[i] = np.float32(np.float32(np.float32(rng >> 33) / np.float32(0xFFFFFFFF)) * np.float32(2.0)) - np.float32(1.0)
+    return out.reshape(n, dim)
+
+
+def test_ivf_flat_build_and_search_pin(oracle):
+    # test_ivf_flat_build_and_search: 3 partitions trained with 10 L2 iterations; top hit in the first cluster;
+    # nprobe 0 behaves as nprobe 1
+    cent, assign = oracle.kmeans_train(_IVF_FLAT_12, 3, "l2", max_iter=10)
+    q = np.array([1.0, 0.0, 0.0, 0.0], dtype=np.float32)
+    ids, dists = oracle.ivf_flat_search(_IVF_FLAT_12, cent, assign, q, 3, 1, "ip")
+    assert len(ids) == 3 and ids[0] <= 3
+    ids0, dists0 = oracle.ivf_flat_search(_IVF_FLAT_12, cent, assign, q, 3, 0, "ip")
+    assert np.array_equal(ids0, ids) and np.array_equal(dists0, dists)
+
+
+def test_ivf_flat_reopen_pin(oracle):
+    data = np.array([1.0, 0.0, 0.0, 1.0, -1.0, 0.0, 0.0, -1.0], dtype=np.float32).reshape(4, 2)
+    cent, assign = oracle.kmeans_train(data, 2, "l2", max_iter=5)
+    ids, _ = oracle.ivf_flat_search(data, cent, assign, [1.0, 0.0], 1, 2, "ip")
+    assert ids[0] == 0
+
+
+def test_ivf_flat_full_probe_matches_brute_force(oracle):
+    # test_ivf_flat_recall: nprobe = all partitions -> the flat scan's top hit (here: the whole top-5, no ties)
+    data = _ivf_flat_lcg_data()
+    cent, assign = oracle.kmeans_train(data, 10, "l2", max_iter=10)
+    ids, dists = oracle.ivf_flat_search(data, cent, assign, data[0], 5, 10, "ip")
+    bf_ids, bf_d = oracle.flat_search(data, data[0], 5, "ip")
+    assert ids[0] == bf_ids[0]
+    assert np.array_equal(ids, bf_ids.astype(np.uint32))
+    assert np.allclose(dists, bf_d, rtol=1e-6)
+
+
+def test_ivf_flat_ip_routing_shortlist(oracle):
+    # inner-product routing on dim >= 64 with >= 64 partitions goes through the 16 highest-variance centroid
+    # dimensions (ivf_flat_mmap.rs:312-345, :383-428); other metrics rank every centroid
+    rng = np.random.default_rng(5)
+    data = rng.random((4000, 64), dtype=np.float32)
+    data[:, 7] *= 9.0       # two loud dimensions must be among the routing dimensions
+    data[:, 40] *= 7.0
+    cent, assign = oracle.kmeans_train(data, 64, "l2", max_iter=5)
+    dims = oracle.ivf_flat_routing_dims(cent)
+    assert len(dims) == 16 and list(dims) == sorted(dims) and 7 in dims and 40 in dims
+    assert len(oracle.ivf_flat_routing_dims(cent[:63])) == 0
+    assert len(oracle.ivf_flat_routing_dims(cent[:, :63])) == 0
+    q = data[17]
+    ids, dists, probes = oracle.ivf_flat_search(data, cent, assign, q, 10, 8, "ip", return_probes=True)
+    assert len(probes) == 8 and len(set(probes.tolist())) == 8
+    assert np.all(np.diff(dists) <= 0)
+    for r, d in zip(ids, dists):
+        assert assign[r] in probes
+        assert np.float32(oracle.compute_distance(q, data[r], "ip")) == d
+    # L2 takes the plain branch: the probed partitions are exactly the 8 nearest centroids
+    _, _, probes_l2 = oracle.ivf_flat_search(data, cent, assign, q, 10, 8, "l2", return_probes=True)
+    cd = np.array([oracle.compute_distance(q, c, "l2") for c in cent], dtype=np.float32)
+    assert set(probes_l2.tolist()) == set(np.argsort(cd, kind="stable")[:8].tolist())
