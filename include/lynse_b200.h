@@ -146,6 +146,14 @@ int lb_index_search(lb_index* idx, int metric, const float* queries, uint32_t nq
 int lb_index_search_pairwise(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k,
                              const uint64_t* allow_bits, uint64_t allow_words, uint32_t* out_rows, float* out_dists,
                              uint32_t* out_counts);
+/* The same search for a collection whose rows are binary16 values (VectorDtype::F16, held decoded in `idx`):
+ * every pair is scored by compute_distance_f16 (src/distance/mod.rs:217-237 -> the scalar f32-query x f16-row
+ * kernels, src/distance/simd.rs:805-1092) as FlatMmap::search / search_filtered do on F16 storage
+ * (src/storage/flat_mmap.rs:905-907 -> exact_flat_search_f16 :1259-1281; :511-520 -> search_filtered_f16
+ * :5329-5437).  The binary metrics use the packed cache, as there. */
+int lb_index_search_f16_rows(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k,
+                             const uint64_t* allow_bits, uint64_t allow_words, uint32_t* out_rows, float* out_dists,
+                             uint32_t* out_counts);
 int lb_index_search_packed(lb_index* idx, int metric, const uint64_t* query_words, uint32_t nq, uint32_t k,
                            uint32_t* out_rows, float* out_dists, uint32_t* out_counts);
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "lb_index_set_plan": (C.c_int, [_vp, C.c_int]),
     "lb_index_search": (C.c_int, [_vp, C.c_int, _f32p, C.c_uint32, C.c_uint32, _u64p, C.c_uint64, _u32p, _f32p, _u32p]),
     "lb_index_search_pairwise": (C.c_int, [_vp, C.c_int, _f32p, C.c_uint32, C.c_uint32, _u64p, C.c_uint64, _u32p, _f32p, _u32p]),
+    "lb_index_search_f16_rows": (C.c_int, [_vp, C.c_int, _f32p, C.c_uint32, C.c_uint32, _u64p, C.c_uint64, _u32p, _f32p, _u32p]),
     "lb_index_search_packed": (C.c_int, [_vp, C.c_int, _u64p, C.c_uint32, C.c_uint32, _u32p, _f32p, _u32p]),
     "lb_index_search_device": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "lb_index_set_timing": (C.c_int, [_vp, C.c_int]),

@@ -47,10 +47,11 @@ class Collection:
         if dtypes not in ("float32", "float16"):
             raise ValueError(f"unsupported dtypes: {dtypes!r}")
         # float16 collections: vectors are rounded to IEEE binary16 at write time exactly as the reference encodes them
-        # (src/storage/dtype.rs:60-67, round-to-nearest-even) and kept DECODED (f32) in HBM, i.e. every search takes
-        # the arithmetic of the reference's F16 batch path, which decodes the store and runs the f32 kernels
-        # (src/engine.rs:5440-5474); the half-width HBM layout with the scalar f16 kernels of the single-query path
-        # (src/distance/simd.rs:805-1092) is not implemented.
+        # (src/storage/dtype.rs:60-67, round-to-nearest-even) and kept DECODED (f32) in HBM — decoding is exact, so the
+        # arithmetic below sees the reference's values.  Unfiltered FLAT batch_search takes the reference's F16 batch
+        # path, which decodes the store and runs the f32 kernels (src/engine.rs:5440-5474); search() and every filtered
+        # search take FlatMmap::search / search_filtered on F16 storage, i.e. the scalar f32-query x f16-row kernels
+        # (src/distance/simd.rs:805-1092) — `lb_index_search_f16_rows`.  The half-width HBM layout is not built.
         self._dtypes = dtypes
         self.name = name
         self.description = description
@@ -355,7 +356,7 @@ class Collection:
             rows = matched if rows is None else rows & matched
         return np.fromiter(sorted(rows), dtype=np.uint64, count=len(rows))
 
-    def _search_rows(self, q: np.ndarray, search_k: int, nprobe: int, subset: Optional[np.ndarray]):
+    def _search_rows(self, q: np.ndarray, search_k: int, nprobe: int, subset: Optional[np.ndarray], single: bool = False):
         """(rows, dists) per query over flushed + pending rows, before id mapping: scan, pending_search, merge_row_results."""
         nq = q.shape[0]
         n_store = len(self._store) if self._store is not None else 0
@@ -369,7 +370,8 @@ class Collection:
                     self._build_ivf()
                 rows, dists, counts = self._ivf.search(q, search_k, nprobe, allow)
             else:
-                rows, dists, counts = self._store.search(q, search_k, self._metric, allow)
+                f16_rows = self._dtypes == "float16" and (single or subset is not None)
+                rows, dists, counts = self._store.search(q, search_k, self._metric, allow, f16_rows=f16_rows)
             out = [(rows[i, :int(counts[i])].astype(np.uint64), dists[i, :int(counts[i])].copy()) for i in range(nq)]
         if self._pending_rows and search_k > 0:
             block = self._pending[0] if len(self._pending) == 1 else np.concatenate(self._pending, axis=0)
@@ -413,8 +415,8 @@ class Collection:
             raise NotImplementedError("document search and external rerankers are outside this package's scope")
         if vector_field != "default":
             raise NotImplementedError("named vector fields are outside this package's scope")
-        return self.batch_search(np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1), k, where=where,
-                                 return_fields=return_fields, nprobe=nprobe, filter_ids=filter_ids)[0]
+        return self._batch_search(np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1), k, where, return_fields, nprobe,
+                                  filter_ids, single=True)[0]
 
     def batch_search(self, vectors, k: int = 10, *, where=None, return_fields: bool = False, nprobe: int = 10, reranker=None,
                      rerank_k=None, rerank_with_fields: bool = False, wire_dtype: str = "float32",
@@ -422,6 +424,9 @@ class Collection:
         del wire_dtype, rerank_with_fields
         if reranker is not None or rerank_k is not None:
             raise NotImplementedError("external rerankers are outside this package's scope")
+        return self._batch_search(vectors, k, where, return_fields, nprobe, filter_ids, single=False)
+
+    def _batch_search(self, vectors, k, where, return_fields, nprobe, filter_ids, single: bool) -> List[ResultView]:
         q = np.ascontiguousarray(vectors, dtype=np.float32)
         if q.ndim == 1:
             q = q.reshape(1, -1)
@@ -433,7 +438,7 @@ class Collection:
                 raise ValueError(f"Dimension mismatch: expected {self._dim}, got {q.shape[1]}")
             subset = self._subset_rows(where, filter_ids)
             search_k = k + len(self._tombstones)             # engine.rs:4735-4741
-            per_query = self._search_rows(q, search_k, int(nprobe), subset)
+            per_query = self._search_rows(q, search_k, int(nprobe), subset, single)
             return [self._finish(r, d, k, return_fields) for (r, d) in per_query]
 
     def __repr__(self) -> str:

@@ -609,6 +609,141 @@ __device__ float compute_distance(int metric, const float* __restrict__ q, const
     return __int_as_float(0x7fc00000);
 }
 
+// ---- f32 query x binary16 row: the scalar kernels of the F16 storage dtype (simd.rs:805-1092) -------------------------
+// Rows of a float16 collection hold exactly binary16-representable values, so `c` may be the decoded row
+// (half::f16::to_f32 is exact).  Every sum is the reference's sequential scalar loop: element order, products and
+// sums rounded separately.  Loads are 8 values at a time, the arithmetic one element at a time.
+template <bool QG, class F>
+__device__ __forceinline__ void scalar_order_foreach(const float* __restrict__ q, const float* __restrict__ c, int dim,
+                                                     bool vec, F&& f) {
+    int chunks = dim >> 3;
+    for (int j = 0; j < chunks; ++j) {
+        Vec8 a = load8<QG>(q + 8 * j, vec), b = load8<true>(c + 8 * j, vec);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f(a.v[i], b.v[i]);
+    }
+    for (int i = chunks * 8; i < dim; ++i) f(QG ? __ldg(q + i) : q[i], __ldg(c + i));
+}
+
+template <bool QG>
+__device__ float inner_product_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    float sum = 0.0f;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) { sum = sum + a * b; });
+    return sum;
+}
+template <bool QG>
+__device__ float l2_squared_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    float sum = 0.0f;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        float diff = a - b;
+        sum = sum + diff * diff;
+    });
+    return sum;
+}
+template <bool QG>
+__device__ float cosine_distance_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    float dot = 0.0f, nq = 0.0f, nc = 0.0f;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        dot = dot + a * b;
+        nq = nq + a * a;
+        nc = nc + b * b;
+    });
+    if (nq == 0.0f || nc == 0.0f) return 1.0f;
+    return 1.0f - dot / (sqrtf(nq) * sqrtf(nc));
+}
+template <bool QG>
+__device__ float manhattan_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    float sum = 0.0f;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) { sum = sum + fabsf(a - b); });
+    return sum;
+}
+template <bool QG>
+__device__ float chebyshev_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    float m = 0.0f;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) { m = rust_max(m, fabsf(a - b)); });
+    return m;
+}
+template <bool QG>
+__device__ float canberra_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    float sum = 0.0f;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        float den = fabsf(a) + fabsf(b);
+        sum = sum + (den == 0.0f ? 0.0f : fabsf(a - b) / den);
+    });
+    return sum;
+}
+template <bool QG>
+__device__ float bray_curtis_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    float num = 0.0f, den = 0.0f;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        num = num + fabsf(a - b);
+        den = den + fabsf(a + b);
+    });
+    if (den == 0.0f) return num == 0.0f ? 0.0f : INFINITY;
+    return num / den;
+}
+template <bool QG>
+__device__ float jensen_shannon_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+    double sa = 0, sb = 0;
+    for (int i = 0; i < dim; ++i) {
+        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
+        if (invalid_mass_value(a) || invalid_mass_value(b)) return INFINITY;
+        sa = sa + (double)a;
+        sb = sb + (double)b;
+    }
+    if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : sqrtf(kLn2);
+    double divergence = 0;
+    for (int i = 0; i < dim; ++i) {
+        double p = (double)(QG ? __ldg(q + i) : q[i]) / sa, qq = (double)__ldg(c + i) / sb, m = 0.5 * (p + qq);
+        if (p > 0.0) divergence = divergence + 0.5 * p * log(p / m);
+        if (qq > 0.0) divergence = divergence + 0.5 * qq * log(qq / m);
+    }
+    return (float)sqrt(fmax(divergence, 0.0));
+}
+template <bool QG>
+__device__ float wasserstein_1d_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+    double sa = 0, sb = 0;
+    for (int i = 0; i < dim; ++i) {
+        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
+        if (invalid_mass_value(a) || invalid_mass_value(b)) return INFINITY;
+        sa = sa + (double)a;
+        sb = sb + (double)b;
+    }
+    if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : INFINITY;
+    double cdf = 0, dist = 0;
+    for (int i = 0; i + 1 < dim; ++i) {
+        cdf = cdf + ((double)(QG ? __ldg(q + i) : q[i]) / sa - (double)__ldg(c + i) / sb);
+        dist = dist + fabs(cdf);
+    }
+    return (float)dist;
+}
+
+// compute_distance_f16 dispatch (src/distance/mod.rs:217-237).  Haversine, correlation and Hellinger repeat their f32
+// formulas on the decoded row; the binary metrics count thresholded bits element by element, as the f32 ones do.
+template <bool QG>
+__device__ float compute_distance_f16order(int metric, const float* __restrict__ q, const float* __restrict__ c, int dim,
+                                           bool vec) {
+    switch (metric) {
+        case LB_IP: return inner_product_f16order<QG>(q, c, dim, vec);
+        case LB_L2: return l2_squared_f16order<QG>(q, c, dim, vec);
+        case LB_COSINE: return cosine_distance_f16order<QG>(q, c, dim, vec);
+        case LB_HAMMING: return hamming_f32<QG>(q, c, dim);
+        case LB_JACCARD:
+        case LB_TANIMOTO: return jaccard_f32<QG>(q, c, dim);
+        case LB_MANHATTAN: return manhattan_f16order<QG>(q, c, dim, vec);
+        case LB_HAVERSINE: return haversine_meters<QG>(q, c, dim);
+        case LB_CORRELATION: return correlation_distance<QG>(q, c, dim);
+        case LB_HELLINGER: return hellinger_distance<QG>(q, c, dim);
+        case LB_WASSERSTEIN: return wasserstein_1d_f16order<QG>(q, c, dim);
+        case LB_DICE: return dice_f32<QG>(q, c, dim);
+        case LB_JENSEN_SHANNON: return jensen_shannon_f16order<QG>(q, c, dim);
+        case LB_CHEBYSHEV: return chebyshev_f16order<QG>(q, c, dim, vec);
+        case LB_CANBERRA: return canberra_f16order<QG>(q, c, dim, vec);
+        case LB_BRAY_CURTIS: return bray_curtis_f16order<QG>(q, c, dim, vec);
+    }
+    return __int_as_float(0x7fc00000);
+}
+
 // ---- packed one-bit rows (simd.rs:765-801) ------------------------------------------------------------------------------
 __device__ __forceinline__ float packed_finish(int metric, uint32_t x /*xor or inter*/, uint32_t y /*union or count*/) {
     if (metric == LB_HAMMING) return (float)x;

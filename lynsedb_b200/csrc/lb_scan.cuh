@@ -43,6 +43,7 @@ struct ScanArgs {
     const uint32_t* small_seg;  // optional [2*n_small] (start,end) ranges of rows living in segments < 4096 rows
     int n_small;
     int ip_single;              // 1: IP uses the two-accumulator kernel for every row (compute_distance semantics)
+    int f16_rows;               // 1: every pair goes through compute_distance_f16's scalar kernels (float16 collections)
     const float* row_stats;     // Jensen-Shannon cached: [n][2] (inv_mass, entropy) or null
     const float* query_stats;   // Jensen-Shannon cached: [nq][2]
     uint64_t* lists;            // [P][nq][k] keys, unsorted
@@ -121,6 +122,7 @@ __device__ __forceinline__ bool in_small_segment(const uint32_t* __restrict__ sm
 template <bool ASC>
 __device__ __forceinline__ float flat_pair_value(const ScanArgs& a, const float* __restrict__ q /*smem*/, int qi,
                                                  const float* __restrict__ c, uint32_t row, bool vec, bool small) {
+    if (a.f16_rows) return compute_distance_f16order<false>(a.metric, q, c, a.dim, vec);  // flat_mmap.rs:1259-1281
     if (!ASC) {
         // IP: rows of segments >= 4096 rows take the batch-8 kernel, smaller segments the single-row kernel
         // (flat_mmap.rs:4845-4869; the <=7 tail rows of a rayon chunk are thread-count dependent)

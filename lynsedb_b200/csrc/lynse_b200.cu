@@ -138,7 +138,10 @@ struct lb_index {
     DevBuf w_queries, w_qwords, w_allow, w_lists, w_counts, w_thr, w_out_rows, w_out_dists, w_out_counts;
     DevBuf w_qb, w_qnorm, w_cand_score, w_cand_row, w_cand_thr, w_flags, w_qstats, w_nq, w_sub_q, w_qmap;
     int plan = LB_PLAN_AUTO;
-    bool pairwise = false;  // this search scores every pair with the single-row kernels on the exact scan
+    // how the running search scores a pair (set under `mu` for the duration of one host-buffer search):
+    // SCORE_FLAT = the FLAT scan's kernels (tensor-core plan allowed), SCORE_PAIRWISE = compute_distance_f32 on the
+    // exact scan, SCORE_F16_ROWS = compute_distance_f16 (scalar order) on the exact scan
+    int score_mode = 0;
     bool timing = false;
     lb_search_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -337,6 +340,7 @@ struct ScanRequest {
     const uint32_t* small_seg = nullptr;
     int n_small = 0;
     int ip_single = 0;
+    int f16_rows = 0;  // score with compute_distance_f16's scalar kernels (old exact kernel only)
     const float* row_stats = nullptr;
     const float* query_stats = nullptr;
     int sqrt_scores = 0;
@@ -349,7 +353,7 @@ struct ScanRequest {
 // scan + merge on idx->stream (k <= n_rows, k <= 2048)
 static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
     // the TMA-staged f32 scan runs one CTA per SM (its ring takes the shared memory): one partition per SM
-    const bool tma_f32 = !r.words && scan2_supported(r.metric) && r.row_stats == nullptr && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+    const bool tma_f32 = !r.words && !r.f16_rows && scan2_supported(r.metric) && r.row_stats == nullptr && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
                          r.row_ids == nullptr && (r.dim & 3) == 0 && r.dim >= 8 && r.n_rows >= 4096 && r.nq <= 4 &&
                          tc_env_int("LYNSE_B200_SCAN_TMA", 1) != 0 &&
                          (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)S3_TQ * (S2_ROWS * 8 + ((r.dim + 3) & ~3) * 4 + 256 * 8) + 2048 <= 226 * 1024;
@@ -375,6 +379,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
     a.small_seg = r.small_seg;
     a.n_small = r.n_small;
     a.ip_single = r.ip_single;
+    a.f16_rows = r.f16_rows;
     a.row_stats = r.row_stats;
     a.query_stats = r.query_stats;
     a.lists = idx->w_lists.as<uint64_t>();
@@ -426,7 +431,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
             default: LB_LAUNCH_PACKED(0); break;
         }
 #undef LB_LAUNCH_PACKED
-    } else if (scan2_supported(r.metric) && r.row_stats == nullptr && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+    } else if (scan2_supported(r.metric) && r.row_stats == nullptr && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
                (size_t)8 * ((r.dim + 3) & ~3) * 4 + 8 * S2_ROWS * 8 + 256 <= 200 * 1024) {
         // streaming scan: the row is read once per query tile (lb_scan2.cuh)
         const int dim_pad = (r.dim + 3) & ~3;
@@ -824,6 +829,8 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
 
 // ---- search on device-resident queries ---------------------------------------------------------------------------------
 // d_queries: f32 [nq][dim] (LB_F32 index) or u64 [nq][n_words] (LB_PACKED_U64 index); results [nq][k], k <= n.
+enum { SCORE_FLAT = 0, SCORE_PAIRWISE = 1, SCORE_F16_ROWS = 2 };
+
 static int search_device_impl(lb_index* idx, int metric, const void* d_queries, int nq, int k, const uint64_t* d_allow,
                               uint32_t* d_rows, float* d_dists, uint32_t* d_counts) {
     idx->stats = lb_search_stats{};
@@ -867,7 +874,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
         idx->stats.plan_used = 2;
         idx->stats.algorithmic_bytes = (uint64_t)idx->n * nw * 8;
-    } else if (idx->plan == LB_PLAN_AUTO && !idx->pairwise && d_allow == nullptr && tc_supported(idx, metric) && k <= 256 && idx->n >= 64) {
+    } else if (idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT && d_allow == nullptr && tc_supported(idx, metric) && k <= 256 && idx->n >= 64) {
         LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr));
         kernels = idx->stats.kernels_launched;
         ms_dom = idx->stats.ms_dominant;
@@ -884,12 +891,13 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         r.allow_bits = d_allow;
         r.small_seg = idx->small_seg.as<uint32_t>();
         r.n_small = idx->n_small;
-        r.ip_single = idx->pairwise ? 1 : 0;
+        r.ip_single = idx->score_mode == SCORE_PAIRWISE ? 1 : 0;
+        r.f16_rows = idx->score_mode == SCORE_F16_ROWS ? 1 : 0;
         r.out_rows = d_rows;
         r.out_dists = d_dists;
         r.out_counts = d_counts;
         std::vector<uint32_t> unhandled;
-        if (metric == LB_JENSEN_SHANNON) {
+        if (metric == LB_JENSEN_SHANNON && !r.f16_rows) {
             // FlatMmap::search Jensen-Shannon branch (flat_mmap.rs:912-921, :926-1111)
             LB_TRY(ensure_js_stats(idx));
             LB_TRY(idx->w_qstats.ensure((size_t)nq * 8));
@@ -912,7 +920,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
             r.sqrt_scores = 1;
         }
         LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
-        if (metric == LB_JENSEN_SHANNON) {
+        if (metric == LB_JENSEN_SHANNON && !r.f16_rows) {
             // queries the cached path cannot serve fall back to the direct kernel (prepare_jensen_shannon_query -> None)
             std::vector<uint32_t> qmap;
             for (int q = 0; q < nq; ++q)
@@ -1174,7 +1182,13 @@ int lb_index_last_stats(const lb_index* idx, lb_search_stats* out) {
     return LB_OK;
 }
 
-static int search_host_common(lb_index* idx, int metric, const void* queries, size_t query_row_bytes, uint32_t nq, uint32_t k,
+struct ScoreModeScope {  // the caller holds idx->mu
+    lb_index* idx;
+    ScoreModeScope(lb_index* i, int mode) : idx(i) { idx->score_mode = mode; }
+    ~ScoreModeScope() { idx->score_mode = SCORE_FLAT; }
+};
+
+static int search_host_common(lb_index* idx, int score_mode, int metric, const void* queries, size_t query_row_bytes, uint32_t nq, uint32_t k,
                               const uint64_t* allow_bits, uint64_t allow_words, uint32_t* out_rows, float* out_dists,
                               uint32_t* out_counts) {
     LB_TRY(check_metric(metric));
@@ -1182,6 +1196,7 @@ static int search_host_common(lb_index* idx, int metric, const void* queries, si
     if (k > (uint32_t)MAX_K) return fail(LB_UNSUPPORTED, "k above 2048 is not supported");
     if (metric == LB_HAVERSINE && idx->dim != 2) return fail(LB_INVALID_ARGUMENT, "haversine requires dimension 2");
     std::lock_guard<std::mutex> lock(idx->mu);
+    ScoreModeScope mode_scope(idx, score_mode);
     DeviceGuard g(idx->device);
     const uint32_t kk = (uint32_t)std::min<uint64_t>(k, idx->n);  // k.min(n) (flat_mmap.rs:836)
     for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
@@ -1233,8 +1248,8 @@ int lb_index_search(lb_index* idx, int metric, const float* queries, uint32_t nq
     if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
     if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "use lb_index_search_packed for a packed index");
     if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
-    return search_host_common(idx, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows, out_dists,
-                              out_counts);
+    return search_host_common(idx, SCORE_FLAT, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows,
+                              out_dists, out_counts);
 }
 
 int lb_index_search_pairwise(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, const uint64_t* allow_bits,
@@ -1242,16 +1257,19 @@ int lb_index_search_pairwise(lb_index* idx, int metric, const float* queries, ui
     if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
     if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "pairwise search needs f32 rows");
     if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
-    {
-        std::lock_guard<std::mutex> lock(idx->mu);
-        idx->pairwise = true;
-    }
-    int st = search_host_common(idx, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows, out_dists, out_counts);
-    {
-        std::lock_guard<std::mutex> lock(idx->mu);
-        idx->pairwise = false;
-    }
-    return st;
+    return search_host_common(idx, SCORE_PAIRWISE, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows,
+                              out_dists, out_counts);
+}
+
+int lb_index_search_f16_rows(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, const uint64_t* allow_bits,
+                             uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "the float16-row search needs (decoded) f32 rows");
+    if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
+    // the binary metrics go through the packed cache whatever the storage dtype (flat_mmap.rs:839-845, :504-510)
+    const int mode = (metric >= 0 && metric < LB_METRIC_COUNT && metric_binary(metric)) ? SCORE_FLAT : SCORE_F16_ROWS;
+    return search_host_common(idx, mode, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows, out_dists,
+                              out_counts);
 }
 
 int lb_index_search_packed(lb_index* idx, int metric, const uint64_t* query_words, uint32_t nq, uint32_t k, uint32_t* out_rows,
@@ -1261,7 +1279,8 @@ int lb_index_search_packed(lb_index* idx, int metric, const uint64_t* query_word
     if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
     if (metric >= 0 && metric < LB_METRIC_COUNT && !metric_binary(metric))
         return fail(LB_INVALID_ARGUMENT, "a packed index only serves hamming/jaccard/tanimoto/dice");
-    return search_host_common(idx, metric, query_words, (size_t)idx->n_words * 8, nq, k, nullptr, 0, out_rows, out_dists, out_counts);
+    return search_host_common(idx, SCORE_FLAT, metric, query_words, (size_t)idx->n_words * 8, nq, k, nullptr, 0, out_rows, out_dists,
+                              out_counts);
 }
 
 int lb_index_search_device(lb_index* idx, int metric, const void* d_queries, uint32_t nq, uint32_t k, uint32_t* d_out_rows,

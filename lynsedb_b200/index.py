@@ -121,12 +121,14 @@ class DeviceIndex:
         N.check(N.lib().lb_index_last_stats(self._h, C.byref(st)))
         return st.as_dict()
 
-    def search(self, queries: np.ndarray, k: int, metric, allow_bits: Optional[np.ndarray] = None, pairwise: bool = False
-               ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    def search(self, queries: np.ndarray, k: int, metric, allow_bits: Optional[np.ndarray] = None, pairwise: bool = False,
+               f16_rows: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """Batched top-k.  Returns ``(rows[nq,k] u32, dists[nq,k] f32, counts[nq] u32)``; entries past
         ``counts[q]`` hold row 0xFFFFFFFF.  Order per query: best score first, ties by ascending row
         (reference src/storage/vector_store.rs:953-970).  ``pairwise=True`` scores every row with the reference's
-        single-pair kernels (``compute_distance_f32``; it only differs from the scan order for IP, in the last ulp)."""
+        single-pair kernels (``compute_distance_f32``; it only differs from the scan order for IP, in the last ulp).
+        ``f16_rows=True`` is the search of a float16 collection's single-query and filtered paths: the rows hold binary16
+        values and every pair goes through the reference's scalar ``compute_distance_f16`` kernels."""
         m = M.require(metric)
         k = int(k)
         if k < 0:
@@ -155,7 +157,10 @@ class DeviceIndex:
             if allow_bits is not None:
                 allow = np.ascontiguousarray(allow_bits, dtype=np.uint64)
                 ab, aw = N.u64ptr(allow), allow.size
-            fn = N.lib().lb_index_search_pairwise if pairwise else N.lib().lb_index_search
+            if pairwise and f16_rows:
+                raise ValueError("pairwise and f16_rows are different scoring rules; pick one")
+            fn = (N.lib().lb_index_search_pairwise if pairwise else
+                  N.lib().lb_index_search_f16_rows if f16_rows else N.lib().lb_index_search)
             N.check(fn(self._h, m, N.fptr(q), nq, k, ab, aw, N.u32ptr(rows), N.fptr(dists), N.u32ptr(counts)))
         return rows, dists, counts
 

@@ -70,6 +70,10 @@ def lib():
                                              C.c_int, u64p, f32p, u32p]
         L.lo_kmeans_train.restype = C.c_uint32
         L.lo_kmeans_train.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, f32p, u32p]
+        L.lo_compute_distance_f16.restype = C.c_float
+        L.lo_compute_distance_f16.argtypes = [f32p, f32p, C.c_uint64, C.c_int]
+        L.lo_store_search_f16.restype = C.c_uint32
+        L.lo_store_search_f16.argtypes = [f32p, u64p, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_int, C.c_int, u64p, f32p]
         L.lo_ivf_flat_search.restype = C.c_uint32
         L.lo_ivf_flat_search.argtypes = [f32p, C.c_uint64, C.c_uint64, f32p, C.c_uint32, u32p, f32p, C.c_uint32, C.c_uint32,
                                          C.c_int, u32p, f32p, u32p, u32p]
@@ -258,3 +262,25 @@ def ivf_flat_routing_dims(centroids):
     out = np.zeros(16, dtype=np.uint32)
     cnt = lib().lo_ivf_flat_routing_dims(_p(c, C.c_float), c.shape[1], c.shape[0], _p(out, C.c_uint32))
     return out[:cnt].copy()
+
+
+def compute_distance_f16(query, row, metric):
+    """compute_distance_f16 (src/distance/mod.rs:217-237): f32 query x binary16 row in the scalar kernels' order.
+    ``row`` is rounded to binary16 first (what the F16 storage dtype holds)."""
+    q = _f32(query).ravel()
+    r = np.ascontiguousarray(np.asarray(row, dtype=np.float32).astype(np.float16).astype(np.float32)).ravel()
+    return float(lib().lo_compute_distance_f16(_p(q, C.c_float), _p(r, C.c_float), q.size, metric_id(metric)))
+
+
+def store_search_f16(data, query, k, metric, segments=None, n_threads=None):
+    """VectorStore::search of a float16 collection for one query -> (u64 rows, f32 dists).  ``data`` is rounded to
+    binary16 first; ``segments`` are the segment row counts (default: one segment)."""
+    d = np.ascontiguousarray(_f32(data).astype(np.float16).astype(np.float32))
+    q = _f32(query).ravel()
+    n, dim = d.shape
+    seg = np.ascontiguousarray(segments if segments is not None else [n], dtype=np.uint64)
+    ids = np.empty(max(k, 1), dtype=np.uint64)
+    dists = np.empty(max(k, 1), dtype=np.float32)
+    cnt = lib().lo_store_search_f16(_p(d, C.c_float), _p(seg, C.c_uint64), seg.size, dim, _p(q, C.c_float), k, metric_id(metric),
+                                    n_threads or host_threads(), _p(ids, C.c_uint64), _p(dists, C.c_float))
+    return ids[:cnt].copy(), dists[:cnt].copy()

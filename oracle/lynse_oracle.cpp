@@ -596,6 +596,116 @@ float compute_distance(const float* a, const float* b, size_t n, int metric) {
     return std::numeric_limits<float>::quiet_NaN();
 }
 
+// ---- simd.rs:805-1092 — f32 query x binary16 candidate row, the scalar kernels of the F16 storage dtype ------
+// `c` holds the candidate's DECODED values (half::f16::to_f32 is exact, so decoding first changes nothing); every
+// accumulation below is the reference's sequential scalar loop (no SIMD lanes, products and sums unfused).
+float inner_product_f16(const float* q, const float* c, size_t n) {
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; ++i) sum += q[i] * c[i];
+    return sum;
+}
+float l2_squared_f16(const float* q, const float* c, size_t n) {
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        float diff = q[i] - c[i];
+        sum += diff * diff;
+    }
+    return sum;
+}
+float cosine_distance_f16(const float* q, const float* c, size_t n) {
+    float dot = 0.0f, nq = 0.0f, nc = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        dot += q[i] * c[i];
+        nq += q[i] * q[i];
+        nc += c[i] * c[i];
+    }
+    if (nq == 0.0f || nc == 0.0f) return 1.0f;
+    return 1.0f - dot / (std::sqrt(nq) * std::sqrt(nc));
+}
+float manhattan_f16(const float* q, const float* c, size_t n) {
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; ++i) sum += std::fabs(q[i] - c[i]);
+    return sum;
+}
+float chebyshev_f16(const float* q, const float* c, size_t n) {
+    float m = 0.0f;
+    for (size_t i = 0; i < n; ++i) m = rust_max(m, std::fabs(q[i] - c[i]));
+    return m;
+}
+float canberra_f16(const float* q, const float* c, size_t n) {
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        float den = std::fabs(q[i]) + std::fabs(c[i]);
+        sum += den == 0.0f ? 0.0f : std::fabs(q[i] - c[i]) / den;
+    }
+    return sum;
+}
+float bray_curtis_f16(const float* q, const float* c, size_t n) {
+    float num = 0.0f, den = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        num += std::fabs(q[i] - c[i]);
+        den += std::fabs(q[i] + c[i]);
+    }
+    if (den == 0.0f) return num == 0.0f ? 0.0f : kInf;
+    return num / den;
+}
+float jensen_shannon_distance_f16(const float* a, const float* b, size_t n) {
+    double sum_a = 0, sum_b = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (invalid_mass_value(a[i]) || invalid_mass_value(b[i])) return kInf;
+        sum_a += (double)a[i];
+        sum_b += (double)b[i];
+    }
+    if (sum_a == 0.0 || sum_b == 0.0) return sum_a == sum_b ? 0.0f : std::sqrt(kLn2);
+    double divergence = 0;
+    for (size_t i = 0; i < n; ++i) {
+        double p = (double)a[i] / sum_a, q = (double)b[i] / sum_b, m = 0.5 * (p + q);
+        if (p > 0.0) divergence += 0.5 * p * std::log(p / m);
+        if (q > 0.0) divergence += 0.5 * q * std::log(q / m);
+    }
+    return (float)std::sqrt(std::max(divergence, 0.0));
+}
+float wasserstein_1d_f16(const float* a, const float* b, size_t n) {
+    double sa = 0, sb = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (invalid_mass_value(a[i]) || invalid_mass_value(b[i])) return kInf;
+        sa += (double)a[i];
+        sb += (double)b[i];
+    }
+    if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : kInf;
+    double cdf = 0, dist = 0;
+    for (size_t i = 0; i + 1 < n; ++i) {
+        cdf += (double)a[i] / sa - (double)b[i] / sb;
+        dist += std::fabs(cdf);
+    }
+    return (float)dist;
+}
+
+// ---- distance/mod.rs:217-237 — compute_distance_f16 ---------------------------------------------------------
+// (Haversine, correlation and Hellinger repeat their f32 formulas on the decoded row; the binary metrics count
+// thresholded bits, which the f32 versions above already do element by element.)
+float compute_distance_f16(const float* q, const float* c, size_t n, int metric) {
+    switch (metric) {
+        case IP: return inner_product_f16(q, c, n);
+        case L2: return l2_squared_f16(q, c, n);
+        case COSINE: return cosine_distance_f16(q, c, n);
+        case HAMMING: return hamming_f32(q, c, n);
+        case JACCARD:
+        case TANIMOTO: return jaccard_f32(q, c, n);
+        case MANHATTAN: return manhattan_f16(q, c, n);
+        case HAVERSINE: return haversine_meters(q, c, n);
+        case CORRELATION: return correlation_distance(q, c, n);
+        case HELLINGER: return hellinger_distance(q, c, n);
+        case WASSERSTEIN: return wasserstein_1d_f16(q, c, n);
+        case DICE: return dice_f32(q, c, n);
+        case JENSEN_SHANNON: return jensen_shannon_distance_f16(q, c, n);
+        case CHEBYSHEV: return chebyshev_f16(q, c, n);
+        case CANBERRA: return canberra_f16(q, c, n);
+        case BRAY_CURTIS: return bray_curtis_f16(q, c, n);
+    }
+    return std::numeric_limits<float>::quiet_NaN();
+}
+
 // ---- flat_mmap.rs:1453-1476, 2132-2176 — sorted-array top-k -----------------
 struct Entry {
     float dist;
@@ -859,6 +969,18 @@ std::vector<Entry> flat_search(const float* cands, size_t n, size_t dim, const f
                                [&](const float* c, size_t) { return compute_distance(query, c, dim, metric); });
 }
 
+// ---- flat_mmap.rs:905-907, 1259-1281, 5047-5180 — FlatMmap::search on an F16 segment -----------------------
+// binary metrics take the packed cache first (as for f32 rows); everything else is fused_topk_parallel_f16 over
+// the scalar kernels (no batch-8 inner product, no Jensen-Shannon cache).
+std::vector<Entry> flat_search_f16(const float* cands, size_t n, size_t dim, const float* query, size_t k, int metric,
+                                   int n_threads) {
+    if (n == 0 || k == 0) return {};
+    if (is_binary(metric)) return flat_search(cands, n, dim, query, k, metric, n_threads);
+    k = std::min(k, n);
+    return fused_topk_parallel(cands, n, dim, k, is_ascending(metric), n_threads,
+                               [&](const float* c, size_t) { return compute_distance_f16(query, c, dim, metric); });
+}
+
 // ---- vector_store.rs:953-1004 — segment fan-out + global merge --------------
 struct Hit {
     uint64_t row;
@@ -866,11 +988,12 @@ struct Hit {
 };
 
 std::vector<Hit> store_search(const float* cands, const uint64_t* seg_rows, size_t n_segs, size_t dim,
-                              const float* query, size_t k, int metric, int n_threads) {
+                              const float* query, size_t k, int metric, int n_threads, bool f16_rows = false) {
     std::vector<Hit> merged;
     uint64_t base = 0;
     for (size_t s = 0; s < n_segs; ++s) {
-        auto local = flat_search(cands + base * dim, seg_rows[s], dim, query, k, metric, n_threads);
+        auto local = f16_rows ? flat_search_f16(cands + base * dim, seg_rows[s], dim, query, k, metric, n_threads)
+                              : flat_search(cands + base * dim, seg_rows[s], dim, query, k, metric, n_threads);
         for (const auto& e : local) merged.push_back({base + e.idx, e.dist});
         base += seg_rows[s];
     }
@@ -1311,6 +1434,23 @@ void lo_packed_batch_search(const uint64_t* data, uint64_t words, uint64_t n, co
             dists[q * k + i] = res[i].dist;
         }
     }
+}
+
+// compute_distance_f16 on a decoded binary16 row
+float lo_compute_distance_f16(const float* q, const float* row, uint64_t dim, int metric) {
+    return compute_distance_f16(q, row, dim, metric);
+}
+
+// VectorStore::search of a float16 collection, one query (each segment: FlatMmap::search on F16 rows).
+// `cands` holds the decoded rows.
+uint32_t lo_store_search_f16(const float* cands, const uint64_t* seg_rows, uint64_t n_segs, uint64_t dim, const float* query,
+                             uint32_t k, int metric, int n_threads, uint64_t* ids, float* dists) {
+    auto res = store_search(cands, seg_rows, n_segs, dim, query, k, metric, std::max(n_threads, 1), true);
+    for (size_t i = 0; i < res.size(); ++i) {
+        ids[i] = res[i].row;
+        dists[i] = res[i].dist;
+    }
+    return (uint32_t)res.size();
 }
 
 // kmeans::train_for_metric; returns the number of centroids (min(requested, n))

@@ -33,8 +33,9 @@ class FakeIndex:
     def close(self):
         pass
 
-    def search(self, q, k, metric, allow_bits=None):
+    def search(self, q, k, metric, allow_bits=None, f16_rows=False):
         assert metric in (M.IP, M.L2)
+        self.f16_calls = getattr(self, "f16_calls", []) + [bool(f16_rows)]
         nq, n = q.shape[0], len(self)
         rows = np.full((nq, k), 0xFFFFFFFF, np.uint32)
         dists = np.full((nq, k), np.nan, np.float32)
@@ -175,3 +176,24 @@ def test_float16_collection_rounds_like_the_reference_encoder(fake):
     assert d == pytest.approx(float(((stored[0] - v[0]) ** 2).sum()), rel=1e-6) and d > 0   # the f16 rounding is visible
     with pytest.raises(ValueError):
         Collection("e", 2, dtypes="int8")
+
+
+def test_float16_collection_routes_single_and_filtered_searches_to_the_scalar_kernels(fake):
+    # FlatMmap::search / search_filtered on F16 storage use the scalar f16 kernels (flat_mmap.rs:905-907, :511-520);
+    # only the unfiltered batch path decodes and runs the f32 kernels (engine.rs:5440-5474)
+    rng = np.random.default_rng(0)
+    coll = Collection("c", 4, dtypes="float16")
+    coll.add(list(range(8)), vectors=rng.random((8, 4), dtype=np.float32))
+    coll.commit()
+    q = rng.random((2, 4), dtype=np.float32)
+    coll.search(q[0], 3)
+    coll.batch_search(q, 3)
+    coll.batch_search(q[:1], 3)
+    coll.batch_search(q, 3, filter_ids=[1, 2, 3])
+    assert coll._store.f16_calls == [True, False, False, True]
+    plain = Collection("d", 4)
+    plain.add(list(range(8)), vectors=rng.random((8, 4), dtype=np.float32))
+    plain.commit()
+    plain.search(q[0], 3)
+    plain.batch_search(q, 3, filter_ids=[1, 2, 3])
+    assert plain._store.f16_calls == [False, False]

@@ -422,3 +422,42 @@ def test_ivf_flat_ip_routing_shortlist(oracle):
     _, _, probes_l2 = oracle.ivf_flat_search(data, cent, assign, q, 10, 8, "l2", return_probes=True)
     cd = np.array([oracle.compute_distance(q, c, "l2") for c in cent], dtype=np.float32)
     assert set(probes_l2.tolist()) == set(np.argsort(cd, kind="stable")[:8].tolist())
+
+
+# ---- float16 storage: the scalar f32-query x f16-row kernels (src/distance/simd.rs:805-1092) ------------------------
+def test_f16_row_kernels_known_answers(oracle):
+    # the f32 known answers (simd.rs:2906-2977) hold on binary16-exact inputs, whichever kernel family computes them
+    a, b = [1.0, 2.0, 3.0, 4.0], [4.0, 3.0, 2.0, 1.0]
+    assert oracle.compute_distance_f16(a, b, "ip") == 20.0
+    assert oracle.compute_distance_f16([1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], "l2") == 2.0
+    assert oracle.compute_distance_f16(a, a, "cosine") == pytest.approx(0.0, abs=1e-6)
+    assert oracle.compute_distance_f16([1.0, 0.0], [0.0, 1.0], "cosine") == 1.0
+    assert oracle.compute_distance_f16([0.0, 0.0], [0.0, 1.0], "cosine") == 1.0      # zero norm -> 1 (simd.rs:842-846)
+    assert oracle.compute_distance_f16([1.0, 2.0, 3.0], [2.0, 4.0, 1.0], "l1") == 5.0
+    assert oracle.compute_distance_f16([1.0, 2.0, 3.0], [2.0, 4.0, 1.0], "chebyshev") == 2.0
+    assert oracle.compute_distance_f16([1.0, 0.0, 2.0], [3.0, 0.0, 2.0], "canberra") == 0.5
+    assert oracle.compute_distance_f16([1.0, 2.0], [2.0, 1.0], "bray_curtis") == pytest.approx(1.0 / 3.0, rel=1e-6)
+    assert oracle.compute_distance_f16([1.0, 0.0], [0.0, 1.0], "jensen_shannon") == pytest.approx(np.sqrt(np.log(2.0)), rel=1e-6)
+    assert oracle.compute_distance_f16([1.0, 0.0], [0.0, 1.0], "wasserstein") == 1.0
+    assert oracle.compute_distance_f16([1.0, -1.0], [1.0, 1.0], "hellinger") == np.inf
+
+
+def test_f16_row_kernels_agree_with_the_f32_kernels_to_rounding(oracle):
+    rng = np.random.default_rng(11)
+    q = rng.random(300, dtype=np.float32)
+    row = rng.random(300, dtype=np.float32).astype(np.float16).astype(np.float32)
+    for metric in ("ip", "l2", "cosine", "l1", "chebyshev", "canberra", "bray_curtis", "jensen_shannon", "wasserstein",
+                   "hellinger", "correlation", "hamming", "jaccard", "dice"):
+        assert oracle.compute_distance_f16(q, row, metric) == pytest.approx(oracle.compute_distance(q, row, metric), rel=2e-5, abs=1e-6)
+    # and the sequential sum really is a different order from the 8-lane kernels
+    assert any(oracle.compute_distance_f16(rng.random(300, dtype=np.float32), row, "ip") != oracle.compute_distance(q, row, "ip")
+               for _ in range(4))
+
+
+def test_f16_collection_reference_cases(oracle):
+    # f16_collection_batch_search_reuses_decoded_candidates (src/engine.rs:8043-8076), single-query flavour
+    data = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0.5, 0.5, 0, 0]], dtype=np.float32)
+    ids, _ = oracle.store_search_f16(data, [1.0, 0.0, 0.0, 0.0], 2, "ip")
+    assert ids.tolist() == [0, 2]
+    ids, _ = oracle.store_search_f16(data, [0.0, 1.0, 0.0, 0.0], 2, "ip")
+    assert ids.tolist() == [1, 2]
