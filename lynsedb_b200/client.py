@@ -188,6 +188,11 @@ class Collection:
             if self._dim is None:
                 raise ValueError("collection dimension is not known yet")
             self._store = DeviceIndex(self._dim, "float32", self._device)
+            if self._dtypes == "float16":
+                # segment boundaries never reach a float16 collection's results: search() scores rows one by one, and the
+                # batch path scans `read_all_f32()` — the whole store as ONE array (src/engine.rs:5448-5453), so the
+                # inner-product small-segment rule is evaluated on the total row count.  One segment says the same.
+                self._store.set_segment_target(1 << 62)
         return self._store
 
     def _flush_pending(self) -> None:

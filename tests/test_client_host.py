@@ -27,6 +27,9 @@ class FakeIndex:
     def segments(self):
         return list(self.appends)
 
+    def set_segment_target(self, n_bytes):
+        self.segment_target = n_bytes
+
     def prepare(self, metric):
         pass
 

@@ -107,3 +107,25 @@ def test_f16_collection_search_takes_the_scalar_path_and_batch_the_decoded_one(L
             assert single.ids.tolist() == want_ids.tolist()
             assert np.array_equal(single.distances.view(np.uint32), want_d.view(np.uint32))
         coll.close()
+
+
+def test_f16_collection_batch_path_scans_the_store_as_one_array(L, oracle):
+    # engine.rs:5448-5453: batch_exact_flat_search_f32 over read_all_f32() — a 100-row flush followed by a 6000-row one
+    # is ONE 6100-row array, so every row takes the batch-8 inner-product order (no small-segment rule)
+    rng = np.random.default_rng(31)
+    dim = 40
+    raw = rng.random((6100, dim), dtype=np.float32)
+    stored = _f16(raw)
+    coll = L.Collection("c", dim, dtypes="float16")
+    coll.add(list(range(100)), vectors=raw[:100])
+    coll.commit()
+    coll.add(list(range(100, 6100)), vectors=raw[100:])
+    coll.commit()
+    assert coll._store.segments() == [6100]
+    q = rng.random((3, dim), dtype=np.float32)
+    res = coll.batch_search(q, 10)
+    ids, dists, counts = oracle.store_batch_search(stored, q, 10, "ip", segment_rows=[6100])
+    for i in range(3):
+        assert res[i].ids.tolist() == ids[i, :counts[i]].tolist()
+        assert np.array_equal(res[i].distances.view(np.uint32), dists[i, :counts[i]].view(np.uint32))
+    coll.close()
