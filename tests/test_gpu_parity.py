@@ -441,3 +441,91 @@ def test_packed_two_million_rows_matches_oracle(L, oracle):
             data = synthetic.rows_packed(42, np.arange(n), 16)
             o_ids, o_d, o_c = oracle.packed_batch_search(data, q, k, metric, n_threads=oracle.host_threads())
             assert np.array_equal(rows, o_ids.astype(np.uint32)) and np.array_equal(dists.view(np.uint32), o_d.view(np.uint32))
+
+
+def test_concurrent_searches_on_one_index_are_serialised(L):
+    # ctypes releases the GIL; the reference holds a read lock per collection (src/python/mod.rs:1187, :1399).  Every
+    # entry point takes the index mutex, and the per-call scoring rule (flat / pairwise / f16 rows) lives under it.
+    import threading
+
+    rng = np.random.default_rng(123)
+    data = rng.random((20000, 64), dtype=np.float32).astype(np.float16).astype(np.float32)
+    queries = rng.random((8, 64), dtype=np.float32)
+    idx = L.DeviceIndex(64)
+    idx.append(data)
+    jobs = [("ip", {}), ("ip", {"pairwise": True}), ("ip", {"f16_rows": True}), ("l2", {}), ("cosine", {"f16_rows": True}),
+            ("l1", {}), ("hamming", {}), ("jensen_shannon", {})]
+    want = [idx.search(queries, 10, m, **kw) for m, kw in jobs]
+    got = [[None] * len(jobs) for _ in range(4)]
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(3):
+                for j in range(len(jobs)):
+                    jj = (j + t) % len(jobs)
+                    m, kw = jobs[jj]
+                    got[t][jj] = idx.search(queries, 10, m, **kw)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    for t in range(4):
+        for j in range(len(jobs)):
+            for a, b in zip(want[j], got[t][j]):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (t, jobs[j])
+    idx.close()
+
+
+@pytest.mark.parametrize("metric", ["ip", "l2", "cosine"])
+def test_tc_plan_adversarial_ties(L, oracle, metric):
+    # every row duplicated 40 times: the coarse pass sees 40-way exact ties at every rank, and the result must still be
+    # the (score, row) order of VectorStore::merge_results (src/storage/vector_store.rs:953-970)
+    rng = np.random.default_rng(17)
+    base = rng.random((256, 64), dtype=np.float32)
+    corpus = np.ascontiguousarray(np.tile(base, (40, 1)))          # 10240 rows
+    queries = np.ascontiguousarray(base[:160] + np.float32(0.001))  # two query tiles -> the CTA-pair kernel too
+    with L.DeviceIndex(64) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, 50, metric)
+        plan = idx.last_stats()["plan_used"]
+    assert plan == 1
+    _check(oracle.store_batch_search(corpus, queries, 50, metric), got, metric, 50)
+
+
+@pytest.mark.parametrize("metric", ["hamming", "tanimoto", "dice"])
+def test_packed_1024_bit_adversarial_ties(L, oracle, metric):
+    # the 1024-bit TMA kernel on a corpus with 8192-way duplicates (adversarial-ties set)
+    rng = np.random.default_rng(23)
+    base = rng.integers(0, 2 ** 63, size=(8, 16), dtype=np.uint64)
+    corpus = np.ascontiguousarray(np.tile(base, (8192, 1)))         # 65536 rows
+    queries = np.ascontiguousarray(base[:5] ^ np.uint64(1))
+    with L.DeviceIndex(1024, "packed") as idx:
+        idx.append(corpus)
+        rows, dists, counts = idx.search(queries, 32, metric)
+    o_ids, o_d, o_c = oracle.packed_batch_search(corpus, queries, 32, metric)
+    assert np.array_equal(counts, o_c)
+    assert np.array_equal(rows, o_ids.astype(np.uint32))
+    assert np.array_equal(dists.view(np.uint32), o_d.view(np.uint32))
+    assert np.array_equal(rows[0], np.arange(32, dtype=np.uint32) * 8)   # the 32 lowest copies of row 0
+
+
+def test_k_limits_and_ragged_dimensions(L, oracle):
+    corpus, queries = _data(5000, 7, 91), _data(3, 7, 92)
+    with L.DeviceIndex(7) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, 2048, "l2")                        # MAX_K
+        _check(oracle.store_batch_search(corpus, queries, 2048, "l2"), got, "l2", 2048)
+        with pytest.raises(RuntimeError, match="k above 2048"):
+            idx.search(queries, 2049, "l2")
+    for dim in (1, 3, 9, 130, 771):                                  # 771: wider than the tensor path takes
+        c, q = _data(4500, dim, dim), _data(2, dim, dim + 1)
+        with L.DeviceIndex(dim) as idx:
+            idx.append(c)
+            for metric in ("ip", "cosine", "l1"):
+                _check(oracle.store_batch_search(c, q, 5, metric), idx.search(q, 5, metric), metric, 5)
