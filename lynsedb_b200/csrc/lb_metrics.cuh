@@ -281,6 +281,20 @@ __device__ float dice_f32(const float* __restrict__ q, const float* __restrict__
 }
 
 // ---- scalar f64 metrics ---------------------------------------------------------------------------------
+// Elements of a pair in index order: loads are 8 values at a time (two 128-bit loads per operand when `vec`), the
+// arithmetic one element at a time — for the kernels whose reference loop is a plain sequential one.
+template <bool QG, class F>
+__device__ __forceinline__ void scalar_order_foreach(const float* __restrict__ q, const float* __restrict__ c, int dim,
+                                                     bool vec, F&& f) {
+    int chunks = dim >> 3;
+    for (int j = 0; j < chunks; ++j) {
+        Vec8 a = load8<QG>(q + 8 * j, vec), b = load8<true>(c + 8 * j, vec);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f(a.v[i], b.v[i]);
+    }
+    for (int i = chunks * 8; i < dim; ++i) f(QG ? __ldg(q + i) : q[i], __ldg(c + i));
+}
+
 __device__ __forceinline__ double clamp_f64(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __device__ __forceinline__ bool invalid_mass_value(float v) { return !isfinite(v) || v < 0.0f; }
 
@@ -303,17 +317,17 @@ __device__ float haversine_meters(const float* __restrict__ q, const float* __re
 
 // simd.rs:632-661
 template <bool QG>
-__device__ float correlation_distance(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+__device__ float correlation_distance(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
     if (dim == 0) return 0.0f;
     double n = (double)dim, sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
-    for (int i = 0; i < dim; ++i) {
-        double av = (double)(QG ? __ldg(q + i) : q[i]), bv = (double)__ldg(c + i);
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        double av = (double)a, bv = (double)b;
         sa = sa + av;
         sb = sb + bv;
         saa = saa + av * av;
         sbb = sbb + bv * bv;
         sab = sab + av * bv;
-    }
+    });
     double var_a = fmax(saa - sa * sa / n, 0.0);
     double var_b = fmax(sbb - sb * sb / n, 0.0);
     double denom = sqrt(var_a * var_b);
@@ -326,39 +340,47 @@ __device__ float correlation_distance(const float* __restrict__ q, const float* 
     return (float)(1.0 - clamp_f64(cov / denom, -1.0, 1.0));
 }
 
-// simd.rs:665-684
+// simd.rs:665-684 (the early return on an invalid value is the same +inf whichever element trips it)
 template <bool QG>
-__device__ float hellinger_distance(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+__device__ float hellinger_distance(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
     double sa = 0, sb = 0, coef = 0;
-    for (int i = 0; i < dim; ++i) {
-        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
-        if (invalid_mass_value(a) || invalid_mass_value(b)) return INFINITY;
+    bool bad = false;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        bad = bad || invalid_mass_value(a) || invalid_mass_value(b);
         sa = sa + (double)a;
         sb = sb + (double)b;
         coef = coef + sqrt((double)a * (double)b);
-    }
+    });
+    if (bad) return INFINITY;
     if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : 1.0f;
     double cc = coef / sqrt(sa * sb);
     return (float)sqrt(1.0 - clamp_f64(cc, 0.0, 1.0));
 }
 
-// simd.rs:688-714
-template <bool QG>
-__device__ float wasserstein_1d(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+// simd.rs:688-714; DIVIDE = wasserstein_1d_f16 (simd.rs:1046-1071), which divides by the masses instead of
+// multiplying by their reciprocals
+template <bool QG, bool DIVIDE>
+__device__ float wasserstein_1d_impl(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
     double sa = 0, sb = 0;
-    for (int i = 0; i < dim; ++i) {
-        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
-        if (invalid_mass_value(a) || invalid_mass_value(b)) return INFINITY;
+    bool bad = false;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        bad = bad || invalid_mass_value(a) || invalid_mass_value(b);
         sa = sa + (double)a;
         sb = sb + (double)b;
-    }
+    });
+    if (bad) return INFINITY;
     if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : INFINITY;
-    double inv_a = 1.0 / sa, inv_b = 1.0 / sb, cdf = 0, dist = 0;
-    for (int i = 0; i + 1 < dim; ++i) {
-        cdf = cdf + ((double)(QG ? __ldg(q + i) : q[i]) * inv_a - (double)__ldg(c + i) * inv_b);
+    const double inv_a = 1.0 / sa, inv_b = 1.0 / sb;
+    double cdf = 0, dist = 0;
+    scalar_order_foreach<QG>(q, c, dim > 0 ? dim - 1 : 0, vec, [&](float a, float b) {  // the last bin never contributes
+        cdf = cdf + (DIVIDE ? ((double)a / sa - (double)b / sb) : ((double)a * inv_a - (double)b * inv_b));
         dist = dist + fabs(cdf);
-    }
+    });
     return (float)dist;
+}
+template <bool QG>
+__device__ float wasserstein_1d(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    return wasserstein_1d_impl<QG, false>(q, c, dim, vec);
 }
 
 // ---- Jensen-Shannon ----------------------------------------------------------------------------------------
@@ -597,9 +619,9 @@ __device__ float compute_distance(int metric, const float* __restrict__ q, const
         case LB_TANIMOTO: return jaccard_f32<QG>(q, c, dim);
         case LB_MANHATTAN: return manhattan<QG>(q, c, dim, vec);
         case LB_HAVERSINE: return haversine_meters<QG>(q, c, dim);
-        case LB_CORRELATION: return correlation_distance<QG>(q, c, dim);
-        case LB_HELLINGER: return hellinger_distance<QG>(q, c, dim);
-        case LB_WASSERSTEIN: return wasserstein_1d<QG>(q, c, dim);
+        case LB_CORRELATION: return correlation_distance<QG>(q, c, dim, vec);
+        case LB_HELLINGER: return hellinger_distance<QG>(q, c, dim, vec);
+        case LB_WASSERSTEIN: return wasserstein_1d<QG>(q, c, dim, vec);
         case LB_DICE: return dice_f32<QG>(q, c, dim);
         case LB_JENSEN_SHANNON: return jensen_shannon_distance<QG>(q, c, dim, vec);
         case LB_CHEBYSHEV: return chebyshev<QG>(q, c, dim, vec);
@@ -613,18 +635,6 @@ __device__ float compute_distance(int metric, const float* __restrict__ q, const
 // Rows of a float16 collection hold exactly binary16-representable values, so `c` may be the decoded row
 // (half::f16::to_f32 is exact).  Every sum is the reference's sequential scalar loop: element order, products and
 // sums rounded separately.  Loads are 8 values at a time, the arithmetic one element at a time.
-template <bool QG, class F>
-__device__ __forceinline__ void scalar_order_foreach(const float* __restrict__ q, const float* __restrict__ c, int dim,
-                                                     bool vec, F&& f) {
-    int chunks = dim >> 3;
-    for (int j = 0; j < chunks; ++j) {
-        Vec8 a = load8<QG>(q + 8 * j, vec), b = load8<true>(c + 8 * j, vec);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f(a.v[i], b.v[i]);
-    }
-    for (int i = chunks * 8; i < dim; ++i) f(QG ? __ldg(q + i) : q[i], __ldg(c + i));
-}
-
 template <bool QG>
 __device__ float inner_product_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
     float sum = 0.0f;
@@ -683,39 +693,27 @@ __device__ float bray_curtis_f16order(const float* __restrict__ q, const float* 
     return num / den;
 }
 template <bool QG>
-__device__ float jensen_shannon_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+__device__ float jensen_shannon_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
     double sa = 0, sb = 0;
-    for (int i = 0; i < dim; ++i) {
-        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
-        if (invalid_mass_value(a) || invalid_mass_value(b)) return INFINITY;
+    bool bad = false;
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        bad = bad || invalid_mass_value(a) || invalid_mass_value(b);
         sa = sa + (double)a;
         sb = sb + (double)b;
-    }
+    });
+    if (bad) return INFINITY;
     if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : sqrtf(kLn2);
     double divergence = 0;
-    for (int i = 0; i < dim; ++i) {
-        double p = (double)(QG ? __ldg(q + i) : q[i]) / sa, qq = (double)__ldg(c + i) / sb, m = 0.5 * (p + qq);
+    scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
+        double p = (double)a / sa, qq = (double)b / sb, m = 0.5 * (p + qq);
         if (p > 0.0) divergence = divergence + 0.5 * p * log(p / m);
         if (qq > 0.0) divergence = divergence + 0.5 * qq * log(qq / m);
-    }
+    });
     return (float)sqrt(fmax(divergence, 0.0));
 }
 template <bool QG>
-__device__ float wasserstein_1d_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim) {
-    double sa = 0, sb = 0;
-    for (int i = 0; i < dim; ++i) {
-        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
-        if (invalid_mass_value(a) || invalid_mass_value(b)) return INFINITY;
-        sa = sa + (double)a;
-        sb = sb + (double)b;
-    }
-    if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : INFINITY;
-    double cdf = 0, dist = 0;
-    for (int i = 0; i + 1 < dim; ++i) {
-        cdf = cdf + ((double)(QG ? __ldg(q + i) : q[i]) / sa - (double)__ldg(c + i) / sb);
-        dist = dist + fabs(cdf);
-    }
-    return (float)dist;
+__device__ float wasserstein_1d_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+    return wasserstein_1d_impl<QG, true>(q, c, dim, vec);
 }
 
 // compute_distance_f16 dispatch (src/distance/mod.rs:217-237).  Haversine, correlation and Hellinger repeat their f32
@@ -732,11 +730,11 @@ __device__ float compute_distance_f16order(int metric, const float* __restrict__
         case LB_TANIMOTO: return jaccard_f32<QG>(q, c, dim);
         case LB_MANHATTAN: return manhattan_f16order<QG>(q, c, dim, vec);
         case LB_HAVERSINE: return haversine_meters<QG>(q, c, dim);
-        case LB_CORRELATION: return correlation_distance<QG>(q, c, dim);
-        case LB_HELLINGER: return hellinger_distance<QG>(q, c, dim);
-        case LB_WASSERSTEIN: return wasserstein_1d_f16order<QG>(q, c, dim);
+        case LB_CORRELATION: return correlation_distance<QG>(q, c, dim, vec);
+        case LB_HELLINGER: return hellinger_distance<QG>(q, c, dim, vec);
+        case LB_WASSERSTEIN: return wasserstein_1d_f16order<QG>(q, c, dim, vec);
         case LB_DICE: return dice_f32<QG>(q, c, dim);
-        case LB_JENSEN_SHANNON: return jensen_shannon_f16order<QG>(q, c, dim);
+        case LB_JENSEN_SHANNON: return jensen_shannon_f16order<QG>(q, c, dim, vec);
         case LB_CHEBYSHEV: return chebyshev_f16order<QG>(q, c, dim, vec);
         case LB_CANBERRA: return canberra_f16order<QG>(q, c, dim, vec);
         case LB_BRAY_CURTIS: return bray_curtis_f16order<QG>(q, c, dim, vec);
