@@ -46,6 +46,7 @@ struct ScanArgs {
     int f16_rows;               // 1: every pair goes through compute_distance_f16's scalar kernels (float16 collections)
     const float* row_stats;     // Jensen-Shannon cached: [n][2] (inv_mass, entropy) or null
     const float* query_stats;   // Jensen-Shannon cached: [nq][2]
+    const double* row_mass;     // Wasserstein streaming scan: [n] f64 row sums (NaN = invalid value in the row) or null
     uint64_t* lists;            // [P][nq][k] keys, unsorted
     uint32_t* counts;           // [P][nq]
     uint64_t* thr;              // [P][nq] current worst kept key (valid when count == k)

@@ -1,5 +1,6 @@
 // lb_scan2.cuh — streaming exact scan for the 8-lane f32 metrics (IP, L2, cosine, L1, Chebyshev, Canberra,
-// Bray-Curtis): every corpus row is read ONCE per query tile and scored against up to 8 queries at a time.
+// Bray-Curtis) and the sequential f64 ones (correlation, Hellinger, Wasserstein): every corpus row is read ONCE per
+// query tile and scored against up to 8 queries at a time.
 //
 // Replaces the same reference loops as lb_scan.cuh (fused_topk_ip_parallel / ip_scan_chunk_topk,
 // fused_topk_parallel, fused_topk_parallel_filtered, direct_access_topk — src/storage/flat_mmap.rs:4845-4982,
@@ -16,9 +17,57 @@ namespace lb {
 
 constexpr int S2_ROWS = 256;   // rows per block step == threads per CTA
 
+__host__ __device__ inline bool scan2_f64(int metric) {
+    return metric == LB_CORRELATION || metric == LB_HELLINGER || metric == LB_WASSERSTEIN;
+}
 __host__ __device__ inline bool scan2_supported(int metric) {
     return metric == LB_IP || metric == LB_L2 || metric == LB_COSINE || metric == LB_MANHATTAN || metric == LB_CHEBYSHEV ||
-           metric == LB_CANBERRA || metric == LB_BRAY_CURTIS;
+           metric == LB_CANBERRA || metric == LB_BRAY_CURTIS || scan2_f64(metric);  // Wasserstein: with ScanArgs::row_mass
+}
+
+// Per-pair constants of the sequential f64 metrics.  Their reference loops (simd.rs:632-714) interleave sums that
+// depend on one operand only with the cross terms; those are independent accumulator chains, so the query-side sums
+// are taken once per query (qa, qb) and Wasserstein's row mass once per row (ra), bit for bit the same values.
+struct PairConst {
+    double qa = 0, qb = 0;  // correlation: sum a, sum a^2; Hellinger / Wasserstein: sum a (NaN: invalid value in the query)
+    double ra = 0, rb = 0;  // Wasserstein: sum b (NaN: invalid value in the row) and its reciprocal; qb = 1 / qa there
+};
+template <int METRIC>
+__device__ inline void scan2_query_consts(const float* __restrict__ q /*smem*/, int dim, double* out /*[2]*/) {
+    double s = 0, ss = 0;
+    bool bad = false;
+    for (int i = 0; i < dim; ++i) {
+        const double av = (double)q[i];
+        s = s + av;
+        if (METRIC == LB_CORRELATION) ss = ss + av * av;
+        else bad = bad || invalid_mass_value(q[i]);
+    }
+    out[0] = bad ? __longlong_as_double(0x7ff8000000000000ll) : s;
+    out[1] = ss;
+}
+// Wasserstein row masses, once per row (the first loop of wasserstein_1d_f32, simd.rs:691-698)
+__global__ void row_mass_kernel(const float* __restrict__ rows, uint64_t n, int dim, double* __restrict__ mass) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const float* c = rows + row * dim;
+    const bool vec = (dim & 3) == 0;
+    double s = 0;
+    bool bad = false;
+    const int chunks = dim >> 3;
+    for (int j = 0; j < chunks; ++j) {
+        const Vec8 b = load8<true>(c + 8 * j, vec);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            bad = bad || invalid_mass_value(b.v[i]);
+            s = s + (double)b.v[i];
+        }
+    }
+    for (int i = chunks * 8; i < dim; ++i) {
+        const float b = __ldg(c + i);
+        bad = bad || invalid_mass_value(b);
+        s = s + (double)b;
+    }
+    mass[row] = bad ? __longlong_as_double(0x7ff8000000000000ll) : s;
 }
 
 // state layout per (row, query): s[0..7] first accumulator vector, s[8..15] second (metrics that have one)
@@ -26,12 +75,40 @@ __host__ __device__ inline bool scan2_supported(int metric) {
 // 4096 rows, or the stateless operator; without it IP needs one accumulator vector only.
 template <int METRIC, bool IP2>
 struct Scan2Op {
-    static constexpr int kState = ((METRIC == LB_IP && IP2) || METRIC == LB_L2 || METRIC == LB_COSINE || METRIC == LB_BRAY_CURTIS) ? 16 : 8;
-    static constexpr int kTQ = 64 / kState;  // queries per tile: 64 accumulator registers per thread either way
+    static constexpr bool kF64 = METRIC == LB_CORRELATION || METRIC == LB_HELLINGER || METRIC == LB_WASSERSTEIN;
+    using T = typename std::conditional<kF64, double, float>::type;
+    static constexpr int kState = kF64 ? (METRIC == LB_WASSERSTEIN ? 2 : 3)
+                                  : (((METRIC == LB_IP && IP2) || METRIC == LB_L2 || METRIC == LB_COSINE || METRIC == LB_BRAY_CURTIS) ? 16 : 8);
+    static constexpr int kTQ = kF64 ? 4 : 64 / kState;  // queries per tile: <= 64 accumulator registers per thread
 
-    // one 8-float chunk; `odd` = chunk index is odd; `two_acc` = IP rows that take the two-accumulator kernel
-    static __device__ __forceinline__ void step(float* s, const Vec8& q, const Vec8& c, bool odd, bool two_acc) {
-        if (METRIC == LB_IP) {
+    // one 8-float chunk, index j; `two_acc` = IP rows that take the two-accumulator kernel
+    static __device__ __forceinline__ void step(T* s, const Vec8& q, const Vec8& c, int j, bool two_acc, int dim, const PairConst& pc) {
+        const bool odd = (j & 1) != 0;
+        if constexpr (METRIC == LB_CORRELATION) {  // simd.rs:632-661: s = {sum b, sum b^2, sum ab}
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double av = (double)q.v[i], bv = (double)c.v[i];
+                s[0] = s[0] + bv;
+                s[1] = s[1] + bv * bv;
+                s[2] = s[2] + av * bv;
+            }
+        } else if constexpr (METRIC == LB_HELLINGER) {  // simd.rs:665-684: s = {sum b, sum sqrt(ab), invalid row value seen}
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (invalid_mass_value(c.v[i])) s[2] = 1.0;
+                s[0] = s[0] + (double)c.v[i];
+                s[1] = s[1] + sqrt((double)q.v[i] * (double)c.v[i]);
+            }
+        } else if constexpr (METRIC == LB_WASSERSTEIN) {  // simd.rs:688-714, second loop: s = {cdf delta, distance}
+            const double inv_a = pc.qb, inv_b = pc.rb;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (8 * j + i < dim - 1) {  // the last bin never contributes
+                    s[0] = s[0] + ((double)q.v[i] * inv_a - (double)c.v[i] * inv_b);
+                    s[1] = s[1] + fabs(s[0]);
+                }
+            }
+        } else if constexpr (METRIC == LB_IP) {
             // batch-8 order: one accumulator (simd.rs:1450-1525); single-row order: even chunks -> acc0, odd -> acc1
             // (simd.rs:1341-1396).  The trailing unpaired chunk has an even index, so it lands in acc0 as it must.
             if (IP2 && two_acc && odd) {
@@ -41,7 +118,7 @@ struct Scan2Op {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s[i] = fmaf(q.v[i], c.v[i], s[i]);
             }
-        } else if (METRIC == LB_L2) {  // simd.rs:1527-1581
+        } else if constexpr (METRIC == LB_L2) {  // simd.rs:1527-1581
             if (odd) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -55,19 +132,19 @@ struct Scan2Op {
                     s[i] = fmaf(d, d, s[i]);
                 }
             }
-        } else if (METRIC == LB_COSINE) {  // simd.rs:1583-1636 (the query norm is the same chain for every row: done once)
+        } else if constexpr (METRIC == LB_COSINE) {  // simd.rs:1583-1636 (the query norm is the same chain for every row: done once)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 s[i] = fmaf(q.v[i], c.v[i], s[i]);
                 s[8 + i] = fmaf(c.v[i], c.v[i], s[8 + i]);
             }
-        } else if (METRIC == LB_MANHATTAN) {  // simd.rs:2134-2158
+        } else if constexpr (METRIC == LB_MANHATTAN) {  // simd.rs:2134-2158
 #pragma unroll
             for (int i = 0; i < 8; ++i) s[i] = s[i] + fabsf(q.v[i] - c.v[i]);
-        } else if (METRIC == LB_CHEBYSHEV) {  // simd.rs:2715-2737
+        } else if constexpr (METRIC == LB_CHEBYSHEV) {  // simd.rs:2715-2737
 #pragma unroll
             for (int i = 0; i < 8; ++i) s[i] = max_ps(s[i], fabsf(q.v[i] - c.v[i]));
-        } else if (METRIC == LB_CANBERRA) {  // simd.rs:2762-2793
+        } else if constexpr (METRIC == LB_CANBERRA) {  // simd.rs:2762-2793
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float num = fabsf(q.v[i] - c.v[i]);
@@ -85,9 +162,50 @@ struct Scan2Op {
     }
 
     // horizontal reduction + scalar tail (elements [tail0, dim)) + final formula
-    static __device__ __forceinline__ float finish(float* s, const float* __restrict__ q /*smem*/, const float* __restrict__ c /*global*/,
-                                                   int tail0, int dim, bool two_acc, float q_norm2) {
-        if (METRIC == LB_IP) {
+    static __device__ __forceinline__ float finish(T* s, const float* __restrict__ q /*smem*/, const float* __restrict__ c /*global*/,
+                                                   int tail0, int dim, bool two_acc, float q_norm2, const PairConst& pc) {
+        if constexpr (METRIC == LB_CORRELATION) {
+            if (dim == 0) return 0.0f;
+            for (int i = tail0; i < dim; ++i) {
+                const double av = (double)q[i], bv = (double)__ldg(c + i);
+                s[0] = s[0] + bv;
+                s[1] = s[1] + bv * bv;
+                s[2] = s[2] + av * bv;
+            }
+            const double n = (double)dim, sa = pc.qa, saa = pc.qb, sb = s[0], sbb = s[1], sab = s[2];
+            const double var_a = fmax(saa - sa * sa / n, 0.0);
+            const double var_b = fmax(sbb - sb * sb / n, 0.0);
+            const double denom = sqrt(var_a * var_b);
+            if (denom <= 2.2204460492503131e-16) {
+                bool same = true;
+                for (int i = 0; i < dim; ++i) same = same && (q[i] == __ldg(c + i));
+                return same ? 0.0f : 1.0f;
+            }
+            const double cov = sab - sa * sb / n;
+            return (float)(1.0 - clamp_f64(cov / denom, -1.0, 1.0));
+        } else if constexpr (METRIC == LB_HELLINGER) {
+            for (int i = tail0; i < dim; ++i) {
+                const float b = __ldg(c + i);
+                if (invalid_mass_value(b)) s[2] = 1.0;
+                s[0] = s[0] + (double)b;
+                s[1] = s[1] + sqrt((double)q[i] * (double)b);
+            }
+            const double sa = pc.qa, sb = s[0];
+            if (s[2] != 0.0 || sa != sa) return INFINITY;
+            if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : 1.0f;
+            const double cc = s[1] / sqrt(sa * sb);
+            return (float)sqrt(1.0 - clamp_f64(cc, 0.0, 1.0));
+        } else if constexpr (METRIC == LB_WASSERSTEIN) {
+            const double sa = pc.qa, sb = pc.ra;
+            if (sa != sa || sb != sb) return INFINITY;
+            if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : INFINITY;
+            const double inv_a = pc.qb, inv_b = pc.rb;
+            for (int i = tail0; i < dim - 1; ++i) {
+                s[0] = s[0] + ((double)q[i] * inv_a - (double)__ldg(c + i) * inv_b);
+                s[1] = s[1] + fabs(s[0]);
+            }
+            return (float)s[1];
+        } else if constexpr (METRIC == LB_IP) {
             if (IP2 && two_acc) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s[i] = s[i] + s[8 + i];
@@ -95,7 +213,7 @@ struct Scan2Op {
             float out = hsum8(s);
             for (int i = tail0; i < dim; ++i) out = out + q[i] * __ldg(c + i);
             return out;
-        } else if (METRIC == LB_L2) {
+        } else if constexpr (METRIC == LB_L2) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) s[i] = s[i] + s[8 + i];
             float sum = hsum8(s);
@@ -104,7 +222,7 @@ struct Scan2Op {
                 sum = sum + diff * diff;
             }
             return sum;
-        } else if (METRIC == LB_COSINE) {
+        } else if constexpr (METRIC == LB_COSINE) {
             float dot = hsum8(s), nb = hsum8(s + 8), na = q_norm2;
             for (int i = tail0; i < dim; ++i) {
                 const float a = q[i], b = __ldg(c + i);
@@ -114,17 +232,17 @@ struct Scan2Op {
             const float denom = sqrtf(na * nb);
             if (denom < 1e-30f) return 1.0f;
             return 1.0f - dot / denom;
-        } else if (METRIC == LB_MANHATTAN) {
+        } else if constexpr (METRIC == LB_MANHATTAN) {
             float sum = lane_sum8(s);
             for (int i = tail0; i < dim; ++i) sum = sum + fabsf(q[i] - __ldg(c + i));
             return sum;
-        } else if (METRIC == LB_CHEBYSHEV) {
+        } else if constexpr (METRIC == LB_CHEBYSHEV) {
             float m = 0.0f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) m = rust_max(m, s[i]);
             for (int i = tail0; i < dim; ++i) m = rust_max(m, fabsf(q[i] - __ldg(c + i)));
             return m;
-        } else if (METRIC == LB_CANBERRA) {
+        } else if constexpr (METRIC == LB_CANBERRA) {
             float sum = lane_sum8(s);
             for (int i = tail0; i < dim; ++i) {
                 const float a = q[i], b = __ldg(c + i);
@@ -170,8 +288,9 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
     uint64_t* sthr = reinterpret_cast<uint64_t*>(sq + S2_TQ * dim_pad);                 // [TQ]
     uint32_t* scnt = reinterpret_cast<uint32_t*>(sthr + S2_TQ);                         // [TQ]
     float* sna = reinterpret_cast<float*>(scnt + S2_TQ);                                // [TQ] cosine |q|^2
+    double* sqc = reinterpret_cast<double*>(sna + S2_TQ);                               // [TQ][2] f64 metrics: query sums
     SmemLists sl;
-    sl.keys = reinterpret_cast<uint64_t*>(sna + S2_TQ);                                 // [TQ][k] when a.smem_lists
+    sl.keys = reinterpret_cast<uint64_t*>(sqc + 2 * S2_TQ);                             // [TQ][k] when a.smem_lists
     sl.counts = reinterpret_cast<uint32_t*>(sl.keys + (size_t)S2_TQ * a.k);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int part = blockIdx.x;
@@ -189,6 +308,7 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
         }
         __syncthreads();
         if (METRIC == LB_COSINE && tid < tq) sna[tid] = cosine_query_norm2(sq + tid * dim_pad, dim);
+        if (Op::kF64 && tid < tq) scan2_query_consts<METRIC>(sq + tid * dim_pad, dim, sqc + 2 * tid);
     };
     if (single_tile) {
         load_tile(0, a.nq);
@@ -221,11 +341,22 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
             }
             if (!single_tile) __syncthreads();
             if (valid) {
-                float st[S2_TQ][Op::kState];
+                typename Op::T st[S2_TQ][Op::kState];
+                PairConst pc[S2_TQ];
 #pragma unroll
-                for (int t = 0; t < S2_TQ; ++t)
+                for (int t = 0; t < S2_TQ; ++t) {
 #pragma unroll
-                    for (int i = 0; i < Op::kState; ++i) st[t][i] = 0.0f;
+                    for (int i = 0; i < Op::kState; ++i) st[t][i] = 0;
+                    if (Op::kF64 && t < tq) {
+                        pc[t].qa = sqc[2 * t];
+                        pc[t].qb = sqc[2 * t + 1];
+                        if (METRIC == LB_WASSERSTEIN) {
+                            pc[t].qb = 1.0 / pc[t].qa;
+                            pc[t].ra = __ldg(a.row_mass + row);
+                            pc[t].rb = 1.0 / pc[t].ra;
+                        }
+                    }
+                }
                 // chunk loop outermost: the row streams through registers once, one chunk ahead of the arithmetic
                 Vec8 cv = chunks > 0 ? load8<true>(c, vec) : Vec8{};
                 for (int j = 0; j < chunks; ++j) {
@@ -238,7 +369,7 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
                     for (int t = 0; t < S2_TQ; ++t) {
                         if (t < tq) {
                             const Vec8 qv = load8<false>(sq + t * dim_pad + 8 * j, vec);  // broadcast
-                            Op::step(st[t], qv, cv, (j & 1) != 0, two_acc);
+                            Op::step(st[t], qv, cv, j, two_acc, dim, pc[t]);
                         }
                     }
                     cv = nx;
@@ -246,7 +377,7 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
 #pragma unroll
                 for (int t = 0; t < S2_TQ; ++t) {
                     if (t < tq) {
-                        const float v = Op::finish(st[t], sq + t * dim_pad, c, chunks * 8, dim, two_acc, METRIC == LB_COSINE ? sna[t] : 0.0f);
+                        const float v = Op::finish(st[t], sq + t * dim_pad, c, chunks * 8, dim, two_acc, METRIC == LB_COSINE ? sna[t] : 0.0f, pc[t]);
                         const uint64_t key = make_key<ASC>(v, row);
                         if (key < sthr[t]) {
                             const uint32_t pos = atomicAdd(&scnt[t], 1u);
@@ -299,7 +430,8 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
     uint64_t* sthr = reinterpret_cast<uint64_t*>(sq + S2_TQ * dim_pad);                 // [TQ]
     uint32_t* scnt = reinterpret_cast<uint32_t*>(sthr + S2_TQ);                         // [TQ]
     float* sna = reinterpret_cast<float*>(scnt + S2_TQ);                                // [TQ]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sna + S2_TQ + 2);                      // full[NSTAGES]
+    double* sqc = reinterpret_cast<double*>(sna + S2_TQ + 2);                           // [TQ][2] f64 metrics: query sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sqc + 2 * S2_TQ);                      // full[NSTAGES]
     const uint32_t full0 = tc::smem_u32(bars);
     SmemLists sl;
     sl.keys = bars + S3_NSTAGES;                                                        // [TQ][k] when a.smem_lists
@@ -336,6 +468,7 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
         }
         __syncthreads();
         if (METRIC == LB_COSINE && tid < tq) sna[tid] = cosine_query_norm2(sq + tid * dim_pad, dim);
+        if (Op::kF64 && tid < tq) scan2_query_consts<METRIC>(sq + tid * dim_pad, dim, sqc + 2 * tid);
     };
     __syncthreads();
     if (tid == 0)
@@ -370,11 +503,22 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
                 }
                 __syncthreads();
             }
-            float st[S2_TQ][Op::kState];
+            typename Op::T st[S2_TQ][Op::kState];
+            PairConst pc[S2_TQ];
 #pragma unroll
-            for (int t = 0; t < S2_TQ; ++t)
+            for (int t = 0; t < S2_TQ; ++t) {
 #pragma unroll
-                for (int i = 0; i < Op::kState; ++i) st[t][i] = 0.0f;
+                for (int i = 0; i < Op::kState; ++i) st[t][i] = 0;
+                if (Op::kF64 && t < tq) {
+                    pc[t].qa = sqc[2 * t];
+                    pc[t].qb = sqc[2 * t + 1];
+                    if (METRIC == LB_WASSERSTEIN && valid) {
+                        pc[t].qb = 1.0 / pc[t].qa;
+                        pc[t].ra = __ldg(a.row_mass + row);
+                        pc[t].rb = 1.0 / pc[t].ra;
+                    }
+                }
+            }
             for (int cc = 0; cc < n_cc; ++cc, ++box) {
                 const uint32_t stage = (uint32_t)(box % S3_NSTAGES), phase = (uint32_t)((box / S3_NSTAGES) & 1u);
                 while (!tc::mbar_try_wait(full0 + 8u * stage, phase)) {
@@ -401,7 +545,7 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
                             for (int t = 0; t < S2_TQ; ++t) {
                                 if (t < tq) {
                                     const Vec8 qv = load8<false>(sq + t * dim_pad + 8 * j, true);  // broadcast
-                                    Op::step(st[t], qv, cv[sub], (j & 1) != 0, two_acc);
+                                    Op::step(st[t], qv, cv[sub], j, two_acc, dim, pc[t]);
                                 }
                             }
                         }
@@ -412,7 +556,7 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
 #pragma unroll
                 for (int t = 0; t < S2_TQ; ++t) {
                     if (t < tq) {
-                        const float v = Op::finish(st[t], sq + t * dim_pad, c, chunks * 8, dim, two_acc, METRIC == LB_COSINE ? sna[t] : 0.0f);
+                        const float v = Op::finish(st[t], sq + t * dim_pad, c, chunks * 8, dim, two_acc, METRIC == LB_COSINE ? sna[t] : 0.0f, pc[t]);
                         const uint64_t key = make_key<ASC>(v, row);
                         if (key < sthr[t]) {
                             const uint32_t pos = atomicAdd(&scnt[t], 1u);

@@ -129,6 +129,8 @@ struct lb_index {
     uint64_t packed_rows = 0;
     DevBuf js_stats;
     uint64_t js_rows = 0;
+    DevBuf mass_stats;       // Wasserstein: f64 row sums, rows [0, mass_rows)
+    uint64_t mass_rows = 0;
     Shadow shadow[3];
     DevBuf max_norm;  // 3 floats, one per shadow kind
     DevBuf small_seg;
@@ -229,6 +231,17 @@ static int ensure_js_stats(lb_index* idx) {
                                                                             (int)idx->dim, idx->js_stats.as<float>() + 2 * first);
     LB_CUDA_TRY(cudaGetLastError());
     idx->js_rows = idx->n;
+    return LB_OK;
+}
+
+static int ensure_mass_stats(lb_index* idx) {
+    if (idx->mass_rows == idx->n) return LB_OK;
+    LB_TRY(idx->mass_stats.ensure((size_t)idx->n * 8, true, idx->stream));
+    const uint64_t first = idx->mass_rows, cnt = idx->n - first;
+    row_mass_kernel<<<(unsigned)ceil_div(cnt, 128), 128, 0, idx->stream>>>(idx->rows.as<float>() + first * idx->dim, cnt, (int)idx->dim,
+                                                                           idx->mass_stats.as<double>() + first);
+    LB_CUDA_TRY(cudaGetLastError());
+    idx->mass_rows = idx->n;
     return LB_OK;
 }
 
@@ -343,6 +356,7 @@ struct ScanRequest {
     int f16_rows = 0;  // score with compute_distance_f16's scalar kernels (old exact kernel only)
     const float* row_stats = nullptr;
     const float* query_stats = nullptr;
+    const double* row_mass = nullptr;  // Wasserstein: f64 row sums (enables the streaming scan for it)
     int sqrt_scores = 0;
     const uint32_t* qmap = nullptr;
     uint32_t* out_rows = nullptr;
@@ -353,7 +367,10 @@ struct ScanRequest {
 // scan + merge on idx->stream (k <= n_rows, k <= 2048)
 static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
     // the TMA-staged f32 scan runs one CTA per SM (its ring takes the shared memory): one partition per SM
-    const bool tma_f32 = !r.words && !r.f16_rows && scan2_supported(r.metric) && r.row_stats == nullptr && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+    const bool s2_metric = scan2_supported(r.metric) && (r.metric != LB_WASSERSTEIN || r.row_mass != nullptr);
+    // (the f64 metrics are bound by arithmetic latency, not by the load pattern: two resident CTAs per SM beat the
+    // one-CTA TMA ring for them — Hellinger 2.1 against 1.3 TB/s, Wasserstein 3.4 against 2.4 at one query)
+    const bool tma_f32 = !r.words && !r.f16_rows && s2_metric && !scan2_f64(r.metric) && r.row_stats == nullptr && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
                          r.row_ids == nullptr && (r.dim & 3) == 0 && r.dim >= 8 && r.n_rows >= 4096 && r.nq <= 4 &&
                          tc_env_int("LYNSE_B200_SCAN_TMA", 1) != 0 &&
                          (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)S3_TQ * (S2_ROWS * 8 + ((r.dim + 3) & ~3) * 4 + 256 * 8) + 2048 <= 226 * 1024;
@@ -380,6 +397,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
     a.n_small = r.n_small;
     a.ip_single = r.ip_single;
     a.f16_rows = r.f16_rows;
+    a.row_mass = r.row_mass;
     a.row_stats = r.row_stats;
     a.query_stats = r.query_stats;
     a.lists = idx->w_lists.as<uint64_t>();
@@ -431,7 +449,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
             default: LB_LAUNCH_PACKED(0); break;
         }
 #undef LB_LAUNCH_PACKED
-    } else if (scan2_supported(r.metric) && r.row_stats == nullptr && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+    } else if (s2_metric && r.row_stats == nullptr && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
                (size_t)8 * ((r.dim + 3) & ~3) * 4 + 8 * S2_ROWS * 8 + 256 <= 200 * 1024) {
         // streaming scan: the row is read once per query tile (lb_scan2.cuh)
         const int dim_pad = (r.dim + 3) & ~3;
@@ -457,7 +475,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
         constexpr int tqv = Scan2Op<M, IP2V>::kTQ < S3_TQ ? Scan2Op<M, IP2V>::kTQ : S3_TQ;                                    \
         a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                                   \
         const size_t smem = (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 +      \
-                            (size_t)tqv * 16 + 128 + 1024 + (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);         \
+                            (size_t)tqv * 32 + 128 + 1024 + (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);         \
         LB_CUDA_TRY(cudaFuncSetAttribute(scan_stream_tma_kernel<M, IP2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         scan_stream_tma_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(tmap, a);                                       \
     } while (0)
@@ -468,6 +486,9 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
                 case LB_MANHATTAN: LB_LAUNCH_S3(LB_MANHATTAN, false); break;
                 case LB_CHEBYSHEV: LB_LAUNCH_S3(LB_CHEBYSHEV, false); break;
                 case LB_CANBERRA: LB_LAUNCH_S3(LB_CANBERRA, false); break;
+                case LB_CORRELATION: LB_LAUNCH_S3(LB_CORRELATION, false); break;
+                case LB_HELLINGER: LB_LAUNCH_S3(LB_HELLINGER, false); break;
+                case LB_WASSERSTEIN: LB_LAUNCH_S3(LB_WASSERSTEIN, false); break;
                 default: LB_LAUNCH_S3(LB_BRAY_CURTIS, false); break;
             }
 #undef LB_LAUNCH_S3
@@ -476,7 +497,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
     do {                                                                                                                  \
         constexpr int tqv = Scan2Op<M, IP2V>::kTQ;                                                                        \
         a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                               \
-        const size_t smem = (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 + (size_t)tqv * 16 + 64 +                \
+        const size_t smem = (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 + (size_t)tqv * 32 + 64 +                \
                             (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);                                     \
         LB_CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<M, IP2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         scan_stream_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(a);                                             \
@@ -488,6 +509,9 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
             case LB_MANHATTAN: LB_LAUNCH_S2(LB_MANHATTAN, false); break;
             case LB_CHEBYSHEV: LB_LAUNCH_S2(LB_CHEBYSHEV, false); break;
             case LB_CANBERRA: LB_LAUNCH_S2(LB_CANBERRA, false); break;
+            case LB_CORRELATION: LB_LAUNCH_S2(LB_CORRELATION, false); break;
+            case LB_HELLINGER: LB_LAUNCH_S2(LB_HELLINGER, false); break;
+            case LB_WASSERSTEIN: LB_LAUNCH_S2(LB_WASSERSTEIN, false); break;
             default: LB_LAUNCH_S2(LB_BRAY_CURTIS, false); break;
         }
         }
@@ -896,6 +920,10 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         r.out_rows = d_rows;
         r.out_dists = d_dists;
         r.out_counts = d_counts;
+        if (metric == LB_WASSERSTEIN && !r.f16_rows) {
+            LB_TRY(ensure_mass_stats(idx));
+            r.row_mass = idx->mass_stats.as<double>();
+        }
         std::vector<uint32_t> unhandled;
         if (metric == LB_JENSEN_SHANNON && !r.f16_rows) {
             // FlatMmap::search Jensen-Shannon branch (flat_mmap.rs:912-921, :926-1111)
@@ -1037,7 +1065,7 @@ void lb_index_destroy(lb_index* idx) {
     {
         DeviceGuard g(idx->device);
         cudaStreamSynchronize(idx->stream);
-        DevBuf* bufs[] = {&idx->rows, &idx->packed, &idx->js_stats, &idx->max_norm, &idx->small_seg, &idx->w_queries,
+        DevBuf* bufs[] = {&idx->rows, &idx->packed, &idx->js_stats, &idx->mass_stats, &idx->max_norm, &idx->small_seg, &idx->w_queries,
                           &idx->w_qwords, &idx->w_allow, &idx->w_lists, &idx->w_counts, &idx->w_thr, &idx->w_out_rows,
                           &idx->w_out_dists, &idx->w_out_counts, &idx->w_qb, &idx->w_qnorm, &idx->w_cand_score,
                           &idx->w_cand_row, &idx->w_cand_thr, &idx->w_flags, &idx->w_qstats, &idx->w_nq, &idx->w_sub_q,
