@@ -22,8 +22,8 @@ __host__ __device__ inline bool scan2_f64(int metric) {
 }
 __host__ __device__ inline bool scan2_supported(int metric) {
     return metric == LB_IP || metric == LB_L2 || metric == LB_COSINE || metric == LB_MANHATTAN || metric == LB_CHEBYSHEV ||
-           metric == LB_CANBERRA || metric == LB_BRAY_CURTIS || scan2_f64(metric);  // Wasserstein: with ScanArgs::row_mass
-}
+           metric == LB_CANBERRA || metric == LB_BRAY_CURTIS || scan2_f64(metric) || metric == LB_JENSEN_SHANNON;
+}   // Wasserstein needs ScanArgs::row_mass, Jensen-Shannon ScanArgs::row_stats (the cached form; queries mass-normalised)
 
 // Per-pair constants of the sequential f64 metrics.  Their reference loops (simd.rs:632-714) interleave sums that
 // depend on one operand only with the cross terms; those are independent accumulator chains, so the query-side sums
@@ -31,6 +31,7 @@ __host__ __device__ inline bool scan2_supported(int metric) {
 struct PairConst {
     double qa = 0, qb = 0;  // correlation: sum a, sum a^2; Hellinger / Wasserstein: sum a (NaN: invalid value in the query)
     double ra = 0, rb = 0;  // Wasserstein: sum b (NaN: invalid value in the row) and its reciprocal; qb = 1 / qa there
+    float q_inv = 0, q_ent = 0, r_inv = 0, r_ent = 0;  // Jensen-Shannon cached scan: (inverse mass, entropy) of query and row
 };
 template <int METRIC>
 __device__ inline void scan2_query_consts(const float* __restrict__ q /*smem*/, int dim, double* out /*[2]*/) {
@@ -107,6 +108,12 @@ struct Scan2Op {
                     s[0] = s[0] + ((double)q.v[i] * inv_a - (double)c.v[i] * inv_b);
                     s[1] = s[1] + fabs(s[0]);
                 }
+            }
+        } else if constexpr (METRIC == LB_JENSEN_SHANNON) {  // mixture term of the cached form, simd.rs:2316-2354
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float sum = q.v[i] + c.v[i] * pc.r_inv;
+                s[i] = fmaf(sum, fast_ln<true>(max_ps(sum, kMinPositive)), s[i]);
             }
         } else if constexpr (METRIC == LB_IP) {
             // batch-8 order: one accumulator (simd.rs:1450-1525); single-row order: even chunks -> acc0, odd -> acc1
@@ -205,6 +212,28 @@ struct Scan2Op {
                 s[1] = s[1] + fabs(s[0]);
             }
             return (float)s[1];
+        } else if constexpr (METRIC == LB_JENSEN_SHANNON) {
+            // the ranking value of jensen_shannon_cached_parallel (flat_mmap.rs:985-1111): squared distance
+            const bool vec = (dim & 3) == 0;
+            if (pc.q_inv == 0.0f) {  // zero-mass query (flat_mmap.rs:938-972)
+                if (pc.r_inv != pc.r_inv || !isfinite(pc.r_ent)) return INFINITY;
+                return pc.r_inv == 0.0f ? 0.0f : kLn2;
+            }
+            if (pc.r_inv <= 0.0f || !isfinite(pc.r_inv) || !isfinite(pc.r_ent)) {
+                const float d = jensen_shannon_precomputed<false>(q, c, dim, vec, pc.q_ent, pc.r_inv, pc.r_ent);
+                return d * d;
+            }
+            float mix = lane_sum8(s);
+            for (int i = tail0; i < dim; ++i) {
+                const float sm = q[i] + __ldg(c + i) * pc.r_inv;
+                if (sm > 0.0f) mix = mix + sm * logf(sm);
+            }
+            const float divergence = fmaxf(kLn2 + 0.5f * (pc.q_ent + pc.r_ent - mix), 0.0f);
+            if (divergence <= kJsStableDivergence) {
+                const float d = jensen_shannon_normalized_query<false>(q, c, dim, vec, pc.r_inv);
+                return d * d;
+            }
+            return divergence;
         } else if constexpr (METRIC == LB_IP) {
             if (IP2 && two_acc) {
 #pragma unroll
@@ -355,6 +384,12 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
                             pc[t].ra = __ldg(a.row_mass + row);
                             pc[t].rb = 1.0 / pc[t].ra;
                         }
+                    }
+                    if (METRIC == LB_JENSEN_SHANNON && t < tq) {
+                        pc[t].q_inv = __ldg(a.query_stats + 2 * (q0 + t));
+                        pc[t].q_ent = __ldg(a.query_stats + 2 * (q0 + t) + 1);
+                        pc[t].r_inv = __ldg(a.row_stats + 2 * (size_t)row);
+                        pc[t].r_ent = __ldg(a.row_stats + 2 * (size_t)row + 1);
                     }
                 }
                 // chunk loop outermost: the row streams through registers once, one chunk ahead of the arithmetic

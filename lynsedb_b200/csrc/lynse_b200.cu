@@ -367,10 +367,11 @@ struct ScanRequest {
 // scan + merge on idx->stream (k <= n_rows, k <= 2048)
 static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
     // the TMA-staged f32 scan runs one CTA per SM (its ring takes the shared memory): one partition per SM
-    const bool s2_metric = scan2_supported(r.metric) && (r.metric != LB_WASSERSTEIN || r.row_mass != nullptr);
+    const bool s2_metric = scan2_supported(r.metric) && (r.metric != LB_WASSERSTEIN || r.row_mass != nullptr) &&
+                           (r.row_stats != nullptr) == (r.metric == LB_JENSEN_SHANNON);  // Jensen-Shannon: the cached form only
     // (the f64 metrics are bound by arithmetic latency, not by the load pattern: two resident CTAs per SM beat the
     // one-CTA TMA ring for them — Hellinger 2.1 against 1.3 TB/s, Wasserstein 3.4 against 2.4 at one query)
-    const bool tma_f32 = !r.words && !r.f16_rows && s2_metric && !scan2_f64(r.metric) && r.row_stats == nullptr && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+    const bool tma_f32 = !r.words && !r.f16_rows && s2_metric && !scan2_f64(r.metric) && r.metric != LB_JENSEN_SHANNON && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
                          r.row_ids == nullptr && (r.dim & 3) == 0 && r.dim >= 8 && r.n_rows >= 4096 && r.nq <= 4 &&
                          tc_env_int("LYNSE_B200_SCAN_TMA", 1) != 0 &&
                          (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)S3_TQ * (S2_ROWS * 8 + ((r.dim + 3) & ~3) * 4 + 256 * 8) + 2048 <= 226 * 1024;
@@ -449,7 +450,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
             default: LB_LAUNCH_PACKED(0); break;
         }
 #undef LB_LAUNCH_PACKED
-    } else if (s2_metric && r.row_stats == nullptr && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+    } else if (s2_metric && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
                (size_t)8 * ((r.dim + 3) & ~3) * 4 + 8 * S2_ROWS * 8 + 256 <= 200 * 1024) {
         // streaming scan: the row is read once per query tile (lb_scan2.cuh)
         const int dim_pad = (r.dim + 3) & ~3;
@@ -486,9 +487,6 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
                 case LB_MANHATTAN: LB_LAUNCH_S3(LB_MANHATTAN, false); break;
                 case LB_CHEBYSHEV: LB_LAUNCH_S3(LB_CHEBYSHEV, false); break;
                 case LB_CANBERRA: LB_LAUNCH_S3(LB_CANBERRA, false); break;
-                case LB_CORRELATION: LB_LAUNCH_S3(LB_CORRELATION, false); break;
-                case LB_HELLINGER: LB_LAUNCH_S3(LB_HELLINGER, false); break;
-                case LB_WASSERSTEIN: LB_LAUNCH_S3(LB_WASSERSTEIN, false); break;
                 default: LB_LAUNCH_S3(LB_BRAY_CURTIS, false); break;
             }
 #undef LB_LAUNCH_S3
@@ -512,6 +510,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
             case LB_CORRELATION: LB_LAUNCH_S2(LB_CORRELATION, false); break;
             case LB_HELLINGER: LB_LAUNCH_S2(LB_HELLINGER, false); break;
             case LB_WASSERSTEIN: LB_LAUNCH_S2(LB_WASSERSTEIN, false); break;
+            case LB_JENSEN_SHANNON: LB_LAUNCH_S2(LB_JENSEN_SHANNON, false); break;
             default: LB_LAUNCH_S2(LB_BRAY_CURTIS, false); break;
         }
         }
