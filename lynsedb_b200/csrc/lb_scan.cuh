@@ -366,6 +366,73 @@ __global__ void __launch_bounds__(1024) merge_lists_kernel(MergeArgs a) {
     if (threadIdx.x == 0) a.out_counts[slot] = n_valid;
 }
 
+// The same merge for small k (k <= 32, P*k <= 4096 keys): no sort.  Every thread holds up to four keys; each warp
+// pulls its k smallest out in order (k warp-wide minimum reductions), then warp 0 merges the 32 sorted runs the same
+// way.  A single-query search over a small corpus spends most of its device time in the merge: this one is a few
+// microseconds where the 2048-wide bitonic sort takes 66 block-wide barriers.
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((uint64_t)mhi << 32) | mlo;
+}
+
+constexpr int MERGE_SMALL_MAX_K = 32;
+constexpr int MERGE_SMALL_MAX_KEYS = 4096;
+
+__global__ void __launch_bounds__(1024) merge_lists_small_kernel(MergeArgs a) {
+    __shared__ uint64_t runs[32][MERGE_SMALL_MAX_K];
+    const int q = blockIdx.x, k = a.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = a.P * k;
+    uint64_t mine[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int slot = tid + j * 1024;
+        uint64_t key = KEY_NONE;
+        if (slot < total) {
+            const int p = slot / k, jj = slot - p * k;
+            const size_t lq = (size_t)p * a.nq + q;
+            if ((uint32_t)jj < a.counts[lq]) key = a.lists[lq * k + jj];
+        }
+        mine[j] = key;
+    }
+    for (int r = 0; r < k; ++r) {
+        uint64_t m = mine[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) m = mine[j] < m ? mine[j] : m;
+        const uint64_t w = warp_min_u64(m);
+        if (w != KEY_NONE) {  // keys are unique: exactly one holder
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (mine[j] == w) mine[j] = KEY_NONE;
+        }
+        if (lane == 0) runs[warp][r] = w;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const int slot = a.qmap ? (int)a.qmap[q] : q;
+    int head = 0;
+    uint32_t n_valid = 0;
+    for (int r = 0; r < k; ++r) {
+        const uint64_t front = head < k ? runs[lane][head] : KEY_NONE;
+        const uint64_t w = warp_min_u64(front);
+        if (w != KEY_NONE && front == w) ++head;
+        if (lane == 0) {
+            uint32_t row = ROW_NONE;
+            float score = __int_as_float(0x7fc00000);
+            if (w != KEY_NONE) {
+                row = key_row(w);
+                score = a.asc ? key_score<true>(w) : key_score<false>(w);
+                if (a.sqrt_scores) score = sqrtf(score);
+                ++n_valid;
+            }
+            a.out_rows[(size_t)slot * k + r] = row;
+            a.out_dists[(size_t)slot * k + r] = score;
+        }
+    }
+    if (lane == 0) a.out_counts[slot] = n_valid;
+}
+
 // ---- side-structure builders ---------------------------------------------------------------------------------
 // pack_binary_f32 (simd.rs:750-757, flat_mmap.rs:1283-1290): bit = x > 0.5, word i/64 bit i%64.  One warp per row.
 __global__ void pack_binary_kernel(const float* __restrict__ rows, uint64_t n, int dim, int n_words, float threshold,

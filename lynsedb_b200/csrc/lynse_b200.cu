@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -71,6 +72,31 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// pinned host staging memory (small batches copy through it: a copy from pageable memory is staged and
+// synchronised by the driver, ~10 us a call)
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return LB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t ncap = std::max<size_t>(bytes, 64 * 1024);
+        if (cudaHostAlloc(&p, ncap, cudaHostAllocDefault) != cudaSuccess) {
+            p = nullptr;
+            return fail(LB_CUDA, "cudaHostAlloc of the staging buffer failed");
+        }
+        cap = ncap;
+        return LB_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct Shadow {
     DevBuf buf;           // tiled, pre-swizzled bf16 rows (layout: lb_tc.cuh)
     uint64_t rows = 0;    // rows converted so far
@@ -91,6 +117,23 @@ static int next_pow2(int x) {
 static int tc_env_int(const char* name, int dflt) {
     const char* env = getenv(name);
     return env && *env ? atoi(env) : dflt;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs a few microseconds per call: remember, per kernel and device,
+// the largest size already granted and only raise it.
+template <class K>
+static cudaError_t ensure_dynamic_smem(K kernel, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> granted;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    int& have = granted[{reinterpret_cast<const void*>(kernel), dev}];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -138,6 +181,8 @@ struct lb_index {
     size_t small_seg_sig = ~(size_t)0;
     // workspace
     DevBuf w_queries, w_qwords, w_allow, w_lists, w_counts, w_thr, w_out_rows, w_out_dists, w_out_counts;
+    DevBuf w_out;            // host-buffer searches: [rows | dists | counts] of one batch, so that one copy brings them back
+    HostBuf h_in, h_out;     // pinned staging for small batches
     DevBuf w_qb, w_qnorm, w_cand_score, w_cand_row, w_cand_thr, w_flags, w_qstats, w_nq, w_sub_q, w_qmap;
     int plan = LB_PLAN_AUTO;
     // how the running search scores a pair (set under `mu` for the duration of one host-buffer search):
@@ -425,8 +470,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
     do {                                                                                                                     \
         a.smem_lists = (r.nq <= PK_TQ && r.k <= 256) ? 1 : 0;                                                                \
         const size_t pk_smem = PK_SMEM_BYTES + (a.smem_lists ? (size_t)PK_TQ * r.k * 8 + PK_TQ * 4 + 16 : 0);                \
-        LB_CUDA_TRY(cudaFuncSetAttribute(scan_packed16_kernel<MODE, HSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                         (int)pk_smem));                                                                     \
+        LB_CUDA_TRY(ensure_dynamic_smem(scan_packed16_kernel<MODE, HSV>, (int)pk_smem));                                             \
         scan_packed16_kernel<MODE, HSV><<<sp.P, PK_ROWS, pk_smem, idx->stream>>>(tmap, a);                                   \
     } while (0)
         if (mode == 0) { if (hs) LB_LAUNCH_PK(0, true); else LB_LAUNCH_PK(0, false); }
@@ -437,7 +481,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
         size_t smem = (size_t)SCAN_TQ * SCAN_THREADS * 8 + (size_t)SCAN_TQ * r.n_words * 8;
 #define LB_LAUNCH_PACKED(W)                                                                                      \
     do {                                                                                                         \
-        LB_CUDA_TRY(cudaFuncSetAttribute(scan_packed_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LB_CUDA_TRY(ensure_dynamic_smem(scan_packed_kernel<W>, (int)smem)); \
         scan_packed_kernel<W><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);                                     \
     } while (0)
         if (smem > 200 * 1024) return fail(LB_UNSUPPORTED, "packed rows wider than 1280 words are not supported");
@@ -477,7 +521,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
         a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                                   \
         const size_t smem = (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 +      \
                             (size_t)tqv * 32 + 128 + 1024 + (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);         \
-        LB_CUDA_TRY(cudaFuncSetAttribute(scan_stream_tma_kernel<M, IP2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LB_CUDA_TRY(ensure_dynamic_smem(scan_stream_tma_kernel<M, IP2V>, (int)smem)); \
         scan_stream_tma_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(tmap, a);                                       \
     } while (0)
             switch (r.metric) {
@@ -497,7 +541,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
         a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                               \
         const size_t smem = (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 + (size_t)tqv * 32 + 64 +                \
                             (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);                                     \
-        LB_CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<M, IP2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LB_CUDA_TRY(ensure_dynamic_smem(scan_stream_kernel<M, IP2V>, (int)smem)); \
         scan_stream_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(a);                                             \
     } while (0)
         switch (r.metric) {
@@ -520,10 +564,10 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
         size_t smem = (size_t)SCAN_TQ * SCAN_THREADS * 8 + (size_t)SCAN_TQ * dim_pad * 4;
         if (smem > 200 * 1024) return fail(LB_UNSUPPORTED, "dimension above 2560 is not supported by the exact scan");
         if (metric_ascending(r.metric)) {
-            LB_CUDA_TRY(cudaFuncSetAttribute(scan_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LB_CUDA_TRY(ensure_dynamic_smem(scan_exact_kernel<true>, (int)smem));
             scan_exact_kernel<true><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);
         } else {
-            LB_CUDA_TRY(cudaFuncSetAttribute(scan_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LB_CUDA_TRY(ensure_dynamic_smem(scan_exact_kernel<false>, (int)smem));
             scan_exact_kernel<false><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);
         }
     }
@@ -545,7 +589,10 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
     m.out_dists = r.out_dists;
     m.out_counts = r.out_counts;
     // few queries: few blocks, so each gets 1024 threads (the block-wide bitonic sort is the latency of a single-query call)
-    merge_lists_kernel<<<r.nq, r.nq <= 64 ? 1024 : 256, (size_t)m.M * 8, idx->stream>>>(m);
+    if (r.k <= MERGE_SMALL_MAX_K && total <= MERGE_SMALL_MAX_KEYS)
+        merge_lists_small_kernel<<<r.nq, 1024, 0, idx->stream>>>(m);
+    else
+        merge_lists_kernel<<<r.nq, r.nq <= 64 ? 1024 : 256, (size_t)m.M * 8, idx->stream>>>(m);
     LB_CUDA_TRY(cudaGetLastError());
     if (kernels) *kernels += 2;
     idx->stats.n_partitions = sp.P;
@@ -687,13 +734,13 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     cfg.numAttrs = 1;
     auto launch_coarse = [&](const tc::TcArgs& args) -> int {
         if (pair && BN == 128) {
-            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128>, (int)tc::SMEM_BYTES));
             LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128>, sh.tmap_full[0], sh.tmap_rem[0], args));
         } else if (pair) {
-            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<64>, (int)tc::SMEM_BYTES));
             LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<64>, sh.tmap_full[1], sh.tmap_rem[1], args));
         } else {
-            LB_CUDA_TRY(cudaFuncSetAttribute(tc::coarse_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_single_kernel, (int)tc::SMEM_BYTES));
             LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel, sh.tmap_full[0], sh.tmap_rem[0], args));
         }
         return LB_OK;
@@ -716,7 +763,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
         // aim at ~10 k rows of the whole corpus above the seeded floor
         int r = (int)ceil_div((uint64_t)10 * k * S, tiles_total);
         r = std::max(4, std::min(r, sa.P * tc::KP / 2));
-        LB_CUDA_TRY(cudaFuncSetAttribute(tc::seed_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm * 8));
+        LB_CUDA_TRY(ensure_dynamic_smem(tc::seed_floor_kernel, sm * 8));
         tc::seed_floor_kernel<<<nq, 256, (size_t)sm * 8, idx->stream>>>(sa.cand_score, sa.cand_row, sa.P, sm, r, a.gthr);
         LB_CUDA_TRY(cudaGetLastError());
         if (a.progress) LB_CUDA_TRY(cudaMemsetAsync(idx->w_progress.p, 0, (size_t)n_slots * tc::PROGRESS_STRIDE * 4, idx->stream));
@@ -752,10 +799,10 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     const int fin_threads = nq <= 64 ? 1024 : 256;  // few queries: few blocks, so each gets 1024 threads
     size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)(fin_threads / 8) * tc::FIN_COLS * 4;  // + row buffers
     if (metric_ascending(metric)) {
-        LB_CUDA_TRY(cudaFuncSetAttribute(tc::finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        LB_CUDA_TRY(ensure_dynamic_smem(tc::finalize_kernel<true>, (int)fsmem));
         tc::finalize_kernel<true><<<nq, fin_threads, fsmem, idx->stream>>>(f);
     } else {
-        LB_CUDA_TRY(cudaFuncSetAttribute(tc::finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        LB_CUDA_TRY(ensure_dynamic_smem(tc::finalize_kernel<false>, (int)fsmem));
         tc::finalize_kernel<false><<<nq, fin_threads, fsmem, idx->stream>>>(f);
     }
     LB_CUDA_TRY(cudaGetLastError());
@@ -855,7 +902,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
 enum { SCORE_FLAT = 0, SCORE_PAIRWISE = 1, SCORE_F16_ROWS = 2 };
 
 static int search_device_impl(lb_index* idx, int metric, const void* d_queries, int nq, int k, const uint64_t* d_allow,
-                              uint32_t* d_rows, float* d_dists, uint32_t* d_counts) {
+                              uint32_t* d_rows, float* d_dists, uint32_t* d_counts, bool sync_at_end = true) {
     idx->stats = lb_search_stats{};
     if (idx->timing) cudaEventRecord(idx->ev[2], idx->stream);
     int kernels = 0;
@@ -897,7 +944,10 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
         idx->stats.plan_used = 2;
         idx->stats.algorithmic_bytes = (uint64_t)idx->n * nw * 8;
-    } else if (idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT && d_allow == nullptr && tc_supported(idx, metric) && k <= 256 && idx->n >= 64) {
+    } else if (idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT && d_allow == nullptr && tc_supported(idx, metric) && k <= 256 && idx->n >= 64 &&
+               // a handful of queries over a small corpus is a latency case: the exact scan is two launches, the tensor
+               // plan three plus a lazily built shadow (100k x 128, one query: 85 against 131 us of device time)
+               !(nq <= 4 && (uint64_t)idx->n * idx->dim * 4 < (256ull << 20))) {
         LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr));
         kernels = idx->stats.kernels_launched;
         ms_dom = idx->stats.ms_dominant;
@@ -975,7 +1025,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         idx->stats.algorithmic_bytes = (uint64_t)idx->n * idx->dim * 4;
     }
     if (idx->timing) cudaEventRecord(idx->ev[3], idx->stream);
-    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    if (sync_at_end || idx->timing) LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));  // (the host path syncs after its copies)
     idx->stats.kernels_launched = kernels;
     idx->stats.ms_dominant = ms_dom;
     if (idx->timing) {
@@ -1066,11 +1116,13 @@ void lb_index_destroy(lb_index* idx) {
         cudaStreamSynchronize(idx->stream);
         DevBuf* bufs[] = {&idx->rows, &idx->packed, &idx->js_stats, &idx->mass_stats, &idx->max_norm, &idx->small_seg, &idx->w_queries,
                           &idx->w_qwords, &idx->w_allow, &idx->w_lists, &idx->w_counts, &idx->w_thr, &idx->w_out_rows,
-                          &idx->w_out_dists, &idx->w_out_counts, &idx->w_qb, &idx->w_qnorm, &idx->w_cand_score,
+                          &idx->w_out_dists, &idx->w_out_counts, &idx->w_out, &idx->w_qb, &idx->w_qnorm, &idx->w_cand_score,
                           &idx->w_cand_row, &idx->w_cand_thr, &idx->w_flags, &idx->w_qstats, &idx->w_nq, &idx->w_sub_q,
                           &idx->w_qmap, &idx->shadow[0].buf, &idx->shadow[1].buf, &idx->shadow[2].buf,
                           &idx->w_send, &idx->w_recv, &idx->w_g_rows, &idx->w_g_dists, &idx->w_g_counts, &idx->w_progress, &idx->w_prof, &idx->w_gfloor};
         for (DevBuf* b : bufs) b->release();
+        idx->h_in.release();
+        idx->h_out.release();
         for (int i = 0; i < 4; ++i)
             if (idx->ev[i]) cudaEventDestroy(idx->ev[i]);
         for (int i = 0; i < 8; ++i)
@@ -1241,22 +1293,42 @@ static int search_host_common(lb_index* idx, int score_mode, int metric, const v
         d_allow = idx->w_allow.as<uint64_t>();
     }
     lb_search_stats acc{};
+    constexpr size_t STAGE_LIMIT = 256 * 1024;  // batches up to this many bytes go through pinned staging
     for (uint32_t q0 = 0; q0 < nq; q0 += QUERY_BATCH) {
         const int nb = (int)std::min<uint32_t>(QUERY_BATCH, nq - q0);
-        LB_TRY(idx->w_queries.ensure((size_t)nb * query_row_bytes));
-        LB_TRY(idx->w_out_rows.ensure((size_t)nb * kk * 4));
-        LB_TRY(idx->w_out_dists.ensure((size_t)nb * kk * 4));
-        LB_TRY(idx->w_out_counts.ensure((size_t)nb * 4));
-        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_queries.p, reinterpret_cast<const char*>(queries) + (size_t)q0 * query_row_bytes,
-                                    (size_t)nb * query_row_bytes, cudaMemcpyHostToDevice, idx->stream));
-        LB_TRY(search_device_impl(idx, metric, idx->w_queries.p, nb, (int)kk, d_allow, idx->w_out_rows.as<uint32_t>(),
-                                  idx->w_out_dists.as<float>(), idx->w_out_counts.as<uint32_t>()));
-        LB_CUDA_TRY(cudaMemcpy2DAsync(out_rows + (size_t)q0 * k, (size_t)k * 4, idx->w_out_rows.p, (size_t)kk * 4, (size_t)kk * 4,
-                                      nb, cudaMemcpyDeviceToHost, idx->stream));
-        LB_CUDA_TRY(cudaMemcpy2DAsync(out_dists + (size_t)q0 * k, (size_t)k * 4, idx->w_out_dists.p, (size_t)kk * 4,
-                                      (size_t)kk * 4, nb, cudaMemcpyDeviceToHost, idx->stream));
-        LB_CUDA_TRY(cudaMemcpyAsync(out_counts + q0, idx->w_out_counts.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, idx->stream));
-        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        const size_t in_bytes = (size_t)nb * query_row_bytes;
+        const size_t rows_bytes = (size_t)nb * kk * 4, out_bytes = 2 * rows_bytes + (size_t)nb * 4;
+        LB_TRY(idx->w_queries.ensure(in_bytes));
+        LB_TRY(idx->w_out.ensure(out_bytes));
+        uint32_t* d_rows = idx->w_out.as<uint32_t>();
+        float* d_dists = reinterpret_cast<float*>(idx->w_out.as<char>() + rows_bytes);
+        uint32_t* d_counts = reinterpret_cast<uint32_t*>(idx->w_out.as<char>() + 2 * rows_bytes);
+        const char* src = reinterpret_cast<const char*>(queries) + (size_t)q0 * query_row_bytes;
+        if (in_bytes <= STAGE_LIMIT) {
+            LB_TRY(idx->h_in.ensure(in_bytes));
+            memcpy(idx->h_in.p, src, in_bytes);
+            src = reinterpret_cast<const char*>(idx->h_in.p);
+        }
+        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_queries.p, src, in_bytes, cudaMemcpyHostToDevice, idx->stream));
+        LB_TRY(search_device_impl(idx, metric, idx->w_queries.p, nb, (int)kk, d_allow, d_rows, d_dists, d_counts, false));
+        if (out_bytes <= STAGE_LIMIT) {
+            LB_TRY(idx->h_out.ensure(out_bytes));
+            LB_CUDA_TRY(cudaMemcpyAsync(idx->h_out.p, idx->w_out.p, out_bytes, cudaMemcpyDeviceToHost, idx->stream));
+            LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+            const char* h = reinterpret_cast<const char*>(idx->h_out.p);
+            for (int q = 0; q < nb; ++q) {
+                memcpy(out_rows + (size_t)(q0 + q) * k, h + (size_t)q * kk * 4, (size_t)kk * 4);
+                memcpy(out_dists + (size_t)(q0 + q) * k, h + rows_bytes + (size_t)q * kk * 4, (size_t)kk * 4);
+            }
+            memcpy(out_counts + q0, h + 2 * rows_bytes, (size_t)nb * 4);
+        } else {
+            LB_CUDA_TRY(cudaMemcpy2DAsync(out_rows + (size_t)q0 * k, (size_t)k * 4, d_rows, (size_t)kk * 4, (size_t)kk * 4, nb,
+                                          cudaMemcpyDeviceToHost, idx->stream));
+            LB_CUDA_TRY(cudaMemcpy2DAsync(out_dists + (size_t)q0 * k, (size_t)k * 4, d_dists, (size_t)kk * 4, (size_t)kk * 4, nb,
+                                          cudaMemcpyDeviceToHost, idx->stream));
+            LB_CUDA_TRY(cudaMemcpyAsync(out_counts + q0, d_counts, (size_t)nb * 4, cudaMemcpyDeviceToHost, idx->stream));
+            LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        }
         acc.plan_used = idx->stats.plan_used;
         acc.n_fallback += idx->stats.n_fallback;
         acc.n_partitions = idx->stats.n_partitions;

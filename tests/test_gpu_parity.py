@@ -254,7 +254,7 @@ def test_tc_raw_scores_pin_operand_layout(L):
     ("ip", 50001, 128, 64, 10),
     ("l2", 30000, 128, 40, 100),
     ("cosine", 30000, 96, 40, 10),
-    ("l2", 12345, 765, 3, 5),
+    ("l2", 12345, 765, 5, 5),
 ])
 def test_tc_plan_matches_oracle(L, oracle, metric, n, dim, nq, k):
     corpus, queries = _data(n, dim, 81), _data(nq, dim, 82)
@@ -304,7 +304,7 @@ def test_tc_uncertified_queries_fall_back_to_the_exact_scan(L, oracle):
 
 # one query tile -> one-CTA kernel, more -> CTA-pair kernel; dims chosen so a tile is 1..12 K blocks, with and
 # without a partial last pipeline stage; row counts that leave a ragged last 64-row tile
-@pytest.mark.parametrize("nq", [1, 128, 129, 300, 1000])
+@pytest.mark.parametrize("nq", [5, 128, 129, 300, 1000])
 @pytest.mark.parametrize("n,dim", [(33333, 320), (4100, 64), (20011, 200), (9000, 768), (70001, 130)])
 def test_tc_kernels_agree_with_oracle(L, oracle, n, dim, nq):
     k = 10
@@ -529,3 +529,14 @@ def test_k_limits_and_ragged_dimensions(L, oracle):
             idx.append(c)
             for metric in ("ip", "cosine", "l1"):
                 _check(oracle.store_batch_search(c, q, 5, metric), idx.search(q, 5, metric), metric, 5)
+
+
+def test_few_queries_on_a_small_corpus_take_the_exact_scan(L, oracle):
+    # plan selection only: up to 4 queries over < 256 MiB of rows is a latency case (two launches instead of three)
+    corpus, queries = _data(30000, 64, 301), _data(5, 64, 302)
+    with L.DeviceIndex(64) as idx:
+        idx.append(corpus)
+        for nq, plan in ((1, 0), (4, 0), (5, 1)):
+            got = idx.search(queries[:nq], 10, "ip")
+            assert idx.last_stats()["plan_used"] == plan
+            _check(oracle.store_batch_search(corpus, queries[:nq], 10, "ip"), got, "ip", 10)

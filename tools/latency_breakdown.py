@@ -18,11 +18,12 @@ with L.DeviceIndex(dim) as idx:
         for metric in ("ip", "l1"):
             for q in qs[:20]:
                 idx.search(q, k, metric)
-            wall, dev = [], []
+            wall, dev, scan = [], [], []
             for q in qs[20:]:
                 t0 = time.perf_counter()
                 idx.search(q, k, metric)
                 wall.append((time.perf_counter() - t0) * 1e6)
                 dev.append(idx.last_stats()["ms_total"] * 1e3)
+                scan.append(idx.last_stats()["ms_dominant"] * 1e3)
             st = idx.last_stats()
-            print(f"plan {plan:5s} metric {metric}: wall median {np.median(wall):.1f} us, device {np.median(dev):.1f} us, kernels {st['kernels_launched']}, plan_used {st['plan_used']}")
+            print(f"plan {plan:5s} metric {metric}: wall median {np.median(wall):.1f} us, device {np.median(dev):.1f} us (dominant kernel {np.median(scan):.1f} us), kernels {st['kernels_launched']}, plan_used {st['plan_used']}")
