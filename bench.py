@@ -55,7 +55,9 @@ def parse_args():
     p.add_argument("--rows", type=int, default=None, help="override corpus rows (development only)")
     p.add_argument("--nq", type=int, default=None)
     p.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
-    p.add_argument("--cpu-sample-queries", type=int, default=96)
+    p.add_argument("--cpu-sample-queries", type=int, default=96, help="queries per step of the --impl reference arm")
+    p.add_argument("--cpu-baseline-queries", type=int, default=256,
+                   help="queries of the cpu_baseline leg of the own arm (about 10 s of CPU work on 16 threads at C2)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--plan", default="auto", choices=["auto", "exact"])
     return p.parse_args()
@@ -480,10 +482,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             sample_rows = min(args.cpu_sample_rows, n_local)
             if packed:
-                cpu_baseline = cpu_reference_packed_qps(metric, rows, dim, k, sample_rows, args.cpu_sample_queries, queries)
+                cpu_baseline = cpu_reference_packed_qps(metric, rows, dim, k, sample_rows, args.cpu_baseline_queries, queries)
             else:
                 corpus_sample = idx.read_rows(0, sample_rows)
-                cpu_baseline = cpu_reference_qps(metric, rows, dim, k, sample_rows, args.cpu_sample_queries, corpus_sample, queries)
+                cpu_baseline = cpu_reference_qps(metric, rows, dim, k, sample_rows, args.cpu_baseline_queries, corpus_sample, queries)
         line = {
             "metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
