@@ -22,14 +22,20 @@ namespace tc {
 // CTA stages a whole 64-row shadow tile per K block (even CTA: tile 2t, odd CTA: tile 2t+1; 32 KiB stages, 6 of them),
 // accumulators at [256, 512); a tile is twice the tensor work for the same MMA -> epilogue -> MMA handshake, which is
 // what bounds the pass when a tile is only a few hundred cycles of MMA (small dimensions).
-template <int BN_>
+// NACC_ = accumulator tiles in flight (TMEM columns [kDCol, 512)): 2 everywhere, 3 for BN_ = 128 with Dp <= 256, where
+// the A operand leaves room.  The epilogue's cost per tile varies a lot at large k (a shortlist insertion is ~800
+// cycles, and the MMA may only reuse a buffer when all eight epilogue warps of the pair have drained it): a third
+// buffer lets the tensor pipe run two tiles ahead, so the pass pays each warp's AVERAGE epilogue time, not the
+// slowest warp of every tile.
+template <int BN_, int NACC_ = 2>
 struct PairCfg {
     static constexpr int kRowsPerCta = BN_ / 2;
     static constexpr int kKbBytes = kRowsPerCta * 128;                  // one K block of this CTA's rows
     static constexpr int kStageBytes = KPS * kKbBytes;                  // 16 / 32 KiB
     static constexpr int kNStages = SMEM_RING_BYTES / kStageBytes;      // 12 / 6
-    static constexpr int kDCol = TMEM_COLS - 2 * BN_;                   // 384 / 256
-    static constexpr int kMaxDp = 2 * kDCol;                            // 768 / 512
+    static constexpr int kNAcc = NACC_;
+    static constexpr int kDCol = TMEM_COLS - NACC_ * BN_;               // 384 / 256 / 128
+    static constexpr int kMaxDp = 2 * kDCol;                            // 768 / 512 / 256
     // instruction descriptor: D=f32, A=B=bf16, K-major, N=BN_, M=256
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
@@ -76,10 +82,11 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int BN_>
+template <int BN_, int NACC_ = 2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
-    using Cfg = PairCfg<BN_>;
+    using Cfg = PairCfg<BN_, NACC_>;
+    constexpr uint32_t NACC = NACC_;
     constexpr int P_NSTAGES = Cfg::kNStages;
     constexpr int P_STAGE_BYTES = Cfg::kStageBytes;
     constexpr uint32_t P_IDESC = Cfg::kIdesc;
@@ -96,9 +103,10 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
     unsigned char* smem = smem_tc2 + (smem_base - smem_u32(smem_tc2));
     const uint32_t bar_base = smem_base + SMEM_BAR_OFF;
     const uint32_t full0 = bar_base, empty0 = bar_base + 8u * P_NSTAGES, tfull0 = bar_base + 8u * (2 * P_NSTAGES),
-                   tempty0 = tfull0 + 16u, aready_bar = tfull0 + 32u;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * P_NSTAGES + 5));
-    volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * P_NSTAGES + 5) + 4);
+                   tempty0 = tfull0 + 8u * NACC, aready_bar = tfull0 + 16u * NACC;
+    static_assert(8 * (2 * P_NSTAGES + 2 * NACC_ + 2) <= 256, "barrier block overflows its 256 bytes");
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * P_NSTAGES + 2 * NACC_ + 1));
+    volatile uint32_t* abort_flag = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR_OFF + 8 * (2 * P_NSTAGES + 2 * NACC_ + 1) + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long prof_c0 = clock64();
@@ -108,7 +116,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             mbar_init(full0 + 8u * s, 1);
             mbar_init(empty0 + 8u * s, 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (uint32_t b = 0; b < NACC; ++b) {
             mbar_init(tfull0 + 8u * b, 1);
             mbar_init(tempty0 + 8u * b, 8);  // 4 epilogue warps x 2 CTAs
         }
@@ -207,10 +215,10 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                 if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
                 tcgen05_fence_after();
                 for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
-                    const uint32_t buf = tile_iter & 1u;
+                    const uint32_t buf = tile_iter % NACC;
                     if (!tempty_ready) {
                         const long long c0 = clock64();
-                        if (!mbar_wait(tempty0 + 8u * buf, ((tile_iter >> 1) & 1u) ^ 1u, abort_flag, 3)) { ok = false; break; }
+                        if (!mbar_wait(tempty0 + 8u * buf, ((tile_iter / NACC) & 1u) ^ 1u, abort_flag, 3)) { ok = false; break; }
                         w_tempty += clock64() - c0;
                         ++n_w_tempty;
                     }
@@ -240,7 +248,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                             full_ready = mbar_test_wait(full0 + 8u * ns, nph);
                             if (s == spt - 1) {
                                 const uint32_t nti = tile_iter + 1;
-                                tempty_ready = mbar_test_wait(tempty0 + 8u * (nti & 1u), ((nti >> 1) & 1u) ^ 1u);
+                                tempty_ready = mbar_test_wait(tempty0 + 8u * (nti % NACC), ((nti / NACC) & 1u) ^ 1u);
                             }
                         }
                         if (leader) {
@@ -298,10 +306,10 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(even_aready);
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
-                const uint32_t buf = tile_iter & 1u;
+                const uint32_t buf = tile_iter % NACC;
                 if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter);
                 const long long ec0 = clock64();
-                if (!mbar_wait(tfull0 + 8u * buf, (tile_iter >> 1) & 1u, abort_flag, 5)) { ok = false; break; }
+                if (!mbar_wait(tfull0 + 8u * buf, (tile_iter / NACC) & 1u, abort_flag, 5)) { ok = false; break; }
                 const long long ec1 = clock64();
                 tcgen05_fence_after();
                 uint32_t v[64];

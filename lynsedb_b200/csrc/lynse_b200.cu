@@ -733,12 +733,16 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     auto launch_coarse = [&](const tc::TcArgs& args) -> int {
-        if (pair && BN == 128) {
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128>, sh.tmap_full[0], sh.tmap_rem[0], args));
+        if (pair && BN == 128 && Dp <= tc::PairCfg<128, 3>::kMaxDp && tc_env_int("LYNSE_B200_TC_NACC", 3) == 3) {
+            // narrow rows leave TMEM room for a third accumulator tile (see PairCfg)
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3>, sh.tmap_full[0], sh.tmap_rem[0], args));
+        } else if (pair && BN == 128) {
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 2>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 2>, sh.tmap_full[0], sh.tmap_rem[0], args));
         } else if (pair) {
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<64>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<64>, sh.tmap_full[1], sh.tmap_rem[1], args));
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<64, 2>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<64, 2>, sh.tmap_full[1], sh.tmap_rem[1], args));
         } else {
             LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_single_kernel, (int)tc::SMEM_BYTES));
             LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel, sh.tmap_full[0], sh.tmap_rem[0], args));
