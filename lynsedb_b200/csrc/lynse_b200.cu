@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1530,6 +1531,8 @@ struct lb_ivf {
     std::vector<uint32_t> assignments, offsets, members;
     std::vector<uint32_t> routing_dims;  // standalone IVF_FLAT inner-product routing (lb_ivf_flat_search), built lazily
     DevBuf d_ids, d_q, d_qw, d_rows, d_dists, d_counts, d_subset;
+    DevBuf d_members, d_seg, d_out, d_allow;  // inverted lists in HBM; per-query (src, dst, len) copy descriptors; packed results
+    HostBuf h_seg, h_out;                     // pinned staging of the descriptors and the results
 };
 
 namespace lb {
@@ -1557,6 +1560,11 @@ int ivf_finish(lb_ivf* ivf) {  // centroid index for the routing scan
     LB_TRY(lb_index_create(&ivf->cidx, ivf->idx->dim, LB_F32, ivf->idx->device));
     LB_TRY(lb_index_append_f32(ivf->cidx, ivf->centroids.data(), ivf->nc));
     build_lists(ivf);
+    {   // the inverted lists live in HBM: a search copies the probed lists device-side
+        DeviceGuard g(ivf->idx->device);
+        LB_TRY(ivf->d_members.ensure(ivf->members.size() * 4));
+        LB_CUDA_TRY(cudaMemcpy(ivf->d_members.p, ivf->members.data(), ivf->members.size() * 4, cudaMemcpyHostToDevice));
+    }
     return LB_OK;
 }
 }  // namespace
@@ -1568,8 +1576,11 @@ void lb_ivf_destroy(lb_ivf* ivf) {
     if (!ivf) return;
     if (ivf->idx) {
         DeviceGuard g(ivf->idx->device);
-        DevBuf* bufs[] = {&ivf->d_ids, &ivf->d_q, &ivf->d_qw, &ivf->d_rows, &ivf->d_dists, &ivf->d_counts, &ivf->d_subset};
+        DevBuf* bufs[] = {&ivf->d_ids, &ivf->d_q, &ivf->d_qw, &ivf->d_rows, &ivf->d_dists, &ivf->d_counts, &ivf->d_subset,
+                          &ivf->d_members, &ivf->d_seg, &ivf->d_out, &ivf->d_allow};
         for (DevBuf* b : bufs) b->release();
+        ivf->h_seg.release();
+        ivf->h_out.release();
     }
     if (ivf->cidx) lb_index_destroy(ivf->cidx);
     delete ivf;
@@ -1788,67 +1799,115 @@ int ivf_rank_centroids(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t 
     return LB_OK;
 }
 
-// Per query: gather the probed lists (whole lists, in probe order), apply the subset filter, score every candidate
-// with compute_distance_f32 / the packed kernels, keep the k best.  `corpus_fallback`: an empty probe falls back to
-// the filtered corpus (IVFIndex::search) instead of returning nothing (IvfFlatMmap::search).
+// Per query: the probed lists (whole lists, in probe order) become one row list in HBM — copied device-side from the
+// resident inverted lists, the host only sends (source, destination, length) per list — the subset filter rides along
+// as the scan's allow-bitset, every candidate is scored with compute_distance_f32 / the packed kernels, the k best
+// are kept.  `corpus_fallback`: a probe without a single allowed row falls back to the filtered corpus
+// (IVFIndex::search) instead of returning nothing (IvfFlatMmap::search).
+__global__ void ivf_expand_lists_kernel(const uint32_t* __restrict__ members, const uint32_t* __restrict__ seg /*[n][3]*/,
+                                        uint32_t* __restrict__ ids) {
+    const uint32_t src = seg[3 * blockIdx.x], dst = seg[3 * blockIdx.x + 1], len = seg[3 * blockIdx.x + 2];
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) ids[dst + i] = members[src + i];
+}
+
 int ivf_scan_probes(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, int metric, const std::vector<uint32_t>& probe, uint32_t np,
                     const uint64_t* allow_bits, bool corpus_fallback, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
     lb_index* idx = ivf->idx;
     const int dim = (int)idx->dim;
     std::lock_guard<std::mutex> lock(idx->mu);
     DeviceGuard g(idx->device);
+    cudaStream_t sm = idx->stream;
     const bool binary = metric_binary(metric);
     const int nw = (dim + 63) / 64;
     if (binary) LB_TRY(ensure_packed(idx));
-    auto allowed = [&](uint32_t r) { return allow_bits == nullptr || ((allow_bits[r >> 6] >> (r & 63)) & 1ull); };
-    std::vector<uint32_t> cand;
-    for (uint32_t q = 0; q < nq; ++q) {
-        cand.clear();
-        for (uint32_t p = 0; p < np; ++p) {
-            const uint32_t c = probe[(size_t)q * np + p];
-            if (c >= ivf->nc) continue;
-            for (uint32_t m = ivf->offsets[c]; m < ivf->offsets[c + 1]; ++m)
-                if (allowed(ivf->members[m])) cand.push_back(ivf->members[m]);
-        }
-        if (cand.empty() && corpus_fallback)
-            for (uint32_t r = 0; r < (uint32_t)ivf->n; ++r)
-                if (allowed(r)) cand.push_back(r);
-        if (cand.empty()) continue;
-        const uint32_t kk = (uint32_t)std::min<size_t>(k, cand.size());
-        LB_TRY(ivf->d_ids.ensure(cand.size() * 4));
-        LB_TRY(ivf->d_q.ensure((size_t)dim * 4));
-        LB_TRY(ivf->d_rows.ensure((size_t)kk * 4));
-        LB_TRY(ivf->d_dists.ensure((size_t)kk * 4));
-        LB_TRY(ivf->d_counts.ensure(4));
-        LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_ids.p, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice, idx->stream));
-        LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_q.p, queries + (size_t)q * dim, (size_t)dim * 4, cudaMemcpyHostToDevice, idx->stream));
+    // queries (and their packed form), the filter: once per call
+    LB_TRY(ivf->d_q.ensure((size_t)nq * dim * 4));
+    LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_q.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, sm));
+    if (binary) {
+        LB_TRY(ivf->d_qw.ensure((size_t)nq * nw * 8));
+        pack_binary_kernel<<<(nq + 7) / 8, 256, 0, sm>>>(ivf->d_q.as<float>(), (uint64_t)nq, dim, nw, 0.5f, ivf->d_qw.as<uint64_t>());
+        LB_CUDA_TRY(cudaGetLastError());
+    }
+    const uint64_t* d_allow = nullptr;
+    if (allow_bits) {
+        const size_t words = (ivf->n + 63) / 64;
+        LB_TRY(ivf->d_allow.ensure(words * 8));
+        LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_allow.p, allow_bits, words * 8, cudaMemcpyHostToDevice, sm));
+        d_allow = ivf->d_allow.as<uint64_t>();
+    }
+    LB_TRY(ivf->h_seg.ensure((size_t)np * 12));
+    LB_TRY(ivf->d_seg.ensure((size_t)np * 12));
+    LB_TRY(ivf->d_out.ensure((size_t)k * 8 + 4));
+    LB_TRY(ivf->h_out.ensure((size_t)k * 8 + 4));
+    uint32_t* seg = reinterpret_cast<uint32_t*>(ivf->h_seg.p);
+    uint32_t* d_rows = ivf->d_out.as<uint32_t>();
+    float* d_dists = reinterpret_cast<float*>(ivf->d_out.as<char>() + (size_t)k * 4);
+    uint32_t* d_count = reinterpret_cast<uint32_t*>(ivf->d_out.as<char>() + (size_t)k * 8);
+    auto scan = [&](uint32_t q, const uint32_t* row_ids, uint64_t n_rows) -> int {  // -> pinned h_out
         ScanRequest r;
-        r.n_rows = cand.size();
-        r.row_ids = ivf->d_ids.as<uint32_t>();
+        r.n_rows = n_rows;
+        r.row_ids = row_ids;
         r.nq = 1;
-        r.k = (int)kk;
+        r.k = (int)std::min<uint64_t>(k, n_rows);
         r.metric = metric;
-        r.out_rows = ivf->d_rows.as<uint32_t>();
-        r.out_dists = ivf->d_dists.as<float>();
-        r.out_counts = ivf->d_counts.as<uint32_t>();
+        r.allow_bits = d_allow;
+        r.out_rows = d_rows;
+        r.out_dists = d_dists;
+        r.out_counts = d_count;
         if (binary) {
-            LB_TRY(ivf->d_qw.ensure((size_t)nw * 8));
-            pack_binary_kernel<<<1, 32, 0, idx->stream>>>(ivf->d_q.as<float>(), 1, dim, nw, 0.5f, ivf->d_qw.as<uint64_t>());
-            LB_CUDA_TRY(cudaGetLastError());
             r.words = idx->packed.as<uint64_t>();
             r.n_words = nw;
-            r.qwords = ivf->d_qw.as<uint64_t>();
+            r.qwords = ivf->d_qw.as<uint64_t>() + (size_t)q * nw;
         } else {
             r.corpus = idx->rows.as<float>();
             r.dim = dim;
-            r.queries = ivf->d_q.as<float>();
+            r.queries = ivf->d_q.as<float>() + (size_t)q * dim;
             r.ip_single = 1;  // compute_distance_f32 -> the single-row IP kernel
         }
         LB_TRY(run_scan(idx, r, nullptr, nullptr));
-        LB_CUDA_TRY(cudaMemcpyAsync(out_rows + (size_t)q * k, ivf->d_rows.p, (size_t)kk * 4, cudaMemcpyDeviceToHost, idx->stream));
-        LB_CUDA_TRY(cudaMemcpyAsync(out_dists + (size_t)q * k, ivf->d_dists.p, (size_t)kk * 4, cudaMemcpyDeviceToHost, idx->stream));
-        LB_CUDA_TRY(cudaMemcpyAsync(out_counts + q, ivf->d_counts.p, 4, cudaMemcpyDeviceToHost, idx->stream));
-        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        LB_CUDA_TRY(cudaMemcpyAsync(ivf->h_out.p, ivf->d_out.p, (size_t)k * 8 + 4, cudaMemcpyDeviceToHost, sm));
+        LB_CUDA_TRY(cudaStreamSynchronize(sm));
+        return LB_OK;
+    };
+    const bool trace = tc_env_int("LYNSE_B200_IVF_TRACE", 0) != 0;
+    for (uint32_t q = 0; q < nq; ++q) {
+        const auto tr0 = std::chrono::steady_clock::now();
+        uint32_t total = 0, n_seg = 0;
+        for (uint32_t p = 0; p < np; ++p) {
+            const uint32_t c = probe[(size_t)q * np + p];
+            if (c >= ivf->nc) continue;
+            const uint32_t len = ivf->offsets[c + 1] - ivf->offsets[c];
+            if (len == 0) continue;
+            seg[3 * n_seg] = ivf->offsets[c];
+            seg[3 * n_seg + 1] = total;
+            seg[3 * n_seg + 2] = len;
+            ++n_seg;
+            total += len;
+        }
+        uint32_t found = 0;
+        if (total > 0) {
+            LB_TRY(ivf->d_ids.ensure((size_t)total * 4));
+            LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_seg.p, seg, (size_t)n_seg * 12, cudaMemcpyHostToDevice, sm));
+            ivf_expand_lists_kernel<<<n_seg, 256, 0, sm>>>(ivf->d_members.as<uint32_t>(), ivf->d_seg.as<uint32_t>(), ivf->d_ids.as<uint32_t>());
+            LB_CUDA_TRY(cudaGetLastError());
+            const auto tr1 = std::chrono::steady_clock::now();
+            LB_TRY(scan(q, ivf->d_ids.as<uint32_t>(), total));
+            found = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ivf->h_out.p) + (size_t)k * 8);
+            if (trace && q < 4) {
+                const auto tr2 = std::chrono::steady_clock::now();
+                fprintf(stderr, "[lynse_b200] ivf query %u: %u rows in %u lists; lists+expand enqueue %.1f us, scan+copy+sync %.1f us\n", q, total, n_seg,
+                        std::chrono::duration<double, std::micro>(tr1 - tr0).count(), std::chrono::duration<double, std::micro>(tr2 - tr1).count());
+            }
+        }
+        if (found == 0 && corpus_fallback && ivf->n > 0) {  // nothing allowed among the probed rows: the filtered corpus
+            LB_TRY(scan(q, nullptr, ivf->n));
+            found = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ivf->h_out.p) + (size_t)k * 8);
+        }
+        if (found == 0) continue;
+        const char* h = reinterpret_cast<const char*>(ivf->h_out.p);
+        memcpy(out_rows + (size_t)q * k, h, (size_t)found * 4);
+        memcpy(out_dists + (size_t)q * k, h + (size_t)k * 4, (size_t)found * 4);
+        out_counts[q] = found;
     }
     return LB_OK;
 }
