@@ -356,6 +356,18 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
         if (valid) row = a.row_ids ? __ldg(a.row_ids + slot) : (uint32_t)slot;
         if (valid && !row_allowed(a.allow_bits, row)) valid = false;
         const float* c = a.corpus + (size_t)row * dim;
+        if (a.row_ids != nullptr) {
+            // gathered rows (IVF lists, id filters): neighbouring threads read unrelated rows, so nothing arrives in L2
+            // ahead of the one-chunk-ahead loads and every 32-byte piece costs a DRAM round trip (measured: 2.3 us per
+            // chunk).  Ask L2 for the whole row now — the next block's row, and on the first block this one's too.
+            auto prefetch_row = [&](uint32_t r) {
+                const char* p = reinterpret_cast<const char*>(a.corpus + (size_t)r * dim);
+                for (int off = 0; off < dim * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+            };
+            if (blk == part_begin && valid) prefetch_row(row);
+            const uint64_t nslot = slot + S2_ROWS;
+            if (nslot < part_end) prefetch_row(__ldg(a.row_ids + nslot));
+        }
         const bool two_acc = METRIC == LB_IP && (a.ip_single || (valid && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row)));
         for (int q0 = 0; q0 < a.nq; q0 += S2_TQ) {
             const int tq = min(S2_TQ, a.nq - q0);

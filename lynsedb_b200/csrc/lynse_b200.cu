@@ -1806,8 +1806,10 @@ int ivf_rank_centroids(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t 
 // (IVFIndex::search) instead of returning nothing (IvfFlatMmap::search).
 __global__ void ivf_expand_lists_kernel(const uint32_t* __restrict__ members, const uint32_t* __restrict__ seg /*[n][3]*/,
                                         uint32_t* __restrict__ ids) {
+    // grid (lists, slices): slice y of a list is its elements [1024 y, 1024 (y + 1))
     const uint32_t src = seg[3 * blockIdx.x], dst = seg[3 * blockIdx.x + 1], len = seg[3 * blockIdx.x + 2];
-    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) ids[dst + i] = members[src + i];
+    const uint32_t lo = blockIdx.y * 1024u, hi = min(len, lo + 1024u);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) ids[dst + i] = members[src + i];
 }
 
 int ivf_scan_probes(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, int metric, const std::vector<uint32_t>& probe, uint32_t np,
@@ -1872,7 +1874,7 @@ int ivf_scan_probes(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, 
     const bool trace = tc_env_int("LYNSE_B200_IVF_TRACE", 0) != 0;
     for (uint32_t q = 0; q < nq; ++q) {
         const auto tr0 = std::chrono::steady_clock::now();
-        uint32_t total = 0, n_seg = 0;
+        uint32_t total = 0, n_seg = 0, max_len = 0;
         for (uint32_t p = 0; p < np; ++p) {
             const uint32_t c = probe[(size_t)q * np + p];
             if (c >= ivf->nc) continue;
@@ -1883,12 +1885,13 @@ int ivf_scan_probes(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t k, 
             seg[3 * n_seg + 2] = len;
             ++n_seg;
             total += len;
+            max_len = std::max(max_len, len);
         }
         uint32_t found = 0;
         if (total > 0) {
             LB_TRY(ivf->d_ids.ensure((size_t)total * 4));
             LB_CUDA_TRY(cudaMemcpyAsync(ivf->d_seg.p, seg, (size_t)n_seg * 12, cudaMemcpyHostToDevice, sm));
-            ivf_expand_lists_kernel<<<n_seg, 256, 0, sm>>>(ivf->d_members.as<uint32_t>(), ivf->d_seg.as<uint32_t>(), ivf->d_ids.as<uint32_t>());
+            ivf_expand_lists_kernel<<<dim3(n_seg, (max_len + 1023) / 1024), 256, 0, sm>>>(ivf->d_members.as<uint32_t>(), ivf->d_seg.as<uint32_t>(), ivf->d_ids.as<uint32_t>());
             LB_CUDA_TRY(cudaGetLastError());
             const auto tr1 = std::chrono::steady_clock::now();
             LB_TRY(scan(q, ivf->d_ids.as<uint32_t>(), total));
