@@ -16,7 +16,6 @@ from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Unio
 
 import numpy as np
 
-from . import _backend
 from . import metrics as M
 from .index import DeviceIndex, make_allow_bits
 from .ivf import DEFAULT_N_CLUSTERS, DEFAULT_NPROBE, IVFIndex
@@ -66,6 +65,7 @@ class Collection:
         self._ivf_params: Dict[str, int] = {}
         self._pending: List[np.ndarray] = []
         self._pending_rows = 0
+        self._pending_index: Optional[DeviceIndex] = None   # the un-flushed rows in HBM, rebuilt when they change
         self._row_ids: List[Any] = []            # row -> external id (engine.rs:3071-3073)
         self._id_rows: Dict[Any, int] = {}
         self._fields: Dict[int, dict] = {}
@@ -84,6 +84,7 @@ class Collection:
             if self._ivf is not None:
                 self._ivf.close()
                 self._ivf = None
+            self._drop_pending_index()
             if self._store is not None:
                 self._store.close()
                 self._store = None
@@ -172,6 +173,7 @@ class Collection:
                 chunk = vec[s:s + batch_size]
                 self._pending.append(chunk)
                 self._pending_rows += chunk.shape[0]
+                self._drop_pending_index()
                 if self._pending_rows >= PENDING_FLUSH_ROWS or self._pending_rows * self._dim * 4 >= PENDING_FLUSH_BYTES:
                     self._flush_pending()
             if self._ivf is not None:
@@ -195,6 +197,19 @@ class Collection:
                 self._store.set_segment_target(1 << 62)
         return self._store
 
+    def _drop_pending_index(self) -> None:
+        if self._pending_index is not None:
+            self._pending_index.close()
+            self._pending_index = None
+
+    def _pending_store(self) -> DeviceIndex:
+        """The un-flushed rows as a device index: one upload per change of the buffer, not one per query."""
+        if self._pending_index is None:
+            block = self._pending[0] if len(self._pending) == 1 else np.concatenate(self._pending, axis=0)
+            self._pending_index = DeviceIndex(self._dim, "float32", self._device)
+            self._pending_index.append(block)
+        return self._pending_index
+
     def _flush_pending(self) -> None:
         """One flush == one ``VectorStore::append`` (never split across segments)."""
         if not self._pending:
@@ -203,6 +218,7 @@ class Collection:
         self._ensure_store().append(block)
         self._pending = []
         self._pending_rows = 0
+        self._drop_pending_index()
 
     def commit(self) -> None:
         with self._lock:
@@ -379,16 +395,21 @@ class Collection:
                 rows, dists, counts = self._store.search(q, search_k, self._metric, allow, f16_rows=f16_rows)
             out = [(rows[i, :int(counts[i])].astype(np.uint64), dists[i, :int(counts[i])].copy()) for i in range(nq)]
         if self._pending_rows and search_k > 0:
-            block = self._pending[0] if len(self._pending) == 1 else np.concatenate(self._pending, axis=0)
-            offsets = np.arange(n_store, n_store + block.shape[0], dtype=np.uint64)
+            # pending_search (src/engine.rs:3310-3360): compute_distance_f32 against every un-flushed row, top-k, then
+            # merge_row_results with the flushed hits
+            n_p = self._pending_rows
+            allow, any_allowed = None, True
             if subset is not None:
-                keep = np.isin(offsets, subset)
-                block, offsets = np.ascontiguousarray(block[keep]), offsets[keep]
-            if block.shape[0]:
+                local = subset[(subset >= n_store) & (subset < n_store + n_p)] - np.uint64(n_store)
+                any_allowed = local.size > 0
+                allow = make_allow_bits(n_p, local)
+            if any_allowed:
                 asc = M.is_ascending(self._metric)
+                prow, pd, pc = self._pending_store().search(q, min(search_k, n_p), self._metric, allow, pairwise=True)
                 for i in range(nq):
-                    pi, pd = _backend.top_k_search(q[i], block, M.NAMES[self._metric], search_k)   # pending_search
-                    out[i] = _merge_row_results(out[i][0], out[i][1], offsets[pi], pd, search_k, asc)
+                    c = int(pc[i])
+                    out[i] = _merge_row_results(out[i][0], out[i][1], prow[i, :c].astype(np.uint64) + np.uint64(n_store),
+                                                pd[i, :c].copy(), search_k, asc)
         return out
 
     def _finish(self, rows: np.ndarray, dists: np.ndarray, k: int, return_fields: bool) -> ResultView:

@@ -979,8 +979,8 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
             r.row_mass = idx->mass_stats.as<double>();
         }
         std::vector<uint32_t> unhandled;
-        if (metric == LB_JENSEN_SHANNON && !r.f16_rows) {
-            // FlatMmap::search Jensen-Shannon branch (flat_mmap.rs:912-921, :926-1111)
+        if (metric == LB_JENSEN_SHANNON && idx->score_mode == SCORE_FLAT) {
+            // FlatMmap::search Jensen-Shannon branch (the per-pair scoring modes call jensen_shannon_distance directly) (flat_mmap.rs:912-921, :926-1111)
             LB_TRY(ensure_js_stats(idx));
             LB_TRY(idx->w_qstats.ensure((size_t)nq * 8));
             LB_TRY(idx->w_nq.ensure((size_t)nq * idx->dim * 4));
@@ -1002,7 +1002,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
             r.sqrt_scores = 1;
         }
         LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
-        if (metric == LB_JENSEN_SHANNON && !r.f16_rows) {
+        if (metric == LB_JENSEN_SHANNON && idx->score_mode == SCORE_FLAT) {
             // queries the cached path cannot serve fall back to the direct kernel (prepare_jensen_shannon_query -> None)
             std::vector<uint32_t> qmap;
             for (int q = 0; q < nq; ++q)

@@ -36,7 +36,7 @@ class FakeIndex:
     def close(self):
         pass
 
-    def search(self, q, k, metric, allow_bits=None, f16_rows=False):
+    def search(self, q, k, metric, allow_bits=None, f16_rows=False, pairwise=False):
         assert metric in (M.IP, M.L2)
         self.f16_calls = getattr(self, "f16_calls", []) + [bool(f16_rows)]
         nq, n = q.shape[0], len(self)
@@ -59,13 +59,6 @@ class FakeIndex:
 @pytest.fixture()
 def fake(monkeypatch):
     monkeypatch.setattr(client_mod, "DeviceIndex", FakeIndex)
-
-    def fake_topk(query, block, metric, k):
-        s = block @ query if metric == "ip" else ((block - query) ** 2).sum(1)
-        order = np.argsort(-s if metric == "ip" else s, kind="stable")[:k]
-        return order.astype(np.uint32), s[order].astype(np.float32)
-
-    monkeypatch.setattr(client_mod._backend, "top_k_search", fake_topk)
 
 
 def test_client_object_model(fake):

@@ -540,3 +540,22 @@ def test_few_queries_on_a_small_corpus_take_the_exact_scan(L, oracle):
             got = idx.search(queries[:nq], 10, "ip")
             assert idx.last_stats()["plan_used"] == plan
             _check(oracle.store_batch_search(corpus, queries[:nq], 10, "ip"), got, "ip", 10)
+
+
+@pytest.mark.parametrize("metric", ["jensen_shannon", "ip", "wasserstein", "hamming"])
+def test_pairwise_search_scores_every_pair_with_compute_distance(L, oracle, metric):
+    # search_range / pending_search semantics (src/engine.rs:6410-6483, :3310-3360): compute_distance_f32 per row — for
+    # Jensen-Shannon that is the direct kernel, not the cached entropy form of the FLAT scan
+    corpus, queries = _data(3000, 24, 401), _data(3, 24, 402)
+    with L.DeviceIndex(24) as idx:
+        idx.append(corpus)
+        rows, dists, counts = idx.search(queries, 7, metric, pairwise=True)
+    for qi in range(3):
+        score = np.array([oracle.compute_distance(queries[qi], r, metric) for r in corpus], dtype=np.float32)
+        order = np.lexsort((np.arange(len(corpus)), -score if metric == "ip" else score))[:7]
+        assert counts[qi] == 7
+        assert np.array_equal(rows[qi], order.astype(np.uint32)), metric
+        if metric in EXACT_BITS:
+            assert np.array_equal(dists[qi].view(np.uint32), score[order].view(np.uint32))
+        else:
+            np.testing.assert_allclose(dists[qi], score[order], rtol=REL_TOL, atol=1e-7)
