@@ -61,9 +61,10 @@ struct TcArgs {
     uint32_t tiles_total;     // ceil(n_rows / 64)
     uint32_t tiles_per_part;
     int P;                    // row partitions
-    float* cand_score;        // [nq][P][KP]
-    uint32_t* cand_row;       // [nq][P][KP]
-    float* cand_thr;          // [nq][P]
+    int lists_per_part;       // shortlists per (query, partition): 1, or 2 when the pair kernel runs two epilogue sets
+    float* cand_score;        // [nq][P * lists_per_part][KP]
+    uint32_t* cand_row;       // [nq][P * lists_per_part][KP]
+    float* cand_thr;          // [nq][P * lists_per_part]
     int share_floor;          // 1: partitions of a query share a shortlist floor through gthr; 2: gthr holds a floor seeded by a
                               // pre-pass over a sample of the corpus and is only read (large k)
     int floor_group;          // m: a published floor is the minimum of the floors of m consecutive partitions, so that at
@@ -460,16 +461,18 @@ struct Shortlist {
             if (may_publish && q_valid && group_m <= 1 && lmin > thr_pub && lmin > thr_g) publish();
         }
     }
-    __device__ __forceinline__ void flush(const TcArgs& a, uint32_t gq, uint32_t part) {
+    // `sub`: which of the partition's lists_per_part shortlists this is (the pair kernel with two epilogue sets)
+    __device__ __forceinline__ void flush(const TcArgs& a, uint32_t gq, uint32_t part, uint32_t sub = 0) {
         if (!q_valid) return;
-        const size_t o = ((size_t)gq * a.P + part) * KP;
+        const size_t list = (size_t)gq * ((size_t)a.P * a.lists_per_part) + (size_t)part * a.lists_per_part + sub;
+        const size_t o = list * KP;
 #pragma unroll
         for (int j = 0; j < KP; j += 4) {
             *reinterpret_cast<float4*>(a.cand_score + o + j) = make_float4(sc[j], sc[j + 1], sc[j + 2], sc[j + 3]);
             *reinterpret_cast<uint4*>(a.cand_row + o + j) = make_uint4(rw[j], rw[j + 1], rw[j + 2], rw[j + 3]);
         }
         // every row this thread dropped scored <= max(lmin, thr_g) at the time, and both only grow
-        a.cand_thr[(size_t)gq * a.P + part] = fmaxf(lmin, thr_g);
+        a.cand_thr[list] = fmaxf(lmin, thr_g);
     }
 };
 

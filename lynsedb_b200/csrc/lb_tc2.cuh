@@ -82,11 +82,16 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int BN_, int NACC_ = 2>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EPI_ = sets of four epilogue warps per CTA.  With two sets (BN_ = 128 only) warps w and w + 4 share a TMEM
+// sub-partition, i.e. the same 32 queries, and each takes one 64-column half of every accumulator tile into its own
+// shortlists (TcArgs::lists_per_part = 2): the epilogue is bound by the issue rate of a single warp per sub-partition
+// at large k, and two warps double it.
+template <int BN_, int NACC_ = 2, int EPI_ = 1>
+__global__ void __launch_bounds__(64 + 128 * EPI_, 1)
 coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
     using Cfg = PairCfg<BN_, NACC_>;
     constexpr uint32_t NACC = NACC_;
+    static_assert(EPI_ == 1 || (EPI_ == 2 && BN_ == 128), "two epilogue sets split a 128-column tile in halves");
     constexpr int P_NSTAGES = Cfg::kNStages;
     constexpr int P_STAGE_BYTES = Cfg::kStageBytes;
     constexpr uint32_t P_IDESC = Cfg::kIdesc;
@@ -118,7 +123,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
         }
         for (uint32_t b = 0; b < NACC; ++b) {
             mbar_init(tfull0 + 8u * b, 1);
-            mbar_init(tempty0 + 8u * b, 8);  // 4 epilogue warps x 2 CTAs
+            mbar_init(tempty0 + 8u * b, 8 * EPI_);  // 4 * EPI_ epilogue warps x 2 CTAs
         }
         mbar_init(aready_bar, 8);
         *abort_flag = 0;
@@ -282,7 +287,8 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
         }
     } else {
         // ===================== epilogue: lane == query (each CTA reads its own 128 accumulator lanes) ==========
-        const int quad = warp & 3;
+        const int quad = warp & 3;                 // TMEM sub-partition of this warp = the 32 queries it serves
+        const int eset = EPI_ == 2 ? (warp - 2) >> 2 : 0;  // which 64-column half of a tile this warp scans (two sets)
         const int ql = quad * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t even_tempty0 = mapa_rank(tempty0, 0), even_aready = mapa_rank(aready_bar, 0);
@@ -299,12 +305,12 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             if (part >= (uint32_t)a.P) break;
             const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
             const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
-            if (r == first_round) load_query_to_tmem(a.qb + (size_t)gq * a.Dp, a.Dp, lane_addr);  // the query tile never changes
+            if (r == first_round && eset == 0) load_query_to_tmem(a.qb + (size_t)gq * a.Dp, a.Dp, lane_addr);  // the query tile never changes
             sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0));
             sl.part = (int)part;
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(even_aready);
+            if (lane == 0 && eset == 0) mbar_arrive_cluster(even_aready);
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter % NACC;
                 if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter);
@@ -315,12 +321,13 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                 uint32_t v[64];
 #pragma unroll
                 for (int h = 0; h < BN_ / 64; ++h) {
+                    if (EPI_ == 2 && h != eset) continue;  // the other set's half
                     if (!(a.debug_mode & 2)) {
                         tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + h * 64, v);
                         tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + h * 64 + 32, v + 32);
                         tmem_ld_wait();
                     }
-                    if (h == BN_ / 64 - 1) {
+                    if (EPI_ == 2 || h == BN_ / 64 - 1) {
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(even_tempty0 + 8u * buf);  // accumulator is in registers
@@ -344,7 +351,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             }
             if (ok) {
                 if (r < 0) sl.absorb_sample();
-                else sl.flush(a, gq, part);
+                else sl.flush(a, gq, part, (uint32_t)eset);
             }
         }
         if (a.prof != nullptr && warp == 2 && lane == 0) {

@@ -645,18 +645,24 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     // crowd into one 16-entry list: P >= 0.75 k.
     const bool seeded = k > tc::KP - 4 && tiles_total >= (uint32_t)(64 * 8) * (uint32_t)n_slots && dump == nullptr &&
                         tc_env_int("LYNSE_B200_TC_SEED", 1) != 0;
+    // two epilogue sets (eight epilogue warps per CTA, two shortlists per partition): 128-row tiles of narrow rows at
+    // large k, where the epilogue's instruction issue rate bounds the pass (LYNSE_B200_TC_EPI=1 turns it off)
+    const bool epi2 = pair && BN == 128 && Dp <= tc::PairCfg<128, 3>::kMaxDp && k > tc::KP - 4 && tc_env_int("LYNSE_B200_TC_EPI", 2) == 2 &&
+                      tc_env_int("LYNSE_B200_TC_NACC", 3) == 3;
+    const uint64_t L = epi2 ? 2 : 1;
     uint64_t parts_per_slot = 1;
     {
         uint64_t want = seeded ? ((uint64_t)3 * k + 3) / 4 : ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
+        want = ceil_div(want, L);  // a partition contributes L shortlists
         const int env_parts = tc_env_int("LYNSE_B200_TC_PARTS", 0);
         if (env_parts > 0) want = (uint64_t)env_parts;
-        while (n_slots * parts_per_slot < want && n_slots * (parts_per_slot + 1) <= 4096 / tc::KP) ++parts_per_slot;
+        while (n_slots * parts_per_slot < want && n_slots * (parts_per_slot + 1) * L <= 4096 / tc::KP) ++parts_per_slot;
     }
     uint64_t P = std::min<uint64_t>(n_slots * parts_per_slot, tiles_total);
     const uint32_t tiles_per_part = (uint32_t)ceil_div(tiles_total, P);
     P = ceil_div(tiles_total, tiles_per_part);
     parts_per_slot = ceil_div(P, n_slots);
-    const uint64_t P_buf = std::max<uint64_t>(P, n_slots);
+    const uint64_t P_buf = std::max<uint64_t>(P, n_slots) * L;
     LB_TRY(idx->w_cand_score.ensure((size_t)nq * P_buf * tc::KP * 4));
     LB_TRY(idx->w_cand_row.ensure((size_t)nq * P_buf * tc::KP * 4));
     LB_TRY(idx->w_cand_thr.ensure((size_t)nq * P_buf * 4));
@@ -675,6 +681,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     a.tiles_total = tiles_total;
     a.tiles_per_part = tiles_per_part;
     a.P = (int)P;
+    a.lists_per_part = (int)L;
     a.cand_score = idx->w_cand_score.as<float>();
     a.cand_row = idx->w_cand_row.as<uint32_t>();
     a.cand_thr = idx->w_cand_thr.as<float>();
@@ -734,7 +741,12 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     auto launch_coarse = [&](const tc::TcArgs& args) -> int {
-        if (pair && BN == 128 && Dp <= tc::PairCfg<128, 3>::kMaxDp && tc_env_int("LYNSE_B200_TC_NACC", 3) == 3) {
+        if (epi2) {
+            cudaLaunchConfig_t cfg2 = cfg;
+            cfg2.blockDim = dim3(64 + 128 * 2);
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 2>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg2, tc::coarse_pair_kernel<128, 3, 2>, sh.tmap_full[0], sh.tmap_rem[0], args));
+        } else if (pair && BN == 128 && Dp <= tc::PairCfg<128, 3>::kMaxDp && tc_env_int("LYNSE_B200_TC_NACC", 3) == 3) {
             // narrow rows leave TMEM room for a third accumulator tile (see PairCfg)
             LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3>, (int)tc::SMEM_BYTES));
             LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3>, sh.tmap_full[0], sh.tmap_rem[0], args));
@@ -764,12 +776,13 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
         sa.gfloor = nullptr;
         sa.sample_tiles = 0;
         LB_TRY(launch_coarse(sa));
-        const int sm = next_pow2(sa.P * tc::KP);
+        const int s_lists = sa.P * (int)L;
+        const int sm = next_pow2(s_lists * tc::KP);
         // aim at ~10 k rows of the whole corpus above the seeded floor
         int r = (int)ceil_div((uint64_t)10 * k * S, tiles_total);
-        r = std::max(4, std::min(r, sa.P * tc::KP / 2));
+        r = std::max(4, std::min(r, s_lists * tc::KP / 2));
         LB_CUDA_TRY(ensure_dynamic_smem(tc::seed_floor_kernel, sm * 8));
-        tc::seed_floor_kernel<<<nq, 256, (size_t)sm * 8, idx->stream>>>(sa.cand_score, sa.cand_row, sa.P, sm, r, a.gthr);
+        tc::seed_floor_kernel<<<nq, 256, (size_t)sm * 8, idx->stream>>>(sa.cand_score, sa.cand_row, s_lists, sm, r, a.gthr);
         LB_CUDA_TRY(cudaGetLastError());
         if (a.progress) LB_CUDA_TRY(cudaMemsetAsync(idx->w_progress.p, 0, (size_t)n_slots * tc::PROGRESS_STRIDE * 4, idx->stream));
         idx->stats.kernels_launched += 2;
@@ -782,8 +795,8 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     f.cand_score = a.cand_score;
     f.cand_row = a.cand_row;
     f.cand_thr = a.cand_thr;
-    f.P = (int)P;
-    f.M1 = next_pow2((int)P * tc::KP);
+    f.P = (int)(P * L);
+    f.M1 = next_pow2((int)(P * L) * tc::KP);
     f.R = std::min(1024, std::max(128, next_pow2(4 * k)));
     f.corpus = idx->rows.as<float>();
     f.dim = (int)idx->dim;
