@@ -62,6 +62,8 @@ struct TcArgs {
     uint32_t tiles_per_part;
     int P;                    // row partitions
     int lists_per_part;       // shortlists per (query, partition): 1, or 2 when the pair kernel runs two epilogue sets
+    const uint64_t* allow_bits;  // optional row filter (bit r = row r allowed, LSB-first u64 words): disallowed rows never
+                                 // enter a shortlist, so floors, certification and result are those of the allowed rows
     float* cand_score;        // [nq][P * lists_per_part][KP]
     uint32_t* cand_row;       // [nq][P * lists_per_part][KP]
     float* cand_thr;          // [nq][P * lists_per_part]
@@ -395,7 +397,8 @@ struct Shortlist {
         lmin = fmin3(fminf(m0, m1), sc[14], sc[15]);
     }
     // 64 accumulator columns of this thread's query = rows row0 .. row0+63.  Called by whole warps.
-    __device__ __forceinline__ void scan64(const uint32_t* v, uint32_t row0, uint32_t row_end, bool disabled) {
+    __device__ __forceinline__ void scan64(const uint32_t* v, uint32_t row0, uint32_t row_end, bool disabled,
+                                           const uint64_t* __restrict__ allow = nullptr) {
         float thr = disabled ? INFINITY : gate();
         // tile maximum with 3-input max: 32 instructions for 64 scores
         float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
@@ -422,8 +425,16 @@ struct Shortlist {
                 mlo &= n_ok >= 32u ? 0xffffffffu : ((1u << n_ok) - 1u);
                 mhi &= n_ok >= 64u ? 0xffffffffu : (n_ok > 32u ? ((1u << (n_ok - 32u)) - 1u) : 0u);
             }
+            bool filtered = false;  // this lane lost a hit to the row filter: its tile maximum may be a disallowed row
+            if (allow != nullptr) {
+                const uint64_t w = row0 < row_end ? __ldg(allow + (row0 >> 6)) : 0ull;  // row0 is a multiple of 64
+                const uint32_t alo = (uint32_t)w, ahi = (uint32_t)(w >> 32);
+                filtered = ((mlo & ~alo) | (mhi & ~ahi)) != 0u;
+                mlo &= alo;
+                mhi &= ahi;
+            }
             // a lane with exactly one hit (the usual case) already holds its score: it is the tile maximum
-            const bool one_hit = __popc(mlo) + __popc(mhi) == 1;
+            const bool one_hit = !filtered && __popc(mlo) + __popc(mhi) == 1;
             if (one_hit) {
                 const int idx = mlo != 0u ? __ffs((int)mlo) - 1 : 32 + __ffs((int)mhi) - 1;
                 insert(fmaxf(m0, m1), row0 + (uint32_t)idx);

@@ -192,7 +192,7 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
 #pragma unroll
                     for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
                 }
-                sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0);
+                sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
             }
             if (ok) {
                 if (r < 0) sl.absorb_sample();

@@ -342,7 +342,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                         for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
                     }
                     const long long sc0 = clock64();
-                    sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0);
+                    sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
                     const long long sd = clock64() - sc0;
                     e_scan += sd;
                     if (sd > 400) { ++n_slow; e_slow += sd; }

@@ -190,6 +190,7 @@ struct lb_index {
     // SCORE_FLAT = the FLAT scan's kernels (tensor-core plan allowed), SCORE_PAIRWISE = compute_distance_f32 on the
     // exact scan, SCORE_F16_ROWS = compute_distance_f16 (scalar order) on the exact scan
     int score_mode = 0;
+    uint64_t allow_count = 0;  // rows allowed by the filter of the running host-buffer search (set with the filter)
     bool timing = false;
     lb_search_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -608,7 +609,7 @@ static int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms
 
 // ---- tensor-core plan ----------------------------------------------------------------------------------------
 static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uint32_t* d_rows, float* d_dists,
-                  uint32_t* d_counts, float* dump) {
+                  uint32_t* d_counts, float* dump, const uint64_t* d_allow = nullptr) {
     const int kind = shadow_kind_for(metric);
     const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
     // one query tile: one CTA per partition (lb_tc1.cuh); more: CTA pairs (tcgen05 cta_group::2, lb_tc2.cuh)
@@ -682,6 +683,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
     a.tiles_per_part = tiles_per_part;
     a.P = (int)P;
     a.lists_per_part = (int)L;
+    a.allow_bits = d_allow;
     a.cand_score = idx->w_cand_score.as<float>();
     a.cand_row = idx->w_cand_row.as<uint32_t>();
     a.cand_thr = idx->w_cand_thr.as<float>();
@@ -903,6 +905,7 @@ static int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int
         r.metric = metric;
         r.small_seg = idx->small_seg.as<uint32_t>();
         r.n_small = idx->n_small;
+        r.allow_bits = d_allow;
         r.qmap = idx->w_qmap.as<uint32_t>();
         r.out_rows = d_rows;
         r.out_dists = d_dists;
@@ -962,11 +965,14 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
         idx->stats.plan_used = 2;
         idx->stats.algorithmic_bytes = (uint64_t)idx->n * nw * 8;
-    } else if (idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT && d_allow == nullptr && tc_supported(idx, metric) && k <= 256 && idx->n >= 64 &&
+    } else if (idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT && tc_supported(idx, metric) && k <= 256 && idx->n >= 64 &&
+               // a row filter rides along as a mask on the hit bits; with few allowed rows the shortlists cannot fill
+               // and certification would send everything to the exact scan anyway
+               (d_allow == nullptr || idx->allow_count >= (uint64_t)std::max(1024, 32 * k)) &&
                // a handful of queries over a small corpus is a latency case: the exact scan is two launches, the tensor
                // plan three plus a lazily built shadow (100k x 128, one query: 85 against 131 us of device time)
                !(nq <= 4 && (uint64_t)idx->n * idx->dim * 4 < (256ull << 20))) {
-        LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr));
+        LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr, d_allow));
         kernels = idx->stats.kernels_launched;
         ms_dom = idx->stats.ms_dominant;
     } else {
@@ -1309,6 +1315,9 @@ static int search_host_common(lb_index* idx, int score_mode, int metric, const v
         LB_TRY(idx->w_allow.ensure(need * 8));
         LB_CUDA_TRY(cudaMemcpyAsync(idx->w_allow.p, allow_bits, need * 8, cudaMemcpyHostToDevice, idx->stream));
         d_allow = idx->w_allow.as<uint64_t>();
+        uint64_t allowed = 0;  // plan selection only (bits past the last row do not matter at this precision)
+        for (uint64_t w = 0; w < need; ++w) allowed += (uint64_t)__builtin_popcountll(allow_bits[w]);
+        idx->allow_count = allowed;
     }
     lb_search_stats acc{};
     constexpr size_t STAGE_LIMIT = 256 * 1024;  // batches up to this many bytes go through pinned staging
