@@ -24,6 +24,7 @@ from .result_view import ResultView
 PENDING_FLUSH_ROWS = 10_000          # src/engine.rs:93-94
 PENDING_FLUSH_BYTES = 32 << 20
 MAX_DATABASES = 64                   # python/lynse/__init__.py:128
+TENSOR_PLAN_MAX_K = 256              # largest k the tensor-core plan of the library serves
 KNOWN_BUILD_KEYS = frozenset({"n_clusters", "n_centroids", "m", "ef_construction", "ef_search", "max_level", "r", "l",
                               "alpha", "max_degree", "nprobe", "replica_count"})  # python/lynse/_index_build.py:49-66
 _DOMAIN_FREE = (M.IP, M.L2, M.COSINE, M.HAMMING, M.JACCARD)
@@ -377,7 +378,8 @@ class Collection:
             rows = matched if rows is None else rows & matched
         return np.fromiter(sorted(rows), dtype=np.uint64, count=len(rows))
 
-    def _search_rows(self, q: np.ndarray, search_k: int, nprobe: int, subset: Optional[np.ndarray], single: bool = False):
+    def _search_rows(self, q: np.ndarray, search_k: int, nprobe: int, subset: Optional[np.ndarray], single: bool = False,
+                     k: Optional[int] = None):
         """(rows, dists) per query over flushed + pending rows, before id mapping: scan, pending_search, merge_row_results."""
         nq = q.shape[0]
         n_store = len(self._store) if self._store is not None else 0
@@ -392,7 +394,18 @@ class Collection:
                 rows, dists, counts = self._ivf.search(q, search_k, nprobe, allow)
             else:
                 f16_rows = self._dtypes == "float16" and (single or subset is not None)
-                rows, dists, counts = self._store.search(q, search_k, self._metric, allow, f16_rows=f16_rows)
+                stored_k = search_k
+                if k is not None and search_k > TENSOR_PLAN_MAX_K >= k:
+                    # many deleted rows: asking for k + |tombstones| would push the search off the tensor-core plan.
+                    # Masking the deleted rows out and asking for k gives the same live top-k (the over-fetch exists
+                    # only to survive the tombstone filter, src/engine.rs:4735-4741, :3286-3308).
+                    dead = np.fromiter((self._id_rows[t] for t in self._tombstones), dtype=np.uint64, count=len(self._tombstones))
+                    dead = dead[dead < n_store]
+                    if allow is None:
+                        allow = np.full((n_store + 63) // 64, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+                    np.bitwise_and.at(allow, (dead >> np.uint64(6)).astype(np.int64), ~(np.uint64(1) << (dead & np.uint64(63))))
+                    stored_k = k
+                rows, dists, counts = self._store.search(q, stored_k, self._metric, allow, f16_rows=f16_rows)
             out = [(rows[i, :int(counts[i])].astype(np.uint64), dists[i, :int(counts[i])].copy()) for i in range(nq)]
         if self._pending_rows and search_k > 0:
             # pending_search (src/engine.rs:3310-3360): compute_distance_f32 against every un-flushed row, top-k, then
@@ -464,7 +477,7 @@ class Collection:
                 raise ValueError(f"Dimension mismatch: expected {self._dim}, got {q.shape[1]}")
             subset = self._subset_rows(where, filter_ids)
             search_k = k + len(self._tombstones)             # engine.rs:4735-4741
-            per_query = self._search_rows(q, search_k, int(nprobe), subset, single)
+            per_query = self._search_rows(q, search_k, int(nprobe), subset, single, k=k)
             return [self._finish(r, d, k, return_fields) for (r, d) in per_query]
 
     def __repr__(self) -> str:

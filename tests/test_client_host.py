@@ -193,3 +193,31 @@ def test_float16_collection_routes_single_and_filtered_searches_to_the_scalar_ke
     plain.search(q[0], 3)
     plain.batch_search(q, 3, filter_ids=[1, 2, 3])
     assert plain._store.f16_calls == [False, False]
+
+
+def test_many_tombstones_become_a_row_mask_with_the_same_result(fake):
+    # k + |tombstones| beyond the tensor plan's k: the deleted rows are masked out and k results are asked for;
+    # the answer is the live top-k either way (src/engine.rs:4735-4741, :3286-3308)
+    rng = np.random.default_rng(4)
+    vecs = rng.random((1000, 4), dtype=np.float32)
+    coll = Collection("c", 4)
+    coll.add(list(range(1000)), vectors=vecs)
+    coll.commit()
+    order = np.argsort(-(vecs @ vecs[0]), kind="stable")
+    coll.delete([int(i) for i in order[1:301]])          # the 300 best after the query itself
+    calls = []
+    real = coll._store.search
+
+    def spy(q, k, metric, allow_bits=None, **kw):
+        calls.append((k, allow_bits is not None))
+        return real(q, k, metric, allow_bits, **kw)
+
+    coll._store.search = spy
+    got = coll.search(vecs[0], 10)
+    assert calls == [(10, True)]
+    live = [int(i) for i in order if int(i) not in set(int(j) for j in order[1:301])][:10]
+    assert got.ids.tolist() == live
+    coll.restore([int(i) for i in order[1:295]])         # 6 tombstones left: back to the over-fetch
+    calls.clear()
+    coll.search(vecs[0], 10)
+    assert calls == [(16, False)]
