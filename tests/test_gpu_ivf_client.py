@@ -137,6 +137,27 @@ def test_collection_matches_flat_oracle_with_pending_and_tombstones(L, oracle):
         assert list(coll.search(queries[0], k).ids) == want
 
 
+def test_collection_with_hundreds_of_deleted_rows_stays_exact(L, oracle):
+    # k + |tombstones| > 256: the client masks the deleted rows out and asks for k (tensor-core plan with a row filter)
+    rng = np.random.default_rng(8)
+    n, dim, k = 30000, 48, 10
+    data = rng.random((n, dim), dtype=np.float32) - np.float32(0.5)      # signed: the queries' best rows barely overlap
+    queries = rng.random((20, dim), dtype=np.float32) - np.float32(0.5)
+    with L.VectorDBClient() as client:
+        coll = client.create_collection("db", "c", dim=dim, default_index="FLAT-IP")
+        coll.add(vectors=data)
+        coll.commit()
+        o_ids, _, _ = oracle.store_batch_search(data, queries, 400, "ip", n_threads=1)
+        dead = sorted({int(x) for x in o_ids[:, :15].ravel()})           # the best 15 of every query: ~300 rows
+        assert len(dead) + k > 256
+        coll.delete(dead)
+        res = coll.batch_search(queries, k)
+        assert coll._store.last_stats()["plan_used"] == 1
+        for i, r in enumerate(res):
+            want = [int(x) for x in o_ids[i] if int(x) not in set(dead)][:k]
+            assert r.ids.tolist() == want
+
+
 def test_collection_ivf_mode(L):
     rng = np.random.default_rng(11)
     data = rng.random((3000, 32), dtype=np.float32)
