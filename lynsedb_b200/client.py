@@ -251,14 +251,16 @@ class Collection:
         self._maybe_build_default_index()
         return total
 
-    def search_range(self, vector, threshold: float, max_results: int = 1000):
-        """``(ids, distances)`` of every live row within ``threshold`` (<= for distances, >= for IP), best first, at most
+    def search_range(self, vector, threshold: float, max_results: int = 1000) -> ResultView:
+        """``ResultView`` (python/lynse/api/local_client.py:1370-1397) of every live row within ``threshold`` (<= for distances, >= for IP), best first, at most
         ``max_results`` — ``Collection::search_range`` (src/engine.rs:6410-6483): per-pair ``compute_distance_f32`` order."""
         q = np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1)
         max_results = int(max_results)
         with self._lock:
             if max_results <= 0 or self._dim is None or not self._row_ids:
-                return np.empty(0, np.int64), np.empty(0, np.float32)
+                idx_type, dist_name = M.parse_index_mode(self._index_mode or "FLAT-IP")
+                return ResultView(ids=np.empty(0, np.int64), distances=np.empty(0, np.float32), k=0, distance=dist_name,
+                                  index=idx_type, result_type="search")
             if q.shape[1] != self._dim:
                 raise ValueError(f"Dimension mismatch: expected {self._dim}, got {q.shape[1]}")
             self._flush_pending()
@@ -277,7 +279,9 @@ class Collection:
                 if len(ids) == max_results:
                     break
             all_int = all(isinstance(i, (int, np.integer)) for i in ids)
-            return (np.asarray(ids, dtype=np.int64 if all_int else object), np.asarray(out, dtype=np.float32))
+            idx_type, dist_name = M.parse_index_mode(self._index_mode or "FLAT-IP")
+            return ResultView(ids=np.asarray(ids, dtype=np.int64 if all_int else object), distances=np.asarray(out, dtype=np.float32),
+                              k=len(ids), distance=dist_name, index=idx_type, result_type="search")
 
     flush = commit
 
@@ -447,15 +451,22 @@ class Collection:
                vector_field: str = "default", reranker=None, rerank_k=None, rerank_with_fields: bool = False, nprobe: int = 10,
                approx: bool = False, eps: float = 1e-4, wire_dtype: str = "float32", filter_ids: Optional[Iterable] = None
                ) -> ResultView:
-        del wire_dtype, approx, eps, rerank_with_fields   # approx: the exact GPU scan supersedes the CPU shortlist heuristics
+        del wire_dtype, rerank_with_fields
         if (vector is None) == (document is None):
             raise ValueError("search() requires exactly one of vector or document")
         if document is not None or embed_func is not None or reranker is not None or rerank_k is not None:
             raise NotImplementedError("document search and external rerankers are outside this package's scope")
         if vector_field != "default":
             raise NotImplementedError("named vector fields are outside this package's scope")
-        return self._batch_search(np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1), k, where, return_fields, nprobe,
-                                  filter_ids, single=True)[0]
+        result = self._batch_search(np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1), k, where, return_fields, nprobe,
+                                    filter_ids, single=True)[0]
+        # approx=True: the ids come from the exact GPU scan (it supersedes the CPU shortlist heuristics); what a caller
+        # can observe of the reference's approximate mode is kept — on an unfiltered FLAT search with a metric that
+        # supports it, distances are rounded to multiples of eps (src/engine.rs:4756-4763, :4817-4819)
+        if (approx and where is None and filter_ids is None and _index_family(self._index_mode or "FLAT-IP") == "FLAT"
+                and self._metric in _APPROX_METRICS and result.distances is not None and len(result.distances)):
+            _round_to_eps(result.distances, eps)
+        return result
 
     def batch_search(self, vectors, k: int = 10, *, where=None, return_fields: bool = False, nprobe: int = 10, reranker=None,
                      rerank_k=None, rerank_with_fields: bool = False, wire_dtype: str = "float32",
@@ -482,6 +493,26 @@ class Collection:
 
     def __repr__(self) -> str:
         return f"Collection(name={self.name!r}, shape={self.shape}, index_mode={self._index_mode!r})"
+
+
+_APPROX_METRICS = (M.IP, M.L2, M.COSINE, M.MANHATTAN, M.CHEBYSHEV, M.CANBERRA, M.BRAY_CURTIS)   # supports_flat_approx
+
+
+def _round_to_eps(distances: np.ndarray, eps) -> None:
+    """``round_distances_to_eps`` in place (src/storage/approx_search.rs:113-143): eps is normalised to a finite value
+    >= 1e-8 (default 1e-4), each finite distance becomes ``round(d / eps) * eps`` in f32, halves away from zero."""
+    try:
+        e = np.float32(eps)
+    except (TypeError, ValueError, OverflowError):
+        e = np.float32("nan")
+    e = np.float32(max(e, np.float32(1e-8))) if np.isfinite(e) and e > 0 else np.float32(1e-4)
+    with np.errstate(all="ignore"):
+        scaled = distances / e
+        t = np.trunc(scaled)
+        r = (t + np.sign(scaled) * (np.abs(scaled - t) >= np.float32(0.5))).astype(np.float32)
+        rounded = (r * e).astype(np.float32)
+        ok = np.isfinite(distances) & np.isfinite(scaled) & np.isfinite(rounded)
+    distances[ok] = rounded[ok]
 
 
 def _merge_row_results(l_rows, l_d, r_rows, r_d, limit: int, ascending: bool):

@@ -221,3 +221,34 @@ def test_many_tombstones_become_a_row_mask_with_the_same_result(fake):
     calls.clear()
     coll.search(vecs[0], 10)
     assert calls == [(16, False)]
+
+
+def test_approx_search_rounds_distances_to_eps_and_search_range_returns_a_view(fake):
+    # tests/standard_tests/test_search.py:30-43 (approx ids == exact ids, distances on the eps grid, non-finite eps falls
+    # back to 1e-4) and :594-616 (search_range returns a ResultView)
+    from lynsedb_b200.client import _round_to_eps
+    rng = np.random.default_rng(12)
+    vecs = rng.random((200, 4), dtype=np.float32)
+    coll = Collection("c", 4)
+    coll.add(list(range(200)), vectors=vecs)
+    coll.commit()
+    exact = coll.search(vecs[3], k=5, approx=False)
+    approx = coll.search(vecs[3], k=5, approx=True, eps=1e-4)
+    assert approx.ids.tolist() == exact.ids.tolist()
+    assert np.max(np.abs(approx.distances - exact.distances)) <= 1e-4
+    scaled = approx.distances / 1e-4
+    assert np.allclose(scaled, np.round(scaled), atol=1e-3)
+    inf_eps = coll.search(vecs[3], k=5, approx=True, eps=float("inf"))
+    assert len(inf_eps.ids) == 5 and np.all(np.isfinite(inf_eps.distances))
+    assert np.array_equal(inf_eps.distances, approx.distances)                      # default eps 1e-4
+    filtered = coll.search(vecs[3], k=5, approx=True, filter_ids=list(range(50)))   # filtered searches stay exact
+    assert np.array_equal(filtered.distances, coll.search(vecs[3], k=5, filter_ids=list(range(50))).distances)
+    d = np.array([0.25, -0.25, 0.35, np.inf, np.nan], dtype=np.float32)
+    _round_to_eps(d, 0.5)
+    assert d[:3].tolist() == [0.5, -0.5, 0.5] and np.isinf(d[3]) and np.isnan(d[4])  # halves away from zero
+    view = coll.search_range(vecs[3], threshold=-1e6)
+    assert isinstance(view, client_mod.ResultView) and len(view.ids) > 0
+    ids, dists, fields = view
+    assert len(ids) == len(dists)
+    assert len(coll.search_range(vecs[3], threshold=1e6).ids) == 0
+    assert len(coll.search_range(vecs[3], threshold=-1e6, max_results=3).ids) <= 3

@@ -199,11 +199,13 @@ def test_load_lynsedb_directory_and_search_range(L, oracle, tmp_path):
         d_all = np.array([oracle.compute_distance(q, v, "l2") for v in allv], dtype=np.float32)
         thr = float(np.sort(d_all)[40])
         coll.delete([int(np.argsort(d_all, kind="stable")[3]) + 5000])
-        got_ids, got_d = coll.search_range(q, thr, max_results=100)
+        got = coll.search_range(q, thr, max_results=100)
+        assert isinstance(got, L.ResultView)
+        got_ids, got_d = got.ids, got.distances
         order = [i for i in np.argsort(d_all, kind="stable") if d_all[i] <= thr and i != np.argsort(d_all, kind="stable")[3]]
         assert got_ids.tolist() == [int(i) + 5000 for i in order]
         assert np.array_equal(got_d.view(np.uint32), d_all[order].view(np.uint32))
-        assert len(coll.search_range(q, thr, max_results=7)[0]) == 7
+        assert len(coll.search_range(q, thr, max_results=7).ids) == 7
 
 
 # ---- standalone IVF_FLAT index: `_core.IvfFlatIndex` (src/python/mod.rs:2049-2156, src/storage/ivf_flat_mmap.rs) ----
