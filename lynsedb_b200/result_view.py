@@ -156,3 +156,37 @@ class ResultView:
         import pandas as pd
 
         return pd.DataFrame(self.to_dict())
+
+    def to_arrow(self):
+        """``pyarrow.Table``: ``id`` / ``distance`` (search), ``id`` / ``vector`` (data), then one column per field
+        name (python/lynse/result_view.py:470-520).  Ids that are not all integers become strings."""
+        try:
+            import pyarrow as pa
+        except ImportError as e:
+            raise ImportError("pyarrow is required for to_arrow(). Install it with: pip install pyarrow") from e
+
+        def id_array(ids):
+            vals = [v.item() if hasattr(v, "item") else v for v in ids]
+            if all(isinstance(v, int) and not isinstance(v, bool) for v in vals):
+                return pa.array(vals, type=pa.int64())
+            return pa.array([str(v) for v in vals], type=pa.string())
+
+        arrays = {}
+        if self._ids is not None:
+            arrays["id"] = id_array(self._ids)
+        if self._result_type == "search" and self._distances is not None:
+            arrays["distance"] = pa.array(np.asarray(self._distances, dtype=np.float32), type=pa.float32())
+        if self._result_type == "data" and self._vectors is not None:
+            arrays["vector"] = pa.array(np.asarray(self._vectors, dtype=np.float32).tolist(), type=pa.list_(pa.float32()))
+        if self._fields:
+            for key in sorted({key for row in self._fields if row for key in row}):
+                arrays[key] = pa.array([row.get(key) if row else None for row in self._fields])
+        return pa.table(arrays)
+
+    def to_polars(self):
+        """``polars.DataFrame`` (python/lynse/result_view.py: requires polars)."""
+        try:
+            import polars as pl
+        except ImportError as e:
+            raise ImportError("polars is required for to_polars(). Install it with: pip install polars") from e
+        return pl.from_arrow(self.to_arrow())

@@ -252,3 +252,17 @@ def test_approx_search_rounds_distances_to_eps_and_search_range_returns_a_view(f
     assert len(ids) == len(dists)
     assert len(coll.search_range(vecs[3], threshold=1e6).ids) == 0
     assert len(coll.search_range(vecs[3], threshold=-1e6, max_results=3).ids) <= 3
+
+
+def test_result_view_arrow_export():
+    # tests/standard_tests/test_result_view.py: to_arrow columns (id, distance, one per field); polars is optional
+    pa = pytest.importorskip("pyarrow")
+    rv = client_mod.ResultView(ids=np.array([3, 1], dtype=np.int64), distances=np.array([0.5, 0.25], dtype=np.float32),
+                               fields=[{"g": 1}, {"g": 2}], k=2, distance="IP", index="Flat")
+    t = rv.to_arrow()
+    assert t.column_names == ["id", "distance", "g"] and t.num_rows == 2
+    assert t.schema.field("id").type == pa.int64() and t.schema.field("distance").type == pa.float32()
+    mixed = client_mod.ResultView(ids=np.array(["a", 7], dtype=object), distances=np.array([0.5, 0.25], dtype=np.float32), k=2)
+    assert mixed.to_arrow().column("id").to_pylist() == ["a", "7"]
+    data = client_mod.ResultView(ids=np.array([1, 2]), vectors=np.zeros((2, 3), np.float32), result_type="data")
+    assert data.to_arrow().column_names == ["id", "vector"]
