@@ -91,6 +91,7 @@ __device__ __forceinline__ uint64_t warp_fold_candidates_t(const uint64_t* __res
     uint32_t cnt = cnt0;
     uint64_t thr = 0xFFFFFFFFFFFFFFFFull;  // KEY_NONE
     if (cnt0 >= (uint32_t)k) thr = *reinterpret_cast<volatile uint64_t*>(thr_p);
+    __syncwarp();  // every lane has read the list header before lane 0 may rewrite it below
     if (cnt0 == 0 && n >= k && n <= 256) {
         // first block of a partition: the list is empty and every row is a candidate.  Take the k smallest by k
         // warp-wide minimum reductions instead of ~n serial insertions (the dominant cost of a short partition).
