@@ -11,7 +11,7 @@
 namespace lb {
 
 // assign_metric: first centroid of minimal rank (rank = distance, or -score for IP), strict <
-__global__ void ivf_assign_kernel(const float* __restrict__ rows, uint64_t n, int dim, const float* __restrict__ centroids, int nc,
+static __global__ void ivf_assign_kernel(const float* __restrict__ rows, uint64_t n, int dim, const float* __restrict__ centroids, int nc,
                                   int metric, uint32_t* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -32,7 +32,7 @@ __global__ void ivf_assign_kernel(const float* __restrict__ rows, uint64_t n, in
 }
 
 // one CTA per centroid, one thread per dimension: sum of the members in row order, then * (1 / count)
-__global__ void ivf_centroid_update_kernel(const float* __restrict__ rows, int dim, const uint32_t* __restrict__ offsets,
+static __global__ void ivf_centroid_update_kernel(const float* __restrict__ rows, int dim, const uint32_t* __restrict__ offsets,
                                            const uint32_t* __restrict__ members, float* __restrict__ centroids) {
     const int c = blockIdx.x;
     const uint32_t lo = offsets[c], hi = offsets[c + 1];
@@ -45,7 +45,7 @@ __global__ void ivf_centroid_update_kernel(const float* __restrict__ rows, int d
     }
 }
 
-__global__ void ivf_gather_rows_kernel(const float* __restrict__ rows, int dim, const uint32_t* __restrict__ ids, uint32_t n_ids,
+static __global__ void ivf_gather_rows_kernel(const float* __restrict__ rows, int dim, const uint32_t* __restrict__ ids, uint32_t n_ids,
                                        float* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (uint64_t)n_ids * dim) return;
@@ -56,7 +56,7 @@ __global__ void ivf_gather_rows_kernel(const float* __restrict__ rows, int dim, 
 
 // min_ranks[i] = min(min_ranks[i], rank(sample[i], centroid)); then the LAST index of maximal min_rank
 // (Iterator::max_by keeps the last of equal maxima) is written to *best.  One CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) ivf_farthest_kernel(const float* __restrict__ sample, uint32_t n, int dim,
+static __global__ void __launch_bounds__(1024) ivf_farthest_kernel(const float* __restrict__ sample, uint32_t n, int dim,
                                                             const float* __restrict__ centroid, int metric,
                                                             float* __restrict__ min_ranks, uint32_t* __restrict__ best) {
     __shared__ uint64_t s_key[32];

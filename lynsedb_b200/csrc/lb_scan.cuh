@@ -323,7 +323,7 @@ struct MergeArgs {
     uint32_t* out_counts;    // [*]
 };
 
-__global__ void __launch_bounds__(1024) merge_lists_kernel(MergeArgs a) {
+static __global__ void __launch_bounds__(1024) merge_lists_kernel(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_merge[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_merge);
     const int q = blockIdx.x;
@@ -380,7 +380,7 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
 constexpr int MERGE_SMALL_MAX_K = 32;
 constexpr int MERGE_SMALL_MAX_KEYS = 4096;
 
-__global__ void __launch_bounds__(1024) merge_lists_small_kernel(MergeArgs a) {
+static __global__ void __launch_bounds__(1024) merge_lists_small_kernel(MergeArgs a) {
     __shared__ uint64_t runs[32][MERGE_SMALL_MAX_K];
     const int q = blockIdx.x, k = a.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = a.P * k;
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(1024) merge_lists_small_kernel(MergeArgs a) {
 
 // ---- side-structure builders ---------------------------------------------------------------------------------
 // pack_binary_f32 (simd.rs:750-757, flat_mmap.rs:1283-1290): bit = x > 0.5, word i/64 bit i%64.  One warp per row.
-__global__ void pack_binary_kernel(const float* __restrict__ rows, uint64_t n, int dim, int n_words, float threshold,
+static __global__ void pack_binary_kernel(const float* __restrict__ rows, uint64_t n, int dim, int n_words, float threshold,
                                    uint64_t* __restrict__ out) {
     uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -450,7 +450,7 @@ __global__ void pack_binary_kernel(const float* __restrict__ rows, uint64_t n, i
 }
 
 // probability_row_stats for every row (flat_mmap.rs:949-983) — also used for the queries.
-__global__ void row_stats_kernel(const float* __restrict__ rows, uint64_t n, int dim, float* __restrict__ stats) {
+static __global__ void row_stats_kernel(const float* __restrict__ rows, uint64_t n, int dim, float* __restrict__ stats) {
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     float inv, ent;
@@ -460,7 +460,7 @@ __global__ void row_stats_kernel(const float* __restrict__ rows, uint64_t n, int
 }
 
 // prepare_jensen_shannon_query (flat_mmap.rs:926-947): q * inv_mass; flag = 1 when the cached path cannot serve it.
-__global__ void js_prepare_queries_kernel(const float* __restrict__ queries, int nq, int dim,
+static __global__ void js_prepare_queries_kernel(const float* __restrict__ queries, int nq, int dim,
                                           const float* __restrict__ qstats, float* __restrict__ nq_out,
                                           uint32_t* __restrict__ unhandled) {
     int q = blockIdx.x;
@@ -474,23 +474,23 @@ __global__ void js_prepare_queries_kernel(const float* __restrict__ queries, int
 }
 
 // one pair (py_compute_distance)
-__global__ void pair_distance_kernel(const float* a, const float* b, int dim, int metric, float* out) {
+static __global__ void pair_distance_kernel(const float* a, const float* b, int dim, int metric, float* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *out = compute_distance<true>(metric, a, b, dim, (dim & 3) == 0);
 }
 
-__global__ void fill_f32_kernel(float* out, uint64_t n, float value) {
+static __global__ void fill_f32_kernel(float* out, uint64_t n, float value) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) out[i] = value;
 }
 
 // synthetic corpora
-__global__ void synth_f32_kernel(float* out, uint64_t n_elems, uint64_t seed, uint64_t elem_offset) {
+static __global__ void synth_f32_kernel(float* out, uint64_t n_elems, uint64_t seed, uint64_t elem_offset) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < n_elems; i += stride) out[i] = synth_f32(seed, elem_offset + i);
 }
-__global__ void synth_u64_kernel(uint64_t* out, uint64_t n_elems, uint64_t seed, uint64_t elem_offset) {
+static __global__ void synth_u64_kernel(uint64_t* out, uint64_t n_elems, uint64_t seed, uint64_t elem_offset) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < n_elems; i += stride) out[i] = synth_u64(seed, elem_offset + i);

@@ -47,7 +47,7 @@ __device__ inline void scan2_query_consts(const float* __restrict__ q /*smem*/, 
     out[1] = ss;
 }
 // Wasserstein row masses, once per row (the first loop of wasserstein_1d_f32, simd.rs:691-698)
-__global__ void row_mass_kernel(const float* __restrict__ rows, uint64_t n, int dim, double* __restrict__ mass) {
+static __global__ void row_mass_kernel(const float* __restrict__ rows, uint64_t n, int dim, double* __restrict__ mass) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     const float* c = rows + row * dim;

@@ -501,7 +501,7 @@ __host__ __device__ inline size_t shadow_chunk_offset(uint64_t row, int chunk /*
     const uint32_t kb = (uint32_t)chunk >> 3, c = (uint32_t)chunk & 7u;
     return (size_t)(((tile * (uint64_t)nkb + kb) * 2 + half) * HALF_BLOCK_BYTES) + (size_t)r * 128 + (size_t)((c ^ (r & 7u)) << 4);
 }
-__global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int Dp,
+static __global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int Dp,
                                     int kind, unsigned char* __restrict__ shadow, float* __restrict__ max_norm) {
     uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -539,7 +539,7 @@ __global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t fir
 
 // Queries: bf16 A operand rows (zero padded to n_mtiles*128 x Dp) + |q| per query.
 //   SHADOW_IP      q                 SHADOW_COSINE  q / |q|          SHADOW_L2  [2q, -1, -1, -1]
-__global__ void prepare_queries_kernel(const float* __restrict__ queries, int nq, int nq_pad, int dim, int Dp, int kind,
+static __global__ void prepare_queries_kernel(const float* __restrict__ queries, int nq, int nq_pad, int dim, int Dp, int kind,
                                        __nv_bfloat16* __restrict__ qb, float* __restrict__ qnorm) {
     int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -574,7 +574,7 @@ __global__ void prepare_queries_kernel(const float* __restrict__ queries, int nq
 // floor the main pass starts with (gthr).  It is a heuristic gate — about r * (rows / sample rows) rows of the corpus
 // score above it — and the certification of finalize_kernel is what keeps the result exact: a floor that turns out
 // too high leaves the query uncertified and it is re-run by the exact scan.
-__global__ void __launch_bounds__(256) seed_floor_kernel(const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_row, int P,
+static __global__ void __launch_bounds__(256) seed_floor_kernel(const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_row, int P,
                                                          int M, int r, uint32_t* __restrict__ gthr) {
     extern __shared__ __align__(16) unsigned char smem_seed[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_seed);

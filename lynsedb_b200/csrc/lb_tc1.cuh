@@ -16,7 +16,7 @@ constexpr int S_STAGE_BYTES = KPS * 2 * HALF_BLOCK_BYTES;  // 32 KiB
 constexpr int S_NSTAGES = SMEM_RING_BYTES / S_STAGE_BYTES;  // 6
 constexpr uint32_t S_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+static __global__ void __launch_bounds__(NUM_THREADS, 1)
 coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
     const int slot = (int)blockIdx.x;
     const int n_rounds = slot < a.n_slots ? a.parts_per_slot : 0;
