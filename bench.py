@@ -39,8 +39,12 @@ WORKLOADS = {
     "c1": ("ip", 100_000, 128, 1000, 10, "FLAT-IP 100k x 128 f32, 1k queries, k=10 (BASELINE configs[0])"),
     "c3": ("l2", 10_000_000, 128, 1024, 100, "FLAT-L2 10M x 128 f32, batch-1024, k=100 (BASELINE configs[2])"),
     "c4": ("hamming", 50_000_000, 1024, 4096, 32, "packed Hamming 50M x 1024-bit, batch-4096, k=32 (BASELINE configs[3])"),
+    "c4t": ("tanimoto", 50_000_000, 1024, 4096, 32, "packed Tanimoto 50M x 1024-bit, batch-4096, k=32 (BASELINE configs[3])"),
+    # weak scaling: 10M rows per GPU, i.e. the full 80M rows at --gpus 8
+    "c5": ("ip", 80_000_000, 768, 1024, 10, "FLAT-IP 80M x 768 f32 row-sharded across 8 GPUs (10M rows per GPU), batch-1024, k=10 (BASELINE configs[4])"),
 }
-PACKED = {"c4"}
+PACKED = {"c4", "c4t"}
+WEAK = {"c5"}
 SEED_CORPUS, SEED_QUERIES = 42, 43
 APPEND_ROWS = 100_000  # ingestion batch, as benchmarks/flat_search_bench.py feeds the reference
 
@@ -60,6 +64,8 @@ def parse_args():
                    help="queries of the cpu_baseline leg of the own arm (about 10 s of CPU work on 16 threads at C2)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--plan", default="auto", choices=["auto", "exact"])
+    p.add_argument("--verify-queries", type=int, default=64, help="queries whose id lists are compared with the exact plan")
+    p.add_argument("--no-c5", action="store_true", help="multi-GPU default run: skip the extra 10M-rows-per-GPU (configs[4]) measurement")
     return p.parse_args()
 
 
@@ -102,7 +108,7 @@ def ncu_traffic(args, world, nq):
     if args.workload != "c2" or args.rows or args.nq or world != 1 or args.plan != "auto":
         return None
     try:
-        d = json.loads((ROOT / "profiles" / "r1_coarse_pair_ncu.json").read_text())["kernels"][0]
+        d = json.loads((ROOT / "profiles" / "r2_coarse_pair_ncu.json").read_text())["kernels"][0]
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
         return rd["value"] * mult[rd["unit"]] + wr["value"] * mult[wr["unit"]]
@@ -290,9 +296,228 @@ def run_reference(args, metric, rows, dim, nq, k, desc):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+class Rig:
+    """One rank's corpus shard + pinned / device buffers + the timed step functions."""
+
+    def __init__(self, args, lib, N, M, comm, rank, world, local_rank, metric, rows, dim, nq, k, packed, dist):
+        from lynsedb_b200.index import DeviceIndex
+        from lynsedb_b200.sharding import shard_range
+
+        self.lib, self.N, self.comm, self.rank, self.world, self.local_rank, self.dist = lib, N, comm, rank, world, local_rank, dist
+        self.metric, self.rows, self.dim, self.nq, self.k, self.packed = metric, rows, dim, nq, k, packed
+        self.base, self.n_local = shard_range(rows, world, rank)
+        self.idx = DeviceIndex(dim, "packed" if packed else "float32", device=local_rank)
+        self.idx.reserve(self.n_local)
+        done = 0
+        while done < self.n_local:
+            m = min(APPEND_ROWS, self.n_local - done)
+            self.idx.append_synthetic(m, SEED_CORPUS, self.base + done)
+            done += m
+        self.idx.set_plan(args.plan)
+        self.m_id = M.require(metric)
+        self.idx.prepare(self.m_id)
+        self.idx.set_timing(True)
+        self.queries = make_queries(metric, nq, dim, packed)
+        self.qbytes = self.queries.nbytes
+        # pinned host staging for the e2e path
+        self.hq, self.hrows, self.hdists, self.hcounts = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        N.check(lib.lb_host_malloc(self.qbytes, C.byref(self.hq)))
+        N.check(lib.lb_host_malloc(nq * k * 8, C.byref(self.hrows)))
+        N.check(lib.lb_host_malloc(nq * k * 4, C.byref(self.hdists)))
+        N.check(lib.lb_host_malloc(nq * 4, C.byref(self.hcounts)))
+        C.memmove(self.hq, self.queries.ctypes.data, self.qbytes)
+        # device-resident buffers for the `value` path
+        self.dq, self.drows, self.ddists, self.dcounts = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        N.check(lib.lb_device_malloc(local_rank, self.qbytes, C.byref(self.dq)))
+        N.check(lib.lb_device_malloc(local_rank, nq * k * 8, C.byref(self.drows)))
+        N.check(lib.lb_device_malloc(local_rank, nq * k * 4, C.byref(self.ddists)))
+        N.check(lib.lb_device_malloc(local_rank, nq * 4, C.byref(self.dcounts)))
+        N.check(lib.lb_memcpy_h2d(local_rank, self.dq, self.hq, self.qbytes))
+
+    def close(self):
+        for p in (self.hq, self.hrows, self.hdists, self.hcounts):
+            self.lib.lb_host_free(p)
+        for p in (self.dq, self.drows, self.ddists, self.dcounts):
+            self.lib.lb_device_free(self.local_rank, p)
+        self.idx.close()
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_device(self):
+        self.N.check(self.lib.lb_sharded_search_device(self.comm, self.idx._h, self.m_id, self.dq, self.nq, self.k, self.base,
+                                                       self.drows, self.ddists, self.dcounts))
+
+    def step_host(self, nq=None):
+        nq = self.nq if nq is None else nq
+        if self.packed:
+            self.N.check(self.lib.lb_sharded_search_packed(self.comm, self.idx._h, self.m_id, C.cast(self.hq, C.POINTER(C.c_uint64)), nq,
+                                                           self.k, self.base, C.cast(self.hrows, C.POINTER(C.c_uint64)),
+                                                           C.cast(self.hdists, C.POINTER(C.c_float)), C.cast(self.hcounts, C.POINTER(C.c_uint32))))
+            return
+        self.N.check(self.lib.lb_sharded_search(self.comm, self.idx._h, self.m_id, C.cast(self.hq, C.POINTER(C.c_float)), nq, self.k,
+                                                self.base, C.cast(self.hrows, C.POINTER(C.c_uint64)), C.cast(self.hdists, C.POINTER(C.c_float)),
+                                                C.cast(self.hcounts, C.POINTER(C.c_uint32))))
+
+    def host_results(self, nq=None):
+        nq = self.nq if nq is None else nq
+        grow = np.ctypeslib.as_array(C.cast(self.hrows, C.POINTER(C.c_uint64)), shape=(nq * self.k,)).reshape(nq, self.k).copy()
+        gd = np.ctypeslib.as_array(C.cast(self.hdists, C.POINTER(C.c_float)), shape=(nq * self.k,)).reshape(nq, self.k).copy()
+        return grow, gd
+
+    def timed(self, fn, steps, slot):
+        lib, N, idx = self.lib, self.N, self.idx
+        self.barrier()
+        N.check(lib.lb_device_synchronize(self.local_rank))
+        N.check(lib.lb_index_event_record(idx._h, slot))
+        dom, launches, fallbacks = [], 0, 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+            st = idx.last_stats()
+            dom.append(st["ms_dominant"])
+            launches += st["kernels_launched"]
+            fallbacks += st["n_fallback"]
+        N.check(lib.lb_index_event_record(idx._h, slot + 1))
+        N.check(lib.lb_device_synchronize(self.local_rank))
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        ms = C.c_float(0)
+        N.check(lib.lb_index_event_elapsed_ms(idx._h, slot, slot + 1, C.byref(ms)))
+        self.barrier()
+        return self.max_over_ranks(float(ms.value)), wall_ms, dom, launches, fallbacks, idx.last_stats()
+
+    def measure(self, steps, warmup):
+        for _ in range(max(warmup, 3)):
+            self.step_device()
+        ms_dev, wall_dev, dom, launches, fallbacks, st = self.timed(self.step_device, steps, 0)
+        for _ in range(2):
+            self.step_host()
+        ms_e2e, wall_e2e, _, _, fb2, _ = self.timed(self.step_host, steps, 2)
+        return {"ms_dev": ms_dev, "wall_dev": wall_dev, "dom": dom, "launches": launches, "fallbacks": fallbacks + fb2, "st": st,
+                "ms_e2e": ms_e2e, "wall_e2e": wall_e2e}
+
+
+def verify_results(rig, args, oracle_mod):
+    """The last e2e result against (1) the oracle's exact scores of the returned rows, (2) the id lists of the exact
+    CUDA-core plan on the same index for a sample of queries (that plan is oracle-verified bit for bit by the GPU
+    tests), (3) for corpora the oracle scans in seconds, the oracle's id lists over the full corpus."""
+    from lynsedb_b200 import synthetic
+
+    metric, dim, nq, k, packed = rig.metric, rig.dim, rig.nq, rig.k, rig.packed
+    grow, gd = rig.host_results()
+    out = {}
+    # (2) every rank runs the exact plan on the sampled queries (a collective when sharded); rank 0 compares
+    ns = min(args.verify_queries, nq)
+    sample = np.unique(np.linspace(0, nq - 1, ns).astype(np.int64))
+    ns = len(sample)
+    sub = np.ascontiguousarray(rig.queries[sample])
+    C.memmove(rig.hq, sub.ctypes.data, sub.nbytes)
+    rig.idx.set_plan("exact")
+    rig.step_host(ns)
+    erow, ed = rig.host_results(ns)
+    rig.idx.set_plan(args.plan)
+    C.memmove(rig.hq, rig.queries.ctypes.data, rig.qbytes)
+    if rig.rank != 0:
+        return None
+    ids_same = bool(np.array_equal(erow, grow[sample]))
+    scores_same = bool(np.array_equal(ed.view(np.uint32), gd[sample].view(np.uint32)))
+    out["ids_exact_vs_exact_plan"] = ids_same
+    out["scores_bit_exact_vs_exact_plan"] = scores_same
+    out["exact_plan_queries_compared"] = int(ns)
+    # (1) exact scores of the returned rows, order, self-hit
+    ok_scores, ok_sorted = True, True
+    checked = sorted({0, min(1, nq - 1), nq // 2, nq - 1})
+    for qi in checked:
+        if packed:
+            rws = synthetic.rows_packed(SEED_CORPUS, grow[qi], dim // 64)
+            for j in range(k):
+                ok_scores &= bool(np.float32(oracle_mod.packed_distance(rig.queries[qi], rws[j], metric)) == gd[qi, j])
+            ok_sorted &= bool(np.all(np.diff(gd[qi]) >= 0)) and bool(np.all((np.diff(gd[qi]) > 0) | (np.diff(grow[qi].astype(np.int64)) > 0)))
+            continue
+        rws = synthetic.rows_f32(SEED_CORPUS, grow[qi], dim)
+        for j in range(k):
+            if metric == "ip":
+                want = oracle_mod.inner_product_batch8_order(rig.queries[qi], rws[j])
+            else:
+                want = oracle_mod.compute_distance(rig.queries[qi], rws[j], metric)
+            ok_scores &= bool(np.float32(want) == gd[qi, j])
+        d = gd[qi] if metric != "ip" else -gd[qi]
+        ok_sorted &= bool(np.all(np.diff(d) >= 0))
+    out.update({"scores_bit_exact_vs_oracle": ok_scores, "sorted": ok_sorted, "queries_checked": len(checked),
+                "self_hit_query0_row": int(grow[0, 0])})
+    # (3) the whole result against the oracle when the corpus is small enough for the CPU (C1)
+    if not packed and rig.world == 1 and rig.rows * dim <= 64_000_000:
+        corpus = rig.idx.read_rows(0, rig.rows)
+        seg, left = [], rig.rows
+        while left > 0:
+            seg.append(min(APPEND_ROWS, left))
+            left -= seg[-1]
+        o_ids, o_d, _ = oracle_mod.store_batch_search(corpus, rig.queries, k, metric, segment_rows=seg, n_threads=oracle_mod.host_threads())
+        out["ids_exact_vs_oracle_full_corpus"] = bool(np.array_equal(o_ids.astype(np.uint64), grow))
+        out["scores_bit_exact_vs_oracle_full_corpus"] = bool(np.array_equal(o_d.view(np.uint32), gd.view(np.uint32)))
+    return out
+
+
+def roofline_of(rig, res, peaks, args, info):
+    st, nq, dim = res["st"], rig.nq, rig.dim
+    dom_ms = statistics.mean(res["dom"]) if res["dom"] else float("nan")
+    flops_per_launch = 2.0 * nq * rig.n_local * dim  # algorithmic: 2*Q*N*D for this rank's shard (SURVEY.md 8d)
+    if st["plan_used"] in (1, 3) and dom_ms > 0:
+        ach = flops_per_launch / (dom_ms * 1e-3) / 1e12
+        eight = st["coarse_operand"] == 1
+        # 8-bit operands: tcgen05 kind::i8 is K = 32 per instruction at the issue cadence of kind::f16's K = 16
+        # (profiles/r2_mma_issue_probe.txt), so its ceiling is twice the measured bf16 one
+        peak = peaks["bf16_tflops_sustained"] * (2.0 if eight else 1.0)
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TOP/s" if eight else "TFLOP/s", "frac": ach / peak,
+                "traffic": ncu_traffic(args, rig.world, nq), "traffic_source": "profiles/r2_coarse_pair_ncu.json (ncu --set full, one launch of this command)",
+                "algorithmic_bytes": float(st["algorithmic_bytes"]),
+                "kernel": "lb::tc::coarse_pair_kernel" if nq > 128 else "lb::tc::coarse_single_kernel", "kernel_ms": dom_ms,
+                "operand": "u8 x u8 -> s32 (tcgen05 kind::i8)" if eight else "bf16 x bf16 -> f32 (tcgen05 kind::f16)",
+                "peak_source": peaks["source"] + (" sustained bf16 x 2 (8-bit operands run two K-steps per bf16 K-step)" if eight
+                                                  else " (sustained bf16: the kernel is timed inside a long step)"),
+                "hbm_gbs_of_kernel": st["algorithmic_bytes"] / (dom_ms * 1e-3) / 1e9,
+                "hbm_frac_of_kernel": st["algorithmic_bytes"] / (dom_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    if dom_ms > 0:
+        bytes_per_launch = float(st["algorithmic_bytes"])
+        ach = bytes_per_launch / (dom_ms * 1e-3) / 1e9
+        kname = "lb::scan_packed16_kernel" if st["plan_used"] == 2 else "lb::scan_stream_kernel"
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "kernel": kname, "kernel_ms": dom_ms, "peak_source": peaks["source"]}
+        if st["plan_used"] == 2 and nq > 8:
+            # at this batch size the packed scan is bound by the POPC pipe, not by HBM
+            pairs = float(nq) * rig.n_local
+            popc_peak = cuda_core_peak("popc_b32_per_clk_per_sm", 16.0) * info["sm_count"] * 1.965e9 / (dim // 32)
+            roofline.update({"bound": "popc", "achieved": pairs / (dom_ms * 1e-3), "peak": popc_peak, "unit": "pairs/s",
+                             "frac": pairs / (dom_ms * 1e-3) / popc_peak,
+                             "peak_source": "profiles/r2_cuda_core_peaks.json popc.b32 rate x SMs x 1.965 GHz / (dim/32 popc per pair)"})
+        return roofline
+    return None
+
+
+def cuda_core_peak(key, default):
+    try:
+        return float(json.loads((ROOT / "profiles" / "r2_cuda_core_peaks.json").read_text())[key])
+    except Exception:
+        return default
+
+
 def main():
     args = parse_args()
     metric, rows, dim, nq, k, desc = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    weak = args.workload in WEAK
+    if weak:
+        rows = rows * world // 8 if args.rows is None else rows  # 10M rows per GPU: the full 80M at 8 GPUs
     if args.rows:
         rows = args.rows
         desc += f" [rows overridden to {rows}]"
@@ -304,15 +529,12 @@ def main():
         return
 
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
     from lynsedb_b200 import _native as N
     from lynsedb_b200 import metrics as M
-    from lynsedb_b200 import synthetic
-    from lynsedb_b200.index import DeviceIndex
 
     lib = N.lib()
     dist = None
@@ -330,184 +552,77 @@ def main():
         dist.broadcast(t, src=0)
         N.check(lib.lb_comm_create(C.byref(comm), local_rank, world, rank, ident.ctypes.data_as(C.POINTER(C.c_uint8))))
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-
-        t = torch.tensor([x], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- corpus shard, generated on the device --------------------------------------------------------
-    from lynsedb_b200.sharding import shard_range
-
     packed = args.workload in PACKED
-    base, n_local = shard_range(rows, world, rank)
-    idx = DeviceIndex(dim, "packed" if packed else "float32", device=local_rank)
-    idx.reserve(n_local)
-    done = 0
-    while done < n_local:
-        m = min(APPEND_ROWS, n_local - done)
-        idx.append_synthetic(m, SEED_CORPUS, base + done)
-        done += m
-    idx.set_plan(args.plan)
-    m_id = M.require(metric)
-    idx.prepare(m_id)
-    idx.set_timing(True)
+    rig = Rig(args, lib, N, M, comm, rank, world, local_rank, metric, rows, dim, nq, k, packed, dist)
     info = N.device_info(local_rank)
-
-    queries = make_queries(metric, nq, dim, packed)
-    qbytes = queries.nbytes
-    # pinned host staging for the e2e path
-    hq, hrows, hdists, hcounts = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-    N.check(lib.lb_host_malloc(qbytes, C.byref(hq)))
-    N.check(lib.lb_host_malloc(nq * k * 8, C.byref(hrows)))
-    N.check(lib.lb_host_malloc(nq * k * 4, C.byref(hdists)))
-    N.check(lib.lb_host_malloc(nq * 4, C.byref(hcounts)))
-    C.memmove(hq, queries.ctypes.data, qbytes)
-    # device-resident buffers for the `value` path
-    dq, drows, ddists, dcounts = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-    N.check(lib.lb_device_malloc(local_rank, qbytes, C.byref(dq)))
-    N.check(lib.lb_device_malloc(local_rank, nq * k * 8, C.byref(drows)))
-    N.check(lib.lb_device_malloc(local_rank, nq * k * 4, C.byref(ddists)))
-    N.check(lib.lb_device_malloc(local_rank, nq * 4, C.byref(dcounts)))
-    N.check(lib.lb_memcpy_h2d(local_rank, dq, hq, qbytes))
-
-    def step_device():
-        N.check(lib.lb_sharded_search_device(comm, idx._h, m_id, dq, nq, k, base, drows, ddists, dcounts))
-
-    def step_host():
-        if packed:
-            N.check(lib.lb_sharded_search_packed(comm, idx._h, m_id, C.cast(hq, C.POINTER(C.c_uint64)), nq, k, base,
-                                                 C.cast(hrows, C.POINTER(C.c_uint64)), C.cast(hdists, C.POINTER(C.c_float)),
-                                                 C.cast(hcounts, C.POINTER(C.c_uint32))))
-            return
-        N.check(lib.lb_sharded_search(comm, idx._h, m_id, C.cast(hq, C.POINTER(C.c_float)), nq, k, base,
-                                      C.cast(hrows, C.POINTER(C.c_uint64)), C.cast(hdists, C.POINTER(C.c_float)),
-                                      C.cast(hcounts, C.POINTER(C.c_uint32))))
-
-    def timed(fn, steps, slot):
-        barrier()
-        N.check(lib.lb_device_synchronize(local_rank))
-        N.check(lib.lb_index_event_record(idx._h, slot))
-        dom, launches, fallbacks = [], 0, 0
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
-            st = idx.last_stats()
-            dom.append(st["ms_dominant"])
-            launches += st["kernels_launched"]
-            fallbacks += st["n_fallback"]
-        N.check(lib.lb_index_event_record(idx._h, slot + 1))
-        N.check(lib.lb_device_synchronize(local_rank))
-        wall_ms = (time.perf_counter() - t0) * 1000.0
-        ms = C.c_float(0)
-        N.check(lib.lb_index_event_elapsed_ms(idx._h, slot, slot + 1, C.byref(ms)))
-        barrier()
-        return max_over_ranks(float(ms.value)), wall_ms, dom, launches, fallbacks, idx.last_stats()
-
-    for _ in range(max(args.warmup, 3)):
-        step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, wall_dev, dom, launches, fallbacks, st = timed(step_device, args.steps, 0)
-    for _ in range(2):
-        step_host()
-    ms_e2e, wall_e2e, _, _, _, _ = timed(step_host, args.steps, 2)
+    res = rig.measure(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- sanity on the last e2e result: scores are the exact f32 values of the returned rows, best first ----
-    verified = None
-    if rank == 0:
-        import oracle
+    import oracle
 
-        grow = np.ctypeslib.as_array(C.cast(hrows, C.POINTER(C.c_uint64)), shape=(nq, k)).copy()
-        gd = np.ctypeslib.as_array(C.cast(hdists, C.POINTER(C.c_float)), shape=(nq, k)).copy()
-        ok_scores, ok_sorted = True, True
-        checked = sorted({0, min(1, nq - 1), nq // 2, nq - 1})
-        for qi in checked:
-            if packed:
-                rws = synthetic.rows_packed(SEED_CORPUS, grow[qi], dim // 64)
-                for j in range(k):
-                    ok_scores &= bool(np.float32(oracle.packed_distance(queries[qi], rws[j], metric)) == gd[qi, j])
-                ok_sorted &= bool(np.all(np.diff(gd[qi]) >= 0)) and bool(np.all((np.diff(gd[qi]) > 0) | (np.diff(grow[qi].astype(np.int64)) > 0)))
-                continue
-            rws = synthetic.rows_f32(SEED_CORPUS, grow[qi], dim)
-            for j in range(k):
-                if metric == "ip":
-                    want = oracle.inner_product_batch8_order(queries[qi], rws[j])
-                else:
-                    want = oracle.compute_distance(queries[qi], rws[j], metric)
-                ok_scores &= bool(np.float32(want) == gd[qi, j])
-            d = gd[qi] if metric != "ip" else -gd[qi]
-            ok_sorted &= bool(np.all(np.diff(d) >= 0))
-        verified = {"scores_bit_exact_vs_oracle": ok_scores, "sorted": ok_sorted, "queries_checked": len(checked),
-                    "self_hit_query0_row": int(grow[0, 0])}
-
-    value = nq * args.steps / (ms_dev / 1000.0)
-    e2e_value = nq * args.steps / (ms_e2e / 1000.0)
+    verified = verify_results(rig, args, oracle)
     peaks = measured_peaks()
-    dom_ms = statistics.mean(dom) if dom else float("nan")
-    flops_per_launch = 2.0 * nq * n_local * dim  # algorithmic: 2*Q*N*D for this rank's shard
-    roofline = None
-    if st["plan_used"] == 1 and dom_ms > 0:
-        ach = flops_per_launch / (dom_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(args, world, nq),
-                    "traffic_source": "profiles/r1_coarse_pair_ncu.json (ncu --set full, one launch of this command)",
-                    "algorithmic_bytes": float(st["algorithmic_bytes"]),
-                    "kernel": "lb::tc::coarse_pair_kernel" if nq > 128 else "lb::tc::coarse_single_kernel", "kernel_ms": dom_ms,
-                    "peak_source": peaks["source"] + " (sustained bf16: the kernel is timed inside a long step)",
-                    "hbm_gbs_of_kernel": st["algorithmic_bytes"] / (dom_ms * 1e-3) / 1e9}
-    elif dom_ms > 0:
-        bytes_per_launch = float(st["algorithmic_bytes"])
-        ach = bytes_per_launch / (dom_ms * 1e-3) / 1e9
-        kname = "lb::scan_packed16_kernel" if st["plan_used"] == 2 else "lb::scan_stream_kernel"
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": None, "kernel": kname, "kernel_ms": dom_ms, "peak_source": peaks["source"]}
-        if st["plan_used"] == 2:
-            # at this batch size the packed scan is bound by the POPC pipe, not by HBM: report both views
-            pairs = float(nq) * n_local
-            roofline["popc_note"] = {"pairs_per_s": pairs / (dom_ms * 1e-3), "popc32_per_pair": dim // 32,
-                                     "bound_pairs_per_s_at_16_popc_per_clk_per_sm": 16.0 * info["sm_count"] * 1.965e9 / (dim // 32)}
+    value = nq * args.steps / (res["ms_dev"] / 1000.0)
+    e2e_value = nq * args.steps / (res["ms_e2e"] / 1000.0)
+    st = res["st"]
+    roofline = roofline_of(rig, res, peaks, args, info)
+
+    # BASELINE configs[4] beside the headline when the default workload runs on several GPUs: 10M rows per GPU
+    # (80M x 768 at 8 GPUs), weak scaling, same queries, same path
+    extra = None
+    if world > 1 and args.workload == "c2" and not args.rows and not args.no_c5:
+        rig.close()
+        rig = Rig(args, lib, N, M, comm, rank, world, local_rank, metric, 10_000_000 * world, dim, nq, k, packed, dist)
+        r5 = rig.measure(max(3, args.steps // 2), 3)
+        steps5 = max(3, args.steps // 2)
+        v5 = verify_results(rig, args, oracle)
+        extra = {"workload": f"FLAT-IP {10 * world}M x 768 f32 row-sharded across {world} GPUs (10M rows per GPU), batch-1024, k=10 (BASELINE configs[4] at 8 GPUs)",
+                 "scaling": "weak", "rows": 10_000_000 * world, "value": nq * steps5 / (r5["ms_dev"] / 1000.0), "unit": "queries/s",
+                 "ms_per_step": r5["ms_dev"] / steps5, "e2e_value": nq * steps5 / (r5["ms_e2e"] / 1000.0), "e2e_ms_per_step": r5["ms_e2e"] / steps5,
+                 "kernel_ms": statistics.mean(r5["dom"]) if r5["dom"] else None, "fallback_queries": int(r5["fallbacks"]), "verified": v5}
 
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            sample_rows = min(args.cpu_sample_rows, n_local)
+            sample_rows = min(args.cpu_sample_rows, rig.n_local)
             if packed:
-                cpu_baseline = cpu_reference_packed_qps(metric, rows, dim, k, sample_rows, args.cpu_baseline_queries, queries)
+                cpu_baseline = cpu_reference_packed_qps(metric, rows, dim, k, sample_rows, args.cpu_baseline_queries, rig.queries)
             else:
-                corpus_sample = idx.read_rows(0, sample_rows)
-                cpu_baseline = cpu_reference_qps(metric, rows, dim, k, sample_rows, args.cpu_baseline_queries, corpus_sample, queries)
+                corpus_sample = rig.idx.read_rows(0, sample_rows)
+                cpu_baseline = cpu_reference_qps(metric, rows, dim, k, sample_rows, args.cpu_baseline_queries, corpus_sample, rig.queries)
+        eight = st["coarse_operand"] == 1
+        if st["plan_used"] == 3:
+            dtype = "u8 {0,1} contraction on tcgen05 kind::i8 (s32 accumulate) + exact u64 popcount rescore"
+        elif st["plan_used"] == 1:
+            dtype = ("u8 coarse contraction (s32 accumulate)" if eight else "bf16 coarse contraction (f32 accumulate)") + " + f32 exact-order rescore"
+        else:
+            dtype = "u64 popcount" if packed else "f32"
         line = {
             "metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": ("u64 popcount" if packed else ("bf16 coarse contraction (f32 accumulate) + f32 exact-order rescore" if st["plan_used"] == 1 else "f32")),
-            "data": "synthetic",
-            "config": {"workload": desc, "rows": rows, "rows_per_gpu": n_local, "dim": dim, "nq": nq, "k": k, "metric": metric,
-                       "sharding": f"contiguous row shards x{world}", "plan": args.plan,
+            "warmup": max(args.warmup, 3), "ms_per_step": res["ms_dev"] / args.steps, "higher_is_better": True,
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": desc, "rows": rows, "rows_per_gpu": rig.n_local if extra is None else (rows + world - 1) // world, "dim": dim,
+                       "nq": nq, "k": k, "metric": metric, "sharding": f"contiguous row shards x{world}", "plan": args.plan,
                        "l2_policy": "inputs larger than L2 (shadow %.1f GB per GPU vs 126 MB L2)" % (st["algorithmic_bytes"] / 1e9),
                        "device": info["name"], "sm_count": info["sm_count"]},
-            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(qbytes),
-                    "d2h_bytes_per_step": int(nq * k * 12 + nq * 4), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(rig.qbytes),
+                    "d2h_bytes_per_step": int(nq * k * 12 + nq * 4), "ms_per_step": res["ms_e2e"] / args.steps},
+            "gpu_launches": int(res["launches"]),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
-            "fallback_queries": int(fallbacks),
+            "fallback_queries": int(res["fallbacks"]),
             "partitions": int(st["n_partitions"]),
-            "wall_ms_per_step": wall_dev / args.steps,
+            "wall_ms_per_step": res["wall_dev"] / args.steps,
             "verified": verified,
         }
+        if extra is not None:
+            line["c5_weak"] = extra
         print(json.dumps(line), flush=True)
-    idx.close()
+    rig.close()
     if comm.value:
         lib.lb_comm_destroy(comm)
     if dist is not None:

@@ -164,7 +164,7 @@ int lb_index_search_device(lb_index* idx, int metric, const void* d_queries, uin
 
 /* Statistics of the most recent search on this index. */
 typedef struct lb_search_stats {
-    uint32_t plan_used;        /* 0 exact scan, 1 tensor coarse + rescore, 2 packed scan */
+    uint32_t plan_used;        /* 0 exact scan, 1 tensor coarse + rescore, 2 packed scan, 3 tensor coarse over {0,1} bytes + exact counts */
     uint32_t n_fallback;       /* queries whose shortlist was not certified and were re-run exactly */
     uint32_t n_partitions;     /* row partitions of the dominant kernel */
     uint32_t kernels_launched; /* kernels launched by the search call */
@@ -172,6 +172,8 @@ typedef struct lb_search_stats {
     float ms_total;            /* CUDA-event duration of all device work of the call */
     uint64_t algorithmic_bytes;/* bytes the dominant kernel must read once (shadow or corpus) */
     uint64_t algorithmic_flops;/* 2*nq*n*dim for the tensor path, else 0 */
+    uint32_t coarse_operand;   /* tensor plans: 0 = bf16 operands (f32 accumulators), 1 = 8-bit operands (s32 accumulators) */
+    uint32_t coarse_hit_mode;  /* tensor plans: 1 = rows above a seeded floor were appended to per-query hit buffers (large k) */
 } lb_search_stats;
 int lb_index_set_timing(lb_index* idx, int enabled);
 int lb_index_last_stats(const lb_index* idx, lb_search_stats* out);
@@ -230,8 +232,19 @@ int lb_comm_barrier(lb_comm* c);
  * global u64 rows.  comm == NULL means a single shard.  Requires k <= rows of every shard. */
 int lb_sharded_search(lb_comm* comm, lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k,
                       uint64_t row_base, uint64_t* out_rows, float* out_dists, uint32_t* out_counts);
+/* the same with a row filter over this rank's shard (allow_bits: bit r = local row r allowed, as lb_index_search):
+ * Collection.search(where=...) / tombstoned rows on a sharded collection (src/storage/vector_store.rs:1006-1039). */
+int lb_sharded_search_filtered(lb_comm* comm, lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k,
+                               uint64_t row_base, const uint64_t* allow_bits, uint64_t allow_words, uint64_t* out_rows,
+                               float* out_dists, uint32_t* out_counts);
 int lb_sharded_search_packed(lb_comm* comm, lb_index* idx, int metric, const uint64_t* query_words, uint32_t nq, uint32_t k,
                              uint64_t row_base, uint64_t* out_rows, float* out_dists, uint32_t* out_counts);
+/* The merge step of the sharded search by itself (tests): n_shards blocks of [nq][k] u32 local rows / f32 scores,
+ * [nq] counts and one row base per shard, laid out shard-major, merged by (score, global row) on `device` —
+ * VectorStore::merge_results (src/storage/vector_store.rs:953-970). */
+int lb_merge_shard_blocks(int device, int metric, int n_shards, uint32_t nq, uint32_t k, const uint32_t* rows, const float* dists,
+                          const uint32_t* counts, const uint64_t* row_bases, uint64_t* out_rows, float* out_dists,
+                          uint32_t* out_counts);
 int lb_sharded_search_device(lb_comm* comm, lb_index* idx, int metric, const void* d_queries, uint32_t nq, uint32_t k,
                              uint64_t row_base, uint64_t* d_out_rows, float* d_out_dists, uint32_t* d_out_counts);
 
@@ -240,13 +253,15 @@ int lb_index_event_record(lb_index* idx, int slot);
 int lb_index_event_elapsed_ms(lb_index* idx, int slot_a, int slot_b, float* ms);
 
 /* ---- diagnostics -------------------------------------------------------- */
-/* Runs the tensor-core coarse kernel on a small problem and dumps the raw
- * accumulator scores [nq][n] (debug builds of the parity tests use it to pin
- * the tcgen05 operand layouts). */
-int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uint32_t n, uint32_t dim, float* out);
-/* tcgen05.mma issue-rate probe (M=128, K=16, bf16): `iters` MMAs round-robin over n_acc accumulators of n columns,
- * A from TMEM (a_in_tmem=1) or shared memory; returns SM cycles (max over CTAs) to completion and to end of issue. */
-int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int grid, uint64_t* cycles_total, uint64_t* cycles_issue);
+/* Runs the tensor-core coarse kernel (inner product) on a small problem and dumps the raw coarse keys [nq][n]
+ * (the parity tests use it to pin the tcgen05 operand layouts).  operand 0: bf16 operands, keys = f32 accumulators;
+ * operand 1: 8-bit operands (rows: u8 with one zero point / scale for the corpus; queries: u8, or s8 when the batch
+ * holds a negative element), keys = the integer accumulators sum(qhat * chat), returned as f32. */
+int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uint32_t n, uint32_t dim, int operand, float* out);
+/* tcgen05.mma issue-rate probe (M=128; kind::f16 K=16 bf16, or kind::i8 K=32 when i8 != 0): `iters` MMAs round-robin
+ * over n_acc accumulators of n columns, A from TMEM (a_in_tmem=1) or shared memory; returns SM cycles (max over CTAs)
+ * to completion and to end of issue. */
+int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int i8, int grid, uint64_t* cycles_total, uint64_t* cycles_issue);
 
 #ifdef __cplusplus
 }

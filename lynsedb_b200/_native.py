@@ -32,6 +32,8 @@ class SearchStats(C.Structure):
         ("ms_total", C.c_float),
         ("algorithmic_bytes", C.c_uint64),
         ("algorithmic_flops", C.c_uint64),
+        ("coarse_operand", C.c_uint32),
+        ("coarse_hit_mode", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -91,12 +93,14 @@ SIGNATURES = {
     "lb_comm_allgather": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "lb_comm_barrier": (C.c_int, [_vp]),
     "lb_sharded_search": (C.c_int, [_vp, _vp, C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint64, _u64p, _f32p, _u32p]),
+    "lb_sharded_search_filtered": (C.c_int, [_vp, _vp, C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint64, _u64p, C.c_uint64, _u64p, _f32p, _u32p]),
+    "lb_merge_shard_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _u32p, _f32p, _u32p, _u64p, _u64p, _f32p, _u32p]),
     "lb_sharded_search_packed": (C.c_int, [_vp, _vp, C.c_int, _u64p, C.c_uint32, C.c_uint32, C.c_uint64, _u64p, _f32p, _u32p]),
     "lb_sharded_search_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_uint64, _vp, _vp, _vp]),
     "lb_index_event_record": (C.c_int, [_vp, C.c_int]),
     "lb_index_event_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
-    "lb_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p]),
-    "lb_debug_tc_scores": (C.c_int, [_f32p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p]),
+    "lb_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p]),
+    "lb_debug_tc_scores": (C.c_int, [_f32p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, C.c_int, _f32p]),
 }
 
 _lib = None

@@ -47,6 +47,7 @@ __host__ __device__ inline uint32_t f32_orderable(float f) {
 #endif
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__host__ __device__ inline uint32_t f32_orderable_bits(uint32_t u) { return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __host__ __device__ inline float f32_from_orderable(uint32_t o) {
     uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
 #ifdef __CUDA_ARCH__

@@ -53,6 +53,10 @@ struct DevBuf {
     }
     template <class T>
     T* as() const { return reinterpret_cast<T*>(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
 };
 
 // pinned host staging memory (small batches copy through it: a copy from pageable memory is staged and
@@ -78,18 +82,41 @@ struct HostBuf {
         p = nullptr;
         cap = 0;
     }
+    HostBuf() = default;
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+    ~HostBuf() { release(); }
 };
 
 struct Shadow {
-    DevBuf buf;           // tiled, pre-swizzled bf16 rows (layout: lb_tc.cuh)
+    DevBuf buf;           // tiled, pre-swizzled operand rows (layout: lb_tc.cuh)
+    DevBuf side;          // per-row side values, padded to whole tiles: f32 |c|^2 (L2 shadow), u32 popcount (bit shadow)
+    DevBuf side2;         // bit shadow: the popcounts as f32 (Jaccard / Dice keys)
+    DevBuf stats;         // tc::ShadowStats on the device
     uint64_t rows = 0;    // rows converted so far
     uint64_t cap_tiles = 0;
-    int Dp = 0;
+    int Dp = 0;           // operand row length in 2-byte units (bf16: padded dim; 8-bit: padded dim / 2)
+    int operand = -1;     // tc::OperandKind, chosen when the shadow is first built
+    float c_scale = 1.0f, c_zero = 0.0f;  // 8-bit operands: value = c_zero + c_scale * u8
+    float range_lo = 0.0f, range_hi = 0.0f;  // element range the quantisation was built for
+    float cmax = 0.0f, emax = 0.0f;          // host copies of the statistics (diagnostics)
+    bool disabled = false;                  // non-finite rows: the plan is not used
     // [0] one-CTA kernel (both halves of a K block per box), [1] CTA-pair kernel (one half); .full = KPS K blocks per
     // box, .rem = the partial last stage of a tile ((Dp/64) % KPS K blocks)
     CUtensorMap tmap_full[2], tmap_rem[2];
     uint64_t tmap_tiles = 0;
     void* tmap_ptr = nullptr;
+    void release() {
+        buf.release();
+        side.release();
+        side2.release();
+        stats.release();
+        rows = 0;
+        cap_tiles = 0;
+        tmap_tiles = 0;
+        tmap_ptr = nullptr;
+        operand = -1;
+    }
 };
 
 inline int next_pow2(int x) {
@@ -159,7 +186,8 @@ struct lb_index {
     uint64_t js_rows = 0;
     DevBuf mass_stats;       // Wasserstein: f64 row sums, rows [0, mass_rows)
     uint64_t mass_rows = 0;
-    Shadow shadow[3];
+    Shadow shadow[3];        // IP, cosine, L2 (tc::ShadowKind)
+    Shadow bits_shadow;      // the packed rows as {0,1} bytes (binary metrics on the tensor cores)
     DevBuf max_norm;  // 3 floats, one per shadow kind
     DevBuf small_seg;
     int n_small = 0;
@@ -168,6 +196,7 @@ struct lb_index {
     DevBuf w_queries, w_qwords, w_allow, w_lists, w_counts, w_thr, w_out_rows, w_out_dists, w_out_counts;
     DevBuf w_out;            // host-buffer searches: [rows | dists | counts] of one batch, so that one copy brings them back
     HostBuf h_in, h_out;     // pinned staging for small batches
+    HostBuf h_tails;         // sharded search: the gathered block tails (one read per step)
     DevBuf w_qb, w_qnorm, w_cand_score, w_cand_row, w_cand_thr, w_flags, w_qstats, w_nq, w_sub_q, w_qmap;
     int plan = LB_PLAN_AUTO;
     // how the running search scores a pair (set under `mu` for the duration of one host-buffer search):
@@ -180,6 +209,20 @@ struct lb_index {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf w_send, w_recv, w_g_rows, w_g_dists, w_g_counts, w_progress, w_prof, w_gfloor;
+    DevBuf w_qaux, w_qrange, w_hits, w_hit_count;
+    // a tensor-core search whose certification flags have not been read back yet (tc_finish)
+    struct PendingTc {
+        bool active = false;
+        int metric = 0, nq = 0, k = 0, bits = 0, n_words = 0;
+        const void* d_queries = nullptr;
+        const uint64_t* d_allow = nullptr;
+        const uint64_t* words = nullptr;
+        uint32_t* d_rows = nullptr;
+        float* d_dists = nullptr;
+        uint32_t* d_counts = nullptr;
+        int grid = 0, cluster = 0, n_slots = 0, P = 0;
+        bool pair = false;
+    } pending_tc;
 };
 
 namespace lb {
@@ -231,9 +274,18 @@ int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom);
 int refresh_small_segments(lb_index* idx);
 // lb_tc_plan.cu: tensor-core coarse pass + exact rescore (IP / cosine / L2)
 int shadow_kind_for(int metric);
-bool tc_supported(const lb_index* idx, int metric);
+bool tc_supported(lb_index* idx, int metric);
 int ensure_shadow(lb_index* idx, int kind);
+// Enqueues prepare -> coarse -> finalize on idx->stream.  defer_check: the certification flags are not read back here;
+// the caller must call tc_finish (after whatever it enqueues behind the search) before it trusts the results.
 int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uint32_t* d_rows, float* d_dists, uint32_t* d_counts,
-           float* dump, const uint64_t* d_allow = nullptr);
+           float* dump, const uint64_t* d_allow = nullptr, bool defer_check = false);
+// the binary metrics (Hamming / Jaccard / Tanimoto / Dice) over packed rows as a {0,1} 8-bit contraction
+bool tc_bits_supported(lb_index* idx, int metric, int n_words, int nq, int k);
+int run_tc_bits(lb_index* idx, int metric, const uint64_t* words, int n_words, const uint64_t* d_qwords, int nq, int k, uint32_t* d_rows,
+                float* d_dists, uint32_t* d_counts, const uint64_t* d_allow = nullptr, bool defer_check = false);
+// Synchronises the stream, reads the flags of the pending tensor-core search and re-runs uncertified queries with the
+// exact scan.  *changed (optional) = results were rewritten (anything enqueued behind the search saw stale results).
+int tc_finish(lb_index* idx, bool* changed = nullptr);
 
 }  // namespace lb

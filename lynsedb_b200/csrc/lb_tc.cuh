@@ -49,32 +49,55 @@ constexpr int TMEM_COLS = 512;
 constexpr int DCOL = TMEM_COLS - 2 * BN;  // accumulators: two buffers of BN columns at [384, 512)
 constexpr uint32_t SMEM_RING_BYTES = 196608;                          // staging ring of either kernel
 constexpr uint32_t SMEM_BAR_OFF = SMEM_RING_BYTES;
-constexpr uint32_t SMEM_BYTES = SMEM_BAR_OFF + 256 + 1024;            // + barriers + alignment slack
+constexpr uint32_t SMEM_SCRATCH_OFF = SMEM_BAR_OFF + 256;               // per-epilogue-warp scratch (side values of a tile)
+constexpr uint32_t SMEM_BYTES = SMEM_SCRATCH_OFF + 8 * 256 + 1024;      // + barriers + scratch of 8 warps + alignment slack
+
+// How the 32-bit accumulator of a (query, row) pair becomes the coarse KEY the epilogue ranks by (larger = better).
+//   mode            operands        accumulator   key                                   side values
+//   CM_F32          bf16 x bf16     f32           acc                                   —
+//   CM_F32_BIAS     bf16 x bf16     f32           acc - bias[row]        (L2: 2q.c-|c|^2) bias = f32 |c|^2 per row
+//   CM_I32          u8/s8 x u8      s32           acc                    (integer)      —
+//   CM_I32_HAMMING  {0,1} x {0,1}   s32           2 acc - bias[row]      (integer)      bias = popcount(row)
+//   CM_JACCARD      {0,1} x {0,1}   s32           acc / (pa + pb - acc)  (f32)          bias = popcount(row), qaux = popcount(query)
+//   CM_DICE         {0,1} x {0,1}   s32           2 acc / (pa + pb)      (f32)          as above
+enum CoarseMode { CM_F32 = 0, CM_F32_BIAS = 1, CM_I32 = 2, CM_I32_HAMMING = 3, CM_JACCARD = 4, CM_DICE = 5 };
+template <int MODE>
+struct ModeTraits {
+    static constexpr bool kI8 = MODE >= CM_I32;                            // tcgen05 kind::i8 (K = 32 per MMA) instead of kind::f16 (K = 16)
+    static constexpr bool kIntKey = MODE == CM_I32 || MODE == CM_I32_HAMMING;
+    static constexpr bool kBias = MODE == CM_F32_BIAS || MODE >= CM_I32_HAMMING;
+    using Key = typename std::conditional<kIntKey, int, float>::type;
+};
 
 struct TcArgs {
-    const __nv_bfloat16* qb;  // [n_mtiles*128][Dp] bf16 queries, zero padded
+    const unsigned char* qb;  // [n_mtiles*128][2*Dp bytes] A operand rows (bf16 or 8-bit), zero padded
     int nq;
     int n_mtiles;             // query tiles of 128; qb is padded to a multiple of the cluster size tiles
-    int Dp;                   // padded dim, multiple of 64, <= MAX_DP
+    int Dp;                   // operand row length in 2-byte units (bf16 elements; 8-bit operands: elements / 2), multiple of 64
     int rem_kb;               // (Dp / 64) % KPS: K blocks of the last, partial stage of a tile (0 = none; uses tmap_rem)
     uint32_t n_rows;
-    uint32_t tiles_total;     // ceil(n_rows / 64)
+    uint32_t tiles_total;     // ceil(n_rows / rows per tile)
     uint32_t tiles_per_part;
     int P;                    // row partitions
     int lists_per_part;       // shortlists per (query, partition): 1, or 2 when the pair kernel runs two epilogue sets
     const uint64_t* allow_bits;  // optional row filter (bit r = row r allowed, LSB-first u64 words): disallowed rows never
                                  // enter a shortlist, so floors, certification and result are those of the allowed rows
-    float* cand_score;        // [nq][P * lists_per_part][KP]
+    const uint32_t* bias;     // per-row side value (CoarseMode), padded to whole tiles (+inf / huge past the last row)
+    const float* qaux;        // per-query side value (CoarseMode), padded like qb
+    const uint32_t* idesc_extra;  // device word OR-ed into the instruction descriptor (8-bit operands: signedness bits)
+    uint32_t* cand_key;       // [nq][P * lists_per_part][KP]  key bits (f32 or s32, see ModeTraits)
     uint32_t* cand_row;       // [nq][P * lists_per_part][KP]
-    float* cand_thr;          // [nq][P * lists_per_part]
+    uint32_t* cand_thr;       // [nq][P * lists_per_part]      key bits: every row dropped by the list scored <= this
     int share_floor;          // 1: partitions of a query share a shortlist floor through gthr; 2: gthr holds a floor seeded by a
                               // pre-pass over a sample of the corpus and is only read (large k)
-    int floor_group;          // m: a published floor is the minimum of the floors of m consecutive partitions, so that at
-                              // least m * KP rows score above it (m = 1 when k <= KP - 4, else ~10 k / KP)
-    float* gfloor;            // [nq][P] floors of the single partitions (initialised to -inf; used when m > 1)
-    uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable f32 bits)
+    uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable key bits)
+    // hit mode (with share_floor == 2): rows above the seeded floor are appended to a per-query buffer instead of
+    // going through the register shortlists
+    uint32_t* hit_count;      // [nq] zero-initialised; null = shortlist mode
+    uint2* hit_buf;           // [nq][hit_cap] (key bits, row)
+    uint32_t hit_cap;
     uint32_t* error_flag;     // set non-zero when a barrier wait timed out
-    float* dump;              // optional [n_mtiles*128][tiles_total*64] raw scores (diagnostics)
+    float* dump;              // optional [n_mtiles*128][tiles_total*rows per tile] keys as f32 (diagnostics)
     // Work mapping: cluster c serves query group (c % n_mgroups) of slot (c / n_mgroups); slot s walks the row
     // partitions s, s + n_slots, s + 2 n_slots, ...  All query groups of a slot stream the same shadow tiles at the
     // same time, so HBM is read once per slot and the other groups are served from L2.
@@ -82,14 +105,12 @@ struct TcArgs {
     int parts_per_slot;
     uint32_t* progress;       // [n_slots][PROGRESS_STRIDE] tiles issued per (slot, query group); zeroed per launch; null = free-running
     int window;               // a query group never runs more than `window` tiles ahead of the slowest group of its slot
-    int prefetch_tiles;       // L2 prefetch distance of the TMA producer, in tiles (0 = off)
-    int sample_tiles;         // > 0: every CTA first scans tiles [0, sample_tiles) only to warm up its shortlist floors
-                              // (round -1, nothing recorded), so the real partitions never start with an open gate
     unsigned long long* prof; // optional [grid][8] cycle counters of the MMA issuer / epilogue (diagnostics)
     int debug_mode;           // diagnostics only (results are garbage): bit 0 = producer skips the TMA loads,
                               // bit 1 = epilogue releases accumulators unread, bit 2 = epilogue reads but does not scan
 };
 constexpr int PROGRESS_STRIDE = 32;
+constexpr uint32_t EPI_SCRATCH_WORDS = 64;   // per epilogue warp: the side values of the 64 rows being scanned
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,6 +196,22 @@ __device__ __forceinline__ void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, u
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with 8-bit integer operands (K = 32 per instruction), s32 accumulators
+__device__ __forceinline__ void umma_ts_i8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Instruction descriptors (cute::UMMA::InstrDescriptor): accumulator format at [4,6) (1 = f32, 2 = s32), A / B format at
+// [7,10) / [10,13) (kind::f16: 1 = bf16; kind::i8: 0 = unsigned, 1 = signed), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t IDESC_A_SIGNED = 1u << 7, IDESC_B_SIGNED = 1u << 10;
+template <bool I8>
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (I8 ? (2u << 4) : ((1u << 4) | (1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -256,7 +293,6 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
     return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 
 // ---- pieces shared by the two coarse kernels ------------------------------------------------------------------
 __device__ __forceinline__ bool elect_one() {
@@ -274,8 +310,9 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return d;
 }
 
-// A operand: the calling thread's query row (bf16 pairs) into TMEM columns [0, Dp/2) of its lane.
-__device__ __forceinline__ void load_query_to_tmem(const __nv_bfloat16* qrow, int Dp, uint32_t lane_addr) {
+// A operand: the calling thread's query row (2*Dp bytes: bf16 pairs or 8-bit quads per word) into TMEM columns
+// [0, Dp/2) of its lane.
+__device__ __forceinline__ void load_query_to_tmem(const unsigned char* qrow, int Dp, uint32_t lane_addr) {
     const uint4* src = reinterpret_cast<const uint4*>(qrow);
     for (int c = 0; c < Dp / 32; ++c) {
         uint32_t w[16];
@@ -295,256 +332,440 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
-// Per-thread shortlist of one (query, row partition): the KP best coarse scores, held in REGISTERS (every index is
-// a compile-time constant) and gated by a register threshold — shared-memory lists stall for thousands of cycles
-// behind the tensor core's operand reads and the TMA writes.  lmin = worst score kept; thr_g = best floor any
-// partition of the query has published through gthr (a row at or below it is outside the global top KP).
-struct Shortlist {
-    float sc[KP];
-    uint32_t rw[KP];
-    float lmin, thr_g, thr_pub;
-    uint32_t g_bits;
-    uint32_t* gthr;
-    float* gfloor_q;     // floors of this query's partitions (floor groups)
-    int group_m, n_parts, part;
-    bool q_valid, share, may_publish;
+// ---- coarse keys ---------------------------------------------------------------------------------------------
+template <class K>
+struct KeyOps;
+template <>
+struct KeyOps<float> {
+    static __device__ __forceinline__ float lowest() { return -INFINITY; }
+    static __device__ __forceinline__ float highest() { return INFINITY; }
+    static __device__ __forceinline__ float max3(float a, float b, float c) { return fmax3(a, b, c); }
+    static __device__ __forceinline__ float min3(float a, float b, float c) { return fmin3(a, b, c); }
+    static __device__ __forceinline__ float from_bits(uint32_t u) { return __uint_as_float(u); }
+    static __device__ __forceinline__ uint32_t bits(float x) { return __float_as_uint(x); }
+    static __device__ __forceinline__ uint32_t orderable(float x) { return f32_orderable(x); }
+    static __device__ __forceinline__ float from_orderable(uint32_t o) { return f32_from_orderable(o); }
+    static __device__ __forceinline__ float as_f32(float x) { return x; }
+};
+template <>
+struct KeyOps<int> {
+    static __device__ __forceinline__ int lowest() { return (int)0x80000000; }
+    static __device__ __forceinline__ int highest() { return 0x7fffffff; }
+    static __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }  // VIMNMX3
+    static __device__ __forceinline__ int min3(int a, int b, int c) { return min(min(a, b), c); }
+    static __device__ __forceinline__ int from_bits(uint32_t u) { return (int)u; }
+    static __device__ __forceinline__ uint32_t bits(int x) { return (uint32_t)x; }
+    static __device__ __forceinline__ uint32_t orderable(int x) { return (uint32_t)x ^ 0x80000000u; }  // lowest() -> 0 = "unset"
+    static __device__ __forceinline__ int from_orderable(uint32_t o) { return (int)(o ^ 0x80000000u); }
+    static __device__ __forceinline__ float as_f32(int x) { return (float)x; }
+};
+// host / finalize side: key bits -> a 32-bit value whose unsigned order is the key order
+__host__ __device__ inline uint32_t key_bits_orderable(uint32_t bits, bool int_key) { return int_key ? (bits ^ 0x80000000u) : f32_orderable_bits(bits); }
 
-    __device__ __forceinline__ void set_groups(float* gfloor_row, int m, int P) {
-        gfloor_q = gfloor_row;
-        group_m = m;
-        n_parts = P;
-    }
-    // The list is full and its floor rose: make it visible to the other partitions of the query.  With floor groups
-    // the value that may gate everybody is the smallest floor of the m partitions of my group (every member has KP
-    // rows above its own floor, hence m * KP rows above the minimum); incomplete groups publish nothing.
-    __device__ __forceinline__ void publish() {
-        if (group_m <= 1) {
-            atomicMax(gthr, f32_orderable(lmin));
-        } else {
-            __stcg(gfloor_q + part, lmin);
-            const int g0 = (part / group_m) * group_m, g1 = g0 + group_m;
-            if (g1 <= n_parts) {
-                float mn = lmin;
-                int p = g0;
-                for (; p + 8 <= g1; p += 8) {  // independent loads: one L2 round trip per eight floors
-                    float f[8];
+// accumulator words -> key bits, in place, for the 64 rows whose side values sit in `side` (shared memory, one word per row)
+template <int MODE>
+__device__ __forceinline__ void keys_from_accumulators(uint32_t* v, const uint32_t* side, float qaux) {
+    constexpr int N = (MODE == CM_F32 || MODE == CM_I32) ? 0 : 64;  // these two modes rank the accumulator itself
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = __ldcg(gfloor_q + p + i);
+    for (int i = 0; i < N; i += 4) {
+        const uint4 s4 = *reinterpret_cast<const uint4*>(side + i);  // same address in every lane: one broadcast read
+        const uint32_t s[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) mn = fminf(mn, f[i]);
-                }
-                for (; p < g1; ++p) mn = fminf(mn, __ldcg(gfloor_q + p));
-                if (mn > -INFINITY) atomicMax(gthr, f32_orderable(mn));
+        for (int j = 0; j < 4; ++j) {
+            if (MODE == CM_F32_BIAS) {
+                v[i + j] = __float_as_uint(__fsub_rn(__uint_as_float(v[i + j]), __uint_as_float(s[j])));
+            } else if (MODE == CM_I32_HAMMING) {
+                const int acc = (int)v[i + j];
+                v[i + j] = (uint32_t)(acc + acc - (int)s[j]);
+            } else {
+                // intersection count (< 2^23) -> f32 without a conversion instruction
+                const float inter = __fsub_rn(__uint_as_float(v[i + j] | 0x4B000000u), 8388608.0f);
+                const float both = __fadd_rn(qaux, __uint_as_float(s[j]));  // popcount(query) + popcount(row), exact
+                const float den = MODE == CM_JACCARD ? __fsub_rn(both, inter) : both;
+                const float num = MODE == CM_JACCARD ? inter : __fadd_rn(inter, inter);
+                // empty query and empty row: the reference's distance is 0 (the best), i.e. similarity 1
+                v[i + j] = __float_as_uint(den > 0.0f ? __fdividef(num, den) : 1.0f);
             }
         }
+    }
+}
+
+// Per-thread shortlist of one (query, row partition): the KP best coarse keys, held in REGISTERS (every index is
+// a compile-time constant) and gated by a register threshold — shared-memory lists stall for thousands of cycles
+// behind the tensor core's operand reads and the TMA writes.  lmin = worst key kept; thr_g = best floor any
+// partition of the query has published through gthr (a row at or below it is outside the global top KP).
+// In hit mode (seeded floor, large k) the list is not used: a row above the floor goes to the query's hit buffer.
+template <class K>
+struct Shortlist {
+    using O = KeyOps<K>;
+    K sc[KP];
+    uint32_t rw[KP];
+    K lmin, thr_g, thr_pub;
+    uint32_t g_bits;
+    uint32_t* gthr;
+    uint32_t* hit_count;
+    uint2* hit_buf;
+    uint32_t hit_cap;
+    bool q_valid, share, may_publish;
+
+    // The list is full and its floor rose: make it visible to the other partitions of the query.
+    __device__ __forceinline__ void publish() {
+        atomicMax(gthr, O::orderable(lmin));
         thr_pub = lmin;
     }
-
-    __device__ __forceinline__ void reset(bool valid, int share_floor, uint32_t* gthr_q) {
+    __device__ __forceinline__ void reset(bool valid, int share_floor, uint32_t* gthr_q, const TcArgs& a, uint32_t gq) {
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
-            sc[j] = -INFINITY;
+            sc[j] = O::lowest();
             rw[j] = ROW_NONE;
         }
         q_valid = valid;
         share = share_floor != 0;
         may_publish = share_floor == 1;
         gthr = gthr_q;
+        hit_count = nullptr;
         if (share_floor == 2 && valid) {  // seeded floor: available from the first tile
             const uint32_t bits = *reinterpret_cast<volatile uint32_t*>(gthr_q);
-            if (bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(bits));
+            if (bits != 0u) thr_g = max(thr_g, O::from_orderable(bits));
+            if (a.hit_count != nullptr) {
+                hit_count = a.hit_count + gq;
+                hit_buf = a.hit_buf + (size_t)gq * a.hit_cap;
+                hit_cap = a.hit_cap;
+            }
         }
-        lmin = -INFINITY;
-        thr_pub = -INFINITY;
+        lmin = O::lowest();
+        thr_pub = O::lowest();
     }
     __device__ __forceinline__ void init_floor() {
-        thr_g = -INFINITY;
+        thr_g = O::lowest();
         g_bits = 0u;
     }
-    __device__ __forceinline__ float gate() const { return q_valid ? fmaxf(lmin, thr_g) : INFINITY; }
-    // end of the warm-up round: the KP-th best score of the sample is a valid floor for every partition (KP rows of
-    // the corpus score at least that much), so it becomes the shared floor and the list starts over
-    __device__ __forceinline__ void absorb_sample() {
-        if (may_publish && q_valid && group_m <= 1 && lmin > thr_g) {
-            thr_g = lmin;
-            atomicMax(gthr, f32_orderable(lmin));
-        }
-    }
+    __device__ __forceinline__ K gate() const { return q_valid ? max(lmin, thr_g) : O::highest(); }
     // refresh the shared floor every 8th tile; the load issued now is consumed 8 tiles later, so its (loaded) L2
     // latency never sits on the per-tile critical path
     __device__ __forceinline__ void poll_floor(uint32_t tile_iter) {
         if (share && (tile_iter & 7u) == 0u) {
-            if (g_bits != 0u) thr_g = fmaxf(thr_g, f32_from_orderable(g_bits));
+            if (g_bits != 0u) thr_g = max(thr_g, O::from_orderable(g_bits));
             g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
-            if (may_publish && group_m > 1 && q_valid && lmin > thr_pub) publish();
         }
     }
-    // replace the current minimum by (score, row) and recompute the minimum: ~70 ALU instructions, no memory
-    __device__ __forceinline__ void insert(float score, uint32_t row) {
+    // replace the current minimum by (key, row) and recompute the minimum: ~70 ALU instructions, no memory
+    __device__ __forceinline__ void insert(K key, uint32_t row) {
         bool done = false;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             const bool hit = !done && sc[j] == lmin;
-            sc[j] = hit ? score : sc[j];
+            sc[j] = hit ? key : sc[j];
             rw[j] = hit ? row : rw[j];
             done = done || hit;
         }
-        float m0 = fmin3(sc[0], sc[1], sc[2]), m1 = fmin3(sc[3], sc[4], sc[5]);
-        m0 = fmin3(m0, sc[6], sc[7]);
-        m1 = fmin3(m1, sc[8], sc[9]);
-        m0 = fmin3(m0, sc[10], sc[11]);
-        m1 = fmin3(m1, sc[12], sc[13]);
-        lmin = fmin3(fminf(m0, m1), sc[14], sc[15]);
+        K m0 = O::min3(sc[0], sc[1], sc[2]), m1 = O::min3(sc[3], sc[4], sc[5]);
+        m0 = O::min3(m0, sc[6], sc[7]);
+        m1 = O::min3(m1, sc[8], sc[9]);
+        m0 = O::min3(m0, sc[10], sc[11]);
+        m1 = O::min3(m1, sc[12], sc[13]);
+        lmin = O::min3(min(m0, m1), sc[14], sc[15]);
     }
-    // 64 accumulator columns of this thread's query = rows row0 .. row0+63.  Called by whole warps.
+    __device__ __forceinline__ void record(K key, uint32_t row) {
+        if (hit_count != nullptr) {
+            const uint32_t slot = atomicAdd(hit_count, 1u);
+            if (slot < hit_cap) hit_buf[slot] = make_uint2(O::bits(key), row);
+        } else {
+            insert(key, row);
+        }
+    }
+    // 32 keys of this thread's query = rows row0 .. row0+31, at least one lane of the warp above its gate.
+    __device__ __forceinline__ void slow32(const uint32_t* v, K gmax, uint32_t row0, uint32_t row_end, K thr, uint32_t allow_word,
+                                           bool have_allow) {
+        uint32_t mask = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mask |= (O::from_bits(v[i]) > thr ? 1u : 0u) << i;
+        const uint32_t raw = mask;
+        if (row0 + 32u > row_end) {  // last tile: rows past the end of the corpus never enter a list
+            const uint32_t n_ok = row_end > row0 ? row_end - row0 : 0u;
+            mask &= n_ok >= 32u ? 0xffffffffu : ((1u << n_ok) - 1u);
+        }
+        if (have_allow) mask &= allow_word;
+        // a lane with exactly one hit (the usual case) already holds its key: it is the group maximum — unless the
+        // masks above removed a hit, in which case the maximum may belong to a removed row
+        if (mask == raw && __popc(mask) == 1) {
+            record(gmax, row0 + (uint32_t)(__ffs((int)mask) - 1));
+            mask = 0u;
+        }
+#pragma unroll 1
+        while (__any_sync(0xffffffffu, mask != 0u)) {
+            if (mask != 0u) {
+                const int idx = __ffs((int)mask) - 1;
+                mask &= mask - 1u;
+                // v[idx] with a run-time idx: 5-level select tree over the register array (31 selects)
+                uint32_t t4[16], t3[8], t2[4], t1[2];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t4[j] = (idx & 16) ? v[16 + j] : v[j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t3[j] = (idx & 8) ? t4[8 + j] : t4[j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t2[j] = (idx & 4) ? t3[4 + j] : t3[j];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) t1[j] = (idx & 2) ? t2[2 + j] : t2[j];
+                const K x = O::from_bits((idx & 1) ? t1[1] : t1[0]);
+                if (x > gate()) record(x, row0 + (uint32_t)idx);  // the gate may have risen since the mask was taken
+            }
+        }
+    }
+    // 64 keys of this thread's query = rows row0 .. row0+63.  Called by whole warps.
+    // The slow path must stay SMALL: a fully unrolled "for each of the 64 keys: compare, insert" is ~90 KB of code
+    // whose sparse execution misses the instruction cache at every step (~7700 cycles per tile measured).  So: the
+    // maxima of the two 32-key groups gate (1) a 32-bit hit mask per lane from straight compares and (2) a rolled loop
+    // that pops each lane's lowest hit and fetches the key with a select tree.
     __device__ __forceinline__ void scan64(const uint32_t* v, uint32_t row0, uint32_t row_end, bool disabled,
                                            const uint64_t* __restrict__ allow = nullptr) {
-        float thr = disabled ? INFINITY : gate();
-        // tile maximum with 3-input max: 32 instructions for 64 scores
-        float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-        float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+        const K thr = disabled ? O::highest() : gate();
+        // group maxima with 3-input max: 32 instructions for 64 keys
+        K m0 = O::max3(O::from_bits(v[0]), O::from_bits(v[1]), O::from_bits(v[2]));
+        K m1 = O::max3(O::from_bits(v[32]), O::from_bits(v[33]), O::from_bits(v[34]));
 #pragma unroll
-        for (int i = 6; i + 3 < 64; i += 4) {
-            m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        for (int i = 3; i + 1 < 31; i += 2) {
+            m0 = O::max3(m0, O::from_bits(v[i]), O::from_bits(v[i + 1]));
+            m1 = O::max3(m1, O::from_bits(v[32 + i]), O::from_bits(v[32 + i + 1]));
         }
-        m0 = fmax3(m0, __uint_as_float(v[62]), __uint_as_float(v[63]));
-        // Slow path, entered by the whole warp when any lane has a candidate.  It must stay SMALL: a fully unrolled
-        // "for each of the 64 scores: compare, insert" is ~90 KB of code whose sparse execution misses the instruction
-        // cache at every step (~7700 cycles per tile measured).  So: (1) a 64-bit hit mask per lane from straight
-        // compares, (2) a rolled loop that pops each lane's lowest hit and fetches the score with a select tree.
-        if (__any_sync(0xffffffffu, fmaxf(m0, m1) > thr)) {
-            uint32_t mlo = 0u, mhi = 0u;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                mlo |= (__uint_as_float(v[i]) > thr ? 1u : 0u) << i;
-                mhi |= (__uint_as_float(v[32 + i]) > thr ? 1u : 0u) << i;
-            }
-            if (row0 + 64u > row_end) {  // last tile: rows past the end of the corpus never enter a list
-                const uint32_t n_ok = row_end > row0 ? row_end - row0 : 0u;
-                mlo &= n_ok >= 32u ? 0xffffffffu : ((1u << n_ok) - 1u);
-                mhi &= n_ok >= 64u ? 0xffffffffu : (n_ok > 32u ? ((1u << (n_ok - 32u)) - 1u) : 0u);
-            }
-            bool filtered = false;  // this lane lost a hit to the row filter: its tile maximum may be a disallowed row
-            if (allow != nullptr) {
-                const uint64_t w = row0 < row_end ? __ldg(allow + (row0 >> 6)) : 0ull;  // row0 is a multiple of 64
-                const uint32_t alo = (uint32_t)w, ahi = (uint32_t)(w >> 32);
-                filtered = ((mlo & ~alo) | (mhi & ~ahi)) != 0u;
-                mlo &= alo;
-                mhi &= ahi;
-            }
-            // a lane with exactly one hit (the usual case) already holds its score: it is the tile maximum
-            const bool one_hit = !filtered && __popc(mlo) + __popc(mhi) == 1;
-            if (one_hit) {
-                const int idx = mlo != 0u ? __ffs((int)mlo) - 1 : 32 + __ffs((int)mhi) - 1;
-                insert(fmaxf(m0, m1), row0 + (uint32_t)idx);
-                mlo = 0u;
-                mhi = 0u;
-            }
-#pragma unroll 1
-            while (__any_sync(0xffffffffu, (mlo | mhi) != 0u)) {
-                if ((mlo | mhi) != 0u) {
-                    int idx;
-                    if (mlo != 0u) {
-                        idx = __ffs((int)mlo) - 1;
-                        mlo &= mlo - 1u;
-                    } else {
-                        idx = 32 + __ffs((int)mhi) - 1;
-                        mhi &= mhi - 1u;
-                    }
-                    // v[idx] with a run-time idx: 6-level select tree over the register array (63 selects)
-                    uint32_t t5[32], t4[16], t3[8], t2[4], t1[2];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) t5[j] = (idx & 32) ? v[32 + j] : v[j];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) t4[j] = (idx & 16) ? t5[16 + j] : t5[j];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) t3[j] = (idx & 8) ? t4[8 + j] : t4[j];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) t2[j] = (idx & 4) ? t3[4 + j] : t3[j];
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) t1[j] = (idx & 2) ? t2[2 + j] : t2[j];
-                    const float x = __uint_as_float((idx & 1) ? t1[1] : t1[0]);
-                    if (x > gate()) insert(x, row0 + (uint32_t)idx);  // the gate may have risen since the mask was taken
-                }
-            }
-            // floor groups publish from poll_floor (every 8th tile): the group minimum costs m loads
-            if (may_publish && q_valid && group_m <= 1 && lmin > thr_pub && lmin > thr_g) publish();
+        m0 = max(m0, O::from_bits(v[31]));
+        m1 = max(m1, O::from_bits(v[63]));
+        if (__any_sync(0xffffffffu, max(m0, m1) > thr)) {
+            uint64_t w = ~0ull;
+            const bool have_allow = allow != nullptr;
+            if (have_allow) w = row0 < row_end ? __ldg(allow + (row0 >> 6)) : 0ull;  // row0 is a multiple of 64
+            if (__any_sync(0xffffffffu, m0 > thr)) slow32(v, m0, row0, row_end, thr, (uint32_t)w, have_allow);
+            if (__any_sync(0xffffffffu, m1 > thr)) slow32(v + 32, m1, row0 + 32u, row_end, thr, (uint32_t)(w >> 32), have_allow);
+            if (may_publish && q_valid && lmin > thr_pub && lmin > thr_g) publish();
         }
     }
     // `sub`: which of the partition's lists_per_part shortlists this is (the pair kernel with two epilogue sets)
     __device__ __forceinline__ void flush(const TcArgs& a, uint32_t gq, uint32_t part, uint32_t sub = 0) {
         if (!q_valid) return;
         const size_t list = (size_t)gq * ((size_t)a.P * a.lists_per_part) + (size_t)part * a.lists_per_part + sub;
-        const size_t o = list * KP;
+        if (hit_count == nullptr) {
+            const size_t o = list * KP;
 #pragma unroll
-        for (int j = 0; j < KP; j += 4) {
-            *reinterpret_cast<float4*>(a.cand_score + o + j) = make_float4(sc[j], sc[j + 1], sc[j + 2], sc[j + 3]);
-            *reinterpret_cast<uint4*>(a.cand_row + o + j) = make_uint4(rw[j], rw[j + 1], rw[j + 2], rw[j + 3]);
+            for (int j = 0; j < KP; j += 4) {
+                *reinterpret_cast<uint4*>(a.cand_key + o + j) = make_uint4(O::bits(sc[j]), O::bits(sc[j + 1]), O::bits(sc[j + 2]), O::bits(sc[j + 3]));
+                *reinterpret_cast<uint4*>(a.cand_row + o + j) = make_uint4(rw[j], rw[j + 1], rw[j + 2], rw[j + 3]);
+            }
         }
         // every row this thread dropped scored <= max(lmin, thr_g) at the time, and both only grow
-        a.cand_thr[list] = fmaxf(lmin, thr_g);
+        a.cand_thr[list] = O::bits(max(lmin, thr_g));
     }
 };
 
 // ---- shadow / query preparation --------------------------------------------------------------------------------
 enum ShadowKind { SHADOW_IP = 0, SHADOW_COSINE = 1, SHADOW_L2 = 2 };
+enum OperandKind { OPERAND_BF16 = 0, OPERAND_U8 = 1 };
 
-// One warp per row: the row's Dp bf16 values (zero padded) written into the tiled, pre-swizzled layout described
-// at the top of this file, + max row norm (for the certification bound).
-//   SHADOW_IP      c
-//   SHADOW_COSINE  c / |c|            (zero rows stay zero: cosine distance 1.0, simd.rs:1631-1633)
-//   SHADOW_L2      [c, n1, n2, n3]    with n1+n2+n3 ~ |c|^2 split into three bf16 pieces (columns dim..dim+2)
-__host__ __device__ inline size_t shadow_chunk_offset(uint64_t row, int chunk /* 16-byte chunk = 8 elements */, int nkb) {
+// Per-shadow statistics, accumulated on the device while the shadow is built.  c' = the transformed row the shadow
+// approximates (c; c / |c| for cosine), c~ = the value the operand really holds (bf16(c'), or zero + scale * u8).
+// The certification of finalize_kernel uses cmax and emax:  |q~.c~ - q'.c'| <= |dq| cmax + |q~| emax  (Cauchy-Schwarz),
+// with every norm MEASURED, which is both rigorous and tighter than the worst case of the element-wise rounding.
+struct ShadowStats {
+    uint32_t cmax_bits;   // max over rows of |c'|           (f32 bits of a non-negative value: unsigned order = value order)
+    uint32_t emax_bits;   // max over rows of |c' - c~|
+    uint32_t vmin_ord;    // orderable bits of the smallest element of c' (range of the 8-bit quantisation)
+    uint32_t vmax_ord;    // ... and of the largest
+    uint32_t nonfinite;   // rows holding NaN / inf: the plan is not used for such a corpus
+    uint32_t e16max_bits; // max over rows of |c' - bf16(c')| (written by the range pass: what a bf16 operand would have cost)
+    uint32_t pad[2];
+};
+// Per-query statistics written by the query preparation kernels.
+struct QStat {
+    float qt_norm;   // |q~|  : norm of the operand's value of the transformed query q' (q; q/|q|; for L2 q — the factor 2 is applied later)
+    float dq_norm;   // |q' - q~|
+    float q_norm;    // |q| of the original query
+    float s_q;       // 8-bit operands: q~_i = s_q * qhat_i
+    float sum_qhat;  // 8-bit operands: sum of qhat_i (exact: |sum| < 2^24)
+    float pad[3];
+};
+
+__host__ __device__ inline size_t shadow_chunk_offset(uint64_t row, int chunk /* 16-byte chunk of the operand row */, int nkb) {
     const uint64_t tile = row >> 6;
     const uint32_t half = (uint32_t)(row >> 5) & 1u, r = (uint32_t)row & 31u;
     const uint32_t kb = (uint32_t)chunk >> 3, c = (uint32_t)chunk & 7u;
     return (size_t)(((tile * (uint64_t)nkb + kb) * 2 + half) * HALF_BLOCK_BYTES) + (size_t)r * 128 + (size_t)((c ^ (r & 7u)) << 4);
 }
-static __global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int Dp,
-                                    int kind, unsigned char* __restrict__ shadow, float* __restrict__ max_norm) {
-    uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+// One warp per row, first pass: |c|, the element range of c' and non-finite rows (everything the 8-bit quantisation needs
+// to know before it can write a byte).
+static __global__ void shadow_range_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int kind,
+                                           ShadowStats* __restrict__ st) {
+    const uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= first_row + n) return;
+    const float* r = rows + row * dim;
+    float ss = 0.0f, mn = INFINITY, mx = -INFINITY;
+    for (int d = lane; d < dim; d += 32) {
+        const float x = __ldg(r + d);
+        ss = fmaf(x, x, ss);
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+    }
+    ss = warp_sum(ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    float scale = 1.0f;
+    if (kind == SHADOW_COSINE) {
+        const float norm = sqrtf(ss);
+        scale = norm > 0.0f ? 1.0f / norm : 0.0f;
+    }
+    float e16 = 0.0f;
+    for (int d = lane; d < dim; d += 32) {
+        const float x = __ldg(r + d) * scale;
+        const float de = x - __bfloat162float(__float2bfloat16_rn(x));
+        e16 = fmaf(de, de, e16);
+    }
+    e16 = warp_sum(e16);
+    if (lane != 0) return;
+    if (!isfinite(ss)) {
+        atomicAdd(&st->nonfinite, 1u);
+        return;
+    }
+    atomicMin(&st->vmin_ord, f32_orderable(mn * scale));
+    atomicMax(&st->vmax_ord, f32_orderable(mx * scale));
+    atomicMax(&st->e16max_bits, __float_as_uint(sqrtf(e16)));
+}
+
+// One warp per row: the row's operand values (zero padded to the operand row length) written into the tiled,
+// pre-swizzled layout described at the top of this file, + the statistics the certification needs.
+//   SHADOW_IP      c' = c
+//   SHADOW_COSINE  c' = c / |c|       (zero rows stay zero: cosine distance 1.0, simd.rs:1631-1633)
+//   SHADOW_L2      c' = c, side[row] = |c|^2 (f32): the epilogue forms 2 q.c - |c|^2 (CM_F32_BIAS)
+// OPERAND_BF16: c~ = bf16(c').  OPERAND_U8: c~ = zero + scale * u8, u8 = clamp(rint((c' - zero) / scale), 0, 255).
+template <int OPK>
+__global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int row_bytes, int kind,
+                                    unsigned char* __restrict__ shadow, float* __restrict__ side, ShadowStats* __restrict__ st,
+                                    float q_scale, float q_zero) {
+    const uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (row >= first_row + n) return;
     const float* r = rows + row * dim;
     float ss = 0.0f;
     for (int d = lane; d < dim; d += 32) {
-        float x = __ldg(r + d);
+        const float x = __ldg(r + d);
         ss = fmaf(x, x, ss);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    float norm = sqrtf(ss);
+    ss = warp_sum(ss);
+    const float norm = sqrtf(ss);
     float scale = 1.0f;
     if (kind == SHADOW_COSINE) scale = norm > 0.0f ? 1.0f / norm : 0.0f;
-    const int nkb = Dp / KBLK;
-    for (int chunk = lane; chunk < Dp / 8; chunk += 32) {
-        __align__(16) __nv_bfloat16 v[8];
+    const int nkb = row_bytes / 128;
+    constexpr int EPC = OPK == OPERAND_BF16 ? 8 : 16;  // elements per 16-byte chunk
+    const float inv_q = OPK == OPERAND_U8 ? 1.0f / q_scale : 0.0f;
+    float err = 0.0f, tss = 0.0f;  // |c' - c~|^2 and |c'|^2
+    for (int chunk = lane; chunk < row_bytes / 16; chunk += 32) {
+        __align__(16) unsigned char out[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int d = chunk * 8 + e;
-            float x = d < dim ? __ldg(r + d) * scale : 0.0f;
-            if (kind == SHADOW_L2 && d >= dim && d < dim + 3) {
-                float n1 = __bfloat162float(__float2bfloat16_rn(ss));
-                float n2 = __bfloat162float(__float2bfloat16_rn(ss - n1));
-                float n3 = (ss - n1) - n2;
-                x = d == dim ? n1 : (d == dim + 1 ? n2 : n3);
+        for (int e = 0; e < EPC; ++e) {
+            const int d = chunk * EPC + e;
+            const float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+            float held;
+            if (OPK == OPERAND_BF16) {
+                const __nv_bfloat16 b = __float2bfloat16_rn(x);
+                reinterpret_cast<__nv_bfloat16*>(out)[e] = b;
+                held = __bfloat162float(b);
+            } else {
+                int u = d < dim ? __float2int_rn((x - q_zero) * inv_q) : 0;
+                u = min(max(u, 0), 255);
+                out[e] = (unsigned char)u;
+                held = d < dim ? fmaf(q_scale, (float)u, q_zero) : 0.0f;
             }
-            v[e] = __float2bfloat16_rn(x);
+            const float de = x - held;
+            err = fmaf(de, de, err);
+            tss = fmaf(x, x, tss);
         }
-        *reinterpret_cast<uint4*>(shadow + shadow_chunk_offset(row, chunk, nkb)) = *reinterpret_cast<const uint4*>(v);
+        *reinterpret_cast<uint4*>(shadow + shadow_chunk_offset(row, chunk, nkb)) = *reinterpret_cast<const uint4*>(out);
     }
-    if (lane == 0 && isfinite(norm)) atomicMax(reinterpret_cast<unsigned int*>(max_norm), __float_as_uint(norm));
+    err = warp_sum(err);
+    tss = warp_sum(tss);
+    if (lane == 0) {
+        if (kind == SHADOW_L2 && side != nullptr) side[row] = ss;
+        if (isfinite(ss)) {
+            atomicMax(&st->cmax_bits, __float_as_uint(sqrtf(tss)));
+            atomicMax(&st->emax_bits, __float_as_uint(sqrtf(err)));
+        } else {
+            atomicAdd(&st->nonfinite, 1u);
+        }
+    }
 }
 
-// Queries: bf16 A operand rows (zero padded to n_mtiles*128 x Dp) + |q| per query.
-//   SHADOW_IP      q                 SHADOW_COSINE  q / |q|          SHADOW_L2  [2q, -1, -1, -1]
-static __global__ void prepare_queries_kernel(const float* __restrict__ queries, int nq, int nq_pad, int dim, int Dp, int kind,
-                                       __nv_bfloat16* __restrict__ qb, float* __restrict__ qnorm) {
-    int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
+// Packed one-bit rows -> one byte per bit ({0,1}, the 8-bit operand of the binary metrics) in the tiled layout,
+// + popcount(row) as the row's side value.  One warp per row; bit i of a row = word i/64, bit i%64 (simd.rs:750-757).
+static __global__ void build_bits_shadow_kernel(const uint64_t* __restrict__ words, uint64_t first_row, uint64_t n, int n_words,
+                                                int row_bytes, unsigned char* __restrict__ shadow, uint32_t* __restrict__ side_u32,
+                                                float* __restrict__ side_f32) {
+    const uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= first_row + n) return;
+    const uint64_t* w = words + row * n_words;
+    const int nkb = row_bytes / 128;
+    uint32_t pop = 0;
+    for (int chunk = lane; chunk < row_bytes / 16; chunk += 32) {  // 16 bits -> 16 bytes
+        const int word = chunk >> 2, sh = (chunk & 3) * 16;
+        const uint32_t bits = word < n_words ? (uint32_t)(__ldg(w + word) >> sh) & 0xffffu : 0u;
+        pop += __popc(bits);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t nib = (bits >> (4 * j)) & 0xfu;
+            o[j] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+        *reinterpret_cast<uint4*>(shadow + shadow_chunk_offset(row, chunk, nkb)) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pop += __shfl_xor_sync(0xffffffffu, pop, o);
+    if (lane == 0) {
+        side_u32[row] = pop;
+        side_f32[row] = (float)pop;
+    }
+}
+static __global__ void fill_u32_kernel(uint32_t* out, uint64_t n, uint32_t value) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = value;
+}
+// packed query words -> {0,1} bytes (A operand rows, zero padded) + popcount as the query's side value
+static __global__ void prepare_bits_queries_kernel(const uint64_t* __restrict__ qwords, int nq, int nq_pad, int n_words, int row_bytes,
+                                                   unsigned char* __restrict__ qb, float* __restrict__ qaux) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (q >= nq_pad) return;
-    __nv_bfloat16* out = qb + (size_t)q * Dp;
+    uint32_t pop = 0;
+    for (int chunk = lane; chunk < row_bytes / 16; chunk += 32) {
+        const int word = chunk >> 2, sh = (chunk & 3) * 16;
+        const uint32_t bits = (q < nq && word < n_words) ? (uint32_t)(__ldg(qwords + (size_t)q * n_words + word) >> sh) & 0xffffu : 0u;
+        pop += __popc(bits);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t nib = (bits >> (4 * j)) & 0xfu;
+            o[j] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+        *reinterpret_cast<uint4*>(qb + (size_t)q * row_bytes + (size_t)chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pop += __shfl_xor_sync(0xffffffffu, pop, o);
+    if (lane == 0) qaux[q] = (float)pop;
+}
+
+// Queries, bf16 operand: A operand rows (zero padded to nq_pad x row_bytes) + statistics.
+//   SHADOW_IP  q' = q       SHADOW_COSINE  q' = q / |q|       SHADOW_L2  q' = q, operand = 2 q~ (exact doubling)
+static __global__ void prepare_queries_kernel(const float* __restrict__ queries, int nq, int nq_pad, int dim, int row_bytes, int kind,
+                                              unsigned char* __restrict__ qb, QStat* __restrict__ qstat) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq_pad) return;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(qb + (size_t)q * row_bytes);
+    const int Dp = row_bytes / 2;
     if (q >= nq) {
         for (int d = lane; d < Dp; d += 32) out[d] = __float2bfloat16_rn(0.0f);
         return;
@@ -552,57 +773,168 @@ static __global__ void prepare_queries_kernel(const float* __restrict__ queries,
     const float* r = queries + (size_t)q * dim;
     float ss = 0.0f;
     for (int d = lane; d < dim; d += 32) {
-        float x = __ldg(r + d);
+        const float x = __ldg(r + d);
         ss = fmaf(x, x, ss);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    float norm = sqrtf(ss);
+    ss = warp_sum(ss);
+    const float norm = sqrtf(ss);
     float scale = 1.0f;
     if (kind == SHADOW_COSINE) scale = norm > 0.0f ? 1.0f / norm : 0.0f;
-    if (kind == SHADOW_L2) scale = 2.0f;
+    float err = 0.0f, hss = 0.0f;
     for (int d = lane; d < Dp; d += 32) {
-        float x = d < dim ? __ldg(r + d) * scale : 0.0f;
-        if (kind == SHADOW_L2 && d >= dim && d < dim + 3) x = -1.0f;
-        out[d] = __float2bfloat16_rn(x);
+        const float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+        const __nv_bfloat16 b = __float2bfloat16_rn(x);
+        const float held = __bfloat162float(b);
+        out[d] = kind == SHADOW_L2 ? __float2bfloat16_rn(2.0f * held) : b;
+        const float de = x - held;
+        err = fmaf(de, de, err);
+        hss = fmaf(held, held, hss);
     }
-    if (lane == 0) qnorm[q] = norm;
+    err = warp_sum(err);
+    hss = warp_sum(hss);
+    if (lane == 0) {
+        QStat s{};
+        s.qt_norm = sqrtf(hss);
+        s.dq_norm = sqrtf(err);
+        s.q_norm = norm;
+        s.s_q = 1.0f;
+        qstat[q] = s;
+    }
+}
+
+// Queries, 8-bit operand, pass 1: per-query element range of q' and whether any query of the batch has a negative element
+// (then the whole batch is quantised as signed bytes: the A format is one bit of the instruction descriptor).
+static __global__ void query_range_kernel(const float* __restrict__ queries, int nq, int dim, int kind, float* __restrict__ qrange /*[nq][2]*/,
+                                          uint32_t* __restrict__ idesc_extra) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float* r = queries + (size_t)q * dim;
+    float ss = 0.0f, mn = INFINITY, mx = -INFINITY;
+    for (int d = lane; d < dim; d += 32) {
+        const float x = __ldg(r + d);
+        ss = fmaf(x, x, ss);
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+    }
+    ss = warp_sum(ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane != 0) return;
+    if (kind == SHADOW_COSINE) {
+        const float norm = sqrtf(ss), scale = norm > 0.0f ? 1.0f / norm : 0.0f;
+        mn *= scale;
+        mx *= scale;
+    }
+    qrange[2 * q] = mn;
+    qrange[2 * q + 1] = mx;
+    if (mn < 0.0f) atomicOr(idesc_extra, IDESC_A_SIGNED);
+}
+// pass 2: q~_i = s_q * qhat_i with qhat a u8 (s_q = max / 255) or, for a batch with negative elements, an s8 (s_q = max|.| / 127)
+static __global__ void quantise_queries_kernel(const float* __restrict__ queries, int nq, int nq_pad, int dim, int row_bytes, int kind,
+                                               const float* __restrict__ qrange, const uint32_t* __restrict__ idesc_extra,
+                                               unsigned char* __restrict__ qb, QStat* __restrict__ qstat) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq_pad) return;
+    unsigned char* out = qb + (size_t)q * row_bytes;
+    if (q >= nq) {
+        for (int d = lane * 4; d < row_bytes; d += 128) *reinterpret_cast<uint32_t*>(out + d) = 0u;
+        return;
+    }
+    const bool is_signed = (__ldg(idesc_extra) & IDESC_A_SIGNED) != 0u;
+    const float* r = queries + (size_t)q * dim;
+    float ss = 0.0f;
+    for (int d = lane; d < dim; d += 32) {
+        const float x = __ldg(r + d);
+        ss = fmaf(x, x, ss);
+    }
+    ss = warp_sum(ss);
+    const float norm = sqrtf(ss);
+    float scale = 1.0f;
+    if (kind == SHADOW_COSINE) scale = norm > 0.0f ? 1.0f / norm : 0.0f;
+    const float amax = fmaxf(fabsf(qrange[2 * q]), fabsf(qrange[2 * q + 1]));
+    const float levels = is_signed ? 127.0f : 255.0f;
+    const float s_q = (amax > 0.0f && isfinite(amax)) ? amax / levels : 1.0f;
+    const float inv = 1.0f / s_q;
+    float err = 0.0f, hss = 0.0f, hsum = 0.0f;
+    for (int d0 = lane * 4; d0 < row_bytes; d0 += 128) {
+        uint32_t word = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int d = d0 + e;
+            const float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+            int u = __float2int_rn(x * inv);
+            u = is_signed ? min(max(u, -127), 127) : min(max(u, 0), 255);
+            const float held = s_q * (float)u;
+            const float de = x - held;
+            err = fmaf(de, de, err);
+            hss = fmaf(held, held, hss);
+            hsum += (float)u;
+            word |= ((uint32_t)u & 0xffu) << (8 * e);
+        }
+        *reinterpret_cast<uint32_t*>(out + d0) = word;
+    }
+    err = warp_sum(err);
+    hss = warp_sum(hss);
+    hsum = warp_sum(hsum);
+    if (lane == 0) {
+        QStat s{};
+        s.qt_norm = sqrtf(hss);
+        s.dq_norm = sqrtf(err);
+        s.q_norm = norm;
+        s.s_q = s_q;
+        s.sum_qhat = hsum;
+        qstat[q] = s;
+    }
 }
 
 // ---- seeded floors for large k ---------------------------------------------------------------------------------
-// After a pre-pass over a sample of the corpus: the r-th best coarse score of the sample, per query, becomes the
+// After a pre-pass over a sample of the corpus: the r-th best coarse key of the sample, per query, becomes the
 // floor the main pass starts with (gthr).  It is a heuristic gate — about r * (rows / sample rows) rows of the corpus
 // score above it — and the certification of finalize_kernel is what keeps the result exact: a floor that turns out
 // too high leaves the query uncertified and it is re-run by the exact scan.
-static __global__ void __launch_bounds__(256) seed_floor_kernel(const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_row, int P,
-                                                         int M, int r, uint32_t* __restrict__ gthr) {
+static __global__ void __launch_bounds__(256) seed_floor_kernel(const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_row, int P,
+                                                                int M, int r, int int_key, uint32_t* __restrict__ gthr) {
     extern __shared__ __align__(16) unsigned char smem_seed[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_seed);
     const int q = blockIdx.x, total = P * KP;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         uint64_t key = KEY_NONE;
-        if (i < total && cand_row[(size_t)q * total + i] != ROW_NONE) key = make_key<false>(cand_score[(size_t)q * total + i], (uint32_t)i);
+        if (i < total && cand_row[(size_t)q * total + i] != ROW_NONE)
+            key = ((uint64_t)(~key_bits_orderable(cand_key[(size_t)q * total + i], int_key != 0)) << 32) | (uint32_t)i;  // best key first
         s[i] = key;
     }
     bitonic_sort_u64(s, M);
-    if (threadIdx.x == 0) gthr[q] = (r >= 1 && r <= M && s[r - 1] != KEY_NONE) ? f32_orderable(key_score<false>(s[r - 1])) : 0u;
+    if (threadIdx.x == 0) gthr[q] = (r >= 1 && r <= M && s[r - 1] != KEY_NONE) ? ~(uint32_t)(s[r - 1] >> 32) : 0u;
 }
 
 // ---- finalize: shortlist -> exact-order rescore -> certified top-k -------------------------------------------------
 struct FinArgs {
-    const float* cand_score;  // [nq][P][KP]
+    // list mode: the shortlists of the partitions
+    const uint32_t* cand_key;  // [nq][P][KP] key bits
     const uint32_t* cand_row;
-    const float* cand_thr;    // [nq][P]
+    const uint32_t* cand_thr;  // [nq][P] key bits
     int P;
-    int M1;                   // pow2 >= P*KP (<= 4096)
+    // hit mode (hit_count != null): the rows above the seeded floor gthr[q]
+    const uint32_t* hit_count;
+    const uint2* hit_buf;
+    uint32_t hit_cap;
+    const uint32_t* gthr;
+    int int_key;              // keys are s32 (8-bit operands) instead of f32
+    int M1;                   // pow2 >= number of candidates read (<= 4096)
     int R;                    // rescore budget, pow2 <= 1024, >= k
     const float* corpus;
     int dim;
     const float* queries;     // original f32 queries [nq][dim]
-    const float* qnorm;       // [nq]
-    const float* max_norm;    // device scalar: max row norm
+    const QStat* qstat;       // [nq]
+    const ShadowStats* sstat;
+    int operand;              // OperandKind
+    float c_scale, c_zero;    // OPERAND_U8: c~ = c_zero + c_scale * u8
     int nq, k, metric;
-    float eps_rel;            // relative error bound of the coarse score
     const uint32_t* small_seg;
     int n_small;
     uint32_t* out_rows;
@@ -682,40 +1014,70 @@ __device__ __forceinline__ float rescore_row_lanes(int metric, bool two_acc_ip, 
     return 1.0f - dot / denom;
 }
 
+// Candidates of query q -> sort keys in s[0, M1) (best coarse key first), sorted; returns through shared words the number of
+// candidates and the orderable bits of T: every row that is NOT a candidate has a coarse key <= T.
+__device__ __forceinline__ void gather_candidates(const FinArgs& a, int q, uint64_t* s, uint32_t* sh_T, uint32_t* sh_ncand, uint32_t* sh_overflow) {
+    const int tid = threadIdx.x;
+    const bool ik = a.int_key != 0;
+    uint32_t local_valid = 0;
+    if (a.hit_count != nullptr) {
+        const uint32_t cnt = a.hit_count[q], n = min(cnt, a.hit_cap);
+        for (int i = tid; i < a.M1; i += blockDim.x) {
+            uint64_t key = KEY_NONE;
+            if ((uint32_t)i < n) {
+                const uint2 h = a.hit_buf[(size_t)q * a.hit_cap + i];
+                key = ((uint64_t)(~key_bits_orderable(h.x, ik)) << 32) | h.y;
+                ++local_valid;
+            }
+            s[i] = key;
+        }
+        if (tid == 0) {
+            *sh_T = a.gthr[q];  // orderable bits of the seeded floor (0 = none: nothing was dropped)
+            *sh_overflow = cnt > a.hit_cap ? 1u : 0u;
+        }
+    } else {
+        const int total = a.P * KP;
+        for (int i = tid; i < a.M1; i += blockDim.x) {
+            uint64_t key = KEY_NONE;
+            if (i < total) {
+                const uint32_t row = a.cand_row[(size_t)q * total + i];
+                if (row != ROW_NONE) {
+                    key = ((uint64_t)(~key_bits_orderable(a.cand_key[(size_t)q * total + i], ik)) << 32) | row;
+                    ++local_valid;
+                }
+            }
+            s[i] = key;
+        }
+        for (int p = tid; p < a.P; p += blockDim.x) atomicMax(sh_T, key_bits_orderable(a.cand_thr[(size_t)q * a.P + p], ik));
+    }
+    if (local_valid) atomicAdd(sh_ncand, local_valid);
+    bitonic_sort_u64(s, a.M1);
+}
+// orderable key bits -> the key as a real number
+__device__ __forceinline__ double key_value(uint32_t ord, bool int_key) {
+    return int_key ? (double)(int)(ord ^ 0x80000000u) : (double)f32_from_orderable(ord);
+}
+
 template <bool ASC>
 __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     extern __shared__ __align__(16) unsigned char smem_fin[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_fin);            // [M1] coarse keys
     uint64_t* e = s + a.M1;                                         // [R] exact keys
     float* sq = reinterpret_cast<float*>(e + a.R);                  // [dim_pad] query
-    __shared__ uint32_t sh_T;      // orderable max of partition thresholds
-    __shared__ uint32_t sh_ncand;
+    __shared__ uint32_t sh_T;      // orderable max of the floors
+    __shared__ uint32_t sh_ncand, sh_overflow;
     const int q = blockIdx.x, tid = threadIdx.x;
     const int dim = a.dim;
     const bool vec = (dim & 3) == 0;
-    if (tid == 0) { sh_T = 0; sh_ncand = 0; }
+    const bool ik = a.int_key != 0;
+    if (tid == 0) { sh_T = 0; sh_ncand = 0; sh_overflow = 0; }
     for (int d = tid; d < dim; d += blockDim.x) sq[d] = a.queries[(size_t)q * dim + d];
     __syncthreads();
-    const int total = a.P * KP;
-    uint32_t local_valid = 0;
-    for (int i = tid; i < a.M1; i += blockDim.x) {
-        uint64_t key = KEY_NONE;
-        if (i < total) {
-            uint32_t row = a.cand_row[(size_t)q * total + i];
-            if (row != ROW_NONE) {
-                key = make_key<false>(a.cand_score[(size_t)q * total + i], row);  // best coarse score first
-                ++local_valid;
-            }
-        }
-        s[i] = key;
-    }
-    if (local_valid) atomicAdd(&sh_ncand, local_valid);
-    for (int p = tid; p < a.P; p += blockDim.x) atomicMax(&sh_T, f32_orderable(a.cand_thr[(size_t)q * a.P + p]));
-    bitonic_sort_u64(s, a.M1);
+    gather_candidates(a, q, s, &sh_T, &sh_ncand, &sh_overflow);
     const int ncand = (int)sh_ncand;
     const int rn = min(ncand, a.R);
-    float T = f32_from_orderable(sh_T);  // every row dropped inside a partition has coarse score <= T
-    if (ncand > a.R) T = fmaxf(T, key_score<false>(s[a.R]));  // ... and so has every candidate cut here
+    uint32_t T_ord = sh_T;  // every row dropped inside a partition has a coarse key <= T (0 = nothing dropped)
+    if (ncand > a.R) T_ord = max(T_ord, ~(uint32_t)(s[a.R] >> 32));  // ... and so has every candidate cut here
     if (vec) {
         // eight threads per row, four rows per warp, blockDim/8 rows per pass of the block (rows are independent:
         // warp-local syncs only)
@@ -766,25 +1128,43 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     if (tid == 0) {
         a.out_counts[q] = kk;
         bool certified;
-        if (T == -INFINITY) {
-            certified = true;  // nothing was dropped anywhere: the shortlist is the whole corpus
+        if (sh_overflow) {
+            certified = false;  // the hit buffer overflowed: candidates were lost
+        } else if (T_ord <= (ik ? 0u : 0x007FFFFFu)) {
+            certified = true;   // no floor above the lowest key: nothing was dropped anywhere, the candidates are the whole corpus
         } else if (kk < a.k) {
             certified = false;
         } else {
-            const float worst = key_score<ASC>(e[a.k - 1]);
-            const float qn = a.qnorm[q], cn = *a.max_norm;
+            // Bound on the exact "similarity" (q.c; cos; 2 q.c - |c|^2) of any dropped row, in real arithmetic:
+            //   sim <= value(T) + |dq| cmax + |q~| emax + accumulation slop + rounding slop of the exact f32 score.
+            // Every norm is measured (QStat, ShadowStats); the slack factors cover the f32 evaluation of those norms.
+            const QStat qs = a.qstat[q];
+            const double cmax = (double)__uint_as_float(a.sstat->cmax_bits) * 1.0001, emax = (double)__uint_as_float(a.sstat->emax_bits) * 1.0001;
+            const double u24 = 5.9604644775390625e-8;
+            const double qtn = (double)qs.qt_norm * 1.0001, qn = (double)qs.q_norm;
+            const double dqn = (double)qs.dq_norm * 1.0001 + 4.0 * u24 * qtn;   // + rounding of the held values themselves
+            double T = key_value(T_ord, ik);
+            double eps = dqn * cmax + qtn * (emax + 4.0 * u24 * cmax);
+            if (a.operand == OPERAND_U8) {
+                // key = sum qhat chat exactly;  q~.c~ = s_q s_c key + s_q z_c sum(qhat)
+                const double sq_ = (double)qs.s_q;
+                T = sq_ * (double)a.c_scale * T + sq_ * (double)a.c_zero * (double)qs.sum_qhat;
+                eps += 1e-9 * (fabs(T) + 1.0);
+            } else {
+                // tensor-core accumulation of the bf16 products in f32 (order unspecified): Dp * 2^-21 relative to |q~||c~|
+                eps += (double)((dim + 63) & ~63) * 4.76837158203125e-7 * qtn * (cmax + emax);
+            }
+            const double worst = (double)key_score<ASC>(e[a.k - 1]);
             if (a.metric == LB_IP) {
-                // dropped row: exact <= coarse + eps <= T + eps
-                const float eps = a.eps_rel * qn * cn;
+                eps += (double)(dim / 8 + 16) * u24 * qn * cmax;                 // rounding of the exact f32 dot product
                 certified = worst > T + eps;
             } else if (a.metric == LB_COSINE) {
-                // coarse = cos of the normalised bf16 vectors; dropped row: dist >= 1 - (T + eps)
-                const float eps = a.eps_rel + 4e-6f;
-                certified = worst < 1.0f - (T + eps);
+                eps += (double)(dim / 4 + 64) * u24;                             // normalisations + the exact f32 cosine
+                certified = worst < 1.0 - (T + eps);
             } else {
-                // coarse = 2 q.c - |c|^2 ; dropped row: dist >= |q|^2 - (T + eps)
-                const float eps = 2.0f * a.eps_rel * qn * cn + 1e-5f * (qn * qn + cn * cn);
-                certified = worst < qn * qn - (T + eps);
+                // key = 2 q~.c~ - fl(|c|^2);  exact dist = |q - c|^2 >= |q|^2 - (T + eps)
+                eps = 2.0 * eps + (double)(dim / 8 + 32) * u24 * 2.0 * (qn + cmax) * (qn + cmax);
+                certified = worst < qn * qn * (1.0 - (double)(dim / 8 + 16) * u24) - (T + eps);
             }
         }
         if (!certified) {
@@ -796,9 +1176,85 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     }
 }
 
+// ---- finalize for the binary metrics: candidates -> exact integer counts on the packed rows -> certified top-k ----
+struct FinBitsArgs {
+    FinArgs f;                 // candidate sources, k, metric, outputs (corpus / queries / stats unused)
+    const uint64_t* words;     // packed rows [n][n_words]
+    const uint64_t* qwords;    // packed queries [nq][n_words]
+    int n_words;
+};
+static __global__ void __launch_bounds__(256) finalize_bits_kernel(FinBitsArgs b) {
+    const FinArgs& a = b.f;
+    extern __shared__ __align__(16) unsigned char smem_finb[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_finb);           // [M1] coarse keys
+    uint64_t* e = s + a.M1;                                         // [R] exact keys
+    uint64_t* sqw = e + a.R;                                        // [n_words] query
+    __shared__ uint32_t sh_T, sh_ncand, sh_overflow;
+    const int q = blockIdx.x, tid = threadIdx.x, nw = b.n_words;
+    const bool ik = a.int_key != 0;
+    if (tid == 0) { sh_T = 0; sh_ncand = 0; sh_overflow = 0; }
+    for (int w = tid; w < nw; w += blockDim.x) sqw[w] = b.qwords[(size_t)q * nw + w];
+    __syncthreads();
+    gather_candidates(a, q, s, &sh_T, &sh_ncand, &sh_overflow);
+    const int ncand = (int)sh_ncand;
+    const int rn = min(ncand, a.R);
+    uint32_t T_ord = sh_T;
+    if (ncand > a.R) T_ord = max(T_ord, ~(uint32_t)(s[a.R] >> 32));
+    uint32_t qpop = 0;
+    for (int w = 0; w < nw; ++w) qpop += __popcll(sqw[w]);
+    for (int i = tid; i < a.R; i += blockDim.x) {
+        uint64_t key = KEY_NONE;
+        if (i < rn) {
+            const uint32_t row = key_row(s[i]);
+            const uint64_t* rw = b.words + (size_t)row * nw;
+            uint32_t x = 0, inter = 0, rpop = 0;
+            for (int w = 0; w < nw; ++w) {
+                const uint64_t rv = __ldg(rw + w), qv = sqw[w];
+                x += __popcll(rv ^ qv);
+                inter += __popcll(rv & qv);
+                rpop += __popcll(rv);
+            }
+            float d;
+            if (a.metric == LB_HAMMING) d = packed_finish(LB_HAMMING, x, 0);
+            else if (a.metric == LB_DICE) d = packed_finish(LB_DICE, inter, qpop + rpop);
+            else d = packed_finish(LB_JACCARD, inter, qpop + rpop - inter);
+            key = make_key<true>(d, row);
+        }
+        e[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_u64(e, a.R);
+    const int kk = min(a.k, rn);
+    for (int i = tid; i < a.k; i += blockDim.x) {
+        uint32_t row = ROW_NONE;
+        float score = __int_as_float(0x7fc00000);
+        if (i < kk) {
+            row = key_row(e[i]);
+            score = key_score<true>(e[i]);
+        }
+        a.out_rows[(size_t)q * a.k + i] = row;
+        a.out_dists[(size_t)q * a.k + i] = score;
+    }
+    if (tid == 0) {
+        a.out_counts[q] = kk;
+        bool certified;
+        if (sh_overflow) certified = false;
+        else if (T_ord <= (ik ? 0u : 0x007FFFFFu)) certified = true;
+        else if (kk < a.k) certified = false;
+        else {
+            const double worst = (double)key_score<true>(e[a.k - 1]);
+            const double T = key_value(T_ord, ik);
+            if (a.metric == LB_HAMMING) certified = worst < (double)qpop - T;  // key = 2 inter - pb = pa - hamming, exact: ties are not certified
+            else certified = worst < 1.0 - (T + 1e-5);                          // key ~ similarity, relative error of the fast division << 1e-5
+        }
+        a.uncertified[q] = certified ? 0u : 1u;
+        if (!certified) atomicAdd(a.n_uncertified, 1u);
+    }
+}
+
 // ---- diagnostics: tcgen05.mma issue-rate probe ------------------------------------------------------------------
 // One warp issues `iters` MMAs (M=128, K=16, bf16) round-robin over `n_acc` independent accumulators of N columns;
-// operands are whatever is in shared memory / TMEM (timing only).  Reports SM cycles from first issue to last commit.
+// operands are whatever is in shared memory / TMEM (timing only); I8 = kind::i8 (K = 32) instead of kind::f16 (K = 16).  Reports SM cycles from first issue to last commit.
 __device__ __forceinline__ void umma_ss_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(
@@ -809,7 +1265,16 @@ __device__ __forceinline__ void umma_ss_bf16(uint32_t d_tmem, uint64_t a_desc, u
         : "memory");
 }
 
-template <int N, int NACC, bool TS>
+__device__ __forceinline__ void umma_ss_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int N, int NACC, bool TS, bool I8>
 __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters16, int commit_every16, unsigned long long* cycles_out) {
     extern __shared__ __align__(16) unsigned char smem_probe[];
     const uint32_t smem_base = (smem_u32(smem_probe) + 1023u) & ~1023u;
@@ -836,7 +1301,7 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters16, int commit
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (warp == 0) {
         const bool leader = elect_one();
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        constexpr uint32_t idesc = make_idesc<I8>(BM, N);
         const uint64_t a_desc = make_b_desc(smem_base);           // 128 rows x 64 bf16, SW128
         const uint64_t b_desc = make_b_desc(smem_base + 16384);   // up to 256 rows x 64 bf16
         constexpr uint32_t d_col0 = TMEM_COLS - NACC * N;
@@ -847,8 +1312,12 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters16, int commit
                 for (int j = 0; j < 16; ++j) {
                     const uint32_t d = tmem_base + d_col0 + (uint32_t)((j % NACC) * N);
                     const uint32_t acc = (j < NACC) ? (it > 0 ? 1u : 0u) : 1u;
-                    if (TS)
+                    if (TS && I8)
+                        umma_ts_i8(d, tmem_base + (uint32_t)(j * 8), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
+                    else if (TS)
                         umma_ts_bf16(d, tmem_base + (uint32_t)(j * 8), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
+                    else if (I8)
+                        umma_ss_i8(d, a_desc + (uint64_t)((j & 3) * 2), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
                     else
                         umma_ss_bf16(d, a_desc + (uint64_t)((j & 3) * 2), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
                 }

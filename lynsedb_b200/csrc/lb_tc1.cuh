@@ -14,13 +14,23 @@ namespace tc {
 
 constexpr int S_STAGE_BYTES = KPS * 2 * HALF_BLOCK_BYTES;  // 32 KiB
 constexpr int S_NSTAGES = SMEM_RING_BYTES / S_STAGE_BYTES;  // 6
-constexpr uint32_t S_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-static __global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool I8>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (I8) umma_ts_i8(d_tmem, a_tmem, b_desc, idesc, accumulate);
+    else umma_ts_bf16(d_tmem, a_tmem, b_desc, idesc, accumulate);
+}
+
+template <int MODE_ = CM_F32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
     const int slot = (int)blockIdx.x;
     const int n_rounds = slot < a.n_slots ? a.parts_per_slot : 0;
-    const int first_round = a.sample_tiles > 0 ? -1 : 0;  // round -1 = warm-up over the sample tiles
+    constexpr int first_round = 0;
+    using MT = ModeTraits<MODE_>;
+    using Key = typename MT::Key;
+    using KO = KeyOps<Key>;
+    constexpr bool I8 = MT::kI8;
     extern __shared__ __align__(16) unsigned char smem_tc1[];
     const uint32_t smem_base = (smem_u32(smem_tc1) + 1023u) & ~1023u;
     unsigned char* smem = smem_tc1 + (smem_base - smem_u32(smem_tc1));
@@ -66,10 +76,10 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
             uint32_t stage = 0, phase = 0;
             bool ok = true;
             for (int r = first_round; r < n_rounds && ok; ++r) {
-                const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
+                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
                 if (part >= (uint32_t)a.P) break;
-                const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
-                const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
+                const uint32_t t0 = part * a.tiles_per_part;
+                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
                 for (uint32_t t = t0; t < t1 && ok; ++t) {
                     for (int s = 0; s < spt; ++s) {
                         if (!mbar_wait(empty0 + 8u * stage, phase ^ 1u, abort_flag, 1)) { ok = false; break; }
@@ -95,11 +105,12 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
         bool ok = true;
         uint32_t full_ready = 0, tempty_ready = 0;
         const uint64_t desc_base = make_b_desc(smem_base);
+        const uint32_t S_IDESC = make_idesc<I8>(BM, BN) | (a.idesc_extra != nullptr ? __ldg(a.idesc_extra) : 0u);
         for (int r = first_round; r < n_rounds && ok; ++r, ++item_iter) {
-            const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
+            const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
             if (part >= (uint32_t)a.P) break;
-            const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
-            const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
+            const uint32_t t0 = part * a.tiles_per_part;
+            const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
             if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
             tcgen05_fence_after();
             for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
@@ -117,7 +128,7 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
                     if (leader) {
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
-                            umma_ts_bf16(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), S_IDESC,
+                            umma_ts<I8>(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), S_IDESC,
                                          (k4 == 0) ? (s > 0 ? 1u : 0u) : 1u);
                     }
                     {
@@ -135,7 +146,7 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
                             if (kb < kbc) {
 #pragma unroll
                                 for (int k4 = 0; k4 < 4; ++k4)
-                                    umma_ts_bf16(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
+                                    umma_ts<I8>(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
                                                  bdesc0 + (uint64_t)(kb * ((2 * HALF_BLOCK_BYTES) >> 4) + k4 * 2), S_IDESC, 1u);
                             }
                         }
@@ -153,27 +164,30 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
         const int ql = quad * 32 + lane;              // query within the tile
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        Shortlist sl;
+        Shortlist<Key> sl;
         uint32_t tile_iter = 0;
         bool ok = true;
         const uint32_t gq = (uint32_t)ql;
         const bool q_valid = gq < (uint32_t)a.nq;
+        const float qaux = a.qaux != nullptr ? __ldg(a.qaux + gq) : 0.0f;
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + SMEM_SCRATCH_OFF) + (warp - 2) * EPI_SCRATCH_WORDS;
+        uint2 side_cur = make_uint2(0u, 0u), side_next = make_uint2(0u, 0u);  // side values of rows 2*lane, 2*lane+1 of a tile
         sl.init_floor();
-        sl.set_groups(a.gfloor != nullptr && q_valid ? a.gfloor + (size_t)gq * a.P : nullptr, a.gfloor != nullptr ? a.floor_group : 1, a.P);
         for (int r = first_round; r < n_rounds && ok; ++r) {
-            const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
+            const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
             if (part >= (uint32_t)a.P) break;
-            const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
-            const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
-            if (r == first_round) load_query_to_tmem(a.qb + (size_t)gq * a.Dp, a.Dp, lane_addr);  // the query tile never changes
-            sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0));
-            sl.part = (int)part;
+            const uint32_t t0 = part * a.tiles_per_part;
+            const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+            if (r == first_round) load_query_to_tmem(a.qb + (size_t)gq * a.Dp * 2, a.Dp, lane_addr);  // the query tile never changes
+            sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0), a, gq);
+            if (MT::kBias && t0 < t1) side_cur = __ldg(reinterpret_cast<const uint2*>(a.bias + (size_t)t0 * BN) + lane);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(aready_bar);
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter & 1u;
                 if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter);
+                if (MT::kBias && t + 1 < t1) side_next = __ldg(reinterpret_cast<const uint2*>(a.bias + (size_t)(t + 1) * BN) + lane);
                 if (!mbar_wait(tfull0 + 8u * buf, (tile_iter >> 1) & 1u, abort_flag, 5)) { ok = false; break; }
                 tcgen05_fence_after();
                 uint32_t v[64];
@@ -187,17 +201,21 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
                 if (lane == 0) mbar_arrive(tempty0 + 8u * buf);  // accumulator is in registers: the buffer may be reused
                 if (a.debug_mode & 2) continue;
                 const uint32_t row0 = t * BN;
-                if (a.dump != nullptr && r >= 0) {
+                if (MT::kBias) {
+                    __syncwarp();  // the previous tile's broadcast reads are done
+                    *reinterpret_cast<uint2*>(scratch + 2 * lane) = side_cur;
+                    __syncwarp();
+                    side_cur = side_next;
+                }
+                keys_from_accumulators<MODE_>(v, scratch, qaux);
+                if (a.dump != nullptr) {
                     float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
+                    for (int i = 0; i < 64; ++i) drow[i] = KO::as_f32(KO::from_bits(v[i]));
                 }
                 sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
             }
-            if (ok) {
-                if (r < 0) sl.absorb_sample();
-                else sl.flush(a, gq, part);
-            }
+            if (ok) sl.flush(a, gq, part);
         }
     }
     tcgen05_fence_before();

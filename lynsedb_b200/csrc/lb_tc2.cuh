@@ -36,8 +36,6 @@ struct PairCfg {
     static constexpr int kNAcc = NACC_;
     static constexpr int kDCol = TMEM_COLS - NACC_ * BN_;               // 384 / 256 / 128
     static constexpr int kMaxDp = 2 * kDCol;                            // 768 / 512 / 256
-    // instruction descriptor: D=f32, A=B=bf16, K-major, N=BN_, M=256
-    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
@@ -60,13 +58,23 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t smem_dst, const CUtens
         ::"r"(smem_dst), "l"(tmap), "r"(0), "r"(0), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void umma_pair_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[tmem] * B[smem]^T over both CTAs of the pair: bf16 x bf16 -> f32 (K = 16) or 8-bit x 8-bit -> s32 (K = 32)
+template <bool I8>
+__device__ __forceinline__ void umma_pair_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (I8)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 __device__ __forceinline__ void umma_pair_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -86,7 +94,8 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 // sub-partition, i.e. the same 32 queries, and each takes one 64-column half of every accumulator tile into its own
 // shortlists (TcArgs::lists_per_part = 2): the epilogue is bound by the issue rate of a single warp per sub-partition
 // at large k, and two warps double it.
-template <int BN_, int NACC_ = 2, int EPI_ = 1>
+// MODE_ = CoarseMode: operand kind of the MMAs and how an accumulator becomes the key the epilogue ranks by.
+template <int BN_, int NACC_ = 2, int EPI_ = 1, int MODE_ = CM_F32>
 __global__ void __launch_bounds__(64 + 128 * EPI_, 1)
 coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
     using Cfg = PairCfg<BN_, NACC_>;
@@ -94,7 +103,10 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
     static_assert(EPI_ == 1 || (EPI_ == 2 && BN_ == 128), "two epilogue sets split a 128-column tile in halves");
     constexpr int P_NSTAGES = Cfg::kNStages;
     constexpr int P_STAGE_BYTES = Cfg::kStageBytes;
-    constexpr uint32_t P_IDESC = Cfg::kIdesc;
+    using MT = ModeTraits<MODE_>;
+    using Key = typename MT::Key;
+    using KO = KeyOps<Key>;
+    constexpr bool I8 = MT::kI8;
     constexpr int DCOL = Cfg::kDCol;   // shadows tc::DCOL
     constexpr int BN = BN_;            // shadows tc::BN
     const uint32_t crank = cluster_ctarank();  // 0 = even CTA (issues the MMAs), 1 = odd CTA
@@ -102,7 +114,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
     const int cluster_id = (int)(blockIdx.x >> 1);
     const int mgroup = cluster_id % n_mgroups, slot = cluster_id / n_mgroups;
     const int n_rounds = slot < a.n_slots ? a.parts_per_slot : 0;
-    const int first_round = a.sample_tiles > 0 ? -1 : 0;  // round -1 = warm-up over the sample tiles
+    constexpr int first_round = 0;
     extern __shared__ __align__(16) unsigned char smem_tc2[];
     const uint32_t smem_base = (smem_u32(smem_tc2) + 1023u) & ~1023u;
     unsigned char* smem = smem_tc2 + (smem_base - smem_u32(smem_tc2));
@@ -158,10 +170,10 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             const uint32_t window = (uint32_t)a.window;
             const uint32_t pair_full0 = full0 & PEER_BIT_MASK;
             for (int r = first_round; r < n_rounds && ok; ++r) {
-                const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
+                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
                 if (part >= (uint32_t)a.P) break;
-                const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
-                const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
+                const uint32_t t0 = part * a.tiles_per_part;
+                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
                 for (uint32_t t = t0; t < t1 && ok; ++t) {
                     if (lockstep && seq >= known_min + window) {
                         const uint64_t w0 = globaltimer_ns();
@@ -210,13 +222,14 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             bool ok = true;
             uint32_t full_ready = 0, tempty_ready = 0;
             const uint64_t desc_base = make_b_desc(smem_base);
+            const uint32_t P_IDESC = make_idesc<I8>(256, BN_) | (a.idesc_extra != nullptr ? __ldg(a.idesc_extra) : 0u);
             long long w_tempty = 0, w_full = 0, n_w_tempty = 0, n_w_full = 0;
             const long long mma_c0 = clock64();
             for (int r = first_round; r < n_rounds && ok; ++r, ++item_iter) {
-                const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
+                const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
                 if (part >= (uint32_t)a.P) break;
-                const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
-                const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
+                const uint32_t t0 = part * a.tiles_per_part;
+                const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
                 if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
                 tcgen05_fence_after();
                 for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
@@ -244,7 +257,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                         if (leader) {
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
-                                umma_pair_ts_bf16(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), P_IDESC,
+                                umma_pair_ts<I8>(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), P_IDESC,
                                                   (k4 == 0) ? (s > 0 ? 1u : 0u) : 1u);
                         }
                         {
@@ -262,7 +275,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                                 if (kb < kbc) {
 #pragma unroll
                                     for (int k4 = 0; k4 < 4; ++k4)
-                                        umma_pair_ts_bf16(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
+                                        umma_pair_ts<I8>(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
                                                           bdesc0 + (uint64_t)(kb * (Cfg::kKbBytes >> 4) + k4 * 2), P_IDESC, 1u);
                                 }
                             }
@@ -292,28 +305,41 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
         const int ql = quad * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t even_tempty0 = mapa_rank(tempty0, 0), even_aready = mapa_rank(aready_bar, 0);
-        Shortlist sl;
+        Shortlist<Key> sl;
         uint32_t tile_iter = 0;
         bool ok = true;
         long long e_wait = 0, e_ld = 0, e_scan = 0, e_slow = 0, n_slow = 0, e_max = 0;
         const uint32_t gq = ((uint32_t)mgroup * 2u + crank) * BM + (uint32_t)ql;
         const bool q_valid = gq < (uint32_t)a.nq;
+        const float qaux = a.qaux != nullptr ? __ldg(a.qaux + gq) : 0.0f;
+        // side values of the rows being scanned: fetched one tile ahead (lane l holds rows 2l, 2l+1 of each 64-row half
+        // this warp scans), passed through this warp's shared-memory scratch, read back as broadcasts
+        constexpr int HPW = EPI_ == 2 ? 1 : BN_ / 64;  // halves per warp
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + SMEM_SCRATCH_OFF) + (warp - 2) * EPI_SCRATCH_WORDS;
+        uint2 side_cur[HPW], side_next[HPW];
+        auto side_load = [&](uint32_t t, uint2* dst) {
+#pragma unroll
+            for (int hh = 0; hh < HPW; ++hh) {
+                const int h = EPI_ == 2 ? eset : hh;
+                dst[hh] = __ldg(reinterpret_cast<const uint2*>(a.bias + (size_t)t * BN + h * 64) + lane);
+            }
+        };
         sl.init_floor();
-        sl.set_groups(a.gfloor != nullptr && q_valid ? a.gfloor + (size_t)gq * a.P : nullptr, a.gfloor != nullptr ? a.floor_group : 1, a.P);
         for (int r = first_round; r < n_rounds && ok; ++r) {
-            const uint32_t part = (uint32_t)slot + (uint32_t)max(r, 0) * (uint32_t)a.n_slots;
+            const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
             if (part >= (uint32_t)a.P) break;
-            const uint32_t t0 = r < 0 ? 0u : part * a.tiles_per_part;
-            const uint32_t t1 = r < 0 ? (uint32_t)a.sample_tiles : min(t0 + a.tiles_per_part, a.tiles_total);
-            if (r == first_round && eset == 0) load_query_to_tmem(a.qb + (size_t)gq * a.Dp, a.Dp, lane_addr);  // the query tile never changes
-            sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0));
-            sl.part = (int)part;
+            const uint32_t t0 = part * a.tiles_per_part;
+            const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
+            if (r == first_round && eset == 0) load_query_to_tmem(a.qb + (size_t)gq * a.Dp * 2, a.Dp, lane_addr);  // the query tile never changes
+            sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0), a, gq);
+            if (MT::kBias && t0 < t1) side_load(t0, side_cur);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0 && eset == 0) mbar_arrive_cluster(even_aready);
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter % NACC;
                 if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter);
+                if (MT::kBias && t + 1 < t1) side_load(t + 1, side_next);
                 const long long ec0 = clock64();
                 if (!mbar_wait(tfull0 + 8u * buf, (tile_iter / NACC) & 1u, abort_flag, 5)) { ok = false; break; }
                 const long long ec1 = clock64();
@@ -336,23 +362,30 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                     }
                     if (a.debug_mode & 2) continue;
                     const uint32_t row0 = t * BN + h * 64;
-                    if (a.dump != nullptr && r >= 0) {
+                    const long long sc0 = clock64();
+                    if (MT::kBias) {
+                        __syncwarp();  // the previous half's broadcast reads are done
+                        *reinterpret_cast<uint2*>(scratch + 2 * lane) = side_cur[EPI_ == 2 ? 0 : h];
+                        __syncwarp();
+                    }
+                    keys_from_accumulators<MODE_>(v, scratch, qaux);
+                    if (a.dump != nullptr) {
                         float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
 #pragma unroll
-                        for (int i = 0; i < 64; ++i) drow[i] = __uint_as_float(v[i]);
+                        for (int i = 0; i < 64; ++i) drow[i] = KO::as_f32(KO::from_bits(v[i]));
                     }
-                    const long long sc0 = clock64();
                     sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
                     const long long sd = clock64() - sc0;
                     e_scan += sd;
                     if (sd > 400) { ++n_slow; e_slow += sd; }
                     if (sd > e_max) e_max = sd;
                 }
+                if (MT::kBias) {
+#pragma unroll
+                    for (int hh = 0; hh < HPW; ++hh) side_cur[hh] = side_next[hh];
+                }
             }
-            if (ok) {
-                if (r < 0) sl.absorb_sample();
-                else sl.flush(a, gq, part, (uint32_t)eset);
-            }
+            if (ok) sl.flush(a, gq, part, (uint32_t)eset);
         }
         if (a.prof != nullptr && warp == 2 && lane == 0) {
             unsigned long long* pr = a.prof + (size_t)blockIdx.x * 8;

@@ -11,30 +11,47 @@ using namespace lb;
 
 namespace lb {
 
+constexpr int TC_MAX_ROW_BYTES = 2 * tc::MAX_DP;   // A operand: row_bytes / 4 <= 384 TMEM columns
+constexpr uint32_t TC_HIT_CAP = 4096;              // hit mode: candidates kept per query
+
 int shadow_kind_for(int metric) {
     return metric == LB_IP ? tc::SHADOW_IP : (metric == LB_COSINE ? tc::SHADOW_COSINE : tc::SHADOW_L2);
 }
-static int shadow_dp(const lb_index* idx, int kind) {
-    int d = (int)idx->dim + (kind == tc::SHADOW_L2 ? 3 : 0);
-    return (d + tc::KBLK - 1) / tc::KBLK * tc::KBLK;
+// operand row length in bytes (a multiple of the 128-byte swizzle row)
+static int operand_row_bytes(int dim, int operand) {
+    const int b = operand == tc::OPERAND_BF16 ? dim * 2 : dim;
+    return (b + 127) / 128 * 128;
 }
-bool tc_supported(const lb_index* idx, int metric) {
+// LYNSE_B200_TC_OPERAND = bf16 | u8 | auto (default).  auto: 8-bit operands for IP / cosine when the measured
+// quantisation error of the corpus is within 2x of what bf16 rounding would have cost (uniform-ish data: 1.3x; heavy
+// tails: 5x and more, which would only send queries to the exact-scan fallback); L2 keeps bf16, whose epilogue budget
+// (one subtraction per score) is what bounds narrow rows.
+static int operand_policy() {
+    const char* env = getenv("LYNSE_B200_TC_OPERAND");
+    if (env && (!strcmp(env, "bf16") || !strcmp(env, "0"))) return 0;
+    if (env && (!strcmp(env, "u8") || !strcmp(env, "i8") || !strcmp(env, "1"))) return 1;
+    return 2;
+}
+static int first_operand(const lb_index* idx, int kind) {
+    const int pol = operand_policy();
+    if (kind == tc::SHADOW_L2) return tc::OPERAND_BF16;
+    if (pol == 0 && operand_row_bytes((int)idx->dim, tc::OPERAND_BF16) <= TC_MAX_ROW_BYTES) return tc::OPERAND_BF16;
+    return tc::OPERAND_U8;
+}
+bool tc_supported(lb_index* idx, int metric) {
     if (idx->dtype != LB_F32) return false;
     if (metric != LB_IP && metric != LB_COSINE && metric != LB_L2) return false;
-    return shadow_dp(idx, shadow_kind_for(metric)) <= tc::MAX_DP;
-}
-
-
-// corpus rows per accumulator tile: 128 for CTA pairs when the A operand leaves room for two 128-column accumulators
-static int tc_rows_per_tile(const lb_index* idx, int kind, bool pair) {
-    if (!pair || shadow_dp(idx, kind) > tc::PairCfg<128>::kMaxDp) return 64;
-    return tc_env_int("LYNSE_B200_TC_BN", 128) == 64 ? 64 : 128;
+    const int kind = shadow_kind_for(metric);
+    const Shadow& sh = idx->shadow[kind];
+    if (sh.disabled) return false;
+    const int operand = sh.operand >= 0 ? sh.operand : first_operand(idx, kind);
+    return operand_row_bytes((int)idx->dim, operand) <= TC_MAX_ROW_BYTES;
 }
 
 static int encode_shadow_map(CUtensorMap* out, void* base, int nkb, uint64_t n_tiles, int box_halves, int box_kb) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    // (256 bf16 = 512 B, 8 rows of 512 B = one 4 KiB half block, 2 halves, tiles * K blocks)
+    // (512 B = 4 rows of one K block, 8 of those = one 4 KiB half block, 2 halves, tiles * K blocks); plain bytes
     cuuint64_t gdim[4] = {256, 8, 2, (cuuint64_t)n_tiles * (cuuint64_t)nkb};
     cuuint64_t gstride[3] = {512, 4096, 8192};
     cuuint32_t box[4] = {256, 8, (cuuint32_t)box_halves, (cuuint32_t)box_kb};
@@ -45,37 +62,60 @@ static int encode_shadow_map(CUtensorMap* out, void* base, int nkb, uint64_t n_t
     return LB_OK;
 }
 
-int ensure_shadow(lb_index* idx, int kind) {
-    Shadow& sh = idx->shadow[kind];
-    const int Dp = shadow_dp(idx, kind);
-    const int nkb = Dp / tc::KBLK;
-    if (!idx->max_norm.p) {
-        LB_TRY(idx->max_norm.ensure(3 * sizeof(float)));
-        LB_CUDA_TRY(cudaMemsetAsync(idx->max_norm.p, 0, 3 * sizeof(float), idx->stream));
-    }
-    const uint64_t need_tiles = (ceil_div(idx->n, tc::BN) + 1) & ~(uint64_t)1;  // even: the 128-row kernel reads tiles in pairs
+static int reset_stats(lb_index* idx, Shadow& sh) {
+    LB_TRY(sh.stats.ensure(sizeof(tc::ShadowStats)));
+    tc::ShadowStats z{};
+    z.vmin_ord = 0xFFFFFFFFu;
+    LB_CUDA_TRY(cudaMemcpyAsync(sh.stats.p, &z, sizeof(z), cudaMemcpyHostToDevice, idx->stream));
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));  // z is a stack object
+    return LB_OK;
+}
+static int read_stats(lb_index* idx, Shadow& sh, tc::ShadowStats* out) {
+    LB_CUDA_TRY(cudaMemcpyAsync(out, sh.stats.p, sizeof(*out), cudaMemcpyDeviceToHost, idx->stream));
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    return LB_OK;
+}
+static float bits_f32(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// (Re)allocates the tiled image for `n` rows of `row_bytes` and, when asked, the side array(s) filled with pad values.
+static int shadow_reserve(lb_index* idx, Shadow& sh, uint64_t n, uint64_t reserve_rows, int row_bytes, int n_side, uint32_t pad0, uint32_t pad1) {
+    const int nkb = row_bytes / 128;
+    const uint64_t need_tiles = (ceil_div(n, tc::BN) + 1) & ~(uint64_t)1;  // even: the 128-row kernels read tiles in pairs
     if (need_tiles > sh.cap_tiles) {
-        // grow with head-room; the tiled image is rebuilt from the f32 rows (a derived structure, like the reference's
+        // grow with head-room; the tiled image is rebuilt from the rows (a derived structure, like the reference's
         // lazily built caches that are dropped on append, flat_mmap.rs:341)
         const uint64_t cap = std::max<uint64_t>(need_tiles, sh.cap_tiles + sh.cap_tiles / 2);
-        const uint64_t reserve_tiles = ceil_div(idx->rows.cap / row_bytes(idx), tc::BN);
+        const uint64_t reserve_tiles = ceil_div(reserve_rows, tc::BN);
         const uint64_t want = std::max(cap, std::min<uint64_t>(reserve_tiles, need_tiles * 4));
         const size_t bytes = (size_t)want * nkb * 2 * tc::HALF_BLOCK_BYTES;
         sh.buf.release();
+        sh.side.release();
+        sh.side2.release();
         LB_TRY(sh.buf.ensure(bytes));
         LB_CUDA_TRY(cudaMemsetAsync(sh.buf.p, 0, bytes, idx->stream));
+        const uint64_t side_words = (want + 2) * tc::BN;  // the epilogue prefetches one tile past the last
+        if (n_side >= 1) {
+            LB_TRY(sh.side.ensure(side_words * 4));
+            tc::fill_u32_kernel<<<1024, 256, 0, idx->stream>>>(sh.side.as<uint32_t>(), side_words, pad0);
+        }
+        if (n_side >= 2) {
+            LB_TRY(sh.side2.ensure(side_words * 4));
+            tc::fill_u32_kernel<<<1024, 256, 0, idx->stream>>>(sh.side2.as<uint32_t>(), side_words, pad1);
+        }
+        LB_CUDA_TRY(cudaGetLastError());
         sh.cap_tiles = want;
         sh.rows = 0;
     }
-    sh.Dp = Dp;
-    if (sh.rows < idx->n) {
-        uint64_t first = sh.rows, cnt = idx->n - first;
-        const int warps = 8;
-        tc::build_shadow_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
-            idx->rows.as<float>(), first, cnt, (int)idx->dim, Dp, kind, sh.buf.as<unsigned char>(), idx->max_norm.as<float>() + kind);
-        LB_CUDA_TRY(cudaGetLastError());
-        sh.rows = idx->n;
-    }
+    sh.Dp = row_bytes / 2;
+    return LB_OK;
+}
+static int shadow_maps(Shadow& sh, uint64_t n) {
+    const int nkb = sh.Dp / tc::KBLK;
+    const uint64_t need_tiles = (ceil_div(n, tc::BN) + 1) & ~(uint64_t)1;
     if (sh.tmap_tiles != need_tiles || sh.tmap_ptr != sh.buf.p) {
         const int rem = nkb % tc::KPS;
         for (int kernel = 0; kernel < 2; ++kernel) {
@@ -89,29 +129,195 @@ int ensure_shadow(lb_index* idx, int kind) {
     return LB_OK;
 }
 
-// ---- tensor-core plan ----------------------------------------------------------------------------------------
-int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uint32_t* d_rows, float* d_dists,
-           uint32_t* d_counts, float* dump, const uint64_t* d_allow) {
-    const int kind = shadow_kind_for(metric);
+int ensure_shadow(lb_index* idx, int kind) {
+    Shadow& sh = idx->shadow[kind];
+    if (sh.disabled) return LB_OK;
+    if (sh.operand < 0) sh.operand = first_operand(idx, kind);
+    const int warps = 8;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int rb = operand_row_bytes((int)idx->dim, sh.operand);
+        if (rb > TC_MAX_ROW_BYTES) return fail(LB_UNSUPPORTED, "dimension too large for the tensor-core plan");
+        if (!sh.stats.p) LB_TRY(reset_stats(idx, sh));
+        LB_TRY(shadow_reserve(idx, sh, idx->n, idx->rows.cap / row_bytes(idx), rb, kind == tc::SHADOW_L2 ? 1 : 0, 0x7F800000u /* +inf */, 0u));
+        if (sh.rows < idx->n) {
+            uint64_t first = sh.rows, cnt = idx->n - first;
+            tc::ShadowStats st{};
+            if (sh.operand == tc::OPERAND_U8) {
+                // pass 1: element range of the new rows; a wider range than the image was quantised for rebuilds it
+                tc::shadow_range_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+                    idx->rows.as<float>(), first, cnt, (int)idx->dim, kind, sh.stats.as<tc::ShadowStats>());
+                LB_CUDA_TRY(cudaGetLastError());
+                LB_TRY(read_stats(idx, sh, &st));
+                if (st.nonfinite) {
+                    sh.disabled = true;
+                    return LB_OK;
+                }
+                const float lo = f32_from_orderable(st.vmin_ord), hi = f32_from_orderable(st.vmax_ord);
+                if (first == 0 || lo < sh.range_lo || hi > sh.range_hi) {
+                    sh.range_lo = lo;
+                    sh.range_hi = hi;
+                    sh.c_zero = lo;
+                    sh.c_scale = hi > lo ? (hi - lo) / 255.0f : 1.0f;
+                    first = 0;
+                    cnt = idx->n;
+                    // the error statistics restart with the new quantisation
+                    LB_CUDA_TRY(cudaMemsetAsync(&sh.stats.as<tc::ShadowStats>()->emax_bits, 0, 4, idx->stream));
+                }
+                tc::build_shadow_kernel<tc::OPERAND_U8><<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+                    idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), sh.side.as<float>(),
+                    sh.stats.as<tc::ShadowStats>(), sh.c_scale, sh.c_zero);
+            } else {
+                tc::build_shadow_kernel<tc::OPERAND_BF16><<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+                    idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), sh.side.as<float>(),
+                    sh.stats.as<tc::ShadowStats>(), 1.0f, 0.0f);
+            }
+            LB_CUDA_TRY(cudaGetLastError());
+            LB_TRY(read_stats(idx, sh, &st));
+            sh.rows = idx->n;
+            sh.cmax = bits_f32(st.cmax_bits);
+            sh.emax = bits_f32(st.emax_bits);
+            if (st.nonfinite) {
+                sh.disabled = true;
+                return LB_OK;
+            }
+            if (sh.operand == tc::OPERAND_U8 && operand_policy() == 2 && operand_row_bytes((int)idx->dim, tc::OPERAND_BF16) <= TC_MAX_ROW_BYTES &&
+                sh.emax > 2.0f * bits_f32(st.e16max_bits)) {
+                // 8-bit quantisation is too coarse for this corpus (heavy tails): use the bf16 operand instead
+                if (getenv("LYNSE_B200_TC_TRACE"))
+                    fprintf(stderr, "[lynse_b200] shadow %d: u8 error %.4g against bf16 %.4g -> bf16 operand\n", kind, sh.emax, bits_f32(st.e16max_bits));
+                sh.release();
+                sh.operand = tc::OPERAND_BF16;
+                continue;
+            }
+            if (getenv("LYNSE_B200_TC_TRACE"))
+                fprintf(stderr, "[lynse_b200] shadow %d: operand %s, %llu rows x %d B, max |c'| %.6g, max |c' - c~| %.6g (bf16 would be %.6g)\n", kind,
+                        sh.operand == tc::OPERAND_U8 ? "u8" : "bf16", (unsigned long long)idx->n, rb, sh.cmax, sh.emax, bits_f32(st.e16max_bits));
+        }
+        break;
+    }
+    return shadow_maps(sh, idx->n);
+}
+
+// ---- the packed rows as {0,1} bytes ---------------------------------------------------------------------------
+static int bits_row_bytes(int n_words) { return (n_words * 64 + 127) / 128 * 128; }
+// Worth it from a few tens of queries on (the image is 8x the packed rows; below that the popcount scan is HBM-bound on
+// 1/8 of the bytes), when the image fits in free memory.  LYNSE_B200_BITS_TC=0 turns the plan off.
+bool tc_bits_supported(lb_index* idx, int metric, int n_words, int nq, int k) {
+    if (!metric_binary(metric) || k > 256 || idx->n < 4096) return false;
+    if (tc_env_int("LYNSE_B200_BITS_TC", 1) == 0) return false;
+    if (bits_row_bytes(n_words) > TC_MAX_ROW_BYTES) return false;
+    if (nq < tc_env_int("LYNSE_B200_BITS_TC_MIN_Q", 32)) return false;
+    if (idx->bits_shadow.disabled) return false;
+    if (idx->bits_shadow.rows == idx->n && idx->bits_shadow.buf.p) return true;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    const size_t need = (size_t)(ceil_div(idx->n, tc::BN) + 2) * tc::BN * (size_t)bits_row_bytes(n_words) + (size_t)idx->n * 8 + idx->bits_shadow.buf.cap;
+    return need + (2ull << 30) < free_b + idx->bits_shadow.buf.cap;
+}
+static int ensure_bits_shadow(lb_index* idx, const uint64_t* words, int n_words) {
+    Shadow& sh = idx->bits_shadow;
+    const int rb = bits_row_bytes(n_words);
+    sh.operand = tc::OPERAND_U8;
+    float big = 1e30f;
+    uint32_t big_bits;
+    memcpy(&big_bits, &big, 4);
+    LB_TRY(shadow_reserve(idx, sh, idx->n, idx->rows.cap / row_bytes(idx), rb, 2, 0x3FFFFFFFu, big_bits));
+    if (sh.rows < idx->n) {
+        const uint64_t first = sh.rows, cnt = idx->n - first;
+        const int warps = 8;
+        tc::build_bits_shadow_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+            words, first, cnt, n_words, rb, sh.buf.as<unsigned char>(), sh.side.as<uint32_t>(), sh.side2.as<float>());
+        LB_CUDA_TRY(cudaGetLastError());
+        sh.rows = idx->n;
+    }
+    return shadow_maps(sh, idx->n);
+}
+
+// ---- coarse pass ------------------------------------------------------------------------------------------------
+struct CoarseJob {
+    Shadow* sh = nullptr;
+    int mode = tc::CM_F32;
+    const unsigned char* qb = nullptr;      // prepared A operand rows
+    const float* qaux = nullptr;
+    const uint32_t* bias = nullptr;
+    const uint32_t* idesc_extra = nullptr;
+    int nq = 0, k = 0;
+    const uint64_t* d_allow = nullptr;
+    float* dump = nullptr;
+    // results of the planning, for finalize
+    int n_lists = 0;       // shortlists per query (list mode)
+    bool hit_mode = false;
+    uint32_t* flags = nullptr;   // [0]=kernel error, [1]=n_uncertified, [2..3] clock probe, [4..4+nq) per-query flags, then gthr[nq]
+    uint32_t* gthr = nullptr;
+};
+static bool mode_int_key(int mode) { return mode == tc::CM_I32 || mode == tc::CM_I32_HAMMING; }
+
+template <int MODE>
+static int launch_coarse_mode(int cfg_id, cudaLaunchConfig_t cfg, const Shadow& sh, const tc::TcArgs& args) {
+    switch (cfg_id) {
+        case 0:
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_single_kernel<MODE>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel<MODE>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            break;
+        case 1:
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<64, 2, 1, MODE>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<64, 2, 1, MODE>, sh.tmap_full[1], sh.tmap_rem[1], args));
+            break;
+        case 2:
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 2, 1, MODE>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 2, 1, MODE>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            break;
+        case 3:
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 1, MODE>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3, 1, MODE>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            break;
+        default:
+            cfg.blockDim = dim3(64 + 128 * 2);
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 2, MODE>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3, 2, MODE>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            break;
+    }
+    return LB_OK;
+}
+static int launch_coarse_any(int mode, int cfg_id, const cudaLaunchConfig_t& cfg, const Shadow& sh, const tc::TcArgs& args) {
+    switch (mode) {
+        case tc::CM_F32: return launch_coarse_mode<tc::CM_F32>(cfg_id, cfg, sh, args);
+        case tc::CM_F32_BIAS: return launch_coarse_mode<tc::CM_F32_BIAS>(cfg_id, cfg, sh, args);
+        case tc::CM_I32: return launch_coarse_mode<tc::CM_I32>(cfg_id, cfg, sh, args);
+        case tc::CM_I32_HAMMING: return launch_coarse_mode<tc::CM_I32_HAMMING>(cfg_id, cfg, sh, args);
+        case tc::CM_JACCARD: return launch_coarse_mode<tc::CM_JACCARD>(cfg_id, cfg, sh, args);
+        default: return launch_coarse_mode<tc::CM_DICE>(cfg_id, cfg, sh, args);
+    }
+}
+
+// rows per accumulator tile of the kernel coarse_pass picks for operand rows of row_b bytes
+static int plan_bn(int row_b, bool pair) {
+    return pair && row_b / 4 <= tc::PairCfg<128, 2>::kDCol && tc_env_int("LYNSE_B200_TC_BN", 128) != 64 ? 128 : 64;
+}
+
+// Plans the partitions, seeds the floors when k is large, and launches the coarse kernel(s) on idx->stream.
+static int coarse_pass(lb_index* idx, CoarseJob& job) {
+    Shadow& sh = *job.sh;
+    const int nq = job.nq, k = job.k;
+    const int Dp = sh.Dp;
+    const int row_b = 2 * Dp;
     const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
     // one query tile: one CTA per partition (lb_tc1.cuh); more: CTA pairs (tcgen05 cta_group::2, lb_tc2.cuh)
     const bool pair = n_mtiles >= 2;
     const int cluster = pair ? 2 : 1;
-    const int BN = tc_rows_per_tile(idx, kind, pair);
-    LB_TRY(ensure_shadow(idx, kind));
-    LB_TRY(refresh_small_segments(idx));
-    Shadow& sh = idx->shadow[kind];
-    const int Dp = sh.Dp;
-    const int n_mgroups = (n_mtiles + cluster - 1) / cluster;
-    const int nq_pad = n_mgroups * cluster * tc::BM;
-    LB_TRY(idx->w_qb.ensure((size_t)nq_pad * Dp * 2));
-    LB_TRY(idx->w_qnorm.ensure((size_t)nq * 4));
-    {
-        const int warps = 8;
-        tc::prepare_queries_kernel<<<(nq_pad + warps - 1) / warps, warps * 32, 0, idx->stream>>>(
-            d_queries, nq, nq_pad, (int)idx->dim, Dp, kind, idx->w_qb.as<__nv_bfloat16>(), idx->w_qnorm.as<float>());
-        LB_CUDA_TRY(cudaGetLastError());
+    // kernel shape: 128-row accumulator tiles when the A operand (row_b / 4 TMEM columns) leaves room for two of them,
+    // a third accumulator tile when it leaves room for three, two epilogue warp sets for narrow rows at large k
+    int cfg_id = 0;
+    int BN = 64;
+    if (pair) {
+        const bool bn128 = plan_bn(row_b, true) == 128;
+        const bool nacc3 = bn128 && row_b / 4 <= tc::PairCfg<128, 3>::kDCol && tc_env_int("LYNSE_B200_TC_NACC", 3) == 3;
+        const bool epi2 = nacc3 && k > tc::KP - 4 && tc_env_int("LYNSE_B200_TC_EPI", 2) == 2;
+        cfg_id = epi2 ? 4 : (nacc3 ? 3 : (bn128 ? 2 : 1));
+        BN = bn128 ? 128 : 64;
     }
+    const uint64_t L = cfg_id == 4 ? 2 : 1;  // shortlists per partition
+    const int n_mgroups = (n_mtiles + cluster - 1) / cluster;
     const uint32_t tiles_total = (uint32_t)ceil_div(idx->n, BN);
     // Slots: groups of n_mgroups co-resident clusters (one per query group) that stream the same row partitions in
     // lockstep, so every shadow tile comes from HBM once and is served to the other query groups of the slot from L2.
@@ -119,22 +325,19 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
     uint64_t n_slots = std::max<uint64_t>(1, G / (uint64_t)n_mgroups);
     n_slots = std::min<uint64_t>(n_slots, tiles_total);
     n_slots = std::min<uint64_t>(n_slots, 4096 / tc::KP);
-    // The certification needs the largest partition floor T (the KP-th best coarse score of one partition) to sit
+    // Large k (no single partition floor is far enough past rank k): a pre-pass over 1/64 of the corpus seeds every
+    // query's floor (seed_floor_kernel) at about rank max(10 k, 512) of the corpus, and the main pass appends every row
+    // above that floor to the query's hit buffer (hit mode): no shortlist upkeep in the accumulator hand-off.
+    const bool seeded = k > tc::KP - 4 && tiles_total >= (uint32_t)(64 * 8) * (uint32_t)n_slots && job.dump == nullptr &&
+                        tc_env_int("LYNSE_B200_TC_SEED", 1) != 0;
+    const bool hit_mode = seeded && tc_env_int("LYNSE_B200_TC_HITS", 1) != 0;
+    // List mode: the certification needs the largest partition floor T (the KP-th best coarse key of one partition) to sit
     // well below the k-th best score overall, so the union of the shortlists must reach far past rank k: aim at
     // P*KP >= 32*k candidates (measured on C3, k = 100: P = 36 leaves 1385 of 1024 queries uncertified, P = 72
-    // five, P >= 144 none).  LYNSE_B200_TC_PARTS overrides.
-    // Large k (no single partition floor is far enough past rank k): a pre-pass over 1/64 of the corpus seeds every
-    // query's floor (seed_floor_kernel); the main pass then only needs enough partitions for the true top-k not to
-    // crowd into one 16-entry list: P >= 0.75 k.
-    const bool seeded = k > tc::KP - 4 && tiles_total >= (uint32_t)(64 * 8) * (uint32_t)n_slots && dump == nullptr &&
-                        tc_env_int("LYNSE_B200_TC_SEED", 1) != 0;
-    // two epilogue sets (eight epilogue warps per CTA, two shortlists per partition): 128-row tiles of narrow rows at
-    // large k, where the epilogue's instruction issue rate bounds the pass (LYNSE_B200_TC_EPI=1 turns it off)
-    const bool epi2 = pair && BN == 128 && Dp <= tc::PairCfg<128, 3>::kMaxDp && k > tc::KP - 4 && tc_env_int("LYNSE_B200_TC_EPI", 2) == 2 &&
-                      tc_env_int("LYNSE_B200_TC_NACC", 3) == 3;
-    const uint64_t L = epi2 ? 2 : 1;
+    // five, P >= 144 none).  With a seeded floor the lists only need room for the true top-k: P >= 0.75 k.
+    // LYNSE_B200_TC_PARTS overrides.
     uint64_t parts_per_slot = 1;
-    {
+    if (!hit_mode) {
         uint64_t want = seeded ? ((uint64_t)3 * k + 3) / 4 : ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
         want = ceil_div(want, L);  // a partition contributes L shortlists
         const int env_parts = tc_env_int("LYNSE_B200_TC_PARTS", 0);
@@ -150,12 +353,17 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
     LB_TRY(idx->w_cand_row.ensure((size_t)nq * P_buf * tc::KP * 4));
     LB_TRY(idx->w_cand_thr.ensure((size_t)nq * P_buf * 4));
     LB_TRY(idx->w_flags.ensure((size_t)nq * 8 + 16));
-    uint32_t* flags = idx->w_flags.as<uint32_t>();  // [0]=kernel error, [1]=n_uncertified, [4..]=per-query flags, then gthr[nq]
+    uint32_t* flags = idx->w_flags.as<uint32_t>();
     LB_CUDA_TRY(cudaMemsetAsync(flags, 0, 16, idx->stream));
     LB_CUDA_TRY(cudaMemsetAsync(flags + 4 + nq, 0, (size_t)nq * 4, idx->stream));
+    if (hit_mode) {
+        LB_TRY(idx->w_hits.ensure((size_t)nq * TC_HIT_CAP * 8));
+        LB_TRY(idx->w_hit_count.ensure((size_t)nq * 4));
+        LB_CUDA_TRY(cudaMemsetAsync(idx->w_hit_count.p, 0, (size_t)nq * 4, idx->stream));
+    }
 
     tc::TcArgs a{};
-    a.qb = idx->w_qb.as<__nv_bfloat16>();
+    a.qb = job.qb;
     a.nq = nq;
     a.n_mtiles = n_mtiles;
     a.Dp = Dp;
@@ -165,42 +373,29 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
     a.tiles_per_part = tiles_per_part;
     a.P = (int)P;
     a.lists_per_part = (int)L;
-    a.allow_bits = d_allow;
-    a.cand_score = idx->w_cand_score.as<float>();
+    a.allow_bits = job.d_allow;
+    a.bias = job.bias;
+    a.qaux = job.qaux;
+    a.idesc_extra = job.idesc_extra;
+    a.cand_key = idx->w_cand_score.as<uint32_t>();
     a.cand_row = idx->w_cand_row.as<uint32_t>();
-    a.cand_thr = idx->w_cand_thr.as<float>();
+    a.cand_thr = idx->w_cand_thr.as<uint32_t>();
     a.gthr = flags + 4 + nq;
     // Shared floors: a published floor must have enough rows above it to be far past rank k (the certification needs
-    // the final floor well below the k-th best score).  For k <= KP - 4 the KP-th best score of one partition will do.
-    // For larger k a valid floor is the minimum over a group of m = ceil(10 k / KP) partitions (>= 10 k rows above it);
-    // that variant is implemented (LYNSE_B200_TC_GROUPS=1) but off: on C3 (k = 100) it only becomes available after
-    // the first m partitions (30 % of the pass) and measured 8.9 ms against 7.6 ms without any sharing.
-    const int m_req = k <= tc::KP - 4 ? 1 : (10 * k + tc::KP - 1) / tc::KP;
-    a.share_floor = ((int)P >= m_req && (m_req == 1 || tc_env_int("LYNSE_B200_TC_GROUPS", 0) != 0)) ? 1 : 0;
+    // the final floor well below the k-th best score).  For k <= KP - 4 the KP-th best key of one partition will do.
+    a.share_floor = k <= tc::KP - 4 ? 1 : 0;
     if (seeded) a.share_floor = 2;
-    a.floor_group = m_req;
-    a.gfloor = nullptr;
-    if (a.share_floor == 1 && m_req > 1) {
-        LB_TRY(idx->w_gfloor.ensure((size_t)nq * P * 4));
-        fill_f32_kernel<<<(unsigned)std::min<uint64_t>(ceil_div((uint64_t)nq * P, 256), 1024), 256, 0, idx->stream>>>(
-            idx->w_gfloor.as<float>(), (uint64_t)nq * P, -INFINITY);
-        LB_CUDA_TRY(cudaGetLastError());
-        a.gfloor = idx->w_gfloor.as<float>();
-    }
+    a.hit_count = nullptr;
+    a.hit_buf = nullptr;
+    a.hit_cap = 0;
     a.error_flag = flags;
-    a.dump = dump;
+    a.dump = job.dump;
     a.n_slots = (int)n_slots;
     a.parts_per_slot = (int)parts_per_slot;
     a.window = tc_env_int("LYNSE_B200_TC_WINDOW", 16);
-    a.prefetch_tiles = tc_env_int("LYNSE_B200_TC_PREFETCH", 0);
     a.debug_mode = tc_env_int("LYNSE_B200_TC_DEBUG", 0);
-    // optional warm-up sample (LYNSE_B200_TC_SAMPLE tiles, scanned by every CTA before its partitions; off by default:
-    // with the compact slow path the open gate at the start of a partition no longer stalls the tensor pipe)
-    a.sample_tiles = 0;
-    if (a.share_floor && tiles_per_part >= 1024) a.sample_tiles = std::min<int>(tc_env_int("LYNSE_B200_TC_SAMPLE", 0), (int)tiles_total);
     a.prof = nullptr;
-    const bool want_prof = getenv("LYNSE_B200_TC_PROF") != nullptr;
-    if (want_prof) {
+    if (getenv("LYNSE_B200_TC_PROF") != nullptr) {
         LB_TRY(idx->w_prof.ensure((size_t)idx->sm_count * 8 * 8));
         LB_CUDA_TRY(cudaMemsetAsync(idx->w_prof.p, 0, (size_t)idx->sm_count * 8 * 8, idx->stream));
         a.prof = idx->w_prof.as<unsigned long long>();
@@ -224,31 +419,9 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    auto launch_coarse = [&](const tc::TcArgs& args) -> int {
-        if (epi2) {
-            cudaLaunchConfig_t cfg2 = cfg;
-            cfg2.blockDim = dim3(64 + 128 * 2);
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 2>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg2, tc::coarse_pair_kernel<128, 3, 2>, sh.tmap_full[0], sh.tmap_rem[0], args));
-        } else if (pair && BN == 128 && Dp <= tc::PairCfg<128, 3>::kMaxDp && tc_env_int("LYNSE_B200_TC_NACC", 3) == 3) {
-            // narrow rows leave TMEM room for a third accumulator tile (see PairCfg)
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3>, sh.tmap_full[0], sh.tmap_rem[0], args));
-        } else if (pair && BN == 128) {
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 2>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 2>, sh.tmap_full[0], sh.tmap_rem[0], args));
-        } else if (pair) {
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<64, 2>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<64, 2>, sh.tmap_full[1], sh.tmap_rem[1], args));
-        } else {
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_single_kernel, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel, sh.tmap_full[0], sh.tmap_rem[0], args));
-        }
-        return LB_OK;
-    };
     if (idx->timing) cudaEventRecord(idx->ev[0], idx->stream);
     if (seeded) {
-        // pre-pass: the first 1/64 of the tiles, one partition per slot, private floors; then the seed
+        // pre-pass: the first 1/64 of the tiles, one partition per slot, private floors, shortlists; then the seed
         tc::TcArgs sa = a;
         const uint32_t S = std::max<uint32_t>(tiles_total / 64, (uint32_t)n_slots * 8);
         sa.tiles_total = S;
@@ -257,47 +430,121 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
         sa.P = (int)ceil_div(S, sa.tiles_per_part);
         sa.parts_per_slot = 1;
         sa.share_floor = 0;
-        sa.gfloor = nullptr;
-        sa.sample_tiles = 0;
-        LB_TRY(launch_coarse(sa));
+        LB_TRY(launch_coarse_any(job.mode, cfg_id, cfg, sh, sa));
         const int s_lists = sa.P * (int)L;
         const int sm = next_pow2(s_lists * tc::KP);
-        // aim at ~10 k rows of the whole corpus above the seeded floor
-        int r = (int)ceil_div((uint64_t)10 * k * S, tiles_total);
-        r = std::max(4, std::min(r, s_lists * tc::KP / 2));
+        // aim at ~max(10 k, 512) rows of the whole corpus above the seeded floor
+        const uint64_t want_rows = std::max<uint64_t>((uint64_t)10 * k, 512);
+        int r = (int)ceil_div(want_rows * S, tiles_total);
+        r = std::max(8, std::min(r, s_lists * tc::KP / 2));
         LB_CUDA_TRY(ensure_dynamic_smem(tc::seed_floor_kernel, sm * 8));
-        tc::seed_floor_kernel<<<nq, 256, (size_t)sm * 8, idx->stream>>>(sa.cand_score, sa.cand_row, s_lists, sm, r, a.gthr);
+        tc::seed_floor_kernel<<<nq, 256, (size_t)sm * 8, idx->stream>>>(sa.cand_key, sa.cand_row, s_lists, sm, r, mode_int_key(job.mode) ? 1 : 0, a.gthr);
         LB_CUDA_TRY(cudaGetLastError());
         if (a.progress) LB_CUDA_TRY(cudaMemsetAsync(idx->w_progress.p, 0, (size_t)n_slots * tc::PROGRESS_STRIDE * 4, idx->stream));
         idx->stats.kernels_launched += 2;
+        if (hit_mode) {
+            a.hit_count = idx->w_hit_count.as<uint32_t>();
+            a.hit_buf = idx->w_hits.as<uint2>();
+            a.hit_cap = TC_HIT_CAP;
+        }
     }
-    LB_TRY(launch_coarse(a));
+    LB_TRY(launch_coarse_any(job.mode, cfg_id, cfg, sh, a));
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
+    idx->stats.kernels_launched += 1;
+    idx->stats.n_partitions = (uint32_t)P;
+    job.n_lists = (int)(P * L);
+    job.hit_mode = hit_mode;
+    idx->stats.coarse_operand = sh.operand == tc::OPERAND_U8 ? 1u : 0u;
+    idx->stats.coarse_hit_mode = hit_mode ? 1u : 0u;
+    job.flags = flags;
+    job.gthr = a.gthr;
+    idx->pending_tc.grid = grid;
+    idx->pending_tc.cluster = cluster;
+    idx->pending_tc.n_slots = (int)n_slots;
+    idx->pending_tc.P = (int)P;
+    idx->pending_tc.pair = pair;
+    return LB_OK;
+}
+
+static void fill_fin_candidates(lb_index* idx, const CoarseJob& job, tc::FinArgs& f) {
+    f.cand_key = idx->w_cand_score.as<uint32_t>();
+    f.cand_row = idx->w_cand_row.as<uint32_t>();
+    f.cand_thr = idx->w_cand_thr.as<uint32_t>();
+    f.P = job.n_lists;
+    f.hit_count = job.hit_mode ? idx->w_hit_count.as<uint32_t>() : nullptr;
+    f.hit_buf = job.hit_mode ? idx->w_hits.as<uint2>() : nullptr;
+    f.hit_cap = job.hit_mode ? TC_HIT_CAP : 0;
+    f.gthr = job.gthr;
+    f.int_key = mode_int_key(job.mode) ? 1 : 0;
+    f.M1 = job.hit_mode ? (int)TC_HIT_CAP : next_pow2(job.n_lists * tc::KP);
+    f.R = std::min(1024, std::max(128, next_pow2(4 * job.k)));
+    f.nq = job.nq;
+    f.k = job.k;
+    f.uncertified = job.flags + 4;
+    f.n_uncertified = job.flags + 1;
+}
+
+// ---- tensor-core plan, dense metrics ---------------------------------------------------------------------------
+int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uint32_t* d_rows, float* d_dists,
+           uint32_t* d_counts, float* dump, const uint64_t* d_allow, bool defer_check) {
+    const int kind = shadow_kind_for(metric);
+    LB_TRY(ensure_shadow(idx, kind));
+    LB_TRY(refresh_small_segments(idx));
+    Shadow& sh = idx->shadow[kind];
+    if (sh.disabled) return fail(LB_UNSUPPORTED, "the corpus holds non-finite values: the tensor-core plan is not available");
+    const int row_b = 2 * sh.Dp;
+    const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
+    const int cluster = n_mtiles >= 2 ? 2 : 1;
+    const int nq_pad = (n_mtiles + cluster - 1) / cluster * cluster * tc::BM;
+    LB_TRY(idx->w_qb.ensure((size_t)nq_pad * row_b));
+    LB_TRY(idx->w_qnorm.ensure((size_t)nq * sizeof(tc::QStat)));
+    const int warps = 8;
+    CoarseJob job;
+    job.sh = &sh;
+    if (sh.operand == tc::OPERAND_U8) {
+        LB_TRY(idx->w_qrange.ensure((size_t)nq * 8 + 16));
+        uint32_t* idesc_extra = reinterpret_cast<uint32_t*>(idx->w_qrange.as<float>() + 2 * (size_t)nq);
+        LB_CUDA_TRY(cudaMemsetAsync(idesc_extra, 0, 4, idx->stream));
+        tc::query_range_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, idx->stream>>>(d_queries, nq, (int)idx->dim, kind,
+                                                                                       idx->w_qrange.as<float>(), idesc_extra);
+        tc::quantise_queries_kernel<<<(nq_pad + warps - 1) / warps, warps * 32, 0, idx->stream>>>(
+            d_queries, nq, nq_pad, (int)idx->dim, row_b, kind, idx->w_qrange.as<float>(), idesc_extra, idx->w_qb.as<unsigned char>(),
+            idx->w_qnorm.as<tc::QStat>());
+        LB_CUDA_TRY(cudaGetLastError());
+        idx->stats.kernels_launched += 1;
+        job.idesc_extra = idesc_extra;
+        job.mode = tc::CM_I32;
+    } else {
+        tc::prepare_queries_kernel<<<(nq_pad + warps - 1) / warps, warps * 32, 0, idx->stream>>>(
+            d_queries, nq, nq_pad, (int)idx->dim, row_b, kind, idx->w_qb.as<unsigned char>(), idx->w_qnorm.as<tc::QStat>());
+        LB_CUDA_TRY(cudaGetLastError());
+        job.mode = kind == tc::SHADOW_L2 ? tc::CM_F32_BIAS : tc::CM_F32;
+        job.bias = kind == tc::SHADOW_L2 ? sh.side.as<uint32_t>() : nullptr;
+    }
+    job.qb = idx->w_qb.as<unsigned char>();
+    job.nq = nq;
+    job.k = k;
+    job.d_allow = d_allow;
+    job.dump = dump;
+    LB_TRY(coarse_pass(idx, job));
 
     tc::FinArgs f{};
-    f.cand_score = a.cand_score;
-    f.cand_row = a.cand_row;
-    f.cand_thr = a.cand_thr;
-    f.P = (int)(P * L);
-    f.M1 = next_pow2((int)(P * L) * tc::KP);
-    f.R = std::min(1024, std::max(128, next_pow2(4 * k)));
+    fill_fin_candidates(idx, job, f);
     f.corpus = idx->rows.as<float>();
     f.dim = (int)idx->dim;
     f.queries = d_queries;
-    f.qnorm = idx->w_qnorm.as<float>();
-    f.max_norm = idx->max_norm.as<float>() + kind;
-    f.nq = nq;
-    f.k = k;
+    f.qstat = idx->w_qnorm.as<tc::QStat>();
+    f.sstat = sh.stats.as<tc::ShadowStats>();
+    f.operand = sh.operand;
+    f.c_scale = sh.c_scale;
+    f.c_zero = sh.c_zero;
     f.metric = metric;
-    f.eps_rel = (0.00390625f * 1.01f + (float)Dp * 4.76837158e-7f) * 1.0001f;
     f.small_seg = idx->small_seg.as<uint32_t>();
     f.n_small = idx->n_small;
     f.out_rows = d_rows;
     f.out_dists = d_dists;
     f.out_counts = d_counts;
-    f.uncertified = flags + 4;
-    f.n_uncertified = flags + 1;
     const int fin_threads = nq <= 64 ? 1024 : 256;  // few queries: few blocks, so each gets 1024 threads
     size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)(fin_threads / 8) * tc::FIN_COLS * 4;  // + row buffers
     if (metric_ascending(metric)) {
@@ -308,12 +555,94 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
         tc::finalize_kernel<false><<<nq, fin_threads, fsmem, idx->stream>>>(f);
     }
     LB_CUDA_TRY(cudaGetLastError());
-    idx->stats.kernels_launched += 3;
-    idx->stats.n_partitions = (uint32_t)P;
+    idx->stats.kernels_launched += 2;
     idx->stats.plan_used = 1;
-    idx->stats.algorithmic_bytes = (uint64_t)idx->n * Dp * 2;
+    idx->stats.algorithmic_bytes = (uint64_t)idx->n * row_b;
     idx->stats.algorithmic_flops = 2ull * (uint64_t)nq * idx->n * idx->dim;
 
+    lb_index::PendingTc& p = idx->pending_tc;
+    p.active = true;
+    p.metric = metric;
+    p.nq = nq;
+    p.k = k;
+    p.bits = 0;
+    p.d_queries = d_queries;
+    p.d_allow = d_allow;
+    p.d_rows = d_rows;
+    p.d_dists = d_dists;
+    p.d_counts = d_counts;
+    if (defer_check) return LB_OK;
+    return tc_finish(idx);
+}
+
+// ---- tensor-core plan, binary metrics ---------------------------------------------------------------------------
+int run_tc_bits(lb_index* idx, int metric, const uint64_t* words, int n_words, const uint64_t* d_qwords, int nq, int k, uint32_t* d_rows,
+                float* d_dists, uint32_t* d_counts, const uint64_t* d_allow, bool defer_check) {
+    LB_TRY(ensure_bits_shadow(idx, words, n_words));
+    Shadow& sh = idx->bits_shadow;
+    const int row_b = 2 * sh.Dp;
+    const int n_mtiles = (nq + tc::BM - 1) / tc::BM;
+    const int cluster = n_mtiles >= 2 ? 2 : 1;
+    const int nq_pad = (n_mtiles + cluster - 1) / cluster * cluster * tc::BM;
+    LB_TRY(idx->w_qb.ensure((size_t)nq_pad * row_b));
+    LB_TRY(idx->w_qaux.ensure((size_t)nq_pad * 4));
+    const int warps = 8;
+    tc::prepare_bits_queries_kernel<<<(nq_pad + warps - 1) / warps, warps * 32, 0, idx->stream>>>(d_qwords, nq, nq_pad, n_words, row_b,
+                                                                                                idx->w_qb.as<unsigned char>(), idx->w_qaux.as<float>());
+    LB_CUDA_TRY(cudaGetLastError());
+    CoarseJob job;
+    job.sh = &sh;
+    job.mode = metric == LB_HAMMING ? tc::CM_I32_HAMMING : (metric == LB_DICE ? tc::CM_DICE : tc::CM_JACCARD);
+    job.qb = idx->w_qb.as<unsigned char>();
+    job.qaux = idx->w_qaux.as<float>();
+    job.bias = metric == LB_HAMMING ? sh.side.as<uint32_t>() : sh.side2.as<uint32_t>();
+    job.nq = nq;
+    job.k = k;
+    job.d_allow = d_allow;
+    LB_TRY(coarse_pass(idx, job));
+
+    tc::FinBitsArgs fb{};
+    fill_fin_candidates(idx, job, fb.f);
+    fb.f.metric = metric;
+    fb.f.out_rows = d_rows;
+    fb.f.out_dists = d_dists;
+    fb.f.out_counts = d_counts;
+    fb.words = words;
+    fb.qwords = d_qwords;
+    fb.n_words = n_words;
+    const size_t fsmem = (size_t)(fb.f.M1 + fb.f.R) * 8 + (size_t)n_words * 8;
+    LB_CUDA_TRY(ensure_dynamic_smem(tc::finalize_bits_kernel, (int)fsmem));
+    tc::finalize_bits_kernel<<<nq, 256, fsmem, idx->stream>>>(fb);
+    LB_CUDA_TRY(cudaGetLastError());
+    idx->stats.kernels_launched += 2;
+    idx->stats.plan_used = 3;
+    idx->stats.algorithmic_bytes = (uint64_t)idx->n * row_b;
+    idx->stats.algorithmic_flops = 2ull * (uint64_t)nq * idx->n * (uint64_t)n_words * 64;
+
+    lb_index::PendingTc& p = idx->pending_tc;
+    p.active = true;
+    p.metric = metric;
+    p.nq = nq;
+    p.k = k;
+    p.bits = 1;
+    p.n_words = n_words;
+    p.words = words;
+    p.d_queries = d_qwords;
+    p.d_allow = d_allow;
+    p.d_rows = d_rows;
+    p.d_dists = d_dists;
+    p.d_counts = d_counts;
+    if (defer_check) return LB_OK;
+    return tc_finish(idx);
+}
+
+// ---- certification flags -> exact-scan fallback -----------------------------------------------------------------
+int tc_finish(lb_index* idx, bool* changed) {
+    if (changed) *changed = false;
+    lb_index::PendingTc& p = idx->pending_tc;
+    if (!p.active) return LB_OK;
+    p.active = false;
+    uint32_t* flags = idx->w_flags.as<uint32_t>();
     uint32_t head[4] = {0, 0, 0, 0};
     LB_CUDA_TRY(cudaMemcpyAsync(head, flags, 16, cudaMemcpyDeviceToHost, idx->stream));
     LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
@@ -322,12 +651,13 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
         cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);
         idx->stats.ms_dominant = ms;
     }
-    if (want_prof) {
+    const int nq = p.nq, k = p.k, grid = p.grid;
+    if (getenv("LYNSE_B200_TC_PROF") != nullptr && idx->w_prof.p) {
         std::vector<unsigned long long> pr((size_t)idx->sm_count * 8);
         LB_CUDA_TRY(cudaMemcpy(pr.data(), idx->w_prof.p, pr.size() * 8, cudaMemcpyDeviceToHost));
         double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int n_lead = 0, n_cta = 0;
-        if (pair) {
+        if (p.pair) {
             double sc[5] = {0, 0, 0, 0, 0};
             double mx = 0;
             for (int b = 1; b < grid && b < idx->sm_count; b += 2) {
@@ -358,45 +688,55 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
                     sum[6] / n_cta / (sum[5] / n_lead), sum[7] / n_cta / (sum[5] / n_lead));
     }
     if (getenv("LYNSE_B200_TC_TRACE") && head[3] > 0)
-        fprintf(stderr, "[lynse_b200] coarse kernel: %.3f ms, %.0f SM MHz, grid %d, cluster %d, slots %d, P %d\n", head[3] * 1e-6,
-                (double)head[2] * 16.0 / (double)head[3] * 1e3, grid, cluster, (int)n_slots, (int)P);
+        fprintf(stderr, "[lynse_b200] coarse kernel: %.3f ms, %.0f SM MHz, grid %d, cluster %d, slots %d, P %d, uncertified %u\n", head[3] * 1e-6,
+                (double)head[2] * 16.0 / (double)head[3] * 1e3, grid, p.cluster, p.n_slots, p.P, head[1]);
     if (head[0] != 0)
         return fail(LB_INTERNAL, "tensor-core coarse kernel: barrier wait timed out (code " + std::to_string(head[0]) + ")");
     idx->stats.n_fallback = head[1];
-    if (head[1] > 0) {
-        // Re-run the uncertified queries with the exact scan and overwrite their result slots.
-        std::vector<uint32_t> fl(nq);
-        LB_CUDA_TRY(cudaMemcpy(fl.data(), flags + 4, (size_t)nq * 4, cudaMemcpyDeviceToHost));
-        std::vector<uint32_t> qmap;
-        for (int q = 0; q < nq; ++q)
-            if (fl[q]) qmap.push_back((uint32_t)q);
-        const int ns = (int)qmap.size();
-        LB_TRY(idx->w_sub_q.ensure((size_t)ns * idx->dim * 4));
-        LB_TRY(idx->w_qmap.ensure((size_t)ns * 4));
-        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_qmap.p, qmap.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, idx->stream));
-        for (int i = 0; i < ns; ++i)
-            LB_CUDA_TRY(cudaMemcpyAsync(idx->w_sub_q.as<float>() + (size_t)i * idx->dim, d_queries + (size_t)qmap[i] * idx->dim,
-                                        (size_t)idx->dim * 4, cudaMemcpyDeviceToDevice, idx->stream));
-        ScanRequest r;
+    if (head[1] == 0) return LB_OK;
+    // Re-run the uncertified queries with the exact scan and overwrite their result slots.
+    if (changed) *changed = true;
+    std::vector<uint32_t> fl(nq);
+    LB_CUDA_TRY(cudaMemcpy(fl.data(), flags + 4, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> qmap;
+    for (int q = 0; q < nq; ++q)
+        if (fl[q]) qmap.push_back((uint32_t)q);
+    const int ns = (int)qmap.size();
+    const size_t qrow = p.bits ? (size_t)p.n_words * 8 : (size_t)idx->dim * 4;
+    LB_TRY(idx->w_sub_q.ensure((size_t)ns * qrow));
+    LB_TRY(idx->w_qmap.ensure((size_t)ns * 4));
+    LB_CUDA_TRY(cudaMemcpyAsync(idx->w_qmap.p, qmap.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, idx->stream));
+    for (int i = 0; i < ns; ++i)
+        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_sub_q.as<unsigned char>() + (size_t)i * qrow,
+                                    reinterpret_cast<const unsigned char*>(p.d_queries) + (size_t)qmap[i] * qrow, qrow, cudaMemcpyDeviceToDevice,
+                                    idx->stream));
+    ScanRequest r;
+    if (p.bits) {
+        r.words = p.words;
+        r.n_words = p.n_words;
+        r.qwords = idx->w_sub_q.as<uint64_t>();
+    } else {
         r.corpus = idx->rows.as<float>();
-        r.n_rows = idx->n;
         r.dim = (int)idx->dim;
         r.queries = idx->w_sub_q.as<float>();
-        r.nq = ns;
-        r.k = k;
-        r.metric = metric;
         r.small_seg = idx->small_seg.as<uint32_t>();
         r.n_small = idx->n_small;
-        r.allow_bits = d_allow;
-        r.qmap = idx->w_qmap.as<uint32_t>();
-        r.out_rows = d_rows;
-        r.out_dists = d_dists;
-        r.out_counts = d_counts;
-        int kern = 0;
-        LB_TRY(run_scan(idx, r, &kern, nullptr));
-        idx->stats.kernels_launched += kern;
-        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
     }
+    r.n_rows = idx->n;
+    r.nq = ns;
+    r.k = k;
+    r.metric = p.metric;
+    r.allow_bits = p.d_allow;
+    r.qmap = idx->w_qmap.as<uint32_t>();
+    r.out_rows = p.d_rows;
+    r.out_dists = p.d_dists;
+    r.out_counts = p.d_counts;
+    int kern = 0;
+    const lb_search_stats keep = idx->stats;
+    LB_TRY(run_scan(idx, r, &kern, nullptr));
+    idx->stats = keep;
+    idx->stats.kernels_launched += kern;
+    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
     return LB_OK;
 }
 
@@ -405,22 +745,23 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
 extern "C" {
 
 // ---- diagnostics ------------------------------------------------------------------------------------------------------------------
-int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uint32_t n, uint32_t dim, float* out) {
+int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uint32_t n, uint32_t dim, int operand, float* out) {
     if (!queries || !rows || !out || nq == 0 || n == 0) return fail(LB_INVALID_ARGUMENT, "bad arguments");
+    if (operand != tc::OPERAND_BF16 && operand != tc::OPERAND_U8) return fail(LB_INVALID_ARGUMENT, "operand must be 0 (bf16) or 1 (u8)");
     int device = 0;
     LB_CUDA_TRY(cudaGetDevice(&device));
     lb_index* idx = nullptr;
     LB_TRY(lb_index_create(&idx, dim, LB_F32, device));
     int st = lb_index_append_f32(idx, rows, n);
     float* dump = nullptr;
-    if (st == LB_OK && !tc_supported(idx, LB_IP)) st = fail(LB_UNSUPPORTED, "dimension too large for the tensor-core path");
+    if (st == LB_OK && operand_row_bytes((int)dim, operand) > TC_MAX_ROW_BYTES) st = fail(LB_UNSUPPORTED, "dimension too large for the tensor-core path");
     if (st == LB_OK) {
         std::lock_guard<std::mutex> lock(idx->mu);
         DeviceGuard g(idx->device);
+        idx->shadow[tc::SHADOW_IP].operand = operand;
         int n_mtiles = ((int)nq + tc::BM - 1) / tc::BM;
         n_mtiles = (n_mtiles + 1) & ~1;  // room for the padded query tile of a 2-CTA cluster
-        const int dbg_bn = tc_rows_per_tile(idx, tc::SHADOW_IP, (int)nq > tc::BM);
-        const size_t ld = (size_t)ceil_div(n, dbg_bn) * dbg_bn;
+        const size_t ld = (size_t)ceil_div(n, 128) * 128;  // the kernel's own leading dimension is tiles * rows per tile <= this
         const size_t dump_elems = (size_t)n_mtiles * tc::BM * ld;
         const int k = (int)std::min<uint32_t>(n, 10);
         cudaError_t e = cudaMalloc(&dump, dump_elems * 4);
@@ -438,7 +779,9 @@ int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uin
             st = run_tc(idx, LB_IP, idx->w_queries.as<float>(), (int)nq, k, idx->w_out_rows.as<uint32_t>(),
                         idx->w_out_dists.as<float>(), idx->w_out_counts.as<uint32_t>(), dump);
         if (st == LB_OK) {
-            e = cudaMemcpy2D(out, (size_t)n * 4, dump, ld * 4, (size_t)n * 4, nq, cudaMemcpyDeviceToHost);
+            const int bn = plan_bn(2 * idx->shadow[tc::SHADOW_IP].Dp, (int)nq > tc::BM);
+            const size_t kld = (size_t)ceil_div(n, bn) * bn;
+            e = cudaMemcpy2D(out, (size_t)n * 4, dump, kld * 4, (size_t)n * 4, nq, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) st = fail(LB_CUDA, cudaGetErrorString(e));
         }
     }
@@ -449,32 +792,34 @@ int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uin
     return st;
 }
 
-int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int grid, uint64_t* cycles_total, uint64_t* cycles_issue) {
+int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int i8, int grid, uint64_t* cycles_total, uint64_t* cycles_issue) {
     if (iters < 16 || grid < 1) return fail(LB_INVALID_ARGUMENT, "bad probe arguments");
     unsigned long long* d = nullptr;
     LB_CUDA_TRY(cudaMalloc(&d, (size_t)grid * 16));
     const size_t smem = 49152 + 64 + 1024;
     cudaError_t e = cudaSuccess;
     bool found = false;
-#define LB_PROBE(NN, NA, TSV)                                                                                         \
-    if (!found && n == NN && n_acc == NA && (a_in_tmem != 0) == TSV) {                                              \
-        found = true;                                                                                                \
-        e = cudaFuncSetAttribute(tc::mma_rate_kernel<NN, NA, TSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) {                                                                                      \
-            tc::mma_rate_kernel<NN, NA, TSV><<<grid, 64, smem>>>(iters / 16, tc_env_int("LYNSE_B200_PROBE_COMMIT", 0), d);                                     \
-            e = cudaDeviceSynchronize();                                                                             \
-        }                                                                                                            \
+#define LB_PROBE(NN, NA, TSV, I8V)                                                                                         \
+    if (!found && n == NN && n_acc == NA && (a_in_tmem != 0) == TSV && (i8 != 0) == I8V) {                                 \
+        found = true;                                                                                                      \
+        e = cudaFuncSetAttribute(tc::mma_rate_kernel<NN, NA, TSV, I8V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) {                                                                                            \
+            tc::mma_rate_kernel<NN, NA, TSV, I8V><<<grid, 64, smem>>>(iters / 16, tc_env_int("LYNSE_B200_PROBE_COMMIT", 0), d); \
+            e = cudaDeviceSynchronize();                                                                                   \
+        }                                                                                                                  \
     }
-    LB_PROBE(64, 1, true)
-    LB_PROBE(64, 2, true)
-    LB_PROBE(128, 1, true)
-    LB_PROBE(64, 1, false)
-    LB_PROBE(64, 2, false)
-    LB_PROBE(64, 4, false)
-    LB_PROBE(128, 1, false)
-    LB_PROBE(128, 2, false)
-    LB_PROBE(256, 1, false)
-    LB_PROBE(256, 2, false)
+    LB_PROBE(64, 1, true, false)
+    LB_PROBE(64, 2, true, false)
+    LB_PROBE(128, 1, true, false)
+    LB_PROBE(128, 2, true, false)
+    LB_PROBE(64, 2, false, false)
+    LB_PROBE(128, 2, false, false)
+    LB_PROBE(256, 2, false, false)
+    LB_PROBE(64, 2, true, true)
+    LB_PROBE(128, 1, true, true)
+    LB_PROBE(128, 2, true, true)
+    LB_PROBE(128, 2, false, true)
+    LB_PROBE(256, 2, false, true)
 #undef LB_PROBE
     if (!found) {
         cudaFree(d);

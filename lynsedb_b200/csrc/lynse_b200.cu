@@ -119,8 +119,10 @@ static int ensure_mass_stats(lb_index* idx) {
 // d_queries: f32 [nq][dim] (LB_F32 index) or u64 [nq][n_words] (LB_PACKED_U64 index); results [nq][k], k <= n.
 enum { SCORE_FLAT = 0, SCORE_PAIRWISE = 1, SCORE_F16_ROWS = 2 };
 
+// defer_tc_check: a tensor-core plan leaves its certification flags unread (the caller runs tc_finish after whatever
+// it enqueues behind the search); implies no synchronisation here.
 static int search_device_impl(lb_index* idx, int metric, const void* d_queries, int nq, int k, const uint64_t* d_allow,
-                              uint32_t* d_rows, float* d_dists, uint32_t* d_counts, bool sync_at_end = true) {
+                              uint32_t* d_rows, float* d_dists, uint32_t* d_counts, bool sync_at_end = true, bool defer_tc_check = false) {
     idx->stats = lb_search_stats{};
     if (idx->timing) cudaEventRecord(idx->ev[2], idx->stream);
     int kernels = 0;
@@ -147,21 +149,31 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
             words = idx->packed.as<uint64_t>();
             qwords = idx->w_qwords.as<uint64_t>();
         }
-        ScanRequest r;
-        r.words = words;
-        r.n_rows = idx->n;
-        r.n_words = nw;
-        r.qwords = qwords;
-        r.nq = nq;
-        r.k = k;
-        r.metric = metric;
-        r.allow_bits = d_allow;
-        r.out_rows = d_rows;
-        r.out_dists = d_dists;
-        r.out_counts = d_counts;
-        LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
-        idx->stats.plan_used = 2;
-        idx->stats.algorithmic_bytes = (uint64_t)idx->n * nw * 8;
+        if (idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT && tc_bits_supported(idx, metric, nw, nq, k) &&
+            (d_allow == nullptr || idx->allow_count >= (uint64_t)std::max(1024, 32 * k))) {
+            // a large batch: the popcounts are a {0,1} contraction on the tensor cores (exact: integer accumulators),
+            // shortlist -> exact counts on the packed rows -> certified, as for the dense metrics
+            idx->stats.kernels_launched = kernels;
+            LB_TRY(run_tc_bits(idx, metric, words, nw, qwords, nq, k, d_rows, d_dists, d_counts, d_allow, defer_tc_check));
+            kernels = idx->stats.kernels_launched;
+            ms_dom = idx->stats.ms_dominant;
+        } else {
+            ScanRequest r;
+            r.words = words;
+            r.n_rows = idx->n;
+            r.n_words = nw;
+            r.qwords = qwords;
+            r.nq = nq;
+            r.k = k;
+            r.metric = metric;
+            r.allow_bits = d_allow;
+            r.out_rows = d_rows;
+            r.out_dists = d_dists;
+            r.out_counts = d_counts;
+            LB_TRY(run_scan(idx, r, &kernels, &ms_dom));
+            idx->stats.plan_used = 2;
+            idx->stats.algorithmic_bytes = (uint64_t)idx->n * nw * 8;
+        }
     } else if (idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT && tc_supported(idx, metric) && k <= 256 && idx->n >= 64 &&
                // a row filter rides along as a mask on the hit bits; with few allowed rows the shortlists cannot fill
                // and certification would send everything to the exact scan anyway
@@ -169,7 +181,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
                // a handful of queries over a small corpus is a latency case: the exact scan is two launches, the tensor
                // plan three plus a lazily built shadow (100k x 128, one query: 85 against 131 us of device time)
                !(nq <= 4 && (uint64_t)idx->n * idx->dim * 4 < (256ull << 20))) {
-        LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr, d_allow));
+        LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr, d_allow, defer_tc_check));
         kernels = idx->stats.kernels_launched;
         ms_dom = idx->stats.ms_dominant;
     } else {
@@ -246,10 +258,10 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
         idx->stats.algorithmic_bytes = (uint64_t)idx->n * idx->dim * 4;
     }
     if (idx->timing) cudaEventRecord(idx->ev[3], idx->stream);
-    if (sync_at_end || idx->timing) LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));  // (the host path syncs after its copies)
+    if ((sync_at_end || idx->timing) && !idx->pending_tc.active) LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));  // (the host path syncs after its copies)
     idx->stats.kernels_launched = kernels;
     idx->stats.ms_dominant = ms_dom;
-    if (idx->timing) {
+    if (idx->timing && !idx->pending_tc.active) {
         float ms = 0;
         cudaEventElapsedTime(&ms, idx->ev[2], idx->ev[3]);
         idx->stats.ms_total = ms;
@@ -344,6 +356,7 @@ void lb_index_destroy(lb_index* idx) {
         for (DevBuf* b : bufs) b->release();
         idx->h_in.release();
         idx->h_out.release();
+        idx->h_tails.release();
         for (int i = 0; i < 4; ++i)
             if (idx->ev[i]) cudaEventDestroy(idx->ev[i]);
         for (int i = 0; i < 8; ++i)
@@ -1371,24 +1384,34 @@ int lb_comm_barrier(lb_comm* c) {
 
 // ---- sharded search: local search -> ncclAllGather -> GPU merge by (score, global row) ------------------------------------------------
 namespace lb {
-// block layout per rank: rows u32 [nq*k] | dists f32 [nq*k] | counts u32 [nq] | pad to 8 | base u64
+// block layout per rank: rows u32 [nq*k] | dists f32 [nq*k] | counts u32 [nq] | pad to 8 | tail: base u64, uncertified u32, status u32
+constexpr size_t SHARD_TAIL_BYTES = 16;
 static size_t shard_block_bytes(uint32_t nq, uint32_t k) {
     size_t b = (size_t)nq * k * 8 + (size_t)nq * 4;
     b = (b + 7) & ~(size_t)7;
-    return b + 8;
+    return b + SHARD_TAIL_BYTES;
 }
-__global__ void shard_pack_tail_kernel(unsigned char* block, size_t base_off, uint64_t row_base) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *reinterpret_cast<uint64_t*>(block + base_off) = row_base;
+// tail of this rank's block: its row base, how many queries of its tensor-core search still wait for the exact-scan
+// fallback (flags[1], read on the device: no host round trip before the collective) and its status (non-zero = this
+// rank's search failed; every rank sees it after the gather and fails with it)
+static __global__ void shard_pack_tail_kernel(unsigned char* block, size_t tail_off, uint64_t row_base, const uint32_t* tc_flags, uint32_t status) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        *reinterpret_cast<uint64_t*>(block + tail_off) = row_base;
+        uint32_t* w = reinterpret_cast<uint32_t*>(block + tail_off + 8);
+        w[0] = tc_flags != nullptr ? tc_flags[1] : 0u;
+        w[1] = status != 0u ? status : (tc_flags != nullptr && tc_flags[0] != 0u ? (uint32_t)LB_INTERNAL : 0u);
+    }
 }
-// one CTA per query; G*k <= 4096
-__global__ void __launch_bounds__(256) merge_shards_kernel(const unsigned char* gathered, int G, size_t block_bytes, int nq, int k,
-                                                           int M, int asc, uint64_t* out_rows, float* out_dists,
-                                                           uint32_t* out_counts) {
+// one CTA per query; G*k <= 4096.  Blocks arrive in rank order and ranks hold ascending row ranges (asserted by the
+// caller through the gathered bases), so (score, shard, position) is (score, global row).
+static __global__ void __launch_bounds__(256) merge_shards_kernel(const unsigned char* gathered, int G, size_t block_bytes, int nq, int k,
+                                                                  int M, int asc, uint64_t* out_rows, float* out_dists,
+                                                                  uint32_t* out_counts) {
     extern __shared__ __align__(16) unsigned char smem_shard[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_shard);
     const int q = blockIdx.x;
     const size_t dists_off = (size_t)nq * k * 4, counts_off = (size_t)nq * k * 8;
-    const size_t base_off = block_bytes - 8;
+    const size_t base_off = block_bytes - SHARD_TAIL_BYTES;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         uint64_t key = KEY_NONE;
         if (i < G * k) {
@@ -1428,33 +1451,83 @@ __global__ void __launch_bounds__(256) merge_shards_kernel(const unsigned char* 
     if (threadIdx.x == 0) out_counts[q] = n_valid;
 }
 
+// Everything is enqueued on the index stream without a host round trip: search (certification flags left on the
+// device), tail, all-gather, merge; then ONE synchronisation reads the gathered tails.  Only when some rank reports
+// uncertified queries (every rank sees the same tails, so every rank takes the same branch) do the ranks run their
+// exact-scan fallbacks and repeat gather + merge.  A rank whose local search failed still takes part in the collective,
+// with its status in the tail, so all ranks fail together instead of hanging in ncclAllGather.
 static int sharded_search_device_impl(lb_comm* comm, lb_index* idx, int metric, const void* d_queries, uint32_t nq, uint32_t k,
-                                      uint64_t row_base, uint64_t* d_out_rows, float* d_out_dists, uint32_t* d_out_counts) {
+                                      uint64_t row_base, uint64_t* d_out_rows, float* d_out_dists, uint32_t* d_out_counts,
+                                      const uint64_t* d_allow = nullptr) {
     const int G = comm ? comm->world : 1;
     if ((uint64_t)G * k > 4096) return fail(LB_UNSUPPORTED, "world_size * k must not exceed 4096");
     const size_t bb = shard_block_bytes(nq, k);
     LB_TRY(idx->w_send.ensure(bb));
     LB_TRY(idx->w_recv.ensure(bb * G));
+    LB_TRY(idx->h_tails.ensure((size_t)G * SHARD_TAIL_BYTES));
     unsigned char* send = idx->w_send.as<unsigned char>();
     uint32_t* s_rows = reinterpret_cast<uint32_t*>(send);
     float* s_dists = reinterpret_cast<float*>(send + (size_t)nq * k * 4);
     uint32_t* s_counts = reinterpret_cast<uint32_t*>(send + (size_t)nq * k * 8);
-    LB_TRY(search_device_impl(idx, metric, d_queries, (int)nq, (int)k, nullptr, s_rows, s_dists, s_counts));
+    int local_status = k > idx->n ? fail(LB_INVALID_ARGUMENT, "k exceeds the rows of this shard") : LB_OK;
+    if (local_status == LB_OK)
+        local_status = search_device_impl(idx, metric, d_queries, (int)nq, (int)k, d_allow, s_rows, s_dists, s_counts, false, true);
+    const std::string local_error = local_status != LB_OK ? std::string(lb_last_error()) : std::string();
     const lb_search_stats local = idx->stats;
-    shard_pack_tail_kernel<<<1, 32, 0, idx->stream>>>(send, bb - 8, row_base);
-    LB_CUDA_TRY(cudaGetLastError());
-    const unsigned char* gathered = send;
-    if (G > 1) {
-        LB_TRY(comm_allgather_on(comm, send, idx->w_recv.p, bb, idx->stream));
-        gathered = idx->w_recv.as<unsigned char>();
-    }
     const int M = std::max(2, next_pow2(G * (int)k));
-    merge_shards_kernel<<<nq, 256, (size_t)M * 8, idx->stream>>>(gathered, G, bb, (int)nq, (int)k, M, metric_ascending(metric) ? 1 : 0,
-                                                               d_out_rows, d_out_dists, d_out_counts);
-    LB_CUDA_TRY(cudaGetLastError());
+    const unsigned char* gathered = G > 1 ? idx->w_recv.as<unsigned char>() : send;
+    auto gather_and_merge = [&]() -> int {
+        shard_pack_tail_kernel<<<1, 32, 0, idx->stream>>>(send, bb - SHARD_TAIL_BYTES, row_base,
+                                                         idx->pending_tc.active ? idx->w_flags.as<uint32_t>() : nullptr, (uint32_t)local_status);
+        LB_CUDA_TRY(cudaGetLastError());
+        if (G > 1) LB_TRY(comm_allgather_on(comm, send, idx->w_recv.p, bb, idx->stream));
+        merge_shards_kernel<<<nq, 256, (size_t)M * 8, idx->stream>>>(gathered, G, bb, (int)nq, (int)k, M, metric_ascending(metric) ? 1 : 0,
+                                                                   d_out_rows, d_out_dists, d_out_counts);
+        LB_CUDA_TRY(cudaGetLastError());
+        LB_CUDA_TRY(cudaMemcpy2DAsync(idx->h_tails.p, SHARD_TAIL_BYTES, gathered + bb - SHARD_TAIL_BYTES, bb, SHARD_TAIL_BYTES, (size_t)G,
+                                      cudaMemcpyDeviceToHost, idx->stream));
+        return LB_OK;
+    };
+    LB_TRY(gather_and_merge());
     LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
-    idx->stats = local;
-    idx->stats.kernels_launched += 2 + (G > 1 ? 1 : 0);
+    const unsigned char* tails = reinterpret_cast<const unsigned char*>(idx->h_tails.p);
+    uint32_t any_uncertified = 0, any_status = 0;
+    uint64_t prev_base = 0;
+    bool ascending = true;
+    for (int g = 0; g < G; ++g) {
+        uint64_t base;
+        uint32_t w[2];
+        memcpy(&base, tails + (size_t)g * SHARD_TAIL_BYTES, 8);
+        memcpy(w, tails + (size_t)g * SHARD_TAIL_BYTES + 8, 8);
+        any_uncertified += w[0];
+        if (w[1] != 0 && any_status == 0) any_status = w[1];
+        if (g > 0 && base < prev_base) ascending = false;
+        prev_base = base;
+    }
+    if (any_status != 0) {
+        idx->pending_tc.active = false;
+        if (local_status != LB_OK) return fail(local_status, local_error);
+        return fail((int)any_status, "a peer rank's shard search failed");
+    }
+    if (!ascending) {
+        idx->pending_tc.active = false;
+        return fail(LB_INVALID_ARGUMENT, "row bases must ascend with the rank (the merge breaks ties by shard order)");
+    }
+    int extra_kernels = 0;
+    lb_search_stats fin = local;
+    if (idx->pending_tc.active) {
+        // reads this rank's flags (stream already idle) and runs its fallback when it has one
+        idx->stats = local;
+        LB_TRY(tc_finish(idx));
+        fin = idx->stats;
+    }
+    if (any_uncertified != 0) {
+        LB_TRY(gather_and_merge());
+        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        extra_kernels = 2 + (G > 1 ? 1 : 0);
+    }
+    idx->stats = fin;
+    idx->stats.kernels_launched += 2 + (G > 1 ? 1 : 0) + extra_kernels;
     return LB_OK;
 }
 }  // namespace lb
@@ -1463,7 +1536,8 @@ static int sharded_check(lb_comm* comm, lb_index* idx, int metric, uint32_t nq, 
     if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
     LB_TRY(check_metric(metric));
     if (comm && comm->device != idx->device) return fail(LB_INVALID_ARGUMENT, "communicator and index live on different devices");
-    if (k == 0 || k > (uint32_t)MAX_K || k > idx->n) return fail(LB_INVALID_ARGUMENT, "k must be in [1, min(shard rows, 2048)] for a sharded search");
+    // rank-uniform preconditions only: anything that depends on this rank's shard is reported through the collective
+    if (k == 0 || k > (uint32_t)MAX_K) return fail(LB_INVALID_ARGUMENT, "k must be in [1, 2048] for a sharded search");
     if (nq == 0 || nq > (uint32_t)QUERY_BATCH) return fail(LB_INVALID_ARGUMENT, "nq must be in [1, 4096] for a sharded search");
     return LB_OK;
 }
@@ -1477,37 +1551,126 @@ int lb_sharded_search_device(lb_comm* comm, lb_index* idx, int metric, const voi
     return sharded_search_device_impl(comm, idx, metric, d_queries, nq, k, row_base, d_out_rows, d_out_dists, d_out_counts);
 }
 
+// A host pointer the device can address directly (pinned, e.g. from lb_host_malloc): the merge kernel writes the
+// result there itself, so no copy follows it.
+static void* device_alias_of_host(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 static int sharded_search_host(lb_comm* comm, lb_index* idx, int metric, const void* queries, size_t query_row_bytes, uint32_t nq,
-                               uint32_t k, uint64_t row_base, uint64_t* out_rows, float* out_dists, uint32_t* out_counts) {
+                               uint32_t k, uint64_t row_base, const uint64_t* allow_bits, uint64_t allow_words, uint64_t* out_rows,
+                               float* out_dists, uint32_t* out_counts) {
     LB_TRY(sharded_check(comm, idx, metric, nq, k));
     if (!queries || !out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(idx->mu);
     DeviceGuard g(idx->device);
     LB_TRY(idx->w_queries.ensure((size_t)nq * query_row_bytes));
-    LB_TRY(idx->w_g_rows.ensure((size_t)nq * k * 8));
-    LB_TRY(idx->w_g_dists.ensure((size_t)nq * k * 4));
-    LB_TRY(idx->w_g_counts.ensure((size_t)nq * 4));
+    const uint64_t* d_allow = nullptr;
+    if (allow_bits != nullptr) {
+        const uint64_t need_words = (idx->n + 63) / 64;
+        if (allow_words < need_words) return fail(LB_INVALID_ARGUMENT, "allow_bits is shorter than the shard");
+        LB_TRY(idx->w_allow.ensure(need_words * 8));
+        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_allow.p, allow_bits, need_words * 8, cudaMemcpyHostToDevice, idx->stream));
+        uint64_t cnt = 0;
+        for (uint64_t w = 0; w < need_words; ++w) {
+            uint64_t x = allow_bits[w];
+            if (w + 1 == need_words && (idx->n & 63)) x &= (1ull << (idx->n & 63)) - 1;
+            cnt += (uint64_t)__builtin_popcountll(x);
+        }
+        idx->allow_count = cnt;
+        d_allow = idx->w_allow.as<uint64_t>();
+    }
+    uint64_t* a_rows = reinterpret_cast<uint64_t*>(device_alias_of_host(out_rows));
+    float* a_dists = reinterpret_cast<float*>(device_alias_of_host(out_dists));
+    uint32_t* a_counts = reinterpret_cast<uint32_t*>(device_alias_of_host(out_counts));
+    const bool direct = a_rows && a_dists && a_counts;
+    if (!direct) {
+        LB_TRY(idx->w_g_rows.ensure((size_t)nq * k * 8));
+        LB_TRY(idx->w_g_dists.ensure((size_t)nq * k * 4));
+        LB_TRY(idx->w_g_counts.ensure((size_t)nq * 4));
+        a_rows = idx->w_g_rows.as<uint64_t>();
+        a_dists = idx->w_g_dists.as<float>();
+        a_counts = idx->w_g_counts.as<uint32_t>();
+    }
     LB_CUDA_TRY(cudaMemcpyAsync(idx->w_queries.p, queries, (size_t)nq * query_row_bytes, cudaMemcpyHostToDevice, idx->stream));
-    LB_TRY(sharded_search_device_impl(comm, idx, metric, idx->w_queries.p, nq, k, row_base, idx->w_g_rows.as<uint64_t>(),
-                                      idx->w_g_dists.as<float>(), idx->w_g_counts.as<uint32_t>()));
-    LB_CUDA_TRY(cudaMemcpyAsync(out_rows, idx->w_g_rows.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, idx->stream));
-    LB_CUDA_TRY(cudaMemcpyAsync(out_dists, idx->w_g_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, idx->stream));
-    LB_CUDA_TRY(cudaMemcpyAsync(out_counts, idx->w_g_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
-    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    LB_TRY(sharded_search_device_impl(comm, idx, metric, idx->w_queries.p, nq, k, row_base, a_rows, a_dists, a_counts, d_allow));
+    if (!direct) {
+        LB_CUDA_TRY(cudaMemcpyAsync(out_rows, idx->w_g_rows.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaMemcpyAsync(out_dists, idx->w_g_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaMemcpyAsync(out_counts, idx->w_g_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
     return LB_OK;
 }
 
 int lb_sharded_search(lb_comm* comm, lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, uint64_t row_base,
                       uint64_t* out_rows, float* out_dists, uint32_t* out_counts) {
     if (idx && idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "use lb_sharded_search_packed for a packed index");
-    return sharded_search_host(comm, idx, metric, queries, idx ? (size_t)idx->dim * 4 : 0, nq, k, row_base, out_rows, out_dists, out_counts);
+    return sharded_search_host(comm, idx, metric, queries, idx ? (size_t)idx->dim * 4 : 0, nq, k, row_base, nullptr, 0, out_rows, out_dists, out_counts);
+}
+
+int lb_sharded_search_filtered(lb_comm* comm, lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, uint64_t row_base,
+                               const uint64_t* allow_bits, uint64_t allow_words, uint64_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    if (idx && idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "use lb_sharded_search_packed for a packed index");
+    return sharded_search_host(comm, idx, metric, queries, idx ? (size_t)idx->dim * 4 : 0, nq, k, row_base, allow_bits, allow_words, out_rows,
+                               out_dists, out_counts);
 }
 
 int lb_sharded_search_packed(lb_comm* comm, lb_index* idx, int metric, const uint64_t* query_words, uint32_t nq, uint32_t k,
                              uint64_t row_base, uint64_t* out_rows, float* out_dists, uint32_t* out_counts) {
     if (idx && idx->dtype != LB_PACKED_U64) return fail(LB_INVALID_ARGUMENT, "index does not store packed rows");
-    return sharded_search_host(comm, idx, metric, query_words, idx ? (size_t)idx->n_words * 8 : 0, nq, k, row_base, out_rows, out_dists,
+    return sharded_search_host(comm, idx, metric, query_words, idx ? (size_t)idx->n_words * 8 : 0, nq, k, row_base, nullptr, 0, out_rows, out_dists,
                                out_counts);
+}
+
+// Test hook for the shard merge: G host blocks of [nq][k] (u32 local rows, f32 scores, counts) with their row bases ->
+// merge_shards_kernel on `device` -> [nq][k] global rows / scores / counts.  No communicator involved: this is the
+// kernel the multi-GPU path runs after its all-gather, on blocks the caller supplies.
+int lb_merge_shard_blocks(int device, int metric, int n_shards, uint32_t nq, uint32_t k, const uint32_t* rows, const float* dists,
+                          const uint32_t* counts, const uint64_t* row_bases, uint64_t* out_rows, float* out_dists, uint32_t* out_counts) {
+    LB_TRY(check_metric(metric));
+    if (n_shards < 1 || nq == 0 || k == 0 || !rows || !dists || !counts || !row_bases || !out_rows || !out_dists || !out_counts)
+        return fail(LB_INVALID_ARGUMENT, "bad arguments");
+    if ((uint64_t)n_shards * k > 4096) return fail(LB_UNSUPPORTED, "n_shards * k must not exceed 4096");
+    DeviceGuard g(device);
+    const size_t bb = shard_block_bytes(nq, k);
+    std::vector<unsigned char> host((size_t)n_shards * bb, 0);
+    for (int s = 0; s < n_shards; ++s) {
+        unsigned char* blk = host.data() + (size_t)s * bb;
+        memcpy(blk, rows + (size_t)s * nq * k, (size_t)nq * k * 4);
+        memcpy(blk + (size_t)nq * k * 4, dists + (size_t)s * nq * k, (size_t)nq * k * 4);
+        memcpy(blk + (size_t)nq * k * 8, counts + (size_t)s * nq, (size_t)nq * 4);
+        memcpy(blk + bb - SHARD_TAIL_BYTES, row_bases + s, 8);
+    }
+    unsigned char* d_blocks = nullptr;
+    uint64_t* d_rows = nullptr;
+    float* d_dists = nullptr;
+    uint32_t* d_counts = nullptr;
+    cudaError_t e = cudaMalloc(&d_blocks, host.size());
+    if (e == cudaSuccess) e = cudaMalloc(&d_rows, (size_t)nq * k * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_dists, (size_t)nq * k * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_counts, (size_t)nq * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_blocks, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const int M = std::max(2, next_pow2(n_shards * (int)k));
+        merge_shards_kernel<<<nq, 256, (size_t)M * 8>>>(d_blocks, n_shards, bb, (int)nq, (int)k, M, metric_ascending(metric) ? 1 : 0, d_rows, d_dists,
+                                                       d_counts);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_rows, d_rows, (size_t)nq * k * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_dists, d_dists, (size_t)nq * k * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_counts, d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_blocks);
+    cudaFree(d_rows);
+    cudaFree(d_dists);
+    cudaFree(d_counts);
+    if (e != cudaSuccess) return fail(LB_CUDA, std::string("lb_merge_shard_blocks: ") + cudaGetErrorString(e));
+    return LB_OK;
 }
 
 int lb_index_event_record(lb_index* idx, int slot) {

@@ -243,10 +243,49 @@ def test_tc_raw_scores_pin_operand_layout(L):
         q = (rng.random((nq, dim), dtype=np.float32) - 0.5)
         c = (rng.random((n, dim), dtype=np.float32) - 0.5)
         out = np.zeros((nq, n), dtype=np.float32)
-        N.check(N.lib().lb_debug_tc_scores(N.fptr(q), nq, N.fptr(c), n, dim, N.fptr(out)))
+        N.check(N.lib().lb_debug_tc_scores(N.fptr(q), nq, N.fptr(c), n, dim, 0, N.fptr(out)))
         want = _bf16_round(q).astype(np.float64) @ _bf16_round(c).astype(np.float64).T
         err = np.abs(out - want).max()
         assert err < 2e-3, f"tcgen05 scores off by {err} for shape {(nq, n, dim)}"
+
+
+def _quantise_rows_u8(c):
+    """build_shadow_kernel<OPERAND_U8>: one zero point / scale for the corpus, f32 arithmetic."""
+    lo, hi = np.float32(c.min()), np.float32(c.max())
+    scale = np.float32((hi - lo) / np.float32(255.0)) if hi > lo else np.float32(1.0)
+    inv = np.float32(1.0) / scale
+    u = np.rint((c - lo).astype(np.float32) * inv)
+    return np.clip(u, 0, 255).astype(np.int64)
+
+
+def _quantise_queries(q):
+    """quantise_queries_kernel: u8 (scale max/255) when the batch has no negative element, else s8 (max|.|/127)."""
+    signed = bool((q < 0).any())
+    levels = np.float32(127.0 if signed else 255.0)
+    amax = np.abs(q).max(axis=1).astype(np.float32)
+    s = np.where(amax > 0, amax / levels, np.float32(1.0)).astype(np.float32)
+    inv = (np.float32(1.0) / s).astype(np.float32)
+    u = np.rint(q * inv[:, None])
+    return (np.clip(u, -127, 127) if signed else np.clip(u, 0, 255)).astype(np.int64)
+
+
+@pytest.mark.parametrize("signed_queries", [False, True])
+def test_tc_raw_scores_8bit_operands_are_exact_integers(L, signed_queries):
+    """kind::i8 operand layouts (A in TMEM, 4 elements per column; B through the same pre-swizzled tiles): the
+    accumulators are the integer dot products of the quantised vectors, bit for bit."""
+    from lynsedb_b200 import _native as N
+
+    rng = np.random.default_rng(72)
+    for (nq, n, dim) in [(5, 200, 64), (130, 333, 200), (128, 1000, 768), (300, 700, 1000)]:
+        q = rng.random((nq, dim), dtype=np.float32)
+        if signed_queries:
+            q -= np.float32(0.5)
+        c = rng.random((n, dim), dtype=np.float32) - np.float32(0.25)
+        out = np.zeros((nq, n), dtype=np.float32)
+        N.check(N.lib().lb_debug_tc_scores(N.fptr(q), nq, N.fptr(c), n, dim, 1, N.fptr(out)))
+        want = _quantise_queries(q) @ _quantise_rows_u8(c).T
+        assert np.abs(want).max() < 2 ** 24
+        assert np.array_equal(out.astype(np.int64), want), f"8-bit accumulators differ for shape {(nq, n, dim)}"
 
 
 @pytest.mark.parametrize("metric,n,dim,nq,k", [
