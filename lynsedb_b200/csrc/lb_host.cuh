@@ -101,6 +101,7 @@ struct Shadow {
     float range_lo = 0.0f, range_hi = 0.0f;  // element range the quantisation was built for
     float cmax = 0.0f, emax = 0.0f;          // host copies of the statistics (diagnostics)
     bool disabled = false;                  // non-finite rows: the plan is not used
+    bool l2_bias = false;                   // L2 shadow: |c|^2 as an f32 side value (no room for the three norm columns)
     // [0] one-CTA kernel (both halves of a K block per box), [1] CTA-pair kernel (one half); .full = KPS K blocks per
     // box, .rem = the partial last stage of a tile ((Dp/64) % KPS K blocks)
     CUtensorMap tmap_full[2], tmap_rem[2];

@@ -50,17 +50,19 @@ constexpr int DCOL = TMEM_COLS - 2 * BN;  // accumulators: two buffers of BN col
 constexpr uint32_t SMEM_RING_BYTES = 196608;                          // staging ring of either kernel
 constexpr uint32_t SMEM_BAR_OFF = SMEM_RING_BYTES;
 constexpr uint32_t SMEM_SCRATCH_OFF = SMEM_BAR_OFF + 256;               // per-epilogue-warp scratch (side values of a tile)
-constexpr uint32_t SMEM_BYTES = SMEM_SCRATCH_OFF + 8 * 256 + 1024;      // + barriers + scratch of 8 warps + alignment slack
+constexpr uint32_t SMEM_SCRATCH_BYTES = 8 * 3 * 128 * 4;                // 8 epilogue warps x EPI_SCRATCH_SLOTS x EPI_SCRATCH_WORDS words
+constexpr uint32_t SMEM_BYTES = SMEM_SCRATCH_OFF + SMEM_SCRATCH_BYTES + 1024;  // + barriers + scratch + alignment slack
 
 // How the 32-bit accumulator of a (query, row) pair becomes the coarse KEY the epilogue ranks by (larger = better).
 //   mode            operands        accumulator   key                                   side values
 //   CM_F32          bf16 x bf16     f32           acc                                   —
-//   CM_F32_BIAS     bf16 x bf16     f32           acc - bias[row]        (L2: 2q.c-|c|^2) bias = f32 |c|^2 per row
+//   CM_F32_BIAS     bf16 x bf16     f32           acc - side[row]        (L2: 2q.c-|c|^2) side = f32 |c|^2 per row
 //   CM_I32          u8/s8 x u8      s32           acc                    (integer)      —
-//   CM_I32_HAMMING  {0,1} x {0,1}   s32           2 acc - bias[row]      (integer)      bias = popcount(row)
-//   CM_JACCARD      {0,1} x {0,1}   s32           acc / (pa + pb - acc)  (f32)          bias = popcount(row), qaux = popcount(query)
-//   CM_DICE         {0,1} x {0,1}   s32           2 acc / (pa + pb)      (f32)          as above
-enum CoarseMode { CM_F32 = 0, CM_F32_BIAS = 1, CM_I32 = 2, CM_I32_HAMMING = 3, CM_JACCARD = 4, CM_DICE = 5 };
+//   CM_I32_HAMMING  {0,1} x {0,1}   s32           2 acc - side[row]      (integer)      side = popcount(row)
+//   CM_RATIO        {0,1} x {0,1}   s32           acc / (pa + pb)        (f32)          side = (f32) popcount(row), qaux = popcount(query)
+// CM_RATIO serves Jaccard / Tanimoto (similarity r / (1 - r)) and Dice (2 r): both grow with r = |a & b| / (|a| + |b|), so
+// r ranks the rows for all of them; the epilogue never divides on the per-score path (see KeyFn).
+enum CoarseMode { CM_F32 = 0, CM_F32_BIAS = 1, CM_I32 = 2, CM_I32_HAMMING = 3, CM_RATIO = 4 };
 template <int MODE>
 struct ModeTraits {
     static constexpr bool kI8 = MODE >= CM_I32;                            // tcgen05 kind::i8 (K = 32 per MMA) instead of kind::f16 (K = 16)
@@ -75,6 +77,7 @@ struct TcArgs {
     int n_mtiles;             // query tiles of 128; qb is padded to a multiple of the cluster size tiles
     int Dp;                   // operand row length in 2-byte units (bf16 elements; 8-bit operands: elements / 2), multiple of 64
     int rem_kb;               // (Dp / 64) % KPS: K blocks of the last, partial stage of a tile (0 = none; uses tmap_rem)
+    int n_ksteps;             // MMA K steps (32 operand bytes each) that hold data; the zero padding behind them is not multiplied
     uint32_t n_rows;
     uint32_t tiles_total;     // ceil(n_rows / rows per tile)
     uint32_t tiles_per_part;
@@ -91,11 +94,12 @@ struct TcArgs {
     int share_floor;          // 1: partitions of a query share a shortlist floor through gthr; 2: gthr holds a floor seeded by a
                               // pre-pass over a sample of the corpus and is only read (large k)
     uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable key bits)
-    // hit mode (with share_floor == 2): rows above the seeded floor are appended to a per-query buffer instead of
-    // going through the register shortlists
-    uint32_t* hit_count;      // [nq] zero-initialised; null = shortlist mode
-    uint2* hit_buf;           // [nq][hit_cap] (key bits, row)
-    uint32_t hit_cap;
+    // hit mode (with share_floor == 2): rows above the seeded floor are appended to the hit region of their
+    // (query, shortlist slot) instead of going through the register shortlists — a private region per epilogue
+    // thread and partition, so appending is one store and a register increment, no atomic
+    uint32_t* hit_count;      // [nq][P * lists_per_part] entries written per region (may exceed hit_cap: overflow); null = shortlist mode
+    uint2* hit_buf;           // [nq][P * lists_per_part][hit_cap] (key bits, row)
+    uint32_t hit_cap;         // entries per region
     uint32_t* error_flag;     // set non-zero when a barrier wait timed out
     float* dump;              // optional [n_mtiles*128][tiles_total*rows per tile] keys as f32 (diagnostics)
     // Work mapping: cluster c serves query group (c % n_mgroups) of slot (c / n_mgroups); slot s walks the row
@@ -110,7 +114,8 @@ struct TcArgs {
                               // bit 1 = epilogue releases accumulators unread, bit 2 = epilogue reads but does not scan
 };
 constexpr int PROGRESS_STRIDE = 32;
-constexpr uint32_t EPI_SCRATCH_WORDS = 64;   // per epilogue warp: the side values of the 64 rows being scanned
+constexpr uint32_t EPI_SCRATCH_SLOTS = 3;    // side values travel global -> shared memory with cp.async, two tiles ahead of their use
+constexpr uint32_t EPI_SCRATCH_WORDS = 128;  // per slot: the side values of the (up to) 128 rows of a tile
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -272,6 +277,24 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) 
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+          "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+          "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+          "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+          "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
@@ -282,6 +305,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 8 bytes global -> shared without passing through registers (LDGSTS); completion through the per-thread async groups
+__device__ __forceinline__ void cp_async_8(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
@@ -362,50 +393,57 @@ struct KeyOps<int> {
 // host / finalize side: key bits -> a 32-bit value whose unsigned order is the key order
 __host__ __device__ inline uint32_t key_bits_orderable(uint32_t bits, bool int_key) { return int_key ? (bits ^ 0x80000000u) : f32_orderable_bits(bits); }
 
-// accumulator words -> key bits, in place, for the 64 rows whose side values sit in `side` (shared memory, one word per row)
+// Accumulator word + side values -> what the epilogue compares.  test(): a value that exceeds test_thr() whenever the
+// key exceeds the lane's gate (it may also exceed it for a few rows just below the gate: every hit is re-checked with
+// its real key); key(): the coarse key itself.  For all modes but CM_RATIO the two are the same number.  CM_RATIO's key
+// is a quotient; its test is the linear form  inter - rho (pa + pb) > -0.01  (rho = the gate, all counts < 2^11 so the
+// f32 evaluation is off by < 1e-4): one fused multiply-add per score instead of a division.
 template <int MODE>
-__device__ __forceinline__ void keys_from_accumulators(uint32_t* v, const uint32_t* side, float qaux) {
-    constexpr int N = (MODE == CM_F32 || MODE == CM_I32) ? 0 : 64;  // these two modes rank the accumulator itself
-#pragma unroll
-    for (int i = 0; i < N; i += 4) {
-        const uint4 s4 = *reinterpret_cast<const uint4*>(side + i);  // same address in every lane: one broadcast read
-        const uint32_t s[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (MODE == CM_F32_BIAS) {
-                v[i + j] = __float_as_uint(__fsub_rn(__uint_as_float(v[i + j]), __uint_as_float(s[j])));
-            } else if (MODE == CM_I32_HAMMING) {
-                const int acc = (int)v[i + j];
-                v[i + j] = (uint32_t)(acc + acc - (int)s[j]);
-            } else {
-                // intersection count (< 2^23) -> f32 without a conversion instruction
-                const float inter = __fsub_rn(__uint_as_float(v[i + j] | 0x4B000000u), 8388608.0f);
-                const float both = __fadd_rn(qaux, __uint_as_float(s[j]));  // popcount(query) + popcount(row), exact
-                const float den = MODE == CM_JACCARD ? __fsub_rn(both, inter) : both;
-                const float num = MODE == CM_JACCARD ? inter : __fadd_rn(inter, inter);
-                // empty query and empty row: the reference's distance is 0 (the best), i.e. similarity 1
-                v[i + j] = __float_as_uint(den > 0.0f ? __fdividef(num, den) : 1.0f);
-            }
+struct KeyFn {
+    using K = typename ModeTraits<MODE>::Key;
+    float qaux, rho, rho_pa;
+    __device__ __forceinline__ void set_gate(K thr) {
+        if (MODE == CM_RATIO) {
+            const float th = KeyOps<K>::as_f32(thr);
+            rho = fmaxf(th, -1.0f);       // keys are >= 0: -1 passes everything, and keeps 0 * rho finite
+            rho_pa = rho * qaux;
         }
     }
-}
+    __device__ __forceinline__ K test_thr(K thr) const { return MODE == CM_RATIO ? KeyOps<K>::from_bits(__float_as_uint(-0.01f)) : thr; }
+    __device__ __forceinline__ K test(uint32_t acc, uint32_t side) const {
+        if (MODE == CM_F32 || MODE == CM_I32) return KeyOps<K>::from_bits(acc);
+        if (MODE == CM_F32_BIAS) return KeyOps<K>::from_bits(__float_as_uint(__fsub_rn(__uint_as_float(acc), __uint_as_float(side))));
+        if (MODE == CM_I32_HAMMING) return KeyOps<K>::from_bits((uint32_t)((int)acc + (int)acc - (int)side));
+        // intersection count (< 2^23) -> f32 without a conversion instruction
+        const float inter = __fsub_rn(__uint_as_float(acc | 0x4B000000u), 8388608.0f);
+        return KeyOps<K>::from_bits(__float_as_uint(__fsub_rn(__fmaf_rn(-rho, __uint_as_float(side), inter), rho_pa)));
+    }
+    __device__ __forceinline__ K key(uint32_t acc, uint32_t side) const {
+        if (MODE != CM_RATIO) return test(acc, side);
+        const float inter = (float)(int)acc, den = __fadd_rn(qaux, __uint_as_float(side));  // popcounts: exact in f32
+        // empty query and empty row: the reference's distance is 0 (the best), i.e. ratio "1"
+        return KeyOps<K>::from_bits(__float_as_uint(den > 0.0f ? __fdividef(inter, den) : 1.0f));
+    }
+};
 
 // Per-thread shortlist of one (query, row partition): the KP best coarse keys, held in REGISTERS (every index is
 // a compile-time constant) and gated by a register threshold — shared-memory lists stall for thousands of cycles
 // behind the tensor core's operand reads and the TMA writes.  lmin = worst key kept; thr_g = best floor any
 // partition of the query has published through gthr (a row at or below it is outside the global top KP).
-// In hit mode (seeded floor, large k) the list is not used: a row above the floor goes to the query's hit buffer.
-template <class K>
+// HITS (seeded floor, large k): there is no list; a row above the floor goes to this thread's hit region.
+template <int MODE, bool HITS>
 struct Shortlist {
+    using K = typename ModeTraits<MODE>::Key;
     using O = KeyOps<K>;
-    K sc[KP];
-    uint32_t rw[KP];
+    static constexpr int NL = HITS ? 1 : KP;
+    K sc[NL];
+    uint32_t rw[NL];
     K lmin, thr_g, thr_pub;
     uint32_t g_bits;
     uint32_t* gthr;
-    uint32_t* hit_count;
     uint2* hit_buf;
-    uint32_t hit_cap;
+    uint32_t hit_n, hit_cap;
+    KeyFn<MODE> fn;
     bool q_valid, share, may_publish;
 
     // The list is full and its floor rose: make it visible to the other partitions of the query.
@@ -413,83 +451,103 @@ struct Shortlist {
         atomicMax(gthr, O::orderable(lmin));
         thr_pub = lmin;
     }
-    __device__ __forceinline__ void reset(bool valid, int share_floor, uint32_t* gthr_q, const TcArgs& a, uint32_t gq) {
+    __device__ __forceinline__ void reset(bool valid, const TcArgs& a, uint32_t gq, uint32_t part, uint32_t sub) {
 #pragma unroll
-        for (int j = 0; j < KP; ++j) {
+        for (int j = 0; j < NL; ++j) {
             sc[j] = O::lowest();
             rw[j] = ROW_NONE;
         }
         q_valid = valid;
-        share = share_floor != 0;
-        may_publish = share_floor == 1;
-        gthr = gthr_q;
-        hit_count = nullptr;
-        if (share_floor == 2 && valid) {  // seeded floor: available from the first tile
-            const uint32_t bits = *reinterpret_cast<volatile uint32_t*>(gthr_q);
+        share = a.share_floor != 0;
+        may_publish = !HITS && a.share_floor == 1;
+        gthr = a.gthr + (valid ? gq : 0);
+        hit_buf = nullptr;
+        hit_n = 0;
+        hit_cap = 0;
+        if (a.share_floor == 2 && valid) {  // seeded floor: available from the first tile
+            const uint32_t bits = *reinterpret_cast<volatile uint32_t*>(gthr);
             if (bits != 0u) thr_g = max(thr_g, O::from_orderable(bits));
-            if (a.hit_count != nullptr) {
-                hit_count = a.hit_count + gq;
-                hit_buf = a.hit_buf + (size_t)gq * a.hit_cap;
-                hit_cap = a.hit_cap;
-            }
+        }
+        if (HITS && valid) {
+            hit_cap = a.hit_cap;
+            hit_buf = a.hit_buf + ((size_t)gq * ((size_t)a.P * a.lists_per_part) + (size_t)part * a.lists_per_part + sub) * a.hit_cap;
         }
         lmin = O::lowest();
         thr_pub = O::lowest();
     }
-    __device__ __forceinline__ void init_floor() {
+    __device__ __forceinline__ void init_floor(float qaux) {
         thr_g = O::lowest();
         g_bits = 0u;
+        fn.qaux = qaux;
     }
-    __device__ __forceinline__ K gate() const { return q_valid ? max(lmin, thr_g) : O::highest(); }
+    __device__ __forceinline__ K gate() const { return q_valid ? (HITS ? thr_g : max(lmin, thr_g)) : O::highest(); }
     // refresh the shared floor every 8th tile; the load issued now is consumed 8 tiles later, so its (loaded) L2
     // latency never sits on the per-tile critical path
     __device__ __forceinline__ void poll_floor(uint32_t tile_iter) {
-        if (share && (tile_iter & 7u) == 0u) {
+        if (!HITS && share && (tile_iter & 7u) == 0u) {
             if (g_bits != 0u) thr_g = max(thr_g, O::from_orderable(g_bits));
             g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
         }
     }
     // replace the current minimum by (key, row) and recompute the minimum: ~70 ALU instructions, no memory
     __device__ __forceinline__ void insert(K key, uint32_t row) {
+        if (HITS) return;
         bool done = false;
 #pragma unroll
-        for (int j = 0; j < KP; ++j) {
+        for (int j = 0; j < NL; ++j) {
             const bool hit = !done && sc[j] == lmin;
             sc[j] = hit ? key : sc[j];
             rw[j] = hit ? row : rw[j];
             done = done || hit;
         }
-        K m0 = O::min3(sc[0], sc[1], sc[2]), m1 = O::min3(sc[3], sc[4], sc[5]);
-        m0 = O::min3(m0, sc[6], sc[7]);
-        m1 = O::min3(m1, sc[8], sc[9]);
-        m0 = O::min3(m0, sc[10], sc[11]);
-        m1 = O::min3(m1, sc[12], sc[13]);
-        lmin = O::min3(min(m0, m1), sc[14], sc[15]);
-    }
-    __device__ __forceinline__ void record(K key, uint32_t row) {
-        if (hit_count != nullptr) {
-            const uint32_t slot = atomicAdd(hit_count, 1u);
-            if (slot < hit_cap) hit_buf[slot] = make_uint2(O::bits(key), row);
-        } else {
-            insert(key, row);
+        if (!HITS) {
+            K m0 = O::min3(sc[0], sc[1], sc[2]), m1 = O::min3(sc[3 % NL], sc[4 % NL], sc[5 % NL]);
+            m0 = O::min3(m0, sc[6 % NL], sc[7 % NL]);
+            m1 = O::min3(m1, sc[8 % NL], sc[9 % NL]);
+            m0 = O::min3(m0, sc[10 % NL], sc[11 % NL]);
+            m1 = O::min3(m1, sc[12 % NL], sc[13 % NL]);
+            lmin = O::min3(min(m0, m1), sc[14 % NL], sc[15 % NL]);
         }
     }
-    // 32 keys of this thread's query = rows row0 .. row0+31, at least one lane of the warp above its gate.
-    __device__ __forceinline__ void slow32(const uint32_t* v, K gmax, uint32_t row0, uint32_t row_end, K thr, uint32_t allow_word,
-                                           bool have_allow) {
+    // hit region append: one store and a register increment (counts past the capacity too: finalize sees the overflow)
+    __device__ __forceinline__ void append(K key, uint32_t row) {
+        if (hit_n < hit_cap) hit_buf[hit_n] = make_uint2(O::bits(key), row);
+        ++hit_n;
+    }
+    // 16 accumulators of this thread's query = rows row0 .. row0+15, at least one lane of the warp above its gate.
+    // `side`: the rows' side values in shared memory.
+    __device__ __forceinline__ void slow16(const uint32_t* v, const uint32_t* side, K gmax, uint32_t row0, uint32_t row_end, K thr, K tthr,
+                                           uint32_t allow16, bool have_allow) {
+        constexpr bool kBias = ModeTraits<MODE>::kBias;
+        if (HITS) {
+            // straight-line, predicated: appending is cheap, and no loop, vote or select tree keeps this path short
+            uint32_t ok = 0xffffu;
+            if (row0 + 16u > row_end) ok = (1u << (row_end > row0 ? row_end - row0 : 0u)) - 1u;
+            if (have_allow) ok &= allow16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t sv = kBias ? side[i] : 0u;
+                if (fn.test(v[i], sv) > tthr && ((ok >> i) & 1u)) {
+                    const K x = fn.key(v[i], sv);
+                    if (MODE != CM_RATIO || x > thr) append(x, row0 + (uint32_t)i);
+                }
+            }
+            return;
+        }
         uint32_t mask = 0u;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mask |= (O::from_bits(v[i]) > thr ? 1u : 0u) << i;
+        for (int i = 0; i < 16; ++i) mask |= (fn.test(v[i], kBias ? side[i] : 0u) > tthr ? 1u : 0u) << i;
         const uint32_t raw = mask;
-        if (row0 + 32u > row_end) {  // last tile: rows past the end of the corpus never enter a list
+        if (row0 + 16u > row_end) {  // last tile: rows past the end of the corpus never enter a list
             const uint32_t n_ok = row_end > row0 ? row_end - row0 : 0u;
-            mask &= n_ok >= 32u ? 0xffffffffu : ((1u << n_ok) - 1u);
+            mask &= (1u << n_ok) - 1u;
         }
-        if (have_allow) mask &= allow_word;
+        if (have_allow) mask &= allow16;
         // a lane with exactly one hit (the usual case) already holds its key: it is the group maximum — unless the
-        // masks above removed a hit, in which case the maximum may belong to a removed row
-        if (mask == raw && __popc(mask) == 1) {
-            record(gmax, row0 + (uint32_t)(__ffs((int)mask) - 1));
+        // masks above removed a hit, in which case the maximum may belong to a removed row (CM_RATIO: the maximum is
+        // a test value, not a key)
+        if (MODE != CM_RATIO && mask == raw && __popc(mask) == 1) {
+            insert(gmax, row0 + (uint32_t)(__ffs((int)mask) - 1));
             mask = 0u;
         }
 #pragma unroll 1
@@ -497,45 +555,56 @@ struct Shortlist {
             if (mask != 0u) {
                 const int idx = __ffs((int)mask) - 1;
                 mask &= mask - 1u;
-                // v[idx] with a run-time idx: 5-level select tree over the register array (31 selects)
-                uint32_t t4[16], t3[8], t2[4], t1[2];
+                // v[idx] with a run-time idx: 4-level select tree over the register array (15 selects)
+                uint32_t t3[8], t2[4], t1[2];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) t4[j] = (idx & 16) ? v[16 + j] : v[j];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) t3[j] = (idx & 8) ? t4[8 + j] : t4[j];
+                for (int j = 0; j < 8; ++j) t3[j] = (idx & 8) ? v[8 + j] : v[j];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) t2[j] = (idx & 4) ? t3[4 + j] : t3[j];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) t1[j] = (idx & 2) ? t2[2 + j] : t2[j];
-                const K x = O::from_bits((idx & 1) ? t1[1] : t1[0]);
-                if (x > gate()) record(x, row0 + (uint32_t)idx);  // the gate may have risen since the mask was taken
+                const K x = fn.key((idx & 1) ? t1[1] : t1[0], kBias ? side[idx] : 0u);
+                if (x > gate()) insert(x, row0 + (uint32_t)idx);  // the gate may have risen since the mask was taken
             }
         }
     }
-    // 64 keys of this thread's query = rows row0 .. row0+63.  Called by whole warps.
-    // The slow path must stay SMALL: a fully unrolled "for each of the 64 keys: compare, insert" is ~90 KB of code
+    // 64 accumulators of this thread's query = rows row0 .. row0+63.  Called by whole warps.
+    // The slow path must stay SMALL: a fully unrolled "for each of the 64 scores: compare, insert" is ~90 KB of code
     // whose sparse execution misses the instruction cache at every step (~7700 cycles per tile measured).  So: the
-    // maxima of the two 32-key groups gate (1) a 32-bit hit mask per lane from straight compares and (2) a rolled loop
-    // that pops each lane's lowest hit and fetches the key with a select tree.
-    __device__ __forceinline__ void scan64(const uint32_t* v, uint32_t row0, uint32_t row_end, bool disabled,
+    // maxima of the four 16-score groups gate (1) a 16-bit hit mask per lane from straight compares and (2) a rolled
+    // loop that pops each lane's lowest hit and fetches the accumulator with a select tree.
+    __device__ __forceinline__ void scan64(const uint32_t* v, const uint32_t* side, uint32_t row0, uint32_t row_end, bool disabled,
                                            const uint64_t* __restrict__ allow = nullptr) {
+        constexpr bool kBias = ModeTraits<MODE>::kBias;
         const K thr = disabled ? O::highest() : gate();
-        // group maxima with 3-input max: 32 instructions for 64 keys
-        K m0 = O::max3(O::from_bits(v[0]), O::from_bits(v[1]), O::from_bits(v[2]));
-        K m1 = O::max3(O::from_bits(v[32]), O::from_bits(v[33]), O::from_bits(v[34]));
+        fn.set_gate(thr);
+        const K tthr = fn.test_thr(thr);
+        K g[4];
 #pragma unroll
-        for (int i = 3; i + 1 < 31; i += 2) {
-            m0 = O::max3(m0, O::from_bits(v[i]), O::from_bits(v[i + 1]));
-            m1 = O::max3(m1, O::from_bits(v[32 + i]), O::from_bits(v[32 + i + 1]));
+        for (int j = 0; j < 4; ++j) {
+            uint32_t s[16];
+            if (kBias) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {  // same address in every lane: broadcast reads
+                    const uint4 s4 = *reinterpret_cast<const uint4*>(side + 16 * j + i);
+                    s[i] = s4.x; s[i + 1] = s4.y; s[i + 2] = s4.z; s[i + 3] = s4.w;
+                }
+            }
+            const uint32_t* a = v + 16 * j;
+            // group maximum with 3-input max: 8 instructions for 16 test values
+            K m = O::max3(fn.test(a[0], kBias ? s[0] : 0u), fn.test(a[1], kBias ? s[1] : 0u), fn.test(a[2], kBias ? s[2] : 0u));
+#pragma unroll
+            for (int i = 3; i + 1 < 16; i += 2) m = O::max3(m, fn.test(a[i], kBias ? s[i] : 0u), fn.test(a[i + 1], kBias ? s[i + 1] : 0u));
+            g[j] = max(m, fn.test(a[15], kBias ? s[15] : 0u));
         }
-        m0 = max(m0, O::from_bits(v[31]));
-        m1 = max(m1, O::from_bits(v[63]));
-        if (__any_sync(0xffffffffu, max(m0, m1) > thr)) {
+        if (__any_sync(0xffffffffu, O::max3(max(g[0], g[1]), g[2], g[3]) > tthr)) {
             uint64_t w = ~0ull;
             const bool have_allow = allow != nullptr;
             if (have_allow) w = row0 < row_end ? __ldg(allow + (row0 >> 6)) : 0ull;  // row0 is a multiple of 64
-            if (__any_sync(0xffffffffu, m0 > thr)) slow32(v, m0, row0, row_end, thr, (uint32_t)w, have_allow);
-            if (__any_sync(0xffffffffu, m1 > thr)) slow32(v + 32, m1, row0 + 32u, row_end, thr, (uint32_t)(w >> 32), have_allow);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (__any_sync(0xffffffffu, g[j] > tthr))
+                    slow16(v + 16 * j, side + 16 * j, g[j], row0 + 16u * j, row_end, thr, tthr, (uint32_t)(w >> (16 * j)) & 0xffffu, have_allow);
             if (may_publish && q_valid && lmin > thr_pub && lmin > thr_g) publish();
         }
     }
@@ -543,12 +612,14 @@ struct Shortlist {
     __device__ __forceinline__ void flush(const TcArgs& a, uint32_t gq, uint32_t part, uint32_t sub = 0) {
         if (!q_valid) return;
         const size_t list = (size_t)gq * ((size_t)a.P * a.lists_per_part) + (size_t)part * a.lists_per_part + sub;
-        if (hit_count == nullptr) {
+        if (HITS) {
+            a.hit_count[list] = hit_n;
+        } else {
             const size_t o = list * KP;
 #pragma unroll
-            for (int j = 0; j < KP; j += 4) {
-                *reinterpret_cast<uint4*>(a.cand_key + o + j) = make_uint4(O::bits(sc[j]), O::bits(sc[j + 1]), O::bits(sc[j + 2]), O::bits(sc[j + 3]));
-                *reinterpret_cast<uint4*>(a.cand_row + o + j) = make_uint4(rw[j], rw[j + 1], rw[j + 2], rw[j + 3]);
+            for (int j = 0; j < NL; j += 4) {
+                *reinterpret_cast<uint4*>(a.cand_key + o + j) = make_uint4(O::bits(sc[j]), O::bits(sc[(j + 1) % NL]), O::bits(sc[(j + 2) % NL]), O::bits(sc[(j + 3) % NL]));
+                *reinterpret_cast<uint4*>(a.cand_row + o + j) = make_uint4(rw[j], rw[(j + 1) % NL], rw[(j + 2) % NL], rw[(j + 3) % NL]);
             }
         }
         // every row this thread dropped scored <= max(lmin, thr_g) at the time, and both only grow
@@ -641,7 +712,9 @@ static __global__ void shadow_range_kernel(const float* __restrict__ rows, uint6
 // pre-swizzled layout described at the top of this file, + the statistics the certification needs.
 //   SHADOW_IP      c' = c
 //   SHADOW_COSINE  c' = c / |c|       (zero rows stay zero: cosine distance 1.0, simd.rs:1631-1633)
-//   SHADOW_L2      c' = c, side[row] = |c|^2 (f32): the epilogue forms 2 q.c - |c|^2 (CM_F32_BIAS)
+//   SHADOW_L2      c' = c; |c|^2 either as three bf16 columns [dim, dim+3) (n1 + n2 + n3 ~ |c|^2: the contraction itself
+//                  forms 2 q.c - |c|^2 against a query of [2q, -1, -1, -1]) or, when side != null, as the f32 side value
+//                  the epilogue subtracts (CM_F32_BIAS: rows whose padded length has no room for the columns)
 // OPERAND_BF16: c~ = bf16(c').  OPERAND_U8: c~ = zero + scale * u8, u8 = clamp(rint((c' - zero) / scale), 0, 255).
 template <int OPK>
 __global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int row_bytes, int kind,
@@ -672,9 +745,15 @@ __global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t fir
             const float x = d < dim ? __ldg(r + d) * scale : 0.0f;
             float held;
             if (OPK == OPERAND_BF16) {
-                const __nv_bfloat16 b = __float2bfloat16_rn(x);
-                reinterpret_cast<__nv_bfloat16*>(out)[e] = b;
+                __nv_bfloat16 b = __float2bfloat16_rn(x);
                 held = __bfloat162float(b);
+                if (kind == SHADOW_L2 && side == nullptr && d >= dim && d < dim + 3) {
+                    const float n1 = __bfloat162float(__float2bfloat16_rn(ss));
+                    const float n2 = __bfloat162float(__float2bfloat16_rn(ss - n1));
+                    const float n3 = (ss - n1) - n2;
+                    b = __float2bfloat16_rn(d == dim ? n1 : (d == dim + 1 ? n2 : n3));
+                }
+                reinterpret_cast<__nv_bfloat16*>(out)[e] = b;
             } else {
                 int u = d < dim ? __float2int_rn((x - q_zero) * inv_q) : 0;
                 u = min(max(u, 0), 255);
@@ -760,6 +839,7 @@ static __global__ void prepare_bits_queries_kernel(const uint64_t* __restrict__ 
 // Queries, bf16 operand: A operand rows (zero padded to nq_pad x row_bytes) + statistics.
 //   SHADOW_IP  q' = q       SHADOW_COSINE  q' = q / |q|       SHADOW_L2  q' = q, operand = 2 q~ (exact doubling)
 static __global__ void prepare_queries_kernel(const float* __restrict__ queries, int nq, int nq_pad, int dim, int row_bytes, int kind,
+                                              int norm_cols /* L2: operand columns [dim, dim+3) = -1 (the shadow holds |c|^2 there) */,
                                               unsigned char* __restrict__ qb, QStat* __restrict__ qstat) {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -785,7 +865,7 @@ static __global__ void prepare_queries_kernel(const float* __restrict__ queries,
         const float x = d < dim ? __ldg(r + d) * scale : 0.0f;
         const __nv_bfloat16 b = __float2bfloat16_rn(x);
         const float held = __bfloat162float(b);
-        out[d] = kind == SHADOW_L2 ? __float2bfloat16_rn(2.0f * held) : b;
+        out[d] = kind == SHADOW_L2 ? __float2bfloat16_rn((norm_cols && d >= dim && d < dim + 3) ? -1.0f : 2.0f * held) : b;
         const float de = x - held;
         err = fmaf(de, de, err);
         hss = fmaf(held, held, hss);
@@ -919,9 +999,9 @@ struct FinArgs {
     const uint32_t* cand_row;
     const uint32_t* cand_thr;  // [nq][P] key bits
     int P;
-    // hit mode (hit_count != null): the rows above the seeded floor gthr[q]
-    const uint32_t* hit_count;
-    const uint2* hit_buf;
+    // hit mode (hit_count != null): the rows above the seeded floor gthr[q], in P hit regions of hit_cap entries
+    const uint32_t* hit_count;  // [nq][P]
+    const uint2* hit_buf;       // [nq][P][hit_cap]
     uint32_t hit_cap;
     const uint32_t* gthr;
     int int_key;              // keys are s32 (8-bit operands) instead of f32
@@ -1014,29 +1094,40 @@ __device__ __forceinline__ float rescore_row_lanes(int metric, bool two_acc_ip, 
     return 1.0f - dot / denom;
 }
 
-// Candidates of query q -> sort keys in s[0, M1) (best coarse key first), sorted; returns through shared words the number of
-// candidates and the orderable bits of T: every row that is NOT a candidate has a coarse key <= T.
-__device__ __forceinline__ void gather_candidates(const FinArgs& a, int q, uint64_t* s, uint32_t* sh_T, uint32_t* sh_ncand, uint32_t* sh_overflow) {
+// Candidates of query q -> sort keys in s[0, M) (best coarse key first), sorted; M = a power of two <= M1 that holds
+// them.  Returns M; through shared words: the number of candidates and the orderable bits of T — every row that is NOT
+// a candidate has a coarse key <= T.
+__device__ __forceinline__ int gather_candidates(const FinArgs& a, int q, uint64_t* s, uint32_t* sh_T, uint32_t* sh_ncand, uint32_t* sh_overflow) {
     const int tid = threadIdx.x;
     const bool ik = a.int_key != 0;
-    uint32_t local_valid = 0;
     if (a.hit_count != nullptr) {
-        const uint32_t cnt = a.hit_count[q], n = min(cnt, a.hit_cap);
-        for (int i = tid; i < a.M1; i += blockDim.x) {
-            uint64_t key = KEY_NONE;
-            if ((uint32_t)i < n) {
-                const uint2 h = a.hit_buf[(size_t)q * a.hit_cap + i];
-                key = ((uint64_t)(~key_bits_orderable(h.x, ik)) << 32) | h.y;
-                ++local_valid;
+        // hit regions of the query's P shortlist slots: compact the written entries into s (order does not matter, they
+        // are sorted next); more than M1 of them, or a region that ran out of room, leaves the query uncertified
+        for (int i = tid; i < a.M1; i += blockDim.x) s[i] = KEY_NONE;
+        __syncthreads();
+        for (int r = 0; r < a.P; ++r) {
+            const uint32_t cnt = a.hit_count[(size_t)q * a.P + r];
+            if (cnt > a.hit_cap && tid == 0) *sh_overflow = 1u;
+            const uint32_t n = min(cnt, a.hit_cap);
+            const uint2* reg = a.hit_buf + ((size_t)q * a.P + r) * a.hit_cap;
+            for (uint32_t i = tid; i < n; i += blockDim.x) {
+                const uint2 h = reg[i];
+                const uint32_t slot = atomicAdd(sh_ncand, 1u);
+                if (slot < (uint32_t)a.M1) s[slot] = ((uint64_t)(~key_bits_orderable(h.x, ik)) << 32) | h.y;
             }
-            s[i] = key;
         }
+        __syncthreads();
         if (tid == 0) {
             *sh_T = a.gthr[q];  // orderable bits of the seeded floor (0 = none: nothing was dropped)
-            *sh_overflow = cnt > a.hit_cap ? 1u : 0u;
+            if (*sh_ncand > (uint32_t)a.M1) {
+                *sh_overflow = 1u;
+                *sh_ncand = (uint32_t)a.M1;
+            }
         }
+        __syncthreads();
     } else {
         const int total = a.P * KP;
+        uint32_t local_valid = 0;
         for (int i = tid; i < a.M1; i += blockDim.x) {
             uint64_t key = KEY_NONE;
             if (i < total) {
@@ -1049,9 +1140,17 @@ __device__ __forceinline__ void gather_candidates(const FinArgs& a, int q, uint6
             s[i] = key;
         }
         for (int p = tid; p < a.P; p += blockDim.x) atomicMax(sh_T, key_bits_orderable(a.cand_thr[(size_t)q * a.P + p], ik));
+        if (local_valid) atomicAdd(sh_ncand, local_valid);
+        __syncthreads();
     }
-    if (local_valid) atomicAdd(sh_ncand, local_valid);
-    bitonic_sort_u64(s, a.M1);
+    int M = a.M1;
+    if (a.hit_count != nullptr) {  // sort only as many slots as hold candidates
+        M = 32;
+        while (M < (int)*sh_ncand) M <<= 1;
+        M = min(M, a.M1);
+    }
+    bitonic_sort_u64(s, M);
+    return M;
 }
 // orderable key bits -> the key as a real number
 __device__ __forceinline__ double key_value(uint32_t ord, bool int_key) {
@@ -1244,8 +1343,15 @@ static __global__ void __launch_bounds__(256) finalize_bits_kernel(FinBitsArgs b
         else {
             const double worst = (double)key_score<true>(e[a.k - 1]);
             const double T = key_value(T_ord, ik);
-            if (a.metric == LB_HAMMING) certified = worst < (double)qpop - T;  // key = 2 inter - pb = pa - hamming, exact: ties are not certified
-            else certified = worst < 1.0 - (T + 1e-5);                          // key ~ similarity, relative error of the fast division << 1e-5
+            if (a.metric == LB_HAMMING) {
+                certified = worst < (double)qpop - T;  // key = 2 inter - pb = pa - hamming, exact: ties are not certified
+            } else {
+                // key ~ r = inter / (pa + pb), off by the fast division's few ulps: a dropped row has r <= T (1 + 1e-6),
+                // i.e. a distance of at least 1 - 2 r (Dice) or 1 - r / (1 - r) (Jaccard / Tanimoto) of that bound
+                const double rb = fmin(T * (1.0 + 1e-6) + 1e-9, 0.5);
+                const double dmin = a.metric == LB_DICE ? 1.0 - 2.0 * rb : (rb < 0.5 ? 1.0 - rb / (1.0 - rb) : 0.0);
+                certified = worst < dmin - 2e-7;
+            }
         }
         a.uncertified[q] = certified ? 0u : 1u;
         if (!certified) atomicAdd(a.n_uncertified, 1u);

@@ -21,7 +21,7 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
     else umma_ts_bf16(d_tmem, a_tmem, b_desc, idesc, accumulate);
 }
 
-template <int MODE_ = CM_F32>
+template <int MODE_ = CM_F32, bool HITS_ = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
     const int slot = (int)blockIdx.x;
@@ -125,11 +125,13 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
                     const int kbc = s < n_full ? KPS : rem;
                     const uint64_t bdesc0 = desc_base + (uint64_t)((stage * S_STAGE_BYTES) >> 4);
                     const uint32_t a0 = tmem_base + (uint32_t)(s * KPS * 4 * 8);
+                    const int ks0 = s * KPS * 4;  // first K step of this stage; steps >= n_ksteps are zero padding
                     if (leader) {
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
-                            umma_ts<I8>(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), S_IDESC,
-                                         (k4 == 0) ? (s > 0 ? 1u : 0u) : 1u);
+                            if (ks0 + k4 < a.n_ksteps)
+                                umma_ts<I8>(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), S_IDESC,
+                                             (k4 == 0) ? (s > 0 ? 1u : 0u) : 1u);
                     }
                     {
                         uint32_t ns = stage + 1, nph = phase;
@@ -146,8 +148,9 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
                             if (kb < kbc) {
 #pragma unroll
                                 for (int k4 = 0; k4 < 4; ++k4)
-                                    umma_ts<I8>(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
-                                                 bdesc0 + (uint64_t)(kb * ((2 * HALF_BLOCK_BYTES) >> 4) + k4 * 2), S_IDESC, 1u);
+                                    if (ks0 + kb * 4 + k4 < a.n_ksteps)
+                                        umma_ts<I8>(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
+                                                     bdesc0 + (uint64_t)(kb * ((2 * HALF_BLOCK_BYTES) >> 4) + k4 * 2), S_IDESC, 1u);
                             }
                         }
                         umma_commit(empty0 + 8u * stage);  // frees the stage once these MMAs have read it
@@ -164,36 +167,43 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
         const int ql = quad * 32 + lane;              // query within the tile
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        Shortlist<Key> sl;
+        Shortlist<MODE_, HITS_> sl;
         uint32_t tile_iter = 0;
         bool ok = true;
         const uint32_t gq = (uint32_t)ql;
         const bool q_valid = gq < (uint32_t)a.nq;
         const float qaux = a.qaux != nullptr ? __ldg(a.qaux + gq) : 0.0f;
-        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + SMEM_SCRATCH_OFF) + (warp - 2) * EPI_SCRATCH_WORDS;
-        uint2 side_cur = make_uint2(0u, 0u), side_next = make_uint2(0u, 0u);  // side values of rows 2*lane, 2*lane+1 of a tile
-        sl.init_floor();
+        // side values of the rows being scanned: cp.async ring, two tiles ahead (see lb_tc2.cuh)
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + SMEM_SCRATCH_OFF) + (warp - 2) * (EPI_SCRATCH_SLOTS * EPI_SCRATCH_WORDS);
+        auto side_fetch = [&](uint32_t t, uint32_t slot) {
+            if (MT::kBias) cp_async_8(smem_u32(scratch + slot * EPI_SCRATCH_WORDS + 2 * lane), a.bias + (size_t)t * BN + 2 * lane);
+            cp_async_commit();
+        };
+        sl.init_floor(qaux);
         for (int r = first_round; r < n_rounds && ok; ++r) {
             const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
             if (part >= (uint32_t)a.P) break;
             const uint32_t t0 = part * a.tiles_per_part;
             const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
             if (r == first_round) load_query_to_tmem(a.qb + (size_t)gq * a.Dp * 2, a.Dp, lane_addr);  // the query tile never changes
-            sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0), a, gq);
-            if (MT::kBias && t0 < t1) side_cur = __ldg(reinterpret_cast<const uint2*>(a.bias + (size_t)t0 * BN) + lane);
+            sl.reset(q_valid, a, gq, part, 0u);
+            if (MT::kBias) {
+                __syncwarp();
+                side_fetch(t0, 0);
+                side_fetch(min(t0 + 1, t1 - 1), 1);
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(aready_bar);
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter & 1u;
                 if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter);
-                if (MT::kBias && t + 1 < t1) side_next = __ldg(reinterpret_cast<const uint2*>(a.bias + (size_t)(t + 1) * BN) + lane);
+                if (MT::kBias) side_fetch(min(t + 2, t1 - 1), (t - t0 + 2) % EPI_SCRATCH_SLOTS);
                 if (!mbar_wait(tfull0 + 8u * buf, (tile_iter >> 1) & 1u, abort_flag, 5)) { ok = false; break; }
                 tcgen05_fence_after();
                 uint32_t v[64];
                 if (!(a.debug_mode & 2)) {
-                    tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN, v);
-                    tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + 32, v + 32);
+                    tmem_ld_32x32b_x64(lane_addr + DCOL + buf * BN, v);
                     tmem_ld_wait();
                 }
                 tcgen05_fence_before();
@@ -202,19 +212,18 @@ coarse_single_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid
                 if (a.debug_mode & 2) continue;
                 const uint32_t row0 = t * BN;
                 if (MT::kBias) {
-                    __syncwarp();  // the previous tile's broadcast reads are done
-                    *reinterpret_cast<uint2*>(scratch + 2 * lane) = side_cur;
+                    cp_async_wait<2>();
                     __syncwarp();
-                    side_cur = side_next;
                 }
-                keys_from_accumulators<MODE_>(v, scratch, qaux);
+                const uint32_t* side = scratch + ((t - t0) % EPI_SCRATCH_SLOTS) * EPI_SCRATCH_WORDS;
                 if (a.dump != nullptr) {
                     float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) drow[i] = KO::as_f32(KO::from_bits(v[i]));
+                    for (int i = 0; i < 64; ++i) drow[i] = KO::as_f32(sl.fn.key(v[i], MT::kBias ? side[i] : 0u));
                 }
-                sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
+                sl.scan64(v, side, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
+                if (MT::kBias) __syncwarp();  // every lane is done reading this tile's slot before a later fetch reuses it
             }
+            if (MT::kBias) cp_async_wait<0>();
             if (ok) sl.flush(a, gq, part);
         }
     }

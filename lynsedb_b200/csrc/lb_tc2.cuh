@@ -95,8 +95,9 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 // shortlists (TcArgs::lists_per_part = 2): the epilogue is bound by the issue rate of a single warp per sub-partition
 // at large k, and two warps double it.
 // MODE_ = CoarseMode: operand kind of the MMAs and how an accumulator becomes the key the epilogue ranks by.
-template <int BN_, int NACC_ = 2, int EPI_ = 1, int MODE_ = CM_F32>
-__global__ void __launch_bounds__(64 + 128 * EPI_, 1)
+// HITS_: the epilogue appends rows above a seeded floor to hit regions instead of keeping shortlists (TcArgs::hit_buf).
+template <int BN_, int NACC_ = 2, int EPI_ = 1, int MODE_ = CM_F32, bool HITS_ = false>
+__global__ void __launch_bounds__(64 + 128 * EPI_, 1)   // (warps are allocated four at a time: 320 threads are budgeted as 384, 168 registers)
 coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
     using Cfg = PairCfg<BN_, NACC_>;
     constexpr uint32_t NACC = NACC_;
@@ -254,11 +255,13 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                         const int kbc = s < n_full ? KPS : rem;
                         const uint64_t bdesc0 = desc_base + (uint64_t)((stage * P_STAGE_BYTES) >> 4);
                         const uint32_t a0 = tmem_base + (uint32_t)(s * KPS * 4 * 8);
+                        const int ks0 = s * KPS * 4;  // first K step of this stage; steps >= n_ksteps are zero padding
                         if (leader) {
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
-                                umma_pair_ts<I8>(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), P_IDESC,
-                                                  (k4 == 0) ? (s > 0 ? 1u : 0u) : 1u);
+                                if (ks0 + k4 < a.n_ksteps)
+                                    umma_pair_ts<I8>(d_tmem, a0 + (uint32_t)(k4 * 8), bdesc0 + (uint64_t)(k4 * 2), P_IDESC,
+                                                      (k4 == 0) ? (s > 0 ? 1u : 0u) : 1u);
                         }
                         {
                             uint32_t ns = stage + 1, nph = phase;
@@ -275,8 +278,9 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                                 if (kb < kbc) {
 #pragma unroll
                                     for (int k4 = 0; k4 < 4; ++k4)
-                                        umma_pair_ts<I8>(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
-                                                          bdesc0 + (uint64_t)(kb * (Cfg::kKbBytes >> 4) + k4 * 2), P_IDESC, 1u);
+                                        if (ks0 + kb * 4 + k4 < a.n_ksteps)
+                                            umma_pair_ts<I8>(d_tmem, a0 + (uint32_t)((kb * 4 + k4) * 8),
+                                                              bdesc0 + (uint64_t)(kb * (Cfg::kKbBytes >> 4) + k4 * 2), P_IDESC, 1u);
                                 }
                             }
                             umma_pair_commit(empty0 + 8u * stage);  // frees the stage in both CTAs once these MMAs have read it
@@ -305,41 +309,51 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
         const int ql = quad * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t even_tempty0 = mapa_rank(tempty0, 0), even_aready = mapa_rank(aready_bar, 0);
-        Shortlist<Key> sl;
+        Shortlist<MODE_, HITS_> sl;
         uint32_t tile_iter = 0;
         bool ok = true;
         long long e_wait = 0, e_ld = 0, e_scan = 0, e_slow = 0, n_slow = 0, e_max = 0;
         const uint32_t gq = ((uint32_t)mgroup * 2u + crank) * BM + (uint32_t)ql;
         const bool q_valid = gq < (uint32_t)a.nq;
         const float qaux = a.qaux != nullptr ? __ldg(a.qaux + gq) : 0.0f;
-        // side values of the rows being scanned: fetched one tile ahead (lane l holds rows 2l, 2l+1 of each 64-row half
-        // this warp scans), passed through this warp's shared-memory scratch, read back as broadcasts
+        // Side values of the rows being scanned: cp.async moves them global -> this warp's shared-memory ring two tiles
+        // ahead of their use (lane l carries rows 2l, 2l+1 of each 64-row half this warp scans), so no register and no
+        // instruction of the tile loop ever waits for the load; the scan reads them back as broadcasts.
         constexpr int HPW = EPI_ == 2 ? 1 : BN_ / 64;  // halves per warp
-        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + SMEM_SCRATCH_OFF) + (warp - 2) * EPI_SCRATCH_WORDS;
-        uint2 side_cur[HPW], side_next[HPW];
-        auto side_load = [&](uint32_t t, uint2* dst) {
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + SMEM_SCRATCH_OFF) + (warp - 2) * (EPI_SCRATCH_SLOTS * EPI_SCRATCH_WORDS / EPI_);
+        constexpr uint32_t SLOT_WORDS = EPI_SCRATCH_WORDS / EPI_;  // 128 (four warps: two halves) or 64 (eight warps: one half)
+        auto side_fetch = [&](uint32_t t, uint32_t slot) {
+            if (MT::kBias) {
 #pragma unroll
-            for (int hh = 0; hh < HPW; ++hh) {
-                const int h = EPI_ == 2 ? eset : hh;
-                dst[hh] = __ldg(reinterpret_cast<const uint2*>(a.bias + (size_t)t * BN + h * 64) + lane);
+                for (int hh = 0; hh < HPW; ++hh) {
+                    const int h = EPI_ == 2 ? eset : hh;
+                    cp_async_8(smem_u32(scratch + slot * SLOT_WORDS + hh * 64 + 2 * lane), a.bias + (size_t)t * BN + h * 64 + 2 * lane);
+                }
             }
+            cp_async_commit();
         };
-        sl.init_floor();
+        sl.init_floor(qaux);
         for (int r = first_round; r < n_rounds && ok; ++r) {
             const uint32_t part = (uint32_t)slot + (uint32_t)r * (uint32_t)a.n_slots;
             if (part >= (uint32_t)a.P) break;
             const uint32_t t0 = part * a.tiles_per_part;
             const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
             if (r == first_round && eset == 0) load_query_to_tmem(a.qb + (size_t)gq * a.Dp * 2, a.Dp, lane_addr);  // the query tile never changes
-            sl.reset(q_valid, a.share_floor, a.gthr + (q_valid ? gq : 0), a, gq);
-            if (MT::kBias && t0 < t1) side_load(t0, side_cur);
+            sl.reset(q_valid, a, gq, part, (uint32_t)eset);
+            // ring: tile t uses slot (t - t0) % 3; tiles t0 and t0 + 1 are in flight before the loop, tile t + 2 is fetched in
+            // iteration t (one commit group per iteration, so wait_group<2> always means "tile t has landed")
+            if (MT::kBias) {
+                __syncwarp();
+                side_fetch(t0, 0);
+                side_fetch(min(t0 + 1, t1 - 1), 1);
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0 && eset == 0) mbar_arrive_cluster(even_aready);
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter % NACC;
                 if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter);
-                if (MT::kBias && t + 1 < t1) side_load(t + 1, side_next);
+                if (MT::kBias) side_fetch(min(t + 2, t1 - 1), (t - t0 + 2) % EPI_SCRATCH_SLOTS);
                 const long long ec0 = clock64();
                 if (!mbar_wait(tfull0 + 8u * buf, (tile_iter / NACC) & 1u, abort_flag, 5)) { ok = false; break; }
                 const long long ec1 = clock64();
@@ -349,8 +363,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                 for (int h = 0; h < BN_ / 64; ++h) {
                     if (EPI_ == 2 && h != eset) continue;  // the other set's half
                     if (!(a.debug_mode & 2)) {
-                        tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + h * 64, v);
-                        tmem_ld_32x32b_x32(lane_addr + DCOL + buf * BN + h * 64 + 32, v + 32);
+                        tmem_ld_32x32b_x64(lane_addr + DCOL + buf * BN + h * 64, v);
                         tmem_ld_wait();
                     }
                     if (EPI_ == 2 || h == BN_ / 64 - 1) {
@@ -363,28 +376,24 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                     if (a.debug_mode & 2) continue;
                     const uint32_t row0 = t * BN + h * 64;
                     const long long sc0 = clock64();
-                    if (MT::kBias) {
-                        __syncwarp();  // the previous half's broadcast reads are done
-                        *reinterpret_cast<uint2*>(scratch + 2 * lane) = side_cur[EPI_ == 2 ? 0 : h];
+                    if (MT::kBias && (EPI_ == 2 || h == 0)) {
+                        cp_async_wait<2>();  // this tile's side values have landed (the two younger groups may be in flight)
                         __syncwarp();
                     }
-                    keys_from_accumulators<MODE_>(v, scratch, qaux);
+                    const uint32_t* side = scratch + ((t - t0) % EPI_SCRATCH_SLOTS) * SLOT_WORDS + (EPI_ == 2 ? 0 : h * 64);
                     if (a.dump != nullptr) {
                         float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
-#pragma unroll
-                        for (int i = 0; i < 64; ++i) drow[i] = KO::as_f32(KO::from_bits(v[i]));
+                        for (int i = 0; i < 64; ++i) drow[i] = KO::as_f32(sl.fn.key(v[i], MT::kBias ? side[i] : 0u));
                     }
-                    sl.scan64(v, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
+                    sl.scan64(v, side, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
                     const long long sd = clock64() - sc0;
                     e_scan += sd;
                     if (sd > 400) { ++n_slow; e_slow += sd; }
                     if (sd > e_max) e_max = sd;
                 }
-                if (MT::kBias) {
-#pragma unroll
-                    for (int hh = 0; hh < HPW; ++hh) side_cur[hh] = side_next[hh];
-                }
+                if (MT::kBias) __syncwarp();  // every lane is done reading this tile's slot before a later fetch reuses it
             }
+            if (MT::kBias) cp_async_wait<0>();
             if (ok) sl.flush(a, gq, part, (uint32_t)eset);
         }
         if (a.prof != nullptr && warp == 2 && lane == 0) {

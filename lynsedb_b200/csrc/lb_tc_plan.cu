@@ -12,7 +12,8 @@ using namespace lb;
 namespace lb {
 
 constexpr int TC_MAX_ROW_BYTES = 2 * tc::MAX_DP;   // A operand: row_bytes / 4 <= 384 TMEM columns
-constexpr uint32_t TC_HIT_CAP = 4096;              // hit mode: candidates kept per query
+constexpr uint32_t TC_HIT_TOTAL = 8192;            // hit mode: entries of a query's hit regions together (each region 64..1024)
+constexpr int TC_FIN_MAX = 4096;                   // candidates finalize can sort per query
 
 int shadow_kind_for(int metric) {
     return metric == LB_IP ? tc::SHADOW_IP : (metric == LB_COSINE ? tc::SHADOW_COSINE : tc::SHADOW_L2);
@@ -21,6 +22,16 @@ int shadow_kind_for(int metric) {
 static int operand_row_bytes(int dim, int operand) {
     const int b = operand == tc::OPERAND_BF16 ? dim * 2 : dim;
     return (b + 127) / 128 * 128;
+}
+// L2 shadow: |c|^2 travels as three extra bf16 columns when the padded row has (or can get) room for them, so the
+// contraction itself yields 2 q.c - |c|^2 and the epilogue ranks raw accumulators; rows of 766..768 dims (and
+// LYNSE_B200_TC_L2_BIAS=1) keep the norm as an f32 side value that the epilogue subtracts (CM_F32_BIAS).
+static bool l2_uses_bias(int dim) {
+    return operand_row_bytes(dim + 3, tc::OPERAND_BF16) > TC_MAX_ROW_BYTES || tc_env_int("LYNSE_B200_TC_L2_BIAS", 0) != 0;
+}
+static int shadow_row_bytes(const lb_index* idx, int kind, int operand) {
+    const int extra = (kind == tc::SHADOW_L2 && operand == tc::OPERAND_BF16 && !l2_uses_bias((int)idx->dim)) ? 3 : 0;
+    return operand_row_bytes((int)idx->dim + extra, operand);
 }
 // LYNSE_B200_TC_OPERAND = bf16 | u8 | auto (default).  auto: 8-bit operands for IP / cosine when the measured
 // quantisation error of the corpus is within 2x of what bf16 rounding would have cost (uniform-ish data: 1.3x; heavy
@@ -35,7 +46,7 @@ static int operand_policy() {
 static int first_operand(const lb_index* idx, int kind) {
     const int pol = operand_policy();
     if (kind == tc::SHADOW_L2) return tc::OPERAND_BF16;
-    if (pol == 0 && operand_row_bytes((int)idx->dim, tc::OPERAND_BF16) <= TC_MAX_ROW_BYTES) return tc::OPERAND_BF16;
+    if (pol == 0 && shadow_row_bytes(idx, kind, tc::OPERAND_BF16) <= TC_MAX_ROW_BYTES) return tc::OPERAND_BF16;
     return tc::OPERAND_U8;
 }
 bool tc_supported(lb_index* idx, int metric) {
@@ -45,7 +56,7 @@ bool tc_supported(lb_index* idx, int metric) {
     const Shadow& sh = idx->shadow[kind];
     if (sh.disabled) return false;
     const int operand = sh.operand >= 0 ? sh.operand : first_operand(idx, kind);
-    return operand_row_bytes((int)idx->dim, operand) <= TC_MAX_ROW_BYTES;
+    return shadow_row_bytes(idx, kind, operand) <= TC_MAX_ROW_BYTES;
 }
 
 static int encode_shadow_map(CUtensorMap* out, void* base, int nkb, uint64_t n_tiles, int box_halves, int box_kb) {
@@ -135,10 +146,11 @@ int ensure_shadow(lb_index* idx, int kind) {
     if (sh.operand < 0) sh.operand = first_operand(idx, kind);
     const int warps = 8;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        const int rb = operand_row_bytes((int)idx->dim, sh.operand);
+        const int rb = shadow_row_bytes(idx, kind, sh.operand);
         if (rb > TC_MAX_ROW_BYTES) return fail(LB_UNSUPPORTED, "dimension too large for the tensor-core plan");
         if (!sh.stats.p) LB_TRY(reset_stats(idx, sh));
-        LB_TRY(shadow_reserve(idx, sh, idx->n, idx->rows.cap / row_bytes(idx), rb, kind == tc::SHADOW_L2 ? 1 : 0, 0x7F800000u /* +inf */, 0u));
+        if (sh.rows == 0) sh.l2_bias = kind == tc::SHADOW_L2 && l2_uses_bias((int)idx->dim);
+        LB_TRY(shadow_reserve(idx, sh, idx->n, idx->rows.cap / row_bytes(idx), rb, sh.l2_bias ? 1 : 0, 0x7F800000u /* +inf */, 0u));
         if (sh.rows < idx->n) {
             uint64_t first = sh.rows, cnt = idx->n - first;
             tc::ShadowStats st{};
@@ -164,11 +176,11 @@ int ensure_shadow(lb_index* idx, int kind) {
                     LB_CUDA_TRY(cudaMemsetAsync(&sh.stats.as<tc::ShadowStats>()->emax_bits, 0, 4, idx->stream));
                 }
                 tc::build_shadow_kernel<tc::OPERAND_U8><<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
-                    idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), sh.side.as<float>(),
+                    idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), nullptr,
                     sh.stats.as<tc::ShadowStats>(), sh.c_scale, sh.c_zero);
             } else {
                 tc::build_shadow_kernel<tc::OPERAND_BF16><<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
-                    idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), sh.side.as<float>(),
+                    idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), sh.l2_bias ? sh.side.as<float>() : nullptr,
                     sh.stats.as<tc::ShadowStats>(), 1.0f, 0.0f);
             }
             LB_CUDA_TRY(cudaGetLastError());
@@ -180,7 +192,7 @@ int ensure_shadow(lb_index* idx, int kind) {
                 sh.disabled = true;
                 return LB_OK;
             }
-            if (sh.operand == tc::OPERAND_U8 && operand_policy() == 2 && operand_row_bytes((int)idx->dim, tc::OPERAND_BF16) <= TC_MAX_ROW_BYTES &&
+            if (sh.operand == tc::OPERAND_U8 && operand_policy() == 2 && shadow_row_bytes(idx, kind, tc::OPERAND_BF16) <= TC_MAX_ROW_BYTES &&
                 sh.emax > 2.0f * bits_f32(st.e16max_bits)) {
                 // 8-bit quantisation is too coarse for this corpus (heavy tails): use the bf16 operand instead
                 if (getenv("LYNSE_B200_TC_TRACE"))
@@ -242,52 +254,64 @@ struct CoarseJob {
     const uint32_t* bias = nullptr;
     const uint32_t* idesc_extra = nullptr;
     int nq = 0, k = 0;
+    int n_ksteps = 0;      // MMA K steps (32 operand bytes) that hold data
     const uint64_t* d_allow = nullptr;
     float* dump = nullptr;
     // results of the planning, for finalize
     int n_lists = 0;       // shortlists per query (list mode)
     bool hit_mode = false;
+    uint32_t hit_cap = 0;
     uint32_t* flags = nullptr;   // [0]=kernel error, [1]=n_uncertified, [2..3] clock probe, [4..4+nq) per-query flags, then gthr[nq]
     uint32_t* gthr = nullptr;
 };
 static bool mode_int_key(int mode) { return mode == tc::CM_I32 || mode == tc::CM_I32_HAMMING; }
 
-template <int MODE>
+// kernel shapes: 0 = one CTA per query tile; CTA pairs: 1 = <64 rows, 2 accumulators>, 2 = <128, 2>, 3 = <128, 3>,
+// 4 = <128, 3, two epilogue sets> (hit mode only: without the shortlist registers the eight epilogue warps fit)
+template <int MODE, bool HITS>
 static int launch_coarse_mode(int cfg_id, cudaLaunchConfig_t cfg, const Shadow& sh, const tc::TcArgs& args) {
     switch (cfg_id) {
         case 0:
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_single_kernel<MODE>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel<MODE>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_single_kernel<MODE, HITS>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_single_kernel<MODE, HITS>, sh.tmap_full[0], sh.tmap_rem[0], args));
             break;
         case 1:
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<64, 2, 1, MODE>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<64, 2, 1, MODE>, sh.tmap_full[1], sh.tmap_rem[1], args));
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<64, 2, 1, MODE, HITS>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<64, 2, 1, MODE, HITS>, sh.tmap_full[1], sh.tmap_rem[1], args));
             break;
         case 2:
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 2, 1, MODE>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 2, 1, MODE>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 2, 1, MODE, HITS>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 2, 1, MODE, HITS>, sh.tmap_full[0], sh.tmap_rem[0], args));
             break;
         case 3:
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 1, MODE>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3, 1, MODE>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 1, MODE, HITS>, (int)tc::SMEM_BYTES));
+            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3, 1, MODE, HITS>, sh.tmap_full[0], sh.tmap_rem[0], args));
             break;
         default:
-            cfg.blockDim = dim3(64 + 128 * 2);
-            LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 2, MODE>, (int)tc::SMEM_BYTES));
-            LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3, 2, MODE>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            if (HITS) {
+                cfg.blockDim = dim3(64 + 128 * 2);
+                LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 2, MODE, true>, (int)tc::SMEM_BYTES));
+                LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3, 2, MODE, true>, sh.tmap_full[0], sh.tmap_rem[0], args));
+            } else {
+                return fail(LB_INTERNAL, "two epilogue sets are a hit-mode kernel shape");
+            }
             break;
     }
     return LB_OK;
 }
-static int launch_coarse_any(int mode, int cfg_id, const cudaLaunchConfig_t& cfg, const Shadow& sh, const tc::TcArgs& args) {
+static int launch_coarse_any(int mode, bool hits, int cfg_id, const cudaLaunchConfig_t& cfg, const Shadow& sh, const tc::TcArgs& args) {
+#define LB_MODE_CASE(M)                                                                       \
+    case M:                                                                                   \
+        return hits ? launch_coarse_mode<M, true>(cfg_id, cfg, sh, args) : launch_coarse_mode<M, false>(cfg_id, cfg, sh, args);
     switch (mode) {
-        case tc::CM_F32: return launch_coarse_mode<tc::CM_F32>(cfg_id, cfg, sh, args);
-        case tc::CM_F32_BIAS: return launch_coarse_mode<tc::CM_F32_BIAS>(cfg_id, cfg, sh, args);
-        case tc::CM_I32: return launch_coarse_mode<tc::CM_I32>(cfg_id, cfg, sh, args);
-        case tc::CM_I32_HAMMING: return launch_coarse_mode<tc::CM_I32_HAMMING>(cfg_id, cfg, sh, args);
-        case tc::CM_JACCARD: return launch_coarse_mode<tc::CM_JACCARD>(cfg_id, cfg, sh, args);
-        default: return launch_coarse_mode<tc::CM_DICE>(cfg_id, cfg, sh, args);
+        LB_MODE_CASE(tc::CM_F32)
+        LB_MODE_CASE(tc::CM_F32_BIAS)
+        LB_MODE_CASE(tc::CM_I32)
+        LB_MODE_CASE(tc::CM_I32_HAMMING)
+        default:
+            return hits ? launch_coarse_mode<tc::CM_RATIO, true>(cfg_id, cfg, sh, args) : launch_coarse_mode<tc::CM_RATIO, false>(cfg_id, cfg, sh, args);
     }
+#undef LB_MODE_CASE
 }
 
 // rows per accumulator tile of the kernel coarse_pass picks for operand rows of row_b bytes
@@ -312,11 +336,9 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     if (pair) {
         const bool bn128 = plan_bn(row_b, true) == 128;
         const bool nacc3 = bn128 && row_b / 4 <= tc::PairCfg<128, 3>::kDCol && tc_env_int("LYNSE_B200_TC_NACC", 3) == 3;
-        const bool epi2 = nacc3 && k > tc::KP - 4 && tc_env_int("LYNSE_B200_TC_EPI", 2) == 2;
-        cfg_id = epi2 ? 4 : (nacc3 ? 3 : (bn128 ? 2 : 1));
+        cfg_id = nacc3 ? 3 : (bn128 ? 2 : 1);
         BN = bn128 ? 128 : 64;
     }
-    const uint64_t L = cfg_id == 4 ? 2 : 1;  // shortlists per partition
     const int n_mgroups = (n_mtiles + cluster - 1) / cluster;
     const uint32_t tiles_total = (uint32_t)ceil_div(idx->n, BN);
     // Slots: groups of n_mgroups co-resident clusters (one per query group) that stream the same row partitions in
@@ -331,6 +353,9 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     const bool seeded = k > tc::KP - 4 && tiles_total >= (uint32_t)(64 * 8) * (uint32_t)n_slots && job.dump == nullptr &&
                         tc_env_int("LYNSE_B200_TC_SEED", 1) != 0;
     const bool hit_mode = seeded && tc_env_int("LYNSE_B200_TC_HITS", 1) != 0;
+    // narrow rows in hit mode: two sets of epilogue warps, each scanning one 64-row half of every tile into its own hit region
+    if (hit_mode && cfg_id == 3 && tc_env_int("LYNSE_B200_TC_EPI", 2) == 2) cfg_id = 4;
+    const uint64_t L = cfg_id == 4 ? 2 : 1;  // shortlists / hit regions per partition
     // List mode: the certification needs the largest partition floor T (the KP-th best coarse key of one partition) to sit
     // well below the k-th best score overall, so the union of the shortlists must reach far past rank k: aim at
     // P*KP >= 32*k candidates (measured on C3, k = 100: P = 36 leaves 1385 of 1024 queries uncertified, P = 72
@@ -356,10 +381,12 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     uint32_t* flags = idx->w_flags.as<uint32_t>();
     LB_CUDA_TRY(cudaMemsetAsync(flags, 0, 16, idx->stream));
     LB_CUDA_TRY(cudaMemsetAsync(flags + 4 + nq, 0, (size_t)nq * 4, idx->stream));
+    // hit regions: one per (query, partition, epilogue set); a region that is never visited (short corpus) must read 0
+    const uint32_t hit_cap = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(64, TC_HIT_TOTAL / (P * L)));
     if (hit_mode) {
-        LB_TRY(idx->w_hits.ensure((size_t)nq * TC_HIT_CAP * 8));
-        LB_TRY(idx->w_hit_count.ensure((size_t)nq * 4));
-        LB_CUDA_TRY(cudaMemsetAsync(idx->w_hit_count.p, 0, (size_t)nq * 4, idx->stream));
+        LB_TRY(idx->w_hits.ensure((size_t)nq * P * L * hit_cap * 8));
+        LB_TRY(idx->w_hit_count.ensure((size_t)nq * P * L * 4));
+        LB_CUDA_TRY(cudaMemsetAsync(idx->w_hit_count.p, 0, (size_t)nq * P * L * 4, idx->stream));
     }
 
     tc::TcArgs a{};
@@ -368,6 +395,7 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     a.n_mtiles = n_mtiles;
     a.Dp = Dp;
     a.rem_kb = (Dp / tc::KBLK) % tc::KPS;
+    a.n_ksteps = job.n_ksteps;
     a.n_rows = (uint32_t)idx->n;
     a.tiles_total = tiles_total;
     a.tiles_per_part = tiles_per_part;
@@ -430,8 +458,9 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
         sa.P = (int)ceil_div(S, sa.tiles_per_part);
         sa.parts_per_slot = 1;
         sa.share_floor = 0;
-        LB_TRY(launch_coarse_any(job.mode, cfg_id, cfg, sh, sa));
-        const int s_lists = sa.P * (int)L;
+        sa.lists_per_part = 1;
+        LB_TRY(launch_coarse_any(job.mode, false, cfg_id == 4 ? 3 : cfg_id, cfg, sh, sa));
+        const int s_lists = sa.P;
         const int sm = next_pow2(s_lists * tc::KP);
         // aim at ~max(10 k, 512) rows of the whole corpus above the seeded floor
         const uint64_t want_rows = std::max<uint64_t>((uint64_t)10 * k, 512);
@@ -445,16 +474,17 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
         if (hit_mode) {
             a.hit_count = idx->w_hit_count.as<uint32_t>();
             a.hit_buf = idx->w_hits.as<uint2>();
-            a.hit_cap = TC_HIT_CAP;
+            a.hit_cap = hit_cap;
         }
     }
-    LB_TRY(launch_coarse_any(job.mode, cfg_id, cfg, sh, a));
+    LB_TRY(launch_coarse_any(job.mode, hit_mode, cfg_id, cfg, sh, a));
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
     idx->stats.kernels_launched += 1;
     idx->stats.n_partitions = (uint32_t)P;
     job.n_lists = (int)(P * L);
     job.hit_mode = hit_mode;
+    job.hit_cap = hit_cap;
     idx->stats.coarse_operand = sh.operand == tc::OPERAND_U8 ? 1u : 0u;
     idx->stats.coarse_hit_mode = hit_mode ? 1u : 0u;
     job.flags = flags;
@@ -474,10 +504,10 @@ static void fill_fin_candidates(lb_index* idx, const CoarseJob& job, tc::FinArgs
     f.P = job.n_lists;
     f.hit_count = job.hit_mode ? idx->w_hit_count.as<uint32_t>() : nullptr;
     f.hit_buf = job.hit_mode ? idx->w_hits.as<uint2>() : nullptr;
-    f.hit_cap = job.hit_mode ? TC_HIT_CAP : 0;
+    f.hit_cap = job.hit_mode ? job.hit_cap : 0;
     f.gthr = job.gthr;
     f.int_key = mode_int_key(job.mode) ? 1 : 0;
-    f.M1 = job.hit_mode ? (int)TC_HIT_CAP : next_pow2(job.n_lists * tc::KP);
+    f.M1 = job.hit_mode ? TC_FIN_MAX : next_pow2(job.n_lists * tc::KP);
     f.R = std::min(1024, std::max(128, next_pow2(4 * job.k)));
     f.nq = job.nq;
     f.k = job.k;
@@ -515,12 +545,15 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
         idx->stats.kernels_launched += 1;
         job.idesc_extra = idesc_extra;
         job.mode = tc::CM_I32;
+        job.n_ksteps = ((int)idx->dim + 31) / 32;
     } else {
+        const bool norm_cols = kind == tc::SHADOW_L2 && !sh.l2_bias;
         tc::prepare_queries_kernel<<<(nq_pad + warps - 1) / warps, warps * 32, 0, idx->stream>>>(
-            d_queries, nq, nq_pad, (int)idx->dim, row_b, kind, idx->w_qb.as<unsigned char>(), idx->w_qnorm.as<tc::QStat>());
+            d_queries, nq, nq_pad, (int)idx->dim, row_b, kind, norm_cols ? 1 : 0, idx->w_qb.as<unsigned char>(), idx->w_qnorm.as<tc::QStat>());
         LB_CUDA_TRY(cudaGetLastError());
-        job.mode = kind == tc::SHADOW_L2 ? tc::CM_F32_BIAS : tc::CM_F32;
-        job.bias = kind == tc::SHADOW_L2 ? sh.side.as<uint32_t>() : nullptr;
+        job.mode = sh.l2_bias ? tc::CM_F32_BIAS : tc::CM_F32;
+        job.bias = sh.l2_bias ? sh.side.as<uint32_t>() : nullptr;
+        job.n_ksteps = ((int)idx->dim + (norm_cols ? 3 : 0) + 15) / 16;
     }
     job.qb = idx->w_qb.as<unsigned char>();
     job.nq = nq;
@@ -592,10 +625,11 @@ int run_tc_bits(lb_index* idx, int metric, const uint64_t* words, int n_words, c
     LB_CUDA_TRY(cudaGetLastError());
     CoarseJob job;
     job.sh = &sh;
-    job.mode = metric == LB_HAMMING ? tc::CM_I32_HAMMING : (metric == LB_DICE ? tc::CM_DICE : tc::CM_JACCARD);
+    job.mode = metric == LB_HAMMING ? tc::CM_I32_HAMMING : tc::CM_RATIO;
     job.qb = idx->w_qb.as<unsigned char>();
     job.qaux = idx->w_qaux.as<float>();
     job.bias = metric == LB_HAMMING ? sh.side.as<uint32_t>() : sh.side2.as<uint32_t>();
+    job.n_ksteps = 2 * n_words;
     job.nq = nq;
     job.k = k;
     job.d_allow = d_allow;
