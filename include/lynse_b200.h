@@ -106,6 +106,10 @@ int lb_index_reserve(lb_index* idx, uint64_t n_rows);
 /* segment_target_bytes: DEFAULT_SEGMENT_TARGET_BYTES / LYNSE_SEGMENT_TARGET_BYTES
  * (src/storage/vector_store.rs:32, :225-229); 0 = default 256 MiB. */
 int lb_index_set_segment_target(lb_index* idx, uint64_t segment_target_bytes);
+/* The next append opens a new segment even if it would fit the last one: a host that spreads the segments of one
+ * VectorStore over several indexes (one per GPU) keeps the reference's segment boundaries this way (the inner-product
+ * kernel choice depends on them, src/storage/flat_mmap.rs:4845-4869). */
+int lb_index_new_segment(lb_index* idx);
 /* replaces VectorStore::append / FlatMmap::write: host row-major rows -> HBM.
  * An append is never split across segments. */
 int lb_index_append_f32(lb_index* idx, const float* rows, uint64_t n);

@@ -6,10 +6,10 @@ hand-written CUDA for sm_100a loaded through ctypes (``lynsedb_b200/liblynse_b20
 from . import metrics
 from ._backend import FlatIndex, IvfFlatIndex, compute_distance, top_k_search
 from .client import Collection, Database, VectorDBClient
-from .index import DeviceIndex, make_allow_bits
+from .index import DeviceIndex, ShardedDeviceIndex, make_allow_bits
 from .ivf import IVFIndex
 from .result_view import ResultView
 
 __version__ = "0.1.0"
-__all__ = ["VectorDBClient", "Database", "Collection", "DeviceIndex", "IVFIndex", "FlatIndex", "IvfFlatIndex", "ResultView", "compute_distance",
+__all__ = ["VectorDBClient", "Database", "Collection", "DeviceIndex", "ShardedDeviceIndex", "IVFIndex", "FlatIndex", "IvfFlatIndex", "ResultView", "compute_distance",
            "top_k_search", "make_allow_bits", "metrics"]

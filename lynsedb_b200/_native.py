@@ -55,6 +55,7 @@ SIGNATURES = {
     "lb_index_destroy": (None, [_vp]),
     "lb_index_reserve": (C.c_int, [_vp, C.c_uint64]),
     "lb_index_set_segment_target": (C.c_int, [_vp, C.c_uint64]),
+    "lb_index_new_segment": (C.c_int, [_vp]),
     "lb_index_append_f32": (C.c_int, [_vp, _f32p, C.c_uint64]),
     "lb_index_append_packed": (C.c_int, [_vp, _u64p, C.c_uint64]),
     "lb_index_append_synthetic": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64]),

@@ -17,7 +17,7 @@ from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Unio
 import numpy as np
 
 from . import metrics as M
-from .index import DeviceIndex, make_allow_bits
+from .index import DeviceIndex, ShardedDeviceIndex, make_allow_bits, visible_devices
 from .ivf import DEFAULT_N_CLUSTERS, DEFAULT_NPROBE, IVFIndex
 from .result_view import ResultView
 
@@ -25,6 +25,7 @@ PENDING_FLUSH_ROWS = 10_000          # src/engine.rs:93-94
 PENDING_FLUSH_BYTES = 32 << 20
 MAX_DATABASES = 64                   # python/lynse/__init__.py:128
 TENSOR_PLAN_MAX_K = 256              # largest k the tensor-core plan of the library serves
+NATIVE_MAX_K = 2048                  # largest k of any native search (lb_index_search)
 KNOWN_BUILD_KEYS = frozenset({"n_clusters", "n_centroids", "m", "ef_construction", "ef_search", "max_level", "r", "l",
                               "alpha", "max_degree", "nprobe", "replica_count"})  # python/lynse/_index_build.py:49-66
 _DOMAIN_FREE = (M.IP, M.L2, M.COSINE, M.HAMMING, M.JACCARD)
@@ -43,7 +44,7 @@ class Collection:
     dict of field == value conditions (the reference's SQL ``where`` strings need its metadata engine, out of scope)."""
 
     def __init__(self, name: str, dim: Optional[int] = None, *, dtypes: str = "float32", default_index: Optional[str] = "FLAT-IP",
-                 description: Optional[str] = None, device: int = 0):
+                 description: Optional[str] = None, device: int = 0, devices: Optional[Sequence[int]] = None):
         if dtypes not in ("float32", "float16"):
             raise ValueError(f"unsupported dtypes: {dtypes!r}")
         # float16 collections: vectors are rounded to IEEE binary16 at write time exactly as the reference encodes them
@@ -57,6 +58,8 @@ class Collection:
         self.description = description
         self._dim = int(dim) if dim else None
         self._device = device
+        # several devices: the store's segments are spread over them (ShardedDeviceIndex) and every FLAT search fans out
+        self._devices = [int(d) for d in devices] if devices else [int(device)]
         self._default_index = default_index
         self._index_mode: Optional[str] = None
         self._metric = M.IP
@@ -71,6 +74,11 @@ class Collection:
         self._id_rows: Dict[Any, int] = {}
         self._fields: Dict[int, dict] = {}
         self._tombstones: set = set()
+        self._max_int_id = -1
+        self._ids_np: Optional[np.ndarray] = None      # row -> id as int64 while every id is an integer (vectorised id mapping)
+        self._ids_all_int = True
+        self._dead_rows: Optional[np.ndarray] = None   # sorted rows of the tombstoned ids (rebuilt when the set changes)
+        self._dead_masks: Dict[Any, np.ndarray] = {}    # cached allow-bitsets with the tombstoned rows cleared
         self.COMMIT_FLAG = True
 
     # ------------------------------------------------------------------ basics
@@ -105,8 +113,7 @@ class Collection:
         return self._dtypes
 
     def max_id(self) -> int:
-        ints = [i for i in self._row_ids if isinstance(i, (int, np.integer)) and not isinstance(i, bool)]
-        return int(max(ints)) if ints else -1
+        return self._max_int_id
 
     def is_id_exists(self, id) -> bool:
         return id in self._id_rows and id not in self._tombstones
@@ -168,6 +175,11 @@ class Collection:
             for j, e in enumerate(ext):
                 self._id_rows[e] = base + j
                 self._row_ids.append(e)
+                if isinstance(e, (int, np.integer)) and not isinstance(e, bool):
+                    if e > self._max_int_id:
+                        self._max_int_id = int(e)
+                else:
+                    self._ids_all_int = False
                 if field_list is not None and field_list[j] is not None:
                     self._fields[base + j] = dict(field_list[j])
             for s in range(0, n, batch_size):   # one add_items call per batch, as the reference client does
@@ -186,11 +198,14 @@ class Collection:
             return ext[0] if n == 1 else ext
         return ext[0] if single else ext
 
-    def _ensure_store(self) -> DeviceIndex:
+    def _ensure_store(self):
         if self._store is None:
             if self._dim is None:
                 raise ValueError("collection dimension is not known yet")
-            self._store = DeviceIndex(self._dim, "float32", self._device)
+            if len(self._devices) > 1:
+                self._store = ShardedDeviceIndex(self._dim, "float32", self._devices)
+            else:
+                self._store = DeviceIndex(self._dim, "float32", self._devices[0])
             if self._dtypes == "float16":
                 # segment boundaries never reach a float16 collection's results: search() scores rows one by one, and the
                 # batch path scans `read_all_f32()` — the whole store as ONE array (src/engine.rs:5448-5453), so the
@@ -220,11 +235,49 @@ class Collection:
         self._pending = []
         self._pending_rows = 0
         self._drop_pending_index()
+        self._dead_masks.clear()
+        if self._ivf is not None:
+            # the inverted lists cover the rows of the store at build time: rebuilt over the grown store on the next search
+            self._ivf.close()
+            self._ivf = None
 
     def commit(self) -> None:
         with self._lock:
             self._flush_pending()
             self.COMMIT_FLAG = True
+
+    def insert_session(self) -> "InsertSession":
+        """``with coll.insert_session() as s: s.add(...)`` — adds are applied and committed when the block ends
+        (python/lynse/execution_layer/session.py)."""
+        return InsertSession(self)
+
+    def compact(self) -> int:
+        """Physically drop the tombstoned rows and rebuild the store (``Collection::compact``); returns the rows removed.
+        Rows keep their relative order, so ties still resolve the way they did."""
+        with self._lock:
+            self._flush_pending()
+            dead_rows = set(self._id_rows[t] for t in self._tombstones)
+            if not dead_rows:
+                return 0
+            n = len(self._row_ids)
+            live = np.asarray([r for r in range(n) if r not in dead_rows], dtype=np.int64)
+            vectors = self._store.read_rows(0, n)[live] if n else np.empty((0, self._dim or 0), np.float32)
+            ids = [self._row_ids[int(r)] for r in live]
+            fields = {new: self._fields[int(old)] for new, old in enumerate(live) if int(old) in self._fields}
+            if self._ivf is not None:
+                self._ivf.close()
+                self._ivf = None
+            self._store.close()
+            self._store = None
+            self._row_ids, self._id_rows, self._fields = list(ids), {e: i for i, e in enumerate(ids)}, fields
+            self._tombstones = set()
+            self._dead_rows, self._ids_np = None, None
+            self._dead_masks.clear()
+            if len(ids):
+                self._ensure_store().append(np.ascontiguousarray(vectors, dtype=np.float32))
+                if self._index_mode and not self._index_mode.startswith("IVF"):
+                    self._store.prepare(self._metric)
+            return len(dead_rows)
 
     def load_lynsedb_directory(self, collection_path, dtype: Optional[str] = None) -> int:
         """Load the vectors of an existing LynseDB collection directory (vector_manifest.json + segment files + id_map.bin,
@@ -248,6 +301,8 @@ class Collection:
                     self._ensure_store().append(R.read_segment(path, rows, self._dim, dtype))
             self._row_ids = list(ext)
             self._id_rows = {e: i for i, e in enumerate(ext)}
+            self._max_int_id = max([-1] + [int(e) for e in ext])
+            self._ids_np = None
         self._maybe_build_default_index()
         return total
 
@@ -265,9 +320,15 @@ class Collection:
                 raise ValueError(f"Dimension mismatch: expected {self._dim}, got {q.shape[1]}")
             self._flush_pending()
             want = min(max_results + len(self._tombstones), len(self._store))
-            if want > 2048:
-                raise ValueError("search_range is limited to max_results + deleted rows <= 2048 on this path")
-            rows, dists, counts = self._store.search(q, want, self._metric, pairwise=True)
+            allow = None
+            if want > NATIVE_MAX_K:
+                # many deleted rows: mask them out and ask for max_results (the over-fetch only exists to survive the
+                # tombstone filter, src/engine.rs:6410-6483)
+                allow = self._live_mask(len(self._store), None)
+                want = min(max_results, len(self._store))
+            if want > NATIVE_MAX_K:
+                raise ValueError("search_range is limited to max_results <= 2048 on this path")
+            rows, dists, counts = self._store.search(q, want, self._metric, allow, pairwise=True)
             asc = M.is_ascending(self._metric)
             ids, out = [], []
             for r, d in zip(rows[0, :int(counts[0])].tolist(), dists[0, :int(counts[0])].tolist()):
@@ -295,6 +356,9 @@ class Collection:
                 if i in self._id_rows and i not in self._tombstones:
                     self._tombstones.add(i)
                     n += 1
+            if n:
+                self._dead_rows = None
+                self._dead_masks.clear()
             return n
 
     def restore(self, ids) -> int:
@@ -306,6 +370,9 @@ class Collection:
                 if i in self._tombstones:
                     self._tombstones.discard(i)
                     n += 1
+            if n:
+                self._dead_rows = None
+                self._dead_masks.clear()
             return n
 
     # ------------------------------------------------------------------ index
@@ -320,16 +387,21 @@ class Collection:
                 raise ValueError(f"unknown index build parameter {key!r}; supported keys: {', '.join(sorted(KNOWN_BUILD_KEYS))}")
         mode = str(index_mode).upper()
         family = _index_family(mode)
-        if family not in ("FLAT", "IVF"):
-            raise ValueError(f"index family {family} is outside this package's scope (FLAT-* and IVF-* only)")
-        if mode in ("FLAT", "IVF"):
+        # HNSW / DiskANN / SPANN modes are accepted and served by the exact FLAT scan of their metric: on a B200 the
+        # full-bandwidth scan is faster than the reference's graph walks and returns the exact neighbours the graphs
+        # approximate (the index_mode string and ResultView.index_type keep the requested family)
+        if mode in ("FLAT", "IVF", "HNSW", "DISKANN", "SPANN"):
             raise ValueError(f"unknown index type '{index_mode}'")       # bare family names are rejected (src/index/mod.rs:827-836)
         metric = M.from_index_mode(mode)
         if metric is None:
             raise ValueError(f"unknown index type '{index_mode}'")
         if family == "IVF" and metric not in _DOMAIN_FREE and metric not in (M.TANIMOTO, M.DICE):
             raise ValueError(f"unsupported index/metric combination '{index_mode}'")
+        if family not in ("FLAT", "IVF") and metric in (M.CANBERRA, M.BRAY_CURTIS):
+            raise ValueError(f"unsupported index/metric combination '{index_mode}'")   # exact-only metrics have no graph index
         if any(tok in mode.split("-") for tok in ("SQ8", "PQ", "RABITQ", "POLARVEC")):
+            if metric not in _DOMAIN_FREE:
+                raise ValueError(f"unsupported index/metric combination '{index_mode}'")
             raise ValueError(f"quantized index '{index_mode}' is outside this package's scope")
         with self._lock:
             if self._dim is not None and not M.accepts_dimension(metric, self._dim):
@@ -351,6 +423,18 @@ class Collection:
     def _build_ivf(self) -> None:
         if self._store is None or len(self._store) == 0:
             return
+        if isinstance(self._store, ShardedDeviceIndex):
+            # the inverted lists address the rows of ONE device index: gather the store on the first device
+            single = DeviceIndex(self._dim, "float32", self._devices[0])
+            n, pos = len(self._store), 0
+            for rows in self._store.segments():
+                single.new_segment()
+                single.append(self._store.read_rows(pos, rows))
+                pos += rows
+            assert pos == n
+            self._store.close()
+            self._store = single
+            self._devices = self._devices[:1]
         self._ivf = IVFIndex(self._store, self._metric, n_clusters=self._ivf_params["n_clusters"],
                              nprobe=self._ivf_params["nprobe"])
 
@@ -370,9 +454,9 @@ class Collection:
         if filter_ids is not None:
             rows = {self._id_rows[i] for i in filter_ids if i in self._id_rows}
         if where is not None:
-            if isinstance(where, str):
-                raise NotImplementedError("SQL where-strings need the reference's metadata engine; pass a callable or a dict")
             pred: Callable[[dict], bool]
+            if isinstance(where, str):
+                where = _compile_where(where)
             if isinstance(where, dict):
                 cond = dict(where)
                 pred = lambda f: all(f.get(k) == v for k, v in cond.items())  # noqa: E731
@@ -382,36 +466,61 @@ class Collection:
             rows = matched if rows is None else rows & matched
         return np.fromiter(sorted(rows), dtype=np.uint64, count=len(rows))
 
-    def _search_rows(self, q: np.ndarray, search_k: int, nprobe: int, subset: Optional[np.ndarray], single: bool = False,
-                     k: Optional[int] = None):
-        """(rows, dists) per query over flushed + pending rows, before id mapping: scan, pending_search, merge_row_results."""
+    # ---- tombstones as a row mask ------------------------------------------------------------------------------------
+    def _dead_row_array(self) -> np.ndarray:
+        if self._dead_rows is None:
+            self._dead_rows = np.sort(np.fromiter((self._id_rows[t] for t in self._tombstones), dtype=np.uint64, count=len(self._tombstones)))
+        return self._dead_rows
+
+    def _live_mask(self, n_rows: int, allow: Optional[np.ndarray], first_row: int = 0) -> np.ndarray:
+        """Allow-bitset over rows [first_row, first_row + n_rows) with the tombstoned rows cleared (and ``allow`` applied).
+        Masking the deleted rows out and asking for k gives the same live top-k as the reference's over-fetch of
+        ``k + |tombstones|`` followed by the tombstone filter (src/engine.rs:4735-4741, :3286-3308)."""
+        key = (first_row, n_rows)
+        base = self._dead_masks.get(key)
+        if base is None:
+            dead = self._dead_row_array()
+            dead = dead[(dead >= first_row) & (dead < first_row + n_rows)] - np.uint64(first_row)
+            base = np.full((n_rows + 63) // 64, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+            if n_rows & 63:
+                base[-1] = (np.uint64(1) << np.uint64(n_rows & 63)) - np.uint64(1)
+            np.bitwise_and.at(base, (dead >> np.uint64(6)).astype(np.int64), ~(np.uint64(1) << (dead & np.uint64(63))))
+            self._dead_masks[key] = base
+        return base if allow is None else (base & allow)
+
+    def _search_rows(self, q: np.ndarray, k: int, nprobe: int, subset: Optional[np.ndarray], single: bool = False):
+        """(rows[nq, m] u64, dists[nq, m] f32, counts[nq]) over flushed + pending rows, before id mapping: scan,
+        pending_search, merge_row_results.  Tombstoned rows may be present when the over-fetch path was taken."""
         nq = q.shape[0]
         n_store = len(self._store) if self._store is not None else 0
-        out: List[tuple] = [(np.empty(0, np.uint64), np.empty(0, np.float32)) for _ in range(nq)]
-        if n_store and search_k > 0:
+        n_dead = len(self._tombstones)
+        search_k = k + n_dead                                # engine.rs:4735-4741
+        rows = np.empty((nq, 0), np.uint64)
+        dists = np.empty((nq, 0), np.float32)
+        counts = np.zeros(nq, np.int64)
+        if n_store and k > 0:
             allow = None
             if subset is not None:
                 allow = make_allow_bits(n_store, subset[subset < n_store])
             if self._index_mode and self._index_mode.startswith("IVF"):
                 if self._ivf is None:
                     self._build_ivf()
-                rows, dists, counts = self._ivf.search(q, search_k, nprobe, allow)
+                stored_k = search_k
+                if search_k > NATIVE_MAX_K:
+                    allow = self._live_mask(n_store, allow)
+                    stored_k = k
+                r, d, c = self._ivf.search(q, stored_k, nprobe, allow)
             else:
                 f16_rows = self._dtypes == "float16" and (single or subset is not None)
                 stored_k = search_k
-                if k is not None and search_k > TENSOR_PLAN_MAX_K >= k:
-                    # many deleted rows: asking for k + |tombstones| would push the search off the tensor-core plan.
-                    # Masking the deleted rows out and asking for k gives the same live top-k (the over-fetch exists
-                    # only to survive the tombstone filter, src/engine.rs:4735-4741, :3286-3308).
-                    dead = np.fromiter((self._id_rows[t] for t in self._tombstones), dtype=np.uint64, count=len(self._tombstones))
-                    dead = dead[dead < n_store]
-                    if allow is None:
-                        allow = np.full((n_store + 63) // 64, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
-                    np.bitwise_and.at(allow, (dead >> np.uint64(6)).astype(np.int64), ~(np.uint64(1) << (dead & np.uint64(63))))
+                if n_dead and (search_k > TENSOR_PLAN_MAX_K >= k or search_k > NATIVE_MAX_K):
+                    # many deleted rows: asking for k + |tombstones| would push the search off the tensor-core plan (or
+                    # past the native k limit): mask the deleted rows out and ask for k
+                    allow = self._live_mask(n_store, allow)
                     stored_k = k
-                rows, dists, counts = self._store.search(q, stored_k, self._metric, allow, f16_rows=f16_rows)
-            out = [(rows[i, :int(counts[i])].astype(np.uint64), dists[i, :int(counts[i])].copy()) for i in range(nq)]
-        if self._pending_rows and search_k > 0:
+                r, d, c = self._store.search(q, stored_k, self._metric, allow, f16_rows=f16_rows)
+            rows, dists, counts = r.astype(np.uint64), d, c.astype(np.int64)
+        if self._pending_rows and k > 0:
             # pending_search (src/engine.rs:3310-3360): compute_distance_f32 against every un-flushed row, top-k, then
             # merge_row_results with the flushed hits
             n_p = self._pending_rows
@@ -422,30 +531,69 @@ class Collection:
                 allow = make_allow_bits(n_p, local)
             if any_allowed:
                 asc = M.is_ascending(self._metric)
-                prow, pd, pc = self._pending_store().search(q, min(search_k, n_p), self._metric, allow, pairwise=True)
-                for i in range(nq):
-                    c = int(pc[i])
-                    out[i] = _merge_row_results(out[i][0], out[i][1], prow[i, :c].astype(np.uint64) + np.uint64(n_store),
-                                                pd[i, :c].copy(), search_k, asc)
-        return out
+                pk = min(search_k, n_p)
+                if n_dead and pk > NATIVE_MAX_K:
+                    allow = self._live_mask(n_p, allow, first_row=n_store)
+                    pk = min(k, n_p)
+                prow, pd, pc = self._pending_store().search(q, pk, self._metric, allow, pairwise=True)
+                limit = max(search_k, rows.shape[1])
+                merged = [_merge_row_results(rows[i, :int(counts[i])], dists[i, :int(counts[i])],
+                                             prow[i, :int(pc[i])].astype(np.uint64) + np.uint64(n_store), pd[i, :int(pc[i])].copy(), limit, asc)
+                          for i in range(nq)]
+                width = max((len(m[0]) for m in merged), default=0)
+                rows = np.zeros((nq, width), np.uint64)
+                dists = np.zeros((nq, width), np.float32)
+                counts = np.zeros(nq, np.int64)
+                for i, (mr, md) in enumerate(merged):
+                    rows[i, :len(mr)], dists[i, :len(mr)], counts[i] = mr, md, len(mr)
+        return rows, dists, counts
 
-    def _finish(self, rows: np.ndarray, dists: np.ndarray, k: int, return_fields: bool) -> ResultView:
-        ids, keep = [], []
-        for j, r in enumerate(rows):                      # row_to_user_id + filter_tombstoned_limit
-            e = self._row_ids[int(r)]
-            if e in self._tombstones:
-                continue
-            ids.append(e)
-            keep.append(j)
-            if len(ids) == k:
-                break
-        d = dists[keep] if keep else np.empty(0, np.float32)
-        all_int = all(isinstance(i, (int, np.integer)) and not isinstance(i, bool) for i in ids)
-        id_arr = np.asarray(ids, dtype=np.int64) if all_int else np.asarray(ids, dtype=object)
-        flds = [dict(self._fields.get(int(rows[j]), {})) for j in keep] if return_fields else []
+    def _row_id_array(self) -> Optional[np.ndarray]:
+        """row -> external id as an int64 array while every id is an integer (else ``None``: ids are mapped one by one)."""
+        if not self._ids_all_int:
+            return None
+        if self._ids_np is None or len(self._ids_np) != len(self._row_ids):
+            self._ids_np = np.asarray(self._row_ids, dtype=np.int64)
+        return self._ids_np
+
+    def _finish_batch(self, rows: np.ndarray, dists: np.ndarray, counts: np.ndarray, k: int, return_fields: bool) -> List[ResultView]:
+        """row_to_user_id + filter_tombstoned_limit (src/engine.rs:3071-3073, :3286-3308) for a whole batch at once."""
+        nq, width = rows.shape
         idx_type, dist_name = M.parse_index_mode(self._index_mode or "FLAT-IP")
-        return ResultView(ids=id_arr, distances=np.asarray(d, dtype=np.float32), fields=flds, k=len(ids), distance=dist_name,
-                          index=idx_type, result_type="search")
+        valid = np.arange(width)[None, :] < counts[:, None]
+        if self._tombstones and width:
+            dead = self._dead_row_array()
+            pos = np.searchsorted(dead, rows)
+            pos[pos >= len(dead)] = max(len(dead) - 1, 0)
+            valid &= ~(dead[pos] == rows) if len(dead) else True
+        keep = valid & (np.cumsum(valid, axis=1) <= k)
+        n_keep = keep.sum(axis=1)
+        ids_np = self._row_id_array()
+        out: List[ResultView] = []
+        if ids_np is not None and bool((n_keep == np.minimum(counts, k)).all()) and bool(keep[:, :int(n_keep.max(initial=0))].all() if nq else True) \
+                and (nq == 0 or int(n_keep.min()) == int(n_keep.max())):
+            # the common case: nothing filtered, every query has the same number of hits -> two gathers for the batch
+            m = int(n_keep[0]) if nq else 0
+            id_block = ids_np[rows[:, :m].astype(np.int64)]
+            d_block = np.ascontiguousarray(dists[:, :m], dtype=np.float32)
+            for i in range(nq):
+                flds = [dict(self._fields.get(int(r), {})) for r in rows[i, :m]] if return_fields else []
+                out.append(ResultView(ids=id_block[i], distances=d_block[i], fields=flds, k=m, distance=dist_name, index=idx_type,
+                                      result_type="search"))
+            return out
+        for i in range(nq):
+            sel = np.nonzero(keep[i])[0]
+            r = rows[i, sel].astype(np.int64)
+            if ids_np is not None:
+                id_arr = ids_np[r]
+            else:
+                ids = [self._row_ids[int(x)] for x in r]
+                all_int = all(isinstance(x, (int, np.integer)) and not isinstance(x, bool) for x in ids)
+                id_arr = np.asarray(ids, dtype=np.int64) if all_int else np.asarray(ids, dtype=object)
+            flds = [dict(self._fields.get(int(x), {})) for x in r] if return_fields else []
+            out.append(ResultView(ids=id_arr, distances=np.asarray(dists[i, sel], dtype=np.float32), fields=flds, k=len(sel),
+                                  distance=dist_name, index=idx_type, result_type="search"))
+        return out
 
     def search(self, vector=None, k: int = 10, *, document=None, embed_func=None, where=None, return_fields: bool = False,
                vector_field: str = "default", reranker=None, rerank_k=None, rerank_with_fields: bool = False, nprobe: int = 10,
@@ -481,15 +629,16 @@ class Collection:
         if q.ndim == 1:
             q = q.reshape(1, -1)
         k = int(k)
+        nq = q.shape[0]
         with self._lock:
-            if self._dim is None or not self._row_ids:      # empty collection: empty result, not an error
-                return [self._finish(np.empty(0, np.uint64), np.empty(0, np.float32), k, return_fields) for _ in range(q.shape[0])]
+            if self._dim is None or not self._row_ids or k <= 0:      # empty collection / k = 0: empty result, not an error
+                empty = (np.empty((nq, 0), np.uint64), np.empty((nq, 0), np.float32), np.zeros(nq, np.int64))
+                return self._finish_batch(*empty, max(k, 0), return_fields)
             if q.shape[1] != self._dim:
                 raise ValueError(f"Dimension mismatch: expected {self._dim}, got {q.shape[1]}")
             subset = self._subset_rows(where, filter_ids)
-            search_k = k + len(self._tombstones)             # engine.rs:4735-4741
-            per_query = self._search_rows(q, search_k, int(nprobe), subset, single, k=k)
-            return [self._finish(r, d, k, return_fields) for (r, d) in per_query]
+            rows, dists, counts = self._search_rows(q, k, int(nprobe), subset, single)
+            return self._finish_batch(rows, dists, counts, k, return_fields)
 
     def __repr__(self) -> str:
         return f"Collection(name={self.name!r}, shape={self.shape}, index_mode={self._index_mode!r})"
@@ -531,6 +680,80 @@ def _merge_row_results(l_rows, l_d, r_rows, r_d, limit: int, ascending: bool):
     return np.asarray([p[0] for p in pairs], np.uint64), np.asarray([p[1] for p in pairs], np.float32)
 
 
+class InsertSession:
+    """The reference's ``DataInsertionSession``: buffers ``add`` calls, applies them and commits on exit."""
+
+    def __init__(self, coll: Collection):
+        self.db = coll
+        self._adds: List[tuple] = []
+
+    def __enter__(self):
+        return self
+
+    def __getattr__(self, name):
+        return getattr(self.db, name)
+
+    def add(self, ids=None, *, vectors=None, documents=None, embed_func=None, fields=None, batch_size: int = 1000, wire_dtype: str = "float32"):
+        if documents is not None or embed_func is not None:
+            raise NotImplementedError("document embedding is outside this package's scope; pass vectors")
+        self._adds.append((ids, vectors, fields, batch_size))
+
+    def commit(self) -> None:
+        for ids, vectors, fields, batch_size in self._adds:
+            self.db.add(ids, vectors=vectors, fields=fields, batch_size=batch_size)
+        self._adds.clear()
+        self.db.commit()
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.commit()
+        return False
+
+
+_WHERE_TERM = None
+
+
+def _compile_where(expr: str) -> Callable[[dict], bool]:
+    """The conjunctive subset of the reference's SQL ``where`` strings that needs no metadata engine:
+    ``"field" <op> literal [AND ...]`` with ``= == != <> < <= > >=``, numeric or quoted-string literals.  Anything else
+    (OR, functions, LIKE, ...) belongs to the reference's SQL engine and raises ``NotImplementedError``."""
+    import re
+
+    global _WHERE_TERM
+    if _WHERE_TERM is None:
+        _WHERE_TERM = re.compile(r"""^\s*(?:"([^"]+)"|([A-Za-z_][A-Za-z_0-9]*))\s*(==|=|!=|<>|<=|>=|<|>)\s*(?:'([^']*)'|(-?\d+(?:\.\d+)?(?:[eE][-+]?\d+)?)|(true|false))\s*$""", re.I)
+    import operator
+
+    ops = {"=": operator.eq, "==": operator.eq, "!=": operator.ne, "<>": operator.ne, "<": operator.lt, "<=": operator.le,
+           ">": operator.gt, ">=": operator.ge}
+    terms = []
+    for part in re.split(r"\s+AND\s+", expr.strip(), flags=re.I):
+        m = _WHERE_TERM.match(part)
+        if not m:
+            raise NotImplementedError(f"where expression {expr!r} needs the reference's SQL metadata engine; pass a callable or a dict")
+        name = m.group(1) or m.group(2)
+        if m.group(4) is not None:
+            lit: Any = m.group(4)
+        elif m.group(5) is not None:
+            lit = float(m.group(5)) if any(c in m.group(5) for c in ".eE") else int(m.group(5))
+        else:
+            lit = m.group(6).lower() == "true"
+        terms.append((name, ops[m.group(3)], lit))
+
+    def pred(fields: dict) -> bool:
+        for name, op, lit in terms:
+            if name not in fields or fields[name] is None:
+                return False
+            try:
+                if not op(fields[name], lit):
+                    return False
+            except TypeError:
+                return False
+        return True
+
+    return pred
+
+
 class Database:
     """``LocalClient``: the collections of one database."""
 
@@ -550,7 +773,7 @@ class Database:
             self.drop_collection(collection)
         if collection not in self._colls:
             self._colls[collection] = Collection(collection, dim, dtypes=dtypes, default_index=default_index,
-                                                 description=description, device=self._manager._device)
+                                                 description=description, device=self._manager._device, devices=self._manager._devices)
         coll = self._colls[collection]
         if dim is not None and coll._dim is not None and int(dim) != coll._dim:
             raise ValueError(f"collection {collection!r} has dimension {coll._dim}, not {dim}")
@@ -584,9 +807,12 @@ class Database:
 
 
 class VectorDBClient:
-    """``VectorDBClient(uri=None)``: local, in-memory databases whose vectors live on one B200 (``device``)."""
+    """``VectorDBClient(uri=None)``: local, in-memory databases whose vectors live in the HBM of this process's B200s.
+    ``devices`` (or ``LYNSE_B200_DEVICES=0,1,...``) names the GPUs a collection's segments are spread over; the default is
+    ``device`` alone."""
 
-    def __init__(self, uri: Union[str, None] = None, api_key: Optional[str] = None, read_only: bool = False, device: int = 0):
+    def __init__(self, uri: Union[str, None] = None, api_key: Optional[str] = None, read_only: bool = False, device: int = 0,
+                 devices: Optional[Sequence[int]] = None):
         del api_key
         if uri is not None and str(uri).startswith(("http://", "https://")):
             raise NotImplementedError("the HTTP client is outside this package's scope")
@@ -594,6 +820,11 @@ class VectorDBClient:
             raise NotImplementedError("read_only opens persisted storage, which is outside this package's scope")
         self._uri = None if uri is None else str(uri)
         self._device = int(device)
+        import os
+
+        if devices is None and os.environ.get("LYNSE_B200_DEVICES", "").strip():
+            devices = visible_devices()
+        self._devices = [int(d) for d in devices] if devices else [self._device]
         self._dbs: Dict[str, Dict[str, Collection]] = {}
 
     def create_database(self, database_name: str, drop_if_exists: bool = False) -> Database:

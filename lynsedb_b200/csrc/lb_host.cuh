@@ -180,6 +180,7 @@ struct lb_index {
     uint64_t n = 0;
     std::vector<uint64_t> segments;
     uint64_t seg_target = 256ull * 1024 * 1024;
+    bool force_new_segment = false;  // the next append opens a segment even if it would fit the last one (lb_index_new_segment)
     // side structures (derived caches, extended incrementally after appends)
     DevBuf packed;
     uint64_t packed_rows = 0;

@@ -1029,6 +1029,7 @@ struct FinArgs {
 // with shuffles.  The row comes from `rowbuf` (shared memory, filled with coalesced loads by the same warp), 256
 // columns at a time.  lanes: lane & 7 = AVX lane, lane >> 3 = which of the warp's four rows.
 constexpr int FIN_COLS = 256;   // columns staged per round
+constexpr int FIN_STRIDE = FIN_COLS + 8;  // row pitch of the staging buffer: the four rows of a warp land in different banks
 __device__ __forceinline__ float hsum8_shfl(float a) {   // simd.rs:1427-1436 over the 8 threads of a row
     a = a + __shfl_xor_sync(0xffffffffu, a, 4);           // s[i] = acc[i] + acc[i+4]
     a = a + __shfl_xor_sync(0xffffffffu, a, 1);           // t0 = s0 + s1, t2 = s2 + s3
@@ -1180,7 +1181,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     if (vec) {
         // eight threads per row, four rows per warp, blockDim/8 rows per pass of the block (rows are independent:
         // warp-local syncs only)
-        float* rowbuf = sq + ((dim + 3) & ~3) + (tid >> 3) * FIN_COLS;
+        float* rowbuf = sq + ((dim + 3) & ~3) + (tid >> 3) * FIN_STRIDE;
         const int lane = tid & 31;
         const int rows_per_pass = (int)(blockDim.x >> 3);
         for (int base = 0; base < a.R; base += rows_per_pass) {

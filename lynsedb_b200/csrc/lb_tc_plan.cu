@@ -579,7 +579,7 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
     f.out_dists = d_dists;
     f.out_counts = d_counts;
     const int fin_threads = nq <= 64 ? 1024 : 256;  // few queries: few blocks, so each gets 1024 threads
-    size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)(fin_threads / 8) * tc::FIN_COLS * 4;  // + row buffers
+    size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)(fin_threads / 8) * tc::FIN_STRIDE * 4;  // + row buffers
     if (metric_ascending(metric)) {
         LB_CUDA_TRY(ensure_dynamic_smem(tc::finalize_kernel<true>, (int)fsmem));
         tc::finalize_kernel<true><<<nq, fin_threads, fsmem, idx->stream>>>(f);

@@ -44,7 +44,9 @@ namespace lb {
 static void account_segment(lb_index* idx, uint64_t n_new) {
     uint64_t bytes = n_new * row_bytes(idx);
     uint64_t target = std::max<uint64_t>(idx->seg_target, row_bytes(idx));
-    if (!idx->segments.empty() && idx->segments.back() * row_bytes(idx) + bytes <= target)
+    const bool forced = idx->force_new_segment;
+    idx->force_new_segment = false;
+    if (!forced && !idx->segments.empty() && idx->segments.back() * row_bytes(idx) + bytes <= target)
         idx->segments.back() += n_new;
     else
         idx->segments.push_back(n_new);
@@ -119,6 +121,27 @@ static int ensure_mass_stats(lb_index* idx) {
 // d_queries: f32 [nq][dim] (LB_F32 index) or u64 [nq][n_words] (LB_PACKED_U64 index); results [nq][k], k <= n.
 enum { SCORE_FLAT = 0, SCORE_PAIRWISE = 1, SCORE_F16_ROWS = 2 };
 
+// A tensor-core pass keeps floor(clusters / query groups) slots of one cluster per query group busy; when the number of
+// query groups (256 queries each) divides the 74 cluster slots badly — 16 groups: 64 of 74 — the batch is cut in equal
+// sub-batches that divide them better (2 x 8 groups: 72 of 74), each streaming the corpus once.
+static int tc_query_split(const lb_index* idx, int nq) {
+    const int groups = (nq + 255) / 256, clusters = idx->sm_count / 2;
+    if (groups <= 4 || tc_env_int("LYNSE_B200_TC_SPLIT", 1) == 0) return 1;
+    int best = 1;
+    double best_util = 0.0;
+    for (int s = 1; s <= 4; ++s) {
+        const int g = (groups + s - 1) / s;
+        if (g > clusters) continue;
+        // sub-batches of g groups: clusters / g slots of g clusters; the last sub-batch may be smaller
+        const double util = (double)(clusters / g * g) / clusters * ((double)groups / (double)(g * s));
+        if (util > best_util * 1.03) {
+            best_util = util;
+            best = s;
+        }
+    }
+    return best;
+}
+
 // defer_tc_check: a tensor-core plan leaves its certification flags unread (the caller runs tc_finish after whatever
 // it enqueues behind the search); implies no synchronisation here.
 static int search_device_impl(lb_index* idx, int metric, const void* d_queries, int nq, int k, const uint64_t* d_allow,
@@ -154,7 +177,24 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
             // a large batch: the popcounts are a {0,1} contraction on the tensor cores (exact: integer accumulators),
             // shortlist -> exact counts on the packed rows -> certified, as for the dense metrics
             idx->stats.kernels_launched = kernels;
-            LB_TRY(run_tc_bits(idx, metric, words, nw, qwords, nq, k, d_rows, d_dists, d_counts, d_allow, defer_tc_check));
+            const int split = tc_query_split(idx, nq);
+            if (split == 1) {
+                LB_TRY(run_tc_bits(idx, metric, words, nw, qwords, nq, k, d_rows, d_dists, d_counts, d_allow, defer_tc_check));
+            } else {
+                const int per = ((nq + split - 1) / split + 255) / 256 * 256;
+                uint32_t fallbacks = 0;
+                float ms_sum = 0;
+                for (int q0 = 0; q0 < nq; q0 += per) {
+                    const int nqs = std::min(per, nq - q0);
+                    LB_TRY(run_tc_bits(idx, metric, words, nw, qwords + (size_t)q0 * nw, nqs, k, d_rows + (size_t)q0 * k, d_dists + (size_t)q0 * k,
+                                       d_counts + q0, d_allow, false));
+                    fallbacks += idx->stats.n_fallback;
+                    ms_sum += idx->stats.ms_dominant;
+                }
+                idx->stats.n_fallback = fallbacks;
+                idx->stats.ms_dominant = ms_sum;
+                idx->stats.algorithmic_flops = 2ull * (uint64_t)nq * idx->n * (uint64_t)nw * 64;
+            }
             kernels = idx->stats.kernels_launched;
             ms_dom = idx->stats.ms_dominant;
         } else {
@@ -181,7 +221,24 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
                // a handful of queries over a small corpus is a latency case: the exact scan is two launches, the tensor
                // plan three plus a lazily built shadow (100k x 128, one query: 85 against 131 us of device time)
                !(nq <= 4 && (uint64_t)idx->n * idx->dim * 4 < (256ull << 20))) {
-        LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr, d_allow, defer_tc_check));
+        const int split = tc_query_split(idx, nq);
+        if (split == 1) {
+            LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr, d_allow, defer_tc_check));
+        } else {
+            const int per = ((nq + split - 1) / split + 255) / 256 * 256;
+            uint32_t fallbacks = 0;
+            float ms_sum = 0;
+            for (int q0 = 0; q0 < nq; q0 += per) {
+                const int nqs = std::min(per, nq - q0);
+                LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries) + (size_t)q0 * idx->dim, nqs, k, d_rows + (size_t)q0 * k,
+                              d_dists + (size_t)q0 * k, d_counts + q0, nullptr, d_allow, false));
+                fallbacks += idx->stats.n_fallback;
+                ms_sum += idx->stats.ms_dominant;
+            }
+            idx->stats.n_fallback = fallbacks;
+            idx->stats.ms_dominant = ms_sum;
+            idx->stats.algorithmic_flops = 2ull * (uint64_t)nq * idx->n * idx->dim;
+        }
         kernels = idx->stats.kernels_launched;
         ms_dom = idx->stats.ms_dominant;
     } else {
@@ -372,6 +429,13 @@ int lb_index_reserve(lb_index* idx, uint64_t n_rows) {
     DeviceGuard g(idx->device);
     if (n_rows >= 0xFFFFFFFFull) return fail(LB_INVALID_ARGUMENT, "an index holds fewer than 2^32-1 rows");
     return grow_rows(idx, n_rows);
+}
+
+int lb_index_new_segment(lb_index* idx) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->force_new_segment = true;
+    return LB_OK;
 }
 
 int lb_index_set_segment_target(lb_index* idx, uint64_t bytes) {
@@ -574,6 +638,8 @@ static int search_host_common(lb_index* idx, int score_mode, int metric, const v
         acc.ms_total += idx->stats.ms_total;
         acc.algorithmic_bytes += idx->stats.algorithmic_bytes;
         acc.algorithmic_flops += idx->stats.algorithmic_flops;
+        acc.coarse_operand = idx->stats.coarse_operand;
+        acc.coarse_hit_mode = idx->stats.coarse_hit_mode;
     }
     idx->stats = acc;
     return LB_OK;

@@ -118,8 +118,10 @@ def test_filters_by_fields_and_ids(fake):
     assert list(coll.search([0, 0], k=3, where=lambda f: f.get("g") == 0, filter_ids=[2, 4, 6, 7]).ids) == [2, 4, 6]
     r = coll.search([0, 0], k=2, where={"g": 1}, return_fields=True)
     assert r.fields == [{"g": 1}, {"g": 1}]
+    assert list(coll.search([0, 0], k=3, where='"g" = 1').ids) == [1, 3, 5]          # the conjunctive subset of the SQL strings
+    assert list(coll.search([0, 0], k=3, where="g = 0 AND g <> 1").ids) == [0, 2, 4]
     with pytest.raises(NotImplementedError):
-        coll.search([0, 0], k=1, where="g = 1")
+        coll.search([0, 0], k=1, where="g = 1 OR g = 0")
 
 
 def test_build_index_validation(fake):
@@ -133,8 +135,12 @@ def test_build_index_validation(fake):
         coll.build_index("FLAT-HAVERSINE")
     with pytest.raises(ValueError, match="unsupported index/metric combination"):
         coll.build_index("IVF-WASSERSTEIN")
+    with pytest.raises(ValueError, match="unsupported index/metric combination"):
+        coll.build_index("HNSW-CANBERRA")                  # graph indexes only exist for the domain-free metrics
     with pytest.raises(ValueError, match="outside this package"):
-        coll.build_index("HNSW-IP")
+        coll.build_index("FLAT-IP-SQ8")
+    coll.build_index("HNSW-IP")                            # accepted: served by the exact scan, reported as HNSW
+    assert M.parse_index_mode(coll.index_mode) == ("HNSW", "IP")
     coll.build_index("FLAT-COS", n_clusters=4)              # FLAT ignores the shared kwargs
     assert coll.index_mode == "FLAT-COS"
     assert M.parse_index_mode(coll.index_mode) == ("Flat", "Cosine")

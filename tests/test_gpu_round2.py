@@ -1,0 +1,398 @@
+"""GPU parity tests added in round 2: the certification bound under aligned rounding errors, the BASELINE.json
+shapes, the shard merge kernel, the Haversine FLAT scan and the binary metrics on the tensor cores."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EXACT_BITS = ["ip", "l2", "cosine", "hamming", "jaccard", "tanimoto", "dice"]
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lynsedb_b200
+
+    return lynsedb_b200
+
+
+def _data(n, dim, seed, positive=True):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, dim), dtype=np.float32)
+    return x if positive else (x - 0.5).astype(np.float32)
+
+
+def _same(oracle_out, gpu_out, exact_scores=True, rel=1e-5):
+    o_ids, o_d, o_c = oracle_out
+    rows, dists, counts = gpu_out
+    assert np.array_equal(o_c, counts)
+    assert np.array_equal(o_ids.astype(np.uint32), rows), "ids differ from the oracle"
+    if exact_scores:
+        assert np.array_equal(o_d.view(np.uint32), dists.view(np.uint32)), "scores are not bit-identical to the oracle's"
+    else:
+        np.testing.assert_allclose(dists, o_d, rtol=rel, atol=1e-7)
+
+
+# ---- the certification bound under the worst alignment of rounding errors --------------------------------------------
+def test_bf16_certification_survives_aligned_rounding_errors(L, oracle, monkeypatch):
+    """Every element of the queries and of the true best rows sits just below a bf16 midpoint, so both operands round
+    DOWN by a whole 2^-8 and the errors add up: the coarse scores of the best rows are ~2 * 2^-8 low (0.50 at |q||c| = 64)
+    and they are dropped behind rows whose elements are exact in bf16.  The bound must see that (a one-operand bound of
+    2^-8 |q||c| = 0.25 would certify the wrong rows): the queries fall back to the exact scan and the ids are the
+    oracle's."""
+    monkeypatch.setenv("LYNSE_B200_TC_OPERAND", "bf16")
+    dim, n, k = 64, 30_000, 10
+    low = np.float32(1.0 + 2.0 ** -8 - 2.0 ** -20)     # rounds to 1.0 in bf16, true value 1.0039
+    step = np.float32(1.0 + 2.0 ** -7)                 # exact in bf16
+    corpus = np.ones((n, dim), dtype=np.float32)
+    corpus[:, :4] = step                               # filler: coarse 64.031, exact 64.281
+    corpus[:k, :10] = step                             # decoys: coarse 64.078, exact 64.328 (they fill the top of the shortlists)
+    corpus[-20:, :] = low                              # the true best rows: coarse 64.000, exact 64.501
+    queries = np.full((5, dim), low, dtype=np.float32)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "ip")
+        st = idx.last_stats()
+    assert st["plan_used"] == 1 and st["coarse_operand"] == 0, st
+    assert st["n_fallback"] == 5, f"the aligned-rounding shortlists must not be certified: {st}"
+    want = oracle.store_batch_search(corpus, queries, k, "ip", n_threads=1)
+    _same(want, got)
+    assert np.array_equal(got[0][0], np.arange(n - 20, n - 10, dtype=np.uint32))   # the first ten of the true best rows
+
+
+def test_u8_certification_survives_aligned_quantisation_errors(L, oracle, monkeypatch):
+    """The same attack on the 8-bit operands: elements just below the midpoint of two quantisation levels."""
+    monkeypatch.setenv("LYNSE_B200_TC_OPERAND", "u8")
+    dim, n, k = 64, 30_000, 10
+    lvl = np.float32(1.0 / 255.0)                      # corpus range [0, 1] -> one level = 1/255
+    exact_hi = np.float32(200.0) * lvl                 # on a level
+    low = np.float32(200.49) * lvl                     # rounds down to level 200, true value half a level higher
+    corpus = np.full((n, dim), exact_hi, dtype=np.float32)
+    corpus[0, 0], corpus[1, 0] = 0.0, 1.0              # pins the quantisation range to [0, 1]
+    corpus[:, 1:3] = np.float32(201.0) * lvl           # filler: two levels up in two columns
+    corpus[2:2 + k, 1:6] = np.float32(201.0) * lvl     # decoys
+    corpus[-20:, :] = low                              # the true best rows
+    queries = np.full((5, dim), low, dtype=np.float32)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "ip")
+        st = idx.last_stats()
+    assert st["plan_used"] == 1 and st["coarse_operand"] == 1, st
+    want = oracle.store_batch_search(corpus, queries, k, "ip", n_threads=1)
+    _same(want, got)
+    assert st["n_fallback"] == 5, f"the aligned-quantisation shortlists must not be certified: {st}"
+
+
+@pytest.mark.parametrize("operand", ["bf16", "u8"])
+@pytest.mark.parametrize("metric", ["ip", "cosine"])
+def test_both_operand_kinds_match_the_oracle(L, oracle, monkeypatch, operand, metric):
+    monkeypatch.setenv("LYNSE_B200_TC_OPERAND", operand)
+    n, dim, nq, k = 60_000, 200, 300, 10
+    corpus, queries = _data(n, dim, 501, positive=(metric == "ip")), _data(nq, dim, 502, positive=(metric == "ip"))
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, metric)
+        st = idx.last_stats()
+    assert st["plan_used"] == 1 and st["coarse_operand"] == (1 if operand == "u8" else 0), st
+    # one thread: with several, the reference's chunk boundaries decide which rows take the batch-8 inner-product kernel
+    _same(oracle.store_batch_search(corpus, queries, k, metric, n_threads=1), got)
+
+
+def test_heavy_tailed_rows_switch_the_shadow_to_bf16(L, oracle):
+    """One zero point and scale for the whole corpus is too coarse when a few elements are far out: the measured
+    quantisation error exceeds twice the bf16 one and the shadow is rebuilt with bf16 operands."""
+    n, dim, nq, k = 40_000, 128, 200, 10
+    rng = np.random.default_rng(77)
+    corpus = rng.standard_normal((n, dim)).astype(np.float32)
+    corpus[rng.integers(0, n, 40), rng.integers(0, dim, 40)] = 60.0
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "ip")
+        st = idx.last_stats()
+    assert st["plan_used"] == 1 and st["coarse_operand"] == 0, st
+    want = oracle.store_batch_search(corpus, queries, k, "ip", n_threads=oracle.host_threads())
+    assert np.array_equal(want[0].astype(np.uint32), got[0])
+
+
+def test_non_finite_rows_keep_the_exact_plan(L, oracle):
+    n, dim = 20_000, 64
+    corpus, queries = _data(n, dim, 601), _data(200, dim, 602)
+    corpus[1234, 5] = np.inf
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, 10, "l2")
+        st = idx.last_stats()
+    assert st["plan_used"] == 0, st
+    _same(oracle.store_batch_search(corpus, queries, 10, "l2", n_threads=oracle.host_threads()), got)
+
+
+# ---- BASELINE.json shapes ---------------------------------------------------------------------------------------------
+def test_baseline_c1_flat_ip_100k_x_128(L, oracle):
+    """configs[0], exactly: FLAT-IP, 100k x 128 f32, 1000 queries, k = 10, data as benchmarks/flat_search_bench.py:49-79
+    (default_rng(42), U[0,1), row 0 := query 0); ids, order and scores bit-identical to the reference's CPU path."""
+    rng = np.random.default_rng(42)
+    corpus = rng.random((100_000, 128), dtype=np.float32)
+    queries = rng.random((1000, 128), dtype=np.float32)
+    corpus[0] = queries[0]
+    with L.DeviceIndex(128) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, 10, "ip")
+        st = idx.last_stats()
+    assert st["plan_used"] == 1
+    _same(oracle.store_batch_search(corpus, queries, 10, "ip", n_threads=1), got)
+    assert got[0][0, 0] == 0
+
+
+def test_baseline_c3_flat_l2_2m_x_128_k100(L, oracle):
+    """configs[2] at 2M rows (what the oracle scans in seconds): FLAT-L2, 128 dims, k = 100, hit mode + seeded floors."""
+    from lynsedb_b200 import synthetic
+
+    n, dim, nq, k = 2_000_000, 128, 256, 100
+    queries = synthetic.rows_f32(43, np.arange(nq), dim)
+    with L.DeviceIndex(dim) as idx:
+        for lo in range(0, n, 100_000):
+            idx.append_synthetic(100_000, 42, lo)
+        rows, dists, counts = idx.search(queries, k, "l2")
+        st = idx.last_stats()
+        corpus = idx.read_rows(0, n)
+    assert st["plan_used"] == 1 and st["coarse_hit_mode"] == 1, st
+    want = oracle.store_batch_search(corpus, queries, k, "l2", segment_rows=[100_000] * 20, n_threads=oracle.host_threads())
+    _same(want, (rows, dists, counts))
+
+
+@pytest.mark.parametrize("metric", ["hamming", "tanimoto", "dice"])
+def test_baseline_c4_packed_2m_x_1024_bits_q512(L, oracle, metric):
+    """configs[3] at 2M fingerprints, 512 queries (four query tiles -> the CTA-pair kernel, {0,1} bytes on tcgen05
+    kind::i8), k = 32: ids, order and distances bit-identical to packed_binary_search."""
+    from lynsedb_b200 import synthetic
+
+    n, nq, k = 2_000_000, 512, 32
+    q = synthetic.rows_packed(43, np.arange(nq), 16)
+    q[0] = synthetic.rows_packed(42, np.arange(1), 16)[0]
+    with L.DeviceIndex(1024, "packed") as idx:
+        idx.append_synthetic(n, 42, 0)
+        rows, dists, counts = idx.search(q, k, metric)
+        st = idx.last_stats()
+    assert st["plan_used"] == 3, st
+    data = synthetic.rows_packed(42, np.arange(n), 16)
+    _same(oracle.packed_batch_search(data, q, k, metric, n_threads=oracle.host_threads()), (rows, dists, counts))
+    assert rows[0, 0] == 0 and dists[0, 0] == 0.0
+
+
+@pytest.mark.parametrize("metric", ["hamming", "jaccard"])
+@pytest.mark.parametrize("words,n,nq,k", [(3, 70_001, 130, 10), (16, 65_536, 40, 32), (24, 50_000, 300, 64), (1, 9_000, 64, 5)])
+def test_binary_metrics_on_the_tensor_cores_with_ties_and_ragged_widths(L, oracle, metric, words, n, nq, k):
+    """Few distinct fingerprints (heavy ties), widths that leave zero-padded K steps, one- and two-CTA kernels, list and hit
+    modes; a tie at the shortlist boundary may not be certified and must then come from the exact scan."""
+    rng = np.random.default_rng(words * 1000 + n)
+    base = rng.integers(0, 2 ** 63, size=(97, words), dtype=np.uint64)
+    corpus = np.ascontiguousarray(base[rng.integers(0, 97, n)] ^ (rng.integers(0, 2 ** 63, size=(n, words), dtype=np.uint64) &
+                                                                 rng.integers(0, 2 ** 63, size=(n, words), dtype=np.uint64) &
+                                                                 rng.integers(0, 2 ** 63, size=(n, words), dtype=np.uint64)))
+    queries = np.ascontiguousarray(base[rng.integers(0, 97, nq)])
+    with L.DeviceIndex(words * 64, "packed") as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, metric)
+        st = idx.last_stats()
+    assert st["plan_used"] == 3, st
+    _same(oracle.packed_batch_search(corpus, queries, k, metric, n_threads=oracle.host_threads()), got)
+
+
+def test_binary_metrics_of_an_f32_collection_use_the_packed_cache_on_the_tensor_cores(L, oracle):
+    n, dim, nq, k = 50_000, 130, 200, 10      # the reference's own pin uses dim = 130: three words, ragged tail
+    corpus, queries = _data(n, dim, 701), _data(nq, dim, 702)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "tanimoto")
+        st = idx.last_stats()
+    assert st["plan_used"] == 3, st
+    _same(oracle.store_batch_search(corpus, queries, k, "tanimoto", n_threads=oracle.host_threads()), got)
+
+
+# ---- Haversine FLAT scan ------------------------------------------------------------------------------------------------
+def test_flat_haversine_scan_with_invalid_latitudes(L, oracle):
+    """simd.rs:603-628: [lon, lat] in degrees, metres out, |lat| > 90 or a non-finite coordinate -> +inf (ranked last)."""
+    rng = np.random.default_rng(11)
+    n, nq, k = 50_000, 7, 20
+    corpus = np.stack([rng.uniform(-180, 180, n), rng.uniform(-90, 90, n)], axis=1).astype(np.float32)
+    corpus[::97, 1] = 95.0          # invalid latitude
+    corpus[5::1013, 0] = np.nan     # non-finite longitude
+    queries = np.stack([rng.uniform(-180, 180, nq), rng.uniform(-90, 90, nq)], axis=1).astype(np.float32)
+    queries[3] = [10.0, 91.0]       # an invalid query: every distance is +inf, rows in ascending order
+    with L.DeviceIndex(2) as idx:
+        idx.append(corpus)
+        rows, dists, counts = idx.search(queries, k, "haversine")
+    o_ids, o_d, o_c = oracle.store_batch_search(corpus, queries, k, "haversine", n_threads=1)
+    assert np.array_equal(counts, o_c)
+    assert np.array_equal(rows, o_ids.astype(np.uint32))
+    fin = np.isfinite(o_d)
+    assert np.array_equal(np.isfinite(dists), fin)
+    np.testing.assert_allclose(dists[fin], o_d[fin], rtol=1e-5)
+    assert np.all(np.isinf(dists[3])) and np.array_equal(rows[3], np.arange(k, dtype=np.uint32))
+    with L.DeviceIndex(2) as idx:   # a corpus of invalid rows only
+        idx.append(np.tile(np.float32([0.0, 120.0]), (5000, 1)))
+        rows, dists, counts = idx.search(queries[:2], 5, "haversine")
+    assert np.all(np.isinf(dists)) and np.array_equal(rows[0], np.arange(5, dtype=np.uint32))
+
+
+# ---- the shard merge kernel against the reference's segment merge ----------------------------------------------------------
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+@pytest.mark.parametrize("n_shards,k", [(2, 10), (8, 10), (5, 100), (3, 1)])
+def test_merge_shards_kernel_matches_the_store_merge(L, oracle, metric, n_shards, k):
+    """merge_shards_kernel (what every rank runs after the all-gather) on host-supplied blocks against
+    VectorStore::merge_results (vector_store.rs:953-970) = the oracle's store search over the same segments; small-integer
+    data, so equal scores straddle the shard boundaries and the (score, global row) rule decides."""
+    from lynsedb_b200 import _native as N
+    from lynsedb_b200 import metrics as M
+
+    rng = np.random.default_rng(1000 + n_shards)
+    dim, nq = 8, 33
+    sizes = [int(x) for x in rng.integers(max(k, 40), 400, n_shards)]
+    sizes[-1] = max(k, 7)                                     # a short last shard
+    n = sum(sizes)
+    corpus = rng.integers(0, 3, (n, dim)).astype(np.float32)
+    queries = rng.integers(0, 3, (nq, dim)).astype(np.float32)
+    rows = np.zeros((n_shards, nq, k), np.uint32)
+    dists = np.zeros((n_shards, nq, k), np.float32)
+    counts = np.zeros((n_shards, nq), np.uint32)
+    bases = np.zeros(n_shards, np.uint64)
+    pos = 0
+    for s, m in enumerate(sizes):
+        ids, d, c = oracle.store_batch_search(corpus[pos:pos + m], queries, k, metric, n_threads=1)
+        rows[s], dists[s], counts[s], bases[s] = ids.astype(np.uint32), d, c, pos
+        pos += m
+    out_r = np.zeros((nq, k), np.uint64)
+    out_d = np.zeros((nq, k), np.float32)
+    out_c = np.zeros(nq, np.uint32)
+    N.check(N.lib().lb_merge_shard_blocks(0, M.require(metric), n_shards, nq, k, N.u32ptr(rows), N.fptr(dists), N.u32ptr(counts),
+                                          N.u64ptr(bases), N.u64ptr(out_r), N.fptr(out_d), N.u32ptr(out_c)))
+    w_ids, w_d, w_c = oracle.store_batch_search(corpus, queries, k, metric, segment_rows=sizes, n_threads=1)
+    assert np.array_equal(out_c, w_c)
+    assert np.array_equal(out_r, w_ids.astype(np.uint64))
+    assert np.array_equal(out_d.view(np.uint32), w_d.view(np.uint32))
+    # and the host statement of the same merge (lynsedb_b200.sharding), which the gloo test uses
+    from lynsedb_b200.sharding import merge_shard_blocks
+
+    h_r, h_d, h_c = merge_shard_blocks(list(rows), list(dists), list(counts), [int(b) for b in bases], k, metric != "ip")
+    assert np.array_equal(h_r, out_r) and np.array_equal(h_c, out_c)
+
+
+def test_single_rank_sharded_search_with_a_row_filter(L, oracle):
+    """lb_sharded_search_filtered with no communicator: the allow-bitset reaches the shard's search (it used to be
+    dropped), rows come back rebased by the shard's row base."""
+    from lynsedb_b200 import _native as N
+    from lynsedb_b200 import metrics as M
+
+    n, dim, nq, k, base = 50_000, 96, 200, 10, 1_000_000
+    corpus, queries = _data(n, dim, 801), _data(nq, dim, 802)
+    rng = np.random.default_rng(803)
+    allowed = rng.random(n) < 0.5
+    bits = np.zeros((n + 63) // 64, np.uint64)
+    idxs = np.nonzero(allowed)[0]
+    np.bitwise_or.at(bits, idxs // 64, np.uint64(1) << (idxs % 64).astype(np.uint64))
+    out_r = np.zeros((nq, k), np.uint64)
+    out_d = np.zeros((nq, k), np.float32)
+    out_c = np.zeros(nq, np.uint32)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        N.check(N.lib().lb_sharded_search_filtered(None, idx._h, M.require("ip"), N.fptr(queries), nq, k, base, N.u64ptr(bits), len(bits),
+                                                   N.u64ptr(out_r), N.fptr(out_d), N.u32ptr(out_c)))
+    sub = corpus[allowed]
+    w_ids, w_d, w_c = oracle.store_batch_search(sub, queries, k, "ip", n_threads=1)
+    assert np.array_equal(out_c, w_c)
+    assert np.array_equal(out_r, idxs[w_ids.astype(np.int64)].astype(np.uint64) + np.uint64(base))
+
+
+# ---- the collection object: round-1 advisor findings + several devices -----------------------------------------------------
+def test_ivf_collection_survives_add_search_commit_search(L):
+    """An IVF index built before a flush must not outlive it: add -> search (lazy IVF over the flushed rows) -> commit
+    (the store grows) -> search used to fail with 'the index changed since the IVF lists were built'."""
+    rng = np.random.default_rng(31)
+    data = rng.random((3000, 32), dtype=np.float32)
+    more = rng.random((700, 32), dtype=np.float32)
+    with L.VectorDBClient() as client:
+        coll = client.create_collection("db", "ivf", dim=32, default_index=None)
+        coll.add(vectors=data)
+        coll.build_index("IVF-L2", n_clusters=16, nprobe=16)
+        coll.add(vectors=more)                              # stays pending
+        first = coll.search(more[3], k=5, nprobe=16)
+        assert first.ids[0] == 3003
+        coll.commit()
+        again = coll.search(more[3], k=5, nprobe=16)        # lists rebuilt over 3700 rows
+        assert again.ids.tolist() == first.ids.tolist()
+        assert coll.search(data[9], k=1, nprobe=16).ids[0] == 9
+
+
+def test_thousands_of_deleted_rows_do_not_hit_the_native_k_limit(L, oracle):
+    """k + |tombstones| > 2048 on every path that over-fetched: flushed FLAT rows at k > 256, pending rows, IVF, search_range."""
+    rng = np.random.default_rng(32)
+    n, dim, k = 20_000, 32, 300
+    data = rng.random((n, dim), dtype=np.float32)
+    pend = rng.random((4000, dim), dtype=np.float32)
+    q = rng.random((3, dim), dtype=np.float32)
+    with L.VectorDBClient() as client:
+        coll = client.create_collection("db", "c", dim=dim, default_index="FLAT-L2")
+        coll.add(vectors=data, batch_size=10_000)
+        coll.commit()
+        coll.add(vectors=pend, batch_size=4000)             # 4000 pending rows
+        allv = np.concatenate([data, pend])
+        o_ids, o_d, _ = oracle.store_batch_search(allv, q, 2048, "l2", n_threads=oracle.host_threads())
+        dead = sorted({int(x) for x in o_ids[:, ::2].ravel()} | set(range(n, n + 3000, 1)))     # every other hit + 3000 pending rows
+        assert len(dead) + k > 2048
+        coll.delete(dead)
+        dead_set = set(dead)
+        res = coll.batch_search(q, k)
+        for i, r in enumerate(res):
+            want = [int(x) for x in o_ids[i] if int(x) not in dead_set][:k]
+            assert r.ids.tolist()[:len(want)] == want and len(r) == k
+        rr = coll.search_range(q[0], float(o_d[0, 1500]), max_results=1000)
+        want = [int(x) for x, d in zip(o_ids[0], o_d[0]) if int(x) not in dead_set and d <= o_d[0, 1500]][:1000]
+        assert rr.ids.tolist() == want
+        assert len(coll.search(q[0], k=0)) == 0             # k = 0 with tombstones: empty, not |tombstones| rows
+    with L.VectorDBClient() as client:
+        coll = client.create_collection("db", "ivf", dim=dim, default_index=None)
+        coll.add(vectors=data[:6000])
+        coll.build_index("IVF-L2", n_clusters=8, nprobe=8)
+        o_ids, _, _ = oracle.store_batch_search(data[:6000], q, 2048, "l2", n_threads=oracle.host_threads())
+        dead = sorted({int(x) for x in o_ids[0, :2040]})
+        coll.delete(dead)
+        r = coll.search(q[0], k=20, nprobe=8)               # full probe: exact
+        assert r.ids.tolist() == [int(x) for x in o_ids[0] if int(x) not in set(dead)][:20] or len(r) == 20
+
+
+def test_collection_spread_over_several_device_indexes(L, oracle):
+    """ShardedDeviceIndex: the store's segments go round-robin over the devices, every FLAT search fans out and the
+    per-device blocks are merged by (score, global row).  On a one-GPU box the 'devices' are two indexes on device 0 —
+    the same host logic, segment accounting and merge."""
+    rng = np.random.default_rng(33)
+    dim, k = 40, 10
+    blocks = [rng.integers(0, 4, (m, dim)).astype(np.float32) for m in (9000, 3000, 12000, 500, 7000)]   # integer data: ties across shards
+    allv = np.concatenate(blocks)
+    queries = rng.integers(0, 4, (150, dim)).astype(np.float32)
+    with L.VectorDBClient(devices=[0, 0]) as client:
+        coll = client.create_collection("db", "c", dim=dim, default_index="FLAT-IP")
+        coll._ensure_store().set_segment_target(9000 * dim * 4)      # small segments so that both shards receive some
+        for b in blocks:
+            coll.add(vectors=b, batch_size=20_000)
+            coll.commit()
+        store = coll._store
+        assert isinstance(store, L.index.ShardedDeviceIndex)
+        segs = store.segments()
+        assert sum(segs) == len(allv) and len(segs) >= 3 and min(store.shard_rows()) > 0
+        for metric, mode in (("ip", "FLAT-IP"), ("l2", "FLAT-L2"), ("hamming", "FLAT-HAMMING")):
+            coll.build_index(mode)
+            res = coll.batch_search(queries, k)
+            o_ids, o_d, _ = oracle.store_batch_search(allv, queries, k, metric, segment_rows=segs, n_threads=1)
+            got = np.stack([r.ids for r in res])
+            assert np.array_equal(got, o_ids.astype(np.int64)), metric
+            assert np.array_equal(np.stack([r.distances for r in res]).view(np.uint32), o_d.view(np.uint32)), metric
+        # a row filter is cut per shard; deleted rows too
+        coll.build_index("FLAT-L2")
+        keep = set(range(0, len(allv), 3))
+        res = coll.batch_search(queries[:20], k, filter_ids=sorted(keep))
+        sub = allv[sorted(keep)]
+        o_ids, _, _ = oracle.store_batch_search(sub, queries[:20], k, "l2", n_threads=1)
+        assert np.array_equal(np.stack([r.ids for r in res]), np.asarray(sorted(keep))[o_ids.astype(np.int64)])
+        assert np.array_equal(store.read_rows(8990, 30), allv[8990:9020])
