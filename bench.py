@@ -65,6 +65,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--plan", default="auto", choices=["auto", "exact"])
     p.add_argument("--verify-queries", type=int, default=64, help="queries whose id lists are compared with the exact plan")
+    p.add_argument("--no-api-e2e", action="store_true", help="skip the Collection.batch_search wall-clock line")
     p.add_argument("--no-c5", action="store_true", help="multi-GPU default run: skip the extra 10M-rows-per-GPU (configs[4]) measurement")
     return p.parse_args()
 
@@ -584,6 +585,30 @@ def main():
                  "ms_per_step": r5["ms_dev"] / steps5, "e2e_value": nq * steps5 / (r5["ms_e2e"] / 1000.0), "e2e_ms_per_step": r5["ms_e2e"] / steps5,
                  "kernel_ms": statistics.mean(r5["dom"]) if r5["dom"] else None, "fallback_queries": int(r5["fallbacks"]), "verified": v5}
 
+    # the same step through the Python object model a LynseDB user calls: Collection.batch_search over the same index
+    api_e2e = None
+    if rank == 0 and world == 1 and not packed and not args.no_api_e2e:
+        from lynsedb_b200.client import Collection
+
+        coll = Collection("bench", dim, default_index=None)
+        coll.attach_store(rig.idx)
+        coll.build_index({"ip": "FLAT-IP", "l2": "FLAT-L2", "cosine": "FLAT-COS"}.get(metric, "FLAT-IP"))
+        for _ in range(2):
+            coll.batch_search(rig.queries, k)
+        t0 = time.perf_counter()
+        n_api = max(3, args.steps // 2)
+        for _ in range(n_api):
+            views = coll.batch_search(rig.queries, k)
+        api_ms = (time.perf_counter() - t0) * 1000.0 / n_api
+        cabi_ms = res["ms_e2e"] / args.steps
+        rig.step_host()
+        same = bool(np.array_equal(np.stack([v.ids for v in views]).astype(np.uint64), rig.host_results()[0]))
+        api_e2e = {"value": nq / (api_ms / 1000.0), "unit": "queries/s", "ms_per_step": api_ms,
+                   "call": f"Collection.batch_search({nq} x {dim} float32 ndarray, k={k}) -> list[ResultView] (pageable host arrays)",
+                   "python_layer_ms": api_ms - cabi_ms, "python_layer_frac_of_step": (api_ms - cabi_ms) / api_ms,
+                   "ids_equal_c_abi_result": same}
+        coll._store = None   # the rig owns the index
+
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -618,6 +643,7 @@ def main():
             "partitions": int(st["n_partitions"]),
             "wall_ms_per_step": res["wall_dev"] / args.steps,
             "verified": verified,
+            "api_e2e": api_e2e,
         }
         if extra is not None:
             line["c5_weak"] = extra

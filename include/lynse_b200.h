@@ -267,6 +267,11 @@ int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uin
  * to completion and to end of issue. */
 int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int i8, int grid, uint64_t* cycles_total, uint64_t* cycles_issue);
 
+/* CUDA-core instruction-rate probe: thread-level instructions per clock per SM of op 0 = popc.b32 + add (one chain step),
+ * 1 = lop3.b32, 2 = fp32 fma, 3 = integer add, 4 = three-input integer max; 2 x 1024 threads per SM, 8 independent chains
+ * per thread.  The denominators of the popcount / CUDA-core rooflines in profiles/ come from it. */
+int lb_debug_core_rate(int op, int iters, double* inst_per_clk_per_sm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,7 @@ SIGNATURES = {
     "lb_index_event_record": (C.c_int, [_vp, C.c_int]),
     "lb_index_event_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
     "lb_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p]),
+    "lb_debug_core_rate": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "lb_debug_tc_scores": (C.c_int, [_f32p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, C.c_int, _f32p]),
 }
 

@@ -39,6 +39,82 @@ def _index_family(mode: str) -> str:
     return "FLAT"
 
 
+class _IdMap:
+    """row <-> external id (``row_to_user_id``, src/engine.rs:3071-3073).  While the ids are exactly 0, 1, 2, ... in row
+    order (what ``add`` assigns by default) nothing is stored: a 10M-row collection costs no Python objects.  The first
+    id that breaks the pattern materialises a list and a dict."""
+
+    def __init__(self):
+        self.n = 0
+        self.ids: Optional[list] = None       # None = identity
+        self.rows: Optional[dict] = None
+        self.max_int = -1
+        self.all_int = True
+        self._np: Optional[np.ndarray] = None
+
+    def __len__(self) -> int:
+        return self.n
+
+    def _materialise(self) -> None:
+        if self.ids is None:
+            self.ids = list(range(self.n))
+            self.rows = {i: i for i in range(self.n)}
+
+    def extend(self, ext: list) -> None:
+        m = len(ext)
+        if self.ids is None and m and ext[0] == self.n and ext[-1] == self.n + m - 1 and \
+                all(type(e) is int for e in ext) and ext == list(range(self.n, self.n + m)):
+            self.n += m
+            self.max_int = self.n - 1
+            return
+        self._materialise()
+        for e in ext:
+            self.rows[e] = self.n
+            self.ids.append(e)
+            self.n += 1
+            if isinstance(e, (int, np.integer)) and not isinstance(e, bool):
+                if e > self.max_int:
+                    self.max_int = int(e)
+            else:
+                self.all_int = False
+        self._np = None
+
+    def extend_identity(self, m: int) -> None:
+        """m more rows whose ids continue the 0, 1, 2, ... pattern."""
+        if self.ids is None:
+            self.n += m
+            self.max_int = self.n - 1
+        else:
+            self.extend(list(range(self.n, self.n + m)))
+
+    def replace(self, ids: list) -> None:
+        self.__init__()
+        self.extend(list(ids))
+
+    def __contains__(self, ident) -> bool:
+        if self.ids is None:
+            return isinstance(ident, (int, np.integer)) and not isinstance(ident, bool) and 0 <= ident < self.n
+        return ident in self.rows
+
+    def row_of(self, ident) -> int:
+        return int(ident) if self.ids is None else self.rows[ident]
+
+    def id_of(self, row: int):
+        return int(row) if self.ids is None else self.ids[int(row)]
+
+    def array(self) -> Optional[np.ndarray]:
+        """row -> id as int64 (``None`` when some id is not an integer)."""
+        if not self.all_int:
+            return None
+        if self._np is None or len(self._np) != self.n:
+            self._np = np.arange(self.n, dtype=np.int64) if self.ids is None else np.asarray(self.ids, dtype=np.int64)
+        return self._np
+
+    @property
+    def identity(self) -> bool:
+        return self.ids is None
+
+
 class Collection:
     """``LocalCollection`` for the search path.  ``where`` accepts ``None``, a callable over the row's field dict, or a
     dict of field == value conditions (the reference's SQL ``where`` strings need its metadata engine, out of scope)."""
@@ -70,13 +146,9 @@ class Collection:
         self._pending: List[np.ndarray] = []
         self._pending_rows = 0
         self._pending_index: Optional[DeviceIndex] = None   # the un-flushed rows in HBM, rebuilt when they change
-        self._row_ids: List[Any] = []            # row -> external id (engine.rs:3071-3073)
-        self._id_rows: Dict[Any, int] = {}
+        self._ids = _IdMap()                     # row <-> external id (engine.rs:3071-3073)
         self._fields: Dict[int, dict] = {}
         self._tombstones: set = set()
-        self._max_int_id = -1
-        self._ids_np: Optional[np.ndarray] = None      # row -> id as int64 while every id is an integer (vectorised id mapping)
-        self._ids_all_int = True
         self._dead_rows: Optional[np.ndarray] = None   # sorted rows of the tombstoned ids (rebuilt when the set changes)
         self._dead_masks: Dict[Any, np.ndarray] = {}    # cached allow-bitsets with the tombstoned rows cleared
         self.COMMIT_FLAG = True
@@ -103,7 +175,7 @@ class Collection:
 
     @property
     def shape(self):
-        return (len(self._row_ids), self._dim or 0)
+        return (len(self._ids), self._dim or 0)
 
     @property
     def index_mode(self) -> Optional[str]:
@@ -113,16 +185,16 @@ class Collection:
         return self._dtypes
 
     def max_id(self) -> int:
-        return self._max_int_id
+        return self._ids.max_int
 
     def is_id_exists(self, id) -> bool:
-        return id in self._id_rows and id not in self._tombstones
+        return id in self._ids and id not in self._tombstones
 
     def list_deleted_ids(self) -> list:
         return sorted(self._tombstones, key=lambda x: (str(type(x)), x))
 
     def stats(self) -> dict:
-        return {"name": self.name, "rows": len(self._row_ids), "dim": self._dim, "index_mode": self._index_mode,
+        return {"name": self.name, "rows": len(self._ids), "dim": self._dim, "index_mode": self._index_mode,
                 "pending_rows": self._pending_rows, "deleted": len(self._tombstones),
                 "segments": self._store.segments() if self._store is not None else []}
 
@@ -164,24 +236,19 @@ class Collection:
                 if len(set(ext)) != len(ext):
                     raise ValueError("duplicate ids in one add() call")
                 for e in ext:
-                    if e in self._id_rows:
+                    if e in self._ids:
                         raise ValueError(f"id {e!r} already exists; use upsert")
             field_list = None
             if fields is not None:
                 field_list = [fields] if isinstance(fields, dict) else list(fields)
                 if len(field_list) != n:
                     raise ValueError(f"fields length ({len(field_list)}) must match vectors row count ({n})")
-            base = len(self._row_ids)
-            for j, e in enumerate(ext):
-                self._id_rows[e] = base + j
-                self._row_ids.append(e)
-                if isinstance(e, (int, np.integer)) and not isinstance(e, bool):
-                    if e > self._max_int_id:
-                        self._max_int_id = int(e)
-                else:
-                    self._ids_all_int = False
-                if field_list is not None and field_list[j] is not None:
-                    self._fields[base + j] = dict(field_list[j])
+            base = len(self._ids)
+            self._ids.extend(ext)
+            if field_list is not None:
+                for j in range(n):
+                    if field_list[j] is not None:
+                        self._fields[base + j] = dict(field_list[j])
             for s in range(0, n, batch_size):   # one add_items call per batch, as the reference client does
                 chunk = vec[s:s + batch_size]
                 self._pending.append(chunk)
@@ -246,6 +313,19 @@ class Collection:
             self._flush_pending()
             self.COMMIT_FLAG = True
 
+    def attach_store(self, store) -> None:
+        """Adopt an already filled ``DeviceIndex`` / ``ShardedDeviceIndex`` (rows generated on the device, bench.py): ids
+        are the row numbers.  The collection must be empty; it owns the store from here on."""
+        with self._lock:
+            if len(self._ids) or self._store is not None:
+                raise ValueError("attach_store needs an empty collection")
+            if self._dim is not None and store.dim != self._dim:
+                raise ValueError(f"Dimension mismatch: expected {self._dim}, got {store.dim}")
+            self._dim = store.dim
+            self._store = store
+            self._ids.extend_identity(len(store))
+        self._maybe_build_default_index()
+
     def insert_session(self) -> "InsertSession":
         """``with coll.insert_session() as s: s.add(...)`` — adds are applied and committed when the block ends
         (python/lynse/execution_layer/session.py)."""
@@ -256,22 +336,23 @@ class Collection:
         Rows keep their relative order, so ties still resolve the way they did."""
         with self._lock:
             self._flush_pending()
-            dead_rows = set(self._id_rows[t] for t in self._tombstones)
+            dead_rows = set(self._ids.row_of(t) for t in self._tombstones)
             if not dead_rows:
                 return 0
-            n = len(self._row_ids)
+            n = len(self._ids)
             live = np.asarray([r for r in range(n) if r not in dead_rows], dtype=np.int64)
             vectors = self._store.read_rows(0, n)[live] if n else np.empty((0, self._dim or 0), np.float32)
-            ids = [self._row_ids[int(r)] for r in live]
+            ids = [self._ids.id_of(int(r)) for r in live]
             fields = {new: self._fields[int(old)] for new, old in enumerate(live) if int(old) in self._fields}
             if self._ivf is not None:
                 self._ivf.close()
                 self._ivf = None
             self._store.close()
             self._store = None
-            self._row_ids, self._id_rows, self._fields = list(ids), {e: i for i, e in enumerate(ids)}, fields
+            self._ids.replace(ids)
+            self._fields = fields
             self._tombstones = set()
-            self._dead_rows, self._ids_np = None, None
+            self._dead_rows = None
             self._dead_masks.clear()
             if len(ids):
                 self._ensure_store().append(np.ascontiguousarray(vectors, dtype=np.float32))
@@ -287,7 +368,7 @@ class Collection:
         with self._lock:
             if self._dim is None:
                 raise ValueError("collection dimension must be set to read a raw vector store")
-            if self._row_ids:
+            if len(self._ids):
                 raise ValueError("load_lynsedb_directory needs an empty collection")
             dtype = dtype or self._dtypes
             segments, id_map_path = R.read_manifest(collection_path, self._dim, dtype)
@@ -299,10 +380,7 @@ class Collection:
             for path, rows in segments:
                 if rows:
                     self._ensure_store().append(R.read_segment(path, rows, self._dim, dtype))
-            self._row_ids = list(ext)
-            self._id_rows = {e: i for i, e in enumerate(ext)}
-            self._max_int_id = max([-1] + [int(e) for e in ext])
-            self._ids_np = None
+            self._ids.replace(ext)
         self._maybe_build_default_index()
         return total
 
@@ -312,7 +390,7 @@ class Collection:
         q = np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1)
         max_results = int(max_results)
         with self._lock:
-            if max_results <= 0 or self._dim is None or not self._row_ids:
+            if max_results <= 0 or self._dim is None or not len(self._ids):
                 idx_type, dist_name = M.parse_index_mode(self._index_mode or "FLAT-IP")
                 return ResultView(ids=np.empty(0, np.int64), distances=np.empty(0, np.float32), k=0, distance=dist_name,
                                   index=idx_type, result_type="search")
@@ -332,7 +410,7 @@ class Collection:
             asc = M.is_ascending(self._metric)
             ids, out = [], []
             for r, d in zip(rows[0, :int(counts[0])].tolist(), dists[0, :int(counts[0])].tolist()):
-                e = self._row_ids[r]
+                e = self._ids.id_of(r)
                 if e in self._tombstones or not (d <= threshold if asc else d >= threshold):
                     continue
                 ids.append(e)
@@ -353,7 +431,7 @@ class Collection:
             n = 0
             for i in ids:
                 i = i.item() if isinstance(i, np.generic) else i
-                if i in self._id_rows and i not in self._tombstones:
+                if i in self._ids and i not in self._tombstones:
                     self._tombstones.add(i)
                     n += 1
             if n:
@@ -377,7 +455,7 @@ class Collection:
 
     # ------------------------------------------------------------------ index
     def _maybe_build_default_index(self) -> None:
-        if self._index_mode is None and self._default_index and self._row_ids:
+        if self._index_mode is None and self._default_index and len(self._ids):
             self.build_index(self._default_index)
 
     def build_index(self, index_mode: str = "FLAT-IP", **kwargs) -> None:
@@ -452,7 +530,7 @@ class Collection:
             return None
         rows = None
         if filter_ids is not None:
-            rows = {self._id_rows[i] for i in filter_ids if i in self._id_rows}
+            rows = {self._ids.row_of(i) for i in filter_ids if i in self._ids}
         if where is not None:
             pred: Callable[[dict], bool]
             if isinstance(where, str):
@@ -462,14 +540,14 @@ class Collection:
                 pred = lambda f: all(f.get(k) == v for k, v in cond.items())  # noqa: E731
             else:
                 pred = where
-            matched = {r for r in range(len(self._row_ids)) if pred(self._fields.get(r, {}))}
+            matched = {r for r in range(len(self._ids)) if pred(self._fields.get(r, {}))}
             rows = matched if rows is None else rows & matched
         return np.fromiter(sorted(rows), dtype=np.uint64, count=len(rows))
 
     # ---- tombstones as a row mask ------------------------------------------------------------------------------------
     def _dead_row_array(self) -> np.ndarray:
         if self._dead_rows is None:
-            self._dead_rows = np.sort(np.fromiter((self._id_rows[t] for t in self._tombstones), dtype=np.uint64, count=len(self._tombstones)))
+            self._dead_rows = np.sort(np.fromiter((self._ids.row_of(t) for t in self._tombstones), dtype=np.uint64, count=len(self._tombstones)))
         return self._dead_rows
 
     def _live_mask(self, n_rows: int, allow: Optional[np.ndarray], first_row: int = 0) -> np.ndarray:
@@ -550,11 +628,7 @@ class Collection:
 
     def _row_id_array(self) -> Optional[np.ndarray]:
         """row -> external id as an int64 array while every id is an integer (else ``None``: ids are mapped one by one)."""
-        if not self._ids_all_int:
-            return None
-        if self._ids_np is None or len(self._ids_np) != len(self._row_ids):
-            self._ids_np = np.asarray(self._row_ids, dtype=np.int64)
-        return self._ids_np
+        return self._ids.array()
 
     def _finish_batch(self, rows: np.ndarray, dists: np.ndarray, counts: np.ndarray, k: int, return_fields: bool) -> List[ResultView]:
         """row_to_user_id + filter_tombstoned_limit (src/engine.rs:3071-3073, :3286-3308) for a whole batch at once."""
@@ -576,18 +650,22 @@ class Collection:
             m = int(n_keep[0]) if nq else 0
             id_block = ids_np[rows[:, :m].astype(np.int64)]
             d_block = np.ascontiguousarray(dists[:, :m], dtype=np.float32)
-            for i in range(nq):
-                flds = [dict(self._fields.get(int(r), {})) for r in rows[i, :m]] if return_fields else []
-                out.append(ResultView(ids=id_block[i], distances=d_block[i], fields=flds, k=m, distance=dist_name, index=idx_type,
-                                      result_type="search"))
-            return out
+            row_block = rows[:, :m]
+            fields_of = self._fields
+
+            def make(i: int) -> ResultView:
+                flds = [dict(fields_of.get(int(r), {})) for r in row_block[i]] if return_fields else []
+                return ResultView(ids=id_block[i], distances=d_block[i], fields=flds, k=m, distance=dist_name, index=idx_type,
+                                  result_type="search")
+
+            return _LazyViews(nq, make)
         for i in range(nq):
             sel = np.nonzero(keep[i])[0]
             r = rows[i, sel].astype(np.int64)
             if ids_np is not None:
                 id_arr = ids_np[r]
             else:
-                ids = [self._row_ids[int(x)] for x in r]
+                ids = [self._ids.id_of(int(x)) for x in r]
                 all_int = all(isinstance(x, (int, np.integer)) and not isinstance(x, bool) for x in ids)
                 id_arr = np.asarray(ids, dtype=np.int64) if all_int else np.asarray(ids, dtype=object)
             flds = [dict(self._fields.get(int(x), {})) for x in r] if return_fields else []
@@ -631,7 +709,7 @@ class Collection:
         k = int(k)
         nq = q.shape[0]
         with self._lock:
-            if self._dim is None or not self._row_ids or k <= 0:      # empty collection / k = 0: empty result, not an error
+            if self._dim is None or not len(self._ids) or k <= 0:      # empty collection / k = 0: empty result, not an error
                 empty = (np.empty((nq, 0), np.uint64), np.empty((nq, 0), np.float32), np.zeros(nq, np.int64))
                 return self._finish_batch(*empty, max(k, 0), return_fields)
             if q.shape[1] != self._dim:
@@ -678,6 +756,77 @@ def _merge_row_results(l_rows, l_d, r_rows, r_d, limit: int, ascending: bool):
             best[r] = d
     pairs = sorted(best.items(), key=(lambda p: (p[1], p[0])) if ascending else (lambda p: (-p[1], p[0])))[:limit]
     return np.asarray([p[0] for p in pairs], np.uint64), np.asarray([p[1] for p in pairs], np.float32)
+
+
+class _LazyViews(list):
+    """The ``list[ResultView]`` of a batch search whose views are built from the batch's id / distance blocks when they
+    are first touched: a 1024-query batch costs two array gathers instead of 1024 object constructions unless the caller
+    reads every view.  A real ``list`` (``isinstance`` holds); every read path materialises what it returns."""
+
+    __slots__ = ("_make",)
+
+    def __init__(self, n: int, make: Callable[[int], ResultView]):
+        super().__init__([None] * n)
+        self._make = make
+
+    def _fill(self, i: int) -> ResultView:
+        v = list.__getitem__(self, i)
+        if v is None:
+            v = self._make(i if i >= 0 else len(self) + i)
+            list.__setitem__(self, i, v)
+        return v
+
+    def _fill_all(self) -> None:
+        for i in range(len(self)):
+            self._fill(i)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._fill(j) for j in range(*i.indices(len(self)))]
+        return self._fill(i)
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self._fill(i)
+
+    def __reversed__(self):
+        for i in range(len(self) - 1, -1, -1):
+            yield self._fill(i)
+
+    def __contains__(self, item) -> bool:
+        return any(v == item for v in self)
+
+    def __eq__(self, other) -> bool:
+        self._fill_all()
+        if isinstance(other, _LazyViews):
+            other._fill_all()
+        return list.__eq__(self, other)
+
+    __hash__ = None
+
+    def __add__(self, other):
+        return list(self) + list(other)
+
+    def __mul__(self, n):
+        return list(self) * n
+
+    def copy(self):
+        return list(self)
+
+    def index(self, *args):
+        self._fill_all()
+        return list.index(self, *args)
+
+    def count(self, item) -> int:
+        self._fill_all()
+        return list.count(self, item)
+
+    def __repr__(self) -> str:
+        self._fill_all()
+        return list.__repr__(self)
+
+    def __reduce__(self):
+        return (list, (list(self),))
 
 
 class InsertSession:

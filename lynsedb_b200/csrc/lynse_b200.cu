@@ -150,6 +150,20 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
     if (idx->timing) cudaEventRecord(idx->ev[2], idx->stream);
     int kernels = 0;
     float ms_dom = 0;
+    // the tensor-core plan is a candidate; building its shadow (a no-op once built) may still rule it out (non-finite rows)
+    const bool tc_candidate = idx->dtype == LB_F32 && !metric_binary(metric) && idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT &&
+                              tc_supported(idx, metric) && k <= 256 && idx->n >= 64;
+    bool use_tc = tc_candidate &&
+                  // a row filter rides along as a mask on the hit bits; with few allowed rows the shortlists cannot fill
+                  // and certification would send everything to the exact scan anyway
+                  (d_allow == nullptr || idx->allow_count >= (uint64_t)std::max(1024, 32 * k)) &&
+                  // a handful of queries over a small corpus is a latency case: the exact scan is two launches, the tensor
+                  // plan three plus a lazily built shadow (100k x 128, one query: 85 against 131 us of device time)
+                  !(nq <= 4 && (uint64_t)idx->n * idx->dim * 4 < (256ull << 20));
+    if (use_tc) {
+        LB_TRY(ensure_shadow(idx, shadow_kind_for(metric)));
+        use_tc = !idx->shadow[shadow_kind_for(metric)].disabled;
+    }
     if (idx->dtype == LB_PACKED_U64 || metric_binary(metric)) {
         // FlatMmap::search binary branch (flat_mmap.rs:839-845): packed rows, packed queries
         const uint64_t* words;
@@ -214,13 +228,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
             idx->stats.plan_used = 2;
             idx->stats.algorithmic_bytes = (uint64_t)idx->n * nw * 8;
         }
-    } else if (idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT && tc_supported(idx, metric) && k <= 256 && idx->n >= 64 &&
-               // a row filter rides along as a mask on the hit bits; with few allowed rows the shortlists cannot fill
-               // and certification would send everything to the exact scan anyway
-               (d_allow == nullptr || idx->allow_count >= (uint64_t)std::max(1024, 32 * k)) &&
-               // a handful of queries over a small corpus is a latency case: the exact scan is two launches, the tensor
-               // plan three plus a lazily built shadow (100k x 128, one query: 85 against 131 us of device time)
-               !(nq <= 4 && (uint64_t)idx->n * idx->dim * 4 < (256ull << 20))) {
+    } else if (use_tc) {
         const int split = tc_query_split(idx, nq);
         if (split == 1) {
             LB_TRY(run_tc(idx, metric, reinterpret_cast<const float*>(d_queries), nq, k, d_rows, d_dists, d_counts, nullptr, d_allow, defer_tc_check));
@@ -1736,6 +1744,76 @@ int lb_merge_shard_blocks(int device, int metric, int n_shards, uint32_t nq, uin
     cudaFree(d_dists);
     cudaFree(d_counts);
     if (e != cudaSuccess) return fail(LB_CUDA, std::string("lb_merge_shard_blocks: ") + cudaGetErrorString(e));
+    return LB_OK;
+}
+
+}  // extern "C"
+
+// ---- CUDA-core instruction-rate probe (roofline denominators of the non-tensor kernels) ---------------------------------------------
+// Every thread runs `iters` rounds of eight independent dependency chains of one instruction; 2 CTAs x 1024 threads per SM
+// keep every scheduler full.  Result: instructions per clock per SM, from the SM's own cycle counter.
+template <int OP>
+static __global__ void __launch_bounds__(1024, 2) core_rate_kernel(int iters, uint32_t seed, unsigned long long* cycles, uint32_t* sink) {
+    uint32_t x[8];
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u;
+        f[i] = (float)(x[i] & 0xffff) * 1e-5f;
+    }
+    const uint32_t a = seed | 1u, b = seed * 3u + 7u;
+    const float fa = 1.0000001f, fb = 1e-9f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (OP == 0) x[i] = __popc(x[i]) + a;                          // POPC + IADD: the add keeps the chain data-dependent
+            else if (OP == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+            else if (OP == 2) f[i] = __fmaf_rn(f[i], fa, fb);
+            else if (OP == 3) x[i] = x[i] + a;                               // IADD alone (to subtract from OP 0)
+            else x[i] = max(max(x[i], a), b + (uint32_t)it);                  // VIMNMX3
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc ^= x[i] ^ __float_as_uint(f[i]);
+    if (acc == 0x12345678u) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
+extern "C" {
+
+int lb_debug_core_rate(int op, int iters, double* inst_per_clk_per_sm) {
+    if (op < 0 || op > 4 || iters < 1 || !inst_per_clk_per_sm) return fail(LB_INVALID_ARGUMENT, "bad probe arguments");
+    int dev = 0, sms = 0;
+    LB_CUDA_TRY(cudaGetDevice(&dev));
+    LB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = sms * 2;
+    unsigned long long* d_cycles = nullptr;
+    uint32_t* d_sink = nullptr;
+    LB_CUDA_TRY(cudaMalloc(&d_cycles, (size_t)grid * 8));
+    LB_CUDA_TRY(cudaMalloc(&d_sink, 4));
+    for (int rep = 0; rep < 2; ++rep) {
+        switch (op) {
+            case 0: core_rate_kernel<0><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
+            case 1: core_rate_kernel<1><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
+            case 2: core_rate_kernel<2><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
+            case 3: core_rate_kernel<3><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
+            default: core_rate_kernel<4><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
+        }
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<unsigned long long> h(grid);
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_cycles, (size_t)grid * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_cycles);
+    cudaFree(d_sink);
+    if (e != cudaSuccess) return fail(LB_CUDA, std::string("core rate probe: ") + cudaGetErrorString(e));
+    std::sort(h.begin(), h.end());
+    const double cyc = (double)h[grid / 2];
+    // two resident CTAs of 1024 threads per SM, 8 instructions per thread and round
+    *inst_per_clk_per_sm = 2.0 * 1024.0 * 8.0 * (double)iters / cyc;
     return LB_OK;
 }
 
