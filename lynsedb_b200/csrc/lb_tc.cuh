@@ -1028,7 +1028,7 @@ struct FinArgs {
 // accumulator still sees its products in the reference's order; the horizontal sums are the reference's trees done
 // with shuffles.  The row comes from `rowbuf` (shared memory, filled with coalesced loads by the same warp), 256
 // columns at a time.  lanes: lane & 7 = AVX lane, lane >> 3 = which of the warp's four rows.
-constexpr int FIN_COLS = 256;   // columns staged per round
+constexpr int FIN_COLS = 128;   // columns staged per round (128: 17 KiB of row buffers per 256-thread block, seven blocks per SM)
 constexpr int FIN_STRIDE = FIN_COLS + 8;  // row pitch of the staging buffer: the four rows of a warp land in different banks
 __device__ __forceinline__ float hsum8_shfl(float a) {   // simd.rs:1427-1436 over the 8 threads of a row
     a = a + __shfl_xor_sync(0xffffffffu, a, 4);           // s[i] = acc[i] + acc[i+4]

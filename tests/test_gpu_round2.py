@@ -149,7 +149,7 @@ def test_baseline_c3_flat_l2_2m_x_128_k100(L, oracle):
     """configs[2] at 2M rows (what the oracle scans in seconds): FLAT-L2, 128 dims, k = 100, hit mode + seeded floors."""
     from lynsedb_b200 import synthetic
 
-    n, dim, nq, k = 2_000_000, 128, 256, 100
+    n, dim, nq, k = 2_000_000, 128, 600, 100       # three query groups: the seeded-floor / hit-mode plan at this size
     queries = synthetic.rows_f32(43, np.arange(nq), dim)
     with L.DeviceIndex(dim) as idx:
         for lo in range(0, n, 100_000):
