@@ -66,8 +66,9 @@ typedef enum lb_metric {
 /* Storage dtype of an index. LB_F32 = VectorDtype::F32 (src/storage/dtype.rs).
  * LB_PACKED_U64 holds pre-packed one-bit rows (the reference's lazily built
  * BinaryData cache, src/storage/flat_mmap.rs:126-160, ingested directly so a
- * 50M x 1024-bit corpus need not exist as f32). */
-typedef enum lb_dtype { LB_F32 = 0, LB_PACKED_U64 = 1 } lb_dtype;
+ * 50M x 1024-bit corpus need not exist as f32).  LB_F16 = VectorDtype::F16 (src/storage/dtype.rs:60-67): rows are kept as
+ * IEEE binary16 in HBM — half the bytes of every scan — and decoded (exactly) on load by every kernel; queries stay f32. */
+typedef enum lb_dtype { LB_F32 = 0, LB_PACKED_U64 = 1, LB_F16 = 2 } lb_dtype;
 
 /* Search plan selector for lb_index_set_plan (diagnostics / tests). */
 typedef enum lb_plan {
@@ -116,6 +117,9 @@ int lb_index_append_f32(lb_index* idx, const float* rows, uint64_t n);
 /* LB_PACKED_U64 indexes: rows of ceil(dim/64) u64 words, bit i of a row at
  * word i/64 bit i%64 (src/distance/simd.rs:750-757). */
 int lb_index_append_packed(lb_index* idx, const uint64_t* words, uint64_t n);
+/* LB_F16 indexes: raw binary16 rows (the reference's on-disk f16 segments, src/storage/vector_store.rs:24-60);
+ * lb_index_append_f32 on an LB_F16 index narrows f32 values with round-to-nearest-even. */
+int lb_index_append_f16(lb_index* idx, const uint16_t* rows, uint64_t n);
 /* synthetic corpus generated on the device (bench / large parity tests):
  * f32: value(row, col) = u24(hash(seed, row*dim+col)) * 2^-24  in [0,1)
  * packed: word(row, w) = hash64(seed, row*words+w).  `row_offset` is the global

@@ -17,7 +17,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("LYNSE_B200_LIB", _HERE / "liblynse_b200.so"))
 
 LB_OK, LB_INVALID_ARGUMENT, LB_DIMENSION_MISMATCH, LB_IO, LB_CUDA, LB_NCCL, LB_UNSUPPORTED, LB_INTERNAL = range(8)
-LB_F32, LB_PACKED_U64 = 0, 1
+LB_F32, LB_PACKED_U64, LB_F16 = 0, 1, 2
 LB_PLAN_AUTO, LB_PLAN_EXACT = 0, 1
 ROW_NONE = 0xFFFFFFFF
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "lb_index_new_segment": (C.c_int, [_vp]),
     "lb_index_append_f32": (C.c_int, [_vp, _f32p, C.c_uint64]),
     "lb_index_append_packed": (C.c_int, [_vp, _u64p, C.c_uint64]),
+    "lb_index_append_f16": (C.c_int, [_vp, C.POINTER(C.c_uint16), C.c_uint64]),
     "lb_index_append_synthetic": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64]),
     "lb_index_len": (C.c_uint64, [_vp]),
     "lb_index_dim": (C.c_uint32, [_vp]),

@@ -269,10 +269,13 @@ class Collection:
         if self._store is None:
             if self._dim is None:
                 raise ValueError("collection dimension is not known yet")
+            # float16 collections keep their rows as binary16 in HBM (half the bytes of every scan); the values were rounded
+            # at write time, so narrowing them is exact
+            row_dtype = "float16" if self._dtypes == "float16" else "float32"
             if len(self._devices) > 1:
-                self._store = ShardedDeviceIndex(self._dim, "float32", self._devices)
+                self._store = ShardedDeviceIndex(self._dim, row_dtype, self._devices)
             else:
-                self._store = DeviceIndex(self._dim, "float32", self._devices[0])
+                self._store = DeviceIndex(self._dim, row_dtype, self._devices[0])
             if self._dtypes == "float16":
                 # segment boundaries never reach a float16 collection's results: search() scores rows one by one, and the
                 # batch path scans `read_all_f32()` — the whole store as ONE array (src/engine.rs:5448-5453), so the
@@ -501,9 +504,11 @@ class Collection:
     def _build_ivf(self) -> None:
         if self._store is None or len(self._store) == 0:
             return
-        if isinstance(self._store, ShardedDeviceIndex):
-            # the inverted lists address the rows of ONE device index: gather the store on the first device
+        if isinstance(self._store, ShardedDeviceIndex) or self._store.dtype != "float32":
+            # the inverted lists address the f32 rows of ONE device index: gather (and decode) the store on the first device
             single = DeviceIndex(self._dim, "float32", self._devices[0])
+            if self._dtypes == "float16":
+                single.set_segment_target(1 << 62)
             n, pos = len(self._store), 0
             for rows in self._store.segments():
                 single.new_segment()

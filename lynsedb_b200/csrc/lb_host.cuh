@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "lb_common.cuh"
 
 namespace lb {
@@ -230,7 +232,7 @@ struct lb_index {
 namespace lb {
 
 inline size_t row_bytes(const lb_index* idx) {
-    return idx->dtype == LB_F32 ? (size_t)idx->dim * 4 : (size_t)idx->n_words * 8;
+    return idx->dtype == LB_F32 ? (size_t)idx->dim * 4 : (idx->dtype == LB_F16 ? (size_t)idx->dim * 2 : (size_t)idx->n_words * 8);
 }
 
 struct DeviceGuard {
@@ -248,6 +250,7 @@ struct DeviceGuard {
 
 struct ScanRequest {
     const float* corpus = nullptr;
+    const __half* corpus_h = nullptr;   // binary16 rows (LB_F16 index) instead of `corpus`
     const uint64_t* words = nullptr;
     uint64_t n_rows = 0;
     int dim = 0, n_words = 0;

@@ -11,6 +11,8 @@
 // bit-identical to the CPU path; the transcendental tails (libm log / sin /
 // cos / asin) agree to the last ulp or two.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "lb_common.cuh"
 
 namespace lb {
@@ -46,6 +48,29 @@ __device__ __forceinline__ Vec8 load8(const float* __restrict__ p, bool vec) {
     return r;
 }
 
+// binary16 rows (float16 collections keep their rows as IEEE half in HBM; decoding is exact): the same 8 elements
+template <bool GLOBAL>
+__device__ __forceinline__ Vec8 load8(const __half* __restrict__ p, bool vec) {
+    Vec8 r;
+    if (vec && (reinterpret_cast<uintptr_t>(p) & 15u) == 0u) {
+        const uint4 x = GLOBAL ? __ldg(reinterpret_cast<const uint4*>(p)) : *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            r.v[2 * i] = f.x;
+            r.v[2 * i + 1] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = __half2float(GLOBAL ? __ldg(p + i) : p[i]);
+    }
+    return r;
+}
+// one row element from global memory
+__device__ __forceinline__ float ldrow(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldrow(const __half* p) { return __half2float(__ldg(p)); }
+
 // simd.rs:1427-1436 — extractf128+add, movehdup+add, movehl+add_ss
 __device__ __forceinline__ float hsum8(const float a[8]) {
     float s0 = a[0] + a[4], s1 = a[1] + a[5], s2 = a[2] + a[6], s3 = a[3] + a[7];
@@ -69,8 +94,8 @@ __device__ __forceinline__ float max_ps(float a, float b) { return a > b ? a : b
 
 // ---- inner product -----------------------------------------------------------------
 // batch-8 order (simd.rs:1450-1525): ONE accumulator vector per row.
-template <bool QG>
-__device__ float ip_batch8_order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float ip_batch8_order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
 #pragma unroll 2
@@ -80,12 +105,12 @@ __device__ float ip_batch8_order(const float* __restrict__ q, const float* __res
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(qv.v[i], cv.v[i], acc[i]);
     }
     float out = hsum8(acc);
-    for (int i = chunks * 8; i < dim; ++i) out = out + (QG ? __ldg(q + i) : q[i]) * __ldg(c + i);
+    for (int i = chunks * 8; i < dim; ++i) out = out + (QG ? __ldg(q + i) : q[i]) * ldrow(c + i);
     return out;
 }
 // single-row order (simd.rs:1341-1396): TWO accumulator vectors over a 16-stride.
-template <bool QG>
-__device__ float ip_single_order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float ip_single_order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
     int j = 0;
@@ -106,13 +131,13 @@ __device__ float ip_single_order(const float* __restrict__ q, const float* __res
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc0[i] = acc0[i] + acc1[i];
     float out = hsum8(acc0);
-    for (int i = chunks * 8; i < dim; ++i) out = out + (QG ? __ldg(q + i) : q[i]) * __ldg(c + i);
+    for (int i = chunks * 8; i < dim; ++i) out = out + (QG ? __ldg(q + i) : q[i]) * ldrow(c + i);
     return out;
 }
 
 // ---- squared L2 (simd.rs:1527-1581) -------------------------------------------------
-template <bool QG>
-__device__ float l2_squared(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float l2_squared(const float* __restrict__ q, CP c, int dim, bool vec) {
     float acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
     int j = 0;
@@ -139,15 +164,15 @@ __device__ float l2_squared(const float* __restrict__ q, const float* __restrict
     for (int i = 0; i < 8; ++i) acc0[i] = acc0[i] + acc1[i];
     float sum = hsum8(acc0);
     for (int i = chunks * 8; i < dim; ++i) {
-        float diff = (QG ? __ldg(q + i) : q[i]) - __ldg(c + i);
+        float diff = (QG ? __ldg(q + i) : q[i]) - ldrow(c + i);
         sum = sum + diff * diff;
     }
     return sum;
 }
 
 // ---- cosine distance (simd.rs:1583-1636) ----------------------------------------------
-template <bool QG>
-__device__ float cosine_distance(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float cosine_distance(const float* __restrict__ q, CP c, int dim, bool vec) {
     float dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, aacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
     for (int j = 0; j < chunks; ++j) {
@@ -161,7 +186,7 @@ __device__ float cosine_distance(const float* __restrict__ q, const float* __res
     }
     float dot = hsum8(dacc), na = hsum8(aacc), nb = hsum8(bacc);
     for (int i = chunks * 8; i < dim; ++i) {
-        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
+        float a = QG ? __ldg(q + i) : q[i], b = ldrow(c + i);
         dot = dot + a * b;
         na = na + a * a;
         nb = nb + b * b;
@@ -172,8 +197,8 @@ __device__ float cosine_distance(const float* __restrict__ q, const float* __res
 }
 
 // ---- L1 (simd.rs:2134-2158) ---------------------------------------------------------------
-template <bool QG>
-__device__ float manhattan(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float manhattan(const float* __restrict__ q, CP c, int dim, bool vec) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
     for (int j = 0; j < chunks; ++j) {
@@ -182,13 +207,13 @@ __device__ float manhattan(const float* __restrict__ q, const float* __restrict_
         for (int i = 0; i < 8; ++i) acc[i] = acc[i] + fabsf(a.v[i] - b.v[i]);
     }
     float sum = lane_sum8(acc);
-    for (int i = chunks * 8; i < dim; ++i) sum = sum + fabsf((QG ? __ldg(q + i) : q[i]) - __ldg(c + i));
+    for (int i = chunks * 8; i < dim; ++i) sum = sum + fabsf((QG ? __ldg(q + i) : q[i]) - ldrow(c + i));
     return sum;
 }
 
 // ---- Chebyshev (simd.rs:2715-2737) -----------------------------------------------------------
-template <bool QG>
-__device__ float chebyshev(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float chebyshev(const float* __restrict__ q, CP c, int dim, bool vec) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
     for (int j = 0; j < chunks; ++j) {
@@ -199,13 +224,13 @@ __device__ float chebyshev(const float* __restrict__ q, const float* __restrict_
     float m = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) m = rust_max(m, acc[i]);
-    for (int i = chunks * 8; i < dim; ++i) m = rust_max(m, fabsf((QG ? __ldg(q + i) : q[i]) - __ldg(c + i)));
+    for (int i = chunks * 8; i < dim; ++i) m = rust_max(m, fabsf((QG ? __ldg(q + i) : q[i]) - ldrow(c + i)));
     return m;
 }
 
 // ---- Canberra (simd.rs:2762-2793) ---------------------------------------------------------------
-template <bool QG>
-__device__ float canberra(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float canberra(const float* __restrict__ q, CP c, int dim, bool vec) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
     for (int j = 0; j < chunks; ++j) {
@@ -220,7 +245,7 @@ __device__ float canberra(const float* __restrict__ q, const float* __restrict__
     }
     float sum = lane_sum8(acc);
     for (int i = chunks * 8; i < dim; ++i) {
-        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
+        float a = QG ? __ldg(q + i) : q[i], b = ldrow(c + i);
         float den = fabsf(a) + fabsf(b);
         if (den != 0.0f) sum = sum + fabsf(a - b) / den;
     }
@@ -228,8 +253,8 @@ __device__ float canberra(const float* __restrict__ q, const float* __restrict__
 }
 
 // ---- Bray-Curtis (simd.rs:2824-2865) ----------------------------------------------------------------
-template <bool QG>
-__device__ float bray_curtis(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float bray_curtis(const float* __restrict__ q, CP c, int dim, bool vec) {
     float nacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
     for (int j = 0; j < chunks; ++j) {
@@ -242,7 +267,7 @@ __device__ float bray_curtis(const float* __restrict__ q, const float* __restric
     }
     float num = lane_sum8(nacc), den = lane_sum8(dacc);
     for (int i = chunks * 8; i < dim; ++i) {
-        float a = QG ? __ldg(q + i) : q[i], b = __ldg(c + i);
+        float a = QG ? __ldg(q + i) : q[i], b = ldrow(c + i);
         num = num + fabsf(a - b);
         den = den + fabsf(a + b);
     }
@@ -251,27 +276,27 @@ __device__ float bray_curtis(const float* __restrict__ q, const float* __restric
 }
 
 // ---- thresholded binary metrics on f32 (simd.rs:175-209, :718-736) -----------------------------------
-template <bool QG>
-__device__ float hamming_f32(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+template <bool QG, class CP>
+__device__ float hamming_f32(const float* __restrict__ q, CP c, int dim) {
     uint32_t count = 0;
-    for (int i = 0; i < dim; ++i) count += (((QG ? __ldg(q + i) : q[i]) > 0.5f) != (__ldg(c + i) > 0.5f));
+    for (int i = 0; i < dim; ++i) count += (((QG ? __ldg(q + i) : q[i]) > 0.5f) != (ldrow(c + i) > 0.5f));
     return (float)count;
 }
-template <bool QG>
-__device__ float jaccard_f32(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+template <bool QG, class CP>
+__device__ float jaccard_f32(const float* __restrict__ q, CP c, int dim) {
     uint32_t inter = 0, uni = 0;
     for (int i = 0; i < dim; ++i) {
-        bool ab = (QG ? __ldg(q + i) : q[i]) > 0.5f, bb = __ldg(c + i) > 0.5f;
+        bool ab = (QG ? __ldg(q + i) : q[i]) > 0.5f, bb = ldrow(c + i) > 0.5f;
         uni += (ab || bb);
         inter += (ab && bb);
     }
     return uni == 0 ? 0.0f : 1.0f - ((float)inter / (float)uni);
 }
-template <bool QG>
-__device__ float dice_f32(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+template <bool QG, class CP>
+__device__ float dice_f32(const float* __restrict__ q, CP c, int dim) {
     uint32_t inter = 0, ca = 0, cb = 0;
     for (int i = 0; i < dim; ++i) {
-        bool ab = (QG ? __ldg(q + i) : q[i]) > 0.5f, bb = __ldg(c + i) > 0.5f;
+        bool ab = (QG ? __ldg(q + i) : q[i]) > 0.5f, bb = ldrow(c + i) > 0.5f;
         ca += ab;
         cb += bb;
         inter += (ab && bb);
@@ -283,8 +308,8 @@ __device__ float dice_f32(const float* __restrict__ q, const float* __restrict__
 // ---- scalar f64 metrics ---------------------------------------------------------------------------------
 // Elements of a pair in index order: loads are 8 values at a time (two 128-bit loads per operand when `vec`), the
 // arithmetic one element at a time — for the kernels whose reference loop is a plain sequential one.
-template <bool QG, class F>
-__device__ __forceinline__ void scalar_order_foreach(const float* __restrict__ q, const float* __restrict__ c, int dim,
+template <bool QG, class F, class CP>
+__device__ __forceinline__ void scalar_order_foreach(const float* __restrict__ q, CP c, int dim,
                                                      bool vec, F&& f) {
     int chunks = dim >> 3;
     for (int j = 0; j < chunks; ++j) {
@@ -292,19 +317,19 @@ __device__ __forceinline__ void scalar_order_foreach(const float* __restrict__ q
 #pragma unroll
         for (int i = 0; i < 8; ++i) f(a.v[i], b.v[i]);
     }
-    for (int i = chunks * 8; i < dim; ++i) f(QG ? __ldg(q + i) : q[i], __ldg(c + i));
+    for (int i = chunks * 8; i < dim; ++i) f(QG ? __ldg(q + i) : q[i], ldrow(c + i));
 }
 
 __device__ __forceinline__ double clamp_f64(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __device__ __forceinline__ bool invalid_mass_value(float v) { return !isfinite(v) || v < 0.0f; }
 
 // simd.rs:603-628
-template <bool QG>
-__device__ float haversine_meters(const float* __restrict__ q, const float* __restrict__ c, int dim) {
+template <bool QG, class CP>
+__device__ float haversine_meters(const float* __restrict__ q, CP c, int dim) {
     if (dim != 2) return INFINITY;
     const double R = 6371008.8;
     const double k = 3.14159265358979323846264338327950288 / 180.0;
-    float a0 = QG ? __ldg(q) : q[0], a1 = QG ? __ldg(q + 1) : q[1], b0 = __ldg(c), b1 = __ldg(c + 1);
+    float a0 = QG ? __ldg(q) : q[0], a1 = QG ? __ldg(q + 1) : q[1], b0 = ldrow(c), b1 = ldrow(c + 1);
     double lon1 = (double)a0 * k, lat1 = (double)a1 * k, lon2 = (double)b0 * k, lat2 = (double)b1 * k;
     if (!isfinite(lon1) || !isfinite(lat1) || !isfinite(lon2) || !isfinite(lat2) || fabsf(a1) > 90.0f ||
         fabsf(b1) > 90.0f)
@@ -316,8 +341,8 @@ __device__ float haversine_meters(const float* __restrict__ q, const float* __re
 }
 
 // simd.rs:632-661
-template <bool QG>
-__device__ float correlation_distance(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float correlation_distance(const float* __restrict__ q, CP c, int dim, bool vec) {
     if (dim == 0) return 0.0f;
     double n = (double)dim, sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
@@ -333,7 +358,7 @@ __device__ float correlation_distance(const float* __restrict__ q, const float* 
     double denom = sqrt(var_a * var_b);
     if (denom <= 2.2204460492503131e-16) {
         bool same = true;
-        for (int i = 0; i < dim; ++i) same = same && ((QG ? __ldg(q + i) : q[i]) == __ldg(c + i));
+        for (int i = 0; i < dim; ++i) same = same && ((QG ? __ldg(q + i) : q[i]) == ldrow(c + i));
         return same ? 0.0f : 1.0f;
     }
     double cov = sab - sa * sb / n;
@@ -341,8 +366,8 @@ __device__ float correlation_distance(const float* __restrict__ q, const float* 
 }
 
 // simd.rs:665-684 (the early return on an invalid value is the same +inf whichever element trips it)
-template <bool QG>
-__device__ float hellinger_distance(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float hellinger_distance(const float* __restrict__ q, CP c, int dim, bool vec) {
     double sa = 0, sb = 0, coef = 0;
     bool bad = false;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
@@ -359,8 +384,8 @@ __device__ float hellinger_distance(const float* __restrict__ q, const float* __
 
 // simd.rs:688-714; DIVIDE = wasserstein_1d_f16 (simd.rs:1046-1071), which divides by the masses instead of
 // multiplying by their reciprocals
-template <bool QG, bool DIVIDE>
-__device__ float wasserstein_1d_impl(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, bool DIVIDE, class CP>
+__device__ float wasserstein_1d_impl(const float* __restrict__ q, CP c, int dim, bool vec) {
     double sa = 0, sb = 0;
     bool bad = false;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
@@ -378,8 +403,8 @@ __device__ float wasserstein_1d_impl(const float* __restrict__ q, const float* _
     });
     return (float)dist;
 }
-template <bool QG>
-__device__ float wasserstein_1d(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float wasserstein_1d(const float* __restrict__ q, CP c, int dim, bool vec) {
     return wasserstein_1d_impl<QG, false>(q, c, dim, vec);
 }
 
@@ -420,8 +445,8 @@ __device__ __forceinline__ float fast_ln(float x) {
 }
 
 // simd.rs:2249-2286
-template <bool QG>
-__device__ float jensen_shannon_avx(const float* __restrict__ a, const float* __restrict__ b, int dim, bool vec,
+template <bool QG, class CP>
+__device__ float jensen_shannon_avx(const float* __restrict__ a, CP b, int dim, bool vec,
                                     float inv_a, float inv_b) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
@@ -440,7 +465,7 @@ __device__ float jensen_shannon_avx(const float* __restrict__ a, const float* __
     }
     float divergence = lane_sum8(acc);
     for (int i = chunks * 8; i < dim; ++i) {
-        float p = (QG ? __ldg(a + i) : a[i]) * inv_a, q = __ldg(b + i) * inv_b;
+        float p = (QG ? __ldg(a + i) : a[i]) * inv_a, q = ldrow(b + i) * inv_b;
         float m = 0.5f * (p + q);
         if (p > 0.0f) divergence = divergence + 0.5f * p * logf(p / m);
         if (q > 0.0f) divergence = divergence + 0.5f * q * logf(q / m);
@@ -449,12 +474,12 @@ __device__ float jensen_shannon_avx(const float* __restrict__ a, const float* __
 }
 
 // simd.rs:1161-1178
-template <bool QG>
-__device__ float jensen_shannon_scalar_f64(const float* __restrict__ a, const float* __restrict__ b, int dim,
+template <bool QG, class CP>
+__device__ float jensen_shannon_scalar_f64(const float* __restrict__ a, CP b, int dim,
                                            double sum_a, double sum_b) {
     double inv_a = 1.0 / sum_a, inv_b = 1.0 / sum_b, divergence = 0;
     for (int i = 0; i < dim; ++i) {
-        double p = (double)(QG ? __ldg(a + i) : a[i]) * inv_a, q = (double)__ldg(b + i) * inv_b, m = 0.5 * (p + q);
+        double p = (double)(QG ? __ldg(a + i) : a[i]) * inv_a, q = (double)ldrow(b + i) * inv_b, m = 0.5 * (p + q);
         if (p > 0.0) divergence = divergence + 0.5 * p * log(p / m);
         if (q > 0.0) divergence = divergence + 0.5 * q * log(q / m);
     }
@@ -462,11 +487,11 @@ __device__ float jensen_shannon_scalar_f64(const float* __restrict__ a, const fl
 }
 
 // simd.rs:235-284 (+ refine_small_jensen_shannon, :1118-1125)
-template <bool QG>
-__device__ float jensen_shannon_distance(const float* __restrict__ a, const float* __restrict__ b, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float jensen_shannon_distance(const float* __restrict__ a, CP b, int dim, bool vec) {
     double sum_a = 0, sum_b = 0;
     for (int i = 0; i < dim; ++i) {
-        float x = QG ? __ldg(a + i) : a[i], y = __ldg(b + i);
+        float x = QG ? __ldg(a + i) : a[i], y = ldrow(b + i);
         if (invalid_mass_value(x) || invalid_mass_value(y)) return INFINITY;
         sum_a = sum_a + (double)x;
         sum_b = sum_b + (double)y;
@@ -478,14 +503,15 @@ __device__ float jensen_shannon_distance(const float* __restrict__ a, const floa
     float distance = jensen_shannon_avx<QG>(a, b, dim, vec, inv_a, inv_b);
     if (distance * distance <= kJsStableDivergence) {
         bool same = true;
-        for (int i = 0; i < dim; ++i) same = same && ((QG ? __ldg(a + i) : a[i]) == __ldg(b + i));
+        for (int i = 0; i < dim; ++i) same = same && ((QG ? __ldg(a + i) : a[i]) == ldrow(b + i));
         if (!same) return jensen_shannon_scalar_f64<QG>(a, b, dim, sum_a, sum_b);
     }
     return distance;
 }
 
 // simd.rs:2288-2312
-__device__ inline float probability_entropy_avx(const float* __restrict__ row, int dim, bool vec, float inv_mass) {
+template <class RP>
+__device__ inline float probability_entropy_avx(RP row, int dim, bool vec, float inv_mass) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
     for (int j = 0; j < chunks; ++j) {
@@ -499,18 +525,19 @@ __device__ inline float probability_entropy_avx(const float* __restrict__ row, i
     }
     float entropy = lane_sum8(acc);
     for (int i = chunks * 8; i < dim; ++i) {
-        float p = __ldg(row + i) * inv_mass;
+        float p = ldrow(row + i) * inv_mass;
         if (p > 0.0f) entropy = entropy + p * logf(p);
     }
     return entropy;
 }
 
 // simd.rs:291-331 — (inverse mass, sum p ln p)
-__device__ inline void probability_row_stats(const float* __restrict__ row, int dim, bool vec, float* inv_mass_out,
+template <class RP>
+__device__ inline void probability_row_stats(RP row, int dim, bool vec, float* inv_mass_out,
                                              float* entropy_out) {
     double sum = 0;
     for (int i = 0; i < dim; ++i) {
-        float v = __ldg(row + i);
+        float v = ldrow(row + i);
         if (invalid_mass_value(v)) {
             *inv_mass_out = __int_as_float(0x7fc00000);
             *entropy_out = INFINITY;
@@ -527,7 +554,7 @@ __device__ inline void probability_row_stats(const float* __restrict__ row, int 
     if (!isfinite(inv_mass) || inv_mass == 0.0f) {
         double e = 0;
         for (int i = 0; i < dim; ++i) {
-            float v = __ldg(row + i);
+            float v = ldrow(row + i);
             if (v > 0.0f) {
                 double p = (double)v / sum;
                 e = e + p * log(p);
@@ -542,8 +569,8 @@ __device__ inline void probability_row_stats(const float* __restrict__ row, int 
 }
 
 // simd.rs:498-536
-template <bool QG>
-__device__ float jensen_shannon_normalized_query(const float* __restrict__ nq, const float* __restrict__ cand, int dim,
+template <bool QG, class CP>
+__device__ float jensen_shannon_normalized_query(const float* __restrict__ nq, CP cand, int dim,
                                                  bool vec, float cand_inv_mass) {
     float distance = jensen_shannon_avx<QG>(nq, cand, dim, vec, 1.0f, cand_inv_mass);
     if (distance * distance <= kJsStableDivergence) return jensen_shannon_distance<QG>(nq, cand, dim, vec);
@@ -551,8 +578,8 @@ __device__ float jensen_shannon_normalized_query(const float* __restrict__ nq, c
 }
 
 // Σ s·ln(s), s = p + c·inv_c (simd.rs:2330-2345, :2376-2402)
-template <bool QG>
-__device__ float js_mixture_term(const float* __restrict__ nq, const float* __restrict__ cand, int dim, bool vec,
+template <bool QG, class CP>
+__device__ float js_mixture_term(const float* __restrict__ nq, CP cand, int dim, bool vec,
                                  float cand_inv_mass) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = dim >> 3;
@@ -568,15 +595,15 @@ __device__ float js_mixture_term(const float* __restrict__ nq, const float* __re
     }
     float mix = lane_sum8(acc);
     for (int i = chunks * 8; i < dim; ++i) {
-        float s = (QG ? __ldg(nq + i) : nq[i]) + __ldg(cand + i) * cand_inv_mass;
+        float s = (QG ? __ldg(nq + i) : nq[i]) + ldrow(cand + i) * cand_inv_mass;
         if (s > 0.0f) mix = mix + s * logf(s);
     }
     return mix;
 }
 
 // simd.rs:337-389 + :2316-2354 — entropy-form distance
-template <bool QG>
-__device__ float jensen_shannon_precomputed(const float* __restrict__ nq, const float* __restrict__ cand, int dim,
+template <bool QG, class CP>
+__device__ float jensen_shannon_precomputed(const float* __restrict__ nq, CP cand, int dim,
                                             bool vec, float query_entropy, float cand_inv_mass, float cand_entropy) {
     if (cand_inv_mass == 0.0f) return sqrtf(kLn2);
     if (!isfinite(cand_entropy)) return INFINITY;
@@ -588,8 +615,8 @@ __device__ float jensen_shannon_precomputed(const float* __restrict__ nq, const 
 }
 
 // simd.rs:418-496 + :2356-2423 — squared distance used for ranking
-template <bool QG>
-__device__ float jensen_shannon_precomputed_divergence(const float* __restrict__ nq, const float* __restrict__ cand,
+template <bool QG, class CP>
+__device__ float jensen_shannon_precomputed_divergence(const float* __restrict__ nq, CP cand,
                                                        int dim, bool vec, float query_entropy, float inv_mass,
                                                        float entropy) {
     if (inv_mass <= 0.0f || !isfinite(inv_mass) || !isfinite(entropy)) {
@@ -607,8 +634,8 @@ __device__ float jensen_shannon_precomputed_divergence(const float* __restrict__
 
 // ---- compute_distance_f32 dispatch (src/distance/mod.rs:193-213) ------------------------------------------------------
 // IP here is the single-row (two-accumulator) kernel, as in the reference.
-template <bool QG>
-__device__ float compute_distance(int metric, const float* __restrict__ q, const float* __restrict__ c, int dim,
+template <bool QG, class CP>
+__device__ float compute_distance(int metric, const float* __restrict__ q, CP c, int dim,
                                   bool vec) {
     switch (metric) {
         case LB_IP: return ip_single_order<QG>(q, c, dim, vec);
@@ -635,14 +662,14 @@ __device__ float compute_distance(int metric, const float* __restrict__ q, const
 // Rows of a float16 collection hold exactly binary16-representable values, so `c` may be the decoded row
 // (half::f16::to_f32 is exact).  Every sum is the reference's sequential scalar loop: element order, products and
 // sums rounded separately.  Loads are 8 values at a time, the arithmetic one element at a time.
-template <bool QG>
-__device__ float inner_product_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float inner_product_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float sum = 0.0f;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) { sum = sum + a * b; });
     return sum;
 }
-template <bool QG>
-__device__ float l2_squared_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float l2_squared_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float sum = 0.0f;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
         float diff = a - b;
@@ -650,8 +677,8 @@ __device__ float l2_squared_f16order(const float* __restrict__ q, const float* _
     });
     return sum;
 }
-template <bool QG>
-__device__ float cosine_distance_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float cosine_distance_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float dot = 0.0f, nq = 0.0f, nc = 0.0f;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
         dot = dot + a * b;
@@ -661,20 +688,20 @@ __device__ float cosine_distance_f16order(const float* __restrict__ q, const flo
     if (nq == 0.0f || nc == 0.0f) return 1.0f;
     return 1.0f - dot / (sqrtf(nq) * sqrtf(nc));
 }
-template <bool QG>
-__device__ float manhattan_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float manhattan_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float sum = 0.0f;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) { sum = sum + fabsf(a - b); });
     return sum;
 }
-template <bool QG>
-__device__ float chebyshev_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float chebyshev_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float m = 0.0f;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) { m = rust_max(m, fabsf(a - b)); });
     return m;
 }
-template <bool QG>
-__device__ float canberra_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float canberra_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float sum = 0.0f;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
         float den = fabsf(a) + fabsf(b);
@@ -682,8 +709,8 @@ __device__ float canberra_f16order(const float* __restrict__ q, const float* __r
     });
     return sum;
 }
-template <bool QG>
-__device__ float bray_curtis_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float bray_curtis_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     float num = 0.0f, den = 0.0f;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
         num = num + fabsf(a - b);
@@ -692,8 +719,8 @@ __device__ float bray_curtis_f16order(const float* __restrict__ q, const float* 
     if (den == 0.0f) return num == 0.0f ? 0.0f : INFINITY;
     return num / den;
 }
-template <bool QG>
-__device__ float jensen_shannon_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float jensen_shannon_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     double sa = 0, sb = 0;
     bool bad = false;
     scalar_order_foreach<QG>(q, c, dim, vec, [&](float a, float b) {
@@ -711,15 +738,15 @@ __device__ float jensen_shannon_f16order(const float* __restrict__ q, const floa
     });
     return (float)sqrt(fmax(divergence, 0.0));
 }
-template <bool QG>
-__device__ float wasserstein_1d_f16order(const float* __restrict__ q, const float* __restrict__ c, int dim, bool vec) {
+template <bool QG, class CP>
+__device__ float wasserstein_1d_f16order(const float* __restrict__ q, CP c, int dim, bool vec) {
     return wasserstein_1d_impl<QG, true>(q, c, dim, vec);
 }
 
 // compute_distance_f16 dispatch (src/distance/mod.rs:217-237).  Haversine, correlation and Hellinger repeat their f32
 // formulas on the decoded row; the binary metrics count thresholded bits element by element, as the f32 ones do.
-template <bool QG>
-__device__ float compute_distance_f16order(int metric, const float* __restrict__ q, const float* __restrict__ c, int dim,
+template <bool QG, class CP>
+__device__ float compute_distance_f16order(int metric, const float* __restrict__ q, CP c, int dim,
                                            bool vec) {
     switch (metric) {
         case LB_IP: return inner_product_f16order<QG>(q, c, dim, vec);

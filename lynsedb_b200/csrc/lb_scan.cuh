@@ -22,13 +22,16 @@
 #pragma once
 #include "lb_metrics.cuh"
 
+#include <type_traits>
+
 namespace lb {
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TQ = 16;  // queries per tile
 
 struct ScanArgs {
-    const float* corpus;        // [n][dim] f32 (null for packed scan)
+    const float* corpus;        // [n][dim] f32 (null for packed scan and for binary16 rows)
+    const __half* corpus_h;     // [n][dim] binary16 rows of a float16 index (kernels instantiated with RT = __half)
     const uint64_t* words;      // [n][n_words] packed rows (packed scan)
     uint32_t n_rows;            // rows scanned (or length of row_ids)
     int dim;
@@ -110,6 +113,12 @@ __device__ __forceinline__ void warp_offer_keys(const uint64_t* __restrict__ ske
     }
 }
 
+template <class RT>
+__device__ __forceinline__ const RT* corpus_rows(const ScanArgs& a) {
+    if constexpr (std::is_same<RT, float>::value) return a.corpus;
+    else return a.corpus_h;
+}
+
 __device__ __forceinline__ bool row_allowed(const uint64_t* __restrict__ allow_bits, uint32_t row) {
     return allow_bits == nullptr || ((__ldg(allow_bits + (row >> 6)) >> (row & 63)) & 1ull);
 }
@@ -120,9 +129,9 @@ __device__ __forceinline__ bool in_small_segment(const uint32_t* __restrict__ sm
 }
 
 // Ranking value of one (query, row) pair for the FLAT scan (flat_mmap.rs:1173-1230 dispatch).
-template <bool ASC>
+template <bool ASC, class CP>
 __device__ __forceinline__ float flat_pair_value(const ScanArgs& a, const float* __restrict__ q /*smem*/, int qi,
-                                                 const float* __restrict__ c, uint32_t row, bool vec, bool small) {
+                                                 CP c, uint32_t row, bool vec, bool small) {
     if (a.f16_rows) return compute_distance_f16order<false>(a.metric, q, c, a.dim, vec);  // flat_mmap.rs:1259-1281
     if (!ASC) {
         // IP: rows of segments >= 4096 rows take the batch-8 kernel, smaller segments the single-row kernel
@@ -141,7 +150,7 @@ __device__ __forceinline__ float flat_pair_value(const ScanArgs& a, const float*
     return compute_distance<false>(a.metric, q, c, a.dim, vec);
 }
 
-template <bool ASC>
+template <bool ASC, class RT = float>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_exact_kernel(ScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_scan[];
     uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_scan);                           // [SCAN_TQ][256]
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_exact_kernel(ScanArgs a) {
         uint32_t row = 0;
         if (valid) row = a.row_ids ? __ldg(a.row_ids + slot) : (uint32_t)slot;
         if (valid && !row_allowed(a.allow_bits, row)) valid = false;
-        const float* c = a.corpus + (size_t)row * dim;
+        const RT* c = corpus_rows<RT>(a) + (size_t)row * dim;
         bool small = valid && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
         for (int q0 = 0; q0 < a.nq; q0 += SCAN_TQ) {
             int tq = min(SCAN_TQ, a.nq - q0);
@@ -435,22 +444,24 @@ static __global__ void __launch_bounds__(1024) merge_lists_small_kernel(MergeArg
 
 // ---- side-structure builders ---------------------------------------------------------------------------------
 // pack_binary_f32 (simd.rs:750-757, flat_mmap.rs:1283-1290): bit = x > 0.5, word i/64 bit i%64.  One warp per row.
-static __global__ void pack_binary_kernel(const float* __restrict__ rows, uint64_t n, int dim, int n_words, float threshold,
+template <class RT>
+__global__ void pack_binary_kernel(const RT* __restrict__ rows, uint64_t n, int dim, int n_words, float threshold,
                                    uint64_t* __restrict__ out) {
     uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= n) return;
-    const float* r = rows + row * dim;
+    const RT* r = rows + row * dim;
     for (int w = 0; w < n_words; ++w) {
         int i0 = w * 64 + lane, i1 = i0 + 32;
-        unsigned lo = __ballot_sync(0xffffffffu, i0 < dim && __ldg(r + i0) > threshold);
-        unsigned hi = __ballot_sync(0xffffffffu, i1 < dim && __ldg(r + i1) > threshold);
+        unsigned lo = __ballot_sync(0xffffffffu, i0 < dim && ldrow(r + i0) > threshold);
+        unsigned hi = __ballot_sync(0xffffffffu, i1 < dim && ldrow(r + i1) > threshold);
         if (lane == 0) out[row * n_words + w] = ((uint64_t)hi << 32) | lo;
     }
 }
 
 // probability_row_stats for every row (flat_mmap.rs:949-983) — also used for the queries.
-static __global__ void row_stats_kernel(const float* __restrict__ rows, uint64_t n, int dim, float* __restrict__ stats) {
+template <class RT>
+__global__ void row_stats_kernel(const RT* __restrict__ rows, uint64_t n, int dim, float* __restrict__ stats) {
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     float inv, ent;

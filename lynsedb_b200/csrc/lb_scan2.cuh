@@ -47,10 +47,11 @@ __device__ inline void scan2_query_consts(const float* __restrict__ q /*smem*/, 
     out[1] = ss;
 }
 // Wasserstein row masses, once per row (the first loop of wasserstein_1d_f32, simd.rs:691-698)
-static __global__ void row_mass_kernel(const float* __restrict__ rows, uint64_t n, int dim, double* __restrict__ mass) {
+template <class RT>
+__global__ void row_mass_kernel(const RT* __restrict__ rows, uint64_t n, int dim, double* __restrict__ mass) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
-    const float* c = rows + row * dim;
+    const RT* c = rows + row * dim;
     const bool vec = (dim & 3) == 0;
     double s = 0;
     bool bad = false;
@@ -64,7 +65,7 @@ static __global__ void row_mass_kernel(const float* __restrict__ rows, uint64_t 
         }
     }
     for (int i = chunks * 8; i < dim; ++i) {
-        const float b = __ldg(c + i);
+        const float b = ldrow(c + i);
         bad = bad || invalid_mass_value(b);
         s = s + (double)b;
     }
@@ -169,12 +170,13 @@ struct Scan2Op {
     }
 
     // horizontal reduction + scalar tail (elements [tail0, dim)) + final formula
-    static __device__ __forceinline__ float finish(T* s, const float* __restrict__ q /*smem*/, const float* __restrict__ c /*global*/,
+    template <class CP>
+    static __device__ __forceinline__ float finish(T* s, const float* __restrict__ q /*smem*/, CP c /*global*/,
                                                    int tail0, int dim, bool two_acc, float q_norm2, const PairConst& pc) {
         if constexpr (METRIC == LB_CORRELATION) {
             if (dim == 0) return 0.0f;
             for (int i = tail0; i < dim; ++i) {
-                const double av = (double)q[i], bv = (double)__ldg(c + i);
+                const double av = (double)q[i], bv = (double)ldrow(c + i);
                 s[0] = s[0] + bv;
                 s[1] = s[1] + bv * bv;
                 s[2] = s[2] + av * bv;
@@ -185,14 +187,14 @@ struct Scan2Op {
             const double denom = sqrt(var_a * var_b);
             if (denom <= 2.2204460492503131e-16) {
                 bool same = true;
-                for (int i = 0; i < dim; ++i) same = same && (q[i] == __ldg(c + i));
+                for (int i = 0; i < dim; ++i) same = same && (q[i] == ldrow(c + i));
                 return same ? 0.0f : 1.0f;
             }
             const double cov = sab - sa * sb / n;
             return (float)(1.0 - clamp_f64(cov / denom, -1.0, 1.0));
         } else if constexpr (METRIC == LB_HELLINGER) {
             for (int i = tail0; i < dim; ++i) {
-                const float b = __ldg(c + i);
+                const float b = ldrow(c + i);
                 if (invalid_mass_value(b)) s[2] = 1.0;
                 s[0] = s[0] + (double)b;
                 s[1] = s[1] + sqrt((double)q[i] * (double)b);
@@ -208,7 +210,7 @@ struct Scan2Op {
             if (sa == 0.0 || sb == 0.0) return sa == sb ? 0.0f : INFINITY;
             const double inv_a = pc.qb, inv_b = pc.rb;
             for (int i = tail0; i < dim - 1; ++i) {
-                s[0] = s[0] + ((double)q[i] * inv_a - (double)__ldg(c + i) * inv_b);
+                s[0] = s[0] + ((double)q[i] * inv_a - (double)ldrow(c + i) * inv_b);
                 s[1] = s[1] + fabs(s[0]);
             }
             return (float)s[1];
@@ -225,7 +227,7 @@ struct Scan2Op {
             }
             float mix = lane_sum8(s);
             for (int i = tail0; i < dim; ++i) {
-                const float sm = q[i] + __ldg(c + i) * pc.r_inv;
+                const float sm = q[i] + ldrow(c + i) * pc.r_inv;
                 if (sm > 0.0f) mix = mix + sm * logf(sm);
             }
             const float divergence = fmaxf(kLn2 + 0.5f * (pc.q_ent + pc.r_ent - mix), 0.0f);
@@ -240,21 +242,21 @@ struct Scan2Op {
                 for (int i = 0; i < 8; ++i) s[i] = s[i] + s[8 + i];
             }
             float out = hsum8(s);
-            for (int i = tail0; i < dim; ++i) out = out + q[i] * __ldg(c + i);
+            for (int i = tail0; i < dim; ++i) out = out + q[i] * ldrow(c + i);
             return out;
         } else if constexpr (METRIC == LB_L2) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) s[i] = s[i] + s[8 + i];
             float sum = hsum8(s);
             for (int i = tail0; i < dim; ++i) {
-                const float diff = q[i] - __ldg(c + i);
+                const float diff = q[i] - ldrow(c + i);
                 sum = sum + diff * diff;
             }
             return sum;
         } else if constexpr (METRIC == LB_COSINE) {
             float dot = hsum8(s), nb = hsum8(s + 8), na = q_norm2;
             for (int i = tail0; i < dim; ++i) {
-                const float a = q[i], b = __ldg(c + i);
+                const float a = q[i], b = ldrow(c + i);
                 dot = dot + a * b;
                 nb = nb + b * b;
             }
@@ -263,18 +265,18 @@ struct Scan2Op {
             return 1.0f - dot / denom;
         } else if constexpr (METRIC == LB_MANHATTAN) {
             float sum = lane_sum8(s);
-            for (int i = tail0; i < dim; ++i) sum = sum + fabsf(q[i] - __ldg(c + i));
+            for (int i = tail0; i < dim; ++i) sum = sum + fabsf(q[i] - ldrow(c + i));
             return sum;
         } else if constexpr (METRIC == LB_CHEBYSHEV) {
             float m = 0.0f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) m = rust_max(m, s[i]);
-            for (int i = tail0; i < dim; ++i) m = rust_max(m, fabsf(q[i] - __ldg(c + i)));
+            for (int i = tail0; i < dim; ++i) m = rust_max(m, fabsf(q[i] - ldrow(c + i)));
             return m;
         } else if constexpr (METRIC == LB_CANBERRA) {
             float sum = lane_sum8(s);
             for (int i = tail0; i < dim; ++i) {
-                const float a = q[i], b = __ldg(c + i);
+                const float a = q[i], b = ldrow(c + i);
                 const float den = fabsf(a) + fabsf(b);
                 if (den != 0.0f) sum = sum + fabsf(a - b) / den;
             }
@@ -282,7 +284,7 @@ struct Scan2Op {
         } else {
             float num = lane_sum8(s), den = lane_sum8(s + 8);
             for (int i = tail0; i < dim; ++i) {
-                const float a = q[i], b = __ldg(c + i);
+                const float a = q[i], b = ldrow(c + i);
                 num = num + fabsf(a - b);
                 den = den + fabsf(a + b);
             }
@@ -305,7 +307,7 @@ __device__ inline float cosine_query_norm2(const float* __restrict__ q /*smem*/,
     return na;
 }
 
-template <int METRIC, bool IP2>
+template <int METRIC, bool IP2, class RT = float>
 __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
     using Op = Scan2Op<METRIC, IP2>;
     constexpr int S2_TQ = Op::kTQ;
@@ -355,14 +357,14 @@ __global__ void __launch_bounds__(S2_ROWS, 2) scan_stream_kernel(ScanArgs a) {
         uint32_t row = 0;
         if (valid) row = a.row_ids ? __ldg(a.row_ids + slot) : (uint32_t)slot;
         if (valid && !row_allowed(a.allow_bits, row)) valid = false;
-        const float* c = a.corpus + (size_t)row * dim;
+        const RT* c = corpus_rows<RT>(a) + (size_t)row * dim;
         if (a.row_ids != nullptr) {
             // gathered rows (IVF lists, id filters): neighbouring threads read unrelated rows, so nothing arrives in L2
             // ahead of the one-chunk-ahead loads and every 32-byte piece costs a DRAM round trip (measured: 2.3 us per
             // chunk).  Ask L2 for the whole row now — the next block's row, and on the first block this one's too.
             auto prefetch_row = [&](uint32_t r) {
-                const char* p = reinterpret_cast<const char*>(a.corpus + (size_t)r * dim);
-                for (int off = 0; off < dim * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+                const char* p = reinterpret_cast<const char*>(corpus_rows<RT>(a) + (size_t)r * dim);
+                for (int off = 0; off < dim * (int)sizeof(RT); off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
             };
             if (blk == part_begin && valid) prefetch_row(row);
             const uint64_t nslot = slot + S2_ROWS;
@@ -463,8 +465,20 @@ constexpr int S3_NSTAGES = 6;                  // 192 KiB in flight per SM: the 
 constexpr int S3_STAGE_BYTES = S2_ROWS * 128;  // 32 KiB: 256 rows x 32 floats
 constexpr int S3_TQ = 4;                       // queries per tile (this kernel serves batches of <= 4)
 
-template <int METRIC, bool IP2>
-__global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __grid_constant__ CUtensorMap tmap, ScanArgs a) {
+// binary16 rows carry twice the arithmetic per staged byte: two CTAs per SM (16 warps), each with a ring of two stages (the
+// query tile, candidate buffer and lists of a CTA take ~21 KiB, so three stages would not leave room for two CTAs), overlap
+// one CTA's arithmetic with the other's loads.
+template <class RT>
+struct S3Cfg {
+    static constexpr int kStages = std::is_same<RT, float>::value ? S3_NSTAGES : 2;
+    static constexpr int kCtasPerSm = std::is_same<RT, float>::value ? 1 : 2;
+};
+
+template <int METRIC, bool IP2, class RT = float>
+__global__ void __launch_bounds__(S2_ROWS, S3Cfg<RT>::kCtasPerSm) scan_stream_tma_kernel(const __grid_constant__ CUtensorMap tmap, ScanArgs a) {
+    constexpr int EPB = 128 / (int)sizeof(RT);   // elements per 128-byte stage row: 32 floats or 64 halves
+    constexpr int CPB = EPB / 8;                 // 8-element chunks per stage row
+    constexpr int NST = S3Cfg<RT>::kStages;
     using Op = Scan2Op<METRIC, IP2>;
     constexpr int S2_TQ = Op::kTQ < S3_TQ ? Op::kTQ : S3_TQ;
     constexpr bool ASC = METRIC != LB_IP;
@@ -472,7 +486,7 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
     const uint32_t smem_base = (tc::smem_u32(smem_s3) + 1023u) & ~1023u;
     unsigned char* smem = smem_s3 + (smem_base - tc::smem_u32(smem_s3));
     const int dim = a.dim, dim_pad = (dim + 3) & ~3;
-    uint64_t* cand = reinterpret_cast<uint64_t*>(smem + S3_NSTAGES * S3_STAGE_BYTES);   // [TQ][256]
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem + NST * S3_STAGE_BYTES);   // [TQ][256]
     float* sq = reinterpret_cast<float*>(cand + S2_TQ * S2_ROWS);                       // [TQ][dim_pad]
     uint64_t* sthr = reinterpret_cast<uint64_t*>(sq + S2_TQ * dim_pad);                 // [TQ]
     uint32_t* scnt = reinterpret_cast<uint32_t*>(sthr + S2_TQ);                         // [TQ]
@@ -481,12 +495,12 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
     uint64_t* bars = reinterpret_cast<uint64_t*>(sqc + 2 * S2_TQ);                      // full[NSTAGES]
     const uint32_t full0 = tc::smem_u32(bars);
     SmemLists sl;
-    sl.keys = bars + S3_NSTAGES;                                                        // [TQ][k] when a.smem_lists
+    sl.keys = bars + NST;                                                        // [TQ][k] when a.smem_lists
     sl.counts = reinterpret_cast<uint32_t*>(sl.keys + (size_t)S2_TQ * a.k);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int part = blockIdx.x;
     const int chunks = dim >> 3;                 // whole 8-float chunks (the rest is the scalar tail)
-    const int n_cc = (dim + 31) >> 5;            // column chunks of 32 floats per row block
+    const int n_cc = (dim + EPB - 1) / EPB;      // column chunks of 128 bytes per row block
     const uint64_t part_begin = (uint64_t)part * a.rows_per_part;
     uint64_t part_end = part_begin + a.rows_per_part;
     if (part_end > a.n_rows) part_end = a.n_rows;
@@ -497,16 +511,16 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
     const uint64_t n_boxes = (uint64_t)n_blocks * n_tiles * n_cc;
 
     if (tid == 0) {
-        for (int s = 0; s < S3_NSTAGES; ++s) tc::mbar_init(full0 + 8u * s, 1);
+        for (int s = 0; s < NST; ++s) tc::mbar_init(full0 + 8u * s, 1);
         tc::fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
     auto issue = [&](uint64_t box) {  // thread 0 only
         const uint32_t blk = (uint32_t)(box / ((uint64_t)n_tiles * n_cc));
         const int cc = (int)(box % n_cc);
-        const uint32_t stage = (uint32_t)(box % S3_NSTAGES);
+        const uint32_t stage = (uint32_t)(box % NST);
         tc::mbar_arrive_expect_tx(full0 + 8u * stage, S3_STAGE_BYTES);
-        tc::tma_load_2d(smem_base + stage * S3_STAGE_BYTES, &tmap, cc * 32, (int)(part_begin + (uint64_t)blk * S2_ROWS), full0 + 8u * stage);
+        tc::tma_load_2d(smem_base + stage * S3_STAGE_BYTES, &tmap, cc * EPB, (int)(part_begin + (uint64_t)blk * S2_ROWS), full0 + 8u * stage);
     };
     auto load_tile = [&](int q0, int tq) {
         for (int i = tid; i < tq * dim; i += S2_ROWS) {
@@ -519,7 +533,7 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
     };
     __syncthreads();
     if (tid == 0)
-        for (uint64_t b = 0; b < (uint64_t)S3_NSTAGES && b < n_boxes; ++b) issue(b);
+        for (uint64_t b = 0; b < (uint64_t)NST && b < n_boxes; ++b) issue(b);
     if (single_tile) {
         load_tile(0, a.nq);
         if (tid < a.nq) {
@@ -536,7 +550,7 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
         bool valid = slot < part_end;
         const uint32_t row = (uint32_t)slot;
         if (valid && !row_allowed(a.allow_bits, row)) valid = false;
-        const float* c = a.corpus + (size_t)row * dim;
+        const RT* c = corpus_rows<RT>(a) + (size_t)row * dim;
         const bool two_acc = METRIC == LB_IP && (a.ip_single || (valid && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row)));
         for (int q0 = 0; q0 < a.nq; q0 += S2_TQ) {
             const int tq = min(S2_TQ, a.nq - q0);
@@ -567,32 +581,43 @@ __global__ void __launch_bounds__(S2_ROWS, 1) scan_stream_tma_kernel(const __gri
                 }
             }
             for (int cc = 0; cc < n_cc; ++cc, ++box) {
-                const uint32_t stage = (uint32_t)(box % S3_NSTAGES), phase = (uint32_t)((box / S3_NSTAGES) & 1u);
+                const uint32_t stage = (uint32_t)(box % NST), phase = (uint32_t)((box / NST) & 1u);
                 while (!tc::mbar_try_wait(full0 + 8u * stage, phase)) {
                 }
-                // my 32 floats of this column chunk
-                Vec8 cv[4];
+                // my 128 bytes of this column chunk: 8 pieces of 16 bytes, piece p at p ^ (row & 7), kept raw (binary16 rows
+                // are decoded chunk by chunk below: half the registers of holding 64 floats)
+                uint4 raw[8];
                 {
-                    const float4* rowp = reinterpret_cast<const float4*>(smem + stage * S3_STAGE_BYTES + tid * 128);
+                    const uint4* rowp = reinterpret_cast<const uint4*>(smem + stage * S3_STAGE_BYTES + tid * 128);
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) {
-                        const float4 x = rowp[p ^ (tid & 7)];
-                        cv[p >> 1].v[(p & 1) * 4 + 0] = x.x; cv[p >> 1].v[(p & 1) * 4 + 1] = x.y;
-                        cv[p >> 1].v[(p & 1) * 4 + 2] = x.z; cv[p >> 1].v[(p & 1) * 4 + 3] = x.w;
-                    }
+                    for (int p = 0; p < 8; ++p) raw[p] = rowp[p ^ (tid & 7)];
                 }
                 __syncthreads();  // every thread holds its piece: the stage can be refilled
-                if (tid == 0 && box + S3_NSTAGES < n_boxes) issue(box + S3_NSTAGES);
+                if (tid == 0 && box + NST < n_boxes) issue(box + NST);
                 if (valid) {
 #pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) {
-                        const int j = cc * 4 + sub;
+                    for (int sub = 0; sub < CPB; ++sub) {
+                        const int j = cc * CPB + sub;
+                        Vec8 cvs;
+                        if constexpr (std::is_same<RT, float>::value) {
+                            const uint4 lo = raw[2 * sub], hi = raw[2 * sub + 1];
+                            cvs.v[0] = __uint_as_float(lo.x); cvs.v[1] = __uint_as_float(lo.y); cvs.v[2] = __uint_as_float(lo.z); cvs.v[3] = __uint_as_float(lo.w);
+                            cvs.v[4] = __uint_as_float(hi.x); cvs.v[5] = __uint_as_float(hi.y); cvs.v[6] = __uint_as_float(hi.z); cvs.v[7] = __uint_as_float(hi.w);
+                        } else {
+                            const uint32_t w[4] = {raw[sub].x, raw[sub].y, raw[sub].z, raw[sub].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                                cvs.v[2 * i] = f.x;
+                                cvs.v[2 * i + 1] = f.y;
+                            }
+                        }
                         if (j < chunks) {
 #pragma unroll
                             for (int t = 0; t < S2_TQ; ++t) {
                                 if (t < tq) {
                                     const Vec8 qv = load8<false>(sq + t * dim_pad + 8 * j, true);  // broadcast
-                                    Op::step(st[t], qv, cv[sub], j, two_acc, dim, pc[t]);
+                                    Op::step(st[t], qv, cvs, j, two_acc, dim, pc[t]);
                                 }
                             }
                         }

@@ -1,0 +1,104 @@
+// lb_scan_dense.cuh — launches of the dense exact scans (lb_scan.cuh, lb_scan2.cuh) for one row type: f32 rows, or the
+// binary16 rows of a float16 index (the same kernels instantiated with RT = __half; every load decodes, exactly).
+// Each row type is instantiated in its own translation unit (lb_scan_plan.cu, lb_scan_f16.cu) to keep the builds short.
+#pragma once
+#include "lb_host.cuh"
+#include "lb_metrics.cuh"
+#include "lb_scan.cuh"
+#include "lb_scan2.cuh"
+
+namespace lb {
+
+struct ScanPlan {
+    int P;
+    uint32_t rows_per_part;
+};
+
+template <class RT>
+int dense_scan_launch(lb_index* idx, const ScanRequest& r, ScanArgs& a, const ScanPlan& sp, bool s2_metric, bool tma_rows) {
+    if (s2_metric && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+               (size_t)8 * ((r.dim + 3) & ~3) * 4 + 8 * S2_ROWS * 8 + 256 <= 200 * 1024) {
+        // streaming scan: the row is read once per query tile (lb_scan2.cuh)
+        const int dim_pad = (r.dim + 3) & ~3;
+        const bool ip2 = r.ip_single || r.n_small > 0;
+        // contiguous rows of a 16-byte-multiple width go through TMA-staged shared memory
+        // (measured on 10M x 768: 4.55 TB/s against 3.74 TB/s at one query, 8.8 against 9.4 ms at four; from eight
+        // queries on the pass is bound by the shared-memory reads of the queries and the direct version is as fast)
+        const bool use_tma = tma_rows;
+        if (use_tma) {
+            PFN_encodeTiled enc = get_encode_tiled();
+            if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+            CUtensorMap tmap;
+            cuuint64_t gdim[2] = {(cuuint64_t)r.dim, (cuuint64_t)r.n_rows};
+            cuuint64_t gstride[1] = {(cuuint64_t)r.dim * sizeof(RT)};
+            cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(RT)), (cuuint32_t)S2_ROWS};
+            cuuint32_t estr[2] = {1, 1};
+            const bool half_rows = !std::is_same<RT, float>::value;
+            void* base = half_rows ? (void*)const_cast<__half*>(r.corpus_h) : (void*)const_cast<float*>(r.corpus);
+            CUresult cr = enc(&tmap, half_rows ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled (f32 rows) failed with CUresult " + std::to_string((int)cr));
+#define LB_LAUNCH_S3(M, IP2V)                                                                                                 \
+    do {                                                                                                                      \
+        constexpr int tqv = Scan2Op<M, IP2V>::kTQ < S3_TQ ? Scan2Op<M, IP2V>::kTQ : S3_TQ;                                    \
+        a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                                   \
+        const size_t smem = (size_t)S3Cfg<RT>::kStages * S3_STAGE_BYTES + (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 +  \
+                            (size_t)tqv * 32 + 128 + 1024 + (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);         \
+        LB_CUDA_TRY(ensure_dynamic_smem(scan_stream_tma_kernel<M, IP2V, RT>, (int)smem)); \
+        scan_stream_tma_kernel<M, IP2V, RT><<<sp.P, S2_ROWS, smem, idx->stream>>>(tmap, a);                                       \
+    } while (0)
+            switch (r.metric) {
+                case LB_IP: if (ip2) LB_LAUNCH_S3(LB_IP, true); else LB_LAUNCH_S3(LB_IP, false); break;
+                case LB_L2: LB_LAUNCH_S3(LB_L2, false); break;
+                case LB_COSINE: LB_LAUNCH_S3(LB_COSINE, false); break;
+                case LB_MANHATTAN: LB_LAUNCH_S3(LB_MANHATTAN, false); break;
+                case LB_CHEBYSHEV: LB_LAUNCH_S3(LB_CHEBYSHEV, false); break;
+                case LB_CANBERRA: LB_LAUNCH_S3(LB_CANBERRA, false); break;
+                default: LB_LAUNCH_S3(LB_BRAY_CURTIS, false); break;
+            }
+#undef LB_LAUNCH_S3
+        } else {
+#define LB_LAUNCH_S2(M, IP2V)                                                                                             \
+    do {                                                                                                                  \
+        constexpr int tqv = Scan2Op<M, IP2V>::kTQ;                                                                        \
+        a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                               \
+        const size_t smem = (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 + (size_t)tqv * 32 + 64 +                \
+                            (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);                                     \
+        LB_CUDA_TRY(ensure_dynamic_smem(scan_stream_kernel<M, IP2V, RT>, (int)smem)); \
+        scan_stream_kernel<M, IP2V, RT><<<sp.P, S2_ROWS, smem, idx->stream>>>(a);                                             \
+    } while (0)
+        switch (r.metric) {
+            case LB_IP: if (ip2) LB_LAUNCH_S2(LB_IP, true); else LB_LAUNCH_S2(LB_IP, false); break;
+            case LB_L2: LB_LAUNCH_S2(LB_L2, false); break;
+            case LB_COSINE: LB_LAUNCH_S2(LB_COSINE, false); break;
+            case LB_MANHATTAN: LB_LAUNCH_S2(LB_MANHATTAN, false); break;
+            case LB_CHEBYSHEV: LB_LAUNCH_S2(LB_CHEBYSHEV, false); break;
+            case LB_CANBERRA: LB_LAUNCH_S2(LB_CANBERRA, false); break;
+            case LB_CORRELATION: LB_LAUNCH_S2(LB_CORRELATION, false); break;
+            case LB_HELLINGER: LB_LAUNCH_S2(LB_HELLINGER, false); break;
+            case LB_WASSERSTEIN: LB_LAUNCH_S2(LB_WASSERSTEIN, false); break;
+            case LB_JENSEN_SHANNON: LB_LAUNCH_S2(LB_JENSEN_SHANNON, false); break;
+            default: LB_LAUNCH_S2(LB_BRAY_CURTIS, false); break;
+        }
+        }
+#undef LB_LAUNCH_S2
+    } else {
+        int dim_pad = (r.dim + 3) & ~3;
+        size_t smem = (size_t)SCAN_TQ * SCAN_THREADS * 8 + (size_t)SCAN_TQ * dim_pad * 4;
+        if (smem > 200 * 1024) return fail(LB_UNSUPPORTED, "dimension above 2560 is not supported by the exact scan");
+        if (metric_ascending(r.metric)) {
+            LB_CUDA_TRY(ensure_dynamic_smem(scan_exact_kernel<true, RT>, (int)smem));
+            scan_exact_kernel<true, RT><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);
+        } else {
+            LB_CUDA_TRY(ensure_dynamic_smem(scan_exact_kernel<false, RT>, (int)smem));
+            scan_exact_kernel<false, RT><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);
+        }
+    }
+    return LB_OK;
+}
+
+extern template int dense_scan_launch<float>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool);
+extern template int dense_scan_launch<__half>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool);
+
+}  // namespace lb

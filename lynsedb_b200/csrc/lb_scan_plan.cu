@@ -1,19 +1,14 @@
 // lb_scan_plan.cu — the exact CUDA-core scans (lb_scan.cuh, lb_scan2.cuh, lb_packed.cuh): plan + launches + merge.
-#include "lb_host.cuh"
-#include "lb_metrics.cuh"
-#include "lb_scan.cuh"
+#include "lb_scan_dense.cuh"
 #include "lb_packed.cuh"
-#include "lb_scan2.cuh"
 
 using namespace lb;
 
 namespace lb {
 
+template int dense_scan_launch<float>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool);
+
 // ---- exact scan plan ------------------------------------------------------------------------------------------
-struct ScanPlan {
-    int P;
-    uint32_t rows_per_part;
-};
 static ScanPlan plan_scan(const lb_index* idx, uint64_t n_rows, int nq, int k, int ctas_per_sm = 2) {
     uint64_t P = std::min<uint64_t>(ceil_div(n_rows, SCAN_THREADS), (uint64_t)idx->sm_count * ctas_per_sm);
     // bound the candidate lists to 512 MiB
@@ -34,10 +29,10 @@ int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
     // (the f64 metrics are bound by arithmetic latency, not by the load pattern: two resident CTAs per SM beat the
     // one-CTA TMA ring for them — Hellinger 2.1 against 1.3 TB/s, Wasserstein 3.4 against 2.4 at one query)
     const bool tma_f32 = !r.words && !r.f16_rows && s2_metric && !scan2_f64(r.metric) && r.metric != LB_JENSEN_SHANNON && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
-                         r.row_ids == nullptr && (r.dim & 3) == 0 && r.dim >= 8 && r.n_rows >= 4096 && r.nq <= 4 &&
+                         r.row_ids == nullptr && (r.dim & (r.corpus_h != nullptr ? 7 : 3)) == 0 && r.dim >= 8 && r.n_rows >= 4096 && r.nq <= 4 &&
                          tc_env_int("LYNSE_B200_SCAN_TMA", 1) != 0 &&
                          (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)S3_TQ * (S2_ROWS * 8 + ((r.dim + 3) & ~3) * 4 + 256 * 8) + 2048 <= 226 * 1024;
-    ScanPlan sp = plan_scan(idx, r.n_rows, r.nq, r.k, tma_f32 ? 1 : 2);
+    ScanPlan sp = plan_scan(idx, r.n_rows, r.nq, r.k, (tma_f32 && r.corpus_h == nullptr) ? 1 : 2);
     size_t nl = (size_t)sp.P * r.nq;
     LB_TRY(idx->w_lists.ensure(nl * r.k * 8));
     LB_TRY(idx->w_counts.ensure(nl * 4));
@@ -45,6 +40,8 @@ int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
     LB_CUDA_TRY(cudaMemsetAsync(idx->w_counts.p, 0, nl * 4, idx->stream));
     ScanArgs a{};
     a.corpus = r.corpus;
+    a.corpus_h = r.corpus_h;
+    const bool f16 = r.corpus_h != nullptr;   // binary16 rows: the kernels are instantiated with RT = __half
     a.words = r.words;
     a.n_rows = (uint32_t)r.n_rows;
     a.dim = r.dim;
@@ -111,82 +108,10 @@ int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
             default: LB_LAUNCH_PACKED(0); break;
         }
 #undef LB_LAUNCH_PACKED
-    } else if (s2_metric && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
-               (size_t)8 * ((r.dim + 3) & ~3) * 4 + 8 * S2_ROWS * 8 + 256 <= 200 * 1024) {
-        // streaming scan: the row is read once per query tile (lb_scan2.cuh)
-        const int dim_pad = (r.dim + 3) & ~3;
-        const bool ip2 = r.ip_single || r.n_small > 0;
-        // contiguous rows of a 16-byte-multiple width go through TMA-staged shared memory
-        // (measured on 10M x 768: 4.55 TB/s against 3.74 TB/s at one query, 8.8 against 9.4 ms at four; from eight
-        // queries on the pass is bound by the shared-memory reads of the queries and the direct version is as fast)
-        const bool use_tma = tma_f32;
-        if (use_tma) {
-            PFN_encodeTiled enc = get_encode_tiled();
-            if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-            CUtensorMap tmap;
-            cuuint64_t gdim[2] = {(cuuint64_t)r.dim, (cuuint64_t)r.n_rows};
-            cuuint64_t gstride[1] = {(cuuint64_t)r.dim * 4};
-            cuuint32_t box[2] = {32, (cuuint32_t)S2_ROWS};
-            cuuint32_t estr[2] = {1, 1};
-            CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(r.corpus), gdim, gstride, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (cr != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled (f32 rows) failed with CUresult " + std::to_string((int)cr));
-#define LB_LAUNCH_S3(M, IP2V)                                                                                                 \
-    do {                                                                                                                      \
-        constexpr int tqv = Scan2Op<M, IP2V>::kTQ < S3_TQ ? Scan2Op<M, IP2V>::kTQ : S3_TQ;                                    \
-        a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                                   \
-        const size_t smem = (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 +      \
-                            (size_t)tqv * 32 + 128 + 1024 + (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);         \
-        LB_CUDA_TRY(ensure_dynamic_smem(scan_stream_tma_kernel<M, IP2V>, (int)smem)); \
-        scan_stream_tma_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(tmap, a);                                       \
-    } while (0)
-            switch (r.metric) {
-                case LB_IP: if (ip2) LB_LAUNCH_S3(LB_IP, true); else LB_LAUNCH_S3(LB_IP, false); break;
-                case LB_L2: LB_LAUNCH_S3(LB_L2, false); break;
-                case LB_COSINE: LB_LAUNCH_S3(LB_COSINE, false); break;
-                case LB_MANHATTAN: LB_LAUNCH_S3(LB_MANHATTAN, false); break;
-                case LB_CHEBYSHEV: LB_LAUNCH_S3(LB_CHEBYSHEV, false); break;
-                case LB_CANBERRA: LB_LAUNCH_S3(LB_CANBERRA, false); break;
-                default: LB_LAUNCH_S3(LB_BRAY_CURTIS, false); break;
-            }
-#undef LB_LAUNCH_S3
-        } else {
-#define LB_LAUNCH_S2(M, IP2V)                                                                                             \
-    do {                                                                                                                  \
-        constexpr int tqv = Scan2Op<M, IP2V>::kTQ;                                                                        \
-        a.smem_lists = (r.nq <= tqv && r.k <= 256) ? 1 : 0;                                                               \
-        const size_t smem = (size_t)tqv * S2_ROWS * 8 + (size_t)tqv * dim_pad * 4 + (size_t)tqv * 32 + 64 +                \
-                            (a.smem_lists ? (size_t)tqv * r.k * 8 + tqv * 4 + 16 : 0);                                     \
-        LB_CUDA_TRY(ensure_dynamic_smem(scan_stream_kernel<M, IP2V>, (int)smem)); \
-        scan_stream_kernel<M, IP2V><<<sp.P, S2_ROWS, smem, idx->stream>>>(a);                                             \
-    } while (0)
-        switch (r.metric) {
-            case LB_IP: if (ip2) LB_LAUNCH_S2(LB_IP, true); else LB_LAUNCH_S2(LB_IP, false); break;
-            case LB_L2: LB_LAUNCH_S2(LB_L2, false); break;
-            case LB_COSINE: LB_LAUNCH_S2(LB_COSINE, false); break;
-            case LB_MANHATTAN: LB_LAUNCH_S2(LB_MANHATTAN, false); break;
-            case LB_CHEBYSHEV: LB_LAUNCH_S2(LB_CHEBYSHEV, false); break;
-            case LB_CANBERRA: LB_LAUNCH_S2(LB_CANBERRA, false); break;
-            case LB_CORRELATION: LB_LAUNCH_S2(LB_CORRELATION, false); break;
-            case LB_HELLINGER: LB_LAUNCH_S2(LB_HELLINGER, false); break;
-            case LB_WASSERSTEIN: LB_LAUNCH_S2(LB_WASSERSTEIN, false); break;
-            case LB_JENSEN_SHANNON: LB_LAUNCH_S2(LB_JENSEN_SHANNON, false); break;
-            default: LB_LAUNCH_S2(LB_BRAY_CURTIS, false); break;
-        }
-        }
-#undef LB_LAUNCH_S2
+    } else if (f16) {
+        LB_TRY(dense_scan_launch<__half>(idx, r, a, sp, s2_metric, tma_f32));
     } else {
-        int dim_pad = (r.dim + 3) & ~3;
-        size_t smem = (size_t)SCAN_TQ * SCAN_THREADS * 8 + (size_t)SCAN_TQ * dim_pad * 4;
-        if (smem > 200 * 1024) return fail(LB_UNSUPPORTED, "dimension above 2560 is not supported by the exact scan");
-        if (metric_ascending(r.metric)) {
-            LB_CUDA_TRY(ensure_dynamic_smem(scan_exact_kernel<true>, (int)smem));
-            scan_exact_kernel<true><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);
-        } else {
-            LB_CUDA_TRY(ensure_dynamic_smem(scan_exact_kernel<false>, (int)smem));
-            scan_exact_kernel<false><<<sp.P, SCAN_THREADS, smem, idx->stream>>>(a);
-        }
+        LB_TRY(dense_scan_launch<float>(idx, r, a, sp, s2_metric, tma_f32));
     }
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);

@@ -667,15 +667,16 @@ __device__ __forceinline__ float warp_sum(float x) {
 }
 // One warp per row, first pass: |c|, the element range of c' and non-finite rows (everything the 8-bit quantisation needs
 // to know before it can write a byte).
-static __global__ void shadow_range_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int kind,
-                                           ShadowStats* __restrict__ st) {
+template <class RT>
+__global__ void shadow_range_kernel(const RT* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int kind,
+                                    ShadowStats* __restrict__ st) {
     const uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= first_row + n) return;
-    const float* r = rows + row * dim;
+    const RT* r = rows + row * dim;
     float ss = 0.0f, mn = INFINITY, mx = -INFINITY;
     for (int d = lane; d < dim; d += 32) {
-        const float x = __ldg(r + d);
+        const float x = ldrow(r + d);
         ss = fmaf(x, x, ss);
         mn = fminf(mn, x);
         mx = fmaxf(mx, x);
@@ -693,7 +694,7 @@ static __global__ void shadow_range_kernel(const float* __restrict__ rows, uint6
     }
     float e16 = 0.0f;
     for (int d = lane; d < dim; d += 32) {
-        const float x = __ldg(r + d) * scale;
+        const float x = ldrow(r + d) * scale;
         const float de = x - __bfloat162float(__float2bfloat16_rn(x));
         e16 = fmaf(de, de, e16);
     }
@@ -716,17 +717,17 @@ static __global__ void shadow_range_kernel(const float* __restrict__ rows, uint6
 //                  forms 2 q.c - |c|^2 against a query of [2q, -1, -1, -1]) or, when side != null, as the f32 side value
 //                  the epilogue subtracts (CM_F32_BIAS: rows whose padded length has no room for the columns)
 // OPERAND_BF16: c~ = bf16(c').  OPERAND_U8: c~ = zero + scale * u8, u8 = clamp(rint((c' - zero) / scale), 0, 255).
-template <int OPK>
-__global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int row_bytes, int kind,
+template <int OPK, class RT>
+__global__ void build_shadow_kernel(const RT* __restrict__ rows, uint64_t first_row, uint64_t n, int dim, int row_bytes, int kind,
                                     unsigned char* __restrict__ shadow, float* __restrict__ side, ShadowStats* __restrict__ st,
                                     float q_scale, float q_zero) {
     const uint64_t row = first_row + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= first_row + n) return;
-    const float* r = rows + row * dim;
+    const RT* r = rows + row * dim;
     float ss = 0.0f;
     for (int d = lane; d < dim; d += 32) {
-        const float x = __ldg(r + d);
+        const float x = ldrow(r + d);
         ss = fmaf(x, x, ss);
     }
     ss = warp_sum(ss);
@@ -742,7 +743,7 @@ __global__ void build_shadow_kernel(const float* __restrict__ rows, uint64_t fir
 #pragma unroll
         for (int e = 0; e < EPC; ++e) {
             const int d = chunk * EPC + e;
-            const float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+            const float x = d < dim ? ldrow(r + d) * scale : 0.0f;
             float held;
             if (OPK == OPERAND_BF16) {
                 __nv_bfloat16 b = __float2bfloat16_rn(x);
@@ -853,7 +854,7 @@ static __global__ void prepare_queries_kernel(const float* __restrict__ queries,
     const float* r = queries + (size_t)q * dim;
     float ss = 0.0f;
     for (int d = lane; d < dim; d += 32) {
-        const float x = __ldg(r + d);
+        const float x = ldrow(r + d);
         ss = fmaf(x, x, ss);
     }
     ss = warp_sum(ss);
@@ -862,7 +863,7 @@ static __global__ void prepare_queries_kernel(const float* __restrict__ queries,
     if (kind == SHADOW_COSINE) scale = norm > 0.0f ? 1.0f / norm : 0.0f;
     float err = 0.0f, hss = 0.0f;
     for (int d = lane; d < Dp; d += 32) {
-        const float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+        const float x = d < dim ? ldrow(r + d) * scale : 0.0f;
         const __nv_bfloat16 b = __float2bfloat16_rn(x);
         const float held = __bfloat162float(b);
         out[d] = kind == SHADOW_L2 ? __float2bfloat16_rn((norm_cols && d >= dim && d < dim + 3) ? -1.0f : 2.0f * held) : b;
@@ -892,7 +893,7 @@ static __global__ void query_range_kernel(const float* __restrict__ queries, int
     const float* r = queries + (size_t)q * dim;
     float ss = 0.0f, mn = INFINITY, mx = -INFINITY;
     for (int d = lane; d < dim; d += 32) {
-        const float x = __ldg(r + d);
+        const float x = ldrow(r + d);
         ss = fmaf(x, x, ss);
         mn = fminf(mn, x);
         mx = fmaxf(mx, x);
@@ -929,7 +930,7 @@ static __global__ void quantise_queries_kernel(const float* __restrict__ queries
     const float* r = queries + (size_t)q * dim;
     float ss = 0.0f;
     for (int d = lane; d < dim; d += 32) {
-        const float x = __ldg(r + d);
+        const float x = ldrow(r + d);
         ss = fmaf(x, x, ss);
     }
     ss = warp_sum(ss);
@@ -946,7 +947,7 @@ static __global__ void quantise_queries_kernel(const float* __restrict__ queries
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int d = d0 + e;
-            const float x = d < dim ? __ldg(r + d) * scale : 0.0f;
+            const float x = d < dim ? ldrow(r + d) * scale : 0.0f;
             int u = __float2int_rn(x * inv);
             u = is_signed ? min(max(u, -127), 127) : min(max(u, 0), 255);
             const float held = s_q * (float)u;
@@ -1007,7 +1008,7 @@ struct FinArgs {
     int int_key;              // keys are s32 (8-bit operands) instead of f32
     int M1;                   // pow2 >= number of candidates read (<= 4096)
     int R;                    // rescore budget, pow2 <= 1024, >= k
-    const float* corpus;
+    const void* corpus;       // f32 or binary16 rows (finalize_kernel's RT)
     int dim;
     const float* queries;     // original f32 queries [nq][dim]
     const QStat* qstat;       // [nq]
@@ -1035,7 +1036,19 @@ __device__ __forceinline__ float hsum8_shfl(float a) {   // simd.rs:1427-1436 ov
     a = a + __shfl_xor_sync(0xffffffffu, a, 1);           // t0 = s0 + s1, t2 = s2 + s3
     return a + __shfl_xor_sync(0xffffffffu, a, 2);        // t0 + t2
 }
-__device__ __forceinline__ float rescore_row_lanes(int metric, bool two_acc_ip, const float* __restrict__ sq, const float* __restrict__ c,
+// the row's 8 threads fetch its columns [col0, col0 + ncol) into rowbuf: 128 contiguous bytes per step
+__device__ __forceinline__ void stage_row(float* rowbuf, const float* __restrict__ c, int col0, int ncol, int sub) {
+    for (int x = sub * 4; x < ncol; x += 32) *reinterpret_cast<float4*>(rowbuf + x) = __ldg(reinterpret_cast<const float4*>(c + col0 + x));
+}
+__device__ __forceinline__ void stage_row(float* rowbuf, const __half* __restrict__ c, int col0, int ncol, int sub) {
+    for (int x = sub * 8; x < ncol; x += 64) {
+        const Vec8 v = load8<true>(c + col0 + x, true);
+        *reinterpret_cast<float4*>(rowbuf + x) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+        *reinterpret_cast<float4*>(rowbuf + x + 4) = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    }
+}
+template <class CP>
+__device__ __forceinline__ float rescore_row_lanes(int metric, bool two_acc_ip, const float* __restrict__ sq, CP c,
                                                    int dim, float* rowbuf /* this row's FIN_COLS floats */, bool row_ok, int lane) {
     const int i = lane & 7, sub = lane & 7;
     const int chunks = dim >> 3;
@@ -1043,9 +1056,7 @@ __device__ __forceinline__ float rescore_row_lanes(int metric, bool two_acc_ip, 
     for (int col0 = 0; col0 < chunks * 8; col0 += FIN_COLS) {
         const int ncol = min(FIN_COLS, chunks * 8 - col0);
         __syncwarp();
-        // the row's 8 threads fetch its columns [col0, col0 + ncol): 8 x 16 B = 128 contiguous bytes per step
-        if (row_ok)
-            for (int x = sub * 4; x < ncol; x += 32) *reinterpret_cast<float4*>(rowbuf + x) = __ldg(reinterpret_cast<const float4*>(c + col0 + x));
+        if (row_ok) stage_row(rowbuf, c, col0, ncol, sub);
         __syncwarp();
         if (row_ok) {
             const int j0 = col0 >> 3, nj = ncol >> 3;
@@ -1072,20 +1083,20 @@ __device__ __forceinline__ float rescore_row_lanes(int metric, bool two_acc_ip, 
     if (metric == LB_IP) {
         if (two_acc_ip) a0 = a0 + a1;
         float out = hsum8_shfl(a0);
-        for (int x = t0; x < dim; ++x) out = out + sq[x] * __ldg(c + (row_ok ? x : 0));
+        for (int x = t0; x < dim; ++x) out = out + sq[x] * ldrow(c + (row_ok ? x : 0));
         return out;
     } else if (metric == LB_L2) {
         a0 = a0 + a1;
         float sum = hsum8_shfl(a0);
         for (int x = t0; x < dim; ++x) {
-            const float diff = sq[x] - __ldg(c + (row_ok ? x : 0));
+            const float diff = sq[x] - ldrow(c + (row_ok ? x : 0));
             sum = sum + diff * diff;
         }
         return sum;
     }
     float dot = hsum8_shfl(a0), na = hsum8_shfl(a1), nb = hsum8_shfl(a2);
     for (int x = t0; x < dim; ++x) {
-        const float qa = sq[x], cb = __ldg(c + (row_ok ? x : 0));
+        const float qa = sq[x], cb = ldrow(c + (row_ok ? x : 0));
         dot = dot + qa * cb;
         na = na + qa * qa;
         nb = nb + cb * cb;
@@ -1158,7 +1169,7 @@ __device__ __forceinline__ double key_value(uint32_t ord, bool int_key) {
     return int_key ? (double)(int)(ord ^ 0x80000000u) : (double)f32_from_orderable(ord);
 }
 
-template <bool ASC>
+template <bool ASC, class RT = float>
 __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     extern __shared__ __align__(16) unsigned char smem_fin[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_fin);            // [M1] coarse keys
@@ -1168,8 +1179,10 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     __shared__ uint32_t sh_ncand, sh_overflow;
     const int q = blockIdx.x, tid = threadIdx.x;
     const int dim = a.dim;
-    const bool vec = (dim & 3) == 0;
+    // lane-parallel rescoring needs 16-byte row pieces: dim % 4 == 0 for f32 rows, dim % 8 == 0 for binary16 rows
+    const bool vec = (dim & (std::is_same<RT, float>::value ? 3 : 7)) == 0;
     const bool ik = a.int_key != 0;
+    const RT* corpus = reinterpret_cast<const RT*>(a.corpus);
     if (tid == 0) { sh_T = 0; sh_ncand = 0; sh_overflow = 0; }
     for (int d = tid; d < dim; d += blockDim.x) sq[d] = a.queries[(size_t)q * dim + d];
     __syncthreads();
@@ -1188,7 +1201,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
             const int i = base + (tid >> 3);
             const bool row_ok = i < rn;
             const uint32_t row = row_ok ? key_row(s[i]) : 0u;
-            const float* c = a.corpus + (size_t)row * dim;
+            const RT* c = corpus + (size_t)row * dim;
             const bool two = a.metric == LB_IP && row_ok && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
             const float v = rescore_row_lanes(a.metric, two, sq, c, dim, rowbuf, row_ok, lane);
             if ((tid & 7) == 0 && i < a.R) e[i] = row_ok ? make_key<ASC>(v, row) : KEY_NONE;
@@ -1198,15 +1211,16 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
             uint64_t key = KEY_NONE;
             if (i < rn) {
                 uint32_t row = key_row(s[i]);
-                const float* c = a.corpus + (size_t)row * dim;
+                const RT* c = corpus + (size_t)row * dim;
+                const bool qvec = (dim & 3) == 0;
                 float v;
                 if (a.metric == LB_IP) {
                     bool small = a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
-                    v = small ? ip_single_order<false>(sq, c, dim, vec) : ip_batch8_order<false>(sq, c, dim, vec);
+                    v = small ? ip_single_order<false>(sq, c, dim, qvec) : ip_batch8_order<false>(sq, c, dim, qvec);
                 } else if (a.metric == LB_L2) {
-                    v = l2_squared<false>(sq, c, dim, vec);
+                    v = l2_squared<false>(sq, c, dim, qvec);
                 } else {
-                    v = cosine_distance<false>(sq, c, dim, vec);
+                    v = cosine_distance<false>(sq, c, dim, qvec);
                 }
                 key = make_key<ASC>(v, row);
             }

@@ -50,7 +50,7 @@ static int first_operand(const lb_index* idx, int kind) {
     return tc::OPERAND_U8;
 }
 bool tc_supported(lb_index* idx, int metric) {
-    if (idx->dtype != LB_F32) return false;
+    if (idx->dtype != LB_F32 && idx->dtype != LB_F16) return false;
     if (metric != LB_IP && metric != LB_COSINE && metric != LB_L2) return false;
     const int kind = shadow_kind_for(metric);
     const Shadow& sh = idx->shadow[kind];
@@ -154,10 +154,16 @@ int ensure_shadow(lb_index* idx, int kind) {
         if (sh.rows < idx->n) {
             uint64_t first = sh.rows, cnt = idx->n - first;
             tc::ShadowStats st{};
+            const bool f16 = idx->dtype == LB_F16;   // binary16 rows: the same kernels with RT = __half
+            const unsigned grid_rows = (unsigned)ceil_div(cnt, warps);
             if (sh.operand == tc::OPERAND_U8) {
                 // pass 1: element range of the new rows; a wider range than the image was quantised for rebuilds it
-                tc::shadow_range_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
-                    idx->rows.as<float>(), first, cnt, (int)idx->dim, kind, sh.stats.as<tc::ShadowStats>());
+                if (f16)
+                    tc::shadow_range_kernel<<<grid_rows, warps * 32, 0, idx->stream>>>(idx->rows.as<__half>(), first, cnt, (int)idx->dim, kind,
+                                                                                      sh.stats.as<tc::ShadowStats>());
+                else
+                    tc::shadow_range_kernel<<<grid_rows, warps * 32, 0, idx->stream>>>(idx->rows.as<float>(), first, cnt, (int)idx->dim, kind,
+                                                                                      sh.stats.as<tc::ShadowStats>());
                 LB_CUDA_TRY(cudaGetLastError());
                 LB_TRY(read_stats(idx, sh, &st));
                 if (st.nonfinite) {
@@ -175,11 +181,21 @@ int ensure_shadow(lb_index* idx, int kind) {
                     // the error statistics restart with the new quantisation
                     LB_CUDA_TRY(cudaMemsetAsync(&sh.stats.as<tc::ShadowStats>()->emax_bits, 0, 4, idx->stream));
                 }
-                tc::build_shadow_kernel<tc::OPERAND_U8><<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
-                    idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), nullptr,
-                    sh.stats.as<tc::ShadowStats>(), sh.c_scale, sh.c_zero);
+                const unsigned grid_all = (unsigned)ceil_div(cnt, warps);
+                if (f16)
+                    tc::build_shadow_kernel<tc::OPERAND_U8><<<grid_all, warps * 32, 0, idx->stream>>>(
+                        idx->rows.as<__half>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), nullptr,
+                        sh.stats.as<tc::ShadowStats>(), sh.c_scale, sh.c_zero);
+                else
+                    tc::build_shadow_kernel<tc::OPERAND_U8><<<grid_all, warps * 32, 0, idx->stream>>>(
+                        idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), nullptr,
+                        sh.stats.as<tc::ShadowStats>(), sh.c_scale, sh.c_zero);
+            } else if (f16) {
+                tc::build_shadow_kernel<tc::OPERAND_BF16><<<grid_rows, warps * 32, 0, idx->stream>>>(
+                    idx->rows.as<__half>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), sh.l2_bias ? sh.side.as<float>() : nullptr,
+                    sh.stats.as<tc::ShadowStats>(), 1.0f, 0.0f);
             } else {
-                tc::build_shadow_kernel<tc::OPERAND_BF16><<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+                tc::build_shadow_kernel<tc::OPERAND_BF16><<<grid_rows, warps * 32, 0, idx->stream>>>(
                     idx->rows.as<float>(), first, cnt, (int)idx->dim, rb, kind, sh.buf.as<unsigned char>(), sh.l2_bias ? sh.side.as<float>() : nullptr,
                     sh.stats.as<tc::ShadowStats>(), 1.0f, 0.0f);
             }
@@ -564,7 +580,7 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
 
     tc::FinArgs f{};
     fill_fin_candidates(idx, job, f);
-    f.corpus = idx->rows.as<float>();
+    f.corpus = idx->rows.p;
     f.dim = (int)idx->dim;
     f.queries = d_queries;
     f.qstat = idx->w_qnorm.as<tc::QStat>();
@@ -580,13 +596,19 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
     f.out_counts = d_counts;
     const int fin_threads = nq <= 64 ? 1024 : 256;  // few queries: few blocks, so each gets 1024 threads
     size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)(fin_threads / 8) * tc::FIN_STRIDE * 4;  // + row buffers
-    if (metric_ascending(metric)) {
-        LB_CUDA_TRY(ensure_dynamic_smem(tc::finalize_kernel<true>, (int)fsmem));
-        tc::finalize_kernel<true><<<nq, fin_threads, fsmem, idx->stream>>>(f);
+#define LB_LAUNCH_FIN(ASCV, RTV)                                                                 \
+    do {                                                                                        \
+        LB_CUDA_TRY(ensure_dynamic_smem(tc::finalize_kernel<ASCV, RTV>, (int)fsmem));           \
+        tc::finalize_kernel<ASCV, RTV><<<nq, fin_threads, fsmem, idx->stream>>>(f);             \
+    } while (0)
+    if (idx->dtype == LB_F16) {
+        if (metric_ascending(metric)) LB_LAUNCH_FIN(true, __half);
+        else LB_LAUNCH_FIN(false, __half);
     } else {
-        LB_CUDA_TRY(ensure_dynamic_smem(tc::finalize_kernel<false>, (int)fsmem));
-        tc::finalize_kernel<false><<<nq, fin_threads, fsmem, idx->stream>>>(f);
+        if (metric_ascending(metric)) LB_LAUNCH_FIN(true, float);
+        else LB_LAUNCH_FIN(false, float);
     }
+#undef LB_LAUNCH_FIN
     LB_CUDA_TRY(cudaGetLastError());
     idx->stats.kernels_launched += 2;
     idx->stats.plan_used = 1;
@@ -750,7 +772,8 @@ int tc_finish(lb_index* idx, bool* changed) {
         r.n_words = p.n_words;
         r.qwords = idx->w_sub_q.as<uint64_t>();
     } else {
-        r.corpus = idx->rows.as<float>();
+        if (idx->dtype == LB_F16) r.corpus_h = idx->rows.as<__half>();
+        else r.corpus = idx->rows.as<float>();
         r.dim = (int)idx->dim;
         r.queries = idx->w_sub_q.as<float>();
         r.small_seg = idx->small_seg.as<uint32_t>();

@@ -79,16 +79,29 @@ int refresh_small_segments(lb_index* idx) {
     return LB_OK;
 }
 
+// f32 <-> binary16 rows (LB_F16 indexes; the host hands over values that are already binary16-exact)
+static __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = __float2half_rn(in[i]);
+}
+static __global__ void f16_to_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = __half2float(in[i]);
+}
+static inline bool dense_rows(const lb_index* idx) { return idx->dtype == LB_F32 || idx->dtype == LB_F16; }
+
 // ---- side structures --------------------------------------------------------------------------------------
 static int ensure_packed(lb_index* idx) {
-    if (idx->dtype != LB_F32) return LB_OK;
+    if (!dense_rows(idx)) return LB_OK;
     if (idx->packed_rows == idx->n) return LB_OK;
     int nw = (idx->dim + 63) / 64;
     LB_TRY(idx->packed.ensure((size_t)idx->n * nw * 8, true, idx->stream));
     uint64_t first = idx->packed_rows, cnt = idx->n - first;
     const int warps = 8;
-    pack_binary_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
-        idx->rows.as<float>() + first * idx->dim, cnt, (int)idx->dim, nw, 0.5f, idx->packed.as<uint64_t>() + first * nw);
+    if (idx->dtype == LB_F16)
+        pack_binary_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+            idx->rows.as<__half>() + first * idx->dim, cnt, (int)idx->dim, nw, 0.5f, idx->packed.as<uint64_t>() + first * nw);
+    else
+        pack_binary_kernel<<<(unsigned)ceil_div(cnt, warps), warps * 32, 0, idx->stream>>>(
+            idx->rows.as<float>() + first * idx->dim, cnt, (int)idx->dim, nw, 0.5f, idx->packed.as<uint64_t>() + first * nw);
     LB_CUDA_TRY(cudaGetLastError());
     idx->packed_rows = idx->n;
     return LB_OK;
@@ -98,8 +111,12 @@ static int ensure_js_stats(lb_index* idx) {
     if (idx->js_rows == idx->n) return LB_OK;
     LB_TRY(idx->js_stats.ensure((size_t)idx->n * 8, true, idx->stream));
     uint64_t first = idx->js_rows, cnt = idx->n - first;
-    row_stats_kernel<<<(unsigned)ceil_div(cnt, 128), 128, 0, idx->stream>>>(idx->rows.as<float>() + first * idx->dim, cnt,
-                                                                            (int)idx->dim, idx->js_stats.as<float>() + 2 * first);
+    if (idx->dtype == LB_F16)
+        row_stats_kernel<<<(unsigned)ceil_div(cnt, 128), 128, 0, idx->stream>>>(idx->rows.as<__half>() + first * idx->dim, cnt,
+                                                                                (int)idx->dim, idx->js_stats.as<float>() + 2 * first);
+    else
+        row_stats_kernel<<<(unsigned)ceil_div(cnt, 128), 128, 0, idx->stream>>>(idx->rows.as<float>() + first * idx->dim, cnt,
+                                                                                (int)idx->dim, idx->js_stats.as<float>() + 2 * first);
     LB_CUDA_TRY(cudaGetLastError());
     idx->js_rows = idx->n;
     return LB_OK;
@@ -109,8 +126,12 @@ static int ensure_mass_stats(lb_index* idx) {
     if (idx->mass_rows == idx->n) return LB_OK;
     LB_TRY(idx->mass_stats.ensure((size_t)idx->n * 8, true, idx->stream));
     const uint64_t first = idx->mass_rows, cnt = idx->n - first;
-    row_mass_kernel<<<(unsigned)ceil_div(cnt, 128), 128, 0, idx->stream>>>(idx->rows.as<float>() + first * idx->dim, cnt, (int)idx->dim,
-                                                                           idx->mass_stats.as<double>() + first);
+    if (idx->dtype == LB_F16)
+        row_mass_kernel<<<(unsigned)ceil_div(cnt, 128), 128, 0, idx->stream>>>(idx->rows.as<__half>() + first * idx->dim, cnt, (int)idx->dim,
+                                                                               idx->mass_stats.as<double>() + first);
+    else
+        row_mass_kernel<<<(unsigned)ceil_div(cnt, 128), 128, 0, idx->stream>>>(idx->rows.as<float>() + first * idx->dim, cnt, (int)idx->dim,
+                                                                               idx->mass_stats.as<double>() + first);
     LB_CUDA_TRY(cudaGetLastError());
     idx->mass_rows = idx->n;
     return LB_OK;
@@ -151,7 +172,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
     int kernels = 0;
     float ms_dom = 0;
     // the tensor-core plan is a candidate; building its shadow (a no-op once built) may still rule it out (non-finite rows)
-    const bool tc_candidate = idx->dtype == LB_F32 && !metric_binary(metric) && idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT &&
+    const bool tc_candidate = dense_rows(idx) && !metric_binary(metric) && idx->plan == LB_PLAN_AUTO && idx->score_mode == SCORE_FLAT &&
                               tc_supported(idx, metric) && k <= 256 && idx->n >= 64;
     bool use_tc = tc_candidate &&
                   // a row filter rides along as a mask on the hit bits; with few allowed rows the shortlists cannot fill
@@ -252,7 +273,8 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
     } else {
         LB_TRY(refresh_small_segments(idx));
         ScanRequest r;
-        r.corpus = idx->rows.as<float>();
+        if (idx->dtype == LB_F16) r.corpus_h = idx->rows.as<__half>();
+        else r.corpus = idx->rows.as<float>();
         r.n_rows = idx->n;
         r.dim = (int)idx->dim;
         r.queries = reinterpret_cast<const float*>(d_queries);
@@ -320,7 +342,7 @@ static int search_device_impl(lb_index* idx, int metric, const void* d_queries, 
             }
         }
         idx->stats.plan_used = 0;
-        idx->stats.algorithmic_bytes = (uint64_t)idx->n * idx->dim * 4;
+        idx->stats.algorithmic_bytes = (uint64_t)idx->n * row_bytes(idx);
     }
     if (idx->timing) cudaEventRecord(idx->ev[3], idx->stream);
     if ((sync_at_end || idx->timing) && !idx->pending_tc.active) LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));  // (the host path syncs after its copies)
@@ -380,7 +402,7 @@ int lb_device_info(int device, char* name, int cap, uint64_t* total_bytes, uint6
 int lb_index_create(lb_index** out, uint32_t dim, int dtype, int device) {
     if (!out) return fail(LB_INVALID_ARGUMENT, "out is null");
     if (dim == 0) return fail(LB_INVALID_ARGUMENT, "dimension must be positive");
-    if (dtype != LB_F32 && dtype != LB_PACKED_U64) return fail(LB_INVALID_ARGUMENT, "unknown dtype");
+    if (dtype != LB_F32 && dtype != LB_PACKED_U64 && dtype != LB_F16) return fail(LB_INVALID_ARGUMENT, "unknown dtype");
     int ndev = 0;
     LB_CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(LB_INVALID_ARGUMENT, "no such CUDA device: " + std::to_string(device));
@@ -467,7 +489,34 @@ static int append_common(lb_index* idx, const void* host, uint64_t n) {
 
 int lb_index_append_f32(lb_index* idx, const float* rows, uint64_t n) {
     if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
-    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "index does not store f32 rows");
+    if (!dense_rows(idx)) return fail(LB_INVALID_ARGUMENT, "index does not store f32 rows");
+    if (!rows && n) return fail(LB_INVALID_ARGUMENT, "rows is null");
+    std::lock_guard<std::mutex> lock(idx->mu);
+    DeviceGuard g(idx->device);
+    if (idx->dtype == LB_F32) return append_common(idx, rows, n);
+    // binary16 index: the values go through an f32 staging buffer and are narrowed on the device (round to nearest even,
+    // src/storage/dtype.rs:60-67; exact for values that already are binary16)
+    if (n == 0) return LB_OK;
+    if (idx->n + n >= 0xFFFFFFFFull) return fail(LB_INVALID_ARGUMENT, "an index holds fewer than 2^32-1 rows");
+    LB_TRY(grow_rows(idx, idx->n + n));
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)idx->dim * 4));
+    for (uint64_t done = 0; done < n; done += chunk_rows) {
+        const uint64_t m = std::min(chunk_rows, n - done), ne = m * idx->dim;
+        LB_TRY(idx->w_queries.ensure(ne * 4));
+        LB_CUDA_TRY(cudaMemcpyAsync(idx->w_queries.p, rows + done * idx->dim, ne * 4, cudaMemcpyHostToDevice, idx->stream));
+        f32_to_f16_kernel<<<(unsigned)idx->sm_count * 8, 256, 0, idx->stream>>>(idx->w_queries.as<float>(),
+                                                                              idx->rows.as<__half>() + (idx->n + done) * idx->dim, ne);
+        LB_CUDA_TRY(cudaGetLastError());
+        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
+    account_segment(idx, n);
+    idx->n += n;
+    return LB_OK;
+}
+
+int lb_index_append_f16(lb_index* idx, const uint16_t* rows, uint64_t n) {
+    if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
+    if (idx->dtype != LB_F16) return fail(LB_INVALID_ARGUMENT, "index does not store binary16 rows");
     if (!rows && n) return fail(LB_INVALID_ARGUMENT, "rows is null");
     std::lock_guard<std::mutex> lock(idx->mu);
     DeviceGuard g(idx->device);
@@ -494,6 +543,15 @@ int lb_index_append_synthetic(lb_index* idx, uint64_t n, uint64_t seed, uint64_t
     if (idx->dtype == LB_F32) {
         uint64_t ne = n * idx->dim;
         synth_f32_kernel<<<blocks, 256, 0, idx->stream>>>(idx->rows.as<float>() + idx->n * idx->dim, ne, seed, row_offset * idx->dim);
+    } else if (idx->dtype == LB_F16) {
+        // the f32 synthetic values narrowed to binary16 (host: synthetic.rows_f32(...).astype(float16)), in pieces of 64 MiB
+        const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)idx->dim * 4));
+        for (uint64_t done = 0; done < n; done += chunk_rows) {
+            const uint64_t m = std::min(chunk_rows, n - done), ne = m * idx->dim;
+            LB_TRY(idx->w_queries.ensure(ne * 4));
+            synth_f32_kernel<<<blocks, 256, 0, idx->stream>>>(idx->w_queries.as<float>(), ne, seed, (row_offset + done) * idx->dim);
+            f32_to_f16_kernel<<<blocks, 256, 0, idx->stream>>>(idx->w_queries.as<float>(), idx->rows.as<__half>() + (idx->n + done) * idx->dim, ne);
+        }
     } else {
         uint64_t ne = n * (uint64_t)idx->n_words;
         synth_u64_kernel<<<blocks, 256, 0, idx->stream>>>(idx->rows.as<uint64_t>() + idx->n * idx->n_words, ne, seed,
@@ -518,10 +576,23 @@ int lb_index_segments(const lb_index* idx, uint64_t* rows_out, int cap, int* n_s
 
 int lb_index_read_rows_f32(lb_index* idx, uint64_t first, uint64_t n, float* out) {
     if (!idx || !out) return fail(LB_INVALID_ARGUMENT, "null argument");
-    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "index does not store f32 rows");
+    if (!dense_rows(idx)) return fail(LB_INVALID_ARGUMENT, "index does not store f32 rows");
     std::lock_guard<std::mutex> lock(idx->mu);
     DeviceGuard g(idx->device);
     if (first + n > idx->n) return fail(LB_INVALID_ARGUMENT, "row range out of bounds");
+    if (idx->dtype == LB_F16) {  // decoded on the device, in pieces of 64 MiB
+        const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)idx->dim * 4));
+        for (uint64_t done = 0; done < n; done += chunk_rows) {
+            const uint64_t m = std::min(chunk_rows, n - done), ne = m * idx->dim;
+            LB_TRY(idx->w_sub_q.ensure(ne * 4));
+            f16_to_f32_kernel<<<(unsigned)idx->sm_count * 8, 256, 0, idx->stream>>>(idx->rows.as<__half>() + (first + done) * idx->dim,
+                                                                                  idx->w_sub_q.as<float>(), ne);
+            LB_CUDA_TRY(cudaGetLastError());
+            LB_CUDA_TRY(cudaMemcpyAsync(out + done * idx->dim, idx->w_sub_q.p, ne * 4, cudaMemcpyDeviceToHost, idx->stream));
+            LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        }
+        return LB_OK;
+    }
     LB_CUDA_TRY(cudaMemcpyAsync(out, idx->rows.as<float>() + first * idx->dim, n * idx->dim * 4, cudaMemcpyDeviceToHost, idx->stream));
     LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
     return LB_OK;
@@ -656,7 +727,7 @@ static int search_host_common(lb_index* idx, int score_mode, int metric, const v
 int lb_index_search(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, const uint64_t* allow_bits,
                     uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
     if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
-    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "use lb_index_search_packed for a packed index");
+    if (!dense_rows(idx)) return fail(LB_INVALID_ARGUMENT, "use lb_index_search_packed for a packed index");
     if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
     return search_host_common(idx, SCORE_FLAT, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows,
                               out_dists, out_counts);
@@ -665,7 +736,7 @@ int lb_index_search(lb_index* idx, int metric, const float* queries, uint32_t nq
 int lb_index_search_pairwise(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, const uint64_t* allow_bits,
                              uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
     if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
-    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "pairwise search needs f32 rows");
+    if (!dense_rows(idx)) return fail(LB_INVALID_ARGUMENT, "pairwise search needs f32 rows");
     if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
     return search_host_common(idx, SCORE_PAIRWISE, metric, queries, (size_t)idx->dim * 4, nq, k, allow_bits, allow_words, out_rows,
                               out_dists, out_counts);
@@ -674,7 +745,7 @@ int lb_index_search_pairwise(lb_index* idx, int metric, const float* queries, ui
 int lb_index_search_f16_rows(lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, const uint64_t* allow_bits,
                              uint64_t allow_words, uint32_t* out_rows, float* out_dists, uint32_t* out_counts) {
     if (!idx) return fail(LB_INVALID_ARGUMENT, "index is null");
-    if (idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "the float16-row search needs (decoded) f32 rows");
+    if (!dense_rows(idx)) return fail(LB_INVALID_ARGUMENT, "the float16-row search needs (decoded) f32 rows");
     if (!out_rows || !out_dists || !out_counts) return fail(LB_INVALID_ARGUMENT, "output buffer is null");
     // the binary metrics go through the packed cache whatever the storage dtype (flat_mmap.rs:839-845, :504-510)
     const int mode = (metric >= 0 && metric < LB_METRIC_COUNT && metric_binary(metric)) ? SCORE_FLAT : SCORE_F16_ROWS;
@@ -1684,13 +1755,13 @@ static int sharded_search_host(lb_comm* comm, lb_index* idx, int metric, const v
 
 int lb_sharded_search(lb_comm* comm, lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, uint64_t row_base,
                       uint64_t* out_rows, float* out_dists, uint32_t* out_counts) {
-    if (idx && idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "use lb_sharded_search_packed for a packed index");
+    if (idx && !dense_rows(idx)) return fail(LB_INVALID_ARGUMENT, "use lb_sharded_search_packed for a packed index");
     return sharded_search_host(comm, idx, metric, queries, idx ? (size_t)idx->dim * 4 : 0, nq, k, row_base, nullptr, 0, out_rows, out_dists, out_counts);
 }
 
 int lb_sharded_search_filtered(lb_comm* comm, lb_index* idx, int metric, const float* queries, uint32_t nq, uint32_t k, uint64_t row_base,
                                const uint64_t* allow_bits, uint64_t allow_words, uint64_t* out_rows, float* out_dists, uint32_t* out_counts) {
-    if (idx && idx->dtype != LB_F32) return fail(LB_INVALID_ARGUMENT, "use lb_sharded_search_packed for a packed index");
+    if (idx && !dense_rows(idx)) return fail(LB_INVALID_ARGUMENT, "use lb_sharded_search_packed for a packed index");
     return sharded_search_host(comm, idx, metric, queries, idx ? (size_t)idx->dim * 4 : 0, nq, k, row_base, allow_bits, allow_words, out_rows,
                                out_dists, out_counts);
 }

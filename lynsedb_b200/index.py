@@ -18,17 +18,20 @@ from . import metrics as M
 
 
 class DeviceIndex:
-    """Rows of one GPU.  ``dtype`` is ``"float32"`` or ``"packed"`` (pre-packed one-bit rows, u64 words)."""
+    """Rows of one GPU.  ``dtype`` is ``"float32"``, ``"float16"`` (rows kept as IEEE binary16 in HBM — half the bytes of
+    every scan — and decoded exactly on load; appends and queries stay float32) or ``"packed"`` (pre-packed one-bit rows,
+    u64 words)."""
+
+    _DTYPES = {"float32": N.LB_F32, "packed": N.LB_PACKED_U64, "float16": N.LB_F16}
 
     def __init__(self, dim: int, dtype: str = "float32", device: int = 0):
-        if dtype not in ("float32", "packed"):
+        if dtype not in self._DTYPES:
             raise ValueError(f"unsupported dtype: {dtype}")
         self._dtype = dtype
         self._dim = int(dim)
         self._device = int(device)
         self._h = C.c_void_p()
-        N.check(N.lib().lb_index_create(C.byref(self._h), self._dim, N.LB_F32 if dtype == "float32" else N.LB_PACKED_U64,
-                                        self._device))
+        N.check(N.lib().lb_index_create(C.byref(self._h), self._dim, self._DTYPES[dtype], self._device))
 
     # -- lifetime -------------------------------------------------------------
     def close(self) -> None:
@@ -222,6 +225,10 @@ class ShardedDeviceIndex:
         return self._dim
 
     @property
+    def dtype(self) -> str:
+        return self._dtype
+
+    @property
     def devices(self):
         return list(self._devices)
 
@@ -247,7 +254,7 @@ class ShardedDeviceIndex:
 
     # -- ingest -------------------------------------------------------------------------------------------------------
     def _row_bytes(self) -> int:
-        return self.n_words * 8 if self._dtype == "packed" else self._dim * 4
+        return self.n_words * 8 if self._dtype == "packed" else self._dim * (2 if self._dtype == "float16" else 4)
 
     def append(self, rows: np.ndarray) -> None:
         rows = np.ascontiguousarray(rows, dtype=np.uint64 if self._dtype == "packed" else np.float32)

@@ -396,3 +396,91 @@ def test_collection_spread_over_several_device_indexes(L, oracle):
         o_ids, _, _ = oracle.store_batch_search(sub, queries[:20], k, "l2", n_threads=1)
         assert np.array_equal(np.stack([r.ids for r in res]), np.asarray(sorted(keep))[o_ids.astype(np.int64)])
         assert np.array_equal(store.read_rows(8990, 30), allv[8990:9020])
+
+
+# ---- binary16 rows in HBM (float16 collections) ------------------------------------------------------------------------------
+ALL_DENSE = ["ip", "l2", "cosine", "l1", "chebyshev", "canberra", "bray_curtis", "correlation", "hellinger", "wasserstein",
+             "jensen_shannon", "hamming", "jaccard", "dice"]
+
+
+@pytest.mark.parametrize("dim", [64, 100, 200])
+def test_binary16_rows_give_the_results_of_the_decoded_rows(L, dim):
+    """An index that keeps its rows as IEEE binary16 (half the HBM bytes) against an f32 index holding the same, already
+    binary16-exact, values: every kernel decodes on load, so ids, order and scores are bit-identical — for the FLAT scans of
+    every metric, the scalar f32-query x f16-row kernels of search() / filtered searches (simd.rs:805-1092), the
+    tensor-core plan (shadow built from the binary16 rows, rescoring on them) and a row filter."""
+    rng = np.random.default_rng(900 + dim)
+    n = 30_000
+    rows = (rng.random((n, dim), dtype=np.float32) + np.float32(0.01)).astype(np.float16).astype(np.float32)
+    rows[::7] *= np.float32(0.25)
+    rows = rows.astype(np.float16).astype(np.float32)
+    queries = rng.random((300, dim), dtype=np.float32)
+    allowed = rng.random(n) < 0.4
+    bits = np.packbits(allowed, bitorder="little")
+    bits = np.concatenate([bits, np.zeros((-len(bits)) % 8, np.uint8)]).view(np.uint64)
+    with L.DeviceIndex(dim, "float16") as h, L.DeviceIndex(dim, "float32") as f:
+        h.append(rows)
+        f.append(rows)
+        assert np.array_equal(h.read_rows(100, 50), rows[100:150])
+        for metric in ALL_DENSE:
+            for nq in (3, 40, 300):
+                if nq == 300 and metric not in ("ip", "l2", "cosine", "hamming", "jaccard"):
+                    continue
+                a, b = h.search(queries[:nq], 10, metric), f.search(queries[:nq], 10, metric)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]), (metric, nq)
+                assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), (metric, nq)
+            a, b = h.search(queries[:5], 10, metric, f16_rows=True), f.search(queries[:5], 10, metric, f16_rows=True)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), ("f16 rows", metric)
+            a, b = h.search(queries[:5], 10, metric, bits, f16_rows=True), f.search(queries[:5], 10, metric, bits, f16_rows=True)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), ("filtered", metric)
+        a, b = h.search(queries, 10, "ip", bits), f.search(queries, 10, "ip", bits)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+        assert h.last_stats()["plan_used"] == 1
+
+
+def test_binary16_rows_halve_the_scan_bytes(L):
+    """The point of the half-width layout: the one-query scan reads dim * 2 bytes per row, and runs about twice as fast."""
+    import time
+
+    n, dim = 2_000_000, 768
+    q = np.random.default_rng(3).random((1, dim), dtype=np.float32)
+    times, stats = {}, {}
+    for dt in ("float32", "float16"):
+        with L.DeviceIndex(dim, dt) as idx:
+            idx.append_synthetic(n, 42, 0)
+            idx.set_timing(True)
+            for _ in range(3):
+                r = idx.search(q, 10, "l1")
+            best = 1e9
+            for _ in range(5):
+                idx.search(q, 10, "l1")
+                best = min(best, idx.last_stats()["ms_dominant"])
+            times[dt], stats[dt] = best, (r, idx.last_stats()["algorithmic_bytes"])
+    assert stats["float16"][1] * 2 == stats["float32"][1] == n * dim * 4
+    assert np.array_equal(stats["float16"][0][2], stats["float32"][0][2])
+    assert times["float16"] < 0.65 * times["float32"], times
+
+
+def test_float16_collection_on_binary16_storage(L, oracle):
+    """The Collection path of a float16 collection now lands on binary16 rows; results stay those of the reference's F16
+    paths (compared through the oracle's f16 restatement, as tests/test_gpu_f16_rows.py does for the decoded layout)."""
+    rng = np.random.default_rng(41)
+    dim, n, k = 48, 9000, 7
+    data = rng.random((n, dim), dtype=np.float32)
+    q = rng.random((6, dim), dtype=np.float32)
+    stored = data.astype(np.float16).astype(np.float32)
+    with L.VectorDBClient() as client:
+        coll = client.create_collection("db", "h", dim=dim, dtypes="float16", default_index="FLAT-L2")
+        coll.add(vectors=data, batch_size=n)
+        coll.commit()
+        assert coll._store.dtype == "float16"
+        single = coll.search(q[0], k)
+        o_ids, o_d = oracle.store_search_f16(stored, q[0], k, "l2", n_threads=1)
+        assert single.ids.tolist() == [int(x) for x in o_ids] and np.array_equal(single.distances.view(np.uint32), o_d.view(np.uint32))
+        batch = coll.batch_search(q, k)
+        w_ids, w_d, _ = oracle.store_batch_search(stored, q, k, "l2", n_threads=1)
+        assert np.array_equal(np.stack([r.ids for r in batch]), w_ids.astype(np.int64))
+        assert np.array_equal(np.stack([r.distances for r in batch]).view(np.uint32), w_d.view(np.uint32))
+        coll.build_index("IVF-L2", n_clusters=8, nprobe=8)      # the lists need f32 rows: the store is decoded once
+        assert coll._store.dtype == "float32"
+        assert coll.search(stored[17], k=1, nprobe=8).ids[0] == 17
