@@ -10,6 +10,10 @@ from .index import DeviceIndex, ShardedDeviceIndex, make_allow_bits
 from .ivf import IVFIndex
 from .result_view import ResultView
 
+import logging as _logging
+
+logger = _logging.getLogger("LynseDB")   # the reference's logger name (python/lynse/utils/utils.py)
+
 __version__ = "0.1.0"
 __all__ = ["VectorDBClient", "Database", "Collection", "DeviceIndex", "ShardedDeviceIndex", "IVFIndex", "FlatIndex", "IvfFlatIndex", "ResultView", "compute_distance",
            "top_k_search", "make_allow_bits", "metrics"]

@@ -699,6 +699,43 @@ class Collection:
             _round_to_eps(result.distances, eps)
         return result
 
+    def search_profile(self, vector, k: int = 10, *, where=None, nprobe: int = 10, approx: bool = False, eps: float = 1e-4) -> dict:
+        """``search_profile`` (python/lynse/api/local_client.py:1049-1059 -> ``Collection::search_with_profile``,
+        src/engine.rs:5005-5054): ``{"items": {k, ids, scores, index}, "profile": {...}}`` with the reference's profile keys
+        (query_kind, vector_field, index_path, total_vectors, filter_expression, filter_matches, scanned_vectors, result_count,
+        filter_us, search_us, rerank_us, total_us) plus ``device`` — what the GPU did (plan, kernels, fallbacks, timings)."""
+        import time
+
+        started = time.perf_counter()
+        q = np.ascontiguousarray(vector, dtype=np.float32).reshape(1, -1)
+        filter_us, filter_matches = 0, None
+        filter_ids = None
+        with self._lock:
+            if where is not None:
+                t0 = time.perf_counter()
+                rows = self._subset_rows(where, None)
+                filter_ids = [self._ids.id_of(int(r)) for r in rows]
+                filter_us = int((time.perf_counter() - t0) * 1e6)
+                filter_matches = len(filter_ids)
+            t0 = time.perf_counter()
+            result = self.search(q[0], k, filter_ids=filter_ids, nprobe=nprobe, approx=approx, eps=eps) if where is not None \
+                else self.search(q[0], k, nprobe=nprobe, approx=approx, eps=eps)
+            search_us = int((time.perf_counter() - t0) * 1e6)
+            total = len(self._ids)
+            family = _index_family(self._index_mode or "FLAT-IP")
+            index_path = "ann_index" if family != "FLAT" else ("flat_mmap_filtered" if where is not None else "flat_mmap")
+            device = self._store.last_stats() if self._store is not None and len(self._store) else {}
+        ids = result.ids.tolist() if result.ids is not None else []
+        return {
+            "items": {"k": int(k), "ids": ids, "scores": [float(x) for x in (result.distances if result.distances is not None else [])],
+                      "index": self._index_mode or "FLAT-IP"},
+            "profile": {"query_kind": "vector", "vector_field": "default", "index_path": index_path, "total_vectors": total,
+                        "filter_expression": where if isinstance(where, str) else (None if where is None else repr(where)),
+                        "filter_matches": filter_matches, "scanned_vectors": filter_matches if filter_matches is not None else total,
+                        "result_count": len(ids), "filter_us": filter_us, "search_us": search_us, "rerank_us": 0,
+                        "total_us": int((time.perf_counter() - started) * 1e6), "device": device},
+        }
+
     def batch_search(self, vectors, k: int = 10, *, where=None, return_fields: bool = False, nprobe: int = 10, reranker=None,
                      rerank_k=None, rerank_with_fields: bool = False, wire_dtype: str = "float32",
                      filter_ids: Optional[Iterable] = None) -> List[ResultView]:

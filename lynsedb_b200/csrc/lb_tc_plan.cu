@@ -366,8 +366,11 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     // Large k (no single partition floor is far enough past rank k): a pre-pass over 1/64 of the corpus seeds every
     // query's floor (seed_floor_kernel) at about rank max(10 k, 512) of the corpus, and the main pass appends every row
     // above that floor to the query's hit buffer (hit mode): no shortlist upkeep in the accumulator hand-off.
-    const bool seeded = k > tc::KP - 4 && tiles_total >= (uint32_t)(64 * 8) * (uint32_t)n_slots && job.dump == nullptr &&
-                        tc_env_int("LYNSE_B200_TC_SEED", 1) != 0;
+    // (LYNSE_B200_TC_SEED_SMALLK=1 sends small k the same way.  Measured on C2: the main pass gets ~5 % faster — 0.12
+    // appends per tile and warp instead of 0.16 shortlist insertions — but the pre-pass costs more than that, at 10M rows
+    // (5.03 against 4.86 ms per step) and on a 1.25M-row shard (0.97 against 0.94 ms): off.)
+    const bool seeded = (k > tc::KP - 4 || tc_env_int("LYNSE_B200_TC_SEED_SMALLK", 0) != 0) &&
+                        tiles_total >= (uint32_t)(64 * 8) * (uint32_t)n_slots && job.dump == nullptr && tc_env_int("LYNSE_B200_TC_SEED", 1) != 0;
     const bool hit_mode = seeded && tc_env_int("LYNSE_B200_TC_HITS", 1) != 0;
     // narrow rows in hit mode: two sets of epilogue warps, each scanning one 64-row half of every tile into its own hit region
     if (hit_mode && cfg_id == 3 && tc_env_int("LYNSE_B200_TC_EPI", 2) == 2) cfg_id = 4;

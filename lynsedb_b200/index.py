@@ -32,6 +32,11 @@ class DeviceIndex:
         self._device = int(device)
         self._h = C.c_void_p()
         N.check(N.lib().lb_index_create(C.byref(self._h), self._dim, self._DTYPES[dtype], self._device))
+        import os
+
+        target = os.environ.get("LYNSE_SEGMENT_TARGET_BYTES", "").strip()     # src/storage/vector_store.rs:225-229
+        if target.isdigit() and int(target) > 0:
+            N.check(N.lib().lb_index_set_segment_target(self._h, int(target)))
 
     # -- lifetime -------------------------------------------------------------
     def close(self) -> None:

@@ -24,7 +24,6 @@ OUT_OF_SCOPE = {
     "test_sparse_search_returns_inner_product_results": "sparse vectors are a separate index (src/sparse)",
     "test_sparse_search_with_filter_and_fields": "sparse vectors",
     "test_batch_search_reranker_applies_per_query": "external rerankers",
-    "test_search_profile_reports_filter_metadata": "search_profile reports the SQL metadata engine's filter plan (ApexBase), which does not exist here",
     "test_filtered_search_respects_where_for_quantized_and_graph_indexes": "SQ8 / PQ quantized index modes are outside the path (DESIGN.md §7)",
     "test_query_filter_ids_empty_list": "Collection.query is the SQL metadata query API",
     "test_query_filter_ids_subset_returns_only_those": "Collection.query is the SQL metadata query API",
