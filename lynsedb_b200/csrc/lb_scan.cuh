@@ -301,15 +301,15 @@ __device__ inline void bitonic_sort_u64(uint64_t* s, int M) {
     for (int size = 2; size <= M; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int i = threadIdx.x; i < M; i += blockDim.x) {
-                int p = i ^ stride;
-                if (p > i) {
-                    bool up = (i & size) == 0;
-                    uint64_t x = s[i], y = s[p];
-                    if ((x > y) == up) {
-                        s[i] = y;
-                        s[p] = x;
-                    }
+            // one thread per compare-exchange pair (i, i + stride): pair t maps to the t-th index whose `stride` bit is clear
+            for (int t = threadIdx.x; t < (M >> 1); t += blockDim.x) {
+                const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                const int p = i | stride;
+                const bool up = (i & size) == 0;
+                const uint64_t x = s[i], y = s[p];
+                if ((x > y) == up) {
+                    s[i] = y;
+                    s[p] = x;
                 }
             }
         }

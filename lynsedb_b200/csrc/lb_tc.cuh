@@ -1117,13 +1117,17 @@ __device__ __forceinline__ int gather_candidates(const FinArgs& a, int q, uint64
         // are sorted next); more than M1 of them, or a region that ran out of room, leaves the query uncertified
         for (int i = tid; i < a.M1; i += blockDim.x) s[i] = KEY_NONE;
         __syncthreads();
-        for (int r = 0; r < a.P; ++r) {
-            const uint32_t cnt = a.hit_count[(size_t)q * a.P + r];
-            if (cnt > a.hit_cap && tid == 0) *sh_overflow = 1u;
-            const uint32_t n = min(cnt, a.hit_cap);
-            const uint2* reg = a.hit_buf + ((size_t)q * a.P + r) * a.hit_cap;
-            for (uint32_t i = tid; i < n; i += blockDim.x) {
-                const uint2 h = reg[i];
+        // one flat sweep over (region, entry): neighbouring threads read neighbouring entries, and every thread has many
+        // independent loads in flight (a loop over the regions would pay one memory round trip per region)
+        const uint32_t cap = a.hit_cap, total = (uint32_t)a.P * cap;
+        const uint32_t* cnts = a.hit_count + (size_t)q * a.P;
+        const uint2* regs = a.hit_buf + (size_t)q * a.P * cap;
+        for (uint32_t idx = tid; idx < total; idx += blockDim.x) {
+            const uint32_t r = idx / cap, i = idx - r * cap;
+            const uint32_t cnt = __ldg(cnts + r);
+            if (i == 0 && cnt > cap) *sh_overflow = 1u;
+            if (i < min(cnt, cap)) {
+                const uint2 h = regs[idx];
                 const uint32_t slot = atomicAdd(sh_ncand, 1u);
                 if (slot < (uint32_t)a.M1) s[slot] = ((uint64_t)(~key_bits_orderable(h.x, ik)) << 32) | h.y;
             }

@@ -470,7 +470,11 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     if (seeded) {
         // pre-pass: the first 1/64 of the tiles, one partition per slot, private floors, shortlists; then the seed
         tc::TcArgs sa = a;
-        const uint32_t S = std::max<uint32_t>(tiles_total / 64, (uint32_t)n_slots * 8);
+        // the sample is as small as it can be for its 8th best key to sit near rank `want_rows` of the corpus:
+        // 8 / want_rows of the tiles (1/64 at k = 32, 1/125 at k = 100), at least eight tiles per slot
+        const uint64_t want_rows = std::max<uint64_t>((uint64_t)10 * k, 512);
+        const uint32_t S = std::max<uint32_t>((uint32_t)std::min<uint64_t>(tiles_total, ceil_div((uint64_t)8 * tiles_total * BN, want_rows * BN)),
+                                              (uint32_t)n_slots * 8);
         sa.tiles_total = S;
         sa.n_rows = (uint32_t)std::min<uint64_t>(idx->n, (uint64_t)S * BN);
         sa.tiles_per_part = (uint32_t)ceil_div(S, n_slots);
@@ -482,7 +486,6 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
         const int s_lists = sa.P;
         const int sm = next_pow2(s_lists * tc::KP);
         // aim at ~max(10 k, 512) rows of the whole corpus above the seeded floor
-        const uint64_t want_rows = std::max<uint64_t>((uint64_t)10 * k, 512);
         int r = (int)ceil_div(want_rows * S, tiles_total);
         r = std::max(8, std::min(r, s_lists * tc::KP / 2));
         LB_CUDA_TRY(ensure_dynamic_smem(tc::seed_floor_kernel, sm * 8));
@@ -528,6 +531,7 @@ static void fill_fin_candidates(lb_index* idx, const CoarseJob& job, tc::FinArgs
     f.int_key = mode_int_key(job.mode) ? 1 : 0;
     f.M1 = job.hit_mode ? TC_FIN_MAX : next_pow2(job.n_lists * tc::KP);
     f.R = std::min(1024, std::max(128, next_pow2(4 * job.k)));
+    if (tc_env_int("LYNSE_B200_FIN_R", 0) > 0) f.R = std::max(next_pow2(job.k), next_pow2(tc_env_int("LYNSE_B200_FIN_R", 0)));  // diagnostics
     f.nq = job.nq;
     f.k = job.k;
     f.uncertified = job.flags + 4;
@@ -597,7 +601,8 @@ int run_tc(lb_index* idx, int metric, const float* d_queries, int nq, int k, uin
     f.out_rows = d_rows;
     f.out_dists = d_dists;
     f.out_counts = d_counts;
-    const int fin_threads = nq <= 64 ? 1024 : 256;  // few queries: few blocks, so each gets 1024 threads
+    int fin_threads = nq <= 64 ? 1024 : 256;  // few queries: few blocks, so each gets 1024 threads
+    if (tc_env_int("LYNSE_B200_FIN_THREADS", 0) > 0) fin_threads = tc_env_int("LYNSE_B200_FIN_THREADS", 0);  // diagnostics
     size_t fsmem = (size_t)(f.M1 + f.R) * 8 + (size_t)((idx->dim + 3) & ~3u) * 4 + (size_t)(fin_threads / 8) * tc::FIN_STRIDE * 4;  // + row buffers
 #define LB_LAUNCH_FIN(ASCV, RTV)                                                                 \
     do {                                                                                        \
