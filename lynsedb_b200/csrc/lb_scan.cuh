@@ -54,6 +54,7 @@ struct ScanArgs {
     uint32_t* counts;           // [P][nq]
     uint64_t* thr;              // [P][nq] current worst kept key (valid when count == k)
     uint32_t rows_per_part;     // multiple of SCAN_THREADS
+    const float* query_tiles;   // row-tile scan (lb_scan3.cuh): the query tiles in the kernel's shared-memory layout
     int smem_lists;             // 1: a batch of one query tile keeps its top-k lists in shared memory (room reserved by the host)
 };
 

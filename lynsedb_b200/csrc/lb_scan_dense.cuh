@@ -6,6 +6,7 @@
 #include "lb_metrics.cuh"
 #include "lb_scan.cuh"
 #include "lb_scan2.cuh"
+#include "lb_scan3.cuh"
 
 namespace lb {
 
@@ -15,8 +16,61 @@ struct ScanPlan {
 };
 
 template <class RT>
-int dense_scan_launch(lb_index* idx, const ScanRequest& r, ScanArgs& a, const ScanPlan& sp, bool s2_metric, bool tma_rows) {
-    if (s2_metric && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
+int dense_scan_launch(lb_index* idx, const ScanRequest& r, ScanArgs& a, const ScanPlan& sp, bool s2_metric, bool tma_rows, bool tile_rows) {
+    if (tile_rows) {
+        // a batch of queries over contiguous f32 rows: register tiles of 4 rows x 16 queries, rows resident in shared memory (lb_scan3.cuh)
+        if constexpr (std::is_same<RT, float>::value) {
+            PFN_encodeTiled enc = get_encode_tiled();
+            if (!enc) return fail(LB_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+            const int nw = scan4_warps(r.dim);
+            CUtensorMap tmap;
+            cuuint64_t gdim[2] = {(cuuint64_t)r.dim, (cuuint64_t)r.n_rows};
+            cuuint64_t gstride[1] = {(cuuint64_t)r.dim * sizeof(float)};
+            cuuint32_t box[2] = {32u, (cuuint32_t)(nw * 4 * S4_R)};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)const_cast<float*>(r.corpus), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled (row tiles) failed with CUresult " + std::to_string((int)cr));
+            const bool ip2 = r.ip_single || r.n_small > 0;
+#define LB_LAUNCH_S4T(M, IP2V, NWV, TQV)                                                                   \
+    do {                                                                                                   \
+        using Cfg = S4Cfg<M, IP2V, TQV>;                                                                   \
+        const int n_tiles = (r.nq + Cfg::kTQ - 1) / Cfg::kTQ;                                              \
+        LB_TRY(idx->w_qtiles.ensure((size_t)n_tiles * Cfg::tile_floats(r.dim) * 4));                       \
+        scan4_query_tiles_kernel<<<n_tiles, 256, 0, idx->stream>>>(r.queries, r.nq, r.dim, Cfg::kTQ, Cfg::kQStride, idx->w_qtiles.as<float>()); \
+        a.query_tiles = idx->w_qtiles.as<float>();                                                         \
+        a.smem_lists = Cfg::smem_lists(r.nq, r.k) ? 1 : 0;                                                 \
+        const size_t smem = Cfg::smem_bytes(NWV, r.dim, r.nq, r.k);                                        \
+        LB_CUDA_TRY(ensure_dynamic_smem(scan_tile_kernel<M, IP2V, NWV, TQV>, (int)smem));                  \
+        scan_tile_kernel<M, IP2V, NWV, TQV><<<sp.P, NWV * 32, smem, idx->stream>>>(tmap, a);               \
+    } while (0)
+#define LB_LAUNCH_S4W(M, IP2V, NWV)                                                                        \
+    do {                                                                                                   \
+        constexpr int tq_sel = (Scan2Op<M, IP2V>::kState == 8 && NWV > 2) ? 16 : 8;                        \
+        LB_LAUNCH_S4T(M, IP2V, NWV, tq_sel);                                                               \
+    } while (0)
+#define LB_LAUNCH_S4(M, IP2V)                                   \
+    do {                                                        \
+        if (nw == 8) LB_LAUNCH_S4W(M, IP2V, 8);                 \
+        else if (nw == 4) LB_LAUNCH_S4W(M, IP2V, 4);            \
+        else LB_LAUNCH_S4W(M, IP2V, 2);                         \
+    } while (0)
+            switch (r.metric) {
+                case LB_IP: if (ip2) LB_LAUNCH_S4(LB_IP, true); else LB_LAUNCH_S4(LB_IP, false); break;
+                case LB_L2: LB_LAUNCH_S4(LB_L2, false); break;
+                case LB_COSINE: LB_LAUNCH_S4(LB_COSINE, false); break;
+                case LB_MANHATTAN: LB_LAUNCH_S4(LB_MANHATTAN, false); break;
+                case LB_CHEBYSHEV: LB_LAUNCH_S4(LB_CHEBYSHEV, false); break;
+                default: LB_LAUNCH_S4(LB_BRAY_CURTIS, false); break;
+            }
+#undef LB_LAUNCH_S4
+#undef LB_LAUNCH_S4W
+#undef LB_LAUNCH_S4T
+        } else {
+            return fail(LB_INTERNAL, "the row-tile scan serves f32 rows");
+        }
+    } else if (s2_metric && !r.f16_rows && tc_env_int("LYNSE_B200_SCAN2", 1) != 0 &&
                (size_t)8 * ((r.dim + 3) & ~3) * 4 + 8 * S2_ROWS * 8 + 256 <= 200 * 1024) {
         // streaming scan: the row is read once per query tile (lb_scan2.cuh)
         const int dim_pad = (r.dim + 3) & ~3;
@@ -98,7 +152,7 @@ int dense_scan_launch(lb_index* idx, const ScanRequest& r, ScanArgs& a, const Sc
     return LB_OK;
 }
 
-extern template int dense_scan_launch<float>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool);
-extern template int dense_scan_launch<__half>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool);
+extern template int dense_scan_launch<float>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool, bool);
+extern template int dense_scan_launch<__half>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool, bool);
 
 }  // namespace lb

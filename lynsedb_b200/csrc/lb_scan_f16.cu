@@ -3,6 +3,6 @@
 
 namespace lb {
 
-template int dense_scan_launch<__half>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool);
+template int dense_scan_launch<__half>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool, bool);
 
 }  // namespace lb

@@ -6,7 +6,7 @@ using namespace lb;
 
 namespace lb {
 
-template int dense_scan_launch<float>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool);
+template int dense_scan_launch<float>(lb_index*, const ScanRequest&, ScanArgs&, const ScanPlan&, bool, bool, bool);
 
 // ---- exact scan plan ------------------------------------------------------------------------------------------
 static ScanPlan plan_scan(const lb_index* idx, uint64_t n_rows, int nq, int k, int ctas_per_sm = 2) {
@@ -32,6 +32,11 @@ int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
                          r.row_ids == nullptr && (r.dim & (r.corpus_h != nullptr ? 7 : 3)) == 0 && r.dim >= 8 && r.n_rows >= 4096 && r.nq <= 4 &&
                          tc_env_int("LYNSE_B200_SCAN_TMA", 1) != 0 &&
                          (size_t)S3_NSTAGES * S3_STAGE_BYTES + (size_t)S3_TQ * (S2_ROWS * 8 + ((r.dim + 3) & ~3) * 4 + 256 * 8) + 2048 <= 226 * 1024;
+    // a dozen queries and more over contiguous f32 rows of up to 512 dims: the row-tile scan (lb_scan3.cuh).  Below that the
+    // streaming scan is HBM-bound anyway; above 512 dims the resident row block leaves too few warps per SM.
+    const bool tile_f32 = !r.words && !r.f16_rows && r.corpus != nullptr && r.corpus_h == nullptr && s2_metric && scan4_supported(r.metric) &&
+                          r.row_ids == nullptr && (r.dim & 3) == 0 && r.dim >= 8 && r.dim <= 512 && r.n_rows >= 4096 &&
+                          r.nq >= tc_env_int("LYNSE_B200_SCAN_TILE_MIN_Q", 12) && tc_env_int("LYNSE_B200_SCAN_TILE", 1) != 0;
     ScanPlan sp = plan_scan(idx, r.n_rows, r.nq, r.k, (tma_f32 && r.corpus_h == nullptr) ? 1 : 2);
     size_t nl = (size_t)sp.P * r.nq;
     LB_TRY(idx->w_lists.ensure(nl * r.k * 8));
@@ -109,9 +114,9 @@ int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
         }
 #undef LB_LAUNCH_PACKED
     } else if (f16) {
-        LB_TRY(dense_scan_launch<__half>(idx, r, a, sp, s2_metric, tma_f32));
+        LB_TRY(dense_scan_launch<__half>(idx, r, a, sp, s2_metric, tma_f32, false));
     } else {
-        LB_TRY(dense_scan_launch<float>(idx, r, a, sp, s2_metric, tma_f32));
+        LB_TRY(dense_scan_launch<float>(idx, r, a, sp, s2_metric, tma_f32 && !tile_f32, tile_f32));
     }
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
@@ -136,7 +141,7 @@ int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
     else
         merge_lists_kernel<<<r.nq, r.nq <= 64 ? 1024 : 256, (size_t)m.M * 8, idx->stream>>>(m);
     LB_CUDA_TRY(cudaGetLastError());
-    if (kernels) *kernels += 2;
+    if (kernels) *kernels += tile_f32 ? 3 : 2;
     idx->stats.n_partitions = sp.P;
     if (idx->timing && ms_dom) {
         LB_CUDA_TRY(cudaEventSynchronize(idx->ev[1]));
