@@ -601,11 +601,22 @@ def main():
             views = coll.batch_search(rig.queries, k)
         api_ms = (time.perf_counter() - t0) * 1000.0 / n_api
         cabi_ms = res["ms_e2e"] / args.steps
+        # the same batch through DeviceIndex.search alone (ctypes call, fresh pageable result arrays): what is left of
+        # api_ms above it is pure Python (tombstone filter, row -> id, result views)
+        store = coll._store
+        for _ in range(2):
+            store.search(rig.queries, k, metric)
+        t0 = time.perf_counter()
+        for _ in range(n_api):
+            store.search(rig.queries, k, metric)
+        native_ms = (time.perf_counter() - t0) * 1000.0 / n_api
         rig.step_host()
         same = bool(np.array_equal(np.stack([v.ids for v in views]).astype(np.uint64), rig.host_results()[0]))
         api_e2e = {"value": nq / (api_ms / 1000.0), "unit": "queries/s", "ms_per_step": api_ms,
                    "call": f"Collection.batch_search({nq} x {dim} float32 ndarray, k={k}) -> list[ResultView] (pageable host arrays)",
-                   "python_layer_ms": api_ms - cabi_ms, "python_layer_frac_of_step": (api_ms - cabi_ms) / api_ms,
+                   "above_c_abi_ms": api_ms - cabi_ms, "above_c_abi_frac_of_step": (api_ms - cabi_ms) / api_ms,
+                   "device_index_search_ms": native_ms,
+                   "python_layer_ms": api_ms - native_ms, "python_layer_frac_of_step": (api_ms - native_ms) / api_ms,
                    "ids_equal_c_abi_result": same}
         coll._store = None   # the rig owns the index
 

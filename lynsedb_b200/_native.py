@@ -101,8 +101,6 @@ SIGNATURES = {
     "lb_sharded_search_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_uint64, _vp, _vp, _vp]),
     "lb_index_event_record": (C.c_int, [_vp, C.c_int]),
     "lb_index_event_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
-    "lb_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p]),
-    "lb_debug_core_rate": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "lb_debug_tc_scores": (C.c_int, [_f32p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, C.c_int, _f32p]),
 }
 
@@ -125,6 +123,30 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+PROBE_LIB_PATH = LIB_PATH.with_name("liblynse_b200_probe.so")
+PROBE_SIGNATURES = {
+    "lb_probe_last_error": (C.c_char_p, []),
+    "lb_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p]),
+    "lb_debug_core_rate": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+}
+_probe_lib = None
+
+
+def probe_lib():
+    """The diagnostic rate probes (include/lynse_b200_probe.h), a library of their own: tools/ only."""
+    global _probe_lib
+    if _probe_lib is None:
+        if not PROBE_LIB_PATH.exists():
+            raise ImportError(f"{PROBE_LIB_PATH} is missing; build it with `make -C lynsedb_b200/csrc`")
+        L = C.CDLL(str(PROBE_LIB_PATH))
+        for name, (res, args) in PROBE_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _probe_lib = L
+    return _probe_lib
 
 
 def last_error() -> str:

@@ -108,6 +108,7 @@ struct TcArgs {
     int n_slots;
     int parts_per_slot;
     uint32_t* progress;       // [n_slots][PROGRESS_STRIDE] tiles issued per (slot, query group); zeroed per launch; null = free-running
+    int poll_mask;            // shared floors are re-read when (tile & poll_mask) == 0 (7: every 8th tile; 0: every tile)
     int window;               // a query group never runs more than `window` tiles ahead of the slowest group of its slot
     unsigned long long* prof; // optional [grid][8] cycle counters of the MMA issuer / epilogue (diagnostics)
     int debug_mode;           // diagnostics only (results are garbage): bit 0 = producer skips the TMA loads,
@@ -483,8 +484,8 @@ struct Shortlist {
     __device__ __forceinline__ K gate() const { return q_valid ? (HITS ? thr_g : max(lmin, thr_g)) : O::highest(); }
     // refresh the shared floor every 8th tile; the load issued now is consumed 8 tiles later, so its (loaded) L2
     // latency never sits on the per-tile critical path
-    __device__ __forceinline__ void poll_floor(uint32_t tile_iter) {
-        if (!HITS && share && (tile_iter & 7u) == 0u) {
+    __device__ __forceinline__ void poll_floor(uint32_t tile_iter, uint32_t mask) {
+        if (!HITS && share && (tile_iter & mask) == 0u) {
             if (g_bits != 0u) thr_g = max(thr_g, O::from_orderable(g_bits));
             g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
         }
@@ -1008,6 +1009,7 @@ struct FinArgs {
     int int_key;              // keys are s32 (8-bit operands) instead of f32
     int M1;                   // pow2 >= number of candidates read (<= 4096)
     int R;                    // rescore budget, pow2 <= 1024, >= k
+    int R1;                   // first round of the rescore (pow2, k <= R1 <= R; 0 = one round)
     const void* corpus;       // f32 or binary16 rows (finalize_kernel's RT)
     int dim;
     const float* queries;     // original f32 queries [nq][dim]
@@ -1192,47 +1194,106 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     __syncthreads();
     gather_candidates(a, q, s, &sh_T, &sh_ncand, &sh_overflow);
     const int ncand = (int)sh_ncand;
-    const int rn = min(ncand, a.R);
-    uint32_t T_ord = sh_T;  // every row dropped inside a partition has a coarse key <= T (0 = nothing dropped)
-    if (ncand > a.R) T_ord = max(T_ord, ~(uint32_t)(s[a.R] >> 32));  // ... and so has every candidate cut here
-    if (vec) {
-        // eight threads per row, four rows per warp, blockDim/8 rows per pass of the block (rows are independent:
-        // warp-local syncs only)
-        float* rowbuf = sq + ((dim + 3) & ~3) + (tid >> 3) * FIN_STRIDE;
-        const int lane = tid & 31;
-        const int rows_per_pass = (int)(blockDim.x >> 3);
-        for (int base = 0; base < a.R; base += rows_per_pass) {
-            const int i = base + (tid >> 3);
-            const bool row_ok = i < rn;
-            const uint32_t row = row_ok ? key_row(s[i]) : 0u;
-            const RT* c = corpus + (size_t)row * dim;
-            const bool two = a.metric == LB_IP && row_ok && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
-            const float v = rescore_row_lanes(a.metric, two, sq, c, dim, rowbuf, row_ok, lane);
-            if ((tid & 7) == 0 && i < a.R) e[i] = row_ok ? make_key<ASC>(v, row) : KEY_NONE;
-        }
-    } else {
-        for (int i = tid; i < a.R; i += blockDim.x) {
-            uint64_t key = KEY_NONE;
-            if (i < rn) {
-                uint32_t row = key_row(s[i]);
+    __shared__ int sh_done;
+    // Rescore the candidates [lo, hi) of the coarse order into e[lo, hi) (KEY_NONE past the last candidate).
+    auto rescore = [&](int lo, int hi) {
+        const int rn = min(ncand, hi);
+        if (vec) {
+            // eight threads per row, four rows per warp, blockDim/8 rows per pass of the block (rows are independent:
+            // warp-local syncs only)
+            float* rowbuf = sq + ((dim + 3) & ~3) + (tid >> 3) * FIN_STRIDE;
+            const int lane = tid & 31;
+            const int rows_per_pass = (int)(blockDim.x >> 3);
+            for (int base = lo; base < hi; base += rows_per_pass) {
+                const int i = base + (tid >> 3);
+                const bool row_ok = i < rn;
+                const uint32_t row = row_ok ? key_row(s[i]) : 0u;
                 const RT* c = corpus + (size_t)row * dim;
-                const bool qvec = (dim & 3) == 0;
-                float v;
-                if (a.metric == LB_IP) {
-                    bool small = a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
-                    v = small ? ip_single_order<false>(sq, c, dim, qvec) : ip_batch8_order<false>(sq, c, dim, qvec);
-                } else if (a.metric == LB_L2) {
-                    v = l2_squared<false>(sq, c, dim, qvec);
-                } else {
-                    v = cosine_distance<false>(sq, c, dim, qvec);
-                }
-                key = make_key<ASC>(v, row);
+                const bool two = a.metric == LB_IP && row_ok && a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
+                const float v = rescore_row_lanes(a.metric, two, sq, c, dim, rowbuf, row_ok, lane);
+                if ((tid & 7) == 0 && i < hi) e[i] = row_ok ? make_key<ASC>(v, row) : KEY_NONE;
             }
-            e[i] = key;
+        } else {
+            for (int i = lo + tid; i < hi; i += blockDim.x) {
+                uint64_t key = KEY_NONE;
+                if (i < rn) {
+                    uint32_t row = key_row(s[i]);
+                    const RT* c = corpus + (size_t)row * dim;
+                    const bool qvec = (dim & 3) == 0;
+                    float v;
+                    if (a.metric == LB_IP) {
+                        bool small = a.n_small > 0 && in_small_segment(a.small_seg, a.n_small, row);
+                        v = small ? ip_single_order<false>(sq, c, dim, qvec) : ip_batch8_order<false>(sq, c, dim, qvec);
+                    } else if (a.metric == LB_L2) {
+                        v = l2_squared<false>(sq, c, dim, qvec);
+                    } else {
+                        v = cosine_distance<false>(sq, c, dim, qvec);
+                    }
+                    key = make_key<ASC>(v, row);
+                }
+                e[i] = key;
+            }
         }
+    };
+    // Thread 0: with the first `cut` candidates rescored and sorted in e, is the top k proven?  Every row that is not
+    // among those candidates has a coarse key <= T: the largest partition floor (nothing is dropped above it inside a
+    // partition) or the key of the first candidate left out.
+    auto certify = [&](int cut) -> bool {
+        uint32_t T_ord = sh_T;
+        if (ncand > cut) T_ord = max(T_ord, ~(uint32_t)(s[cut] >> 32));
+        const int kk = min(a.k, min(ncand, cut));
+        if (sh_overflow) return false;                       // the hit buffer overflowed: candidates were lost
+        if (T_ord <= (ik ? 0u : 0x007FFFFFu)) return true;   // no floor above the lowest key and no candidate left out: the candidates are the whole corpus
+        if (kk < a.k) return false;
+        // Bound on the exact "similarity" (q.c; cos; 2 q.c - |c|^2) of any dropped row, in real arithmetic:
+        //   sim <= value(T) + |dq| cmax + |q~| emax + accumulation slop + rounding slop of the exact f32 score.
+        // Every norm is measured (QStat, ShadowStats); the slack factors cover the f32 evaluation of those norms.
+        const QStat qs = a.qstat[q];
+        const double cmax = (double)__uint_as_float(a.sstat->cmax_bits) * 1.0001, emax = (double)__uint_as_float(a.sstat->emax_bits) * 1.0001;
+        const double u24 = 5.9604644775390625e-8;
+        const double qtn = (double)qs.qt_norm * 1.0001, qn = (double)qs.q_norm;
+        const double dqn = (double)qs.dq_norm * 1.0001 + 4.0 * u24 * qtn;   // + rounding of the held values themselves
+        double T = key_value(T_ord, ik);
+        double eps = dqn * cmax + qtn * (emax + 4.0 * u24 * cmax);
+        if (a.operand == OPERAND_U8) {
+            // key = sum qhat chat exactly;  q~.c~ = s_q s_c key + s_q z_c sum(qhat)
+            const double sq_ = (double)qs.s_q;
+            T = sq_ * (double)a.c_scale * T + sq_ * (double)a.c_zero * (double)qs.sum_qhat;
+            eps += 1e-9 * (fabs(T) + 1.0);
+        } else {
+            // tensor-core accumulation of the bf16 products in f32 (order unspecified): Dp * 2^-21 relative to |q~||c~|
+            eps += (double)((dim + 63) & ~63) * 4.76837158203125e-7 * qtn * (cmax + emax);
+        }
+        const double worst = (double)key_score<ASC>(e[a.k - 1]);
+        if (a.metric == LB_IP) {
+            eps += (double)(dim / 8 + 16) * u24 * qn * cmax;                 // rounding of the exact f32 dot product
+            return worst > T + eps;
+        } else if (a.metric == LB_COSINE) {
+            eps += (double)(dim / 4 + 64) * u24;                             // normalisations + the exact f32 cosine
+            return worst < 1.0 - (T + eps);
+        }
+        // key = 2 q~.c~ - fl(|c|^2);  exact dist = |q - c|^2 >= |q|^2 - (T + eps)
+        eps = 2.0 * eps + (double)(dim / 8 + 32) * u24 * 2.0 * (qn + cmax) * (qn + cmax);
+        return worst < qn * qn * (1.0 - (double)(dim / 8 + 16) * u24) - (T + eps);
+    };
+    // Two rounds: most queries are already proven by the first half of the rescore budget (the rows it fetches are
+    // what the kernel waits for); the rest take the second half and are judged on the whole budget as before.
+    const int R1 = (a.R >= 64 && a.R1 > 0) ? a.R1 : a.R;
+    int cut = R1;
+    rescore(0, R1);
+    bitonic_sort_u64(e, R1);
+    if (tid == 0) sh_done = (R1 == a.R || ncand <= R1 || certify(R1)) ? 1 : 0;
+    __syncthreads();
+    bool certified = true;
+    if (!sh_done) {
+        cut = a.R;
+        rescore(R1, a.R);
+        bitonic_sort_u64(e, a.R);
+        if (tid == 0) certified = certify(a.R);
+    } else if (tid == 0 && (R1 == a.R || ncand <= R1)) {
+        certified = certify(R1);   // (the short-circuit above skipped it)
     }
-    bitonic_sort_u64(e, a.R);
-    const int kk = min(a.k, rn);
+    const int kk = min(a.k, min(ncand, cut));
     for (int i = tid; i < a.k; i += blockDim.x) {
         uint32_t row = ROW_NONE;
         float score = __int_as_float(0x7fc00000);
@@ -1245,46 +1306,6 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinArgs a) {
     }
     if (tid == 0) {
         a.out_counts[q] = kk;
-        bool certified;
-        if (sh_overflow) {
-            certified = false;  // the hit buffer overflowed: candidates were lost
-        } else if (T_ord <= (ik ? 0u : 0x007FFFFFu)) {
-            certified = true;   // no floor above the lowest key: nothing was dropped anywhere, the candidates are the whole corpus
-        } else if (kk < a.k) {
-            certified = false;
-        } else {
-            // Bound on the exact "similarity" (q.c; cos; 2 q.c - |c|^2) of any dropped row, in real arithmetic:
-            //   sim <= value(T) + |dq| cmax + |q~| emax + accumulation slop + rounding slop of the exact f32 score.
-            // Every norm is measured (QStat, ShadowStats); the slack factors cover the f32 evaluation of those norms.
-            const QStat qs = a.qstat[q];
-            const double cmax = (double)__uint_as_float(a.sstat->cmax_bits) * 1.0001, emax = (double)__uint_as_float(a.sstat->emax_bits) * 1.0001;
-            const double u24 = 5.9604644775390625e-8;
-            const double qtn = (double)qs.qt_norm * 1.0001, qn = (double)qs.q_norm;
-            const double dqn = (double)qs.dq_norm * 1.0001 + 4.0 * u24 * qtn;   // + rounding of the held values themselves
-            double T = key_value(T_ord, ik);
-            double eps = dqn * cmax + qtn * (emax + 4.0 * u24 * cmax);
-            if (a.operand == OPERAND_U8) {
-                // key = sum qhat chat exactly;  q~.c~ = s_q s_c key + s_q z_c sum(qhat)
-                const double sq_ = (double)qs.s_q;
-                T = sq_ * (double)a.c_scale * T + sq_ * (double)a.c_zero * (double)qs.sum_qhat;
-                eps += 1e-9 * (fabs(T) + 1.0);
-            } else {
-                // tensor-core accumulation of the bf16 products in f32 (order unspecified): Dp * 2^-21 relative to |q~||c~|
-                eps += (double)((dim + 63) & ~63) * 4.76837158203125e-7 * qtn * (cmax + emax);
-            }
-            const double worst = (double)key_score<ASC>(e[a.k - 1]);
-            if (a.metric == LB_IP) {
-                eps += (double)(dim / 8 + 16) * u24 * qn * cmax;                 // rounding of the exact f32 dot product
-                certified = worst > T + eps;
-            } else if (a.metric == LB_COSINE) {
-                eps += (double)(dim / 4 + 64) * u24;                             // normalisations + the exact f32 cosine
-                certified = worst < 1.0 - (T + eps);
-            } else {
-                // key = 2 q~.c~ - fl(|c|^2);  exact dist = |q - c|^2 >= |q|^2 - (T + eps)
-                eps = 2.0 * eps + (double)(dim / 8 + 32) * u24 * 2.0 * (qn + cmax) * (qn + cmax);
-                certified = worst < qn * qn * (1.0 - (double)(dim / 8 + 16) * u24) - (T + eps);
-            }
-        }
         if (!certified) {
             a.uncertified[q] = 1;
             atomicAdd(a.n_uncertified, 1u);
@@ -1375,95 +1396,6 @@ static __global__ void __launch_bounds__(256) finalize_bits_kernel(FinBitsArgs b
         a.uncertified[q] = certified ? 0u : 1u;
         if (!certified) atomicAdd(a.n_uncertified, 1u);
     }
-}
-
-// ---- diagnostics: tcgen05.mma issue-rate probe ------------------------------------------------------------------
-// One warp issues `iters` MMAs (M=128, K=16, bf16) round-robin over `n_acc` independent accumulators of N columns;
-// operands are whatever is in shared memory / TMEM (timing only); I8 = kind::i8 (K = 32) instead of kind::f16 (K = 16).  Reports SM cycles from first issue to last commit.
-__device__ __forceinline__ void umma_ss_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_ss_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-template <int N, int NACC, bool TS, bool I8>
-__global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters16, int commit_every16, unsigned long long* cycles_out) {
-    extern __shared__ __align__(16) unsigned char smem_probe[];
-    const uint32_t smem_base = (smem_u32(smem_probe) + 1023u) & ~1023u;
-    unsigned char* smem = smem_probe + (smem_base - smem_u32(smem_probe));
-    const uint32_t bar = smem_base + 49152;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 49152 + 32);
-    for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
-    const uint32_t bar2 = bar + 8;  // receives the intermediate commits; nobody waits on it
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar2, 1);
-        fence_barrier_init();
-    }
-    const int warp = threadIdx.x >> 5;
-    if (warp == 0) {
-        __syncwarp();
-        tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
-        tmem_relinquish();
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    if (warp == 0) {
-        const bool leader = elect_one();
-        constexpr uint32_t idesc = make_idesc<I8>(BM, N);
-        const uint64_t a_desc = make_b_desc(smem_base);           // 128 rows x 64 bf16, SW128
-        const uint64_t b_desc = make_b_desc(smem_base + 16384);   // up to 256 rows x 64 bf16
-        constexpr uint32_t d_col0 = TMEM_COLS - NACC * N;
-        long long t0 = clock64(), t1 = t0;
-        if (leader) {
-            for (int it = 0; it < iters16; ++it) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint32_t d = tmem_base + d_col0 + (uint32_t)((j % NACC) * N);
-                    const uint32_t acc = (j < NACC) ? (it > 0 ? 1u : 0u) : 1u;
-                    if (TS && I8)
-                        umma_ts_i8(d, tmem_base + (uint32_t)(j * 8), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
-                    else if (TS)
-                        umma_ts_bf16(d, tmem_base + (uint32_t)(j * 8), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
-                    else if (I8)
-                        umma_ss_i8(d, a_desc + (uint64_t)((j & 3) * 2), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
-                    else
-                        umma_ss_bf16(d, a_desc + (uint64_t)((j & 3) * 2), b_desc + (uint64_t)((j & 3) * 2), idesc, acc);
-                }
-                if (commit_every16 > 0 && (it + 1) % commit_every16 == 0) umma_commit(bar2);
-            }
-            umma_commit(bar);
-            t1 = clock64();
-        }
-        __syncwarp();
-        while (!mbar_try_wait(bar, 0)) {
-        }
-        long long t2 = clock64();
-        if (leader) {
-            cycles_out[2 * blockIdx.x] = (unsigned long long)(t2 - t0);
-            cycles_out[2 * blockIdx.x + 1] = (unsigned long long)(t1 - t0);
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace tc

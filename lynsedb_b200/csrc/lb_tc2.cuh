@@ -352,7 +352,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             if (lane == 0 && eset == 0) mbar_arrive_cluster(even_aready);
             for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
                 const uint32_t buf = tile_iter % NACC;
-                if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter);
+                if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter, (uint32_t)a.poll_mask);
                 if (MT::kBias) side_fetch(min(t + 2, t1 - 1), (t - t0 + 2) % EPI_SCRATCH_SLOTS);
                 const long long ec0 = clock64();
                 if (!mbar_wait(tfull0 + 8u * buf, (tile_iter / NACC) & 1u, abort_flag, 5)) { ok = false; break; }

@@ -377,12 +377,13 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     const uint64_t L = cfg_id == 4 ? 2 : 1;  // shortlists / hit regions per partition
     // List mode: the certification needs the largest partition floor T (the KP-th best coarse key of one partition) to sit
     // well below the k-th best score overall, so the union of the shortlists must reach far past rank k: aim at
-    // P*KP >= 32*k candidates (measured on C3, k = 100: P = 36 leaves 1385 of 1024 queries uncertified, P = 72
-    // five, P >= 144 none).  With a seeded floor the lists only need room for the true top-k: P >= 0.75 k.
+    // P*KP >= 24*k candidates (measured on C3, k = 100: P = 36 leaves 1385 of 1024 queries uncertified, P = 72
+    // five, P >= 144 none; on C2, k = 10, one partition per slot — P = 18, 288 candidates — certifies every query and
+    // halves finalize's sort: 5.12 -> 5.05 ms per step at 10M rows, 0.867 -> 0.844 ms on a 1.25M-row shard).  With a seeded floor the lists only need room for the true top-k: P >= 0.75 k.
     // LYNSE_B200_TC_PARTS overrides.
     uint64_t parts_per_slot = 1;
     if (!hit_mode) {
-        uint64_t want = seeded ? ((uint64_t)3 * k + 3) / 4 : ((uint64_t)32 * k + tc::KP - 1) / tc::KP;
+        uint64_t want = seeded ? ((uint64_t)3 * k + 3) / 4 : ((uint64_t)24 * k + tc::KP - 1) / tc::KP;
         want = ceil_div(want, L);  // a partition contributes L shortlists
         const int env_parts = tc_env_int("LYNSE_B200_TC_PARTS", 0);
         if (env_parts > 0) want = (uint64_t)env_parts;
@@ -440,6 +441,7 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     a.n_slots = (int)n_slots;
     a.parts_per_slot = (int)parts_per_slot;
     a.window = tc_env_int("LYNSE_B200_TC_WINDOW", 16);
+    a.poll_mask = tc_env_int("LYNSE_B200_TC_POLL", 7);
     a.debug_mode = tc_env_int("LYNSE_B200_TC_DEBUG", 0);
     a.prof = nullptr;
     if (getenv("LYNSE_B200_TC_PROF") != nullptr) {
@@ -532,6 +534,8 @@ static void fill_fin_candidates(lb_index* idx, const CoarseJob& job, tc::FinArgs
     f.M1 = job.hit_mode ? TC_FIN_MAX : next_pow2(job.n_lists * tc::KP);
     f.R = std::min(1024, std::max(128, next_pow2(4 * job.k)));
     if (tc_env_int("LYNSE_B200_FIN_R", 0) > 0) f.R = std::max(next_pow2(job.k), next_pow2(tc_env_int("LYNSE_B200_FIN_R", 0)));  // diagnostics
+    // first round: half the budget when that still is at least 2k candidates (LYNSE_B200_FIN_TWO_ROUNDS=0: one round)
+    f.R1 = (tc_env_int("LYNSE_B200_FIN_TWO_ROUNDS", 1) != 0 && f.R >= 64 && f.R / 2 >= 2 * job.k) ? f.R / 2 : 0;
     f.nq = job.nq;
     f.k = job.k;
     f.uncertified = job.flags + 4;
@@ -855,53 +859,6 @@ int lb_debug_tc_scores(const float* queries, uint32_t nq, const float* rows, uin
     lb_index_destroy(idx);
     set_error(keep);
     return st;
-}
-
-int lb_debug_mma_rate(int n, int n_acc, int iters, int a_in_tmem, int i8, int grid, uint64_t* cycles_total, uint64_t* cycles_issue) {
-    if (iters < 16 || grid < 1) return fail(LB_INVALID_ARGUMENT, "bad probe arguments");
-    unsigned long long* d = nullptr;
-    LB_CUDA_TRY(cudaMalloc(&d, (size_t)grid * 16));
-    const size_t smem = 49152 + 64 + 1024;
-    cudaError_t e = cudaSuccess;
-    bool found = false;
-#define LB_PROBE(NN, NA, TSV, I8V)                                                                                         \
-    if (!found && n == NN && n_acc == NA && (a_in_tmem != 0) == TSV && (i8 != 0) == I8V) {                                 \
-        found = true;                                                                                                      \
-        e = cudaFuncSetAttribute(tc::mma_rate_kernel<NN, NA, TSV, I8V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) {                                                                                            \
-            tc::mma_rate_kernel<NN, NA, TSV, I8V><<<grid, 64, smem>>>(iters / 16, tc_env_int("LYNSE_B200_PROBE_COMMIT", 0), d); \
-            e = cudaDeviceSynchronize();                                                                                   \
-        }                                                                                                                  \
-    }
-    LB_PROBE(64, 1, true, false)
-    LB_PROBE(64, 2, true, false)
-    LB_PROBE(128, 1, true, false)
-    LB_PROBE(128, 2, true, false)
-    LB_PROBE(64, 2, false, false)
-    LB_PROBE(128, 2, false, false)
-    LB_PROBE(256, 2, false, false)
-    LB_PROBE(64, 2, true, true)
-    LB_PROBE(128, 1, true, true)
-    LB_PROBE(128, 2, true, true)
-    LB_PROBE(128, 2, false, true)
-    LB_PROBE(256, 2, false, true)
-#undef LB_PROBE
-    if (!found) {
-        cudaFree(d);
-        return fail(LB_INVALID_ARGUMENT, "probe shape not instantiated");
-    }
-    std::vector<unsigned long long> h((size_t)grid * 2);
-    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (e != cudaSuccess) return fail(LB_CUDA, std::string("mma probe: ") + cudaGetErrorString(e));
-    unsigned long long mt = 0, mi = 0;
-    for (int i = 0; i < grid; ++i) {
-        mt = std::max(mt, h[2 * i]);
-        mi = std::max(mi, h[2 * i + 1]);
-    }
-    *cycles_total = mt;
-    *cycles_issue = mi;
-    return LB_OK;
 }
 
 }  // extern "C"

@@ -906,7 +906,8 @@ struct lb_ivf {
     uint64_t n = 0;              // rows covered by the lists
     std::vector<float> centroids;
     std::vector<uint32_t> assignments, offsets, members;
-    std::vector<uint32_t> routing_dims;  // standalone IVF_FLAT inner-product routing (lb_ivf_flat_search), built lazily
+    std::vector<uint32_t> routing_dims;  // standalone IVF_FLAT inner-product routing (lb_ivf_flat_search), built on first use
+    std::once_flag routing_once;         // ... exactly once, whichever thread searches first
     DevBuf d_ids, d_q, d_qw, d_rows, d_dists, d_counts, d_subset;
     DevBuf d_members, d_seg, d_out, d_allow;  // inverted lists in HBM; per-query (src, dst, len) copy descriptors; packed results
     HostBuf h_seg, h_out;                     // pinned staging of the descriptors and the results
@@ -1366,7 +1367,7 @@ int lb_ivf_flat_search(lb_ivf* ivf, const float* queries, uint32_t nq, uint32_t 
         for (uint32_t q = 0; q < nq; ++q)
             for (uint32_t c = 0; c < nc; ++c) probe[(size_t)q * np + c] = c;
     } else if (metric == LB_IP && dim >= 64 && nc >= 64) {
-        if (ivf->routing_dims.empty()) ivf->routing_dims = ivf_routing_dims(ivf->centroids, dim, nc);
+        std::call_once(ivf->routing_once, [&] { ivf->routing_dims = ivf_routing_dims(ivf->centroids, dim, nc); });
         const size_t shortlist = std::min<size_t>(std::max<size_t>(std::min<size_t>((size_t)np * 3, 96), 24), nc);
         probe.assign((size_t)nq * np, ROW_NONE);
         std::vector<std::pair<float, uint32_t>> best(shortlist);
@@ -1820,73 +1821,7 @@ int lb_merge_shard_blocks(int device, int metric, int n_shards, uint32_t nq, uin
 
 }  // extern "C"
 
-// ---- CUDA-core instruction-rate probe (roofline denominators of the non-tensor kernels) ---------------------------------------------
-// Every thread runs `iters` rounds of eight independent dependency chains of one instruction; 2 CTAs x 1024 threads per SM
-// keep every scheduler full.  Result: instructions per clock per SM, from the SM's own cycle counter.
-template <int OP>
-static __global__ void __launch_bounds__(1024, 2) core_rate_kernel(int iters, uint32_t seed, unsigned long long* cycles, uint32_t* sink) {
-    uint32_t x[8];
-    float f[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        x[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u;
-        f[i] = (float)(x[i] & 0xffff) * 1e-5f;
-    }
-    const uint32_t a = seed | 1u, b = seed * 3u + 7u;
-    const float fa = 1.0000001f, fb = 1e-9f;
-    __syncthreads();
-    const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (OP == 0) x[i] = __popc(x[i]) + a;                          // POPC + IADD: the add keeps the chain data-dependent
-            else if (OP == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
-            else if (OP == 2) f[i] = __fmaf_rn(f[i], fa, fb);
-            else if (OP == 3) x[i] = x[i] + a;                               // IADD alone (to subtract from OP 0)
-            else x[i] = max(max(x[i], a), b + (uint32_t)it);                  // VIMNMX3
-        }
-    }
-    const long long t1 = clock64();
-    uint32_t acc = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc ^= x[i] ^ __float_as_uint(f[i]);
-    if (acc == 0x12345678u) sink[0] = acc;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
-}
-
 extern "C" {
-
-int lb_debug_core_rate(int op, int iters, double* inst_per_clk_per_sm) {
-    if (op < 0 || op > 4 || iters < 1 || !inst_per_clk_per_sm) return fail(LB_INVALID_ARGUMENT, "bad probe arguments");
-    int dev = 0, sms = 0;
-    LB_CUDA_TRY(cudaGetDevice(&dev));
-    LB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = sms * 2;
-    unsigned long long* d_cycles = nullptr;
-    uint32_t* d_sink = nullptr;
-    LB_CUDA_TRY(cudaMalloc(&d_cycles, (size_t)grid * 8));
-    LB_CUDA_TRY(cudaMalloc(&d_sink, 4));
-    for (int rep = 0; rep < 2; ++rep) {
-        switch (op) {
-            case 0: core_rate_kernel<0><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
-            case 1: core_rate_kernel<1><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
-            case 2: core_rate_kernel<2><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
-            case 3: core_rate_kernel<3><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
-            default: core_rate_kernel<4><<<grid, 1024>>>(iters, 12345u, d_cycles, d_sink); break;
-        }
-    }
-    cudaError_t e = cudaDeviceSynchronize();
-    std::vector<unsigned long long> h(grid);
-    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_cycles, (size_t)grid * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_cycles);
-    cudaFree(d_sink);
-    if (e != cudaSuccess) return fail(LB_CUDA, std::string("core rate probe: ") + cudaGetErrorString(e));
-    std::sort(h.begin(), h.end());
-    const double cyc = (double)h[grid / 2];
-    // two resident CTAs of 1024 threads per SM, 8 instructions per thread and round
-    *inst_per_clk_per_sm = 2.0 * 1024.0 * 8.0 * (double)iters / cyc;
-    return LB_OK;
-}
 
 int lb_index_event_record(lb_index* idx, int slot) {
     if (!idx || slot < 0 || slot >= 8) return fail(LB_INVALID_ARGUMENT, "bad event slot");

@@ -1,0 +1,7 @@
+#!/bin/bash
+for parts in 18 36; do
+for rows in 1250000 10000000; do
+LYNSE_B200_TC_PARTS=$parts python bench.py --workload c2 --rows $rows --steps 20 --warmup 5 --no-cpu-baseline --no-api-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('parts=$parts c2 rows $rows: ms/step %.3f e2e %.3f kernel %.3f fb %d ids %s P %s' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['kernel_ms'], d['fallback_queries'], d['verified'].get('ids_exact_vs_exact_plan'), d['partitions']))"
+done
+done
+LYNSE_B200_TC_PARTS=18 python bench.py --workload c1 --steps 20 --warmup 5 --no-cpu-baseline --no-api-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('parts=18 c1: ms/step %.3f e2e %.3f kernel %.3f fb %d ids %s P %s' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['kernel_ms'], d['fallback_queries'], d['verified'].get('ids_exact_vs_exact_plan'), d['partitions']))"

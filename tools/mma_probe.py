@@ -6,7 +6,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from lynsedb_b200 import _native as N  # noqa: E402
 
-lib = N.lib()
+lib = N.probe_lib()   # liblynse_b200_probe.so (include/lynse_b200_probe.h)
 iters = 4096
 print("kind  a_src  N  n_acc grid  cyc/MMA(total) cyc/MMA(issue)  ideal   (kind::f16: M=128 x N x K=16; kind::i8: M=128 x N x K=32)")
 for grid in (1, 148):
