@@ -639,6 +639,24 @@ class Collection:
         """row_to_user_id + filter_tombstoned_limit (src/engine.rs:3071-3073, :3286-3308) for a whole batch at once."""
         nq, width = rows.shape
         idx_type, dist_name = M.parse_index_mode(self._index_mode or "FLAT-IP")
+        ids_np = self._row_id_array()
+        fields_of = self._fields
+
+        def lazy(row_block: np.ndarray, d_block: np.ndarray, m: int) -> List[ResultView]:
+            # one id gather for the batch (none at all while ids are the row numbers); views are built when first touched
+            id_block = row_block.astype(np.int64) if self._ids.identity else ids_np[row_block.astype(np.int64)]
+
+            def make(i: int) -> ResultView:
+                flds = [dict(fields_of.get(int(r), {})) for r in row_block[i]] if return_fields else []
+                return ResultView(ids=id_block[i], distances=d_block[i], fields=flds, k=m, distance=dist_name, index=idx_type,
+                                  result_type="search")
+
+            return _LazyViews(nq, make)
+
+        m = min(k, width)
+        if ids_np is not None and nq and not self._tombstones and int(counts.min()) >= m:
+            # the common case: nothing deleted, every query has its k hits -> no masks, no prefix sums
+            return lazy(rows[:, :m], np.ascontiguousarray(dists[:, :m], dtype=np.float32), m)
         valid = np.arange(width)[None, :] < counts[:, None]
         if self._tombstones and width:
             dead = self._dead_row_array()
@@ -647,23 +665,12 @@ class Collection:
             valid &= ~(dead[pos] == rows) if len(dead) else True
         keep = valid & (np.cumsum(valid, axis=1) <= k)
         n_keep = keep.sum(axis=1)
-        ids_np = self._row_id_array()
         out: List[ResultView] = []
         if ids_np is not None and bool((n_keep == np.minimum(counts, k)).all()) and bool(keep[:, :int(n_keep.max(initial=0))].all() if nq else True) \
                 and (nq == 0 or int(n_keep.min()) == int(n_keep.max())):
-            # the common case: nothing filtered, every query has the same number of hits -> two gathers for the batch
+            # nothing filtered out of the leading columns, every query has the same number of hits
             m = int(n_keep[0]) if nq else 0
-            id_block = ids_np[rows[:, :m].astype(np.int64)]
-            d_block = np.ascontiguousarray(dists[:, :m], dtype=np.float32)
-            row_block = rows[:, :m]
-            fields_of = self._fields
-
-            def make(i: int) -> ResultView:
-                flds = [dict(fields_of.get(int(r), {})) for r in row_block[i]] if return_fields else []
-                return ResultView(ids=id_block[i], distances=d_block[i], fields=flds, k=m, distance=dist_name, index=idx_type,
-                                  result_type="search")
-
-            return _LazyViews(nq, make)
+            return lazy(rows[:, :m], np.ascontiguousarray(dists[:, :m], dtype=np.float32), m)
         for i in range(nq):
             sel = np.nonzero(keep[i])[0]
             r = rows[i, sel].astype(np.int64)

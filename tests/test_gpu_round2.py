@@ -484,3 +484,24 @@ def test_float16_collection_on_binary16_storage(L, oracle):
         coll.build_index("IVF-L2", n_clusters=8, nprobe=8)      # the lists need f32 rows: the store is decoded once
         assert coll._store.dtype == "float32"
         assert coll.search(stored[17], k=1, nprobe=8).ids[0] == 17
+
+
+# ---- finalize: two-round rescore ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric,k", [("ip", 10), ("l2", 40), ("cosine", 1)])
+def test_two_round_rescore_equals_one_round(L, oracle, monkeypatch, metric, k):
+    """finalize rescans half of its budget first and the rest only when that half does not prove the top k: both settings
+    return the oracle's ids and score bits, whether or not the first round suffices (clustered scores make it fail)."""
+    rng = np.random.default_rng(77)
+    n, dim, nq = 60_000, 96, 33
+    corpus = rng.random((n, dim), dtype=np.float32)
+    corpus[1000:1400] = corpus[500] + rng.normal(0, 1e-3, (400, dim)).astype(np.float32)   # 400 near-duplicates: a dense score cluster
+    queries = rng.random((nq, dim), dtype=np.float32)
+    queries[:8] = corpus[500] + rng.normal(0, 1e-3, (8, dim)).astype(np.float32)            # ... which these queries land in
+    want = oracle.store_batch_search(corpus, queries, k, metric, n_threads=1)
+    for flag in ("1", "0"):
+        monkeypatch.setenv("LYNSE_B200_FIN_TWO_ROUNDS", flag)
+        with L.DeviceIndex(dim) as idx:
+            idx.append(corpus)
+            got = idx.search(queries, k, metric)
+            assert idx.last_stats()["plan_used"] == 1
+        _same(want, got)

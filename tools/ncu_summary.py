@@ -89,3 +89,50 @@ def launch(path, out):
 
 if __name__ == "__main__":
     {"full": full, "launch": launch}[sys.argv[1]](sys.argv[2], sys.argv[3])
+
+
+def raw_csv(raw, out, note):
+    """`ncu -i rep --page raw --csv` output (already exported on the GPU box) -> the same small JSON as full()."""
+    rows = list(csv.reader(open(raw)))
+    hdr, units = rows[0], rows[1]
+    kernels = []
+    for vals in rows[2:]:
+        d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+        k = {"kernel": d.get("Kernel Name", ("?", ""))[0]}
+        for key in KEYS:
+            if key in d:
+                v, u = d[key]
+                try:
+                    v = float(v.replace(",", ""))
+                except ValueError:
+                    pass
+                k[key] = {"value": v, "unit": u}
+        kernels.append(k)
+    json.dump({"source": raw, "note": note, "command": "ncu --set full --clock-control none --import-source on (tools/gpu_r2_ncu.sh)",
+               "kernels": kernels}, open(out, "w"), indent=1)
+
+
+def steps(path, title, f):
+    """Launch list (gpu__time_duration.sum per launch) -> the kernels of the LAST step of the run and their share of it."""
+    lines = open(path).read().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
+    rows = list(csv.reader(lines[start:]))
+    h = rows[0]
+    ki, mi, vi, ui = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit")
+    seq = []
+    for r in rows[1:]:
+        if len(r) > vi and r[mi] == "gpu__time_duration.sum":
+            mult = {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[ui], 1.0)
+            seq.append((r[ki].split("(")[0].replace("void ", ""), float(r[vi].replace(",", "")) * mult))
+    # a step starts at the query preparation kernel; take the last complete one before the verification launches
+    starts = [i for i, (n, _) in enumerate(seq) if "quantise_queries" in n or "prepare_queries" in n or "prepare_bits_queries" in n or "query_range" in n]
+    firsts = [i for j, i in enumerate(starts) if j == 0 or starts[j - 1] != i - 1]
+    if len(firsts) < 2:
+        return
+    a, b = firsts[-2], firsts[-1]
+    step = seq[a:b]
+    total = sum(t for _, t in step)
+    f.write(f"\n### {title}\n\n| kernel | time (us) | share of the step's device time |\n|---|---|---|\n")
+    for n, t in step:
+        f.write(f"| {n} | {t:.1f} | {100 * t / total:.1f}% |\n")
+    f.write(f"| **sum** | **{total:.1f}** | |\n")
