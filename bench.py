@@ -104,12 +104,13 @@ def measured_peaks():
 
 def ncu_traffic(args, world, nq):
     """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the dominant kernel, per launch, from the committed
-    `ncu --set full` capture of this same command (profiles/r1_coarse_pair_ncu.json); None when the run is not the
-    captured configuration."""
-    if args.workload != "c2" or args.rows or args.nq or world != 1 or args.plan != "auto":
+    `ncu --set full` capture of this same command (profiles/r2_coarse_pair*_ncu.json); None when the run is not a
+    captured configuration.  (C4's step is two launches of 2048 queries: the figure is per launch, like `achieved`.)"""
+    name = {"c2": "r2_coarse_pair_ncu.json", "c3": "r2_coarse_pair_c3_ncu.json", "c4": "r2_coarse_pair_c4_ncu.json"}.get(args.workload)
+    if name is None or args.rows or args.nq or world != 1 or args.plan != "auto":
         return None
     try:
-        d = json.loads((ROOT / "profiles" / "r2_coarse_pair_ncu.json").read_text())["kernels"][0]
+        d = json.loads((ROOT / "profiles" / name).read_text())["kernels"][0]
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
         return rd["value"] * mult[rd["unit"]] + wr["value"] * mult[wr["unit"]]
@@ -480,7 +481,7 @@ def roofline_of(rig, res, peaks, args, info):
         # (profiles/r2_mma_issue_probe.txt), so its ceiling is twice the measured bf16 one
         peak = peaks["bf16_tflops_sustained"] * (2.0 if eight else 1.0)
         return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TOP/s" if eight else "TFLOP/s", "frac": ach / peak,
-                "traffic": ncu_traffic(args, rig.world, nq), "traffic_source": "profiles/r2_coarse_pair_ncu.json (ncu --set full, one launch of this command)",
+                "traffic": ncu_traffic(args, rig.world, nq), "traffic_source": "profiles/r2_coarse_pair[_c3|_c4]_ncu.json (ncu --set full, one launch of this command)",
                 "algorithmic_bytes": float(st["algorithmic_bytes"]),
                 "kernel": "lb::tc::coarse_pair_kernel" if nq > 128 else "lb::tc::coarse_single_kernel", "kernel_ms": dom_ms,
                 "operand": "u8 x u8 -> s32 (tcgen05 kind::i8)" if eight else "bf16 x bf16 -> f32 (tcgen05 kind::f16)",
