@@ -297,6 +297,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t* v) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, naming the 32 destination registers of the load it completes as read-write operands: when other work
+// runs between a tcgen05.ld and its wait (the pipelined epilogue), no use of those registers can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait_32(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -569,20 +580,27 @@ struct Shortlist {
             }
         }
     }
-    // 64 accumulators of this thread's query = rows row0 .. row0+63.  Called by whole warps.
+    // 16 * NG accumulators of this thread's query = rows row0 .. row0 + 16 NG - 1 (row0 a multiple of 32).  Called by whole warps.
     // The slow path must stay SMALL: a fully unrolled "for each of the 64 scores: compare, insert" is ~90 KB of code
     // whose sparse execution misses the instruction cache at every step (~7700 cycles per tile measured).  So: the
-    // maxima of the four 16-score groups gate (1) a 16-bit hit mask per lane from straight compares and (2) a rolled
+    // maxima of the 16-score groups gate (1) a 16-bit hit mask per lane from straight compares and (2) a rolled
     // loop that pops each lane's lowest hit and fetches the accumulator with a select tree.
-    __device__ __forceinline__ void scan64(const uint32_t* v, const uint32_t* side, uint32_t row0, uint32_t row_end, bool disabled,
-                                           const uint64_t* __restrict__ allow = nullptr) {
+    // The scan in two parts, so that a caller can put work (releasing the accumulator buffer) between the cheap test and
+    // the rare slow path: scan_fast computes the group maxima against the current gate and tells whether any lane of the
+    // warp has a hit; scan_slow visits the groups that do.  Nothing else may touch the gate in between.
+    template <int NG>
+    struct ScanState {
+        K g[NG];
+        K thr, tthr;
+    };
+    template <int NG>
+    __device__ __forceinline__ bool scan_fast(const uint32_t* v, const uint32_t* side, bool disabled, ScanState<NG>& st) {
         constexpr bool kBias = ModeTraits<MODE>::kBias;
-        const K thr = disabled ? O::highest() : gate();
-        fn.set_gate(thr);
-        const K tthr = fn.test_thr(thr);
-        K g[4];
+        st.thr = disabled ? O::highest() : gate();
+        fn.set_gate(st.thr);
+        st.tthr = fn.test_thr(st.thr);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NG; ++j) {
             uint32_t s[16];
             if (kBias) {
 #pragma unroll
@@ -596,18 +614,39 @@ struct Shortlist {
             K m = O::max3(fn.test(a[0], kBias ? s[0] : 0u), fn.test(a[1], kBias ? s[1] : 0u), fn.test(a[2], kBias ? s[2] : 0u));
 #pragma unroll
             for (int i = 3; i + 1 < 16; i += 2) m = O::max3(m, fn.test(a[i], kBias ? s[i] : 0u), fn.test(a[i + 1], kBias ? s[i + 1] : 0u));
-            g[j] = max(m, fn.test(a[15], kBias ? s[15] : 0u));
+            st.g[j] = max(m, fn.test(a[15], kBias ? s[15] : 0u));
         }
-        if (__any_sync(0xffffffffu, O::max3(max(g[0], g[1]), g[2], g[3]) > tthr)) {
-            uint64_t w = ~0ull;
-            const bool have_allow = allow != nullptr;
-            if (have_allow) w = row0 < row_end ? __ldg(allow + (row0 >> 6)) : 0ull;  // row0 is a multiple of 64
+        K gall = st.g[0];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (__any_sync(0xffffffffu, g[j] > tthr))
-                    slow16(v + 16 * j, side + 16 * j, g[j], row0 + 16u * j, row_end, thr, tthr, (uint32_t)(w >> (16 * j)) & 0xffffu, have_allow);
-            if (may_publish && q_valid && lmin > thr_pub && lmin > thr_g) publish();
-        }
+        for (int j = 1; j < NG; ++j) gall = max(gall, st.g[j]);
+        return __any_sync(0xffffffffu, gall > st.tthr) != 0;
+    }
+    template <int NG>
+    __device__ __forceinline__ void scan_slow(const uint32_t* v, const uint32_t* side, uint32_t row0, uint32_t row_end,
+                                              const uint64_t* __restrict__ allow, const ScanState<NG>& st) {
+        uint64_t w = ~0ull;
+        const bool have_allow = allow != nullptr;
+        if (have_allow) w = row0 < row_end ? __ldg(allow + (row0 >> 6)) >> (row0 & 63u) : 0ull;  // bit 0 = row0
+#pragma unroll
+        for (int j = 0; j < NG; ++j)
+            if (__any_sync(0xffffffffu, st.g[j] > st.tthr))
+                slow16(v + 16 * j, side + 16 * j, st.g[j], row0 + 16u * j, row_end, st.thr, st.tthr, (uint32_t)(w >> (16 * j)) & 0xffffu, have_allow);
+        if (may_publish && q_valid && lmin > thr_pub && lmin > thr_g) publish();
+    }
+    // 16 * NG accumulators of this thread's query = rows row0 .. row0 + 16 NG - 1 (row0 a multiple of 32).  Called by whole warps.
+    // The slow path must stay SMALL: a fully unrolled "for each of the 64 scores: compare, insert" is ~90 KB of code
+    // whose sparse execution misses the instruction cache at every step (~7700 cycles per tile measured).  So: the
+    // maxima of the 16-score groups gate (1) a 16-bit hit mask per lane from straight compares and (2) a rolled
+    // loop that pops each lane's lowest hit and fetches the accumulator with a select tree.
+    template <int NG>
+    __device__ __forceinline__ void scan_groups(const uint32_t* v, const uint32_t* side, uint32_t row0, uint32_t row_end, bool disabled,
+                                                const uint64_t* __restrict__ allow = nullptr) {
+        ScanState<NG> st;
+        if (scan_fast<NG>(v, side, disabled, st)) scan_slow<NG>(v, side, row0, row_end, allow, st);
+    }
+    __device__ __forceinline__ void scan64(const uint32_t* v, const uint32_t* side, uint32_t row0, uint32_t row_end, bool disabled,
+                                           const uint64_t* __restrict__ allow = nullptr) {
+        scan_groups<4>(v, side, row0, row_end, disabled, allow);
     }
     // `sub`: which of the partition's lists_per_part shortlists this is (the pair kernel with two epilogue sets)
     __device__ __forceinline__ void flush(const TcArgs& a, uint32_t gq, uint32_t part, uint32_t sub = 0) {

@@ -350,48 +350,105 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0 && eset == 0) mbar_arrive_cluster(even_aready);
-            for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
-                const uint32_t buf = tile_iter % NACC;
-                if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter, (uint32_t)a.poll_mask);
-                if (MT::kBias) side_fetch(min(t + 2, t1 - 1), (t - t0 + 2) % EPI_SCRATCH_SLOTS);
-                const long long ec0 = clock64();
-                if (!mbar_wait(tfull0 + 8u * buf, (tile_iter / NACC) & 1u, abort_flag, 5)) { ok = false; break; }
-                const long long ec1 = clock64();
-                tcgen05_fence_after();
+            if constexpr (!MT::kBias && EPI_ == 2) {
+                // Pipelined drain (two epilogue sets, modes without side values — the short tiles of narrow rows, where the
+                // TMEM read latency, ~200 cycles per 64 columns, is a third of a tile's budget): this warp's 64 columns of a
+                // tile come out of TMEM as two units of 32, A in v[0, 32) and B in v[32, 64).  B's load is in flight under
+                // the test of A; the tile's buffer is released as soon as B has landed — before any slow path, so a warp
+                // with a hit never holds the accumulator ring up —; the next tile's A is in flight under the whole of B.
+                const uint32_t col0 = (uint32_t)eset * 64u;
+                const bool scan_disabled = (a.debug_mode & 4) != 0;
+                using SL = Shortlist<MODE_, HITS_>;
                 uint32_t v[64];
-#pragma unroll
-                for (int h = 0; h < BN_ / 64; ++h) {
-                    if (EPI_ == 2 && h != eset) continue;  // the other set's half
-                    if (!(a.debug_mode & 2)) {
-                        tmem_ld_32x32b_x64(lane_addr + DCOL + buf * BN + h * 64, v);
-                        tmem_ld_wait();
-                    }
-                    if (EPI_ == 2 || h == BN_ / 64 - 1) {
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(even_tempty0 + 8u * buf);  // accumulator is in registers
-                        e_wait += ec1 - ec0;
-                        e_ld += clock64() - ec1;
-                    }
-                    if (a.debug_mode & 2) continue;
-                    const uint32_t row0 = t * BN + h * 64;
-                    const long long sc0 = clock64();
-                    if (MT::kBias && (EPI_ == 2 || h == 0)) {
-                        cp_async_wait<2>();  // this tile's side values have landed (the two younger groups may be in flight)
-                        __syncwarp();
-                    }
-                    const uint32_t* side = scratch + ((t - t0) % EPI_SCRATCH_SLOTS) * SLOT_WORDS + (EPI_ == 2 ? 0 : h * 64);
+                auto acquire = [&](uint32_t ti) -> bool {   // tile (running index ti) complete in TMEM?
+                    const long long ec0 = clock64();
+                    if (!mbar_wait(tfull0 + 8u * (ti % NACC), (ti / NACC) & 1u, abort_flag, 5)) return false;
+                    e_wait += clock64() - ec0;
+                    tcgen05_fence_after();
+                    return true;
+                };
+                auto unit_addr = [&](uint32_t ti, uint32_t uu) { return lane_addr + DCOL + (ti % NACC) * BN + col0 + uu * 32u; };
+                auto dump_unit = [&](const uint32_t* src, uint32_t row0) {
                     if (a.dump != nullptr) {
                         float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
-                        for (int i = 0; i < 64; ++i) drow[i] = KO::as_f32(sl.fn.key(v[i], MT::kBias ? side[i] : 0u));
+                        for (int i = 0; i < 32; ++i) drow[i] = KO::as_f32(sl.fn.key(src[i], 0u));
                     }
-                    sl.scan64(v, side, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
-                    const long long sd = clock64() - sc0;
+                };
+                ok = t1 == t0 || acquire(tile_iter);
+                if (ok && t1 > t0) tmem_ld_32x32b_x32(unit_addr(tile_iter, 0u), v);
+                for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
+                    if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter, (uint32_t)a.poll_mask);
+                    const uint32_t rowA = t * BN + col0, rowB = rowA + 32u;
+                    const long long lc0 = clock64();
+                    tmem_ld_wait_32(v);                                            // A has landed
+                    tmem_ld_32x32b_x32(unit_addr(tile_iter, 1u), v + 32);          // B on its way
+                    const long long sc0 = clock64();
+                    typename SL::template ScanState<2> stA, stB;
+                    dump_unit(v, rowA);
+                    const bool hitA = sl.template scan_fast<2>(v, nullptr, scan_disabled, stA);
+                    const long long sc1 = clock64();
+                    tmem_ld_wait_32(v + 32);                                       // B has landed: the tile is in registers
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(even_tempty0 + 8u * (tile_iter % NACC));
+                    const long long sc2 = clock64();
+                    e_ld += (sc0 - lc0) + (sc2 - sc1);
+                    if (hitA) sl.template scan_slow<2>(v, nullptr, rowA, a.n_rows, a.allow_bits, stA);
+                    if (t + 1 < t1) {                                              // next tile's A under the scan of B
+                        ok = acquire(tile_iter + 1u);
+                        if (ok) tmem_ld_32x32b_x32(unit_addr(tile_iter + 1u, 0u), v);
+                    }
+                    dump_unit(v + 32, rowB);
+                    if (sl.template scan_fast<2>(v + 32, nullptr, scan_disabled, stB)) sl.template scan_slow<2>(v + 32, nullptr, rowB, a.n_rows, a.allow_bits, stB);
+                    const long long sd = (sc1 - sc0) + (clock64() - sc2);
                     e_scan += sd;
                     if (sd > 400) { ++n_slow; e_slow += sd; }
                     if (sd > e_max) e_max = sd;
                 }
-                if (MT::kBias) __syncwarp();  // every lane is done reading this tile's slot before a later fetch reuses it
+            } else {
+                for (uint32_t t = t0; t < t1; ++t, ++tile_iter) {
+                    const uint32_t buf = tile_iter % NACC;
+                    if (!(a.debug_mode & 128)) sl.poll_floor(tile_iter, (uint32_t)a.poll_mask);
+                    if (MT::kBias) side_fetch(min(t + 2, t1 - 1), (t - t0 + 2) % EPI_SCRATCH_SLOTS);
+                    const long long ec0 = clock64();
+                    if (!mbar_wait(tfull0 + 8u * buf, (tile_iter / NACC) & 1u, abort_flag, 5)) { ok = false; break; }
+                    const long long ec1 = clock64();
+                    tcgen05_fence_after();
+                    uint32_t v[64];
+#pragma unroll
+                    for (int h = 0; h < BN_ / 64; ++h) {
+                        if (EPI_ == 2 && h != eset) continue;  // the other set's half
+                        if (!(a.debug_mode & 2)) {
+                            tmem_ld_32x32b_x64(lane_addr + DCOL + buf * BN + h * 64, v);
+                            tmem_ld_wait();
+                        }
+                        if (EPI_ == 2 || h == BN_ / 64 - 1) {
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(even_tempty0 + 8u * buf);  // accumulator is in registers
+                            e_wait += ec1 - ec0;
+                            e_ld += clock64() - ec1;
+                        }
+                        if (a.debug_mode & 2) continue;
+                        const uint32_t row0 = t * BN + h * 64;
+                        const long long sc0 = clock64();
+                        if (MT::kBias && (EPI_ == 2 || h == 0)) {
+                            cp_async_wait<2>();  // this tile's side values have landed (the two younger groups may be in flight)
+                            __syncwarp();
+                        }
+                        const uint32_t* side = scratch + ((t - t0) % EPI_SCRATCH_SLOTS) * SLOT_WORDS + (EPI_ == 2 ? 0 : h * 64);
+                        if (a.dump != nullptr) {
+                            float* drow = a.dump + (size_t)gq * ((size_t)a.tiles_total * BN) + row0;
+                            for (int i = 0; i < 64; ++i) drow[i] = KO::as_f32(sl.fn.key(v[i], MT::kBias ? side[i] : 0u));
+                        }
+                        sl.scan64(v, side, row0, a.n_rows, (a.debug_mode & 4) != 0, a.allow_bits);
+                        const long long sd = clock64() - sc0;
+                        e_scan += sd;
+                        if (sd > 400) { ++n_slow; e_slow += sd; }
+                        if (sd > e_max) e_max = sd;
+                    }
+                    if (MT::kBias) __syncwarp();  // every lane is done reading this tile's slot before a later fetch reuses it
+                }
             }
             if (MT::kBias) cp_async_wait<0>();
             if (ok) sl.flush(a, gq, part, (uint32_t)eset);
