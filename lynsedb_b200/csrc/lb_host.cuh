@@ -197,7 +197,7 @@ struct lb_index {
     int n_small = 0;
     size_t small_seg_sig = ~(size_t)0;
     // workspace
-    DevBuf w_queries, w_qwords, w_allow, w_lists, w_counts, w_thr, w_out_rows, w_out_dists, w_out_counts, w_qtiles;
+    DevBuf w_queries, w_qwords, w_allow, w_lists, w_counts, w_thr, w_out_rows, w_out_dists, w_out_counts, w_qtiles, w_pbest;
     DevBuf w_out;            // host-buffer searches: [rows | dists | counts] of one batch, so that one copy brings them back
     HostBuf h_in, h_out;     // pinned staging for small batches
     HostBuf h_tails;         // sharded search: the gathered block tails (one read per step)

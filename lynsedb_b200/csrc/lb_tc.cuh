@@ -94,6 +94,10 @@ struct TcArgs {
     int share_floor;          // 1: partitions of a query share a shortlist floor through gthr; 2: gthr holds a floor seeded by a
                               // pre-pass over a sample of the corpus and is only read (large k)
     uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable key bits)
+    uint32_t* pbest2;         // optional [nq][PBEST_STRIDE] zero-initialised: second-best key (orderable bits) each partition of a
+                              // query holds so far.  When all partitions run at once, the smallest of them is a floor with at
+                              // least two rows above it in EVERY partition — 2 P rows, far tighter early in the pass than the
+                              // 16th best of one partition's rows so far, which is all a single list knows
     // hit mode (with share_floor == 2): rows above the seeded floor are appended to the hit region of their
     // (query, shortlist slot) instead of going through the register shortlists — a private region per epilogue
     // thread and partition, so appending is one store and a register increment, no atomic
@@ -115,6 +119,7 @@ struct TcArgs {
                               // bit 1 = epilogue releases accumulators unread, bit 2 = epilogue reads but does not scan
 };
 constexpr int PROGRESS_STRIDE = 32;
+constexpr int PBEST_STRIDE = 20;   // partitions per query the second-best exchange serves (five 16-byte loads per poll)
 constexpr uint32_t EPI_SCRATCH_SLOTS = 3;    // side values travel global -> shared memory with cp.async, two tiles ahead of their use
 constexpr uint32_t EPI_SCRATCH_WORDS = 128;  // per slot: the side values of the (up to) 128 rows of a tile
 
@@ -453,6 +458,14 @@ struct Shortlist {
     K lmin, thr_g, thr_pub;
     uint32_t g_bits;
     uint32_t* gthr;
+    // second-best exchange (list mode, every partition of the query in flight): best and second-best key of this list,
+    // where this list publishes its second best, the query's row of the exchange, the words loaded by the last poll
+    K best1, best2;
+    uint32_t* pb_slot;
+    const uint32_t* pb_row;
+    uint4 pb_v[PBEST_STRIDE / 4];
+    uint32_t pb_n;             // partitions of the query (0 = exchange off)
+    bool pb_loaded;
     uint2* hit_buf;
     uint32_t hit_n, hit_cap;
     KeyFn<MODE> fn;
@@ -486,6 +499,17 @@ struct Shortlist {
         }
         lmin = O::lowest();
         thr_pub = O::lowest();
+        best1 = O::lowest();
+        best2 = O::lowest();
+        pb_n = 0u;
+        pb_loaded = false;
+        pb_slot = nullptr;
+        pb_row = nullptr;
+        if (!HITS && valid && a.pbest2 != nullptr && a.share_floor == 1 && a.parts_per_slot == 1 && a.lists_per_part == 1 && a.P <= PBEST_STRIDE) {
+            pb_n = (uint32_t)a.P;
+            pb_row = a.pbest2 + (size_t)gq * PBEST_STRIDE;
+            pb_slot = a.pbest2 + (size_t)gq * PBEST_STRIDE + part;
+        }
     }
     __device__ __forceinline__ void init_floor(float qaux) {
         thr_g = O::lowest();
@@ -499,11 +523,41 @@ struct Shortlist {
         if (!HITS && share && (tile_iter & mask) == 0u) {
             if (g_bits != 0u) thr_g = max(thr_g, O::from_orderable(g_bits));
             g_bits = *reinterpret_cast<volatile uint32_t*>(gthr);
+            if (pb_n != 0u) {
+                // the smallest second-best over the query's partitions (0 = some partition has not published yet: no floor)
+                if (pb_loaded) {
+                    uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int i = 0; i < PBEST_STRIDE / 4; ++i) {
+                        const uint32_t w[4] = {pb_v[i].x, pb_v[i].y, pb_v[i].z, pb_v[i].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) m = min(m, (uint32_t)(4 * i + j) < pb_n ? w[j] : 0xFFFFFFFFu);
+                    }
+                    if (m != 0u) thr_g = max(thr_g, O::from_orderable(m));
+                }
+#pragma unroll
+                for (int i = 0; i < PBEST_STRIDE / 4; ++i) {
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(pb_v[i].x), "=r"(pb_v[i].y), "=r"(pb_v[i].z), "=r"(pb_v[i].w)
+                                 : "l"(pb_row + 4 * i));
+                }
+                pb_loaded = true;
+            }
         }
     }
     // replace the current minimum by (key, row) and recompute the minimum: ~70 ALU instructions, no memory
     __device__ __forceinline__ void insert(K key, uint32_t row) {
         if (HITS) return;
+        if (pb_n != 0u) {
+            const K old2 = best2;
+            if (key > best1) {
+                best2 = best1;
+                best1 = key;
+            } else if (key > best2) {
+                best2 = key;
+            }
+            if (best2 > old2) *reinterpret_cast<volatile uint32_t*>(pb_slot) = O::orderable(best2);  // single writer
+        }
         bool done = false;
 #pragma unroll
         for (int j = 0; j < NL; ++j) {

@@ -433,6 +433,15 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     // the final floor well below the k-th best score).  For k <= KP - 4 the KP-th best key of one partition will do.
     a.share_floor = k <= tc::KP - 4 ? 1 : 0;
     if (seeded) a.share_floor = 2;
+    // second-best exchange between the partitions of a query (list mode, every partition in flight at once, few enough of
+    // them for one poll): LYNSE_B200_TC_PBEST=0 turns it off
+    a.pbest2 = nullptr;
+    if (a.share_floor == 1 && parts_per_slot == 1 && L == 1 && P >= 8 && P <= (uint64_t)tc::PBEST_STRIDE && 2 * P >= (uint64_t)k + 4 &&
+        tc_env_int("LYNSE_B200_TC_PBEST", 1) != 0) {
+        LB_TRY(idx->w_pbest.ensure((size_t)nq * tc::PBEST_STRIDE * 4));
+        LB_CUDA_TRY(cudaMemsetAsync(idx->w_pbest.p, 0, (size_t)nq * tc::PBEST_STRIDE * 4, idx->stream));
+        a.pbest2 = idx->w_pbest.as<uint32_t>();
+    }
     a.hit_count = nullptr;
     a.hit_buf = nullptr;
     a.hit_cap = 0;
