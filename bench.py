@@ -571,11 +571,13 @@ def main():
     e2e_value = nq * args.steps / (res["ms_e2e"] / 1000.0)
     st = res["st"]
     roofline = roofline_of(rig, res, peaks, args, info)
-    if rank == 0 and roofline and roofline.get("bound") == "tensor" and clocks and clocks.get("sm_mhz"):
+    kernel_mhz = float(st.get("coarse_sm_mhz") or 0.0)
+    if rank == 0 and roofline and roofline.get("bound") == "tensor" and kernel_mhz > 0:
         # what the tensor pipe can do at the SM clock this run actually held (the B200 power-caps dense 8-bit / bf16 MMAs):
         # 4096 bf16 MACs (8192 8-bit MACs) per clock per SM, i.e. the 64-cycle M128 x N128 MMA of profiles/r2_mma_issue_probe.txt
         macs = 8192.0 if st["coarse_operand"] == 1 else 4096.0
-        pipe = 2.0 * macs * info["sm_count"] * clocks["sm_mhz"] * 1e6 / 1e12
+        pipe = 2.0 * macs * info["sm_count"] * kernel_mhz * 1e6 / 1e12
+        roofline["kernel_sm_mhz"] = kernel_mhz   # the kernel's own cycle counter over its own wall time (nvidia-smi samples too coarsely)
         roofline["pipe_peak_at_observed_clock"] = pipe
         roofline["frac_of_pipe_at_observed_clock"] = roofline["achieved"] / pipe
 

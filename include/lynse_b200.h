@@ -182,6 +182,8 @@ typedef struct lb_search_stats {
     uint64_t algorithmic_flops;/* 2*nq*n*dim for the tensor path, else 0 */
     uint32_t coarse_operand;   /* tensor plans: 0 = bf16 operands (f32 accumulators), 1 = 8-bit operands (s32 accumulators) */
     uint32_t coarse_hit_mode;  /* tensor plans: 1 = rows above a seeded floor were appended to per-query hit buffers (large k) */
+    float coarse_sm_mhz;       /* tensor plans: SM clock the coarse kernel actually ran at (its own cycle counter over its own wall time) */
+    uint32_t reserved;
 } lb_search_stats;
 int lb_index_set_timing(lb_index* idx, int enabled);
 int lb_index_last_stats(const lb_index* idx, lb_search_stats* out);

@@ -34,6 +34,8 @@ class SearchStats(C.Structure):
         ("algorithmic_flops", C.c_uint64),
         ("coarse_operand", C.c_uint32),
         ("coarse_hit_mode", C.c_uint32),
+        ("coarse_sm_mhz", C.c_float),
+        ("reserved", C.c_uint32),
     ]
 
     def as_dict(self):

@@ -770,6 +770,7 @@ int tc_finish(lb_index* idx, bool* changed) {
     if (head[0] != 0)
         return fail(LB_INTERNAL, "tensor-core coarse kernel: barrier wait timed out (code " + std::to_string(head[0]) + ")");
     idx->stats.n_fallback = head[1];
+    if (head[3] > 0) idx->stats.coarse_sm_mhz = (float)((double)head[2] * 16.0 / (double)head[3] * 1e3);  // cycles >> 4 over nanoseconds of CTA 0
     if (head[1] == 0) return LB_OK;
     // Re-run the uncertified queries with the exact scan and overwrite their result slots.
     if (changed) *changed = true;

@@ -719,6 +719,7 @@ static int search_host_common(lb_index* idx, int score_mode, int metric, const v
         acc.algorithmic_flops += idx->stats.algorithmic_flops;
         acc.coarse_operand = idx->stats.coarse_operand;
         acc.coarse_hit_mode = idx->stats.coarse_hit_mode;
+        acc.coarse_sm_mhz = idx->stats.coarse_sm_mhz;
     }
     idx->stats = acc;
     return LB_OK;
