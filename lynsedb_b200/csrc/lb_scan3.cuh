@@ -27,9 +27,15 @@ __host__ __device__ inline bool scan4_supported(int metric) {
            metric == LB_BRAY_CURTIS;
 }
 
-// warps per CTA: the row block (16 rows per warp) takes at most 64 KiB, so two CTAs fit an SM and one computes while
-// the other waits for its rows
-inline int scan4_warps(int dim) { return dim <= 128 ? 8 : (dim <= 256 ? 4 : 2); }
+// warps per CTA: four (a 64-row block, at most 64 KiB up to 256 dims) or two (32 rows, up to 512 dims), so that two CTAs
+// fit an SM and one computes while the other waits for its rows.  Measured at 64 queries (tools/gpu_r2_tile_shapes.sh,
+// L1 on 4.1 GB of rows): 256 dims — 4 warps 6.8 ms, 8 warps (one CTA per SM) 7.2, 2 warps x 4 CTAs 8.1; 128 dims — 4 warps
+// 8.5 ms, 8 warps 9.1.  LYNSE_B200_SCAN_TILE_NW forces 4 or 2.
+inline int scan4_warps(int dim) {
+    const char* env = getenv("LYNSE_B200_SCAN_TILE_NW");
+    if (env && (atoi(env) == 4 || atoi(env) == 2)) return atoi(env);
+    return dim <= 256 ? 4 : 2;
+}
 
 // TQW: queries per register tile.  16 for the one-accumulator metrics (64 accumulators per thread), 8 for the
 // two-accumulator ones — and for everything above 256 dims, where the smaller query tile lets two CTAs share an SM.
@@ -114,7 +120,7 @@ __device__ __forceinline__ void lane_step(float& s0, float& s1, float q, float c
 }
 
 template <int METRIC, bool IP2, int NW, int TQW>
-__global__ void __launch_bounds__(NW * 32, 2) scan_tile_kernel(const __grid_constant__ CUtensorMap tmap, ScanArgs a) {
+__global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(const __grid_constant__ CUtensorMap tmap, ScanArgs a) {
     using Op = Scan2Op<METRIC, IP2>;
     using Cfg = S4Cfg<METRIC, IP2, TQW>;
     constexpr int R = S4_R, TQ = Cfg::kTQ, KS = Op::kState, SROW = Cfg::kSRow, QS = Cfg::kQStride;

@@ -52,8 +52,7 @@ int dense_scan_launch(lb_index* idx, const ScanRequest& r, ScanArgs& a, const Sc
     } while (0)
 #define LB_LAUNCH_S4(M, IP2V)                                   \
     do {                                                        \
-        if (nw == 8) LB_LAUNCH_S4W(M, IP2V, 8);                 \
-        else if (nw == 4) LB_LAUNCH_S4W(M, IP2V, 4);            \
+        if (nw == 4) LB_LAUNCH_S4W(M, IP2V, 4);                 \
         else LB_LAUNCH_S4W(M, IP2V, 2);                         \
     } while (0)
             switch (r.metric) {

@@ -37,7 +37,9 @@ int run_scan(lb_index* idx, const ScanRequest& r, int* kernels, float* ms_dom) {
     const bool tile_f32 = !r.words && !r.f16_rows && r.corpus != nullptr && r.corpus_h == nullptr && s2_metric && scan4_supported(r.metric) &&
                           r.row_ids == nullptr && (r.dim & 3) == 0 && r.dim >= 8 && r.dim <= 512 && r.n_rows >= 4096 &&
                           r.nq >= tc_env_int("LYNSE_B200_SCAN_TILE_MIN_Q", 12) && tc_env_int("LYNSE_B200_SCAN_TILE", 1) != 0;
-    ScanPlan sp = plan_scan(idx, r.n_rows, r.nq, r.k, (tma_f32 && r.corpus_h == nullptr) ? 1 : 2);
+    int ctas_per_sm = (tma_f32 && r.corpus_h == nullptr) ? 1 : 2;
+    if (tile_f32) ctas_per_sm = std::max(1, std::min(tc_env_int("LYNSE_B200_SCAN_TILE_CTAS", 2), 4));
+    ScanPlan sp = plan_scan(idx, r.n_rows, r.nq, r.k, ctas_per_sm);
     size_t nl = (size_t)sp.P * r.nq;
     LB_TRY(idx->w_lists.ensure(nl * r.k * 8));
     LB_TRY(idx->w_counts.ensure(nl * 4));
