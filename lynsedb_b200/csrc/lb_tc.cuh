@@ -94,6 +94,7 @@ struct TcArgs {
     int share_floor;          // 1: partitions of a query share a shortlist floor through gthr; 2: gthr holds a floor seeded by a
                               // pre-pass over a sample of the corpus and is only read (large k)
     uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable key bits)
+    int pbest_first;          // diagnostics: the exchange publishes the BEST key of a list instead of its second best
     uint32_t* pbest2;         // optional [nq][PBEST_STRIDE] zero-initialised: second-best key (orderable bits) each partition of a
                               // query holds so far.  When all partitions run at once, the smallest of them is a floor with at
                               // least two rows above it in EVERY partition — 2 P rows, far tighter early in the pass than the
@@ -465,7 +466,7 @@ struct Shortlist {
     const uint32_t* pb_row;
     uint4 pb_v[PBEST_STRIDE / 4];
     uint32_t pb_n;             // partitions of the query (0 = exchange off)
-    bool pb_loaded;
+    bool pb_loaded, pb_first;
     uint2* hit_buf;
     uint32_t hit_n, hit_cap;
     KeyFn<MODE> fn;
@@ -503,10 +504,12 @@ struct Shortlist {
         best2 = O::lowest();
         pb_n = 0u;
         pb_loaded = false;
+        pb_first = false;
         pb_slot = nullptr;
         pb_row = nullptr;
         if (!HITS && valid && a.pbest2 != nullptr && a.share_floor == 1 && a.parts_per_slot == 1 && a.lists_per_part == 1 && a.P <= PBEST_STRIDE) {
             pb_n = (uint32_t)a.P;
+            pb_first = a.pbest_first != 0;
             pb_row = a.pbest2 + (size_t)gq * PBEST_STRIDE;
             pb_slot = a.pbest2 + (size_t)gq * PBEST_STRIDE + part;
         }
@@ -549,14 +552,18 @@ struct Shortlist {
     __device__ __forceinline__ void insert(K key, uint32_t row) {
         if (HITS) return;
         if (pb_n != 0u) {
-            const K old2 = best2;
+            const K old2 = best2, old1 = best1;
             if (key > best1) {
                 best2 = best1;
                 best1 = key;
             } else if (key > best2) {
                 best2 = key;
             }
-            if (best2 > old2) *reinterpret_cast<volatile uint32_t*>(pb_slot) = O::orderable(best2);  // single writer
+            if (pb_first) {
+                if (best1 > old1) *reinterpret_cast<volatile uint32_t*>(pb_slot) = O::orderable(best1);
+            } else if (best2 > old2) {
+                *reinterpret_cast<volatile uint32_t*>(pb_slot) = O::orderable(best2);  // single writer
+            }
         }
         bool done = false;
 #pragma unroll

@@ -436,11 +436,13 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     // second-best exchange between the partitions of a query (list mode, every partition in flight at once, few enough of
     // them for one poll): LYNSE_B200_TC_PBEST=0 turns it off
     a.pbest2 = nullptr;
+    a.pbest_first = 0;
     if (a.share_floor == 1 && parts_per_slot == 1 && L == 1 && P >= 8 && P <= (uint64_t)tc::PBEST_STRIDE && 2 * P >= (uint64_t)k + 4 &&
         tc_env_int("LYNSE_B200_TC_PBEST", 1) != 0) {
         LB_TRY(idx->w_pbest.ensure((size_t)nq * tc::PBEST_STRIDE * 4));
         LB_CUDA_TRY(cudaMemsetAsync(idx->w_pbest.p, 0, (size_t)nq * tc::PBEST_STRIDE * 4, idx->stream));
         a.pbest2 = idx->w_pbest.as<uint32_t>();
+        a.pbest_first = tc_env_int("LYNSE_B200_TC_PBEST", 1) == 2 && P >= (uint64_t)k + 4 ? 1 : 0;
     }
     a.hit_count = nullptr;
     a.hit_buf = nullptr;
