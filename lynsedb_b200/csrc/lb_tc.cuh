@@ -2,29 +2,34 @@
 //
 // The dense metrics (IP, and through it cosine and L2) are a Q x C^T contraction
 // (reference hot loop: src/storage/flat_mmap.rs:2179-2256 ip_scan_chunk_topk over
-// simd::inner_product_batch8_f32, src/distance/simd.rs:1450-1525).  On B200 that
-// contraction runs on the 5th-generation tensor cores over a bf16 shadow of the
-// corpus; a per-query shortlist is kept in the accumulator epilogue, and the
-// shortlist is re-scored in f32 in the reference's exact summation order, so the
-// returned ids / order / scores are the reference's, not the bf16 ones.  A
-// shortlist is only accepted when a rigorous bound proves no dropped row could
-// enter the top-k (see finalize_kernel); otherwise the query is re-run by the
-// exact scan of lb_scan.cuh.
+// simd::inner_product_batch8_f32, src/distance/simd.rs:1450-1525); so are the binary
+// metrics once the bits are bytes (|a & b| = a . b over {0,1}; packed_binary_search,
+// flat_mmap.rs:1345-1409).  On B200 that contraction runs on the 5th-generation tensor
+// cores over a narrow shadow of the corpus — 8-bit operands (tcgen05 kind::i8, exact
+// s32 accumulators) for IP / cosine / the binary metrics, bf16 (kind::f16) for L2 and
+// for corpora the 8-bit quantisation does not suit —; a per-query shortlist (or, for
+// large k, every row above a seeded floor) is kept in the accumulator epilogue and
+// re-scored in f32 in the reference's exact summation order, so the returned ids /
+// order / scores are the reference's, not the shadow's.  A shortlist is only accepted
+// when a bound built from MEASURED norms proves no dropped row could enter the top-k
+// (finalize_kernel::certify); otherwise the query is re-run by the exact scan of
+// lb_scan.cuh.
 //
 // Shadow layout in HBM (a derived structure, so it is stored the way the tensor core wants to read it): rows are
-// grouped in tiles of 64, a tile is cut in K blocks of 64 bf16, and every (tile, K block) is two 4 KiB half blocks
+// grouped in tiles of 64, a tile is cut in K blocks of 128 operand bytes (64 bf16 or 128 8-bit elements), and every (tile, K block) is two 4 KiB half blocks
 // of 32 rows x 128 B whose 16-byte chunks are already permuted with the 128-byte shared-memory swizzle
 // (chunk c of row r sits at chunk c ^ (r & 7)).  A pipeline stage is therefore ONE contiguous TMA box
 // (SWIZZLE_NONE) instead of 4 boxes of 32-64 strided rows, DRAM pages are read front to back, and the bytes
 // land in shared memory exactly as a SWIZZLE_128B K-major UMMA descriptor expects them.
-//   byte offset of element (row, d):  (((row/64) * NKB + d/64) * 2 + (row%64)/32) * 4096
-//                                     + (row%32) * 128 + ((((d%64)/8) ^ (row & 7)) << 4) + (d%8) * 2
+//   byte offset of bf16 element (row, d):  (((row/64) * NKB + d/64) * 2 + (row%64)/32) * 4096
+//                                          + (row%32) * 128 + ((((d%64)/8) ^ (row & 7)) << 4) + (d%8) * 2
+//   (8-bit operands: the same with 128 elements per K block and 16 per chunk — shadow_chunk_offset)
 //
 // Kernels: lb_tc1.cuh (one CTA per 128 queries; used when a batch has a single query tile) and lb_tc2.cuh
 // (CTA pairs, tcgen05 cta_group::2, for two or more query tiles).  Both keep the A operand (the 128 queries
-// of the CTA, bf16) in TMEM columns [0, Dp/2), stream 64-row corpus tiles through a shared-memory ring, double
-// buffer the f32 accumulators in TMEM columns [384, 512), and run a lane == query epilogue that keeps a private
-// KP-entry shortlist per (query, row partition).
+// of the CTA) in TMEM columns [0, row bytes / 4), stream corpus tiles through a shared-memory ring, keep two or three
+// 32-bit accumulator tiles in the TMEM columns behind it, and run a lane == query epilogue that keeps a private
+// KP-entry shortlist per (query, row partition) or appends the rows above a seeded floor to a hit region.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
