@@ -397,10 +397,17 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     LB_TRY(idx->w_cand_score.ensure((size_t)nq * P_buf * tc::KP * 4));
     LB_TRY(idx->w_cand_row.ensure((size_t)nq * P_buf * tc::KP * 4));
     LB_TRY(idx->w_cand_thr.ensure((size_t)nq * P_buf * 4));
-    LB_TRY(idx->w_flags.ensure((size_t)nq * 8 + 16));
+    // Everything a search needs zeroed lives in ONE buffer, cleared with one memset (each separate clear is a launch in
+    // front of the coarse kernel): [head 4 words | per-query flags nq | shared floors nq | pad] [second-best exchange
+    // nq x PBEST_STRIDE] [lockstep progress n_slots x PROGRESS_STRIDE]
+    const size_t z_flags = (((size_t)nq * 8 + 16) + 255) & ~(size_t)255;
+    const size_t z_pbest = (size_t)nq * tc::PBEST_STRIDE * 4;
+    const size_t z_progress = (size_t)n_slots * tc::PROGRESS_STRIDE * 4;
+    LB_TRY(idx->w_flags.ensure(z_flags + z_pbest + z_progress));
     uint32_t* flags = idx->w_flags.as<uint32_t>();
-    LB_CUDA_TRY(cudaMemsetAsync(flags, 0, 16, idx->stream));
-    LB_CUDA_TRY(cudaMemsetAsync(flags + 4 + nq, 0, (size_t)nq * 4, idx->stream));
+    uint32_t* z_pbest_p = reinterpret_cast<uint32_t*>(idx->w_flags.as<char>() + z_flags);
+    uint32_t* z_progress_p = reinterpret_cast<uint32_t*>(idx->w_flags.as<char>() + z_flags + z_pbest);
+    LB_CUDA_TRY(cudaMemsetAsync(flags, 0, z_flags + z_pbest + z_progress, idx->stream));
     // hit regions: one per (query, partition, epilogue set); a region that is never visited (short corpus) must read 0
     const uint32_t hit_cap = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(64, TC_HIT_TOTAL / (P * L)));
     if (hit_mode) {
@@ -439,9 +446,7 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     a.pbest_first = 0;
     if (a.share_floor == 1 && parts_per_slot == 1 && L == 1 && P >= 8 && P <= (uint64_t)tc::PBEST_STRIDE && 2 * P >= (uint64_t)k + 4 &&
         tc_env_int("LYNSE_B200_TC_PBEST", 1) != 0) {
-        LB_TRY(idx->w_pbest.ensure((size_t)nq * tc::PBEST_STRIDE * 4));
-        LB_CUDA_TRY(cudaMemsetAsync(idx->w_pbest.p, 0, (size_t)nq * tc::PBEST_STRIDE * 4, idx->stream));
-        a.pbest2 = idx->w_pbest.as<uint32_t>();
+        a.pbest2 = z_pbest_p;
         a.pbest_first = tc_env_int("LYNSE_B200_TC_PBEST", 1) == 2 && P >= (uint64_t)k + 4 ? 1 : 0;
     }
     a.hit_count = nullptr;
@@ -462,9 +467,7 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     }
     a.progress = nullptr;
     if (n_mgroups > 1 && a.window > 0) {
-        LB_TRY(idx->w_progress.ensure((size_t)n_slots * tc::PROGRESS_STRIDE * 4));
-        LB_CUDA_TRY(cudaMemsetAsync(idx->w_progress.p, 0, (size_t)n_slots * tc::PROGRESS_STRIDE * 4, idx->stream));
-        a.progress = idx->w_progress.as<uint32_t>();
+        a.progress = z_progress_p;
     }
     const int grid = (int)n_slots * n_mgroups * cluster;
     cudaLaunchConfig_t cfg{};
@@ -504,7 +507,7 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
         LB_CUDA_TRY(ensure_dynamic_smem(tc::seed_floor_kernel, sm * 8));
         tc::seed_floor_kernel<<<nq, 256, (size_t)sm * 8, idx->stream>>>(sa.cand_key, sa.cand_row, s_lists, sm, r, mode_int_key(job.mode) ? 1 : 0, a.gthr);
         LB_CUDA_TRY(cudaGetLastError());
-        if (a.progress) LB_CUDA_TRY(cudaMemsetAsync(idx->w_progress.p, 0, (size_t)n_slots * tc::PROGRESS_STRIDE * 4, idx->stream));
+        if (a.progress) LB_CUDA_TRY(cudaMemsetAsync(z_progress_p, 0, z_progress, idx->stream));
         idx->stats.kernels_launched += 2;
         if (hit_mode) {
             a.hit_count = idx->w_hit_count.as<uint32_t>();
