@@ -27,24 +27,28 @@ __host__ __device__ inline bool scan4_supported(int metric) {
            metric == LB_BRAY_CURTIS;
 }
 
-// warps per CTA: four (a 64-row block, at most 64 KiB up to 256 dims) or two (32 rows, up to 512 dims), so that two CTAs
-// fit an SM and one computes while the other waits for its rows.  Measured at 64 queries (tools/gpu_r2_tile_shapes.sh,
-// L1 on 4.1 GB of rows): 256 dims — 4 warps 6.8 ms, 8 warps (one CTA per SM) 7.2, 2 warps x 4 CTAs 8.1; 128 dims — 4 warps
-// 8.5 ms, 8 warps 9.1.  LYNSE_B200_SCAN_TILE_NW forces 4 or 2.
+// CTA shapes (lb_scan_dense.cuh picks per metric): up to 256 dims a 64-row block (at most 64 KiB, so two CTAs fit an SM and
+// one computes while the other waits for its rows) worked by eight warps — two per row group, each with half of the tile's
+// sixteen queries — or by four; up to 512 dims two warps over a 32-row block with eight queries per tile.
+// scan4_warps: 8 = the 64-row shapes, 2 = the 32-row shape.  LYNSE_B200_SCAN_TILE_NW forces 8 or 2.
 inline int scan4_warps(int dim) {
     const char* env = getenv("LYNSE_B200_SCAN_TILE_NW");
-    if (env && (atoi(env) == 4 || atoi(env) == 2)) return atoi(env);
-    return dim <= 256 ? 4 : 2;
+    if (env && (atoi(env) == 8 || atoi(env) == 2)) return atoi(env);
+    return dim <= 256 ? 8 : 2;
 }
+inline int scan4_block_rows(int nw) { return nw == 8 ? 64 : 32; }
 
-// TQW: queries per register tile.  16 for the one-accumulator metrics (64 accumulators per thread), 8 for the
-// two-accumulator ones — and for everything above 256 dims, where the smaller query tile lets two CTAs share an SM.
-template <int METRIC, bool IP2, int TQW>
+// TQW: queries per tile in shared memory; QSP: how many warps share a row group, each taking TQW / QSP of the tile's
+// queries (QSP = 2: eight warps per CTA over the same 64 rows, 16 warps per SM instead of 8 — the chunk loop leaves a
+// third of the issue slots empty with two warps per scheduler).  R x (TQW / QSP) x accumulators per pair <= 64 registers.
+template <int METRIC, bool IP2, int TQW, int QSP = 1>
 struct S4Cfg {
     using Op = Scan2Op<METRIC, IP2>;
-    static_assert(TQW == 8 || (TQW == 16 && Op::kState == 8), "64 accumulators per thread at most");
     static constexpr int kTQ = TQW;
-    static constexpr int kSRow = kTQ * Op::kState + 8;       // scratch words per row group: 136 = 8 mod 32, conflict-free
+    static constexpr int kTQT = TQW / QSP;                   // queries per thread
+    static_assert(TQW % QSP == 0 && kTQT % 4 == 0, "a thread reads its queries as 16-byte pieces");
+    static_assert(S4_R * kTQT * (Op::kState / 8) <= 64, "64 accumulators per thread at most");
+    static constexpr int kSRow = kTQT * Op::kState + 8;      // scratch words per row group of a warp: = 8 mod 32, conflict-free
     static constexpr int kQStride = kTQ + 4;                 // words per element of the transposed query tile (20 / 12)
     // one query tile as the kernel wants it in shared memory: [dim & ~7][kQStride] element-major, then [kTQ][8] tail elements
     static size_t tile_floats(int dim) { return (size_t)(dim & ~7) * kQStride + (size_t)kTQ * 8; }
@@ -52,8 +56,9 @@ struct S4Cfg {
     static bool smem_lists(int nq, int k) { return (size_t)nq * k * 8 + (size_t)nq * 16 <= 16384; }
     // shared memory of a CTA of NW warps for rows of `dim` floats (+ 1 KiB alignment slack)
     static size_t smem_bytes(int nw, int dim, int nq, int k) {
-        const size_t rows = (size_t)((dim + 31) / 32) * (size_t)(nw * 4 * S4_R) * 128;
-        const size_t cand = (size_t)kTQ * (nw * 4 * S4_R) * 8;
+        const size_t rb = (size_t)(nw / QSP) * 4 * S4_R;
+        const size_t rows = (size_t)((dim + 31) / 32) * rb * 128;
+        const size_t cand = (size_t)kTQ * rb * 8;
         const size_t q = (size_t)(dim & ~7) * kQStride * 4 + (size_t)2 * kTQ * 8 * 4;
         const size_t scratch = (size_t)nw * 4 * kSRow * 4;
         const size_t misc = (size_t)kTQ * 16 + 64 + (METRIC == LB_COSINE ? (size_t)((nq + 3) & ~3) * 4 : 0);
@@ -119,12 +124,12 @@ __device__ __forceinline__ void lane_step(float& s0, float& s1, float q, float c
     }
 }
 
-template <int METRIC, bool IP2, int NW, int TQW>
-__global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(const __grid_constant__ CUtensorMap tmap, ScanArgs a) {
+template <int METRIC, bool IP2, int NW, int TQW, int QSP = 1>
+__global__ void __launch_bounds__(NW * 32, 2) scan_tile_kernel(const __grid_constant__ CUtensorMap tmap, ScanArgs a) {
     using Op = Scan2Op<METRIC, IP2>;
-    using Cfg = S4Cfg<METRIC, IP2, TQW>;
-    constexpr int R = S4_R, TQ = Cfg::kTQ, KS = Op::kState, SROW = Cfg::kSRow, QS = Cfg::kQStride;
-    constexpr int RB = NW * 4 * R, NT = NW * 32;
+    using Cfg = S4Cfg<METRIC, IP2, TQW, QSP>;
+    constexpr int R = S4_R, TQ = Cfg::kTQ, TQT = Cfg::kTQT, KS = Op::kState, SROW = Cfg::kSRow, QS = Cfg::kQStride;
+    constexpr int RB = (NW / QSP) * 4 * R, NT = NW * 32;
     constexpr bool ASC = METRIC != LB_IP;
     constexpr bool TWO = KS == 16 && METRIC != LB_COSINE;  // two accumulators per pair
     extern __shared__ __align__(16) unsigned char smem_s4[];
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(con
     const bool slists = a.smem_lists != 0;
     const uint32_t bar_rows = tc::smem_u32(bar), bar_q = bar_rows + 8u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane >> 3, li = lane & 7;
+    const int rwarp = warp / QSP, qh = warp % QSP;   // which 16 rows of the block, which TQT queries of the tile
     const int part = blockIdx.x;
     const uint64_t part_begin = (uint64_t)part * a.rows_per_part;
     uint64_t part_end = part_begin + a.rows_per_part;
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(con
     int rl[R];
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
-        rl[rr] = warp * (4 * R) + (rr >> 1) * 8 + sub * 2 + (rr & 1);
+        rl[rr] = rwarp * (4 * R) + (rr >> 1) * 8 + sub * 2 + (rr & 1);
         a0[rr] = (uint32_t)rl[rr] * 128u + ((((uint32_t)li >> 2) ^ ((uint32_t)rl[rr] & 7u)) << 4) + ((uint32_t)li & 3u) * 4u;
     }
     __syncthreads();
@@ -254,12 +260,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(con
                 phase_q ^= 1u;
             }
 
-            float acc0[R][TQ], acc1[R][TQ], nb[R];
+            float acc0[R][TQT], acc1[R][TQT], nb[R];
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
                 nb[rr] = 0.0f;
 #pragma unroll
-                for (int t = 0; t < TQ; ++t) {
+                for (int t = 0; t < TQT; ++t) {
                     acc0[rr][t] = 0.0f;
                     acc1[rr][t] = 0.0f;
                 }
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(con
             // four chunks per round: the row words sit at a0 ^ (s << 5) of the round's column chunk, the query words
             // 8 * QS floats further per chunk — running pointers, no index arithmetic in the loop
             const unsigned char* rptr = smem;
-            const float* qptr = sqt + (size_t)li * QS;
+            const float* qptr = sqt + (size_t)li * QS + qh * TQT;
             auto body = [&](auto s_tag) {
                 constexpr int S = decltype(s_tag)::value;
                 constexpr bool ODD = (S & 1) != 0;
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(con
                 }
                 const float4* qp = reinterpret_cast<const float4*>(qptr + S * 8 * QS);
 #pragma unroll
-                for (int t4 = 0; t4 < TQ / 4; ++t4) {
+                for (int t4 = 0; t4 < TQT / 4; ++t4) {
                     const float4 q4 = qp[t4];
                     const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
@@ -310,14 +316,15 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(con
                 if (tile + 1 == n_tiles && blk + 1 < n_blocks) fetch_rows(blk + 1);  // this block's rows are no longer read
             }
 
-            // the eight lanes of a pair meet in the warp's scratch; thread (sub, li) finishes queries li, li + 8 of row rr
+            // the eight lanes of a pair meet in the warp's scratch; thread (sub, li) finishes queries li (and li + 8) of the
+            // warp's share of the tile, for row rr
             float* ws = scratch + (size_t)(warp * 4 + sub) * SROW;
             const uint64_t* gate = slists ? lgate + q0 : tgate;
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
                 __syncwarp();
 #pragma unroll
-                for (int t = 0; t < TQ; ++t) {
+                for (int t = 0; t < TQT; ++t) {
                     ws[t * KS + li] = acc0[rr][t];
                     if (KS == 16) ws[t * KS + 8 + li] = TWO ? acc1[rr][t] : nb[rr];
                 }
@@ -325,13 +332,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 2) scan_tile_kernel(con
                 if (valid[rr]) {
                     const float* c = a.corpus + (size_t)row[rr] * dim;
 #pragma unroll
-                    for (int tt = 0; tt < TQ / 8; ++tt) {
-                        const int t = li + 8 * tt;
-                        if (t < tq) {
+                    for (int tt = 0; tt < (TQT + 7) / 8; ++tt) {
+                        const int tl = li + 8 * tt;            // query of this warp's share
+                        const int t = qh * TQT + tl;           // ... of the tile
+                        if (tl < TQT && t < tq) {
                             float s[KS];
 #pragma unroll
                             for (int x = 0; x < KS; x += 4) {
-                                const float4 v4 = *reinterpret_cast<const float4*>(ws + t * KS + x);
+                                const float4 v4 = *reinterpret_cast<const float4*>(ws + tl * KS + x);
                                 s[x] = v4.x; s[x + 1] = v4.y; s[x + 2] = v4.z; s[x + 3] = v4.w;
                             }
                             PairConst pc;

@@ -26,34 +26,37 @@ int dense_scan_launch(lb_index* idx, const ScanRequest& r, ScanArgs& a, const Sc
             CUtensorMap tmap;
             cuuint64_t gdim[2] = {(cuuint64_t)r.dim, (cuuint64_t)r.n_rows};
             cuuint64_t gstride[1] = {(cuuint64_t)r.dim * sizeof(float)};
-            cuuint32_t box[2] = {32u, (cuuint32_t)(nw * 4 * S4_R)};
+            cuuint32_t box[2] = {32u, (cuuint32_t)(scan4_block_rows(nw))};
             cuuint32_t estr[2] = {1, 1};
             CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)const_cast<float*>(r.corpus), gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (cr != CUDA_SUCCESS) return fail(LB_CUDA, "cuTensorMapEncodeTiled (row tiles) failed with CUresult " + std::to_string((int)cr));
             const bool ip2 = r.ip_single || r.n_small > 0;
-#define LB_LAUNCH_S4T(M, IP2V, NWV, TQV)                                                                   \
+#define LB_LAUNCH_S4T(M, IP2V, NWV, TQV, QSPV)                                                             \
     do {                                                                                                   \
-        using Cfg = S4Cfg<M, IP2V, TQV>;                                                                   \
+        using Cfg = S4Cfg<M, IP2V, TQV, QSPV>;                                                             \
         const int n_tiles = (r.nq + Cfg::kTQ - 1) / Cfg::kTQ;                                              \
         LB_TRY(idx->w_qtiles.ensure((size_t)n_tiles * Cfg::tile_floats(r.dim) * 4));                       \
         scan4_query_tiles_kernel<<<n_tiles, 256, 0, idx->stream>>>(r.queries, r.nq, r.dim, Cfg::kTQ, Cfg::kQStride, idx->w_qtiles.as<float>()); \
         a.query_tiles = idx->w_qtiles.as<float>();                                                         \
         a.smem_lists = Cfg::smem_lists(r.nq, r.k) ? 1 : 0;                                                 \
         const size_t smem = Cfg::smem_bytes(NWV, r.dim, r.nq, r.k);                                        \
-        LB_CUDA_TRY(ensure_dynamic_smem(scan_tile_kernel<M, IP2V, NWV, TQV>, (int)smem));                  \
-        scan_tile_kernel<M, IP2V, NWV, TQV><<<sp.P, NWV * 32, smem, idx->stream>>>(tmap, a);               \
+        LB_CUDA_TRY(ensure_dynamic_smem(scan_tile_kernel<M, IP2V, NWV, TQV, QSPV>, (int)smem));            \
+        scan_tile_kernel<M, IP2V, NWV, TQV, QSPV><<<sp.P, NWV * 32, smem, idx->stream>>>(tmap, a);         \
     } while (0)
-#define LB_LAUNCH_S4W(M, IP2V, NWV)                                                                        \
-    do {                                                                                                   \
-        constexpr int tq_sel = (Scan2Op<M, IP2V>::kState == 8 && NWV > 2) ? 16 : 8;                        \
-        LB_LAUNCH_S4T(M, IP2V, NWV, tq_sel);                                                               \
-    } while (0)
-#define LB_LAUNCH_S4(M, IP2V)                                   \
-    do {                                                        \
-        if (nw == 4) LB_LAUNCH_S4W(M, IP2V, 4);                 \
-        else LB_LAUNCH_S4W(M, IP2V, 2);                         \
+// up to 256 dims, 64-row blocks: the one-accumulator metrics (IP, L1, Chebyshev) run eight warps, two per row group, each
+// with eight of the tile's sixteen queries (16 warps per SM); the two-accumulator ones (L2, cosine, Bray-Curtis; IP over
+// small segments) four warps with eight queries per tile — measured at 64 queries over 4M x 256: L1 6.80 -> 6.35 ms,
+// Chebyshev 11.3 -> 9.9 with the eight warps, but L2 8.7 -> 10.0 and Bray-Curtis 12.5 -> 14.0 (64 accumulators under the
+// 128-register cap of a 256-thread CTA; up to 128 dims they take the eight warps too: L2 11.8 -> 10.7 ms over 8M x 128).
+// Up to 512 dims: two warps, 32-row blocks, eight queries per tile.
+#define LB_LAUNCH_S4(M, IP2V)                                                            \
+    do {                                                                                 \
+        constexpr bool one_acc = Scan2Op<M, IP2V>::kState == 8;                          \
+        if (nw == 8 && (one_acc || r.dim <= 128)) LB_LAUNCH_S4T(M, IP2V, 8, 16, 2);      \
+        else if (nw == 8) LB_LAUNCH_S4T(M, IP2V, (one_acc ? 8 : 4), (one_acc ? 16 : 8), (one_acc ? 2 : 1)); \
+        else LB_LAUNCH_S4T(M, IP2V, 2, 8, 1);                                            \
     } while (0)
             switch (r.metric) {
                 case LB_IP: if (ip2) LB_LAUNCH_S4(LB_IP, true); else LB_LAUNCH_S4(LB_IP, false); break;
@@ -64,7 +67,6 @@ int dense_scan_launch(lb_index* idx, const ScanRequest& r, ScanArgs& a, const Sc
                 default: LB_LAUNCH_S4(LB_BRAY_CURTIS, false); break;
             }
 #undef LB_LAUNCH_S4
-#undef LB_LAUNCH_S4W
 #undef LB_LAUNCH_S4T
         } else {
             return fail(LB_INTERNAL, "the row-tile scan serves f32 rows");
