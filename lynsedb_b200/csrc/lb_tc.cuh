@@ -57,6 +57,19 @@ constexpr uint32_t SMEM_BAR_OFF = SMEM_RING_BYTES;
 constexpr uint32_t SMEM_SCRATCH_OFF = SMEM_BAR_OFF + 256;               // per-epilogue-warp scratch (side values of a tile)
 constexpr uint32_t SMEM_SCRATCH_BYTES = 8 * 3 * 128 * 4;                // 8 epilogue warps x EPI_SCRATCH_SLOTS x EPI_SCRATCH_WORDS words
 constexpr uint32_t SMEM_BYTES = SMEM_SCRATCH_OFF + SMEM_SCRATCH_BYTES + 1024;  // + barriers + scratch + alignment slack
+// Pair kernel with helper warps (lb_tc2.cuh, HELP_): the scratch area holds, per (scanner, helper) warp pair, a queue of
+// HQ_SLOTS hit groups (16 accumulators x 32 lanes each) and a control block: words [0, HQ_SLOTS) first row of the
+// slot's group (HQ_END = the scanner is done), mbarriers full[s] at byte 32 + 8 s and empty[s] at byte 64 + 8 s, and two
+// words per lane that are deliberately NOT synchronised: the helper's gate (single writer, only grows; the scanner tests
+// against whatever it reads — a stale gate only queues a group the helper then drops) and the floor of the scanner's
+// pre-pass.  (Through global memory instead, the scanner's load sits on every tile's critical path: +10 %.)
+constexpr uint32_t HQ_SLOTS = 4;
+constexpr uint32_t HQ_ENTRY_WORDS = 16 * 32;
+constexpr uint32_t HQ_CTRL_WORDS = 96;   // ... [32, 64) the helper's gate per lane, [64, 96) the floor of the scanner's pre-pass
+constexpr uint32_t HQ_END = 0xFFFFFFFFu;
+constexpr uint32_t HQ_BYTES = 4 * (HQ_SLOTS * HQ_ENTRY_WORDS + HQ_CTRL_WORDS) * 4;
+constexpr uint32_t SMEM_BYTES_HELP = SMEM_SCRATCH_OFF + HQ_BYTES + 1024;
+static_assert(SMEM_BYTES_HELP <= 227 * 1024, "helper queues do not fit next to the staging ring");
 
 // How the 32-bit accumulator of a (query, row) pair becomes the coarse KEY the epilogue ranks by (larger = better).
 //   mode            operands        accumulator   key                                   side values
@@ -110,6 +123,11 @@ struct TcArgs {
     uint32_t* hit_count;      // [nq][P * lists_per_part] entries written per region (may exceed hit_cap: overflow); null = shortlist mode
     uint2* hit_buf;           // [nq][P * lists_per_part][hit_cap] (key bits, row)
     uint32_t hit_cap;         // entries per region
+    // helper-warp kernel with the second-best exchange: every partition first runs its first pre_tiles tiles through the
+    // tensor cores only to learn its two best keys (group maxima: nothing is queued), waits for the floor the exchange
+    // then yields, and starts over with the whole partition — so the lists never see a partition's first tiles without
+    // a floor, when every row is a hit (0 = off)
+    int pre_tiles;
     uint32_t* error_flag;     // set non-zero when a barrier wait timed out
     float* dump;              // optional [n_mtiles*128][tiles_total*rows per tile] keys as f32 (diagnostics)
     // Work mapping: cluster c serves query group (c % n_mgroups) of slot (c / n_mgroups); slot s walks the row

@@ -96,9 +96,18 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 // at large k, and two warps double it.
 // MODE_ = CoarseMode: operand kind of the MMAs and how an accumulator becomes the key the epilogue ranks by.
 // HITS_: the epilogue appends rows above a seeded floor to hit regions instead of keeping shortlists (TcArgs::hit_buf).
-template <int BN_, int NACC_ = 2, int EPI_ = 1, int MODE_ = CM_F32, bool HITS_ = false>
-__global__ void __launch_bounds__(64 + 128 * EPI_, 1)   // (warps are allocated four at a time: 320 threads are budgeted as 384, 168 registers)
+// HELP_ (list mode, one epilogue set, keys without side values, one partition per slot): four HELPER warps (6..9) own the
+// shortlists.  The scanner warps (2..5) only read the accumulators, release them, compute the group maxima against the
+// gate their helper last wrote, and pass the 16-row groups that hold a hit through a small shared-memory queue.  A
+// list insertion is ~1500 cycles of dependent instructions on a warp that is alone on its scheduler; with the lists in
+// the epilogue warp itself some warp of the pair's eight is in that path at nearly every tile of a short shard, and the
+// MMAs (two accumulators in flight) wait for it: 2090 cycles per tile against 1536 of tensor work on a 1.25M-row shard
+// of C2, exactly 1552 when the scan is switched off.  Scanner w and helper w + 4 share a scheduler, so the helper's
+// latency-bound instruction stream fills issue slots the scanner leaves empty.
+template <int BN_, int NACC_ = 2, int EPI_ = 1, int MODE_ = CM_F32, bool HITS_ = false, bool HELP_ = false>
+__global__ void __launch_bounds__(64 + 128 * (EPI_ + (HELP_ ? 1 : 0)), 1)   // (warps are allocated four at a time: 320 threads are budgeted as 384, 168 registers)
 coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_constant__ CUtensorMap tmap_rem, TcArgs a) {
+    static_assert(!HELP_ || (EPI_ == 1 && !HITS_ && BN_ == 128 && (MODE_ == CM_I32 || MODE_ == CM_F32)), "helper warps: list mode, one set, keys without side values");
     using Cfg = PairCfg<BN_, NACC_>;
     constexpr uint32_t NACC = NACC_;
     static_assert(EPI_ == 1 || (EPI_ == 2 && BN_ == 128), "two epilogue sets split a 128-column tile in halves");
@@ -110,6 +119,11 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
     constexpr bool I8 = MT::kI8;
     constexpr int DCOL = Cfg::kDCol;   // shadows tc::DCOL
     constexpr int BN = BN_;            // shadows tc::BN
+    // Pre-pass of the second-best exchange (helper-warp kernel): a partition's tile sequence is its first `pre` tiles
+    // (group maxima only), then all of its tiles.  Producer, MMA issuer and scanners walk the same flattened sequence.
+    auto pre_of = [&](uint32_t t0, uint32_t t1) -> uint32_t {
+        return (HELP_ && a.pre_tiles > 0 && a.pbest2 != nullptr) ? min((uint32_t)a.pre_tiles, t1 - t0) : 0u;
+    };
     const uint32_t crank = cluster_ctarank();  // 0 = even CTA (issues the MMAs), 1 = odd CTA
     const int n_mgroups = (a.n_mtiles + 1) / 2;
     const int cluster_id = (int)(blockIdx.x >> 1);
@@ -149,6 +163,19 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
         tmem_alloc_pair(smem_u32(tmem_ptr_smem), TMEM_COLS);
         tmem_relinquish_pair();
     }
+    if (HELP_ && warp >= 6) {   // queue barriers; every lane's gate and pre-pass floor at "nothing seen yet"
+        const uint32_t cb = smem_base + SMEM_SCRATCH_OFF + 4 * HQ_SLOTS * HQ_ENTRY_WORDS * 4 + (uint32_t)(warp & 3) * HQ_CTRL_WORDS * 4;
+        if (lane == 0) {
+            for (uint32_t sI = 0; sI < HQ_SLOTS; ++sI) {
+                mbar_init(cb + 32u + 8u * sI, 1);
+                mbar_init(cb + 64u + 8u * sI, 1);
+            }
+            fence_barrier_init();
+        }
+        volatile uint32_t* gw = reinterpret_cast<volatile uint32_t*>(smem + SMEM_SCRATCH_OFF + 4 * HQ_SLOTS * HQ_ENTRY_WORDS * 4) + (warp & 3) * HQ_CTRL_WORDS + 32;
+        gw[lane] = KO::bits(KO::lowest());
+        gw[32 + lane] = KO::bits(KO::lowest());
+    }
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();  // both CTAs' barriers are initialised before anything remote can arrive
@@ -175,7 +202,9 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                 if (part >= (uint32_t)a.P) break;
                 const uint32_t t0 = part * a.tiles_per_part;
                 const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
-                for (uint32_t t = t0; t < t1 && ok; ++t) {
+                const uint32_t pre = pre_of(t0, t1), n_seq = pre + (t1 - t0);
+                for (uint32_t i = 0; i < n_seq && ok; ++i) {
+                    const uint32_t t = t0 + (i < pre ? i : i - pre);
                     if (lockstep && seq >= known_min + window) {
                         const uint64_t w0 = globaltimer_ns();
                         while (true) {
@@ -233,7 +262,8 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                 const uint32_t t1 = min(t0 + a.tiles_per_part, a.tiles_total);
                 if (!mbar_wait(aready_bar, item_iter & 1u, abort_flag, 2)) break;
                 tcgen05_fence_after();
-                for (uint32_t t = t0; t < t1 && ok; ++t, ++tile_iter) {
+                const uint32_t n_seq = pre_of(t0, t1) + (t1 - t0);   // the MMAs do not depend on which tile it is
+                for (uint32_t i = 0; i < n_seq && ok; ++i, ++tile_iter) {
                     const uint32_t buf = tile_iter % NACC;
                     if (!tempty_ready) {
                         const long long c0 = clock64();
@@ -300,6 +330,185 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                 pr[3] = (unsigned long long)n_w_tempty;
                 pr[4] = (unsigned long long)n_w_full;
                 pr[5] = tile_iter;
+            }
+        }
+    } else if (HELP_) {
+        // ===================== scanner warps 2..5 and helper warps 6..9 (see the kernel comment) =====================
+        if constexpr (HELP_) {
+            const int quad = warp & 3;
+            const int ql = quad * 32 + lane;
+            const uint32_t gq = ((uint32_t)mgroup * 2u + crank) * BM + (uint32_t)ql;
+            const bool q_valid = gq < (uint32_t)a.nq;
+            uint32_t* ent = reinterpret_cast<uint32_t*>(smem + SMEM_SCRATCH_OFF) + quad * (HQ_SLOTS * HQ_ENTRY_WORDS);
+            uint32_t* ctrl = reinterpret_cast<uint32_t*>(smem + SMEM_SCRATCH_OFF + 4 * HQ_SLOTS * HQ_ENTRY_WORDS * 4) + quad * HQ_CTRL_WORDS;
+            const uint32_t cb = smem_base + SMEM_SCRATCH_OFF + 4 * HQ_SLOTS * HQ_ENTRY_WORDS * 4 + (uint32_t)quad * HQ_CTRL_WORDS * 4;
+            const uint32_t qfull0 = cb + 32u, qempty0 = cb + 64u;   // full[s] / empty[s] of this pair's queue
+            volatile uint32_t* hg_gate = ctrl + 32 + lane;    // written by the helper, read by the scanner (unsynchronised on purpose)
+            volatile uint32_t* hg_floor = ctrl + 64 + lane;   // written by the scanner, read by the helper
+            const uint32_t part = (uint32_t)slot;   // one partition per slot
+            const bool have_part = n_rounds > 0 && part < (uint32_t)a.P;
+            const uint32_t t0 = part * a.tiles_per_part;
+            const uint32_t t1 = have_part ? min(t0 + a.tiles_per_part, a.tiles_total) : t0;
+            if (warp < 6) {
+                // ---------- scanner: accumulators -> group maxima -> queue ----------
+                const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+                const uint32_t even_tempty0 = mapa_rank(tempty0, 0), even_aready = mapa_rank(aready_bar, 0);
+                long long e_wait = 0, e_ld = 0, e_scan = 0, e_slow = 0, n_slow = 0, e_max = 0;
+                uint32_t tile_iter = 0, head = 0;
+                bool ok = true;
+                if (have_part) {
+                    load_query_to_tmem(a.qb + (size_t)gq * a.Dp * 2, a.Dp, lane_addr);
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(even_aready);
+                }
+                // pre-pass state: this partition's two best keys so far, the floor the exchange yields at its end
+                const uint32_t pre = have_part ? pre_of(t0, t1) : 0u, n_seq = pre + (t1 - t0);
+                const bool exch = pre != 0u && q_valid && a.share_floor == 1 && a.P <= PBEST_STRIDE;
+                const uint32_t* pb_row = a.pbest2 != nullptr ? a.pbest2 + (size_t)(q_valid ? gq : 0u) * PBEST_STRIDE : nullptr;
+                Key best1 = KO::lowest(), best2 = KO::lowest(), pub2 = KO::lowest(), floor0 = KO::lowest();
+                for (uint32_t i = 0; i < n_seq && ok; ++i, ++tile_iter) {
+                    const uint32_t t = t0 + (i < pre ? i : i - pre);
+                    const bool pre_mode = i < pre;
+                    const bool whole = (t + 1u) * BN <= a.n_rows;   // no padding rows among the group maxima
+                    if (pre != 0u && i == pre) {
+                        // every partition of the query has published its second best (they run side by side: bounded wait;
+                        // a late one only means this pass starts without a floor, as it does without a pre-pass)
+                        for (uint32_t it = 0; it < 1024u; ++it) {
+                            bool done = true;
+                            if (exch) {
+                                uint32_t mn = 0xFFFFFFFFu;
+                                for (int pp = 0; pp < a.P; ++pp) mn = min(mn, ld_relaxed_gpu(pb_row + pp));
+                                done = mn != 0u;
+                                if (done) floor0 = KO::from_orderable(mn);
+                            }
+                            if (__all_sync(0xffffffffu, done)) break;
+                            __nanosleep(256);
+                        }
+                        // the helper folds it into its floor: every row this warp drops from now on scored <= max(gate, floor0),
+                        // and the list's final floor (cand_thr) must cover that
+                        *hg_floor = KO::bits(floor0);
+                    }
+                    const uint32_t buf = tile_iter % NACC;
+                    const Key thr = pre_mode ? KO::highest() : (q_valid && !(a.debug_mode & 4) ? max(KO::from_bits(*hg_gate), floor0) : KO::highest());
+                    const long long ec0 = clock64();
+                    if (!mbar_wait(tfull0 + 8u * buf, (tile_iter / NACC) & 1u, abort_flag, 5)) { ok = false; break; }
+                    const long long ec1 = clock64();
+                    tcgen05_fence_after();
+                    uint32_t v[64];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        tmem_ld_32x32b_x64(lane_addr + DCOL + buf * BN + h * 64, v);
+                        tmem_ld_wait();
+                        if (h == 1) {
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(even_tempty0 + 8u * buf);  // accumulator is in registers
+                            e_wait += ec1 - ec0;
+                            e_ld += clock64() - ec1;
+                        }
+                        const long long sc0 = clock64();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t* x = v + 16 * j;
+                            Key m = KO::max3(KO::from_bits(x[0]), KO::from_bits(x[1]), KO::from_bits(x[2]));
+#pragma unroll
+                            for (int i = 3; i + 1 < 16; i += 2) m = KO::max3(m, KO::from_bits(x[i]), KO::from_bits(x[i + 1]));
+                            m = max(m, KO::from_bits(x[15]));
+                            if (pre_mode && whole) {   // one row of this partition per group: its two best keys so far
+                                const Key lo = min(m, best1);
+                                best1 = max(m, best1);
+                                best2 = max(best2, lo);
+                            }
+                            if (__any_sync(0xffffffffu, m > thr)) {
+                                // back-pressure: the slot this entry goes to must have been consumed
+                                const uint32_t qs = head % HQ_SLOTS;
+                                if (!mbar_wait(qempty0 + 8u * qs, ((head / HQ_SLOTS) & 1u) ^ 1u, abort_flag, 6)) { ok = false; break; }
+                                uint32_t* e = ent + qs * HQ_ENTRY_WORDS;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) e[i * 32 + lane] = x[i];
+                                if (lane == 0) ctrl[qs] = t * BN + (uint32_t)(h * 64 + j * 16);
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(qfull0 + 8u * qs);
+                                ++head;
+                            }
+                        }
+                        const long long sd = clock64() - sc0;
+                        e_scan += sd;
+                        if (sd > 400) { ++n_slow; e_slow += sd; }
+                        if (sd > e_max) e_max = sd;
+                        if (!ok) break;
+                    }
+                    if (pre_mode && exch && best2 > pub2) {
+                        st_relaxed_gpu(a.pbest2 + (size_t)gq * PBEST_STRIDE + part, KO::orderable(best2));  // single writer until the helper's lists take over
+                        pub2 = best2;
+                    }
+                }
+                // end of the stream (also after a failed wait: the helper must not be left waiting)
+                {
+                    const uint32_t qs = head % HQ_SLOTS;
+                    if (*abort_flag == 0u && mbar_wait(qempty0 + 8u * qs, ((head / HQ_SLOTS) & 1u) ^ 1u, abort_flag, 6)) {
+                        if (lane == 0) ctrl[qs] = HQ_END;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(qfull0 + 8u * qs);
+                    }
+                }
+                if (a.prof != nullptr && warp == 2 && lane == 0) {
+                    unsigned long long* pr = a.prof + (size_t)blockIdx.x * 8;
+                    pr[6] = (unsigned long long)e_wait;
+                    pr[7] = (unsigned long long)e_ld;
+                    if (crank == 1) {
+                        pr[0] = (unsigned long long)e_scan;
+                        pr[1] = (unsigned long long)e_slow;
+                        pr[2] = (unsigned long long)n_slow;
+                        pr[3] = (unsigned long long)e_max;
+                        pr[4] = tile_iter;
+                    }
+                }
+            } else {
+                // ---------- helper: queue -> shortlists, floors, the gate the scanner tests against ----------
+                Shortlist<MODE_, false> sl;
+                const float qaux = a.qaux != nullptr ? __ldg(a.qaux + gq) : 0.0f;
+                sl.init_floor(qaux);
+                if (have_part) {
+                    sl.reset(q_valid, a, gq, part, 0u);
+                    *hg_gate = KO::bits(sl.gate());
+                }
+                const bool have_allow = a.allow_bits != nullptr;
+                uint32_t tail = 0;
+                while (have_part) {
+                    const uint32_t qs = tail % HQ_SLOTS;
+                    if (!mbar_wait(qfull0 + 8u * qs, (tail / HQ_SLOTS) & 1u, abort_flag, 7)) break;   // (an aborted launch ends here)
+                    const uint32_t* e = ent + qs * HQ_ENTRY_WORDS;
+                    const uint32_t row0 = ctrl[qs];
+                    if (row0 == HQ_END) break;
+                    uint32_t w[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = e[i * 32 + lane];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(qempty0 + 8u * qs);   // the group is in registers: the slot is free
+                    ++tail;
+                    if (!(a.debug_mode & 128)) sl.poll_floor(tail, (uint32_t)a.poll_mask >> 1);   // every 4th entry (tiles: every 8th)
+                    sl.thr_g = max(sl.thr_g, KO::from_bits(*hg_floor));   // the scanner's pre-pass floor
+                    const Key thr = sl.gate();
+                    sl.fn.set_gate(thr);
+                    const Key tthr = sl.fn.test_thr(thr);
+                    Key gmax = KO::max3(KO::from_bits(w[0]), KO::from_bits(w[1]), KO::from_bits(w[2]));
+#pragma unroll
+                    for (int i = 3; i + 1 < 16; i += 2) gmax = KO::max3(gmax, KO::from_bits(w[i]), KO::from_bits(w[i + 1]));
+                    gmax = max(gmax, KO::from_bits(w[15]));
+                    if (__any_sync(0xffffffffu, gmax > tthr)) {
+                        uint32_t allow16 = 0xffffu;
+                        if (have_allow) allow16 = row0 < a.n_rows ? (uint32_t)(__ldg(a.allow_bits + (row0 >> 6)) >> (row0 & 63u)) & 0xffffu : 0u;
+                        sl.slow16(w, nullptr, gmax, row0, a.n_rows, thr, tthr, allow16, have_allow);
+                        if (sl.may_publish && sl.q_valid && sl.lmin > sl.thr_pub && sl.lmin > sl.thr_g) sl.publish();
+                    }
+                    *hg_gate = KO::bits(sl.gate());
+                }
+                if (have_part) {
+                    sl.thr_g = max(sl.thr_g, KO::from_bits(*hg_floor));   // (no entry may have arrived since it was set)
+                    sl.flush(a, gq, part, 0u);
+                }
             }
         }
     } else {

@@ -303,6 +303,23 @@ static int launch_coarse_mode(int cfg_id, cudaLaunchConfig_t cfg, const Shadow& 
             LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 1, MODE, HITS>, (int)tc::SMEM_BYTES));
             LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3, 1, MODE, HITS>, sh.tmap_full[0], sh.tmap_rem[0], args));
             break;
+        case 6:
+        case 7:
+            // list mode with helper warps (lb_tc2.cuh, HELP_): 6 = two accumulator tiles, 7 = three
+            if constexpr (!HITS && (MODE == tc::CM_I32 || MODE == tc::CM_F32)) {
+                cfg.blockDim = dim3(64 + 128 * 2);
+                cfg.dynamicSmemBytes = tc::SMEM_BYTES_HELP;
+                if (cfg_id == 6) {
+                    LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 2, 1, MODE, false, true>, (int)tc::SMEM_BYTES_HELP));
+                    LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 2, 1, MODE, false, true>, sh.tmap_full[0], sh.tmap_rem[0], args));
+                } else {
+                    LB_CUDA_TRY(ensure_dynamic_smem(tc::coarse_pair_kernel<128, 3, 1, MODE, false, true>, (int)tc::SMEM_BYTES_HELP));
+                    LB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::coarse_pair_kernel<128, 3, 1, MODE, false, true>, sh.tmap_full[0], sh.tmap_rem[0], args));
+                }
+            } else {
+                return fail(LB_INTERNAL, "helper warps are a list-mode kernel shape for keys without side values");
+            }
+            break;
         default:
             if (HITS) {
                 cfg.blockDim = dim3(64 + 128 * 2);
@@ -515,7 +532,23 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
             a.hit_cap = hit_cap;
         }
     }
-    LB_TRY(launch_coarse_any(job.mode, hit_mode, cfg_id, cfg, sh, a));
+    // list mode, 128-row tiles, one partition per slot, keys without side values: the shortlists move to helper warps
+    int main_cfg = cfg_id;
+    if (!hit_mode && (cfg_id == 2 || cfg_id == 3) && parts_per_slot == 1 && (job.mode == tc::CM_I32 || job.mode == tc::CM_F32) &&
+        job.dump == nullptr && tc_env_int("LYNSE_B200_TC_HELPER", 1) != 0)
+        main_cfg = cfg_id == 2 ? 6 : 7;
+    // ... with a pre-pass of the second-best exchange when the partitions are long enough for it to be a small share
+    // (no row filter: group maxima cannot tell allowed rows from filtered ones)
+    a.pre_tiles = 0;
+    if (main_cfg >= 6 && a.pbest2 != nullptr && a.pbest_first == 0 && job.d_allow == nullptr) {
+        // 1/16 of a partition, at most 32 tiles (measured on a 1.25M-row shard of C2, 543 tiles per partition: kernel
+        // 0.685 ms without, 0.663 / 0.652 / 0.642 / 0.637 with 4 / 8 / 16 / 32 tiles)
+        const int pre_env = tc_env_int("LYNSE_B200_TC_PRE", -1);
+        // (C1, 44 tiles per partition: 0.135 / 0.125 / 0.110 ms with 2 / 4 / 8 tiles — short partitions are all "first tiles")
+        const uint32_t pre_auto = std::min<uint32_t>(32, std::max<uint32_t>(tiles_per_part / 16, std::min<uint32_t>(8, tiles_per_part / 4)));
+        a.pre_tiles = pre_env >= 0 ? std::min<int>(pre_env, (int)tiles_per_part / 4) : (int)pre_auto;
+    }
+    LB_TRY(launch_coarse_any(job.mode, hit_mode, main_cfg, cfg, sh, a));
     LB_CUDA_TRY(cudaGetLastError());
     if (idx->timing) cudaEventRecord(idx->ev[1], idx->stream);
     idx->stats.kernels_launched += 1;

@@ -505,3 +505,80 @@ def test_two_round_rescore_equals_one_round(L, oracle, monkeypatch, metric, k):
             got = idx.search(queries, k, metric)
             assert idx.last_stats()["plan_used"] == 1
         _same(want, got)
+
+
+# ---- helper warps (list mode of the pair kernel: the shortlists live in warps 6..9, fed through a shared-memory queue) ----
+@pytest.mark.parametrize("metric,operand,positive,dim", [("ip", "u8", True, 96), ("ip", "u8", False, 96), ("ip", "bf16", True, 96),
+                                                          ("cosine", "u8", False, 200), ("l2", "auto", True, 64),
+                                                          ("ip", "u8", True, 768)])
+def test_helper_warp_kernel_matches_oracle_and_the_epilogue_lists(L, oracle, monkeypatch, metric, operand, positive, dim):
+    """1024 queries (four query groups -> 18 row partitions, all in flight: second-best exchange + its pre-pass) and
+    k = 10: ids, order and score bits are the oracle's, and the kernel without helper warps
+    (LYNSE_B200_TC_HELPER=0) returns the same bytes.  dim 96 / 64: three accumulator tiles; 200 / 768: two."""
+    monkeypatch.setenv("LYNSE_B200_TC_OPERAND", operand)
+    n, nq, k = (150_000 if dim <= 200 else 60_000), 1024, 10
+    corpus = _data(n, dim, 7, positive)
+    queries = _data(nq, dim, 8, positive)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, metric)
+        st = idx.last_stats()
+        monkeypatch.setenv("LYNSE_B200_TC_HELPER", "0")
+        got_lists = idx.search(queries, k, metric)
+        st_lists = idx.last_stats()
+    assert st["plan_used"] == 1 and st_lists["plan_used"] == 1, (st, st_lists)
+    # (one thread: which rows of a chunk take the reference's batch-8 or its single-row IP kernel depends on the chunking)
+    _same(oracle.store_batch_search(corpus, queries, k, metric, n_threads=1), got)
+    for a, b in zip(got, got_lists):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_helper_warp_kernel_with_ties_and_a_ragged_last_tile(L, oracle):
+    """Many rows share the best score (duplicates spread over every partition) and the corpus ends inside a tile: ties
+    resolve by row as in the reference, and padding rows never count as a partition's best keys in the pre-pass."""
+    n, dim, nq, k = 100_003, 64, 1024, 12
+    rng = np.random.default_rng(11)
+    corpus = rng.random((n, dim), dtype=np.float32)
+    queries = rng.random((nq, dim), dtype=np.float32)
+    dup = rng.choice(n - 1, size=400, replace=False)
+    corpus[dup] = corpus[dup[0]] * np.float32(1.5)        # 400 identical strong rows
+    best = n - 4   # in the ragged last tile, but not among the <= 7 tail rows whose IP kernel depends on the reference's chunking
+    corpus[best] = corpus[dup[0]] * np.float32(2.0)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "ip")
+        st = idx.last_stats()
+    assert st["plan_used"] == 1, st
+    _same(oracle.store_batch_search(corpus, queries, k, "ip", n_threads=1), got)
+    assert (got[0][:, 0] == best).all()
+
+
+def test_helper_warp_kernel_with_a_row_filter(L, oracle):
+    """A filtered search keeps the helper warps (the filter is applied where the hits are inserted) but not the
+    pre-pass of the exchange: group maxima cannot tell allowed rows from filtered ones."""
+    n, dim, nq, k = 120_000, 64, 1024, 10
+    corpus = _data(n, dim, 21)
+    queries = _data(nq, dim, 22)
+    allowed = np.arange(0, n, 2)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "l2", allow_bits=L.make_allow_bits(n, allowed))
+        st = idx.last_stats()
+    assert st["plan_used"] == 1, st
+    want = oracle.store_batch_search(np.ascontiguousarray(corpus[allowed]), queries, k, "l2", n_threads=oracle.host_threads())
+    assert np.array_equal(allowed[want[0].astype(np.int64)].astype(np.uint32), got[0])
+    assert np.array_equal(want[1].view(np.uint32), got[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("nq", [256, 1024])
+def test_helper_warp_kernel_small(L, oracle, nq):
+    """Small corpora: 256 queries = one query group, 74 partitions, no exchange; 1024 queries = four groups, 18
+    partitions, exchange with its pre-pass."""
+    n, dim, k = 40_000, 64, 10
+    corpus, queries = _data(n, dim, 31), _data(nq, dim, 32)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "l2")
+        st = idx.last_stats()
+    assert st["plan_used"] == 1, st
+    _same(oracle.store_batch_search(corpus, queries, k, "l2", n_threads=1), got)
