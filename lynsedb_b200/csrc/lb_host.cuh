@@ -291,6 +291,7 @@ int run_tc_bits(lb_index* idx, int metric, const uint64_t* words, int n_words, c
                 float* d_dists, uint32_t* d_counts, const uint64_t* d_allow = nullptr, bool defer_check = false);
 // Synchronises the stream, reads the flags of the pending tensor-core search and re-runs uncertified queries with the
 // exact scan.  *changed (optional) = results were rewritten (anything enqueued behind the search saw stale results).
-int tc_finish(lb_index* idx, bool* changed = nullptr);
+// `head`: the first four flag words, already copied to the host behind the search and synchronised (saves the copy + wait)
+int tc_finish(lb_index* idx, bool* changed = nullptr, const uint32_t* head = nullptr);
 
 }  // namespace lb

@@ -752,15 +752,19 @@ int run_tc_bits(lb_index* idx, int metric, const uint64_t* words, int n_words, c
 }
 
 // ---- certification flags -> exact-scan fallback -----------------------------------------------------------------
-int tc_finish(lb_index* idx, bool* changed) {
+int tc_finish(lb_index* idx, bool* changed, const uint32_t* head_ready) {
     if (changed) *changed = false;
     lb_index::PendingTc& p = idx->pending_tc;
     if (!p.active) return LB_OK;
     p.active = false;
     uint32_t* flags = idx->w_flags.as<uint32_t>();
     uint32_t head[4] = {0, 0, 0, 0};
-    LB_CUDA_TRY(cudaMemcpyAsync(head, flags, 16, cudaMemcpyDeviceToHost, idx->stream));
-    LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    if (head_ready != nullptr) {
+        memcpy(head, head_ready, 16);
+    } else {
+        LB_CUDA_TRY(cudaMemcpyAsync(head, flags, 16, cudaMemcpyDeviceToHost, idx->stream));
+        LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
     if (idx->timing) {
         float ms = 0;
         cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);

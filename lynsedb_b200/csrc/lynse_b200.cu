@@ -690,11 +690,31 @@ static int search_host_common(lb_index* idx, int score_mode, int metric, const v
             src = reinterpret_cast<const char*>(idx->h_in.p);
         }
         LB_CUDA_TRY(cudaMemcpyAsync(idx->w_queries.p, src, in_bytes, cudaMemcpyHostToDevice, idx->stream));
-        LB_TRY(search_device_impl(idx, metric, idx->w_queries.p, nb, (int)kk, d_allow, d_rows, d_dists, d_counts, false));
+        // a tensor-core plan leaves its certification flags unread: they come back with the results (one wait per batch),
+        // and only a batch with uncertified queries — re-run by the exact scan inside tc_finish — copies its results again
+        LB_TRY(search_device_impl(idx, metric, idx->w_queries.p, nb, (int)kk, d_allow, d_rows, d_dists, d_counts, false, true));
+        const bool flags_pending = idx->pending_tc.active;
+        uint32_t* flag_head = nullptr;
+        if (flags_pending) {
+            LB_TRY(idx->h_tails.ensure(16));
+            flag_head = reinterpret_cast<uint32_t*>(idx->h_tails.p);
+        }
+        auto finish_flags = [&](bool* changed) -> int {
+            *changed = false;
+            if (!flags_pending) return LB_OK;
+            return tc_finish(idx, changed, flag_head);
+        };
         if (out_bytes <= STAGE_LIMIT) {
             LB_TRY(idx->h_out.ensure(out_bytes));
             LB_CUDA_TRY(cudaMemcpyAsync(idx->h_out.p, idx->w_out.p, out_bytes, cudaMemcpyDeviceToHost, idx->stream));
+            if (flags_pending) LB_CUDA_TRY(cudaMemcpyAsync(flag_head, idx->w_flags.p, 16, cudaMemcpyDeviceToHost, idx->stream));
             LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+            bool changed = false;
+            LB_TRY(finish_flags(&changed));
+            if (changed) {
+                LB_CUDA_TRY(cudaMemcpyAsync(idx->h_out.p, idx->w_out.p, out_bytes, cudaMemcpyDeviceToHost, idx->stream));
+                LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+            }
             const char* h = reinterpret_cast<const char*>(idx->h_out.p);
             for (int q = 0; q < nb; ++q) {
                 memcpy(out_rows + (size_t)(q0 + q) * k, h + (size_t)q * kk * 4, (size_t)kk * 4);
@@ -707,7 +727,18 @@ static int search_host_common(lb_index* idx, int score_mode, int metric, const v
             LB_CUDA_TRY(cudaMemcpy2DAsync(out_dists + (size_t)q0 * k, (size_t)k * 4, d_dists, (size_t)kk * 4, (size_t)kk * 4, nb,
                                           cudaMemcpyDeviceToHost, idx->stream));
             LB_CUDA_TRY(cudaMemcpyAsync(out_counts + q0, d_counts, (size_t)nb * 4, cudaMemcpyDeviceToHost, idx->stream));
+            if (flags_pending) LB_CUDA_TRY(cudaMemcpyAsync(flag_head, idx->w_flags.p, 16, cudaMemcpyDeviceToHost, idx->stream));
             LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+            bool changed = false;
+            LB_TRY(finish_flags(&changed));
+            if (changed) {
+                LB_CUDA_TRY(cudaMemcpy2DAsync(out_rows + (size_t)q0 * k, (size_t)k * 4, d_rows, (size_t)kk * 4, (size_t)kk * 4, nb,
+                                              cudaMemcpyDeviceToHost, idx->stream));
+                LB_CUDA_TRY(cudaMemcpy2DAsync(out_dists + (size_t)q0 * k, (size_t)k * 4, d_dists, (size_t)kk * 4, (size_t)kk * 4, nb,
+                                              cudaMemcpyDeviceToHost, idx->stream));
+                LB_CUDA_TRY(cudaMemcpyAsync(out_counts + q0, d_counts, (size_t)nb * 4, cudaMemcpyDeviceToHost, idx->stream));
+                LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+            }
         }
         acc.plan_used = idx->stats.plan_used;
         acc.n_fallback += idx->stats.n_fallback;
@@ -1608,10 +1639,11 @@ static int sharded_search_device_impl(lb_comm* comm, lb_index* idx, int metric, 
                                       const uint64_t* d_allow = nullptr) {
     const int G = comm ? comm->world : 1;
     if ((uint64_t)G * k > 4096) return fail(LB_UNSUPPORTED, "world_size * k must not exceed 4096");
+    const auto tr_begin = std::chrono::steady_clock::now();
     const size_t bb = shard_block_bytes(nq, k);
     LB_TRY(idx->w_send.ensure(bb));
     LB_TRY(idx->w_recv.ensure(bb * G));
-    LB_TRY(idx->h_tails.ensure((size_t)G * SHARD_TAIL_BYTES));
+    LB_TRY(idx->h_tails.ensure((size_t)G * SHARD_TAIL_BYTES + 16));   // + this rank's flag head (read with the same wait)
     unsigned char* send = idx->w_send.as<unsigned char>();
     uint32_t* s_rows = reinterpret_cast<uint32_t*>(send);
     float* s_dists = reinterpret_cast<float*>(send + (size_t)nq * k * 4);
@@ -1636,7 +1668,14 @@ static int sharded_search_device_impl(lb_comm* comm, lb_index* idx, int metric, 
         return LB_OK;
     };
     LB_TRY(gather_and_merge());
+    // this rank's certification flags ride along with the tails: one wait, one wake-up per step
+    uint32_t* flag_head = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(idx->h_tails.p) + (size_t)G * SHARD_TAIL_BYTES);
+    const bool flags_pending = idx->pending_tc.active;
+    if (flags_pending)
+        LB_CUDA_TRY(cudaMemcpyAsync(flag_head, idx->w_flags.p, 16, cudaMemcpyDeviceToHost, idx->stream));
+    const auto tr_enq = std::chrono::steady_clock::now();
     LB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    const auto tr_sync = std::chrono::steady_clock::now();
     const unsigned char* tails = reinterpret_cast<const unsigned char*>(idx->h_tails.p);
     uint32_t any_uncertified = 0, any_status = 0;
     uint64_t prev_base = 0;
@@ -1665,7 +1704,7 @@ static int sharded_search_device_impl(lb_comm* comm, lb_index* idx, int metric, 
     if (idx->pending_tc.active) {
         // reads this rank's flags (stream already idle) and runs its fallback when it has one
         idx->stats = local;
-        LB_TRY(tc_finish(idx));
+        LB_TRY(tc_finish(idx, nullptr, flags_pending ? flag_head : nullptr));
         fin = idx->stats;
     }
     if (any_uncertified != 0) {
@@ -1675,6 +1714,12 @@ static int sharded_search_device_impl(lb_comm* comm, lb_index* idx, int metric, 
     }
     idx->stats = fin;
     idx->stats.kernels_launched += 2 + (G > 1 ? 1 : 0) + extra_kernels;
+    if (tc_env_int("LYNSE_B200_TC_TRACE", 0) != 0) {
+        const auto tr_end = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[lynse_b200] sharded step (host clock): enqueue %.1f us, wait for the device %.1f us, flags + fallback %.1f us\n",
+                us(tr_begin, tr_enq), us(tr_enq, tr_sync), us(tr_sync, tr_end));
+    }
     return LB_OK;
 }
 }  // namespace lb
