@@ -113,6 +113,7 @@ struct TcArgs {
                               // pre-pass over a sample of the corpus and is only read (large k)
     uint32_t* gthr;           // [nq] zero-initialised: best published shortlist floor per query (orderable key bits)
     int pbest_first;          // diagnostics: the exchange publishes the BEST key of a list instead of its second best
+    int pbest_depth;          // which of a list's best keys the exchange publishes: 2 .. 4 (the floor then has depth x P rows above it)
     uint32_t* pbest2;         // optional [nq][PBEST_STRIDE] zero-initialised: second-best key (orderable bits) each partition of a
                               // query holds so far.  When all partitions run at once, the smallest of them is a floor with at
                               // least two rows above it in EVERY partition — 2 P rows, far tighter early in the pass than the
@@ -484,7 +485,8 @@ struct Shortlist {
     uint32_t* gthr;
     // second-best exchange (list mode, every partition of the query in flight): best and second-best key of this list,
     // where this list publishes its second best, the query's row of the exchange, the words loaded by the last poll
-    K best1, best2;
+    K best1, best2, best3, best4;
+    int pb_depth;
     uint32_t* pb_slot;
     const uint32_t* pb_row;
     uint4 pb_v[PBEST_STRIDE / 4];
@@ -525,6 +527,9 @@ struct Shortlist {
         thr_pub = O::lowest();
         best1 = O::lowest();
         best2 = O::lowest();
+        best3 = O::lowest();
+        best4 = O::lowest();
+        pb_depth = a.pbest_depth;
         pb_n = 0u;
         pb_loaded = false;
         pb_first = false;
@@ -575,17 +580,18 @@ struct Shortlist {
     __device__ __forceinline__ void insert(K key, uint32_t row) {
         if (HITS) return;
         if (pb_n != 0u) {
-            const K old2 = best2, old1 = best1;
-            if (key > best1) {
-                best2 = best1;
-                best1 = key;
-            } else if (key > best2) {
-                best2 = key;
-            }
+            // the list's four best keys, sorted; the exchange publishes the pb_depth-th of them (single writer, only grows)
+            const K old1 = best1, oldp = pb_depth <= 2 ? best2 : (pb_depth == 3 ? best3 : best4);
+            K x = key, t;
+            t = max(best1, x); x = min(best1, x); best1 = t;
+            t = max(best2, x); x = min(best2, x); best2 = t;
+            t = max(best3, x); x = min(best3, x); best3 = t;
+            best4 = max(best4, x);
+            const K newp = pb_depth <= 2 ? best2 : (pb_depth == 3 ? best3 : best4);
             if (pb_first) {
                 if (best1 > old1) *reinterpret_cast<volatile uint32_t*>(pb_slot) = O::orderable(best1);
-            } else if (best2 > old2) {
-                *reinterpret_cast<volatile uint32_t*>(pb_slot) = O::orderable(best2);  // single writer
+            } else if (newp > oldp) {
+                *reinterpret_cast<volatile uint32_t*>(pb_slot) = O::orderable(newp);
             }
         }
         bool done = false;

@@ -461,6 +461,11 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     // them for one poll): LYNSE_B200_TC_PBEST=0 turns it off
     a.pbest2 = nullptr;
     a.pbest_first = 0;
+    // Which of a list's best keys it publishes: the floor (the smallest over the P partitions) has depth x P rows above it.
+    // Depth 2 (36 rows at P = 18) sits so close to the k = 10-th score that a batch now and then holds a query or two the
+    // 8-bit bound cannot certify — on a 5M-row shard of C2 two of 1024, every step, each re-run by the exact scan: 2.4 -> 5.3
+    // ms per step.  Depth 4 (72 rows): none on 1.25M / 2.5M / 5M / 10M rows.
+    a.pbest_depth = std::max(2, std::min(4, tc_env_int("LYNSE_B200_TC_PBEST_DEPTH", 4)));
     if (a.share_floor == 1 && parts_per_slot == 1 && L == 1 && P >= 8 && P <= (uint64_t)tc::PBEST_STRIDE && 2 * P >= (uint64_t)k + 4 &&
         tc_env_int("LYNSE_B200_TC_PBEST", 1) != 0) {
         a.pbest2 = z_pbest_p;
