@@ -356,6 +356,15 @@ class Rig:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
     def step_device(self):
         self.N.check(self.lib.lb_sharded_search_device(self.comm, self.idx._h, self.m_id, self.dq, self.nq, self.k, self.base,
                                                        self.drows, self.ddists, self.dcounts))
@@ -396,7 +405,8 @@ class Rig:
         ms = C.c_float(0)
         N.check(lib.lb_index_event_elapsed_ms(idx._h, slot, slot + 1, C.byref(ms)))
         self.barrier()
-        return self.max_over_ranks(float(ms.value)), wall_ms, dom, launches, fallbacks, idx.last_stats()
+        # fallbacks of EVERY rank: one rank's exact-scan re-run holds all of them up at the gather
+        return self.max_over_ranks(float(ms.value)), wall_ms, dom, launches, int(self.sum_over_ranks(float(fallbacks))), idx.last_stats()
 
     def measure(self, steps, warmup):
         for _ in range(max(warmup, 3)):
