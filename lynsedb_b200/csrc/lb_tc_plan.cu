@@ -466,8 +466,9 @@ static int coarse_pass(lb_index* idx, CoarseJob& job) {
     // 8-bit bound cannot certify — on a 5M-row shard of C2 two of 1024, every step, each re-run by the exact scan: 2.4 -> 5.3
     // ms per step.  Depth 4 (72 rows): none on 1.25M / 2.5M / 5M / 10M rows.
     a.pbest_depth = std::max(2, std::min(4, tc_env_int("LYNSE_B200_TC_PBEST_DEPTH", 4)));
-    if (a.share_floor == 1 && parts_per_slot == 1 && L == 1 && P >= 8 && P <= (uint64_t)tc::PBEST_STRIDE && 2 * P >= (uint64_t)k + 4 &&
-        tc_env_int("LYNSE_B200_TC_PBEST", 1) != 0) {
+    // ... and only when that is at least 6 k rows (k = 10, P = 18: 72): fewer partitions keep the lists' own floors
+    if (a.share_floor == 1 && parts_per_slot == 1 && L == 1 && P >= 8 && P <= (uint64_t)tc::PBEST_STRIDE &&
+        (uint64_t)a.pbest_depth * P >= (uint64_t)6 * k && tc_env_int("LYNSE_B200_TC_PBEST", 1) != 0) {
         a.pbest2 = z_pbest_p;
         a.pbest_first = tc_env_int("LYNSE_B200_TC_PBEST", 1) == 2 && P >= (uint64_t)k + 4 ? 1 : 0;
     }
