@@ -604,3 +604,15 @@ def test_c2_shard_of_a_two_gpu_run_certifies_every_query(L):
     assert st["plan_used"] == 1 and st["n_fallback"] == 0, st
     assert np.array_equal(rows[sample], e_rows)
     assert np.array_equal(dists[sample].view(np.uint32), e_dists.view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [2432, 2500, 7000, 20_000])
+def test_helper_warp_kernel_with_fewer_partitions_than_slots(L, oracle, n):
+    """Corpora of a few dozen tiles: some cluster slots get no partition at all (their scanner warps only close the
+    queue, their helpers never start), partitions are one or two tiles long, and the last tile is ragged."""
+    dim, nq, k = 64, 1024, 10
+    corpus, queries = _data(n, dim, 41), _data(nq, dim, 42)
+    with L.DeviceIndex(dim) as idx:
+        idx.append(corpus)
+        got = idx.search(queries, k, "l2")
+    _same(oracle.store_batch_search(corpus, queries, k, "l2", n_threads=1), got)
