@@ -11,6 +11,8 @@
 //     both CTAs — a release at cluster scope costs ~1400 cycles under a loaded memory system).
 // Work: cluster c serves query group (c % n_mgroups) of slot (c / n_mgroups); the query groups of a slot stream the
 // same row partitions in lockstep (TcArgs::progress / window) so HBM is read once per slot.
+// Warp roles: 0 TMA producer, 1 MMA issuer (even CTA), 2..5 epilogue (2..9 with two epilogue sets); in the HELP_ shape
+// 2..5 are scanners and 6..9 the helper warps that own the shortlists (see the comment at the kernel).
 #pragma once
 #include "lb_tc.cuh"
 
