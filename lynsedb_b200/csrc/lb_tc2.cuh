@@ -417,7 +417,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
 #pragma unroll
                             for (int i = 3; i + 1 < 16; i += 2) m = KO::max3(m, KO::from_bits(x[i]), KO::from_bits(x[i + 1]));
                             m = max(m, KO::from_bits(x[15]));
-                            if (pre_mode && whole) {   // one row of this partition per group: its two best keys so far
+                            if (pre_mode && (whole || t * BN + (uint32_t)(h * 64 + j * 16 + 16) <= a.n_rows)) {   // a group of corpus rows only: one row of this partition, its two best keys so far
                                 const Key lo = min(m, best1);
                                 best1 = max(m, best1);
                                 best2 = max(best2, lo);
@@ -444,6 +444,14 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                     if (pre_mode && exch && best2 > pub2) {
                         st_relaxed_gpu(a.pbest2 + (size_t)gq * PBEST_STRIDE + part, KO::orderable(best2));  // single writer until the helper's lists take over
                         pub2 = best2;
+                    }
+                    if (pre_mode && exch && i + 1u == pre && !(pub2 > KO::lowest())) {
+                        // a partition of a single ragged tile with fewer than two whole groups: publish "no floor" rather than
+                        // let the other partitions of the query wait out their bound
+                        Key none;
+                        if constexpr (MT::kIntKey) none = KO::lowest() + 1;
+                        else none = -3.0e38f;
+                        st_relaxed_gpu(a.pbest2 + (size_t)gq * PBEST_STRIDE + part, KO::orderable(none));
                     }
                 }
                 // end of the stream (also after a failed wait: the helper must not be left waiting)

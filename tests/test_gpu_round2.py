@@ -606,10 +606,12 @@ def test_c2_shard_of_a_two_gpu_run_certifies_every_query(L):
     assert np.array_equal(dists[sample].view(np.uint32), e_dists.view(np.uint32))
 
 
-@pytest.mark.parametrize("n", [2432, 2500, 7000, 20_000])
+@pytest.mark.parametrize("n", [2432, 2500, 7000, 8710, 8724, 20_000])
 def test_helper_warp_kernel_with_fewer_partitions_than_slots(L, oracle, n):
     """Corpora of a few dozen tiles: some cluster slots get no partition at all (their scanner warps only close the
-    queue, their helpers never start), partitions are one or two tiles long, and the last tile is ragged."""
+    queue, their helpers never start), partitions are one or two tiles long, and the last tile is ragged.  8710 / 8724
+    rows: 18 partitions of four tiles with the exchange and its pre-pass on, the last partition a single tile of 6 / 20
+    rows — fewer than two whole 16-row groups, so it publishes "no floor" instead of a second-best key."""
     dim, nq, k = 64, 1024, 10
     corpus, queries = _data(n, dim, 41), _data(nq, dim, 42)
     with L.DeviceIndex(dim) as idx:
