@@ -379,8 +379,19 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                         for (uint32_t it = 0; it < 1024u; ++it) {
                             bool done = true;
                             if (exch) {
+                                uint4 w4[PBEST_STRIDE / 4];   // the query's row of the exchange: five independent 16-byte loads
+#pragma unroll
+                                for (int c = 0; c < PBEST_STRIDE / 4; ++c)
+                                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=r"(w4[c].x), "=r"(w4[c].y), "=r"(w4[c].z), "=r"(w4[c].w)
+                                                 : "l"(pb_row + 4 * c));
                                 uint32_t mn = 0xFFFFFFFFu;
-                                for (int pp = 0; pp < a.P; ++pp) mn = min(mn, ld_relaxed_gpu(pb_row + pp));
+#pragma unroll
+                                for (int c = 0; c < PBEST_STRIDE / 4; ++c) {
+                                    const uint32_t w[4] = {w4[c].x, w4[c].y, w4[c].z, w4[c].w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) mn = min(mn, 4 * c + e < a.P ? w[e] : 0xFFFFFFFFu);
+                                }
                                 done = mn != 0u;
                                 if (done) floor0 = KO::from_orderable(mn);
                             }
