@@ -421,22 +421,35 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                             e_ld += clock64() - ec1;
                         }
                         const long long sc0 = clock64();
+                        // group maxima with 3-input max, ONE vote for the half (as the epilogue warps' fast path does): the
+                        // per-group votes only run in a half that holds a hit
+                        Key g[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const uint32_t* x = v + 16 * j;
                             Key m = KO::max3(KO::from_bits(x[0]), KO::from_bits(x[1]), KO::from_bits(x[2]));
 #pragma unroll
                             for (int i = 3; i + 1 < 16; i += 2) m = KO::max3(m, KO::from_bits(x[i]), KO::from_bits(x[i + 1]));
-                            m = max(m, KO::from_bits(x[15]));
-                            if (pre_mode && (whole || t * BN + (uint32_t)(h * 64 + j * 16 + 16) <= a.n_rows)) {   // a group of corpus rows only: one row of this partition, its two best keys so far
-                                const Key lo = min(m, best1);
-                                best1 = max(m, best1);
-                                best2 = max(best2, lo);
-                            }
-                            if (__any_sync(0xffffffffu, m > thr)) {
+                            g[j] = max(m, KO::from_bits(x[15]));
+                        }
+                        if (pre_mode) {   // one row of this partition per group of corpus rows: its two best keys so far
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (whole || t * BN + (uint32_t)(h * 64 + j * 16 + 16) <= a.n_rows) {
+                                    const Key lo = min(g[j], best1);
+                                    best1 = max(g[j], best1);
+                                    best2 = max(best2, lo);
+                                }
+                        }
+                        const Key gall = max(max(g[0], g[1]), max(g[2], g[3]));
+                        if (__any_sync(0xffffffffu, gall > thr)) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (!ok || !__any_sync(0xffffffffu, g[j] > thr)) continue;
+                                const uint32_t* x = v + 16 * j;
                                 // back-pressure: the slot this entry goes to must have been consumed
                                 const uint32_t qs = head % HQ_SLOTS;
-                                if (!mbar_wait(qempty0 + 8u * qs, ((head / HQ_SLOTS) & 1u) ^ 1u, abort_flag, 6)) { ok = false; break; }
+                                if (!mbar_wait(qempty0 + 8u * qs, ((head / HQ_SLOTS) & 1u) ^ 1u, abort_flag, 6)) { ok = false; continue; }
                                 uint32_t* e = ent + qs * HQ_ENTRY_WORDS;
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) e[i * 32 + lane] = x[i];
@@ -497,6 +510,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                 }
                 const bool have_allow = a.allow_bits != nullptr;
                 uint32_t tail = 0;
+                long long h_busy = 0;   // cycles between taking a group off the queue and being ready for the next (diagnostics)
                 while (have_part) {
                     const uint32_t qs = tail % HQ_SLOTS;
                     if (!mbar_wait(qfull0 + 8u * qs, (tail / HQ_SLOTS) & 1u, abort_flag, 7)) break;   // (an aborted launch ends here)
@@ -509,6 +523,7 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                     __syncwarp();
                     if (lane == 0) mbar_arrive(qempty0 + 8u * qs);   // the group is in registers: the slot is free
                     ++tail;
+                    const long long hc0 = clock64();
                     if (!(a.debug_mode & 128)) sl.poll_floor(tail, (uint32_t)a.poll_mask >> 1);   // every 4th entry (tiles: every 8th)
                     sl.thr_g = max(sl.thr_g, KO::from_bits(*hg_floor));   // the scanner's pre-pass floor
                     const Key thr = sl.gate();
@@ -525,7 +540,10 @@ coarse_pair_kernel(const __grid_constant__ CUtensorMap tmap_full, const __grid_c
                         if (sl.may_publish && sl.q_valid && sl.lmin > sl.thr_pub && sl.lmin > sl.thr_g) sl.publish();
                     }
                     *hg_gate = KO::bits(sl.gate());
+                    h_busy += clock64() - hc0;
                 }
+                if (a.prof != nullptr && warp == 6 && lane == 0 && crank == 1)   // odd CTA, slot 5: busy cycles << 24 | groups taken
+                    a.prof[(size_t)blockIdx.x * 8 + 5] = ((unsigned long long)h_busy << 24) | (unsigned long long)(tail & 0xFFFFFFu);
                 if (have_part) {
                     sl.thr_g = max(sl.thr_g, KO::from_bits(*hg_floor));   // (no entry may have arrived since it was set)
                     sl.flush(a, gq, part, 0u);

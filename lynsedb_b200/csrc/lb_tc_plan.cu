@@ -784,15 +784,20 @@ int tc_finish(lb_index* idx, bool* changed, const uint32_t* head_ready) {
         int n_lead = 0, n_cta = 0;
         if (p.pair) {
             double sc[5] = {0, 0, 0, 0, 0};
-            double mx = 0;
+            double mx = 0, h_busy = 0, h_groups = 0;
             for (int b = 1; b < grid && b < idx->sm_count; b += 2) {
                 for (int i = 0; i < 5; ++i) sc[i] += (double)pr[(size_t)b * 8 + i];
                 mx = std::max(mx, (double)pr[(size_t)b * 8 + 3]);
+                h_busy += (double)(pr[(size_t)b * 8 + 5] >> 24);           // helper-warp kernel: one helper warp per odd CTA
+                h_groups += (double)(pr[(size_t)b * 8 + 5] & 0xFFFFFFull);
                 for (int i = 0; i < 6; ++i) pr[(size_t)b * 8 + i] = 0;
             }
             if (sc[4] > 0)
                 fprintf(stderr, "[lynse_b200] scan (one warp per odd CTA): %.0f cycles/tile, slow tiles %.3f/tile at %.0f cycles each, longest %.0f\n",
                         sc[0] / sc[4], sc[2] / sc[4], sc[2] > 0 ? sc[1] / sc[2] : 0.0, mx);
+            if (sc[4] > 0 && h_groups > 0)
+                fprintf(stderr, "[lynse_b200] helper (one warp per odd CTA): %.3f queued groups per tile, %.0f cycles per group\n", h_groups / sc[4],
+                        h_busy / h_groups);
         }
         for (int b = 0; b < grid && b < idx->sm_count; ++b) {
             if (pr[(size_t)b * 8] > 0) {
